@@ -1,0 +1,158 @@
+"""Minimal stand-in for the `porepy` surface PyGeoN's FEM hot path touches.
+
+TEST INFRASTRUCTURE ONLY.  porepy is a third-party dependency of the reference
+(pyproject.toml:26-28, pinned only to the moving `develop` branch) and is not
+installed in this image.  None of the hot path's arithmetic lives in porepy: it
+supplies the grid container (`pp.Grid`), `pp.SecondOrderTensor` and a few names.
+This module provides exactly that surface so that the UNMODIFIED reference
+source under /root/reference/src can be imported to (a) pin the numpy oracle
+and (b) generate the golden fixtures under tests/golden/.
+
+Never imported by the product package `pygeon_b200`.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sps
+
+PARAMETERS = "parameters"
+DISCRETIZATION_MATRICES = "discretization_matrices"
+
+
+def initialize_data(data: dict, keyword: str, specified_parameters: dict | None = None):
+    """Same contract as porepy's helper: data[PARAMETERS][keyword] = params."""
+    data.setdefault(PARAMETERS, {})
+    data.setdefault(DISCRETIZATION_MATRICES, {})
+    data[PARAMETERS].setdefault(keyword, {})
+    data[PARAMETERS][keyword].update(specified_parameters or {})
+    data[DISCRETIZATION_MATRICES].setdefault(keyword, {})
+    return data
+
+
+class SecondOrderTensor:
+    """Symmetric 3x3 tensor per cell, `.values` of shape (3, 3, nc)."""
+
+    def __init__(self, kxx, kyy=None, kzz=None, kxy=None, kxz=None, kyz=None):
+        kxx = np.atleast_1d(np.asarray(kxx, dtype=float))
+        nc = kxx.size
+        z = np.zeros(nc)
+        kyy = kxx if kyy is None else np.asarray(kyy, dtype=float)
+        kzz = kxx if kzz is None else np.asarray(kzz, dtype=float)
+        kxy = z if kxy is None else np.asarray(kxy, dtype=float)
+        kxz = z if kxz is None else np.asarray(kxz, dtype=float)
+        kyz = z if kyz is None else np.asarray(kyz, dtype=float)
+        self.values = np.array(
+            [[kxx, kxy, kxz], [kxy, kyy, kyz], [kxz, kyz, kzz]], dtype=float
+        )
+
+    def copy(self):
+        out = SecondOrderTensor(np.ones(self.values.shape[2]))
+        out.values = self.values.copy()
+        return out
+
+
+class Grid:
+    """Simplicial-grid container with the attributes the hot path reads."""
+
+    def __init__(self, dim, nodes, face_nodes, cell_faces, name="grid", **_):
+        self.dim = int(dim)
+        self.nodes = np.asarray(nodes, dtype=float)
+        self.face_nodes = sps.csc_array(face_nodes)
+        self.cell_faces = sps.csc_array(cell_faces)
+        self.name = name
+        self.num_nodes = self.nodes.shape[1]
+        self.num_faces = self.face_nodes.shape[1]
+        self.num_cells = self.cell_faces.shape[1]
+        self.tags: dict = {}
+        bnd = np.abs(self.cell_faces).sum(axis=1) == 1
+        bnd = np.asarray(bnd).ravel()
+        self.tags["domain_boundary_faces"] = bnd
+        self.tags["tip_faces"] = np.zeros(self.num_faces, dtype=bool)
+        self.tags["fracture_faces"] = np.zeros(self.num_faces, dtype=bool)
+        self.tags["domain_boundary_nodes"] = (
+            (self.face_nodes.astype(bool) @ bnd.astype(int)) > 0
+        )
+        self.tags["tip_nodes"] = np.zeros(self.num_nodes, dtype=bool)
+        self.tags["fracture_nodes"] = np.zeros(self.num_nodes, dtype=bool)
+
+    def __hash__(self):
+        return id(self)
+
+    def __eq__(self, other):
+        return self is other
+
+    def cell_nodes(self):
+        mat = (self.face_nodes.astype(int) @ np.abs(self.cell_faces).astype(int)) > 0
+        return sps.csc_array(mat)
+
+    def num_cell_nodes(self):
+        return np.asarray(self.cell_nodes().sum(axis=0)).ravel()
+
+    def compute_geometry(self):
+        d = self.dim
+        x = self.nodes
+        fn = self.face_nodes.indices.reshape(self.num_faces, -1)
+        self.face_centers = x[:, fn].mean(axis=2)
+        cn = self.cell_nodes()
+        cn_idx = cn.indices.reshape(self.num_cells, d + 1)
+        self.cell_centers = x[:, cn_idx].mean(axis=2)
+        if d == 1:
+            self.face_normals = np.zeros((3, self.num_faces))
+            self.face_normals[0] = 1.0
+            self.face_areas = np.ones(self.num_faces)
+            e = x[:, cn_idx[:, 1]] - x[:, cn_idx[:, 0]]
+            self.cell_volumes = np.linalg.norm(e, axis=0)
+        elif d == 2:
+            t = x[:, fn[:, 1]] - x[:, fn[:, 0]]
+            self.face_normals = np.vstack([t[1], -t[0], np.zeros(self.num_faces)])
+            self.face_areas = np.linalg.norm(t, axis=0)
+            a = x[:, cn_idx[:, 1]] - x[:, cn_idx[:, 0]]
+            b = x[:, cn_idx[:, 2]] - x[:, cn_idx[:, 0]]
+            self.cell_volumes = 0.5 * np.abs(a[0] * b[1] - a[1] * b[0])
+        else:
+            a = x[:, fn[:, 1]] - x[:, fn[:, 0]]
+            b = x[:, fn[:, 2]] - x[:, fn[:, 0]]
+            self.face_normals = 0.5 * np.cross(a, b, axis=0)
+            self.face_areas = np.linalg.norm(self.face_normals, axis=0)
+            p = x[:, cn_idx]  # (3, nc, 4)
+            e1, e2, e3 = (p[:, :, k] - p[:, :, 0] for k in (1, 2, 3))
+            self.cell_volumes = np.abs(np.einsum("ic,ic->c", e1, np.cross(e2, e3, axis=0))) / 6.0
+        if d >= 2:
+            # invariant: cell_faces[f, c] = +1  <=>  face_normals[:, f] points out of c
+            f, c, s = sps.find(self.cell_faces)
+            out = np.einsum(
+                "if,if->f", self.face_normals[:, f], self.face_centers[:, f] - self.cell_centers[:, c]
+            )
+            if not np.all(np.sign(out) == np.sign(s)):
+                raise ValueError("cell_faces signs inconsistent with node-order normals")
+
+    def copy(self):
+        import copy as _copy
+
+        return _copy.copy(self)
+
+
+class MortarGrid:  # only used as a base class / in annotations
+    pass
+
+
+class MixedDimensionalGrid:  # only used as a base class / in annotations
+    pass
+
+
+class _Dummy:
+    def __init__(self, name="dummy"):
+        self._name = name
+
+    def __getattr__(self, item):
+        return _Dummy(f"{self._name}.{item}")
+
+    def __call__(self, *a, **k):
+        raise NotImplementedError(f"porepy stand-in: {self._name} is not available")
+
+
+def __getattr__(name):
+    if name.startswith("__"):
+        raise AttributeError(name)
+    return _Dummy(name)

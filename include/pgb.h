@@ -1,0 +1,164 @@
+/*
+ * pgb.h - C ABI of libpgb.so, the B200 (sm_100a) FEM assembly-and-solve hot path.
+ *
+ * The reference (compgeo-mox/pygeon) is pure Python and has no FFI: its "plugin"
+ * boundary is the pg.Discretization method signatures and the `solver` callable
+ * of pg.LinearSystem.solve.  The entry points below are what a ctypes binding
+ * placed behind those methods calls; each one names the
+ * reference code it replaces (paths relative to /root/reference/src/pygeon).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer; the only allocations made here are the Krylov drivers'
+ *     O(maxiter) residual history, a few KB of scalars and a mapped pinned stop flag;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*)
+ *     unless stated otherwise; return value 0 = ok, non-zero = error with
+ *     pgb_last_error() describing it (thread-local);
+ *   - ids are int32, values fp64, COO positions uint32 (n_coo < 2^32).
+ *   - "slot a" of a cell is the a-th entry of its cell_faces column; local node a
+ *     is the node opposite face slot a.
+ */
+#ifndef PGB_H
+#define PGB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int pgb_version(void);
+const char* pgb_last_error(void);
+
+/* ---- grid packing ------------------------------------------------------------
+ * Replaces Grid.compute_opposite_nodes (grids/grid.py:279-309),
+ * PwLinears.get_dof_lookup_array (discretizations/fem/l2.py:598-612) and the
+ * fancy-index gathers of BDM1/Nedelec1.proj_to_PwPolynomials
+ * (fem/hdiv.py:470-507, fem/hcurl.py:232-289).
+ *
+ *   cf_idx [nc*(d+1)]  cell_faces.indices          cf_sgn [nc*(d+1)] cell_faces.data as int8
+ *   fn_idx [nf*d]      face_nodes.indices
+ * out:
+ *   cell_nodes [nc*(d+1)]  node opposite each face slot
+ *   sign_bits  [nc]        bit a set <=> cell_faces sign of slot a is -1
+ *   err_flag   [1]         set to 1 if some cell is not a simplex (NotImplementedError
+ *                          "Grid is not simplicial", grid.py:298-301)
+ */
+int pgb_pack_cells(int dim, int64_t nc, const int32_t* cf_idx, const int8_t* cf_sgn,
+                   const int32_t* fn_idx, int32_t* cell_nodes, uint8_t* sign_bits,
+                   int32_t* err_flag, void* stream);
+
+/* BDM1 dofs (fem/hdiv.py:474-480): dof of (face slot a, pos) = f_a + pos*nf, pos = slot of
+ * the node in face_nodes.indices of f_a.  cell_dofs [nc*d*(d+1)], jslot_bits[nc]: 2 bits per
+ * (a,pos) = local node slot of that face node. */
+int pgb_pack_bdm1(int dim, int64_t nc, int64_t nf, const int32_t* cf_idx, const int32_t* fn_idx,
+                  const int32_t* cell_nodes, int32_t* cell_dofs, uint32_t* jslot_bits,
+                  void* stream);
+
+/* Nedelec0 edges.  3D (fem/hcurl.py:232-246, grids/grid.py:149-216): edge id of local pair
+ * (p,q), p<q in the order (01)(02)(03)(12)(13)(23), looked up in face_ridges / ridge_peaks.
+ * edge_bits: bit e (0..5) set <=> ridge_peaks order is (q,p) (Whitney form flipped);
+ * bits 8+4*... see pgb_pack.cu: 2 curl-sign bits per edge (sign of the edge in its two faces).
+ * 2D: the edge of face slot a joins the two other slots; bit a set <=> face_ridges.indices
+ * order is (hi slot, lo slot).  fr_* = face_ridges (indices, data as int8), rp_idx =
+ * ridge_peaks.indices. */
+int pgb_pack_edges3d(int64_t nc, const int32_t* cf_idx, const int32_t* fr_idx,
+                     const int8_t* fr_sgn, const int32_t* rp_idx, const int32_t* cell_nodes,
+                     int32_t* cell_edges, uint32_t* edge_bits, int32_t* err_flag, void* stream);
+int pgb_pack_edges2d(int64_t nc, const int32_t* cf_idx, const int32_t* fr_idx,
+                     const int32_t* cell_nodes, uint32_t* edge_bits, void* stream);
+
+/* coords[nn][4] (3D, padded) or [nn][2] (2D) = R @ nodes, nodes given as (3, nn) row-major
+ * (sd.nodes), R = sd.rotation_matrix (d x 3, host pointer). */
+int pgb_prep_coords(int dim, int64_t nn, const double* nodes, const double* R_host,
+                    double* coords, void* stream);
+
+/* ---- K1: per-cell local matrices ------------------------------------------------
+ * One thread per cell, fp64.  vals is [nc][L*L] row-major (local row a, local col b).
+ * Replaces the implicit local matrices of Discretization._assemble_inner_product
+ * (discretizations/discretization.py:112-136: Pi.T @ M @ Pi) and assemble_stiff_matrix
+ * (:154-183: B.T @ A @ B); closed forms in SURVEY.md section 8(a).
+ *   K      (3,3,nc) row-major = SecondOrderTensor.values, or NULL (identity)
+ *   R_host d x 3 rotation matrix (host)      w  [nc] or NULL (1)
+ * The matrix produced is A[a][b] = u_a^T (R K R^T) u_b, whose CSR arrays are the CSC arrays
+ * of the reference's matrix (its contraction at fem/vec_l2.py:113-114 yields R K^T R^T).
+ */
+enum {
+  PGB_L1_MASS = 0,      /* fem/h1.py:218-237 + fem/l2.py:63-86,457-470     L = d+1      */
+  PGB_L1_STIFF = 1,     /* (K grad u, grad v): 3D stiff and assemble_grad_grad_matrix h1.py:39-63 */
+  PGB_L1_STIFF_ROT = 2, /* 2D assemble_stiff_matrix = (K rot grad u, rot grad v), h1.py:46-48     */
+  PGB_RT0_MASS = 3,     /* fem/hdiv.py:255-274,450-509                      L = d+1      */
+  PGB_BDM1_MASS = 4,    /* fem/hdiv.py:450-509                              L = d(d+1)   */
+  PGB_N0_MASS = 5,      /* fem/hcurl.py:44-61,215-291                       L = d(d+1)/2 */
+  PGB_N0_CURLCURL = 6,  /* fem/hcurl.py:82-106 via discretization.py:154-183             */
+  PGB_P0_MASS = 7,      /* fem/l2.py:335-353: diag(w/|c|)                   L = 1        */
+  PGB_RT0_DIVDIV = 8,   /* RT0 stiff = cell_faces diag(w/|c|) cell_faces^T (hdiv.py:177-192 via
+                           discretization.py:154-183); also Nedelec0 stiff in 2D     L = d+1 */
+  PGB_BDM1_DIVDIV = 9   /* BDM1 stiff, div = div_RT0 @ hstack([I]*d)/d (hdiv.py:353-371)  L = d(d+1) */
+};
+int pgb_local_size(int kind, int dim); /* L */
+int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
+                       const uint8_t* sign_bits, const uint32_t* aux_bits, const double* coords,
+                       const double* K, const double* R_host, const double* w, double* vals,
+                       void* stream);
+
+/* ---- K2: COO -> CSR, deterministic, no floating-point atomics --------------------
+ * Replaces scipy's COO->CSC constructor and SpGEMM duplicate summation
+ * (e.g. fem/hdiv.py:509, fem/hcurl.py:291, fem/h1.py:237, discretization.py:136).
+ * COO entry i = cell*L*L + a*L + b has row cell_dofs[cell*L+a], col cell_dofs[cell*L+b].
+ *
+ * symbolic_sort: stable LSD radix sort of the packed (row,col) keys, payload = COO position.
+ *   workspace: pgb_csr_workspace_bytes(n_coo, n_rows) bytes.
+ *   perm [n_coo] out: COO positions in sorted order.  nnz_host: number of distinct keys
+ *   (the call synchronises the stream to return it).
+ * symbolic_finish: indptr (int32 if idx64==0 else int64) [n_rows+1], indices [nnz],
+ *   seg [nnz+1]: start of each entry's run in perm.
+ * numeric: data[k] = sum over its run of vals[perm[.]], warp-shuffle segmented reduce in
+ *   fixed order (bit-reproducible).
+ */
+int64_t pgb_csr_workspace_bytes(int64_t n_coo, int64_t n_rows);
+int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell_dofs,
+                          void* workspace, int64_t workspace_bytes, uint32_t* perm,
+                          int64_t* nnz_host, void* stream);
+int pgb_csr_symbolic_finish(int64_t n_rows, int64_t n_coo, int64_t nnz, const void* workspace,
+                            void* indptr, int idx64, int32_t* indices, uint32_t* seg,
+                            void* stream);
+int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t* seg, const double* vals,
+                    double* data, void* stream);
+
+/* ---- K3: SpMV and fused Krylov steps ----------------------------------------------
+ * The reference has no iterative solver (numerics/linear_system.py:79-94 takes any
+ * `solver(A, b) -> x`); these implement the recurrences of scipy.sparse.linalg.cg / minres
+ * (scipy 1.18.1), which are the oracle.  indptr is int32 (idx64==0) or int64.
+ */
+/* threads_per_row: 2,4,8,16,32 or 0 = choose from nnz/row (costs one device->host read). */
+int pgb_spmv(int64_t n_rows, const void* indptr, int idx64, const int32_t* indices,
+             const double* data, const double* x, double* y, int threads_per_row, void* stream);
+
+/* Whole CG solve on one GPU.  x (in: x0, out: solution), work: 3*n doubles.
+ * dinv: optional Jacobi preconditioner (1/diag) or NULL.  resid_host[maxiter+1] (host, may be
+ * NULL) receives ||r_k||_2 for k = 0..iters.  Stops when ||r|| <= max(atol, rtol*||b||), checked
+ * every iteration like scipy.  Synchronises the stream.  *iters_host = iterations done,
+ * *info_host = 0 converged / maxiter otherwise. */
+int pgb_cg(int64_t n, const void* indptr, int idx64, const int32_t* indices, const double* data,
+           const double* b, double* x, const double* dinv, double rtol, double atol, int maxiter,
+           double* work, int* iters_host, int* info_host, double* resid_host, void* stream);
+
+/* Whole MINRES solve (Paige-Saunders as in scipy).  work: 6*n doubles. */
+int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_t* indices,
+               const double* data, const double* b, double* x, double shift, double rtol,
+               int maxiter, double* work, int* iters_host, int* info_host, double* resid_host,
+               void* stream);
+
+/* Building blocks used by the multi-GPU drivers (halo exchange / allreduce happen between
+ * them on the host side through NCCL). */
+int pgb_dot_partials(int64_t n, const double* x, const double* y, double* partials /*[PGB_NPART]*/,
+                     void* stream);
+int pgb_reduce_partials(const double* partials, int count, double* out, void* stream);
+int pgb_axpby(int64_t n, double a, const double* x, double b, double* y, void* stream);
+#define PGB_NPART 1184
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGB_H */

@@ -422,7 +422,27 @@ def local_nedelec0_curlcurl(sd, tabs, w, K):
     return np.einsum("cae,cab,cbf->cef", C, A_rt0, C), eid
 
 
+def local_rt0_divdiv(sd, tabs, w, K):
+    """RT0 stiffness B^T diag(w/|c|) B with B = cell_faces^T: s_a s_b w/|c| (hdiv.py:177-192,
+    l2.py:335-353 through discretization.py:154-183)."""
+    _, vol, _ = local_geometry(sd, tabs)
+    s = tabs["signs"]
+    return s[:, :, None] * s[:, None, :] * (w / vol)[:, None, None], tabs["faces"]
+
+
+def local_bdm1_divdiv(sd, tabs, w, K):
+    """BDM1 stiffness: div = div_RT0 @ hstack([I]*d)/d (hdiv.py:322-336, 353-371)."""
+    d, nc, nf = sd.dim, sd.num_cells, sd.num_faces
+    _, vol, _ = local_geometry(sd, tabs)
+    s = np.repeat(tabs["signs"], d, axis=1)
+    A = s[:, :, None] * s[:, None, :] * (w / (vol * d * d))[:, None, None]
+    dofs = (tabs["faces"][:, :, None] + nf * np.arange(d)[None, None, :]).reshape(nc, d * (d + 1))
+    return A, dofs
+
+
 _LOCAL = {
+    ("rt0", "stiff"): local_rt0_divdiv,
+    ("bdm1", "stiff"): local_bdm1_divdiv,
     ("lagrange1", "mass"): local_lagrange1_mass,
     ("lagrange1", "stiff"): local_lagrange1_stiff,
     ("rt0", "mass"): local_rt0_mass,

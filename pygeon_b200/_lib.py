@@ -1,0 +1,84 @@
+"""ctypes binding of libpgb.so (the C ABI in include/pgb.h).
+
+There is no CPU fallback: importing this module without the built library raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgb.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -m pygeon_b200._build` "
+        "(nvcc, sm_100a).  pygeon_b200 has no CPU fallback."
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+_p, _i, _l, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+
+_SIGS = {
+    "pgb_version": (_i, []),
+    "pgb_last_error": (C.c_char_p, []),
+    "pgb_pack_cells": (_i, [_i, _l, _p, _p, _p, _p, _p, _p, _p]),
+    "pgb_pack_bdm1": (_i, [_i, _l, _l, _p, _p, _p, _p, _p, _p]),
+    "pgb_pack_edges3d": (_i, [_l, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pgb_pack_edges2d": (_i, [_l, _p, _p, _p, _p, _p]),
+    "pgb_prep_coords": (_i, [_i, _l, _p, _p, _p, _p]),
+    "pgb_local_size": (_i, [_i, _i]),
+    "pgb_local_matrices": (_i, [_i, _i, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pgb_csr_workspace_bytes": (_l, [_l, _l]),
+    "pgb_csr_symbolic_sort": (_i, [_l, _l, _i, _p, _p, _l, _p, C.POINTER(C.c_int64), _p]),
+    "pgb_csr_symbolic_finish": (_i, [_l, _l, _l, _p, _p, _i, _p, _p, _p]),
+    "pgb_csr_numeric": (_i, [_l, _p, _p, _p, _p, _p]),
+    "pgb_spmv": (_i, [_l, _p, _i, _p, _p, _p, _p, _i, _p]),
+    "pgb_cg": (_i, [_l, _p, _i, _p, _p, _p, _p, _p, _d, _d, _i, _p, C.POINTER(_i), C.POINTER(_i), _p, _p]),
+    "pgb_minres": (_i, [_l, _p, _i, _p, _p, _p, _p, _d, _d, _i, _p, C.POINTER(_i), C.POINTER(_i), _p, _p]),
+    "pgb_dot_partials": (_i, [_l, _p, _p, _p, _p]),
+    "pgb_reduce_partials": (_i, [_p, _i, _p, _p]),
+    "pgb_axpby": (_i, [_l, _d, _p, _d, _p, _p]),
+}
+for _name, (_res, _args) in _SIGS.items():
+    _f = getattr(lib, _name)  # AttributeError here = header and library disagree
+    _f.restype = _res
+    _f.argtypes = _args
+
+EXPORTS = tuple(_SIGS)
+
+KIND = {
+    "l1_mass": 0,
+    "l1_stiff": 1,
+    "l1_stiff_rot": 2,
+    "rt0_mass": 3,
+    "bdm1_mass": 4,
+    "n0_mass": 5,
+    "n0_curlcurl": 6,
+    "p0_mass": 7,
+    "rt0_divdiv": 8,
+    "bdm1_divdiv": 9,
+}
+NPART = 1184
+
+
+class PgbError(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise PgbError(lib.pgb_last_error().decode())
+
+
+def launches() -> int:
+    return _launch_count[0]
+
+
+_launch_count = [0]
+
+
+def count(n: int) -> None:
+    _launch_count[0] += n

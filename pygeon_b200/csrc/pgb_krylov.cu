@@ -1,0 +1,674 @@
+// K3: CSR SpMV (sub-warp per row, persistent grid) and the fused vector steps of CG / MINRES.
+//
+// The recurrences are those of scipy.sparse.linalg.cg and .minres (scipy 1.18.1,
+// _isolve/iterative.py and _isolve/minres.py), which are the oracle for this part: the reference
+// itself only exposes the `solver(A, b)` plug-in point (numerics/linear_system.py:79-94).
+//
+// Reductions are two-stage and atomic-free: every kernel that produces a dot product writes one
+// partial per block into a fixed-size array (PGB_NPART slots, unused slots zeroed), and every
+// consumer kernel re-reduces that array in a fixed order.  Scalars never leave the device during
+// the iteration; the host polls a mapped pinned flag to stop launching.
+#include <math.h>
+#include "pgb_common.cuh"
+
+namespace {
+
+constexpr int KB = 256;  // threads per block for all Krylov kernels
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int NPART = PGB_NPART;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+
+// fixed-order block sum, result valid in every thread
+__device__ __forceinline__ double block_sum(double v, double* ws /*[KB/32]*/) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) ws[w] = v;
+  __syncthreads();
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < KB / 32; ++i) s += ws[i];
+  return s;
+}
+
+__device__ __forceinline__ double sum_partials(const double* __restrict__ parts, double* ws) {
+  double s = 0;
+  for (int i = threadIdx.x; i < NPART; i += KB) s += parts[i];
+  return block_sum(s, ws);
+}
+
+__device__ __forceinline__ void write_partial(double* parts, double v) {
+  if (threadIdx.x == 0) parts[blockIdx.x] = v;
+  if (blockIdx.x == 0)
+    for (int i = gridDim.x + threadIdx.x; i < NPART; i += KB) parts[i] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// SpMV
+// ------------------------------------------------------------------------------------------
+struct MinresScal {
+  // persistent state (scipy variable names)
+  double beta1, beta, oldb, dbar, epsln, phibar, rhs1, rhs2, tnorm2, gmax, gmin, cs, sn;
+  double Anorm, Acond, rnorm, root, ynorm;
+  // per-iteration coefficients produced by the scalar kernel
+  double alfa, oldeps, delta, denom, phi, inv_beta;
+  double rtol, shift;
+  int itn, istop, pending, done, maxiter;
+};
+
+struct CgScal {
+  double rho, rho_prev, atol_user, rtol, bnorm2;
+  int done, iters;
+};
+
+enum { SPMV_PLAIN = 0, SPMV_CG = 1, SPMV_MINRES = 2 };
+
+struct SpmvArgs {
+  int64_t n;
+  const void* indptr;
+  const int32_t* indices;
+  const double* data;
+  const double* x;
+  double* y;
+  double* parts;         // CG / MINRES: partial dot(x, y)
+  const CgScal* cg;      // SPMV_CG
+  const MinresScal* mr;  // SPMV_MINRES
+  const double* r1;      // SPMV_MINRES
+  int itn;               // SPMV_MINRES: 1-based iteration
+};
+
+template <int TPR, typename IP, int MODE>
+__global__ void __launch_bounds__(KB) k_spmv(SpmvArgs a) {
+  __shared__ double ws[KB / 32];
+  if (MODE == SPMV_CG && a.cg->done) return;
+  if (MODE == SPMV_MINRES && a.mr->done) return;
+  constexpr int RPB = KB / TPR;  // rows per block-tile
+  const int sub = threadIdx.x % TPR;
+  const int grp = threadIdx.x / TPR;
+  const IP* __restrict__ ip = reinterpret_cast<const IP*>(a.indptr);
+  double shift = 0.0, coef = 0.0;
+  if (MODE == SPMV_MINRES) {
+    shift = a.mr->shift;
+    coef = (a.itn >= 2) ? a.mr->beta / a.mr->oldb : 0.0;
+  }
+  double dot = 0.0;
+  const int64_t ntiles = (a.n + RPB - 1) / RPB;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int64_t row = t * RPB + grp;
+    double s = 0.0;
+    if (row < a.n) {
+      IP lo = ip[row], hi = ip[row + 1];
+      for (IP j = lo + sub; j < hi; j += TPR) s += a.data[j] * __ldg(a.x + a.indices[j]);
+    }
+#pragma unroll
+    for (int d = TPR / 2; d > 0; d >>= 1) s += __shfl_xor_sync(FULL, s, d);
+    if (row < a.n && sub == 0) {
+      if (MODE == SPMV_MINRES) {
+        double xv = a.x[row];
+        if (shift != 0.0) s -= shift * xv;
+        if (a.itn >= 2) s -= coef * a.r1[row];
+        dot += xv * s;
+      } else if (MODE == SPMV_CG) {
+        dot += a.x[row] * s;
+      }
+      a.y[row] = s;
+    }
+  }
+  if (MODE != SPMV_PLAIN) {
+    double tot = block_sum(dot, ws);
+    write_partial(a.parts, tot);
+  }
+}
+
+template <int TPR, typename IP, int MODE>
+int launch_spmv_t(const SpmvArgs& a, cudaStream_t s) {
+  static int grid = 0;
+  if (!grid) {
+    int occ = 0;
+    PGB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv<TPR, IP, MODE>, KB, 0));
+    int dev = 0, sms = PGB_SMS;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    grid = occ * sms;
+    if (grid > NPART) grid = NPART;
+    if (grid < 1) grid = 1;
+  }
+  int64_t ntiles = (a.n + (KB / TPR) - 1) / (KB / TPR);
+  int g = (int)(ntiles < grid ? (ntiles < 1 ? 1 : ntiles) : grid);
+  k_spmv<TPR, IP, MODE><<<g, KB, 0, s>>>(a);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename IP, int MODE>
+int launch_spmv_ip(const SpmvArgs& a, int tpr, cudaStream_t s) {
+  switch (tpr) {
+    case 2: return launch_spmv_t<2, IP, MODE>(a, s);
+    case 4: return launch_spmv_t<4, IP, MODE>(a, s);
+    case 8: return launch_spmv_t<8, IP, MODE>(a, s);
+    case 16: return launch_spmv_t<16, IP, MODE>(a, s);
+    default: return launch_spmv_t<32, IP, MODE>(a, s);
+  }
+}
+
+template <int MODE>
+int launch_spmv(const SpmvArgs& a, int idx64, int tpr, cudaStream_t s) {
+  return idx64 ? launch_spmv_ip<int64_t, MODE>(a, tpr, s) : launch_spmv_ip<int32_t, MODE>(a, tpr, s);
+}
+
+int pick_tpr(double avg) {
+  if (avg <= 3.0) return 2;
+  if (avg <= 6.0) return 4;
+  if (avg <= 12.0) return 8;
+  if (avg <= 48.0) return 16;
+  return 32;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic vector helpers
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KB) k_dot(int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                                            double* parts) {
+  __shared__ double ws[KB / 32];
+  double s = 0;
+  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB) s += x[i] * y[i];
+  write_partial(parts, block_sum(s, ws));
+}
+
+__global__ void __launch_bounds__(KB) k_reduce(const double* parts, int count, double* out) {
+  __shared__ double ws[KB / 32];
+  double s = 0;
+  for (int i = threadIdx.x; i < count; i += KB) s += parts[i];
+  s = block_sum(s, ws);
+  if (threadIdx.x == 0) *out = s;
+}
+
+__global__ void __launch_bounds__(KB) k_axpby(int64_t n, double a, const double* __restrict__ x, double b,
+                                              double* __restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB)
+    y[i] = a * x[i] + (b == 0.0 ? 0.0 : b * y[i]);
+}
+
+int vec_grid(int64_t n) {
+  int64_t g = pgb_cdiv(n, KB);
+  if (g > NPART) g = NPART;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------
+// CG
+// ------------------------------------------------------------------------------------------
+// r = b - q ; partials rr, rho = r.z (z = dinv*r), bb
+__global__ void __launch_bounds__(KB) k_cg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q,
+                                                const double* __restrict__ dinv, double* __restrict__ r,
+                                                double* p_rr, double* p_rho, double* p_bb) {
+  __shared__ double ws[KB / 32];
+  double rr = 0, rho = 0, bb = 0;
+  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB) {
+    double bi = b[i];
+    double ri = bi - q[i];
+    r[i] = ri;
+    rr += ri * ri;
+    rho += ri * (dinv ? dinv[i] * ri : ri);
+    bb += bi * bi;
+  }
+  write_partial(p_rr, block_sum(rr, ws));
+  write_partial(p_rho, block_sum(rho, ws));
+  write_partial(p_bb, block_sum(bb, ws));
+}
+
+// top of iteration k: convergence check, then p = z + beta p
+__global__ void __launch_bounds__(KB) k_cg_p(int64_t n, int k, const double* __restrict__ r,
+                                             const double* __restrict__ dinv, double* __restrict__ p,
+                                             const double* p_rr, const double* p_rho, const double* p_bb,
+                                             CgScal* sc, double* resid, volatile int* host_flag) {
+  __shared__ double ws[KB / 32];
+  if (sc->done) return;
+  double rr = sum_partials(p_rr, ws);
+  double rho = sum_partials(p_rho, ws);
+  double bb = sum_partials(p_bb, ws);
+  double rnorm = sqrt(rr);
+  double atol = fmax(sc->atol_user, sc->rtol * sqrt(bb));
+  bool done = rnorm < atol;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    resid[k] = rnorm;
+    sc->bnorm2 = bb;
+    if (done) {
+      sc->done = 1;
+      *host_flag = 1;
+      __threadfence_system();
+    } else {
+      sc->rho = rho;
+      sc->iters = k + 1;
+    }
+  }
+  if (done) return;
+  double beta = (k > 0) ? rho / sc->rho_prev : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB) {
+    double z = dinv ? dinv[i] * r[i] : r[i];
+    p[i] = (k > 0) ? z + beta * p[i] : z;
+  }
+}
+
+// alpha = rho / (p.q); x += alpha p; r -= alpha q; partials rr, rho
+__global__ void __launch_bounds__(KB) k_cg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ q,
+                                              const double* __restrict__ dinv, double* __restrict__ x,
+                                              double* __restrict__ r, const double* p_pq, double* p_rr,
+                                              double* p_rho, CgScal* sc) {
+  __shared__ double ws[KB / 32];
+  if (sc->done) return;
+  double pq = sum_partials(p_pq, ws);
+  double rho_cur = sc->rho;
+  double alpha = rho_cur / pq;
+  double rr = 0, rho = 0;
+  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB) {
+    x[i] += alpha * p[i];
+    double ri = r[i] - alpha * q[i];
+    r[i] = ri;
+    rr += ri * ri;
+    rho += ri * (dinv ? dinv[i] * ri : ri);
+  }
+  write_partial(p_rr, block_sum(rr, ws));
+  write_partial(p_rho, block_sum(rho, ws));
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc->rho_prev = rho_cur;
+}
+
+// ------------------------------------------------------------------------------------------
+// MINRES
+// ------------------------------------------------------------------------------------------
+// r1 = b - q ; y = psolve(r1); partials beta1^2 = r1.y, bb
+__global__ void __launch_bounds__(KB) k_mr_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q,
+                                                const double* __restrict__ dinv, double* __restrict__ r1,
+                                                double* p_b1, double* p_bb) {
+  __shared__ double ws[KB / 32];
+  double b1 = 0, bb = 0;
+  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB) {
+    double bi = b[i];
+    double ri = bi - q[i];
+    r1[i] = ri;
+    b1 += ri * (dinv ? dinv[i] * ri : ri);
+    bb += bi * bi;
+  }
+  write_partial(p_b1, block_sum(b1, ws));
+  write_partial(p_bb, block_sum(bb, ws));
+}
+
+// v = psolve(r) * s ; w = w2 = 0
+__global__ void __launch_bounds__(KB) k_mr_start(int64_t n, const double* __restrict__ r, const double* __restrict__ dinv,
+                                                 const MinresScal* sc, double* __restrict__ v, double* __restrict__ w,
+                                                 double* __restrict__ w2) {
+  double s = 1.0 / sc->beta;
+  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB) {
+    v[i] = (dinv ? dinv[i] * r[i] : r[i]) * s;
+    w[i] = 0.0;
+    w2[i] = 0.0;
+  }
+}
+
+// y -= (alfa/beta) r2  (y becomes the new r2); partial beta^2 = r2new . psolve(r2new)
+__global__ void __launch_bounds__(KB) k_mr_c(int64_t n, double* __restrict__ y, const double* __restrict__ r2,
+                                             const double* __restrict__ dinv, const double* p_alfa, double* p_beta,
+                                             MinresScal* sc) {
+  __shared__ double ws[KB / 32];
+  if (sc->done) return;
+  double alfa = sum_partials(p_alfa, ws);
+  double c = alfa / sc->beta;
+  double bt = 0;
+  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB) {
+    double yi = y[i] - c * r2[i];
+    y[i] = yi;
+    bt += yi * (dinv ? dinv[i] * yi : yi);
+  }
+  write_partial(p_beta, block_sum(bt, ws));
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc->alfa = alfa;
+}
+
+__device__ void mr_tests(MinresScal* sc, double ynorm) {
+  const double eps = 2.220446049250313e-16;
+  sc->ynorm = ynorm;
+  double Anorm = sc->Anorm;
+  double epsx = Anorm * ynorm * eps;
+  double test1 = (ynorm == 0.0 || Anorm == 0.0) ? INFINITY : sc->rnorm / (Anorm * ynorm);
+  double test2 = (Anorm == 0.0) ? INFINITY : sc->root / Anorm;
+  int istop = sc->pending;
+  if (istop == 0) {
+    double t1 = 1.0 + test1, t2 = 1.0 + test2;
+    if (t2 <= 1.0) istop = 2;
+    if (t1 <= 1.0) istop = 1;
+    if (sc->itn >= sc->maxiter) istop = 6;
+    if (sc->Acond >= 0.1 / eps) istop = 4;
+    if (epsx >= sc->beta1) istop = 3;
+    if (test2 <= sc->rtol) istop = 2;
+    if (test1 <= sc->rtol) istop = 1;
+  }
+  sc->istop = istop;
+}
+
+// one thread: (i) stopping tests of the previous iteration (needs ||x|| from its x-update),
+// (ii) Lanczos / rotation scalars of the current one.
+__global__ void k_mr_scalars(int itn, const double* p_beta, const double* p_xx, MinresScal* sc, double* resid,
+                             volatile int* host_flag, int test_only) {
+  __shared__ double ws[KB / 32];
+  if (sc->done) return;
+  double xx = sum_partials(p_xx, ws);
+  double bt = sum_partials(p_beta, ws);
+  if (threadIdx.x != 0) return;
+  const double eps = 2.220446049250313e-16;
+  if (itn >= 2 || test_only) {
+    mr_tests(sc, sqrt(xx));
+    if (sc->istop != 0) {
+      sc->done = 1;
+      *host_flag = 1;
+      __threadfence_system();
+      return;
+    }
+  }
+  if (test_only) return;
+  double alfa = sc->alfa;
+  double oldb = sc->beta;
+  double beta = sqrt(bt);  // bt < 0 cannot happen for an SPD preconditioner
+  sc->tnorm2 += alfa * alfa + oldb * oldb + beta * beta;
+  if (itn == 1 && beta / sc->beta1 <= 10 * eps) sc->pending = -1;
+  double oldeps = sc->epsln;
+  double delta = sc->cs * sc->dbar + sc->sn * alfa;
+  double gbar = sc->sn * sc->dbar - sc->cs * alfa;
+  double epsln = sc->sn * beta;
+  double dbar = -sc->cs * beta;
+  double root = hypot(gbar, dbar);
+  double gamma = fmax(hypot(gbar, beta), eps);
+  double cs = gbar / gamma, sn = beta / gamma;
+  double phi = cs * sc->phibar;
+  double phibar = sn * sc->phibar;
+  sc->oldeps = oldeps;
+  sc->delta = delta;
+  sc->denom = 1.0 / gamma;
+  sc->phi = phi;
+  sc->inv_beta = 1.0 / beta;
+  sc->epsln = epsln;
+  sc->dbar = dbar;
+  sc->cs = cs;
+  sc->sn = sn;
+  sc->phibar = phibar;
+  sc->gmax = fmax(sc->gmax, gamma);
+  sc->gmin = fmin(sc->gmin, gamma);
+  double z = sc->rhs1 / gamma;
+  sc->rhs1 = sc->rhs2 - delta * z;
+  sc->rhs2 = -epsln * z;
+  sc->Anorm = sqrt(sc->tnorm2);
+  sc->rnorm = phibar;
+  sc->root = root;
+  sc->Acond = sc->gmax / sc->gmin;
+  sc->oldb = oldb;
+  sc->beta = beta;
+  sc->itn = itn;
+  resid[itn] = phibar;
+}
+
+// w = (v - oldeps w1 - delta w2) denom, stored over w1 (= w_{k-2}, dead afterwards); x += phi w;
+// v = psolve(r2)/beta; partial x.x
+__global__ void __launch_bounds__(KB) k_mr_d(int64_t n, double* __restrict__ v, double* __restrict__ w1,
+                                             const double* __restrict__ w2, const double* __restrict__ r2,
+                                             const double* __restrict__ dinv, double* __restrict__ x, double* p_xx,
+                                             const MinresScal* sc) {
+  __shared__ double ws[KB / 32];
+  if (sc->done) return;
+  double oldeps = sc->oldeps, delta = sc->delta, denom = sc->denom, phi = sc->phi, ib = sc->inv_beta;
+  double xx = 0;
+  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB) {
+    double wn = (v[i] - oldeps * w1[i] - delta * w2[i]) * denom;
+    w1[i] = wn;
+    double xi = x[i] + phi * wn;
+    x[i] = xi;
+    xx += xi * xi;
+    v[i] = (dinv ? dinv[i] * r2[i] : r2[i]) * ib;
+  }
+  write_partial(p_xx, block_sum(xx, ws));
+}
+
+__global__ void k_mr_setup(MinresScal* sc, const double* p_b1, const double* p_bb, double rtol, double shift,
+                           int maxiter, double* out2) {
+  __shared__ double ws[KB / 32];
+  double b1 = sum_partials(p_b1, ws);
+  double bb = sum_partials(p_bb, ws);
+  if (threadIdx.x != 0) return;
+  MinresScal s = {};
+  s.beta1 = sqrt(fmax(b1, 0.0));
+  s.beta = s.beta1;
+  s.phibar = s.beta1;
+  s.rhs1 = s.beta1;
+  s.gmin = 1.7976931348623157e308;
+  s.cs = -1.0;
+  s.rtol = rtol;
+  s.shift = shift;
+  s.maxiter = maxiter;
+  *sc = s;
+  out2[0] = b1;
+  out2[1] = bb;
+}
+
+// small persistent scratch shared by the drivers
+struct Scratch {
+  int* flag_host = nullptr;  // mapped pinned
+  int* flag_dev = nullptr;
+  void* scal = nullptr;  // device, 1 KB
+  double* parts = nullptr;  // device, 8 * NPART doubles
+  double* resid = nullptr;  // device
+  int resid_cap = 0;
+};
+thread_local Scratch g_scr;
+
+int ensure_scratch(int maxiter) {
+  Scratch& s = g_scr;
+  if (!s.flag_host) {
+    PGB_CHECK(cudaHostAlloc((void**)&s.flag_host, 64, cudaHostAllocMapped));
+    PGB_CHECK(cudaHostGetDevicePointer((void**)&s.flag_dev, s.flag_host, 0));
+    PGB_CHECK(cudaMalloc(&s.scal, 1024));
+    PGB_CHECK(cudaMalloc((void**)&s.parts, sizeof(double) * 8 * NPART));
+  }
+  if (s.resid_cap < maxiter + 2) {
+    if (s.resid) cudaFree(s.resid);
+    PGB_CHECK(cudaMalloc((void**)&s.resid, sizeof(double) * (size_t)(maxiter + 2)));
+    s.resid_cap = maxiter + 2;
+  }
+  return 0;
+}
+
+double avg_row(int64_t n, const void* indptr, int idx64, cudaStream_t s) {
+  int64_t nnz = 0;
+  if (idx64) {
+    cudaMemcpyAsync(&nnz, (const int64_t*)indptr + n, 8, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+  } else {
+    int32_t t = 0;
+    cudaMemcpyAsync(&t, (const int32_t*)indptr + n, 4, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    nnz = t;
+  }
+  return n > 0 ? (double)nnz / (double)n : 0.0;
+}
+
+}  // namespace
+
+extern "C" int pgb_spmv(int64_t n_rows, const void* indptr, int idx64, const int32_t* indices,
+                        const double* data, const double* x, double* y, int threads_per_row,
+                        void* stream) {
+  if (n_rows == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  SpmvArgs a = {};
+  a.n = n_rows; a.indptr = indptr; a.indices = indices; a.data = data; a.x = x; a.y = y;
+  int tpr = threads_per_row > 0 ? threads_per_row : pick_tpr(avg_row(n_rows, indptr, idx64, s));
+  return launch_spmv<SPMV_PLAIN>(a, idx64, tpr, s);
+}
+
+extern "C" int pgb_dot_partials(int64_t n, const double* x, const double* y, double* partials, void* stream) {
+  k_dot<<<vec_grid(n), KB, 0, (cudaStream_t)stream>>>(n, x, y, partials);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_reduce_partials(const double* partials, int count, double* out, void* stream) {
+  k_reduce<<<1, KB, 0, (cudaStream_t)stream>>>(partials, count, out);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_axpby(int64_t n, double a, const double* x, double b, double* y, void* stream) {
+  if (n == 0) return 0;
+  k_axpby<<<vec_grid(n), KB, 0, (cudaStream_t)stream>>>(n, a, x, b, y);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_cg(int64_t n, const void* indptr, int idx64, const int32_t* indices,
+                      const double* data, const double* b, double* x, const double* dinv, double rtol,
+                      double atol, int maxiter, double* work, int* iters_host, int* info_host,
+                      double* resid_host, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  PGB_REQUIRE(n > 0 && maxiter >= 0, "pgb_cg: bad arguments");
+  if (ensure_scratch(maxiter)) return 1;
+  Scratch& S = g_scr;
+  double* r = work;
+  double* p = work + n;
+  double* q = work + 2 * n;
+  double *p_rr = S.parts, *p_rho = S.parts + NPART, *p_bb = S.parts + 2 * NPART, *p_pq = S.parts + 3 * NPART;
+  CgScal* sc = (CgScal*)S.scal;
+  CgScal h = {};
+  h.atol_user = atol;
+  h.rtol = rtol;
+  *S.flag_host = 0;
+  PGB_CHECK(cudaMemcpyAsync(sc, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  const int tpr = pick_tpr(avg_row(n, indptr, idx64, s));
+  const int vg = vec_grid(n);
+
+  SpmvArgs a = {};
+  a.n = n; a.indptr = indptr; a.indices = indices; a.data = data;
+  a.x = x; a.y = q;
+  if (launch_spmv<SPMV_PLAIN>(a, idx64, tpr, s)) return 1;
+  k_cg_init<<<vg, KB, 0, s>>>(n, b, q, dinv, r, p_rr, p_rho, p_bb);
+  PGB_LAUNCH_CHECK();
+  a.x = p; a.y = q; a.parts = p_pq; a.cg = sc;
+  int launched = 0;
+  for (int k = 0; k <= maxiter; ++k) {
+    if (*(volatile int*)S.flag_host) break;
+    if (k == maxiter) break;
+    k_cg_p<<<vg, KB, 0, s>>>(n, k, r, dinv, p, p_rr, p_rho, p_bb, sc, S.resid, S.flag_dev);
+    if (launch_spmv<SPMV_CG>(a, idx64, tpr, s)) return 1;
+    k_cg_xr<<<vg, KB, 0, s>>>(n, p, q, dinv, x, r, p_pq, p_rr, p_rho, sc);
+    PGB_LAUNCH_CHECK();
+    ++launched;
+  }
+  // final residual record (also catches convergence exactly at maxiter for the history)
+  if (launched == maxiter) {
+    k_reduce<<<1, KB, 0, s>>>(p_rr, NPART, S.resid + maxiter + 1);
+    PGB_LAUNCH_CHECK();
+  }
+  PGB_CHECK(cudaMemcpyAsync(&h, sc, sizeof(h), cudaMemcpyDeviceToHost, s));
+  PGB_CHECK(cudaStreamSynchronize(s));
+  int iters = h.iters;
+  if (h.bnorm2 == 0.0) {  // scipy: return b (= 0)
+    PGB_CHECK(cudaMemsetAsync(x, 0, sizeof(double) * n, s));
+    iters = 0;
+    h.done = 1;
+  }
+  if (iters_host) *iters_host = iters;
+  if (info_host) *info_host = h.done ? 0 : maxiter;
+  if (resid_host) {
+    int cnt = h.done ? iters + 1 : iters;
+    if (cnt > 0) PGB_CHECK(cudaMemcpyAsync(resid_host, S.resid, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s));
+    if (!h.done && launched == maxiter) {
+      double rr = 0;
+      PGB_CHECK(cudaMemcpyAsync(&rr, S.resid + maxiter + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+      PGB_CHECK(cudaStreamSynchronize(s));
+      resid_host[iters] = sqrt(rr);
+    }
+    PGB_CHECK(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+
+extern "C" int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_t* indices,
+                          const double* data, const double* b, double* x, double shift, double rtol,
+                          int maxiter, double* work, int* iters_host, int* info_host,
+                          double* resid_host, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  PGB_REQUIRE(n > 0 && maxiter >= 0, "pgb_minres: bad arguments");
+  if (ensure_scratch(maxiter)) return 1;
+  Scratch& S = g_scr;
+  const double* dinv = nullptr;
+  double* v = work;
+  double* rb[3] = {work + n, work + 2 * n, work + 3 * n};  // r1, r2, y rotate
+  double* wb[2] = {work + 4 * n, work + 5 * n};
+  double *p_alfa = S.parts, *p_beta = S.parts + NPART, *p_xx = S.parts + 2 * NPART, *p_b1 = S.parts + 3 * NPART,
+         *p_bb = S.parts + 4 * NPART;
+  double* out2 = S.parts + 5 * NPART;
+  MinresScal* sc = (MinresScal*)S.scal;
+  *S.flag_host = 0;
+  const int tpr = pick_tpr(avg_row(n, indptr, idx64, s));
+  const int vg = vec_grid(n);
+
+  SpmvArgs a = {};
+  a.n = n; a.indptr = indptr; a.indices = indices; a.data = data;
+  a.x = x; a.y = rb[2];
+  if (launch_spmv<SPMV_PLAIN>(a, idx64, tpr, s)) return 1;
+  k_mr_init<<<vg, KB, 0, s>>>(n, b, rb[2], dinv, rb[0], p_b1, p_bb);
+  k_mr_setup<<<1, KB, 0, s>>>(sc, p_b1, p_bb, rtol, shift, maxiter, out2);
+  PGB_LAUNCH_CHECK();
+  double hb[2];
+  PGB_CHECK(cudaMemcpyAsync(hb, out2, sizeof(hb), cudaMemcpyDeviceToHost, s));
+  PGB_CHECK(cudaStreamSynchronize(s));
+  if (iters_host) *iters_host = 0;
+  if (info_host) *info_host = 0;
+  if (hb[0] == 0.0) return 0;  // beta1 == 0: x0 solves the system
+  if (hb[1] == 0.0) {          // b == 0: scipy returns b
+    PGB_CHECK(cudaMemsetAsync(x, 0, sizeof(double) * n, s));
+    return 0;
+  }
+  // r2 = r1 (same buffer until the first rotation: scipy aliases them)
+  double* r1 = rb[0];
+  double* r2 = rb[0];
+  double* y = rb[1];
+  double* spare = rb[2];
+  double *w_new = wb[0], *w_old = wb[1];  // w_{k-1}, w_{k-2}
+  k_mr_start<<<vg, KB, 0, s>>>(n, r1, dinv, sc, v, w_new, w_old);
+  k_dot<<<vg, KB, 0, s>>>(n, x, x, p_xx);
+  PGB_LAUNCH_CHECK();
+  a.parts = p_alfa; a.mr = sc;
+  int itn = 0;
+  while (itn < maxiter) {
+    if (*(volatile int*)S.flag_host) break;
+    ++itn;
+    a.x = v; a.y = y; a.r1 = r1; a.itn = itn;
+    if (launch_spmv<SPMV_MINRES>(a, idx64, tpr, s)) return 1;
+    k_mr_c<<<vg, KB, 0, s>>>(n, y, r2, dinv, p_alfa, p_beta, sc);
+    // rotate: r1 <- r2, r2 <- y, y <- a free buffer
+    double* old_r1 = r1;
+    r1 = r2;
+    r2 = y;
+    y = (old_r1 == r1) ? spare : old_r1;
+    k_mr_scalars<<<1, KB, 0, s>>>(itn, p_beta, p_xx, sc, S.resid, S.flag_dev, 0);
+    // scipy: w1 = w2; w2 = w; w = (v - oldeps w1 - delta w2) denom.  The new w overwrites w_{k-2}.
+    k_mr_d<<<vg, KB, 0, s>>>(n, v, w_old, w_new, r2, dinv, x, p_xx, sc);
+    PGB_LAUNCH_CHECK();
+    double* t = w_old;
+    w_old = w_new;
+    w_new = t;
+  }
+  k_mr_scalars<<<1, KB, 0, s>>>(itn + 1, p_beta, p_xx, sc, S.resid, S.flag_dev, 1);
+  PGB_LAUNCH_CHECK();
+  MinresScal h;
+  PGB_CHECK(cudaMemcpyAsync(&h, sc, sizeof(h), cudaMemcpyDeviceToHost, s));
+  PGB_CHECK(cudaStreamSynchronize(s));
+  if (iters_host) *iters_host = h.itn;
+  if (info_host) *info_host = (h.istop == 6) ? maxiter : 0;
+  if (resid_host && h.itn > 0) {
+    PGB_CHECK(cudaMemcpyAsync(resid_host, S.resid + 1, sizeof(double) * h.itn, cudaMemcpyDeviceToHost, s));
+    PGB_CHECK(cudaStreamSynchronize(s));
+  }
+  return 0;
+}

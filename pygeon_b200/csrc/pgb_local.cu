@@ -1,0 +1,452 @@
+// K1: per-cell local matrices, fp64, one thread per cell.
+//
+// Loads: cell->node ids as one 16-byte vector per cell (3D), sign / aux bit words, optional
+// weight and tensor (SoA over cells -> coalesced), node coordinates gathered as 16-byte vectors
+// from the padded [nn][4] (3D) / [nn][2] (2D) table.  Stores: each thread writes its L*L values
+// to a shared-memory tile laid out [k][thread] (conflict-free), then the block streams the tile
+// to vals[cell][k] with fully coalesced 8-byte stores.
+//
+// Closed forms: SURVEY.md section 8(a); each kind cites the reference code it replaces in pgb.h.
+#include "pgb_common.cuh"
+
+namespace {
+
+constexpr int BLOCK = 128;
+
+struct Params {
+  int64_t nc;
+  const int32_t* cell_nodes;
+  const uint8_t* sign_bits;
+  const uint32_t* aux_bits;
+  const double* coords;
+  const double* K;
+  const double* w;
+  double* vals;
+  double R[9];
+  int r_ident;
+};
+
+template <int D>
+struct Geo {
+  double X[D + 1][D];
+  double G[D + 1][D];
+  double vol;
+};
+
+template <int D>
+__device__ __forceinline__ void load_nodes(const Params& p, int64_t c, double (&X)[D + 1][D]) {
+  if constexpr (D == 3) {
+    int4 cn = reinterpret_cast<const int4*>(p.cell_nodes)[c];
+    int ids[4] = {cn.x, cn.y, cn.z, cn.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const double2* q = reinterpret_cast<const double2*>(p.coords) + 2 * (int64_t)ids[a];
+      double2 xy = __ldg(q);
+      double2 z_ = __ldg(q + 1);
+      X[a][0] = xy.x;
+      X[a][1] = xy.y;
+      X[a][2] = z_.x;
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      int id = p.cell_nodes[c * 3 + a];
+      double2 xy = __ldg(reinterpret_cast<const double2*>(p.coords) + id);
+      X[a][0] = xy.x;
+      X[a][1] = xy.y;
+    }
+  }
+}
+
+// |c| and barycentric gradients from the node coordinates alone
+template <int D>
+__device__ __forceinline__ void gradients(Geo<D>& g) {
+  if constexpr (D == 3) {
+    double e1[3], e2[3], e3[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      e1[i] = g.X[1][i] - g.X[0][i];
+      e2[i] = g.X[2][i] - g.X[0][i];
+      e3[i] = g.X[3][i] - g.X[0][i];
+    }
+    double c23[3] = {e2[1] * e3[2] - e2[2] * e3[1], e2[2] * e3[0] - e2[0] * e3[2], e2[0] * e3[1] - e2[1] * e3[0]};
+    double c31[3] = {e3[1] * e1[2] - e3[2] * e1[1], e3[2] * e1[0] - e3[0] * e1[2], e3[0] * e1[1] - e3[1] * e1[0]};
+    double c12[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    double det = e1[0] * c23[0] + e1[1] * c23[1] + e1[2] * c23[2];
+    double inv = 1.0 / det;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      g.G[1][i] = c23[i] * inv;
+      g.G[2][i] = c31[i] * inv;
+      g.G[3][i] = c12[i] * inv;
+      g.G[0][i] = -(g.G[1][i] + g.G[2][i] + g.G[3][i]);
+    }
+    g.vol = fabs(det) * (1.0 / 6.0);
+  } else {
+    double a = g.X[1][0] - g.X[0][0], b = g.X[1][1] - g.X[0][1];
+    double c = g.X[2][0] - g.X[0][0], d = g.X[2][1] - g.X[0][1];
+    double det = a * d - b * c;
+    double inv = 1.0 / det;
+    g.G[1][0] = d * inv;
+    g.G[1][1] = -c * inv;
+    g.G[2][0] = -b * inv;
+    g.G[2][1] = a * inv;
+    g.G[0][0] = -(g.G[1][0] + g.G[2][0]);
+    g.G[0][1] = -(g.G[1][1] + g.G[2][1]);
+    g.vol = fabs(det) * 0.5;
+  }
+}
+
+// Kr = R K R^T (d x d)
+template <int D>
+__device__ __forceinline__ void load_tensor(const Params& p, int64_t c, double (&Kr)[D][D]) {
+  if (p.r_ident) {
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) Kr[i][j] = p.K[(int64_t)(i * 3 + j) * p.nc + c];
+  } else {
+    double K3[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) K3[i][j] = p.K[(int64_t)(i * 3 + j) * p.nc + c];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double s = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) s += p.R[i * 3 + a] * K3[a][b] * p.R[j * 3 + b];
+        Kr[i][j] = s;
+      }
+  }
+}
+
+// v^T Kr u helpers: KV[n] = Kr V[n]
+template <int D, int N, bool HAS_K>
+__device__ __forceinline__ void apply_tensor(const double (&Kr)[D][D], const double (&V)[N][D], double (&KV)[N][D]) {
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      if constexpr (HAS_K) {
+        double s = 0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) s += Kr[i][j] * V[n][j];
+        KV[n][i] = s;
+      } else {
+        KV[n][i] = V[n][i];
+      }
+    }
+}
+
+template <int D>
+__device__ __forceinline__ double dotd(const double (&a)[D], const double (&b)[D]) {
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) s += a[i] * b[i];
+  return s;
+}
+
+template <int D>
+__device__ __forceinline__ double mhat(int i, int j) {
+  constexpr double base = 1.0 / ((D + 1) * (D + 2));
+  return (i == j) ? 2.0 * base : base;
+}
+
+// RT0 local mass into A[(D+1)][(D+1)]:  w s_a s_b/(d^2|c|) [ T/((d+1)(d+2)) + y_a^T Kr y_b ]
+template <int D, bool HAS_K>
+__device__ __forceinline__ void rt0_local(const Geo<D>& g, const double (&Kr)[D][D], unsigned sbits, double w,
+                                          double (&A)[D + 1][D + 1]) {
+  double Y[D + 1][D], KY[D + 1][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double m = 0;
+#pragma unroll
+    for (int a = 0; a <= D; ++a) m += g.X[a][i];
+    m *= 1.0 / (D + 1);
+#pragma unroll
+    for (int a = 0; a <= D; ++a) Y[a][i] = g.X[a][i] - m;
+  }
+  apply_tensor<D, D + 1, HAS_K>(Kr, Y, KY);
+  double T = 0;
+#pragma unroll
+  for (int a = 0; a <= D; ++a) T += dotd<D>(Y[a], KY[a]);
+  T *= 1.0 / ((D + 1) * (D + 2));
+  double coef = w / ((double)(D * D) * g.vol);
+#pragma unroll
+  for (int a = 0; a <= D; ++a)
+#pragma unroll
+    for (int b = 0; b <= D; ++b) {
+      double s = (((sbits >> a) ^ (sbits >> b)) & 1u) ? -coef : coef;
+      A[a][b] = s * (dotd<D>(Y[a], KY[b]) + T);
+    }
+}
+
+__device__ __forceinline__ void pair3(int e, int& p, int& q) {
+  constexpr int P[6] = {0, 0, 0, 1, 1, 2};
+  constexpr int Q[6] = {1, 2, 3, 2, 3, 3};
+  p = P[e];
+  q = Q[e];
+}
+
+template <int KIND, int D>
+struct LocalSize {
+  static constexpr int L = (KIND == PGB_BDM1_MASS || KIND == PGB_BDM1_DIVDIV)   ? D * (D + 1)
+                           : (KIND == PGB_N0_MASS || KIND == PGB_N0_CURLCURL) ? D * (D + 1) / 2
+                           : (KIND == PGB_P0_MASS)                            ? 1
+                                                                              : D + 1;
+};
+
+template <int KIND, int D, bool HAS_K, bool HAS_W>
+__global__ void __launch_bounds__(BLOCK) k_local(Params p) {
+  constexpr int L = LocalSize<KIND, D>::L;
+  constexpr int LL = L * L;
+  constexpr bool STAGED = (LL <= 36);
+  __shared__ double tile[STAGED ? LL * (BLOCK + 1) : 1];
+
+  const int tid = threadIdx.x;
+  const int64_t c0 = (int64_t)blockIdx.x * BLOCK;
+  const int64_t c = c0 + tid;
+  const bool live = c < p.nc;
+
+  auto emit = [&](int k, double v) {
+    if constexpr (STAGED)
+      tile[k * (BLOCK + 1) + tid] = v;
+    else
+      p.vals[c * LL + k] = v;
+  };
+
+  if (live) {
+    Geo<D> g;
+    load_nodes<D>(p, c, g.X);
+    gradients<D>(g);
+    double w = 1.0;
+    if constexpr (HAS_W) w = p.w[c];
+    double Kr[D][D];
+    if constexpr (HAS_K) load_tensor<D>(p, c, Kr);
+
+    if constexpr (KIND == PGB_P0_MASS) {
+      emit(0, w / g.vol);
+    } else if constexpr (KIND == PGB_RT0_DIVDIV) {
+      unsigned sb = p.sign_bits[c];
+      double wv = w / g.vol;
+#pragma unroll
+      for (int a = 0; a <= D; ++a)
+#pragma unroll
+        for (int b = 0; b <= D; ++b) emit(a * L + b, (((sb >> a) ^ (sb >> b)) & 1u) ? -wv : wv);
+    } else if constexpr (KIND == PGB_BDM1_DIVDIV) {
+      unsigned sb = p.sign_bits[c];
+      double wv = w / (g.vol * (double)(D * D));
+#pragma unroll
+      for (int r = 0; r < L; ++r)
+#pragma unroll
+        for (int q = 0; q < L; ++q) emit(r * L + q, (((sb >> (r / D)) ^ (sb >> (q / D))) & 1u) ? -wv : wv);
+    } else if constexpr (KIND == PGB_L1_MASS) {
+      double wv = w * g.vol;
+#pragma unroll
+      for (int a = 0; a <= D; ++a)
+#pragma unroll
+        for (int b = 0; b <= D; ++b) emit(a * L + b, wv * mhat<D>(a, b));
+    } else if constexpr (KIND == PGB_L1_STIFF || KIND == PGB_L1_STIFF_ROT) {
+      double Gv[D + 1][D], KG[D + 1][D];
+#pragma unroll
+      for (int a = 0; a <= D; ++a) {
+        if constexpr (KIND == PGB_L1_STIFF_ROT && D == 2) {
+          Gv[a][0] = g.G[a][1];
+          Gv[a][1] = -g.G[a][0];
+        } else {
+#pragma unroll
+          for (int i = 0; i < D; ++i) Gv[a][i] = g.G[a][i];
+        }
+      }
+      apply_tensor<D, D + 1, HAS_K>(Kr, Gv, KG);
+      double wv = w * g.vol;
+#pragma unroll
+      for (int a = 0; a <= D; ++a)
+#pragma unroll
+        for (int b = 0; b <= D; ++b) emit(a * L + b, wv * dotd<D>(Gv[a], KG[b]));
+    } else if constexpr (KIND == PGB_RT0_MASS) {
+      double A[D + 1][D + 1];
+      rt0_local<D, HAS_K>(g, Kr, p.sign_bits[c], w, A);
+#pragma unroll
+      for (int a = 0; a <= D; ++a)
+#pragma unroll
+        for (int b = 0; b <= D; ++b) emit(a * L + b, A[a][b]);
+    } else if constexpr (KIND == PGB_N0_MASS) {
+      double KG[D + 1][D], GKG[D + 1][D + 1];
+      apply_tensor<D, D + 1, HAS_K>(Kr, g.G, KG);
+#pragma unroll
+      for (int a = 0; a <= D; ++a)
+#pragma unroll
+        for (int b = 0; b <= D; ++b) GKG[a][b] = dotd<D>(g.G[a], KG[b]);
+      unsigned bits = p.aux_bits[c];
+      double wv = w * g.vol;
+#pragma unroll
+      for (int e = 0; e < L; ++e) {
+        int pe, qe;
+        if constexpr (D == 3) pair3(e, pe, qe);
+        else { pe = (e == 0) ? 1 : 0; qe = (e == 2) ? 1 : 2; }
+#pragma unroll
+        for (int f = 0; f < L; ++f) {
+          int rf, sf;
+          if constexpr (D == 3) pair3(f, rf, sf);
+          else { rf = (f == 0) ? 1 : 0; sf = (f == 2) ? 1 : 2; }
+          double v = mhat<D>(pe, rf) * GKG[qe][sf] - mhat<D>(pe, sf) * GKG[qe][rf] -
+                     mhat<D>(qe, rf) * GKG[pe][sf] + mhat<D>(qe, sf) * GKG[pe][rf];
+          double s = (((bits >> e) ^ (bits >> f)) & 1u) ? -wv : wv;
+          emit(e * L + f, s * v);
+        }
+      }
+    } else if constexpr (KIND == PGB_N0_CURLCURL) {
+      if constexpr (D == 2) {
+        unsigned sb = p.sign_bits[c];
+        double wv = w / g.vol;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) emit(a * 3 + b, (((sb >> a) ^ (sb >> b)) & 1u) ? -wv : wv);
+      } else {
+        double A[4][4];
+        rt0_local<3, HAS_K>(g, Kr, p.sign_bits[c], w, A);
+        unsigned bits = p.aux_bits[c];
+        constexpr int FA[6] = {2, 1, 1, 0, 0, 0};
+        constexpr int FB[6] = {3, 3, 2, 3, 2, 1};
+#pragma unroll
+        for (int e = 0; e < 6; ++e) {
+          double sea = ((bits >> (8 + 2 * e)) & 1u) ? -1.0 : 1.0;
+          double seb = ((bits >> (9 + 2 * e)) & 1u) ? -1.0 : 1.0;
+#pragma unroll
+          for (int f = 0; f < 6; ++f) {
+            double sfa = ((bits >> (8 + 2 * f)) & 1u) ? -1.0 : 1.0;
+            double sfb = ((bits >> (9 + 2 * f)) & 1u) ? -1.0 : 1.0;
+            double v = sea * (sfa * A[FA[e]][FA[f]] + sfb * A[FA[e]][FB[f]]) +
+                       seb * (sfa * A[FB[e]][FA[f]] + sfb * A[FB[e]][FB[f]]);
+            emit(e * 6 + f, v);
+          }
+        }
+      }
+    } else if constexpr (KIND == PGB_BDM1_MASS) {
+      unsigned bits = p.aux_bits[c];
+      unsigned sb = p.sign_bits[c];
+      double T[L][D], KT[L][D];
+      int js[L];
+      double inv = 1.0 / ((double)D * g.vol);
+#pragma unroll
+      for (int a = 0; a <= D; ++a)
+#pragma unroll
+        for (int pos = 0; pos < D; ++pos) {
+          int r = a * D + pos;
+          int j = (bits >> (2 * r)) & 3u;
+          js[r] = j;
+          double s = ((sb >> a) & 1u) ? -inv : inv;
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            double xj = g.X[0][i];
+#pragma unroll
+            for (int t = 1; t <= D; ++t) xj = (j == t) ? g.X[t][i] : xj;
+            T[r][i] = (xj - g.X[a][i]) * s;
+          }
+        }
+      apply_tensor<D, L, HAS_K>(Kr, T, KT);
+      double wv = w * g.vol;
+      constexpr double base = 1.0 / ((D + 1) * (D + 2));
+#pragma unroll
+      for (int r = 0; r < L; ++r)
+#pragma unroll
+        for (int q = 0; q < L; ++q) {
+          double m = (js[r] == js[q]) ? 2.0 * base : base;
+          emit(r * L + q, wv * m * dotd<D>(T[r], KT[q]));
+        }
+    }
+  }
+
+  if constexpr (STAGED) {
+    __syncthreads();
+    int64_t rem = p.nc - c0;
+    int nb = rem < BLOCK ? (int)rem : BLOCK;
+    double* out = p.vals + c0 * LL;
+    for (int i = tid; i < nb * LL; i += BLOCK) {
+      int cell = i / LL, k = i - cell * LL;
+      out[i] = tile[k * (BLOCK + 1) + cell];
+    }
+  }
+}
+
+template <int KIND, int D>
+int launch(const Params& p, cudaStream_t s) {
+  unsigned grid = pgb_grid(p.nc, BLOCK);
+  bool hk = p.K != nullptr, hw = p.w != nullptr;
+  if (hk && hw) k_local<KIND, D, true, true><<<grid, BLOCK, 0, s>>>(p);
+  else if (hk) k_local<KIND, D, true, false><<<grid, BLOCK, 0, s>>>(p);
+  else if (hw) k_local<KIND, D, false, true><<<grid, BLOCK, 0, s>>>(p);
+  else k_local<KIND, D, false, false><<<grid, BLOCK, 0, s>>>(p);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int D>
+int dispatch(int kind, const Params& p, cudaStream_t s) {
+  switch (kind) {
+    case PGB_L1_MASS: return launch<PGB_L1_MASS, D>(p, s);
+    case PGB_L1_STIFF: return launch<PGB_L1_STIFF, D>(p, s);
+    case PGB_L1_STIFF_ROT: return launch<PGB_L1_STIFF_ROT, D>(p, s);
+    case PGB_RT0_MASS: return launch<PGB_RT0_MASS, D>(p, s);
+    case PGB_BDM1_MASS: return launch<PGB_BDM1_MASS, D>(p, s);
+    case PGB_N0_MASS: return launch<PGB_N0_MASS, D>(p, s);
+    case PGB_N0_CURLCURL: return launch<PGB_N0_CURLCURL, D>(p, s);
+    case PGB_P0_MASS: return launch<PGB_P0_MASS, D>(p, s);
+    case PGB_RT0_DIVDIV: return launch<PGB_RT0_DIVDIV, D>(p, s);
+    case PGB_BDM1_DIVDIV: return launch<PGB_BDM1_DIVDIV, D>(p, s);
+  }
+  pgb_set_error("pgb_local_matrices: unknown kind %d", kind);
+  return 2;
+}
+
+}  // namespace
+
+extern "C" int pgb_local_size(int kind, int dim) {
+  switch (kind) {
+    case PGB_BDM1_MASS:
+    case PGB_BDM1_DIVDIV: return dim * (dim + 1);
+    case PGB_N0_MASS:
+    case PGB_N0_CURLCURL: return dim * (dim + 1) / 2;
+    case PGB_P0_MASS: return 1;
+    default: return dim + 1;
+  }
+}
+
+extern "C" int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
+                                  const uint8_t* sign_bits, const uint32_t* aux_bits,
+                                  const double* coords, const double* K, const double* R_host,
+                                  const double* w, double* vals, void* stream) {
+  PGB_REQUIRE(dim == 2 || dim == 3, "pgb_local_matrices: dim must be 2 or 3");
+  PGB_REQUIRE(cell_nodes && coords && vals, "pgb_local_matrices: null pointer");
+  if (kind == PGB_RT0_MASS || kind == PGB_BDM1_MASS || kind == PGB_N0_CURLCURL ||
+      kind == PGB_RT0_DIVDIV || kind == PGB_BDM1_DIVDIV)
+    PGB_REQUIRE(sign_bits, "pgb_local_matrices: sign_bits required");
+  if (kind == PGB_BDM1_MASS || kind == PGB_N0_MASS || (kind == PGB_N0_CURLCURL && dim == 3))
+    PGB_REQUIRE(aux_bits, "pgb_local_matrices: aux_bits required");
+  if (nc == 0) return 0;
+  Params p;
+  p.nc = nc;
+  p.cell_nodes = cell_nodes;
+  p.sign_bits = sign_bits;
+  p.aux_bits = aux_bits;
+  p.coords = coords;
+  p.K = K;
+  p.w = w;
+  p.vals = vals;
+  bool ident = true;
+  for (int i = 0; i < 9; ++i) {
+    double r = (R_host && i < dim * 3) ? R_host[i] : ((i / 3 == i % 3 && i < dim * 3) ? 1.0 : 0.0);
+    p.R[i] = r;
+    if (i < dim * 3 && r != ((i / 3 == i % 3) ? 1.0 : 0.0)) ident = false;
+  }
+  p.r_ident = ident ? 1 : 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dim == 3 ? dispatch<3>(kind, p, s) : dispatch<2>(kind, p, s);
+}

@@ -1,0 +1,251 @@
+"""``pg.Discretization`` operator API on top of the CUDA engine.
+
+Same class names, constructor and method signatures as the reference
+(``src/pygeon/discretizations/discretization.py:14-358`` and the ``fem/`` classes named in each
+docstring), restricted to the rows of the hot-path scope table: mass and
+stiffness matrices of ``Lagrange1``, ``RT0``, ``BDM1``, ``Nedelec0`` and ``PwConstants`` on 2D
+triangle / 3D tetrahedral grids, plus the differential (incidence) matrices.
+
+Every ``assemble_*`` returns a ``scipy.sparse.csc_array`` like the reference; the ``*_device``
+variants return a :class:`~pygeon_b200.engine.DeviceCSR` that stays in HBM for the GPU solvers.
+Matrices carry the *structural* pattern (all pairs of dofs sharing a cell, explicit zeros kept,
+sorted indices); the reference's scipy SpGEMM drops entries whose floating-point sum is exactly
+0.0, which is value dependent.
+"""
+
+from __future__ import annotations
+
+import abc
+from typing import Type
+
+import numpy as np
+import scipy.sparse as sps
+
+from . import engine
+from .constants import SCALAR, SECOND_ORDER_TENSOR, UNITARY_DATA, VECTOR, WEIGHT
+from .params import get_cell_data
+
+
+class Discretization(abc.ABC):
+    """Abstract base (``discretization.py:14-58``)."""
+
+    poly_order: int
+    tensor_order: int
+    _space: str
+
+    def __init__(self, keyword: str = UNITARY_DATA) -> None:
+        self.keyword = keyword
+
+    def __repr__(self) -> str:
+        s = f"Discretization of type {self.__class__.__name__}"
+        if hasattr(self, "keyword"):
+            s += f" with keyword {self.keyword}"
+        return s
+
+    @abc.abstractmethod
+    def ndof(self, sd) -> int: ...
+
+    # ---- coefficients ------------------------------------------------------------------
+    def _coefficients(self, sd, data):
+        w = get_cell_data(sd, data, self.keyword, WEIGHT)
+        K = None
+        if self.tensor_order != SCALAR or True:
+            K = get_cell_data(sd, data, self.keyword, SECOND_ORDER_TENSOR)
+        return w, K
+
+    # ---- mass --------------------------------------------------------------------------
+    def assemble_mass_matrix_device(self, sd, data: dict | None = None) -> engine.DeviceCSR:
+        w, K = self._coefficients(sd, data)
+        if self.tensor_order == SCALAR:
+            K = None  # the scalar broken-P1 mass ignores the tensor (fem/l2.py:63-86)
+        return engine.assemble_device(self._space, "mass", sd, w, K)
+
+    def assemble_mass_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
+        """``(Pi.T @ M @ Pi).tocsc()`` of ``discretization.py:65-89,112-136``."""
+        if self.ndof(sd) == 0:
+            return sps.csc_array((0, 0))
+        return self.assemble_mass_matrix_device(sd, data).to_scipy("csc")
+
+    # ---- stiffness ---------------------------------------------------------------------
+    def _stiff_form(self, sd) -> str:
+        return "stiff"
+
+    def assemble_stiff_matrix_device(self, sd, data: dict | None = None) -> engine.DeviceCSR:
+        w, K = self._coefficients(sd, data)
+        form = self._stiff_form(sd)
+        if form in ("stiff2d",) or self._space in ("rt0", "bdm1"):
+            K = None  # range space is PwConstants: only the weight enters (fem/l2.py:335-353)
+        return engine.assemble_device(self._space, form, sd, w, K)
+
+    def assemble_stiff_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
+        """``(B.T @ A @ B).tocsc()`` of ``discretization.py:154-183``."""
+        self.get_range_discr_class(sd.dim)  # raises like the reference when there is none
+        return self.assemble_stiff_matrix_device(sd, data).to_scipy("csc")
+
+    @abc.abstractmethod
+    def assemble_diff_matrix(self, sd) -> sps.csc_array: ...
+
+    @abc.abstractmethod
+    def get_range_discr_class(self, dim: int) -> Type["Discretization"]: ...
+
+
+class PwConstants(Discretization):
+    """``fem/l2.py:284-353``: one dof per cell (the integral), mass = diag(w/|c|)."""
+
+    poly_order = 0
+    tensor_order = SCALAR
+    _space = "p0"
+
+    def ndof(self, sd) -> int:
+        return sd.num_cells
+
+    def assemble_mass_diagonal_device(self, sd, data: dict | None = None):
+        w = get_cell_data(sd, data, self.keyword, WEIGHT)
+        return engine.cell_volumes_inverse_weighted(sd, w)
+
+    def assemble_mass_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
+        if self.ndof(sd) == 0:
+            return sps.csc_array((0, 0))
+        diag = self.assemble_mass_diagonal_device(sd, data).cpu().numpy()
+        return sps.diags_array(diag).tocsc()
+
+    def assemble_lumped_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
+        return self.assemble_mass_matrix(sd, data)
+
+    def assemble_stiff_matrix(self, sd, data=None):
+        raise NotImplementedError("There's no zero discretization in PyGeoN")
+
+    def assemble_diff_matrix(self, sd) -> sps.csc_array:
+        return sps.csc_array((0, self.ndof(sd)))
+
+    def get_range_discr_class(self, dim: int):
+        raise NotImplementedError("There's no zero discretization in PyGeoN")
+
+
+class Lagrange1(Discretization):
+    """``fem/h1.py:13-324``: nodal P1."""
+
+    poly_order = 1
+    tensor_order = SCALAR
+    _space = "lagrange1"
+
+    def ndof(self, sd) -> int:
+        return sd.num_nodes
+
+    def _stiff_form(self, sd) -> str:
+        # 2D: B^T M_RT0 B = (K rot grad u, rot grad v), see fem/h1.py:46-48
+        return "stiff_rot" if sd.dim == 2 else "stiff"
+
+    def assemble_grad_grad_matrix_device(self, sd, data: dict | None = None) -> engine.DeviceCSR:
+        w, K = self._coefficients(sd, data)
+        return engine.assemble_device(self._space, "stiff", sd, w, K)
+
+    def assemble_grad_grad_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
+        """``(K grad u, grad v)`` (``fem/h1.py:39-63``)."""
+        return self.assemble_grad_grad_matrix_device(sd, data).to_scipy("csc")
+
+    def assemble_diff_matrix(self, sd) -> sps.csc_array:
+        """``fem/h1.py:152-179``."""
+        match sd.dim:
+            case 3:
+                return sd.ridge_peaks.T.tocsc()
+            case 2:
+                return sd.face_ridges.T.tocsc()
+            case 1:
+                return sd.cell_faces.T.tocsc()
+            case 0:
+                return sps.csc_array((0, 0))
+            case _:
+                raise ValueError("Dimension must be 0, 1, 2, or 3.")
+
+    def get_range_discr_class(self, dim: int):
+        match dim:
+            case 3:
+                return Nedelec0
+            case 2:
+                return RT0
+            case 1:
+                return PwConstants
+            case _:
+                raise NotImplementedError("There's no zero discretization in PyGeoN")
+
+
+class RT0(Discretization):
+    """``fem/hdiv.py:13-274``: one dof per face."""
+
+    poly_order = 1
+    tensor_order = VECTOR
+    _space = "rt0"
+
+    def ndof(self, sd) -> int:
+        return sd.num_faces
+
+    def assemble_diff_matrix(self, sd) -> sps.csc_array:
+        """``fem/hdiv.py:177-192``."""
+        return sps.csc_array(sd.cell_faces.T)
+
+    def get_range_discr_class(self, _dim: int):
+        return PwConstants
+
+
+class BDM1(Discretization):
+    """``fem/hdiv.py:277-509``: d dofs per face, dof (f, pos) -> f + pos*num_faces."""
+
+    poly_order = 1
+    tensor_order = VECTOR
+    _space = "bdm1"
+
+    def ndof(self, sd) -> int:
+        return sd.face_nodes.nnz
+
+    def proj_to_RT0(self, sd) -> sps.csc_array:
+        return (sps.hstack([sps.eye_array(sd.num_faces)] * sd.dim) / sd.dim).tocsc()
+
+    def proj_from_RT0(self, sd) -> sps.csc_array:
+        return sps.vstack([sps.eye_array(sd.num_faces)] * sd.dim).tocsc()
+
+    def assemble_diff_matrix(self, sd) -> sps.csc_array:
+        """``fem/hdiv.py:353-371``."""
+        return (sps.csc_array(sd.cell_faces.T) @ self.proj_to_RT0(sd)).tocsc()
+
+    def get_range_discr_class(self, _dim: int):
+        return PwConstants
+
+
+class Nedelec0(Discretization):
+    """``fem/hcurl.py:11-180``: one dof per edge (ridge in 3D, face in 2D)."""
+
+    poly_order = 1
+    tensor_order = VECTOR
+    _space = "nedelec0"
+
+    def ndof(self, sd) -> int:
+        return sd.num_edges
+
+    def _stiff_form(self, sd) -> str:
+        return "stiff2d" if sd.dim == 2 else "stiff"
+
+    def assemble_diff_matrix(self, sd) -> sps.csc_array:
+        """``fem/hcurl.py:82-106``."""
+        match sd.dim:
+            case 3:
+                diff = sd.face_ridges.T
+            case 2:
+                diff = sd.cell_faces.T
+            case _:
+                diff = sps.csc_array((0, self.ndof(sd)))
+        return diff.tocsc()
+
+    def assemble_lumped_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
+        """Row sums of the mass matrix on the diagonal (``fem/hcurl.py:63-80``)."""
+        diag_mass = self.assemble_mass_matrix(sd, data).sum(axis=0)
+        return sps.diags_array(np.asarray(diag_mass).flatten()).tocsc()
+
+    def get_range_discr_class(self, dim: int):
+        match dim:
+            case 2:
+                return PwConstants
+            case 3:
+                return RT0
+            case _:
+                raise NotImplementedError

@@ -1,0 +1,358 @@
+"""Device-side assembly engine: grid packing, local matrices (K1), COO->CSR (K2).
+
+torch is used for device memory, streams and copies only; every compute step is a call into
+libpgb.so through :mod:`pygeon_b200._lib`.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sps
+import torch
+
+from . import _lib
+from ._lib import KIND, check, lib
+
+_I32 = torch.int32
+
+
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("pygeon_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _to_dev(arr: np.ndarray, dev, dtype=None) -> torch.Tensor:
+    """Host numpy -> device tensor (async when the source is pinned), cast on the device."""
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    t = t.to(dev, non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t
+
+
+def _sign_i8(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype == torch.int8:
+        return t
+    return torch.where(t < 0, -1, 1).to(torch.int8)
+
+
+# --------------------------------------------------------------------------------------
+# packed grid
+# --------------------------------------------------------------------------------------
+@dataclass
+class GridPack:
+    """Device-resident per-cell tables of one grid (see include/pgb.h, "grid packing")."""
+
+    dim: int
+    nc: int
+    nf: int
+    nn: int
+    ne: int
+    device: torch.device
+    R: np.ndarray
+    coords: torch.Tensor
+    cf_idx: torch.Tensor
+    fn_idx: torch.Tensor
+    cell_nodes: torch.Tensor
+    sign_bits: torch.Tensor
+    _sd: object = None
+    _edges: tuple | None = None
+    _bdm1: tuple | None = None
+    plans: dict = field(default_factory=dict)
+
+    @staticmethod
+    def from_grid(sd, device=None) -> "GridPack":
+        dev = _device(device)
+        d = int(sd.dim)
+        if d not in (2, 3):
+            raise NotImplementedError("only 2D triangle and 3D tetrahedral grids are supported")
+        nc, nf, nn = int(sd.num_cells), int(sd.num_faces), int(sd.num_nodes)
+        cf, fn = sd.cell_faces, sd.face_nodes
+        if cf.indices.size != nc * (d + 1) or fn.indices.size != nf * d:
+            raise NotImplementedError("Grid is not simplicial; cannot compute opposite node.")
+        if nc and (np.any(cf.indptr[:: max(nc // 64, 1)] % (d + 1)) or cf.indptr[-1] != nc * (d + 1)):
+            raise NotImplementedError("Grid is not simplicial; cannot compute opposite node.")
+        R = np.ascontiguousarray(getattr(sd, "rotation_matrix", np.eye(d, 3)), dtype=np.float64)
+        with torch.cuda.device(dev):
+            s = _stream()
+            cf_idx = _to_dev(cf.indices, dev, _I32)
+            cf_sgn = _sign_i8(_to_dev(cf.data, dev))
+            fn_idx = _to_dev(fn.indices, dev, _I32)
+            nodes = _to_dev(np.asarray(sd.nodes, dtype=np.float64), dev)
+            coords = torch.empty((nn, 4 if d == 3 else 2), dtype=torch.float64, device=dev)
+            check(lib.pgb_prep_coords(d, nn, nodes.data_ptr(), R.ctypes.data, coords.data_ptr(), s))
+            cell_nodes = torch.empty((nc, d + 1), dtype=_I32, device=dev)
+            sign_bits = torch.empty((nc,), dtype=torch.uint8, device=dev)
+            err = torch.zeros((1,), dtype=_I32, device=dev)
+            check(
+                lib.pgb_pack_cells(
+                    d, nc, cf_idx.data_ptr(), cf_sgn.data_ptr(), fn_idx.data_ptr(),
+                    cell_nodes.data_ptr(), sign_bits.data_ptr(), err.data_ptr(), s,
+                )
+            )
+            _lib.count(2)
+            if int(err.item()):
+                raise NotImplementedError("Grid is not simplicial; cannot compute opposite node.")
+        ne = nf if d == 2 else int(getattr(sd, "num_ridges", 0))
+        return GridPack(d, nc, nf, nn, ne, dev, R, coords, cf_idx, fn_idx, cell_nodes, sign_bits, _sd=sd)
+
+    # -- Nedelec0 tables ----------------------------------------------------------------
+    def edges(self):
+        """(cell_edges (nc, E) int32, edge_bits (nc,) int32-as-uint32)."""
+        if self._edges is None:
+            sd, dev, d, nc = self._sd, self.device, self.dim, self.nc
+            with torch.cuda.device(dev):
+                s = _stream()
+                bits = torch.empty((nc,), dtype=_I32, device=dev)
+                fr = sd.face_ridges
+                if d == 2:
+                    if fr.indices.size != 2 * self.nf:
+                        raise NotImplementedError("face_ridges must have 2 entries per face")
+                    fr_idx = _to_dev(fr.indices, dev, _I32)
+                    check(lib.pgb_pack_edges2d(nc, self.cf_idx.data_ptr(), fr_idx.data_ptr(),
+                                               self.cell_nodes.data_ptr(), bits.data_ptr(), s))
+                    self._edges = (self.cf_idx.view(nc, 3), bits)
+                else:
+                    rp = sd.ridge_peaks
+                    if fr.indices.size != 3 * self.nf or rp.indices.size != 2 * self.ne:
+                        raise NotImplementedError("Grid is not simplicial")
+                    fr_idx = _to_dev(fr.indices, dev, _I32)
+                    fr_sgn = _sign_i8(_to_dev(fr.data, dev))
+                    rp_idx = _to_dev(rp.indices, dev, _I32)
+                    ce = torch.empty((nc, 6), dtype=_I32, device=dev)
+                    err = torch.zeros((1,), dtype=_I32, device=dev)
+                    check(lib.pgb_pack_edges3d(nc, self.cf_idx.data_ptr(), fr_idx.data_ptr(),
+                                               fr_sgn.data_ptr(), rp_idx.data_ptr(),
+                                               self.cell_nodes.data_ptr(), ce.data_ptr(),
+                                               bits.data_ptr(), err.data_ptr(), s))
+                    if int(err.item()):
+                        raise ValueError("face_ridges / ridge_peaks are inconsistent with the cells")
+                    self._edges = (ce, bits)
+                _lib.count(1)
+        return self._edges
+
+    def bdm1(self):
+        """(cell_dofs (nc, d(d+1)) int32, jslot_bits (nc,))."""
+        if self._bdm1 is None:
+            d, nc, dev = self.dim, self.nc, self.device
+            with torch.cuda.device(dev):
+                dofs = torch.empty((nc, d * (d + 1)), dtype=_I32, device=dev)
+                bits = torch.empty((nc,), dtype=_I32, device=dev)
+                check(lib.pgb_pack_bdm1(d, nc, self.nf, self.cf_idx.data_ptr(), self.fn_idx.data_ptr(),
+                                        self.cell_nodes.data_ptr(), dofs.data_ptr(), bits.data_ptr(),
+                                        _stream()))
+                _lib.count(1)
+            self._bdm1 = (dofs, bits)
+        return self._bdm1
+
+    # -- dof tables per space --------------------------------------------------------------
+    def dofs(self, space: str):
+        """(cell_dofs (nc, L) int32 tensor, ndof)."""
+        d = self.dim
+        if space == "lagrange1":
+            return self.cell_nodes, self.nn
+        if space == "rt0":
+            return self.cf_idx.view(self.nc, d + 1), self.nf
+        if space == "nedelec0":
+            return self.edges()[0], self.ne
+        if space == "bdm1":
+            return self.bdm1()[0], d * self.nf
+        raise KeyError(space)
+
+
+# --------------------------------------------------------------------------------------
+# symbolic plan + device CSR
+# --------------------------------------------------------------------------------------
+@dataclass
+class CsrPlan:
+    n_rows: int
+    n_coo: int
+    nnz: int
+    perm: torch.Tensor  # uint32 stored as int32
+    seg: torch.Tensor
+    indptr: torch.Tensor
+    indices: torch.Tensor
+
+
+@dataclass
+class DeviceCSR:
+    """A CSR matrix resident on the GPU (int32 indices; indptr int32 or int64; fp64 data)."""
+
+    shape: tuple
+    indptr: torch.Tensor
+    indices: torch.Tensor
+    data: torch.Tensor
+
+    @property
+    def nnz(self) -> int:
+        return int(self.indices.numel())
+
+    @property
+    def idx64(self) -> int:
+        return 1 if self.indptr.dtype == torch.int64 else 0
+
+    def to_scipy(self, fmt: str = "csc"):
+        """Host copy.  ``fmt='csc'`` reinterprets the CSR arrays as CSC (valid because the
+        engine builds the transpose-consistent matrix, see pgb.h K1 note)."""
+        ip = self.indptr.cpu().numpy()
+        ix = self.indices.cpu().numpy()
+        da = self.data.cpu().numpy()
+        cls = sps.csc_array if fmt == "csc" else sps.csr_array
+        if self.shape[0] == 0:
+            return cls(self.shape)
+        return cls((da, ix, ip), shape=self.shape)
+
+    @staticmethod
+    def from_scipy(A, device=None) -> "DeviceCSR":
+        dev = _device(device)
+        A = sps.csr_array(A)
+        A.sum_duplicates()
+        A.sort_indices()
+        it = torch.int64 if A.nnz >= 2**31 else _I32
+        return DeviceCSR(
+            tuple(A.shape),
+            _to_dev(A.indptr, dev, it),
+            _to_dev(A.indices, dev, _I32),
+            _to_dev(A.data.astype(np.float64, copy=False), dev),
+        )
+
+
+def symbolic(pack: GridPack, space: str) -> CsrPlan:
+    """Sort-by-(row,col) of the cell->dof incidences: pattern + gather permutation."""
+    key = ("plan", space)
+    if key in pack.plans:
+        return pack.plans[key]
+    dofs, n_rows = pack.dofs(space)
+    nc, L = int(dofs.shape[0]), int(dofs.shape[1])
+    n_coo = nc * L * L
+    dev = pack.device
+    with torch.cuda.device(dev):
+        s = _stream()
+        dofs = dofs.contiguous()
+        ws_bytes = int(lib.pgb_csr_workspace_bytes(n_coo, n_rows))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        perm = torch.empty((max(n_coo, 1),), dtype=_I32, device=dev)
+        nnz = C.c_int64(0)
+        check(lib.pgb_csr_symbolic_sort(n_rows, nc, L, dofs.data_ptr(), ws.data_ptr(), ws_bytes,
+                                        perm.data_ptr(), C.byref(nnz), s))
+        nnz = int(nnz.value)
+        it = torch.int64 if nnz >= 2**31 else _I32
+        indptr = torch.empty((n_rows + 1,), dtype=it, device=dev)
+        indices = torch.empty((nnz,), dtype=_I32, device=dev)
+        seg = torch.empty((nnz + 1,), dtype=_I32, device=dev)
+        check(lib.pgb_csr_symbolic_finish(n_rows, n_coo, nnz, ws.data_ptr(), indptr.data_ptr(),
+                                          1 if it == torch.int64 else 0, indices.data_ptr(),
+                                          seg.data_ptr(), s))
+        bits = max(1, int(n_rows - 1).bit_length()) if n_rows > 1 else 1
+        passes = (2 * bits + 7) // 8
+        _lib.count(passes * 5 + 3)
+        del ws
+    plan = CsrPlan(n_rows, n_coo, nnz, perm, seg, indptr, indices)
+    pack.plans[key] = plan
+    return plan
+
+
+_FORMS = {
+    ("lagrange1", "mass"): "l1_mass",
+    ("lagrange1", "stiff"): "l1_stiff",
+    ("lagrange1", "stiff_rot"): "l1_stiff_rot",
+    ("rt0", "mass"): "rt0_mass",
+    ("bdm1", "mass"): "bdm1_mass",
+    ("nedelec0", "mass"): "n0_mass",
+    ("nedelec0", "stiff"): "n0_curlcurl",
+    ("nedelec0", "stiff2d"): "rt0_divdiv",
+    ("rt0", "stiff"): "rt0_divdiv",
+    ("bdm1", "stiff"): "bdm1_divdiv",
+}
+
+
+def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None) -> torch.Tensor:
+    """K1: vals (nc, L*L) on the device.  ``w`` (nc,) / ``K`` (3,3,nc) are device tensors or None."""
+    d, nc, dev = pack.dim, pack.nc, pack.device
+    L = int(lib.pgb_local_size(KIND[kind], d))
+    aux = None
+    if kind in ("n0_mass",) or (kind == "n0_curlcurl" and d == 3):
+        aux = pack.edges()[1]
+    elif kind == "bdm1_mass":
+        aux = pack.bdm1()[1]
+    with torch.cuda.device(dev):
+        vals = out if out is not None else torch.empty((nc, L * L), dtype=torch.float64, device=dev)
+        check(
+            lib.pgb_local_matrices(
+                KIND[kind], d, nc, pack.cell_nodes.data_ptr(), pack.sign_bits.data_ptr(), _ptr(aux),
+                pack.coords.data_ptr(), _ptr(K), pack.R.ctypes.data, _ptr(w), vals.data_ptr(), _stream(),
+            )
+        )
+        _lib.count(1)
+    return vals
+
+
+def numeric(plan: CsrPlan, vals: torch.Tensor, out=None) -> torch.Tensor:
+    """K2 numeric phase: gather through the permutation + segmented reduce."""
+    dev = vals.device
+    with torch.cuda.device(dev):
+        data = out if out is not None else torch.empty((plan.nnz,), dtype=torch.float64, device=dev)
+        check(lib.pgb_csr_numeric(plan.nnz, plan.perm.data_ptr(), plan.seg.data_ptr(), vals.data_ptr(),
+                                  data.data_ptr(), _stream()))
+        _lib.count(1)
+    return data
+
+
+_CACHE_ATTR = "_pgb200_pack"
+cache_enabled = True
+
+
+def get_pack(sd, device=None) -> GridPack:
+    """Packed grid, cached on the grid object (the reference caches per grid too:
+    ``sd.opposite_nodes`` grid.py:291-307 and ``functools.cache`` hdiv.py:255,450)."""
+    dev = _device(device)
+    pack = getattr(sd, _CACHE_ATTR, None) if cache_enabled else None
+    if pack is None or pack.device != dev:
+        pack = GridPack.from_grid(sd, dev)
+        if cache_enabled:
+            try:
+                setattr(sd, _CACHE_ATTR, pack)
+            except AttributeError:
+                pass
+    return pack
+
+
+def clear_cache(sd) -> None:
+    if hasattr(sd, _CACHE_ATTR):
+        delattr(sd, _CACHE_ATTR)
+
+
+def assemble_device(space: str, form: str, sd, w=None, K=None, device=None) -> DeviceCSR:
+    """Full assembly on the device: pack (cached) -> K1 -> K2.  ``w``/``K`` are host numpy
+    arrays in the reference's layout or None."""
+    pack = get_pack(sd, device)
+    dev = pack.device
+    kind = _FORMS[(space, form)]
+    wd = None if w is None else _to_dev(w, dev)
+    Kd = None if K is None else _to_dev(K, dev)
+    plan = symbolic(pack, space)
+    vals = local_matrices(pack, kind, wd, Kd)
+    data = numeric(plan, vals)
+    n = plan.n_rows
+    return DeviceCSR((n, n), plan.indptr, plan.indices, data)
+
+
+def cell_volumes_inverse_weighted(sd, w=None, device=None) -> torch.Tensor:
+    """diag of the P0 mass matrix, w/|c| (fem/l2.py:335-353)."""
+    pack = get_pack(sd, device)
+    wd = None if w is None else _to_dev(w, pack.device)
+    return local_matrices(pack, "p0_mass", wd, None).view(-1)

@@ -411,3 +411,20 @@ def structured_grid(dim: int, n: int, perturb: float = 0.0, seed: int = 0, devic
     sd._geometry_done = False
     sd._structured = {k: con[k] for k in con if k in ("face_ridges", "face_ridge_sign", "ridge_peaks")}
     return sd
+
+
+def reference_element(dim: int) -> SimplexGrid:
+    """Reference triangle / tetrahedron with the face numbering and signs of
+    ``pg.reference_element`` (``grids/create_grid.py:159-195``): face a is opposite node a,
+    nodes are the origin and the unit vectors."""
+    if dim not in (2, 3):
+        raise ValueError("Dimension must be 2 or 3.")
+    nodes = np.eye(AMBIENT_DIM, dim + 1, k=1)
+    faces = [[j for j in range(dim + 1) if j != a] for a in range(dim + 1)]
+    indices = np.array(faces).ravel()
+    indptr = np.arange(0, indices.size + 1, dim)
+    face_nodes = sps.csc_array((np.ones(indices.size), indices, indptr))
+    signs = np.array([1.0, -1.0, 1.0, -1.0][: dim + 1])
+    cell_faces = sps.csc_array(signs[:, None])
+    name = "reference_triangle" if dim == 2 else "reference_tetrahedron"
+    return SimplexGrid(dim, nodes, face_nodes, cell_faces, name)

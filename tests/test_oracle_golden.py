@@ -1,0 +1,90 @@
+"""Pin the CPU oracle: known-answer matrices of the reference's own tests + golden fixtures
+generated from the reference (oracle/gen_golden.py).  Runs on CPU."""
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from oracle import fem_oracle as fo
+from pygeon_b200.grid import reference_element
+
+FORMS = [("lagrange1", "mass"), ("lagrange1", "stiff"), ("lagrange1", "gradgrad"), ("rt0", "mass"),
+         ("rt0", "stiff"), ("bdm1", "mass"), ("bdm1", "stiff"), ("nedelec0", "mass"), ("nedelec0", "stiff")]
+
+# --- known answers copied as data from the reference's tests (file:line in each id) ------------
+KNOWN = {
+    # tests/discretizations/fem/hdiv/test_rt0.py:25-63
+    ("rt0", "mass", 2): np.array([[1, 0, 0], [0, 2, 1], [0, 1, 2]]) / 6,
+    ("rt0", "mass", 3): np.array([[6, -1, 1, -1], [-1, 16, 4, -4], [1, 4, 16, 4], [-1, -4, 4, 16]]) / 30,
+    # tests/discretizations/fem/hcurl/test_nedelec0.py:19-51
+    ("nedelec0", "mass", 2): np.array([[1, 0, 0], [0, 2, 1], [0, 1, 2]]) / 6,
+    ("nedelec0", "mass", 3): np.array(
+        [[10, 5, 5, 0, 0, 0], [5, 10, 5, 0, 0, 0], [5, 5, 10, 0, 0, 0],
+         [0, 0, 0, 4, 1, -1], [0, 0, 0, 1, 4, 1], [0, 0, 0, -1, 1, 4]]) / 120,
+    # tests/discretizations/fem/hdiv/test_bdm1.py:19-68
+    ("bdm1", "mass", 2): np.array(
+        [[2, 1, 0, 0, 1, 2], [1, 2, 0, 0, 1, 1], [0, 0, 2, -1, 1, 1],
+         [0, 0, -1, 2, -2, -1], [1, 1, 1, -2, 4, 2], [2, 1, 1, -1, 2, 4]]) / 24,
+    ("bdm1", "mass", 3): np.array(
+        [[2, 1, 0, 0, 0, 1, 2, -2, 0, 1, 0, 0], [1, 2, 0, 0, 0, 1, 1, -1, 0, 1, 0, 0],
+         [0, 0, 2, 0, -1, 1, 1, 0, 0, 0, 1, 1], [0, 0, 0, 2, 0, 0, 0, 1, 1, -1, 1, 1],
+         [0, 0, -1, 0, 2, -2, -1, 0, 0, 0, -1, -2], [1, 1, 1, 0, -2, 4, 2, -1, 0, 1, 1, 2],
+         [2, 1, 1, 0, -1, 2, 4, -2, 0, 1, 1, 1], [-2, -1, 0, 1, 0, -1, -2, 4, 1, -2, 1, 1],
+         [0, 0, 0, 1, 0, 0, 0, 1, 2, -2, 2, 1], [1, 1, 0, -1, 0, 1, 1, -2, -2, 4, -2, -1],
+         [0, 0, 1, 1, -1, 1, 1, 1, 2, -2, 4, 2], [0, 0, 1, 1, -2, 2, 1, 1, 1, -1, 2, 4]]) / 30,
+    # tests/discretizations/fem/h1/test_lagrange1.py:25-63 (mass), :99-134 (stiff)
+    ("lagrange1", "mass", 2): np.array([[2, 1, 1], [1, 2, 1], [1, 1, 2]]) / 24,
+    ("lagrange1", "mass", 3): np.array([[2, 1, 1, 1], [1, 2, 1, 1], [1, 1, 2, 1], [1, 1, 1, 2]]) / 120,
+    ("lagrange1", "stiff", 2): np.array([[2, -1, -1], [-1, 1, 0], [-1, 0, 1]]) / 2,
+    ("lagrange1", "stiff", 3): np.array([[3, -1, -1, -1], [-1, 1, 0, 0], [-1, 0, 1, 0], [-1, 0, 0, 1]]) / 6,
+}
+
+
+@pytest.mark.parametrize("key", sorted(KNOWN), ids=lambda k: f"{k[0]}-{k[1]}-{k[2]}d")
+@pytest.mark.parametrize("route", ["port", "closed"])
+def test_known_answer_reference_element(key, route):
+    space, form, dim = key
+    sd = reference_element(dim)
+    sd.compute_geometry()
+    if route == "port":
+        A = fo.port_mass(space, sd) if form == "mass" else fo.port_stiff(space, sd)
+    else:
+        A = fo.closed_form(space, form, sd)
+    assert np.allclose(A.toarray(), KNOWN[key], rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("space,form", FORMS)
+def test_closed_form_matches_golden(golden, space, form):
+    ref = golden.matrix(space, form)
+    kw = {"rot2d": False} if form == "gradgrad" else {}
+    f = "stiff" if form == "gradgrad" else form
+    A = fo.closed_form(space, f, golden.sd, golden.data, "key", **kw)
+    assert np.array_equal(A.indptr, ref.indptr)
+    assert np.array_equal(A.indices, ref.indices)
+    scale = np.abs(ref.data).max()
+    assert np.abs(A.data - ref.data).max() <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("space,form", [f for f in FORMS if f[1] != "gradgrad"])
+def test_port_matches_golden(golden, space, form):
+    ref = golden.matrix(space, form)
+    A = fo.port_mass(space, golden.sd, golden.data, "key") if form == "mass" else fo.port_stiff(
+        space, golden.sd, golden.data, "key")
+    scale = np.abs(ref.data).max()
+    assert abs(sps.csr_array(A) - ref).max() <= 1e-12 * scale
+    assert sps.csr_array(A).nnz == int(golden.z[f"{space}_{form}_refnnz"])  # same SpGEMM pruning
+
+
+def test_p0_mass_matches_golden(golden):
+    d = fo.p0_mass(golden.sd, golden.data, "key").diagonal()
+    assert np.allclose(d, golden.z["p0_mass_diag"], rtol=1e-13)
+
+
+def test_coo_to_csr_edge_cases():
+    # empty rows, duplicates, explicit zeros kept
+    rows = np.array([3, 0, 3, 0, 5])
+    cols = np.array([1, 0, 1, 0, 5])
+    vals = np.array([1.0, 2.0, -1.0, 0.5, 0.0])
+    A = fo.coo_to_csr(rows, cols, vals, 7)
+    assert A.nnz == 3 and np.array_equal(A.indptr, [0, 1, 1, 1, 2, 2, 3, 3])
+    assert np.array_equal(A.data, [2.5, 0.0, 0.0])

@@ -51,6 +51,79 @@ def _sign_i8(t: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------
+# raw grid on the device
+# --------------------------------------------------------------------------------------
+@dataclass
+class RawGrid:
+    """The grid arrays the engine reads, resident on the device, exactly as the grid object
+    stores them: ``cell_faces`` (indices, signs), ``face_nodes.indices``, ``nodes`` (3, nn) and,
+    for Nedelec0, ``face_ridges`` (indices, signs) / ``ridge_peaks.indices``."""
+
+    dim: int
+    nc: int
+    nf: int
+    nn: int
+    ne: int
+    device: torch.device
+    R: np.ndarray
+    cf_idx: torch.Tensor
+    cf_sgn: torch.Tensor
+    fn_idx: torch.Tensor
+    nodes: torch.Tensor
+    fr_idx: torch.Tensor | None = None
+    fr_sgn: torch.Tensor | None = None
+    rp_idx: torch.Tensor | None = None
+    check: bool = True
+    _sd: object = None
+    h2d_bytes: int = 0
+
+    @staticmethod
+    def upload(sd, device=None, ridges: bool = False) -> "RawGrid":
+        dev = _device(device)
+        d = int(sd.dim)
+        if d not in (2, 3):
+            raise NotImplementedError("only 2D triangle and 3D tetrahedral grids are supported")
+        nc, nf, nn = int(sd.num_cells), int(sd.num_faces), int(sd.num_nodes)
+        cf, fn = sd.cell_faces, sd.face_nodes
+        if cf.indices.size != nc * (d + 1) or fn.indices.size != nf * d:
+            raise NotImplementedError("Grid is not simplicial; cannot compute opposite node.")
+        if nc and (np.any(cf.indptr[:: max(nc // 64, 1)] % (d + 1)) or cf.indptr[-1] != nc * (d + 1)):
+            raise NotImplementedError("Grid is not simplicial; cannot compute opposite node.")
+        R = np.ascontiguousarray(getattr(sd, "rotation_matrix", np.eye(d, 3)), dtype=np.float64)
+        nodes_h = np.asarray(sd.nodes, dtype=np.float64)
+        with torch.cuda.device(dev):
+            raw = RawGrid(
+                d, nc, nf, nn, nf if d == 2 else int(getattr(sd, "num_ridges", 0)), dev, R,
+                _to_dev(cf.indices, dev, _I32), _sign_i8(_to_dev(cf.data, dev)),
+                _to_dev(fn.indices, dev, _I32), _to_dev(nodes_h, dev), _sd=sd,
+            )
+        raw.h2d_bytes = cf.indices.nbytes + cf.data.nbytes + fn.indices.nbytes + nodes_h.nbytes
+        if ridges:
+            raw.need_ridges()
+        return raw
+
+    def need_ridges(self) -> None:
+        if self.fr_idx is not None:
+            return
+        sd, dev, d = self._sd, self.device, self.dim
+        fr = sd.face_ridges
+        with torch.cuda.device(dev):
+            if d == 2:
+                if fr.indices.size != 2 * self.nf:
+                    raise NotImplementedError("face_ridges must have 2 entries per face")
+                self.fr_idx = _to_dev(fr.indices, dev, _I32)
+                self.h2d_bytes += fr.indices.nbytes
+            else:
+                rp = sd.ridge_peaks
+                if fr.indices.size != 3 * self.nf or rp.indices.size != 2 * self.ne:
+                    raise NotImplementedError("Grid is not simplicial")
+                self.fr_idx = _to_dev(fr.indices, dev, _I32)
+                self.fr_sgn = _sign_i8(_to_dev(fr.data, dev))
+                self.rp_idx = _to_dev(rp.indices, dev, _I32)
+                self.h2d_bytes += fr.indices.nbytes + fr.data.nbytes + rp.indices.nbytes
+
+
+# --------------------------------------------------------------------------------------
 # packed grid
 # --------------------------------------------------------------------------------------
 @dataclass
@@ -69,77 +142,60 @@ class GridPack:
     fn_idx: torch.Tensor
     cell_nodes: torch.Tensor
     sign_bits: torch.Tensor
-    _sd: object = None
+    _raw: object = None
     _edges: tuple | None = None
     _bdm1: tuple | None = None
     plans: dict = field(default_factory=dict)
 
     @staticmethod
     def from_grid(sd, device=None) -> "GridPack":
-        dev = _device(device)
-        d = int(sd.dim)
-        if d not in (2, 3):
-            raise NotImplementedError("only 2D triangle and 3D tetrahedral grids are supported")
-        nc, nf, nn = int(sd.num_cells), int(sd.num_faces), int(sd.num_nodes)
-        cf, fn = sd.cell_faces, sd.face_nodes
-        if cf.indices.size != nc * (d + 1) or fn.indices.size != nf * d:
-            raise NotImplementedError("Grid is not simplicial; cannot compute opposite node.")
-        if nc and (np.any(cf.indptr[:: max(nc // 64, 1)] % (d + 1)) or cf.indptr[-1] != nc * (d + 1)):
-            raise NotImplementedError("Grid is not simplicial; cannot compute opposite node.")
-        R = np.ascontiguousarray(getattr(sd, "rotation_matrix", np.eye(d, 3)), dtype=np.float64)
+        """Upload the grid's raw arrays (H2D) and pack them."""
+        return GridPack.from_raw(RawGrid.upload(sd, device))
+
+    @staticmethod
+    def from_raw(raw: "RawGrid") -> "GridPack":
+        """Pack device-resident raw connectivity: coordinates + node-opposite-face tables."""
+        dev, d, nc, nf, nn = raw.device, raw.dim, raw.nc, raw.nf, raw.nn
         with torch.cuda.device(dev):
             s = _stream()
-            cf_idx = _to_dev(cf.indices, dev, _I32)
-            cf_sgn = _sign_i8(_to_dev(cf.data, dev))
-            fn_idx = _to_dev(fn.indices, dev, _I32)
-            nodes = _to_dev(np.asarray(sd.nodes, dtype=np.float64), dev)
             coords = torch.empty((nn, 4 if d == 3 else 2), dtype=torch.float64, device=dev)
-            check(lib.pgb_prep_coords(d, nn, nodes.data_ptr(), R.ctypes.data, coords.data_ptr(), s))
+            check(lib.pgb_prep_coords(d, nn, raw.nodes.data_ptr(), raw.R.ctypes.data, coords.data_ptr(), s))
             cell_nodes = torch.empty((nc, d + 1), dtype=_I32, device=dev)
             sign_bits = torch.empty((nc,), dtype=torch.uint8, device=dev)
             err = torch.zeros((1,), dtype=_I32, device=dev)
             check(
                 lib.pgb_pack_cells(
-                    d, nc, cf_idx.data_ptr(), cf_sgn.data_ptr(), fn_idx.data_ptr(),
+                    d, nc, raw.cf_idx.data_ptr(), raw.cf_sgn.data_ptr(), raw.fn_idx.data_ptr(),
                     cell_nodes.data_ptr(), sign_bits.data_ptr(), err.data_ptr(), s,
                 )
             )
             _lib.count(2)
-            if int(err.item()):
+            if raw.check and int(err.item()):
                 raise NotImplementedError("Grid is not simplicial; cannot compute opposite node.")
-        ne = nf if d == 2 else int(getattr(sd, "num_ridges", 0))
-        return GridPack(d, nc, nf, nn, ne, dev, R, coords, cf_idx, fn_idx, cell_nodes, sign_bits, _sd=sd)
+        return GridPack(d, nc, nf, nn, raw.ne, dev, raw.R, coords, raw.cf_idx, raw.fn_idx, cell_nodes,
+                        sign_bits, _raw=raw)
 
     # -- Nedelec0 tables ----------------------------------------------------------------
     def edges(self):
         """(cell_edges (nc, E) int32, edge_bits (nc,) int32-as-uint32)."""
         if self._edges is None:
-            sd, dev, d, nc = self._sd, self.device, self.dim, self.nc
+            raw, dev, d, nc = self._raw, self.device, self.dim, self.nc
+            raw.need_ridges()
             with torch.cuda.device(dev):
                 s = _stream()
                 bits = torch.empty((nc,), dtype=_I32, device=dev)
-                fr = sd.face_ridges
                 if d == 2:
-                    if fr.indices.size != 2 * self.nf:
-                        raise NotImplementedError("face_ridges must have 2 entries per face")
-                    fr_idx = _to_dev(fr.indices, dev, _I32)
-                    check(lib.pgb_pack_edges2d(nc, self.cf_idx.data_ptr(), fr_idx.data_ptr(),
+                    check(lib.pgb_pack_edges2d(nc, self.cf_idx.data_ptr(), raw.fr_idx.data_ptr(),
                                                self.cell_nodes.data_ptr(), bits.data_ptr(), s))
                     self._edges = (self.cf_idx.view(nc, 3), bits)
                 else:
-                    rp = sd.ridge_peaks
-                    if fr.indices.size != 3 * self.nf or rp.indices.size != 2 * self.ne:
-                        raise NotImplementedError("Grid is not simplicial")
-                    fr_idx = _to_dev(fr.indices, dev, _I32)
-                    fr_sgn = _sign_i8(_to_dev(fr.data, dev))
-                    rp_idx = _to_dev(rp.indices, dev, _I32)
                     ce = torch.empty((nc, 6), dtype=_I32, device=dev)
                     err = torch.zeros((1,), dtype=_I32, device=dev)
-                    check(lib.pgb_pack_edges3d(nc, self.cf_idx.data_ptr(), fr_idx.data_ptr(),
-                                               fr_sgn.data_ptr(), rp_idx.data_ptr(),
+                    check(lib.pgb_pack_edges3d(nc, self.cf_idx.data_ptr(), raw.fr_idx.data_ptr(),
+                                               raw.fr_sgn.data_ptr(), raw.rp_idx.data_ptr(),
                                                self.cell_nodes.data_ptr(), ce.data_ptr(),
                                                bits.data_ptr(), err.data_ptr(), s))
-                    if int(err.item()):
+                    if raw.check and int(err.item()):
                         raise ValueError("face_ridges / ridge_peaks are inconsistent with the cells")
                     self._edges = (ce, bits)
                 _lib.count(1)

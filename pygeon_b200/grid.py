@@ -92,6 +92,14 @@ class SimplexGrid:
     def num_cell_nodes(self) -> np.ndarray:
         return np.diff(self.cell_nodes().indptr)
 
+    def compute_connectivity(self) -> None:
+        """Ridges / peaks only (no metric quantities): what the assembly engine reads besides
+        ``nodes``, ``cell_faces`` and ``face_nodes``.  Cheap enough for 10^8-cell grids."""
+        self.rotation_matrix = np.eye(self.dim, AMBIENT_DIM)
+        self.tags.setdefault("domain_boundary_faces", np.bincount(self.cell_faces.indices, minlength=self.num_faces) == 1)
+        self._compute_ridges()
+        self.num_edges = self.num_faces if self.dim == 2 else self.num_ridges
+
     def compute_geometry(self) -> None:
         """Geometry + ridges/peaks + edge properties (``grid.py:39-64``)."""
         d = self.dim

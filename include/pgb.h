@@ -107,22 +107,29 @@ int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
  * (e.g. fem/hdiv.py:509, fem/hcurl.py:291, fem/h1.py:237, discretization.py:136).
  * COO entry i = cell*L*L + a*L + b has row cell_dofs[cell*L+a], col cell_dofs[cell*L+b].
  *
- * symbolic_sort: stable LSD radix sort of the packed (row,col) keys, payload = COO position.
- *   workspace: pgb_csr_workspace_bytes(n_coo, n_rows) bytes.
+ * Two symbolic algorithms produce the same arrays:
+ *   mode 0 (two level, default): (1) stable LSD radix sort of the nc*L incidences (cell, a) by
+ *     dof id (32-bit keys) = the transpose of the cell->dof table; (2) one sub-warp per row
+ *     gathers the row's candidates (col, src), sorts them with a register bitonic network and
+ *     removes duplicate columns; (3) a scan of the row counts and a compaction.  Needs every dof
+ *     to be shared by at most 512/L cells; otherwise returns 3 and the caller retries with mode 1.
+ *   mode 1 (full sort): stable LSD radix sort of all nc*L*L packed (row,col) keys (64-bit) with
+ *     the COO position as payload, then head-flag compaction.
+ * symbolic_sort: workspace of pgb_csr_workspace_bytes(nc, L, n_rows, mode) bytes.
  *   perm [n_coo] out: COO positions in sorted order.  nnz_host: number of distinct keys
  *   (the call synchronises the stream to return it).
  * symbolic_finish: indptr (int32 if idx64==0 else int64) [n_rows+1], indices [nnz],
  *   seg [nnz+1]: start of each entry's run in perm.
- * numeric: data[k] = sum over its run of vals[perm[.]], warp-shuffle segmented reduce in
- *   fixed order (bit-reproducible).
+ * numeric: data[k] = sum over its run of vals[perm[.]]: lane-sequential partial sums combined by
+ *   a warp-shuffle segmented scan, in a fixed order (bit-reproducible).
  */
-int64_t pgb_csr_workspace_bytes(int64_t n_coo, int64_t n_rows);
-int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell_dofs,
+int64_t pgb_csr_workspace_bytes(int64_t nc, int L, int64_t n_rows, int mode);
+int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell_dofs, int mode,
                           void* workspace, int64_t workspace_bytes, uint32_t* perm,
                           int64_t* nnz_host, void* stream);
-int pgb_csr_symbolic_finish(int64_t n_rows, int64_t n_coo, int64_t nnz, const void* workspace,
-                            void* indptr, int idx64, int32_t* indices, uint32_t* seg,
-                            void* stream);
+int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mode, int64_t nnz,
+                            const void* workspace, void* indptr, int idx64, int32_t* indices,
+                            uint32_t* seg, void* stream);
 int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t* seg, const double* vals,
                     double* data, void* stream);
 

@@ -21,14 +21,18 @@ constexpr unsigned FULL = 0xffffffffu;
 
 constexpr int SCAN_G = PGB_NPART;  // chunks of the two-level scans (<= 2048)
 
+// Key source of a radix pass.  KeyT = uint64_t: packed (row,col) of COO entry i (fallback path);
+// KeyT = uint32_t: the dof id of incidence i = cell*L + a (incidence transpose).  In the first
+// pass `keys` is null and the key is generated from cell_dofs on the fly.
+template <typename KeyT>
 struct KeySrc {
-  const uint64_t* keys;  // nullptr in the first pass: generate from cell_dofs
+  const KeyT* keys;
   const int32_t* dofs;
   uint32_t L, LL;
   int cb;  // column bits
 };
 
-__device__ __forceinline__ uint64_t load_key(const KeySrc& s, uint32_t i) {
+__device__ __forceinline__ uint64_t load_key(const KeySrc<uint64_t>& s, uint32_t i) {
   if (s.keys) return s.keys[i];
   uint32_t cell = i / s.LL;
   uint32_t r = i - cell * s.LL;
@@ -37,8 +41,14 @@ __device__ __forceinline__ uint64_t load_key(const KeySrc& s, uint32_t i) {
   return ((uint64_t)(uint32_t)__ldg(d + a) << s.cb) | (uint64_t)(uint32_t)__ldg(d + b);
 }
 
+__device__ __forceinline__ uint32_t load_key(const KeySrc<uint32_t>& s, uint32_t i) {
+  if (s.keys) return s.keys[i];
+  return (uint32_t)__ldg(s.dofs + i);
+}
+
 // ---- pass 1/3: per-tile digit histogram, written digit-major ---------------------------------
-__global__ void __launch_bounds__(SORT_BLOCK) k_radix_hist(KeySrc src, uint32_t n, int shift, uint32_t ntiles,
+template <typename KeyT>
+__global__ void __launch_bounds__(SORT_BLOCK) k_radix_hist(KeySrc<KeyT> src, uint32_t n, int shift, uint32_t ntiles,
                                                            uint32_t* __restrict__ hist) {
   __shared__ uint32_t h[RADIX];
   h[threadIdx.x] = 0;
@@ -147,22 +157,24 @@ __global__ void __launch_bounds__(256) k_scan_apply(uint32_t* __restrict__ data,
 }
 
 // ---- pass 3/3: stable scatter ---------------------------------------------------------------
+template <typename KeyT>
 struct ScatterSmem {
   uint32_t whist[SORT_WARPS][RADIX];
   uint32_t dstart[RADIX];
   uint32_t goff[RADIX];
   uint32_t ws[8];
   uint32_t svals[SORT_TILE];
-  uint64_t skeys[SORT_TILE];
+  KeyT skeys[SORT_TILE];
 };
 
-__global__ void __launch_bounds__(SORT_BLOCK) k_radix_scatter(KeySrc src, const uint32_t* __restrict__ vals_in, uint32_t n,
+template <typename KeyT>
+__global__ void __launch_bounds__(SORT_BLOCK) k_radix_scatter(KeySrc<KeyT> src, const uint32_t* __restrict__ vals_in, uint32_t n,
                                                               int shift, uint32_t ntiles,
                                                               const uint32_t* __restrict__ hist_scanned,
-                                                              uint64_t* __restrict__ keys_out,
+                                                              KeyT* __restrict__ keys_out,
                                                               uint32_t* __restrict__ vals_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(smem_raw);
+  ScatterSmem<KeyT>& sm = *reinterpret_cast<ScatterSmem<KeyT>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t tile0 = blockIdx.x * (uint32_t)SORT_TILE;
   const uint32_t count = (n - tile0 < (uint32_t)SORT_TILE) ? (n - tile0) : (uint32_t)SORT_TILE;
@@ -172,13 +184,13 @@ __global__ void __launch_bounds__(SORT_BLOCK) k_radix_scatter(KeySrc src, const 
   sm.goff[tid] = hist_scanned[(uint64_t)tid * ntiles + blockIdx.x];
   __syncthreads();
 
-  uint64_t key[SORT_ITEMS];
+  KeyT key[SORT_ITEMS];
   uint16_t rank[SORT_ITEMS];
   const uint32_t wbase = tile0 + w * (32 * SORT_ITEMS);
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; ++i) {
     uint32_t idx = wbase + i * 32 + lane;
-    key[i] = (idx < n) ? load_key(src, idx) : ~0ull;
+    key[i] = (idx < n) ? load_key(src, idx) : (KeyT)~(KeyT)0;
   }
   const uint32_t lt = (1u << lane) - 1;
 #pragma unroll
@@ -219,7 +231,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) k_radix_scatter(KeySrc src, const 
   }
   __syncthreads();
   for (uint32_t j = tid; j < count; j += SORT_BLOCK) {
-    uint64_t k = sm.skeys[j];
+    KeyT k = sm.skeys[j];
     uint32_t d = (uint32_t)(k >> shift) & (RADIX - 1);
     uint32_t g = sm.goff[d] + (j - sm.dstart[d]);
     keys_out[g] = k;
@@ -296,48 +308,265 @@ __global__ void k_fill_indptr_empty(int64_t n_rows, IP* indptr) {
   if (i <= n_rows) indptr[i] = 0;
 }
 
-// ---- numeric: warp-shuffle segmented reduce --------------------------------------------------
+// ---- two-level symbolic: incidence transpose + per-row register sort ---------------------------
+// After the incidences (cell, a) have been sorted by dof id, row r of the matrix owns the
+// incidences [row_start[r], row_start[r+1]); each contributes the L candidates
+// (col = dofs[cell][b], src = inc*L + b).  In the globally sorted COO order row r therefore
+// occupies exactly the positions [L*row_start[r], L*row_start[r+1]), so perm can be written in
+// place once the row's candidates are sorted by (col, src).
+
+__global__ void __launch_bounds__(256) k_row_starts(const uint32_t* __restrict__ keys, uint32_t n, int64_t n_rows,
+                                                    uint32_t* __restrict__ row_start) {
+  uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= n) return;
+  int64_t k = keys[i];
+  int64_t prev = (i == 0) ? -1 : (int64_t)keys[i - 1];
+  for (int64_t r = prev + 1; r <= k; ++r) row_start[r] = i;
+  if (i == n - 1)
+    for (int64_t r = k + 1; r <= n_rows; ++r) row_start[r] = n;
+}
+
+// max number of incidences of one dof (integer max: order independent)
+__global__ void __launch_bounds__(256) k_max_row(int64_t n_rows, const uint32_t* __restrict__ row_start,
+                                                 uint32_t* __restrict__ max_count) {
+  __shared__ uint32_t ws[8];
+  uint32_t mx = 0;
+  for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * 256) {
+    uint32_t c = row_start[r + 1] - row_start[r];
+    mx = c > mx ? c : mx;
+  }
+  mx = __reduce_max_sync(FULL, mx);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) ws[w] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; ++q) mx = ws[q] > mx ? ws[q] : mx;
+    atomicMax(max_count, mx);
+  }
+}
+
+template <int G, int ITEMS, int L>
+__global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t* __restrict__ row_start,
+                                                 const uint32_t* __restrict__ inc_sorted,
+                                                 const int32_t* __restrict__ dofs, uint32_t* __restrict__ perm,
+                                                 int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ useg_tmp,
+                                                 uint32_t* __restrict__ row_nnz) {
+  constexpr int N = G * ITEMS;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;  // lane within the group
+  const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
+  const bool live = r < n_rows;
+  uint32_t rs = 0, re = 0;
+  if (live) {
+    rs = row_start[r];
+    re = row_start[r + 1];
+  }
+  const uint32_t ncand = (re - rs) * L;
+  const uint32_t base = rs * L;
+
+  // gather candidates, blocked layout: element e = gl*ITEMS + i
+  uint64_t key[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    uint32_t e = gl * ITEMS + i;
+    key[i] = ~0ull;
+    if (e < ncand) {
+      uint32_t q = e / L, b = e - q * L;
+      uint32_t inc = inc_sorted[rs + q];
+      uint32_t cell = inc / L;
+      uint32_t col = (uint32_t)__ldg(dofs + (int64_t)cell * L + b);
+      key[i] = ((uint64_t)col << 32) | (uint64_t)(inc * L + b);
+    }
+  }
+  // bitonic sort, ascending, N elements spread over G lanes
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= ITEMS) {
+        const int lj = j / ITEMS;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+          uint64_t other = __shfl_xor_sync(FULL, key[i], lj);
+          int e = gl * ITEMS + i;
+          bool lower = (e & j) == 0;
+          bool asc = (e & k) == 0;
+          uint64_t mn = key[i] < other ? key[i] : other;
+          uint64_t mx = key[i] < other ? other : key[i];
+          key[i] = (lower == asc) ? mn : mx;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+          if ((i & j) == 0) {
+            int e = gl * ITEMS + i;
+            bool asc = (e & k) == 0;
+            uint64_t a = key[i], b = key[i | j];
+            bool sw = asc ? (a > b) : (a < b);
+            key[i] = sw ? b : a;
+            key[i | j] = sw ? a : b;
+          }
+        }
+      }
+    }
+  }
+  // unique columns: head(e) = e == 0 || col(e) != col(e-1)
+  uint32_t prev_last = (uint32_t)(__shfl_up_sync(FULL, key[ITEMS - 1], 1) >> 32);
+  uint32_t heads = 0;  // bit i set: element i of this lane starts a run
+  int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    uint32_t e = gl * ITEMS + i;
+    uint32_t col = (uint32_t)(key[i] >> 32);
+    uint32_t pc = (i == 0) ? prev_last : (uint32_t)(key[i - 1] >> 32);
+    bool h = (e < ncand) && (e == 0 || col != pc);
+    heads |= (h ? 1u : 0u) << i;
+    cnt += h;
+  }
+  // exclusive scan of cnt over the G lanes of the group
+  int inc_ = cnt;
+#pragma unroll
+  for (int d = 1; d < G; d <<= 1) {
+    int t = __shfl_up_sync(FULL, inc_, d);
+    if (gl >= d) inc_ += t;
+  }
+  int total = __shfl_sync(FULL, inc_, (lane - gl) + G - 1);
+  int rank = inc_ - cnt;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    uint32_t e = gl * ITEMS + i;
+    if (e < ncand) {
+      perm[base + e] = (uint32_t)key[i];
+      if ((heads >> i) & 1u) {
+        ucol_tmp[base + rank] = (int32_t)(key[i] >> 32);
+        useg_tmp[base + rank] = base + e;
+        ++rank;
+      }
+    }
+  }
+  if (live && gl == 0) row_nnz[r] = (uint32_t)total;
+}
+
+// row_nnz has been exclusively scanned in place (row_off); copy each row's unique columns / run
+// starts from their scratch position to the final CSR arrays.
+template <typename IP>
+__global__ void __launch_bounds__(256) k_compact(int64_t n_rows, int L, const uint32_t* __restrict__ row_start,
+                                                 const uint32_t* __restrict__ row_off,
+                                                 const int32_t* __restrict__ ucol_tmp,
+                                                 const uint32_t* __restrict__ useg_tmp, IP* __restrict__ indptr,
+                                                 int32_t* __restrict__ indices, uint32_t* __restrict__ seg,
+                                                 uint32_t n_coo) {
+  // 8 lanes per row
+  const int gl = threadIdx.x & 7;
+  const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
+  if (r > n_rows) return;
+  uint32_t o0 = row_off[r];
+  if (gl == 0) indptr[r] = (IP)o0;
+  if (r == n_rows) {
+    if (gl == 0) seg[o0] = n_coo;
+    return;
+  }
+  uint32_t cnt = row_off[r + 1] - o0;
+  uint32_t base = row_start[r] * (uint32_t)L;
+  for (uint32_t k = gl; k < cnt; k += 8) {
+    indices[o0 + k] = ucol_tmp[base + k];
+    seg[o0 + k] = useg_tmp[base + k];
+  }
+}
+
+// ---- numeric: lane-sequential partial sums + warp-shuffle segmented scan ------------------------
+// A warp owns NUM_OPW consecutive output entries, i.e. the contiguous sorted positions
+// [seg[k0], seg[k0+NUM_OPW)).  The positions are split evenly over the 32 lanes; every lane sums
+// its slice sequentially (runs that start and end inside the slice are stored directly), and the
+// pieces of runs that cross lane boundaries are combined with one segmented inclusive scan over
+// the lanes (5 shuffle steps per warp tile).  Fixed order => bit-reproducible, no atomics.
 constexpr int NUM_BLOCK = 256;
+constexpr int NUM_OPW = 128;  // outputs per warp
 
 __global__ void __launch_bounds__(NUM_BLOCK) k_numeric(int64_t nnz, const uint32_t* __restrict__ perm,
                                                        const uint32_t* __restrict__ seg,
                                                        const double* __restrict__ vals, double* __restrict__ data) {
-  __shared__ double acc[NUM_BLOCK / 32][32];
+  __shared__ uint32_t sseg[NUM_BLOCK / 32][NUM_OPW + 1];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t k0 = ((int64_t)blockIdx.x * (NUM_BLOCK / 32) + w) * 32;
+  const int64_t k0 = ((int64_t)blockIdx.x * (NUM_BLOCK / 32) + w) * NUM_OPW;
   if (k0 >= nnz) return;
-  const int64_t k = k0 + lane;
-  const bool own = k < nnz;
-  const uint32_t s_l = seg[own ? k : nnz];
-  const uint32_t S = __shfl_sync(FULL, s_l, 0);
-  const int64_t kend = (k0 + 32 < nnz) ? k0 + 32 : nnz;
-  const uint32_t E = seg[kend];
-  acc[w][lane] = 0.0;
+  const int nout = (int)((nnz - k0 < NUM_OPW) ? (nnz - k0) : NUM_OPW);
+  for (int i = lane; i <= nout; i += 32) sseg[w][i] = seg[k0 + i];
   __syncwarp();
-  int heads_before = 0;
-  for (uint32_t chunk = S; chunk < E; chunk += 32) {
-    uint32_t p = chunk + lane;
-    bool valid = p < E;
-    double v = valid ? vals[perm[p]] : 0.0;
-    uint32_t rel = s_l - chunk;  // wraps to a huge value when s_l < chunk
-    uint32_t mybit = (own && rel < 32u) ? (1u << rel) : 0u;
-    uint32_t heads = __reduce_or_sync(FULL, mybit);
-    // segmented inclusive scan: add the value d lanes below unless a head lies in (lane-d, lane]
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      double t = __shfl_up_sync(FULL, v, d);
-      uint32_t upto = (lane == 31) ? FULL : ((2u << lane) - 1u);
-      uint32_t below = (lane >= d) ? ((1u << (lane - d + 1)) - 1u) : FULL;
-      if (lane >= d && !(heads & upto & ~below)) v += t;
-    }
-    uint32_t upto = (lane == 31) ? FULL : ((2u << lane) - 1u);
-    bool tail = valid && (lane == 31 || ((heads >> (lane + 1)) & 1u) || p == E - 1);
-    int out_lane = heads_before + __popc(heads & upto) - 1;
-    if (tail) acc[w][out_lane] += v;
-    heads_before += __popc(heads);
-    __syncwarp();
+  const uint32_t S = sseg[w][0], E = sseg[w][nout];
+  const uint32_t len = E - S;
+  const uint32_t c = (len + 31) / 32;
+  uint32_t p = S + lane * c;
+  uint32_t pe = (p + c < E) ? p + c : E;
+  if (p > E) p = E;
+  // o = index (relative to k0) of the run containing position p: last o with sseg[o] <= p
+  int lo = 0, hi = nout;  // invariant: sseg[lo] <= p < sseg[hi] (when p < E)
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (sseg[w][mid] <= p) lo = mid; else hi = mid;
   }
-  if (own) data[k] = acc[w][lane];
+  int o = lo;
+  const bool nonempty = p < pe;
+  const bool starts_at_head = nonempty && (sseg[w][o] == p);
+  double acc = 0.0;      // running sum of the current run piece
+  double first = 0.0;    // piece before the first head in the slice (belongs to an earlier lane's run)
+  bool seen_head = starts_at_head;
+  int o_first = o;       // run the `first` piece belongs to
+  uint32_t next_head = nonempty ? sseg[w][o + 1] : 0;
+  constexpr int U = 8;  // gathers in flight per lane
+  for (uint32_t q0 = p; q0 < pe; q0 += U) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = (q0 + u < pe) ? vals[perm[q0 + u]] : 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t q = q0 + u;
+      if (q < pe) {
+        if (q == next_head) {  // a new run starts at q: close the previous piece
+          if (seen_head) data[k0 + o] = acc;  // run began inside this slice: complete
+          else first = acc;
+          seen_head = true;
+          acc = 0.0;
+          ++o;
+          next_head = sseg[w][o + 1];
+        }
+        acc += v[u];
+      }
+    }
+  }
+  // lane summary: `first` (if !starts_at_head) continues run o_first; `acc` is the open piece of run o
+  // (== first piece when no head was seen).  has_head: a run starts somewhere in this slice.
+  const bool has_head = seen_head;
+  if (!has_head) first = acc;  // whole slice is one piece of an earlier run
+  double open = has_head ? acc : 0.0;
+  // carry[i] = sum of open pieces of lanes j < i back to (and including) the nearest lane with a head
+  // -> exclusive segmented scan of `open`/`first` over lanes.
+  // value v_i: contribution lane i passes on = has_head ? open : first(+carry).
+  double v = has_head ? open : first;
+  bool f = has_head;  // reset flag
+  // inclusive segmented scan (flag = run restarts in this lane)
+  double incl = v;
+  bool fl = f;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double t = __shfl_up_sync(FULL, incl, d);
+    bool tf = __shfl_up_sync(FULL, fl ? 1 : 0, d) != 0;
+    if (lane >= d && !fl) {
+      incl += t;
+      fl = tf;
+    }
+  }
+  double carry_in = __shfl_up_sync(FULL, incl, 1);
+  if (lane == 0) carry_in = 0.0;
+  // the run continued into this lane ends here if this lane has a head (then `first` closes it) ...
+  const bool empty_next = !__shfl_down_sync(FULL, nonempty ? 1 : 0, 1) || lane == 31;
+  const bool next_starts_head = __shfl_down_sync(FULL, starts_at_head ? 1 : 0, 1) != 0;
+  if (nonempty && !starts_at_head && has_head) data[k0 + o_first] = carry_in + first;
+  // ... and the open piece of this lane is complete if the next lane starts with a head / is empty
+  if (nonempty && (empty_next || next_starts_head)) {
+    double tot = has_head ? open : carry_in + first;
+    data[k0 + o] = tot;
+  }
 }
 
 int bits_for(int64_t n) {
@@ -346,26 +575,7 @@ int bits_for(int64_t n) {
   return b;
 }
 
-struct WsLayout {
-  int64_t keys_a, keys_b, perm_b, hist, parts, meta, total;
-};
-
-WsLayout ws_layout(int64_t n_coo) {
-  auto al = [](int64_t x) { return (x + 255) / 256 * 256; };
-  int64_t ntiles = pgb_cdiv(n_coo > 0 ? n_coo : 1, SORT_TILE);
-  WsLayout l;
-  int64_t o = 0;
-  l.keys_a = o; o += al(n_coo * 8);
-  l.keys_b = o; o += al(n_coo * 8);
-  l.perm_b = o; o += al(n_coo * 4);
-  l.hist = o;   o += al(ntiles * RADIX * 4);
-  l.parts = o;  o += al(2048 * 4);
-  l.meta = o;   o += 256;  // [0]=which key buffer holds the sorted keys, [1]=cb, [2]=nnz (uint32)
-  l.total = o;
-  return l;
-}
-
-int scan_u32(uint32_t* data, uint64_t n, uint32_t* parts, cudaStream_t s) {
+int scan_u32(uint32_t* data, uint64_t n, uint32_t* parts, uint32_t* total_out, cudaStream_t s) {
   uint64_t g = pgb_cdiv((int64_t)n, 1024);
   if (g > SCAN_G) g = SCAN_G;
   if (g < 1) g = 1;
@@ -373,78 +583,183 @@ int scan_u32(uint32_t* data, uint64_t n, uint32_t* parts, cudaStream_t s) {
   chunk = pgb_cdiv((int64_t)chunk, 1024) * 1024;
   g = pgb_cdiv((int64_t)n, (int64_t)chunk);
   k_scan_reduce<<<(unsigned)g, 256, 0, s>>>(data, n, chunk, parts);
-  k_scan_parts<<<1, 256, 0, s>>>(parts, (int)g, nullptr);
+  k_scan_parts<<<1, 256, 0, s>>>(parts, (int)g, total_out);
   k_scan_apply<<<(unsigned)g, 256, 0, s>>>(data, n, chunk, parts);
   PGB_LAUNCH_CHECK();
   return 0;
 }
 
-}  // namespace
-
-extern "C" int64_t pgb_csr_workspace_bytes(int64_t n_coo, int64_t n_rows) {
-  (void)n_rows;
-  return ws_layout(n_coo).total;
-}
-
-extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell_dofs,
-                                     void* workspace, int64_t workspace_bytes, uint32_t* perm,
-                                     int64_t* nnz_host, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  const int64_t n_coo = nc * L * L;
-  PGB_REQUIRE(n_coo < ((int64_t)1 << 32) - SORT_TILE, "pgb_csr_symbolic_sort: n_coo must be < 2^32");
-  PGB_REQUIRE(n_rows > 0 && n_rows < ((int64_t)1 << 31), "pgb_csr_symbolic_sort: n_rows out of range");
-  WsLayout l = ws_layout(n_coo);
-  PGB_REQUIRE(workspace_bytes >= l.total, "pgb_csr_symbolic_sort: workspace too small");
-  if (n_coo == 0) {
-    *nnz_host = 0;
-    return 0;
-  }
-  char* ws = (char*)workspace;
-  uint64_t* kbuf[2] = {(uint64_t*)(ws + l.keys_a), (uint64_t*)(ws + l.keys_b)};
-  uint32_t* pbuf[2] = {perm, (uint32_t*)(ws + l.perm_b)};
-  uint32_t* hist = (uint32_t*)(ws + l.hist);
-  uint32_t* parts = (uint32_t*)(ws + l.parts);
-  uint32_t* meta = (uint32_t*)(ws + l.meta);
-
-  const int cb = bits_for(n_rows);
-  const int total_bits = 2 * cb;
-  const int passes = (total_bits + RADIX_BITS - 1) / RADIX_BITS;
-  const uint32_t n = (uint32_t)n_coo;
-  const uint32_t ntiles = (uint32_t)pgb_cdiv(n_coo, SORT_TILE);
-
+// Stable LSD radix sort of n (key, payload) pairs.  Pass p reads buffer (p-1)&1 ... and the final
+// pass writes kbuf[0] / pbuf[0].  Keys of the first pass come from `src` (generated on the fly),
+// payloads of the first pass are the positions 0..n-1.
+template <typename KeyT>
+int radix_sort(KeySrc<KeyT> src, uint32_t n, int total_bits, KeyT* kbuf[2], uint32_t* pbuf[2], uint32_t* hist,
+               uint32_t* parts, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    PGB_CHECK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(ScatterSmem)));
+    PGB_CHECK(cudaFuncSetAttribute(k_radix_scatter<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(ScatterSmem<KeyT>)));
     attr_set = true;
   }
-  // ping-pong so that the final payload lands in `perm` (pbuf[0]): pass p writes pbuf[dst].
+  const int passes = (total_bits + RADIX_BITS - 1) / RADIX_BITS;
+  const uint32_t ntiles = (uint32_t)pgb_cdiv((int64_t)n, SORT_TILE);
   int dst = (passes % 2 == 1) ? 0 : 1;
-  KeySrc src{nullptr, cell_dofs, (uint32_t)L, (uint32_t)(L * L), cb};
   const uint32_t* pin = nullptr;
   for (int p = 0; p < passes; ++p) {
     int shift = p * RADIX_BITS;
-    k_radix_hist<<<ntiles, SORT_BLOCK, 0, s>>>(src, n, shift, ntiles, hist);
+    k_radix_hist<KeyT><<<ntiles, SORT_BLOCK, 0, s>>>(src, n, shift, ntiles, hist);
     PGB_LAUNCH_CHECK();
-    if (scan_u32(hist, (uint64_t)ntiles * RADIX, parts, s)) return 1;
-    k_radix_scatter<<<ntiles, SORT_BLOCK, sizeof(ScatterSmem), s>>>(src, pin, n, shift, ntiles, hist,
-                                                                     kbuf[dst], pbuf[dst]);
+    if (scan_u32(hist, (uint64_t)ntiles * RADIX, parts, nullptr, s)) return 1;
+    k_radix_scatter<KeyT><<<ntiles, SORT_BLOCK, sizeof(ScatterSmem<KeyT>), s>>>(src, pin, n, shift, ntiles, hist,
+                                                                                 kbuf[dst], pbuf[dst]);
     PGB_LAUNCH_CHECK();
     src.keys = kbuf[dst];
     pin = pbuf[dst];
     dst ^= 1;
   }
-  const int sorted_buf = dst ^ 1;  // buffer written by the last pass
-  // count distinct keys
-  uint64_t g = pgb_cdiv(n_coo, 1024);
+  return 0;
+}
+
+constexpr int MODE_TWO_LEVEL = 0, MODE_FULL_SORT = 1;
+constexpr uint32_t MAX_ROW_CAND = 512;  // capacity of the largest k_rowsort instance
+
+struct WsLayout {
+  // full sort
+  int64_t keys_a, keys_b, perm_b;
+  // two level
+  int64_t ikeys_a, ikeys_b, ipay_a, ipay_b, row_start, row_nnz, ucol, useg;
+  // shared
+  int64_t hist, parts, meta, total;
+};
+
+WsLayout ws_layout(int64_t n_coo, int64_t n_inc, int64_t n_rows, int mode) {
+  auto al = [](int64_t x) { return (x + 255) / 256 * 256; };
+  WsLayout l = {};
+  int64_t o = 0;
+  int64_t nsort = (mode == MODE_FULL_SORT) ? n_coo : n_inc;
+  int64_t ntiles = pgb_cdiv(nsort > 0 ? nsort : 1, SORT_TILE);
+  l.meta = o;  o += 256;  // uint32: [0] mode, [1] cb, [2] nnz, [3] max incidences per row
+  l.parts = o; o += al(2048 * 4);
+  l.hist = o;  o += al(ntiles * RADIX * 4);
+  if (mode == MODE_FULL_SORT) {
+    l.keys_a = o; o += al(n_coo * 8);
+    l.keys_b = o; o += al(n_coo * 8);
+    l.perm_b = o; o += al(n_coo * 4);
+  } else {
+    l.ikeys_a = o;   o += al(n_inc * 4);
+    l.ikeys_b = o;   o += al(n_inc * 4);
+    l.ipay_a = o;    o += al(n_inc * 4);
+    l.ipay_b = o;    o += al(n_inc * 4);
+    l.row_start = o; o += al((n_rows + 2) * 4);
+    l.row_nnz = o;   o += al((n_rows + 2) * 4);
+    l.ucol = o;      o += al(n_coo * 4);
+    l.useg = o;      o += al(n_coo * 4);
+  }
+  l.total = o;
+  return l;
+}
+
+struct ChunkGrid {
+  uint64_t g, chunk;
+};
+ChunkGrid chunk_grid(int64_t n) {
+  uint64_t g = pgb_cdiv(n, 1024);
   if (g > SCAN_G) g = SCAN_G;
-  uint64_t chunk = pgb_cdiv(pgb_cdiv(n_coo, (int64_t)g), 1024) * 1024;
-  g = pgb_cdiv(n_coo, (int64_t)chunk);
-  k_count_heads<<<(unsigned)g, 256, 0, s>>>(kbuf[sorted_buf], (uint64_t)n_coo, chunk, parts);
-  k_scan_parts<<<1, 256, 0, s>>>(parts, (int)g, meta + 2);
+  if (g < 1) g = 1;
+  uint64_t chunk = pgb_cdiv(pgb_cdiv(n, (int64_t)g), 1024) * 1024;
+  g = pgb_cdiv(n, (int64_t)chunk);
+  return {g, chunk};
+}
+
+template <int G, int ITEMS>
+int launch_rowsort_l(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
+                     uint32_t* perm, int32_t* ucol, uint32_t* useg, uint32_t* row_nnz, cudaStream_t s) {
+  unsigned grid = pgb_grid(n_rows * G, 256);
+  switch (L) {
+    case 3: k_rowsort<G, ITEMS, 3><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
+    case 4: k_rowsort<G, ITEMS, 4><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
+    case 6: k_rowsort<G, ITEMS, 6><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
+    case 12: k_rowsort<G, ITEMS, 12><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
+    default: pgb_set_error("k_rowsort: unsupported local size %d", L); return 2;
+  }
   PGB_LAUNCH_CHECK();
-  uint32_t m[2] = {(uint32_t)sorted_buf, (uint32_t)cb};
+  return 0;
+}
+
+int launch_rowsort(uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc,
+                   const int32_t* dofs, uint32_t* perm, int32_t* ucol, uint32_t* useg, uint32_t* row_nnz,
+                   cudaStream_t s) {
+#define PGB_RS(G, I) return launch_rowsort_l<G, I>(L, n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz, s)
+  if (max_cand <= 8) PGB_RS(4, 2);
+  if (max_cand <= 16) PGB_RS(8, 2);
+  if (max_cand <= 32) PGB_RS(8, 4);
+  if (max_cand <= 64) PGB_RS(16, 4);
+  if (max_cand <= 128) PGB_RS(32, 4);
+  if (max_cand <= 256) PGB_RS(32, 8);
+  PGB_RS(32, 16);
+#undef PGB_RS
+}
+
+}  // namespace
+
+extern "C" int64_t pgb_csr_workspace_bytes(int64_t nc, int L, int64_t n_rows, int mode) {
+  return ws_layout(nc * L * L, nc * L, n_rows, mode).total;
+}
+
+extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell_dofs, int mode,
+                                     void* workspace, int64_t workspace_bytes, uint32_t* perm,
+                                     int64_t* nnz_host, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n_coo = nc * L * L, n_inc = nc * L;
+  PGB_REQUIRE(mode == MODE_TWO_LEVEL || mode == MODE_FULL_SORT, "pgb_csr_symbolic_sort: bad mode");
+  PGB_REQUIRE(n_coo < ((int64_t)1 << 32) - SORT_TILE, "pgb_csr_symbolic_sort: n_coo must be < 2^32");
+  PGB_REQUIRE(n_rows > 0 && n_rows < ((int64_t)1 << 31), "pgb_csr_symbolic_sort: n_rows out of range");
+  WsLayout l = ws_layout(n_coo, n_inc, n_rows, mode);
+  PGB_REQUIRE(workspace_bytes >= l.total, "pgb_csr_symbolic_sort: workspace too small");
+  *nnz_host = 0;
+  char* ws = (char*)workspace;
+  uint32_t* meta = (uint32_t*)(ws + l.meta);
+  uint32_t* parts = (uint32_t*)(ws + l.parts);
+  uint32_t* hist = (uint32_t*)(ws + l.hist);
+  const int cb = bits_for(n_rows);
+  uint32_t m[4] = {(uint32_t)mode, (uint32_t)cb, 0u, 0u};
   PGB_CHECK(cudaMemcpyAsync(meta, m, sizeof(m), cudaMemcpyHostToDevice, s));
+  if (n_coo == 0) return 0;
+
+  if (mode == MODE_FULL_SORT) {
+    uint64_t* kbuf[2] = {(uint64_t*)(ws + l.keys_a), (uint64_t*)(ws + l.keys_b)};
+    uint32_t* pbuf[2] = {perm, (uint32_t*)(ws + l.perm_b)};
+    KeySrc<uint64_t> src{nullptr, cell_dofs, (uint32_t)L, (uint32_t)(L * L), cb};
+    if (radix_sort<uint64_t>(src, (uint32_t)n_coo, 2 * cb, kbuf, pbuf, hist, parts, s)) return 1;
+    ChunkGrid cg = chunk_grid(n_coo);
+    k_count_heads<<<(unsigned)cg.g, 256, 0, s>>>(kbuf[0], (uint64_t)n_coo, cg.chunk, parts);
+    k_scan_parts<<<1, 256, 0, s>>>(parts, (int)cg.g, meta + 2);
+    PGB_LAUNCH_CHECK();
+  } else {
+    uint32_t* kbuf[2] = {(uint32_t*)(ws + l.ikeys_a), (uint32_t*)(ws + l.ikeys_b)};
+    uint32_t* pbuf[2] = {(uint32_t*)(ws + l.ipay_a), (uint32_t*)(ws + l.ipay_b)};
+    uint32_t* row_start = (uint32_t*)(ws + l.row_start);
+    uint32_t* row_nnz = (uint32_t*)(ws + l.row_nnz);
+    KeySrc<uint32_t> src{nullptr, cell_dofs, (uint32_t)L, (uint32_t)(L * L), cb};
+    if (radix_sort<uint32_t>(src, (uint32_t)n_inc, cb, kbuf, pbuf, hist, parts, s)) return 1;
+    k_row_starts<<<pgb_grid(n_inc, 256), 256, 0, s>>>(kbuf[0], (uint32_t)n_inc, n_rows, row_start);
+    k_max_row<<<(unsigned)(n_rows < 256 * 1184 ? pgb_grid(n_rows, 256) : 1184), 256, 0, s>>>(n_rows, row_start, meta + 3);
+    PGB_LAUNCH_CHECK();
+    uint32_t max_inc = 0;
+    PGB_CHECK(cudaMemcpyAsync(&max_inc, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PGB_CHECK(cudaStreamSynchronize(s));
+    if (max_inc * (uint32_t)L > MAX_ROW_CAND) {
+      pgb_set_error("pgb_csr_symbolic_sort: a dof is shared by %u cells (> %u candidates per row); "
+                    "use mode 1 (full sort)", max_inc, MAX_ROW_CAND);
+      return 3;
+    }
+    PGB_CHECK(cudaMemsetAsync(row_nnz + n_rows, 0, 2 * sizeof(uint32_t), s));
+    if (launch_rowsort(max_inc * (uint32_t)L, L, n_rows, row_start, pbuf[0], cell_dofs, perm,
+                       (int32_t*)(ws + l.ucol), (uint32_t*)(ws + l.useg), row_nnz, s))
+      return 1;
+    if (scan_u32(row_nnz, (uint64_t)n_rows + 1, parts, nullptr, s)) return 1;
+    PGB_CHECK(cudaMemcpyAsync(meta + 2, row_nnz + n_rows, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  }
   uint32_t nnz32 = 0;
   PGB_CHECK(cudaMemcpyAsync(&nnz32, meta + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   PGB_CHECK(cudaStreamSynchronize(s));
@@ -452,34 +767,43 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
   return 0;
 }
 
-extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t n_coo, int64_t nnz,
-                                       const void* workspace, void* indptr, int idx64,
-                                       int32_t* indices, uint32_t* seg, void* stream) {
+extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mode, int64_t nnz,
+                                       const void* workspace, void* indptr, int idx64, int32_t* indices,
+                                       uint32_t* seg, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n_coo = nc * L * L, n_inc = nc * L;
   if (n_coo == 0) {
     if (idx64) k_fill_indptr_empty<int64_t><<<pgb_grid(n_rows + 1, 256), 256, 0, s>>>(n_rows, (int64_t*)indptr);
     else k_fill_indptr_empty<int32_t><<<pgb_grid(n_rows + 1, 256), 256, 0, s>>>(n_rows, (int32_t*)indptr);
     PGB_LAUNCH_CHECK();
     return 0;
   }
-  WsLayout l = ws_layout(n_coo);
+  WsLayout l = ws_layout(n_coo, n_inc, n_rows, mode);
   const char* ws = (const char*)workspace;
-  uint32_t m[2];
-  PGB_CHECK(cudaMemcpyAsync(m, ws + l.meta, sizeof(m), cudaMemcpyDeviceToHost, s));
-  PGB_CHECK(cudaStreamSynchronize(s));
-  const uint64_t* keys = (const uint64_t*)(ws + (m[0] == 0 ? l.keys_a : l.keys_b));
-  const uint32_t* parts = (const uint32_t*)(ws + l.parts);
-  const int cb = (int)m[1];
-  uint64_t g = pgb_cdiv(n_coo, 1024);
-  if (g > SCAN_G) g = SCAN_G;
-  uint64_t chunk = pgb_cdiv(pgb_cdiv(n_coo, (int64_t)g), 1024) * 1024;
-  g = pgb_cdiv(n_coo, (int64_t)chunk);
-  if (idx64)
-    k_emit_unique<int64_t><<<(unsigned)g, 256, 0, s>>>(keys, (uint64_t)n_coo, chunk, parts, cb, n_rows,
-                                                       (uint32_t)nnz, (int64_t*)indptr, indices, seg);
-  else
-    k_emit_unique<int32_t><<<(unsigned)g, 256, 0, s>>>(keys, (uint64_t)n_coo, chunk, parts, cb, n_rows,
-                                                       (uint32_t)nnz, (int32_t*)indptr, indices, seg);
+  const int cb = bits_for(n_rows);
+  if (mode == MODE_FULL_SORT) {
+    const uint64_t* keys = (const uint64_t*)(ws + l.keys_a);
+    const uint32_t* parts = (const uint32_t*)(ws + l.parts);
+    ChunkGrid cg = chunk_grid(n_coo);
+    if (idx64)
+      k_emit_unique<int64_t><<<(unsigned)cg.g, 256, 0, s>>>(keys, (uint64_t)n_coo, cg.chunk, parts, cb, n_rows,
+                                                            (uint32_t)nnz, (int64_t*)indptr, indices, seg);
+    else
+      k_emit_unique<int32_t><<<(unsigned)cg.g, 256, 0, s>>>(keys, (uint64_t)n_coo, cg.chunk, parts, cb, n_rows,
+                                                            (uint32_t)nnz, (int32_t*)indptr, indices, seg);
+  } else {
+    const uint32_t* row_start = (const uint32_t*)(ws + l.row_start);
+    const uint32_t* row_off = (const uint32_t*)(ws + l.row_nnz);
+    const int32_t* ucol = (const int32_t*)(ws + l.ucol);
+    const uint32_t* useg = (const uint32_t*)(ws + l.useg);
+    unsigned grid = pgb_grid((n_rows + 1) * 8, 256);
+    if (idx64)
+      k_compact<int64_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, useg, (int64_t*)indptr, indices,
+                                              seg, (uint32_t)n_coo);
+    else
+      k_compact<int32_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, useg, (int32_t*)indptr, indices,
+                                              seg, (uint32_t)n_coo);
+  }
   PGB_LAUNCH_CHECK();
   return 0;
 }
@@ -487,7 +811,7 @@ extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t n_coo, int64_t nn
 extern "C" int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t* seg,
                                const double* vals, double* data, void* stream) {
   if (nnz == 0) return 0;
-  int64_t warps = pgb_cdiv(nnz, 32);
+  int64_t warps = pgb_cdiv(nnz, NUM_OPW);
   unsigned grid = (unsigned)pgb_cdiv(warps, NUM_BLOCK / 32);
   k_numeric<<<grid, NUM_BLOCK, 0, (cudaStream_t)stream>>>(nnz, perm, seg, vals, data);
   PGB_LAUNCH_CHECK();

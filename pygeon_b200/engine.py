@@ -287,8 +287,12 @@ class DeviceCSR:
         )
 
 
-def symbolic(pack: GridPack, space: str) -> CsrPlan:
+symbolic_mode = 0  # 0 = two-level (default), 1 = full (row,col) radix sort; see include/pgb.h
+
+
+def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
     """Sort-by-(row,col) of the cell->dof incidences: pattern + gather permutation."""
+    mode = symbolic_mode if mode is None else mode
     key = ("plan", space)
     if key in pack.plans:
         return pack.plans[key]
@@ -299,23 +303,32 @@ def symbolic(pack: GridPack, space: str) -> CsrPlan:
     with torch.cuda.device(dev):
         s = _stream()
         dofs = dofs.contiguous()
-        ws_bytes = int(lib.pgb_csr_workspace_bytes(n_coo, n_rows))
-        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         perm = torch.empty((max(n_coo, 1),), dtype=_I32, device=dev)
-        nnz = C.c_int64(0)
-        check(lib.pgb_csr_symbolic_sort(n_rows, nc, L, dofs.data_ptr(), ws.data_ptr(), ws_bytes,
-                                        perm.data_ptr(), C.byref(nnz), s))
+        while True:
+            ws_bytes = int(lib.pgb_csr_workspace_bytes(nc, L, n_rows, mode))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            nnz = C.c_int64(0)
+            rc = lib.pgb_csr_symbolic_sort(n_rows, nc, L, dofs.data_ptr(), mode, ws.data_ptr(), ws_bytes,
+                                           perm.data_ptr(), C.byref(nnz), s)
+            if rc == 3 and mode == 0:  # a dof shared by too many cells for the register sort
+                mode = 1
+                del ws
+                continue
+            check(rc)
+            break
         nnz = int(nnz.value)
         it = torch.int64 if nnz >= 2**31 else _I32
         indptr = torch.empty((n_rows + 1,), dtype=it, device=dev)
         indices = torch.empty((nnz,), dtype=_I32, device=dev)
         seg = torch.empty((nnz + 1,), dtype=_I32, device=dev)
-        check(lib.pgb_csr_symbolic_finish(n_rows, n_coo, nnz, ws.data_ptr(), indptr.data_ptr(),
+        check(lib.pgb_csr_symbolic_finish(n_rows, nc, L, mode, nnz, ws.data_ptr(), indptr.data_ptr(),
                                           1 if it == torch.int64 else 0, indices.data_ptr(),
                                           seg.data_ptr(), s))
         bits = max(1, int(n_rows - 1).bit_length()) if n_rows > 1 else 1
-        passes = (2 * bits + 7) // 8
-        _lib.count(passes * 5 + 3)
+        if mode == 1:
+            _lib.count(((2 * bits + 7) // 8) * 5 + 3)
+        else:
+            _lib.count(((bits + 7) // 8) * 5 + 6)
         del ws
     plan = CsrPlan(n_rows, n_coo, nnz, perm, seg, indptr, indices)
     pack.plans[key] = plan

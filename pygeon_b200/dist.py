@@ -1,0 +1,365 @@
+"""Cell-partitioned multi-GPU path.
+
+One process per GPU.  The grid is partitioned **by cells** into contiguous z-slabs; a dof (node,
+face, edge) is owned by the lowest rank that has a cell touching it.  Every rank assembles all
+rows it owns by also evaluating the single layer of halo cells that touch owned dofs - redundant
+compute, **no communication during assembly**.  The result is a row-block-distributed CSR whose
+columns are renumbered ``[owned | ghost]``; the distributed solve needs one halo exchange of
+ghost vector entries per SpMV (grouped point-to-point over NCCL / NVLink, at most two neighbours
+for slabs) and one all-reduce of a scalar per dot product.
+
+The reference has no distributed path at all (no MPI / NCCL anywhere); the
+single-GPU operators are the oracle: tests check that the distributed rows equal the global
+matrix's rows and that the distributed CG reproduces the single-GPU iterates.
+
+Everything in this module except the ``pgb_*`` kernel calls is device agnostic, so the
+partition / exchange logic is covered by world_size-2 ``gloo`` tests on CPU.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .grid import SimplexGrid, structured_grid
+
+
+# --------------------------------------------------------------------------------------
+# structured slab partition
+# --------------------------------------------------------------------------------------
+@dataclass
+class SlabLayout:
+    n: int  # cubes per side in x and y
+    nz_total: int  # cube layers of the global box
+    world: int
+    rank: int
+    z0: int  # first owned layer
+    z1: int  # one past the last owned layer
+
+    @property
+    def nz_owned(self) -> int:
+        return self.z1 - self.z0
+
+    @property
+    def halo_top(self) -> bool:
+        return self.rank < self.world - 1
+
+    @property
+    def nz_local(self) -> int:
+        return self.nz_owned + (1 if self.halo_top else 0)
+
+
+def slab_layout(n: int, nz_total: int, world: int, rank: int) -> SlabLayout:
+    """Contiguous split of the ``nz_total`` cube layers (cells are numbered layer by layer)."""
+    if nz_total < world:
+        raise ValueError("need at least one cube layer per rank")
+    base, rem = divmod(nz_total, world)
+    z0 = rank * base + min(rank, rem)
+    z1 = z0 + base + (1 if rank < rem else 0)
+    return SlabLayout(n, nz_total, world, rank, z0, z1)
+
+
+def local_slab_grid(layout: SlabLayout, device="cpu", geometry: bool = False) -> SimplexGrid:
+    """Owned cube layers plus the halo layer above them, as a local grid."""
+    sd = structured_grid(3, layout.n, device=device, nz=layout.nz_local, z0=layout.z0)
+    if geometry:
+        sd.compute_geometry()
+    else:
+        sd.compute_connectivity()
+    sd._layout = layout
+    return sd
+
+
+def _dof_z_range(sd: SimplexGrid, space: str):
+    """(zmin, zmax) local lattice layer of the nodes of every local dof, as int64 tensors."""
+    st = sd._structured
+    n = st["n"]
+    m2 = (n + 1) ** 2
+    if space == "lagrange1":
+        z = torch.arange(sd.num_nodes, dtype=torch.int64) // m2
+        return z, z
+    if space == "rt0":
+        fn = torch.from_numpy(sd.face_nodes.indices.reshape(sd.num_faces, 3).astype(np.int64)) // m2
+        return fn.min(dim=1).values, fn.max(dim=1).values
+    if space == "nedelec0":
+        rp = torch.from_numpy(sd.ridge_peaks.indices.reshape(sd.num_ridges, 2).astype(np.int64)) // m2
+        return rp.min(dim=1).values, rp.max(dim=1).values
+    if space == "p0":
+        z = torch.arange(sd.num_cells, dtype=torch.int64) // (6 * n * n)
+        return z, z + 1
+    raise KeyError(space)
+
+
+def owned_mask(sd: SimplexGrid, space: str) -> torch.Tensor:
+    """True for the local dofs this rank owns (lowest rank with a cell touching the dof)."""
+    lay: SlabLayout = sd._layout
+    zmin, zmax = _dof_z_range(sd, space)
+    in_plane = zmin == zmax
+    # cells touching the dof live in layers zmin-1 and zmin (in-plane dof) or zmin (spanning dof)
+    lowest_layer = torch.where(in_plane, torch.clamp(zmin - 1, min=0), zmin)
+    mask = lowest_layer < lay.nz_owned
+    if lay.rank > 0:
+        mask &= ~(in_plane & (zmin == 0))  # bottom plane belongs to the rank below
+    return mask
+
+
+def global_keys(sd: SimplexGrid, space: str) -> torch.Tensor:
+    """A partition-independent int64 key per local dof (lattice key shifted by the slab offset)."""
+    st = sd._structured
+    lay: SlabLayout = sd._layout
+    n, sh = st["n"], st["key_bits"]
+    node_off = lay.z0 * (n + 1) ** 2
+    if space == "lagrange1":
+        return torch.arange(sd.num_nodes, dtype=torch.int64) + node_off
+    if space == "rt0":
+        return st["face_keys"].cpu() + (node_off << (2 * sh))
+    if space == "nedelec0":
+        return st["edge_keys"].cpu() + (node_off << sh)
+    if space == "p0":
+        return torch.arange(sd.num_cells, dtype=torch.int64) + lay.z0 * 6 * n * n
+    raise KeyError(space)
+
+
+# --------------------------------------------------------------------------------------
+# distributed CSR
+# --------------------------------------------------------------------------------------
+@dataclass
+class DistCSR:
+    """Rows of the owned dofs; columns renumbered [owned (n_owned) | ghost (n_ghost)]."""
+
+    n_owned: int
+    n_ghost: int
+    indptr: torch.Tensor
+    indices: torch.Tensor
+    data: torch.Tensor
+    owned_local: torch.Tensor  # local grid ids of the owned dofs (row order)
+    ghost_local: torch.Tensor  # local grid ids of the ghost dofs (ghost-block order)
+    owned_keys: torch.Tensor
+    send_idx: dict = field(default_factory=dict)  # peer -> indices into the owned block
+    recv_range: dict = field(default_factory=dict)  # peer -> (start, count) inside the ghost block
+    group: object = None
+
+    @property
+    def n_local(self) -> int:
+        return self.n_owned + self.n_ghost
+
+    @property
+    def nnz(self) -> int:
+        return int(self.indices.numel())
+
+
+def _all_gather_var(t: torch.Tensor, group=None) -> list:
+    """all_gather of 1-D int64 tensors of different lengths (pads to the max length)."""
+    world = dist.get_world_size(group)
+    dev = t.device
+    size = torch.tensor([t.numel()], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(size) for _ in range(world)]
+    dist.all_gather(sizes, size, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(max(sizes), 1)
+    buf = torch.zeros(mx, dtype=t.dtype, device=dev)
+    buf[: t.numel()] = t
+    out = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    return [o[:s] for o, s in zip(out, sizes)]
+
+
+def build_dist_csr(indptr, indices, data, owned: torch.Tensor, keys: torch.Tensor, group=None,
+                   comm_device=None) -> DistCSR:
+    """Extract the owned rows of a locally assembled CSR (local ids) and set up the halo exchange.
+
+    ``indptr / indices / data``: CSR over all local dofs (torch tensors, any device);
+    ``owned``: bool mask over local dofs; ``keys``: partition-independent int64 key per local dof.
+    ``comm_device``: device of the tensors handed to the collectives (cuda for nccl, cpu for gloo).
+    """
+    dev = indices.device
+    comm_device = dev if comm_device is None else torch.device(comm_device)
+    owned = owned.to(dev)
+    keys = keys.to(dev)
+    n_local = owned.numel()
+    own = torch.nonzero(owned).flatten()
+    n_owned = int(own.numel())
+    ip = indptr.to(torch.int64)
+    lens = ip[own + 1] - ip[own]
+    new_ip = torch.zeros(n_owned + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens, 0, out=new_ip[1:])
+    nnz = int(new_ip[-1].item())
+    # positions of the kept entries in the old arrays
+    row_of = torch.repeat_interleave(torch.arange(n_owned, device=dev), lens)
+    pos = ip[own][row_of] + (torch.arange(nnz, device=dev) - new_ip[:-1][row_of])
+    cols = indices[pos].to(torch.int64)
+    vals = data[pos]
+    # ghost columns: referenced, not owned
+    ref = torch.zeros(n_local, dtype=torch.bool, device=dev)
+    ref[cols] = True
+    ghost = torch.nonzero(ref & ~owned).flatten()
+    gkeys = keys[ghost]
+
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    okeys = keys[own]
+    send_idx, recv_range = {}, {}
+    if world > 1:
+        okeys_sorted, oorder = torch.sort(okeys)
+        all_g = _all_gather_var(gkeys.to(comm_device), group)
+        masks = []
+        hits = {}
+        for q, gq in enumerate(all_g):
+            gq = gq.to(dev)
+            if q == rank or gq.numel() == 0 or n_owned == 0:
+                m = torch.zeros(gq.numel(), dtype=torch.bool, device=dev)
+            else:
+                p = torch.searchsorted(okeys_sorted, gq).clamp(max=n_owned - 1)
+                m = okeys_sorted[p] == gq
+                hits[q] = oorder[p[m]]
+            masks.append(m)
+        for q, h in hits.items():
+            if h.numel():
+                send_idx[q] = h
+        allm = _all_gather_var(torch.cat(masks).to(torch.int64).to(comm_device), group)
+        off = sum(g.numel() for g in all_g[:rank])
+        ng = int(ghost.numel())
+        owner = torch.full((ng,), -1, dtype=torch.int64, device=dev)
+        for q, mq in enumerate(allm):
+            mine = mq[off: off + ng].to(dev).bool()
+            if (owner[mine] >= 0).any():
+                raise RuntimeError("a ghost dof is claimed by two owners")
+            owner[mine] = q
+        if ng and (owner < 0).any():
+            raise RuntimeError("a ghost dof has no owner")
+        # order the ghost block by (owner, position in the original ghost list) so that every peer's
+        # values arrive contiguously and in the order the peer sends them
+        order = torch.argsort(owner * max(ng, 1) + torch.arange(ng, device=dev))
+        ghost = ghost[order]
+        owner = owner[order]
+        for q in range(world):
+            cnt = int((owner == q).sum().item())
+            if cnt:
+                start = int(torch.nonzero(owner == q)[0].item())
+                recv_range[q] = (start, cnt)
+    elif ghost.numel():
+        raise RuntimeError("ghost dofs in a single-rank run")
+    # renumber the columns
+    newid = torch.full((n_local,), -1, dtype=torch.int64, device=dev)
+    newid[own] = torch.arange(n_owned, device=dev)
+    newid[ghost] = n_owned + torch.arange(ghost.numel(), device=dev)
+    ncols = newid[cols]
+    it = torch.int64 if nnz >= 2**31 else torch.int32
+    return DistCSR(n_owned, int(ghost.numel()), new_ip.to(it), ncols.to(torch.int32), vals, own, ghost, okeys,
+                   send_idx, recv_range, group)
+
+
+def halo_exchange(A: DistCSR, x: torch.Tensor, comm_device=None) -> None:
+    """Fill the ghost block ``x[n_owned:]`` with the owners' values (grouped isend/irecv)."""
+    if not A.send_idx and not A.recv_range:
+        return
+    cdev = x.device if comm_device is None else torch.device(comm_device)
+    ops, recvs, keep = [], [], []
+    for q, (start, cnt) in sorted(A.recv_range.items()):
+        view = x[A.n_owned + start: A.n_owned + start + cnt]
+        if view.device == cdev:
+            buf = view
+        else:
+            buf = torch.empty(cnt, dtype=x.dtype, device=cdev)
+            recvs.append((view, buf))
+        ops.append(dist.P2POp(dist.irecv, buf, q, group=A.group))
+    for q, idx in sorted(A.send_idx.items()):
+        buf = x[idx].to(cdev)
+        keep.append(buf)
+        ops.append(dist.P2POp(dist.isend, buf, q, group=A.group))
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+    for view, buf in recvs:
+        view.copy_(buf)
+
+
+# --------------------------------------------------------------------------------------
+# distributed assembly + solve (GPU)
+# --------------------------------------------------------------------------------------
+def assemble_slab(space: str, form: str, sd: SimplexGrid, data=None, keyword="unitary_data", group=None) -> DistCSR:
+    """Assemble the owned rows of ``space``/``form`` on this rank's slab grid (owned + halo cells)."""
+    from . import engine
+    from .constants import SECOND_ORDER_TENSOR, WEIGHT
+    from .params import get_cell_data
+
+    w = get_cell_data(sd, data, keyword, WEIGHT)
+    K = get_cell_data(sd, data, keyword, SECOND_ORDER_TENSOR)
+    if space == "lagrange1":
+        K = None if form == "mass" else K
+    A = engine.assemble_device(space, form, sd, w, K)
+    return build_dist_csr(A.indptr, A.indices, A.data, owned_mask(sd, space), global_keys(sd, space), group)
+
+
+def dist_spmv(A: DistCSR, x: torch.Tensor, y: torch.Tensor, tpr: int = 0) -> None:
+    """y[:n_owned] = A @ x after refreshing the ghost block of x."""
+    from ._lib import check, lib
+    from .engine import _stream
+
+    halo_exchange(A, x)
+    check(lib.pgb_spmv(A.n_owned, A.indptr.data_ptr(), 1 if A.indptr.dtype == torch.int64 else 0,
+                       A.indices.data_ptr(), A.data.data_ptr(), x.data_ptr(), y.data_ptr(), tpr, _stream()))
+
+
+class _Dot:
+    def __init__(self, device, group):
+        from ._lib import NPART
+
+        self.parts = torch.zeros(NPART, dtype=torch.float64, device=device)
+        self.out = torch.zeros(1, dtype=torch.float64, device=device)
+        self.group = group
+        self.npart = NPART
+
+    def __call__(self, n, x, y) -> float:
+        from ._lib import check, lib
+        from .engine import _stream
+
+        check(lib.pgb_dot_partials(n, x.data_ptr(), y.data_ptr(), self.parts.data_ptr(), _stream()))
+        check(lib.pgb_reduce_partials(self.parts.data_ptr(), self.npart, self.out.data_ptr(), _stream()))
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.out, group=self.group)
+        return float(self.out.item())
+
+
+def dist_cg(A: DistCSR, b: torch.Tensor, *, rtol=1e-5, atol=0.0, maxiter=1000):
+    """CG on the row-distributed operator; same recurrence and stopping rule as
+    ``scipy.sparse.linalg.cg`` (and :func:`pygeon_b200.solvers.cg_device`).  ``b`` holds the owned
+    entries.  Returns (x_owned, info, iterations, residual norms)."""
+    from ._lib import check, lib
+    from .engine import _stream
+
+    dev = b.device
+    n = A.n_owned
+    dot = _Dot(dev, A.group)
+    tpr = 0
+    if A.nnz and n:
+        avg = A.nnz / n
+        tpr = 2 if avg <= 3 else 4 if avg <= 6 else 8 if avg <= 12 else 16 if avg <= 48 else 32
+    x = torch.zeros(A.n_local, dtype=torch.float64, device=dev)
+    p = torch.zeros(A.n_local, dtype=torch.float64, device=dev)
+    r = b.clone()
+    q = torch.empty(n, dtype=torch.float64, device=dev)
+    bnorm = np.sqrt(dot(n, b, b))
+    atol = max(float(atol), float(rtol) * bnorm)
+    hist = []
+    if bnorm == 0.0:
+        return x[:n], 0, 0, np.zeros(0)
+    rho_prev = 1.0
+    s = _stream
+    for it in range(maxiter):
+        rho = dot(n, r, r)
+        rn = np.sqrt(rho)
+        hist.append(rn)
+        if rn < atol:
+            return x[:n], 0, it, np.array(hist)
+        beta = rho / rho_prev if it > 0 else 0.0
+        check(lib.pgb_axpby(n, 1.0, r.data_ptr(), beta, p.data_ptr(), s()))  # p = r + beta p
+        dist_spmv(A, p, q, tpr)
+        alpha = rho / dot(n, p, q)
+        check(lib.pgb_axpby(n, alpha, p.data_ptr(), 1.0, x.data_ptr(), s()))  # x += alpha p
+        check(lib.pgb_axpby(n, -alpha, q.data_ptr(), 1.0, r.data_ptr(), s()))  # r -= alpha q
+        rho_prev = rho
+    hist.append(np.sqrt(dot(n, r, r)))
+    return x[:n], maxiter, maxiter, np.array(hist)

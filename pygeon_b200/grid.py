@@ -233,8 +233,10 @@ def _unique_sorted(keys: torch.Tensor):
     return torch.unique(keys, sorted=True, return_inverse=True)
 
 
-def structured_connectivity(dim: int, n: int, device="cpu") -> dict:
-    """Connectivity of the 2-triangle / 6-Kuhn-tet split of an n^dim lattice.
+def structured_connectivity(dim: int, n: int, device="cpu", nz: int | None = None) -> dict:
+    """Connectivity of the 2-triangle / 6-Kuhn-tet split of an n^dim lattice (3D: n x n x nz
+    cubes when ``nz`` is given; z is the slowest axis, so a z-slab of a taller box has the same
+    numbering up to constant shifts).
 
     Returns int32 torch tensors on ``device`` (all row-major, one row per entity):
 
@@ -245,6 +247,7 @@ def structured_connectivity(dim: int, n: int, device="cpu") -> dict:
     """
     dev = torch.device(device)
     m = n + 1
+    nz = n if nz is None else int(nz)
     i64 = torch.int64
     ar = torch.arange(n, device=dev, dtype=i64)
     if dim == 2:
@@ -261,7 +264,7 @@ def structured_connectivity(dim: int, n: int, device="cpu") -> dict:
         ).reshape(-1, 3)
         nbits, stride = 2, (1, m)
     elif dim == 3:
-        kk, jj, ii = torch.meshgrid(ar, ar, ar, indexing="ij")
+        kk, jj, ii = torch.meshgrid(torch.arange(nz, device=dev, dtype=i64), ar, ar, indexing="ij")
         base = (ii + m * jj + m * m * kk).reshape(-1)
         off = (1, m, m * m)
         tets = []
@@ -275,7 +278,8 @@ def structured_connectivity(dim: int, n: int, device="cpu") -> dict:
     else:
         raise ValueError("dim must be 2 or 3")
     nc = v.shape[0]
-    nn = m**dim
+    size = (m, m) if dim == 2 else (m, m, nz + 1)
+    nn = int(np.prod(size))
 
     def step_code(delta: torch.Tensor) -> torch.Tensor:
         # delta = sx + sy*m (+ sz*m^2) with s in {0,1}; code = sx + 2 sy + 4 sz.
@@ -324,7 +328,7 @@ def structured_connectivity(dim: int, n: int, device="cpu") -> dict:
 
     # lattice coordinates
     ids = torch.arange(nn, device=dev, dtype=i64)
-    lat = torch.stack([(ids // stride[a]) % m for a in range(dim)], dim=1)
+    lat = torch.stack([(ids // stride[a]) % size[a] for a in range(dim)], dim=1)
 
     # ---- signs: +1 iff node-order normal points out of the cell (away from the opposite node)
     sign = torch.empty((nc, dim + 1), dtype=torch.int8, device=dev)
@@ -355,6 +359,9 @@ def structured_connectivity(dim: int, n: int, device="cpu") -> dict:
         "cell_face_sign": sign_sorted.contiguous(),
         "face_nodes": face_nodes.to(torch.int32).contiguous(),
         "lattice": lat.to(torch.int32).contiguous(),
+        "cell_nodes": v,  # (nc, d+1) int64 ascending node ids
+        "face_keys": ufk,  # sorted int64 lattice keys: lo node << (d-1)*key_bits | step codes
+        "key_bits": sh,
     }
     if dim == 3:
         # ---- edges: all 6 local pairs
@@ -368,6 +375,7 @@ def structured_connectivity(dim: int, n: int, device="cpu") -> dict:
         hi = lo + code_offset(uek & ((1 << sh) - 1))
         out["ridge_peaks"] = torch.stack([lo, hi], dim=1).to(torch.int32).contiguous()
         out["num_ridges"] = nr
+        out["edge_keys"] = uek  # sorted int64: lo node << key_bits | step code
         # face_ridges: ridge k joins face node k and k+1 (cyclic)
         fr = []
         fs = []
@@ -389,21 +397,28 @@ def _csc_from_rows(idx: np.ndarray, data: np.ndarray, nrows: int) -> sps.csc_arr
     return sps.csc_array((data.ravel(), idx.ravel(), indptr), shape=(nrows, ncols))
 
 
-def structured_grid(dim: int, n: int, perturb: float = 0.0, seed: int = 0, device="cpu") -> SimplexGrid:
+def structured_grid(dim: int, n: int, perturb: float = 0.0, seed: int = 0, device="cpu",
+                    nz: int | None = None, z0: int = 0) -> SimplexGrid:
     """Unit square / cube, ``n`` cells per side, 2-triangle / 6-Kuhn-tet split.
 
     The analogue of ``pg.unit_grid(dim, 1/n, structured=True, as_mdg=False)``
     followed by ``compute_geometry()`` (``create_grid.py:115-156``).  ``perturb``
     moves interior nodes by ``U(-perturb, perturb)/n`` per coordinate (defeats the
-    exact cancellations of the lattice in parity tests).
+    exact cancellations of the lattice in parity tests).  In 3D ``nz`` / ``z0`` give the slab of
+    ``nz`` cube layers starting at layer ``z0`` of a taller box with the same mesh size ``1/n``
+    (used by the cell-partitioned multi-GPU path); the lattice keys of its faces / edges are kept
+    in ``sd._structured`` so that dofs can be matched across slabs.
     """
-    con = structured_connectivity(dim, n, device=device)
+    con = structured_connectivity(dim, n, device=device, nz=nz)
     lat = con["lattice"].cpu().numpy().astype(np.float64)
     nodes = np.zeros((3, con["num_nodes"]))
     nodes[:dim] = lat.T / n
+    if dim == 3 and z0:
+        nodes[2] += z0 / n
     if perturb:
         rng = np.random.default_rng(seed)
-        interior = np.all((lat > 0) & (lat < n), axis=1)
+        top = np.array([n] * dim) if nz is None or dim == 2 else np.array([n, n, nz])
+        interior = np.all((lat > 0) & (lat < top), axis=1)
         nodes[:dim, interior] += rng.uniform(-perturb, perturb, size=(dim, int(interior.sum()))) / n
     cf = con["cell_faces"].cpu().numpy()
     sg = con["cell_face_sign"].cpu().numpy()
@@ -417,7 +432,9 @@ def structured_grid(dim: int, n: int, perturb: float = 0.0, seed: int = 0, devic
     sd.cell_faces = _csc_from_rows(cf, sg.astype(np.float64), sd.num_faces)
     sd.tags = {}
     sd._geometry_done = False
-    sd._structured = {k: con[k] for k in con if k in ("face_ridges", "face_ridge_sign", "ridge_peaks")}
+    keep = ("face_ridges", "face_ridge_sign", "ridge_peaks", "face_keys", "edge_keys", "key_bits", "cell_nodes")
+    sd._structured = {k: con[k] for k in con if k in keep}
+    sd._structured.update(n=n, nz=(n if nz is None else nz), z0=z0)
     return sd
 
 

@@ -1,0 +1,119 @@
+"""world_size-2/3 gloo tests (CPU) of the cell-partitioned multi-GPU host logic: slab layout,
+dof ownership, owned-row extraction, ghost renumbering and the halo exchange.  The local matrices
+come from the CPU oracle here; on the GPU box tests/test_dist_gpu.py does the same with the CUDA
+assembly."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pygeon_b200 import dist as pd
+from pygeon_b200.grid import structured_grid
+
+N, NZ = 3, 5
+CASES = [("lagrange1", "stiff"), ("rt0", "mass"), ("nedelec0", "mass")]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _global_ids(full, space, keys):
+    st = full._structured
+    if space == "lagrange1":
+        return keys.numpy()
+    table = st["face_keys"] if space == "rt0" else st["edge_keys"]
+    pos = torch.searchsorted(table, keys)
+    assert torch.equal(table[pos], keys)
+    return pos.numpy()
+
+
+def _worker(rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from oracle import fem_oracle as fo
+
+        full = structured_grid(3, N, nz=NZ)
+        full.compute_geometry()
+        lay = pd.slab_layout(N, NZ, world, rank)
+        sd = pd.local_slab_grid(lay, geometry=True)
+        assert sd.num_cells == 6 * N * N * lay.nz_local
+        rng = np.random.default_rng(0)
+        for space, form in CASES:
+            kw = {"rot2d": False} if space == "lagrange1" else {}
+            Aloc = fo.closed_form(space, form, sd, **kw)
+            Aglob = fo.closed_form(space, form, full, **kw).tocsr()
+            own = pd.owned_mask(sd, space)
+            keys = pd.global_keys(sd, space)
+            D = pd.build_dist_csr(torch.from_numpy(Aloc.indptr.astype(np.int64)), torch.from_numpy(Aloc.indices),
+                                  torch.from_numpy(Aloc.data), own, keys)
+            # ownership partitions the global dofs
+            gid_owned = _global_ids(full, space, D.owned_keys)
+            allo = pd._all_gather_var(torch.from_numpy(gid_owned.astype(np.int64)))
+            cat = np.sort(torch.cat(allo).numpy())
+            assert np.array_equal(cat, np.arange(Aglob.shape[0])), space
+            # rows equal the global rows
+            loc = sps.csr_array((D.data.numpy(), D.indices.numpy(), D.indptr.numpy()), shape=(D.n_owned, D.n_local))
+            colkeys = torch.cat([keys[D.owned_local], keys[D.ghost_local]])
+            gcol = _global_ids(full, space, colkeys)
+            P = sps.csr_array((np.ones(D.n_local), (np.arange(D.n_local), gcol)), shape=(D.n_local, Aglob.shape[1]))
+            rows_glob = Aglob[gid_owned]
+            diff = abs(loc @ P - rows_glob).max()
+            assert diff <= 1e-13 * abs(Aglob).max(), (space, diff)
+            ones = loc.copy()
+            ones.data = np.ones_like(ones.data)
+            gones = rows_glob.copy()
+            gones.data = np.ones_like(gones.data)
+            assert abs(ones @ P - gones).max() == 0  # identical structural pattern
+            # halo exchange + local matvec == global matvec
+            xg = rng.normal(size=Aglob.shape[1])
+            x = torch.zeros(D.n_local, dtype=torch.float64)
+            x[: D.n_owned] = torch.from_numpy(xg[gid_owned])
+            pd.halo_exchange(D, x)
+            assert np.array_equal(x.numpy(), xg[gcol]), space
+            y = loc @ x.numpy()
+            assert np.abs(y - (Aglob @ xg)[gid_owned]).max() <= 1e-12 * np.abs(Aglob @ xg).max()
+            # at most two neighbours for a slab partition
+            assert set(D.send_idx) <= {rank - 1, rank + 1} and set(D.recv_range) <= {rank - 1, rank + 1}
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        q.put((rank, traceback.format_exc()))
+        raise
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_partition_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_slab_layout_covers_all_layers():
+    for world in (1, 2, 3, 8):
+        lays = [pd.slab_layout(4, 19, world, r) for r in range(world)]
+        assert lays[0].z0 == 0 and lays[-1].z1 == 19
+        assert all(a.z1 == b.z0 for a, b in zip(lays, lays[1:]))
+        assert max(l.nz_owned for l in lays) - min(l.nz_owned for l in lays) <= 1
+        assert not lays[-1].halo_top and all(l.halo_top for l in lays[:-1])

@@ -1,0 +1,93 @@
+"""Pin the oracle (both restatements) and the grid container against the UNMODIFIED reference,
+imported from /root/reference with the porepy stand-in.  Only runs where the reference source is
+present (the build container); the GPU box uses the golden fixtures generated from it."""
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from oracle import fem_oracle as fo
+from oracle import ref_loader
+from pygeon_b200.grid import reference_element, structured_grid
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference source not present")
+
+TOL = 1e-12
+GRIDS = [(2, 4, 0.2), (3, 3, 0.2), (3, 4, 0.0), (2, 8, 0.0)]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_loader.load()
+
+
+def _data(pg, pp, nc, sym, seed=0):
+    rng = np.random.default_rng(seed)
+    A = rng.normal(size=(3, 3, nc))
+    K = np.einsum("iac,jac->ijc", A, A) + np.eye(3)[:, :, None]
+    if not sym:
+        K = K + 0.3 * rng.normal(size=(3, 3, nc))
+    sot = pp.SecondOrderTensor(np.ones(nc))
+    sot.values = K
+    return {pp.PARAMETERS: {"k": {pg.SECOND_ORDER_TENSOR: sot, pg.WEIGHT: rng.uniform(0.5, 2, nc)}}}
+
+
+@pytest.mark.parametrize("dim,n,pert", GRIDS)
+def test_grid_container_matches_reference(ref, dim, n, pert):
+    """SimplexGrid computes the same ridges / geometry as pg.Grid on the same raw arrays."""
+    sd = structured_grid(dim, n, perturb=pert)
+    sd.compute_geometry()
+    g = ref_loader.ref_grid(sd)
+    for a in ("face_ridges", "ridge_peaks"):
+        A, B = getattr(sd, a), getattr(g, a)
+        assert A.shape == B.shape and abs(A - B).nnz == 0
+    for a in ("cell_volumes", "face_normals", "cell_centers", "face_centers", "edge_tangents"):
+        assert np.allclose(getattr(sd, a), getattr(g, a), rtol=1e-14, atol=1e-15)
+    assert sd.num_edges == g.num_edges and abs(sd.mesh_size - g.mesh_size) < 1e-15
+    assert np.array_equal(sd.compute_opposite_nodes().toarray(), g.compute_opposite_nodes().toarray())
+    if dim == 3:  # cochain property, tests/numerics/test_differentials.py:13-22
+        assert abs(sd.cell_faces.T.astype(int) @ sd.face_ridges.T).sum() == 0
+        assert abs(sd.face_ridges.T @ sd.ridge_peaks.T).sum() == 0
+
+
+@pytest.mark.parametrize("dim,n,pert", GRIDS)
+@pytest.mark.parametrize("mode", ["default", "sym", "nonsym"])
+@pytest.mark.parametrize("which_grid", ["reference_object", "simplex_grid"])
+def test_oracle_matches_reference(ref, dim, n, pert, mode, which_grid):
+    pg, pp = ref
+    sd = structured_grid(dim, n, perturb=pert)
+    sd.compute_geometry()
+    g = ref_loader.ref_grid(sd)
+    G = g if which_grid == "reference_object" else sd
+    data = None if mode == "default" else _data(pg, pp, sd.num_cells, mode == "sym")
+    tabs = fo.cell_tables(G)
+    cls = {"lagrange1": pg.Lagrange1, "rt0": pg.RT0, "bdm1": pg.BDM1, "nedelec0": pg.Nedelec0}
+
+    def check(refm, port, closed):
+        refm = sps.csr_array(refm)
+        scale = abs(refm).max()
+        if port is not None:
+            assert abs(refm - port).max() <= TOL * scale
+            assert sps.csr_array(port).nnz == refm.nnz
+        refS = fo.canonicalise(refm, closed)  # asserts pattern(ref) is inside the structural pattern
+        assert np.abs(refS.data - closed.data).max() <= TOL * scale
+
+    for space, c in cls.items():
+        check(c("k").assemble_mass_matrix(g, data), fo.port_mass(space, G, data, "k", tabs),
+              fo.closed_form(space, "mass", G, data, "k", tabs))
+        check(c("k").assemble_stiff_matrix(g, data), fo.port_stiff(space, G, data, "k", tabs),
+              fo.closed_form(space, "stiff", G, data, "k", tabs))
+    check(pg.Lagrange1("k").assemble_grad_grad_matrix(g, data), None,
+          fo.closed_form("lagrange1", "stiff", G, data, "k", tabs, rot2d=False))
+    d0 = pg.PwConstants("k").assemble_mass_matrix(g, data).diagonal()
+    assert np.allclose(fo.p0_mass(G, data, "k").diagonal(), d0, rtol=1e-14)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_reference_element_matches(ref, dim):
+    pg, _ = ref
+    a = reference_element(dim)
+    b = pg.reference_element(dim)
+    assert np.array_equal(a.nodes, b.nodes)
+    assert np.array_equal(a.face_nodes.indices, b.face_nodes.indices)
+    assert np.array_equal(a.cell_faces.toarray(), b.cell_faces.toarray())

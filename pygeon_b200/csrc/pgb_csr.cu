@@ -345,13 +345,19 @@ __global__ void __launch_bounds__(256) k_max_row(int64_t n_rows, const uint32_t*
   }
 }
 
-template <int G, int ITEMS, int L>
+// KeyT = uint32_t: key = (col << log2(N)) | e with e the candidate's position before sorting (the
+// incidences of a row are in ascending cell order, so e orders ties exactly like src = inc*L + b);
+// used whenever n_rows * N fits in 32 bits.  KeyT = uint64_t: key = (col << 32) | src.
+template <int G, int ITEMS, int L, typename KeyT>
 __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t* __restrict__ row_start,
                                                  const uint32_t* __restrict__ inc_sorted,
                                                  const int32_t* __restrict__ dofs, uint32_t* __restrict__ perm,
                                                  int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ useg_tmp,
                                                  uint32_t* __restrict__ row_nnz) {
   constexpr int N = G * ITEMS;
+  constexpr bool K32 = sizeof(KeyT) == 4;
+  constexpr int EB = (N <= 8) ? 3 : (N <= 16) ? 4 : (N <= 32) ? 5 : (N <= 64) ? 6 : (N <= 128) ? 7 : (N <= 256) ? 8 : 9;
+  constexpr int CSH = K32 ? EB : 32;  // column shift inside the key
   const int lane = threadIdx.x & 31;
   const int gl = lane % G;  // lane within the group
   const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
@@ -365,17 +371,17 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
   const uint32_t base = rs * L;
 
   // gather candidates, blocked layout: element e = gl*ITEMS + i
-  uint64_t key[ITEMS];
+  KeyT key[ITEMS];
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     uint32_t e = gl * ITEMS + i;
-    key[i] = ~0ull;
+    key[i] = (KeyT) ~(KeyT)0;
     if (e < ncand) {
       uint32_t q = e / L, b = e - q * L;
       uint32_t inc = inc_sorted[rs + q];
       uint32_t cell = inc / L;
       uint32_t col = (uint32_t)__ldg(dofs + (int64_t)cell * L + b);
-      key[i] = ((uint64_t)col << 32) | (uint64_t)(inc * L + b);
+      key[i] = ((KeyT)col << CSH) | (KeyT)(K32 ? e : inc * L + b);
     }
   }
   // bitonic sort, ascending, N elements spread over G lanes
@@ -387,12 +393,12 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
         const int lj = j / ITEMS;
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
-          uint64_t other = __shfl_xor_sync(FULL, key[i], lj);
+          KeyT other = __shfl_xor_sync(FULL, key[i], lj);
           int e = gl * ITEMS + i;
           bool lower = (e & j) == 0;
           bool asc = (e & k) == 0;
-          uint64_t mn = key[i] < other ? key[i] : other;
-          uint64_t mx = key[i] < other ? other : key[i];
+          KeyT mn = key[i] < other ? key[i] : other;
+          KeyT mx = key[i] < other ? other : key[i];
           key[i] = (lower == asc) ? mn : mx;
         }
       } else {
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
           if ((i & j) == 0) {
             int e = gl * ITEMS + i;
             bool asc = (e & k) == 0;
-            uint64_t a = key[i], b = key[i | j];
+            KeyT a = key[i], b = key[i | j];
             bool sw = asc ? (a > b) : (a < b);
             key[i] = sw ? b : a;
             key[i | j] = sw ? a : b;
@@ -411,14 +417,14 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
     }
   }
   // unique columns: head(e) = e == 0 || col(e) != col(e-1)
-  uint32_t prev_last = (uint32_t)(__shfl_up_sync(FULL, key[ITEMS - 1], 1) >> 32);
+  uint32_t prev_last = (uint32_t)(__shfl_up_sync(FULL, key[ITEMS - 1], 1) >> CSH);
   uint32_t heads = 0;  // bit i set: element i of this lane starts a run
   int cnt = 0;
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     uint32_t e = gl * ITEMS + i;
-    uint32_t col = (uint32_t)(key[i] >> 32);
-    uint32_t pc = (i == 0) ? prev_last : (uint32_t)(key[i - 1] >> 32);
+    uint32_t col = (uint32_t)(key[i] >> CSH);
+    uint32_t pc = (i == 0) ? prev_last : (uint32_t)(key[i - 1] >> CSH);
     bool h = (e < ncand) && (e == 0 || col != pc);
     heads |= (h ? 1u : 0u) << i;
     cnt += h;
@@ -436,9 +442,17 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
   for (int i = 0; i < ITEMS; ++i) {
     uint32_t e = gl * ITEMS + i;
     if (e < ncand) {
-      perm[base + e] = (uint32_t)key[i];
+      uint32_t src;
+      if (K32) {
+        uint32_t e0 = (uint32_t)key[i] & ((1u << EB) - 1u);  // position before sorting
+        uint32_t q = e0 / L, b = e0 - q * L;
+        src = inc_sorted[rs + q] * L + b;
+      } else {
+        src = (uint32_t)key[i];
+      }
+      perm[base + e] = src;
       if ((heads >> i) & 1u) {
-        ucol_tmp[base + rank] = (int32_t)(key[i] >> 32);
+        ucol_tmp[base + rank] = (int32_t)(key[i] >> CSH);
         useg_tmp[base + rank] = base + e;
         ++rank;
       }
@@ -476,12 +490,15 @@ __global__ void __launch_bounds__(256) k_compact(int64_t n_rows, int L, const ui
 
 // ---- numeric: lane-sequential partial sums + warp-shuffle segmented scan ------------------------
 // A warp owns NUM_OPW consecutive output entries, i.e. the contiguous sorted positions
-// [seg[k0], seg[k0+NUM_OPW)).  The positions are split evenly over the 32 lanes; every lane sums
-// its slice sequentially (runs that start and end inside the slice are stored directly), and the
-// pieces of runs that cross lane boundaries are combined with one segmented inclusive scan over
-// the lanes (5 shuffle steps per warp tile).  Fixed order => bit-reproducible, no atomics.
+// [seg[k0], seg[k0+NUM_OPW)).  It walks them in steps of 32*NUM_C positions: lane l takes the
+// NUM_C consecutive positions [B + l*NUM_C, ...) (a warp-wide step reads 1 KB of perm contiguously),
+// issues its NUM_C gathers together, sums them sequentially (runs that start and end inside the
+// slice are stored directly), and the pieces of runs that cross lane boundaries are combined with
+// one segmented inclusive scan over the lanes (5 shuffle steps per step); the open piece of the
+// last lane is carried into the next step.  Fixed order => bit-reproducible, no atomics.
 constexpr int NUM_BLOCK = 256;
 constexpr int NUM_OPW = 128;  // outputs per warp
+constexpr int NUM_C = 8;      // positions per lane per step
 
 __global__ void __launch_bounds__(NUM_BLOCK) k_numeric(int64_t nnz, const uint32_t* __restrict__ perm,
                                                        const uint32_t* __restrict__ seg,
@@ -493,79 +510,84 @@ __global__ void __launch_bounds__(NUM_BLOCK) k_numeric(int64_t nnz, const uint32
   const int nout = (int)((nnz - k0 < NUM_OPW) ? (nnz - k0) : NUM_OPW);
   for (int i = lane; i <= nout; i += 32) sseg[w][i] = seg[k0 + i];
   __syncwarp();
-  const uint32_t S = sseg[w][0], E = sseg[w][nout];
-  const uint32_t len = E - S;
-  const uint32_t c = (len + 31) / 32;
-  uint32_t p = S + lane * c;
-  uint32_t pe = (p + c < E) ? p + c : E;
-  if (p > E) p = E;
-  // o = index (relative to k0) of the run containing position p: last o with sseg[o] <= p
-  int lo = 0, hi = nout;  // invariant: sseg[lo] <= p < sseg[hi] (when p < E)
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (sseg[w][mid] <= p) lo = mid; else hi = mid;
-  }
-  int o = lo;
-  const bool nonempty = p < pe;
-  const bool starts_at_head = nonempty && (sseg[w][o] == p);
-  double acc = 0.0;      // running sum of the current run piece
-  double first = 0.0;    // piece before the first head in the slice (belongs to an earlier lane's run)
-  bool seen_head = starts_at_head;
-  int o_first = o;       // run the `first` piece belongs to
-  uint32_t next_head = nonempty ? sseg[w][o + 1] : 0;
-  constexpr int U = 8;  // gathers in flight per lane
-  for (uint32_t q0 = p; q0 < pe; q0 += U) {
-    double v[U];
+  const uint32_t* ss = sseg[w];
+  const uint32_t S = ss[0], E = ss[nout];
+  double carry = 0.0;  // open piece of the run that continues from the previous step
+  for (uint32_t B = S; B < E; B += 32 * NUM_C) {
+    uint32_t p = B + lane * NUM_C;
+    if (p > E) p = E;
+    const uint32_t pe = (p + NUM_C < E) ? p + NUM_C : E;
+    const bool nonempty = p < pe;
+    double v[NUM_C];
 #pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = (q0 + u < pe) ? vals[perm[q0 + u]] : 0.0;
+    for (int u = 0; u < NUM_C; ++u) v[u] = (p + u < pe) ? vals[perm[p + u]] : 0.0;
+    // o = run containing p: last o with ss[o] <= p
+    int lo = 0, hi = nout;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (ss[mid] <= p) lo = mid; else hi = mid;
+    }
+    int o = lo;
+    const bool starts_at_head = nonempty && (ss[o] == p);
+    const int o_first = o;
+    double acc = 0.0, first = 0.0;
+    bool seen_head = starts_at_head;
+    uint32_t next_head = nonempty ? ss[o + 1] : 0u;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      uint32_t q = q0 + u;
+    for (int u = 0; u < NUM_C; ++u) {
+      uint32_t q = p + u;
       if (q < pe) {
         if (q == next_head) {  // a new run starts at q: close the previous piece
           if (seen_head) data[k0 + o] = acc;  // run began inside this slice: complete
-          else first = acc;
+          else first = acc;                   // piece of a run that began in an earlier lane / step
           seen_head = true;
           acc = 0.0;
           ++o;
-          next_head = sseg[w][o + 1];
+          next_head = ss[o + 1];
         }
         acc += v[u];
       }
     }
-  }
-  // lane summary: `first` (if !starts_at_head) continues run o_first; `acc` is the open piece of run o
-  // (== first piece when no head was seen).  has_head: a run starts somewhere in this slice.
-  const bool has_head = seen_head;
-  if (!has_head) first = acc;  // whole slice is one piece of an earlier run
-  double open = has_head ? acc : 0.0;
-  // carry[i] = sum of open pieces of lanes j < i back to (and including) the nearest lane with a head
-  // -> exclusive segmented scan of `open`/`first` over lanes.
-  // value v_i: contribution lane i passes on = has_head ? open : first(+carry).
-  double v = has_head ? open : first;
-  bool f = has_head;  // reset flag
-  // inclusive segmented scan (flag = run restarts in this lane)
-  double incl = v;
-  bool fl = f;
+    const bool has_head = seen_head;
+    if (!has_head) first = acc;  // the whole slice is one piece of an earlier run
+    // inclusive segmented scan over lanes of the value each lane passes on
+    // (its open piece if a run starts in it, else its single piece), restarted at lanes with a head
+    double incl = has_head ? acc : first;
+    bool fl = has_head;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    double t = __shfl_up_sync(FULL, incl, d);
-    bool tf = __shfl_up_sync(FULL, fl ? 1 : 0, d) != 0;
-    if (lane >= d && !fl) {
-      incl += t;
-      fl = tf;
+    for (int d = 1; d < 32; d <<= 1) {
+      double t = __shfl_up_sync(FULL, incl, d);
+      bool tf = __shfl_up_sync(FULL, fl ? 1 : 0, d) != 0;
+      if (lane >= d && !fl) {
+        incl += t;
+        fl = tf;
+      }
     }
-  }
-  double carry_in = __shfl_up_sync(FULL, incl, 1);
-  if (lane == 0) carry_in = 0.0;
-  // the run continued into this lane ends here if this lane has a head (then `first` closes it) ...
-  const bool empty_next = !__shfl_down_sync(FULL, nonempty ? 1 : 0, 1) || lane == 31;
-  const bool next_starts_head = __shfl_down_sync(FULL, starts_at_head ? 1 : 0, 1) != 0;
-  if (nonempty && !starts_at_head && has_head) data[k0 + o_first] = carry_in + first;
-  // ... and the open piece of this lane is complete if the next lane starts with a head / is empty
-  if (nonempty && (empty_next || next_starts_head)) {
-    double tot = has_head ? open : carry_in + first;
-    data[k0 + o] = tot;
+    // carry from the previous step reaches every lane up to (and including) the first lane with a head
+    const bool reached = !fl;  // no head in lanes 0..lane
+    double carry_in = __shfl_up_sync(FULL, incl, 1);
+    bool reached_prev = __shfl_up_sync(FULL, reached ? 1 : 0, 1) != 0;
+    if (lane == 0) {
+      carry_in = carry;
+    } else if (reached_prev) {
+      carry_in += carry;
+    }
+    // close the run that continues into this lane (it ends at this lane's first head)
+    if (nonempty && !starts_at_head && has_head) data[k0 + o_first] = carry_in + first;
+    // value of the open run at the end of this lane
+    const double open_tot = has_head ? acc : carry_in + first;
+    const uint32_t nxt = __shfl_down_sync(FULL, p, 1);  // first position of the next lane
+    const bool last_nonempty = nonempty && (lane == 31 || pe == E || nxt >= E);
+    bool ends_here;
+    if (lane == 31 || pe == E) ends_here = nonempty && (pe == E || ss[o + 1] == pe);
+    else ends_here = nonempty && (ss[o + 1] == pe);
+    if (ends_here) data[k0 + o] = open_tot;
+    // carry into the next step: the open run of the last non-empty lane, if it continues
+    double c_next = (last_nonempty && !ends_here) ? open_tot : 0.0;
+    int src_lane = 31;
+    unsigned ne = __ballot_sync(FULL, nonempty);
+    if (ne) src_lane = 31 - __clz(ne);
+    carry = __shfl_sync(FULL, c_next, src_lane);
   }
 }
 
@@ -620,7 +642,8 @@ int radix_sort(KeySrc<KeyT> src, uint32_t n, int total_bits, KeyT* kbuf[2], uint
   return 0;
 }
 
-constexpr int MODE_TWO_LEVEL = 0, MODE_FULL_SORT = 1;
+constexpr int MODE_TWO_LEVEL = 0, MODE_FULL_SORT = 1, MODE_TWO_LEVEL_KEY64 = 2;
+bool g_force_key64 = false;  // mode 2: exercise the 64-bit-key row sort (tests)
 constexpr uint32_t MAX_ROW_CAND = 512;  // capacity of the largest k_rowsort instance
 
 struct WsLayout {
@@ -671,25 +694,34 @@ ChunkGrid chunk_grid(int64_t n) {
   return {g, chunk};
 }
 
-template <int G, int ITEMS>
+template <int G, int ITEMS, typename KeyT>
 int launch_rowsort_l(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
                      uint32_t* perm, int32_t* ucol, uint32_t* useg, uint32_t* row_nnz, cudaStream_t s) {
   unsigned grid = pgb_grid(n_rows * G, 256);
   switch (L) {
-    case 3: k_rowsort<G, ITEMS, 3><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
-    case 4: k_rowsort<G, ITEMS, 4><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
-    case 6: k_rowsort<G, ITEMS, 6><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
-    case 12: k_rowsort<G, ITEMS, 12><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
+    case 3: k_rowsort<G, ITEMS, 3, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
+    case 4: k_rowsort<G, ITEMS, 4, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
+    case 6: k_rowsort<G, ITEMS, 6, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
+    case 12: k_rowsort<G, ITEMS, 12, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
     default: pgb_set_error("k_rowsort: unsupported local size %d", L); return 2;
   }
   PGB_LAUNCH_CHECK();
   return 0;
 }
 
+template <int G, int ITEMS>
+int launch_rowsort_k(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
+                     uint32_t* perm, int32_t* ucol, uint32_t* useg, uint32_t* row_nnz, cudaStream_t s) {
+  // 32-bit keys when (col, position-in-row) fits strictly below the padding value 0xffffffff
+  if ((uint64_t)n_rows * (uint64_t)(G * ITEMS) <= 0xffffffffull && !g_force_key64)
+    return launch_rowsort_l<G, ITEMS, uint32_t>(L, n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz, s);
+  return launch_rowsort_l<G, ITEMS, uint64_t>(L, n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz, s);
+}
+
 int launch_rowsort(uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc,
                    const int32_t* dofs, uint32_t* perm, int32_t* ucol, uint32_t* useg, uint32_t* row_nnz,
                    cudaStream_t s) {
-#define PGB_RS(G, I) return launch_rowsort_l<G, I>(L, n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz, s)
+#define PGB_RS(G, I) return launch_rowsort_k<G, I>(L, n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz, s)
   if (max_cand <= 8) PGB_RS(4, 2);
   if (max_cand <= 16) PGB_RS(8, 2);
   if (max_cand <= 32) PGB_RS(8, 4);
@@ -711,7 +743,8 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
                                      int64_t* nnz_host, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n_coo = nc * L * L, n_inc = nc * L;
-  PGB_REQUIRE(mode == MODE_TWO_LEVEL || mode == MODE_FULL_SORT, "pgb_csr_symbolic_sort: bad mode");
+  PGB_REQUIRE(mode >= 0 && mode <= 2, "pgb_csr_symbolic_sort: bad mode");
+  g_force_key64 = (mode == MODE_TWO_LEVEL_KEY64);
   PGB_REQUIRE(n_coo < ((int64_t)1 << 32) - SORT_TILE, "pgb_csr_symbolic_sort: n_coo must be < 2^32");
   PGB_REQUIRE(n_rows > 0 && n_rows < ((int64_t)1 << 31), "pgb_csr_symbolic_sort: n_rows out of range");
   WsLayout l = ws_layout(n_coo, n_inc, n_rows, mode);

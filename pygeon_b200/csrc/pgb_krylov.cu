@@ -82,15 +82,20 @@ struct SpmvArgs {
   int itn;               // SPMV_MINRES: 1-based iteration
 };
 
+constexpr int SPMV_UR = 4;  // rows per sub-warp per outer iteration (loads of all rows issued together)
+
 template <int TPR, typename IP, int MODE>
 __global__ void __launch_bounds__(KB) k_spmv(SpmvArgs a) {
   __shared__ double ws[KB / 32];
   if (MODE == SPMV_CG && a.cg->done) return;
   if (MODE == SPMV_MINRES && a.mr->done) return;
   constexpr int RPB = KB / TPR;  // rows per block-tile
+  constexpr int UR = SPMV_UR;
   const int sub = threadIdx.x % TPR;
   const int grp = threadIdx.x / TPR;
   const IP* __restrict__ ip = reinterpret_cast<const IP*>(a.indptr);
+  const double* __restrict__ data = a.data;
+  const int32_t* __restrict__ indices = a.indices;
   double shift = 0.0, coef = 0.0;
   if (MODE == SPMV_MINRES) {
     shift = a.mr->shift;
@@ -98,25 +103,52 @@ __global__ void __launch_bounds__(KB) k_spmv(SpmvArgs a) {
   }
   double dot = 0.0;
   const int64_t ntiles = (a.n + RPB - 1) / RPB;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    int64_t row = t * RPB + grp;
-    double s = 0.0;
-    if (row < a.n) {
-      IP lo = ip[row], hi = ip[row + 1];
-      for (IP j = lo + sub; j < hi; j += TPR) s += a.data[j] * __ldg(a.x + a.indices[j]);
-    }
+  for (int64_t t = (int64_t)blockIdx.x * UR; t < ntiles; t += (int64_t)gridDim.x * UR) {
+    int64_t row[UR];
+    IP lo[UR], hi[UR];
 #pragma unroll
-    for (int d = TPR / 2; d > 0; d >>= 1) s += __shfl_xor_sync(FULL, s, d);
-    if (row < a.n && sub == 0) {
-      if (MODE == SPMV_MINRES) {
-        double xv = a.x[row];
-        if (shift != 0.0) s -= shift * xv;
-        if (a.itn >= 2) s -= coef * a.r1[row];
-        dot += xv * s;
-      } else if (MODE == SPMV_CG) {
-        dot += a.x[row] * s;
+    for (int u = 0; u < UR; ++u) {
+      row[u] = (t + u) * RPB + grp;
+      bool ok = row[u] < a.n;
+      lo[u] = ok ? ip[row[u]] : (IP)0;
+      hi[u] = ok ? ip[row[u] + 1] : (IP)0;
+    }
+    double dv[UR];
+    int32_t ci[UR];
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      IP j = lo[u] + sub;
+      bool ok = j < hi[u];
+      dv[u] = ok ? data[j] : 0.0;
+      ci[u] = ok ? indices[j] : -1;
+    }
+    double s[UR];
+#pragma unroll
+    for (int u = 0; u < UR; ++u) s[u] = (ci[u] >= 0) ? dv[u] * __ldg(a.x + ci[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < UR; ++u)
+      for (IP j = lo[u] + sub + TPR; j < hi[u]; j += TPR) s[u] += data[j] * __ldg(a.x + indices[j]);
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+#pragma unroll
+      for (int d = TPR / 2; d > 0; d >>= 1) s[u] += __shfl_xor_sync(FULL, s[u], d);
+    }
+    if (sub == 0) {
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        if (row[u] < a.n) {
+          double sv = s[u];
+          if (MODE == SPMV_MINRES) {
+            double xv = a.x[row[u]];
+            if (shift != 0.0) sv -= shift * xv;
+            if (a.itn >= 2) sv -= coef * a.r1[row[u]];
+            dot += xv * sv;
+          } else if (MODE == SPMV_CG) {
+            dot += a.x[row[u]] * sv;
+          }
+          a.y[row[u]] = sv;
+        }
       }
-      a.y[row] = s;
     }
   }
   if (MODE != SPMV_PLAIN) {
@@ -138,7 +170,7 @@ int launch_spmv_t(const SpmvArgs& a, cudaStream_t s) {
     if (grid > NPART) grid = NPART;
     if (grid < 1) grid = 1;
   }
-  int64_t ntiles = (a.n + (KB / TPR) - 1) / (KB / TPR);
+  int64_t ntiles = ((a.n + (KB / TPR) - 1) / (KB / TPR) + SPMV_UR - 1) / SPMV_UR;
   int g = (int)(ntiles < grid ? (ntiles < 1 ? 1 : ntiles) : grid);
   k_spmv<TPR, IP, MODE><<<g, KB, 0, s>>>(a);
   PGB_LAUNCH_CHECK();
@@ -161,11 +193,13 @@ int launch_spmv(const SpmvArgs& a, int idx64, int tpr, cudaStream_t s) {
   return idx64 ? launch_spmv_ip<int64_t, MODE>(a, tpr, s) : launch_spmv_ip<int32_t, MODE>(a, tpr, s);
 }
 
+// threads per row, tuned on B200 with 4 rows in flight per sub-warp (scripts/spmv_bench.py):
+// RT0 (7 nnz/row) best at 2, P1 (14.8) at 4, Nedelec (16.2) at 4-8
 int pick_tpr(double avg) {
-  if (avg <= 3.0) return 2;
-  if (avg <= 6.0) return 4;
-  if (avg <= 12.0) return 8;
-  if (avg <= 48.0) return 16;
+  if (avg <= 9.0) return 2;
+  if (avg <= 18.0) return 4;
+  if (avg <= 40.0) return 8;
+  if (avg <= 100.0) return 16;
   return 32;
 }
 

@@ -336,7 +336,7 @@ def dist_cg(A: DistCSR, b: torch.Tensor, *, rtol=1e-5, atol=0.0, maxiter=1000):
     tpr = 0
     if A.nnz and n:
         avg = A.nnz / n
-        tpr = 2 if avg <= 3 else 4 if avg <= 6 else 8 if avg <= 12 else 16 if avg <= 48 else 32
+        tpr = 2 if avg <= 9 else 4 if avg <= 18 else 8 if avg <= 40 else 16 if avg <= 100 else 32
     x = torch.zeros(A.n_local, dtype=torch.float64, device=dev)
     p = torch.zeros(A.n_local, dtype=torch.float64, device=dev)
     r = b.clone()

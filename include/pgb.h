@@ -94,7 +94,11 @@ enum {
   PGB_P0_MASS = 7,      /* fem/l2.py:335-353: diag(w/|c|)                   L = 1        */
   PGB_RT0_DIVDIV = 8,   /* RT0 stiff = cell_faces diag(w/|c|) cell_faces^T (hdiv.py:177-192 via
                            discretization.py:154-183); also Nedelec0 stiff in 2D     L = d+1 */
-  PGB_BDM1_DIVDIV = 9   /* BDM1 stiff, div = div_RT0 @ hstack([I]*d)/d (hdiv.py:353-371)  L = d(d+1) */
+  PGB_BDM1_DIVDIV = 9,  /* BDM1 stiff, div = div_RT0 @ hstack([I]*d)/d (hdiv.py:353-371)  L = d(d+1) */
+  PGB_DARCY_SADDLE = 10 /* symmetrised mixed-Darcy block system [[M, -B^T], [-B, 0]] with M = RT0 mass,
+                           B = P0mass @ div (tutorials/fluid_flow/darcy.ipynb cell 10,
+                           tests/patch_tests/test_laplacian_mixed.py:50), assembled in one pass:
+                           local dofs = (faces of the cell, num_faces + cell)        L = d+2 */
 };
 int pgb_local_size(int kind, int dim); /* L */
 int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
@@ -159,6 +163,24 @@ int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_t* indices,
 
 /* Building blocks used by the multi-GPU drivers (halo exchange / allreduce happen between
  * them on the host side through NCCL). */
+/* CG step API: the fused kernels of pgb_cg one by one, so that a multi-GPU driver can interleave
+ * the halo exchange (before step_spmv) and the all-reduce of the partial sums (step_reduce with
+ * from_red = 0, all-reduce of scratch[4*PGB_NPART + i], step_reduce with from_red = 1).
+ * mask bits: 1 = r.r, 2 = r.z, 4 = b.b, 8 = p.q.  scratch: pgb_cg_scratch_doubles(maxiter) doubles;
+ * scratch[4*PGB_NPART + 8] holds the int `done` flag, the residual norms start at
+ * scratch[4*PGB_NPART + 32]. */
+int64_t pgb_cg_scratch_doubles(int maxiter);
+int pgb_cg_step_init(int64_t n, const double* b, const double* q, const double* dinv, double* r,
+                     double rtol, double atol, double* scratch, void* stream);
+int pgb_cg_step_reduce(double* scratch, int mask, int from_red, void* stream);
+int pgb_cg_step_p(int64_t n, int k, const double* r, const double* dinv, double* p, double* scratch,
+                  void* stream);
+int pgb_cg_step_spmv(int64_t n, const void* indptr, int idx64, const int32_t* indices,
+                     const double* data, const double* p, double* q, int threads_per_row,
+                     double* scratch, void* stream);
+int pgb_cg_step_xr(int64_t n, const double* p, const double* q, const double* dinv, double* x,
+                   double* r, double* scratch, void* stream);
+
 int pgb_dot_partials(int64_t n, const double* x, const double* y, double* partials /*[PGB_NPART]*/,
                      void* stream);
 int pgb_reduce_partials(const double* partials, int count, double* out, void* stream);

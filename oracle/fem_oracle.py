@@ -239,6 +239,15 @@ def p0_mass(sd, data=None, keyword="unitary_data"):
     return sps.diags_array(w / sd.cell_volumes).tocsc()
 
 
+def darcy_saddle(sd, data=None, keyword="unitary_data", tabs=None, route="closed"):
+    """Symmetrised mixed-Darcy system [[M, -B^T], [-B, 0]] built the reference's way
+    (tutorials/fluid_flow/darcy.ipynb cell 10 with the second block row negated): M = RT0 mass,
+    B = P0 mass @ div."""
+    M = port_mass("rt0", sd, data, keyword, tabs) if route == "port" else closed_form("rt0", "mass", sd, data, keyword, tabs)
+    B = p0_mass(sd, data, keyword) @ diff_matrix("rt0", sd)
+    return sps.block_array([[M, -B.T], [-B, None]]).tocsr()
+
+
 def port_stiff(space: str, sd, data=None, keyword="unitary_data", tabs=None):
     """``(B.T @ A @ B).tocsc()`` with A the range-space mass (discretization.py:154-183)."""
     d = sd.dim

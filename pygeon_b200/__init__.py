@@ -27,6 +27,10 @@ def __getattr__(name):
         from . import solvers as _s
 
         return getattr(_s, name)
+    if name in ("darcy_saddle_device", "darcy_saddle_matrix"):
+        from . import darcy as _dz
+
+        return getattr(_dz, name)
     if name in ("DeviceCSR",):
         from . import engine as _e
 

@@ -38,6 +38,12 @@ _SIGS = {
     "pgb_spmv": (_i, [_l, _p, _i, _p, _p, _p, _p, _i, _p]),
     "pgb_cg": (_i, [_l, _p, _i, _p, _p, _p, _p, _p, _d, _d, _i, _p, C.POINTER(_i), C.POINTER(_i), _p, _p]),
     "pgb_minres": (_i, [_l, _p, _i, _p, _p, _p, _p, _d, _d, _i, _p, C.POINTER(_i), C.POINTER(_i), _p, _p]),
+    "pgb_cg_scratch_doubles": (_l, [_i]),
+    "pgb_cg_step_init": (_i, [_l, _p, _p, _p, _p, _d, _d, _p, _p]),
+    "pgb_cg_step_reduce": (_i, [_p, _i, _i, _p]),
+    "pgb_cg_step_p": (_i, [_l, _i, _p, _p, _p, _p, _p]),
+    "pgb_cg_step_spmv": (_i, [_l, _p, _i, _p, _p, _p, _p, _i, _p, _p]),
+    "pgb_cg_step_xr": (_i, [_l, _p, _p, _p, _p, _p, _p, _p]),
     "pgb_dot_partials": (_i, [_l, _p, _p, _p, _p]),
     "pgb_reduce_partials": (_i, [_p, _i, _p, _p]),
     "pgb_axpby": (_i, [_l, _d, _p, _d, _p, _p]),
@@ -60,6 +66,7 @@ KIND = {
     "p0_mass": 7,
     "rt0_divdiv": 8,
     "bdm1_divdiv": 9,
+    "darcy_saddle": 10,
 }
 NPART = 1184
 

@@ -701,6 +701,7 @@ int launch_rowsort_l(int L, int64_t n_rows, const uint32_t* row_start, const uin
   switch (L) {
     case 3: k_rowsort<G, ITEMS, 3, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
     case 4: k_rowsort<G, ITEMS, 4, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
+    case 5: k_rowsort<G, ITEMS, 5, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
     case 6: k_rowsort<G, ITEMS, 6, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
     case 12: k_rowsort<G, ITEMS, 12, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
     default: pgb_set_error("k_rowsort: unsupported local size %d", L); return 2;

@@ -527,6 +527,45 @@ double avg_row(int64_t n, const void* indptr, int idx64, cudaStream_t s) {
   return n > 0 ? (double)nnz / (double)n : 0.0;
 }
 
+// ---- step API helpers (multi-GPU drivers): move partial sums to / from a contiguous buffer ------
+// red[i] = sum(parts_i) for the arrays selected by `mask`
+__global__ void __launch_bounds__(KB) k_parts_to_red(double* scratch, int mask) {
+  __shared__ double ws[KB / 32];
+  for (int i = 0; i < 4; ++i) {
+    if (!((mask >> i) & 1)) continue;
+    double s = sum_partials(scratch + (size_t)i * NPART, ws);
+    if (threadIdx.x == 0) scratch[4 * NPART + i] = s;
+  }
+}
+// parts_i = (red[i], 0, 0, ...) so that the fused kernels see the globally reduced value
+__global__ void __launch_bounds__(KB) k_red_to_parts(double* scratch, int mask) {
+  for (int i = 0; i < 4; ++i) {
+    if (!((mask >> i) & 1)) continue;
+    double* p = scratch + (size_t)i * NPART;
+    double v = scratch[4 * NPART + i];
+    for (int j = threadIdx.x; j < NPART; j += KB) p[j] = (j == 0) ? v : 0.0;
+  }
+}
+
+struct StepScratch {
+  double *p_rr, *p_rho, *p_bb, *p_pq, *red;
+  CgScal* sc;
+  int* flag;
+  double* resid;
+};
+__host__ StepScratch step_scratch(double* scratch) {
+  StepScratch t;
+  t.p_rr = scratch;
+  t.p_rho = scratch + NPART;
+  t.p_bb = scratch + 2 * NPART;
+  t.p_pq = scratch + 3 * NPART;
+  t.red = scratch + 4 * NPART;                       // 8 doubles
+  t.flag = (int*)(scratch + 4 * NPART + 8);          // 1 double slot: done flag (int)
+  t.sc = (CgScal*)(scratch + 4 * NPART + 16);        // 16 doubles reserved
+  t.resid = scratch + 4 * NPART + 32;                // residual history follows
+  return t;
+}
+
 }  // namespace
 
 extern "C" int pgb_spmv(int64_t n_rows, const void* indptr, int idx64, const int32_t* indices,
@@ -704,5 +743,63 @@ extern "C" int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_
     PGB_CHECK(cudaMemcpyAsync(resid_host, S.resid + 1, sizeof(double) * h.itn, cudaMemcpyDeviceToHost, s));
     PGB_CHECK(cudaStreamSynchronize(s));
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CG step API: the same fused kernels as pgb_cg, launched one by one so that a multi-GPU driver
+// can put the halo exchange (before the SpMV) and the all-reduce of the partial sums (after the
+// kernels that produce them) in between.  All scalars stay on the device.
+// scratch layout (doubles): [4*NPART partial arrays: rr, rho, bb, pq][8: red][8: flag][16: scalars]
+// [maxiter+2: residual history];  pgb_cg_scratch_doubles(maxiter) gives the size.
+// ---------------------------------------------------------------------------------------------
+extern "C" int64_t pgb_cg_scratch_doubles(int maxiter) { return 4 * (int64_t)NPART + 32 + maxiter + 2; }
+
+extern "C" int pgb_cg_step_init(int64_t n, const double* b, const double* q, const double* dinv, double* r,
+                                double rtol, double atol, double* scratch, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  StepScratch t = step_scratch(scratch);
+  CgScal h = {};
+  h.atol_user = atol;
+  h.rtol = rtol;
+  PGB_CHECK(cudaMemsetAsync(t.flag, 0, 8, s));
+  PGB_CHECK(cudaMemcpyAsync(t.sc, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  k_cg_init<<<vec_grid(n), KB, 0, s>>>(n, b, q, dinv, r, t.p_rr, t.p_rho, t.p_bb);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+/* mask bits: 1 = rr, 2 = rho, 4 = bb, 8 = pq.  to_red: parts -> scratch[4*NPART + i]; from_red: back. */
+extern "C" int pgb_cg_step_reduce(double* scratch, int mask, int from_red, void* stream) {
+  if (from_red) k_red_to_parts<<<1, KB, 0, (cudaStream_t)stream>>>(scratch, mask);
+  else k_parts_to_red<<<1, KB, 0, (cudaStream_t)stream>>>(scratch, mask);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_cg_step_p(int64_t n, int k, const double* r, const double* dinv, double* p, double* scratch,
+                             void* stream) {
+  StepScratch t = step_scratch(scratch);
+  k_cg_p<<<vec_grid(n), KB, 0, (cudaStream_t)stream>>>(n, k, r, dinv, p, t.p_rr, t.p_rho, t.p_bb, t.sc, t.resid,
+                                                         t.flag);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_cg_step_spmv(int64_t n, const void* indptr, int idx64, const int32_t* indices,
+                                const double* data, const double* p, double* q, int threads_per_row,
+                                double* scratch, void* stream) {
+  StepScratch t = step_scratch(scratch);
+  SpmvArgs a = {};
+  a.n = n; a.indptr = indptr; a.indices = indices; a.data = data;
+  a.x = p; a.y = q; a.parts = t.p_pq; a.cg = t.sc;
+  return launch_spmv<SPMV_CG>(a, idx64, threads_per_row > 0 ? threads_per_row : 4, (cudaStream_t)stream);
+}
+
+extern "C" int pgb_cg_step_xr(int64_t n, const double* p, const double* q, const double* dinv, double* x,
+                              double* r, double* scratch, void* stream) {
+  StepScratch t = step_scratch(scratch);
+  k_cg_xr<<<vec_grid(n), KB, 0, (cudaStream_t)stream>>>(n, p, q, dinv, x, r, t.p_pq, t.p_rr, t.p_rho, t.sc);
+  PGB_LAUNCH_CHECK();
   return 0;
 }

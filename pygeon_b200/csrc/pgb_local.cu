@@ -198,6 +198,7 @@ struct LocalSize {
   static constexpr int L = (KIND == PGB_BDM1_MASS || KIND == PGB_BDM1_DIVDIV)   ? D * (D + 1)
                            : (KIND == PGB_N0_MASS || KIND == PGB_N0_CURLCURL) ? D * (D + 1) / 2
                            : (KIND == PGB_P0_MASS)                            ? 1
+                           : (KIND == PGB_DARCY_SADDLE)                       ? D + 2
                                                                               : D + 1;
 };
 
@@ -231,6 +232,20 @@ __global__ void __launch_bounds__(BLOCK) k_local(Params p) {
 
     if constexpr (KIND == PGB_P0_MASS) {
       emit(0, w / g.vol);
+    } else if constexpr (KIND == PGB_DARCY_SADDLE) {
+      double A[D + 1][D + 1];
+      unsigned sb = p.sign_bits[c];
+      rt0_local<D, HAS_K>(g, Kr, sb, w, A);
+      double bv = w / g.vol;  // P0 mass (w/|c|) times the +-1 of the divergence
+#pragma unroll
+      for (int a = 0; a <= D; ++a) {
+#pragma unroll
+        for (int b = 0; b <= D; ++b) emit(a * L + b, A[a][b]);
+        double ba = ((sb >> a) & 1u) ? bv : -bv;  // -B^T entry: -(s_a w/|c|)
+        emit(a * L + (D + 1), ba);
+        emit((D + 1) * L + a, ba);
+      }
+      emit((D + 1) * L + (D + 1), 0.0);
     } else if constexpr (KIND == PGB_RT0_DIVDIV) {
       unsigned sb = p.sign_bits[c];
       double wv = w / g.vol;
@@ -401,6 +416,7 @@ int dispatch(int kind, const Params& p, cudaStream_t s) {
     case PGB_P0_MASS: return launch<PGB_P0_MASS, D>(p, s);
     case PGB_RT0_DIVDIV: return launch<PGB_RT0_DIVDIV, D>(p, s);
     case PGB_BDM1_DIVDIV: return launch<PGB_BDM1_DIVDIV, D>(p, s);
+    case PGB_DARCY_SADDLE: return launch<PGB_DARCY_SADDLE, D>(p, s);
   }
   pgb_set_error("pgb_local_matrices: unknown kind %d", kind);
   return 2;
@@ -415,6 +431,7 @@ extern "C" int pgb_local_size(int kind, int dim) {
     case PGB_N0_MASS:
     case PGB_N0_CURLCURL: return dim * (dim + 1) / 2;
     case PGB_P0_MASS: return 1;
+    case PGB_DARCY_SADDLE: return dim + 2;
     default: return dim + 1;
   }
 }
@@ -426,7 +443,7 @@ extern "C" int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* 
   PGB_REQUIRE(dim == 2 || dim == 3, "pgb_local_matrices: dim must be 2 or 3");
   PGB_REQUIRE(cell_nodes && coords && vals, "pgb_local_matrices: null pointer");
   if (kind == PGB_RT0_MASS || kind == PGB_BDM1_MASS || kind == PGB_N0_CURLCURL ||
-      kind == PGB_RT0_DIVDIV || kind == PGB_BDM1_DIVDIV)
+      kind == PGB_RT0_DIVDIV || kind == PGB_BDM1_DIVDIV || kind == PGB_DARCY_SADDLE)
     PGB_REQUIRE(sign_bits, "pgb_local_matrices: sign_bits required");
   if (kind == PGB_BDM1_MASS || kind == PGB_N0_MASS || (kind == PGB_N0_CURLCURL && dim == 3))
     PGB_REQUIRE(aux_bits, "pgb_local_matrices: aux_bits required");

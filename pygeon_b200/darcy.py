@@ -1,0 +1,35 @@
+"""One-pass assembly of the mixed-Darcy RT0-P0 block system.
+
+The reference stacks the blocks on the host with ``sps.block_array([[M, -B.T], [B, None]])``
+(tutorials/fluid_flow/darcy.ipynb cell 10; tests/patch_tests/test_laplacian_mixed.py:50), where
+``M = RT0.assemble_mass_matrix`` (fem/hdiv.py:255-274) and ``B = PwConstants mass @ div``
+(fem/l2.py:335-353, fem/hdiv.py:177-192).  That matrix is not symmetric; MINRES needs the second
+block row negated.  Here the **symmetrised** system
+
+    [[ M, -B^T ],
+     [ -B,  0  ]]      unknowns (face fluxes, cell pressures), rhs (f_u, -f_p)
+
+is assembled directly on the device as one CSR: every cell contributes a (d+2)x(d+2) local block
+over the dofs (its faces, num_faces + cell).  The zero pressure block is kept as explicit zeros on
+the diagonal (structural pattern).
+"""
+
+from __future__ import annotations
+
+import scipy.sparse as sps
+
+from . import engine
+from .constants import SECOND_ORDER_TENSOR, UNITARY_DATA, WEIGHT
+from .params import get_cell_data
+
+
+def darcy_saddle_device(sd, data: dict | None = None, keyword: str = UNITARY_DATA) -> engine.DeviceCSR:
+    w = get_cell_data(sd, data, keyword, WEIGHT)
+    K = get_cell_data(sd, data, keyword, SECOND_ORDER_TENSOR)
+    return engine.assemble_device("darcy", "saddle", sd, w, K)
+
+
+def darcy_saddle_matrix(sd, data: dict | None = None, keyword: str = UNITARY_DATA) -> sps.csc_array:
+    """Host copy (CSC).  For non-symmetric tensors the CSR arrays are reinterpreted as CSC exactly as
+    for the mass matrices (see pgb.h, K1 note)."""
+    return darcy_saddle_device(sd, data, keyword).to_scipy("csc")

@@ -323,20 +323,80 @@ class _Dot:
         return float(self.out.item())
 
 
-def dist_cg(A: DistCSR, b: torch.Tensor, *, rtol=1e-5, atol=0.0, maxiter=1000):
-    """CG on the row-distributed operator; same recurrence and stopping rule as
-    ``scipy.sparse.linalg.cg`` (and :func:`pygeon_b200.solvers.cg_device`).  ``b`` holds the owned
-    entries.  Returns (x_owned, info, iterations, residual norms)."""
+def _tpr(A: DistCSR) -> int:
+    if not A.nnz or not A.n_owned:
+        return 2
+    avg = A.nnz / A.n_owned
+    return 2 if avg <= 9 else 4 if avg <= 18 else 8 if avg <= 40 else 16 if avg <= 100 else 32
+
+
+def dist_cg(A: DistCSR, b: torch.Tensor, *, rtol=1e-5, atol=0.0, maxiter=1000, check_every=8):
+    """CG on the row-distributed operator with the **same fused device kernels** as the single-GPU
+    driver (``pgb_cg_step_*``): scalars never leave the device; per iteration one grouped halo
+    exchange (before the SpMV) and two tiny all-reduces of partial sums (p.q; then r.r and r.z).
+    The host only polls the ``done`` flag every ``check_every`` iterations.  Recurrence and stopping
+    rule are those of ``scipy.sparse.linalg.cg``.  ``b`` holds the owned entries.
+    Returns (x_owned, info, iterations, residual norms)."""
+    from ._lib import NPART, check, lib
+    from .engine import _stream
+
+    dev = b.device
+    n = A.n_owned
+    multi = dist.is_initialized() and dist.get_world_size(A.group) > 1
+    tpr = _tpr(A)
+    idx64 = 1 if A.indptr.dtype == torch.int64 else 0
+    scratch = torch.zeros(int(lib.pgb_cg_scratch_doubles(int(maxiter))), dtype=torch.float64, device=dev)
+    sp = scratch.data_ptr()
+    red = scratch[4 * NPART: 4 * NPART + 4]
+    flags = scratch[4 * NPART + 8: 4 * NPART + 9].view(torch.int32)
+    scal_i = scratch[4 * NPART + 16 + 5: 4 * NPART + 16 + 6].view(torch.int32)  # (done, iters)
+    hist_d = scratch[4 * NPART + 32:]
+    x = torch.zeros(A.n_local, dtype=torch.float64, device=dev)
+    p = torch.zeros(A.n_local, dtype=torch.float64, device=dev)
+    r = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    q = torch.zeros(max(n, 1), dtype=torch.float64, device=dev)
+
+    def allreduce(lo, hi):
+        mask = sum(1 << i for i in range(lo, hi))
+        check(lib.pgb_cg_step_reduce(sp, mask, 0, _stream()))
+        if multi:
+            dist.all_reduce(red[lo:hi], group=A.group)
+        check(lib.pgb_cg_step_reduce(sp, mask, 1, _stream()))
+
+    check(lib.pgb_cg_step_init(n, b.data_ptr(), q.data_ptr(), 0, r.data_ptr(), float(rtol), float(atol), sp, _stream()))
+    allreduce(0, 3)
+    if float(red[2].item()) == 0.0:  # scipy: b == 0 -> x = 0
+        return x[:n], 0, 0, np.zeros(0)
+    launched = 0
+    for k in range(int(maxiter)):
+        check(lib.pgb_cg_step_p(n, k, r.data_ptr(), 0, p.data_ptr(), sp, _stream()))
+        halo_exchange(A, p)
+        check(lib.pgb_cg_step_spmv(n, A.indptr.data_ptr(), idx64, A.indices.data_ptr(), A.data.data_ptr(),
+                                   p.data_ptr(), q.data_ptr(), tpr, sp, _stream()))
+        allreduce(3, 4)
+        check(lib.pgb_cg_step_xr(n, p.data_ptr(), q.data_ptr(), 0, x.data_ptr(), r.data_ptr(), sp, _stream()))
+        allreduce(0, 2)
+        launched += 1
+        if check_every and (k + 1) % check_every == 0 and int(flags[0].item()):
+            break
+    done, iters = (int(v) for v in scal_i.cpu())
+    if done:
+        hist = hist_d[: iters + 1].cpu().numpy()
+        return x[:n], 0, iters, hist
+    hist = np.concatenate([hist_d[:iters].cpu().numpy(), [float(np.sqrt(max(float(red[0].item()), 0.0)))]])
+    return x[:n], int(maxiter), iters, hist
+
+
+def dist_cg_host(A: DistCSR, b: torch.Tensor, *, rtol=1e-5, atol=0.0, maxiter=1000):
+    """Host-driven variant (generic kernels ``pgb_spmv / pgb_dot_partials / pgb_axpby``, two host
+    syncs per iteration); kept as a cross-check of :func:`dist_cg`."""
     from ._lib import check, lib
     from .engine import _stream
 
     dev = b.device
     n = A.n_owned
     dot = _Dot(dev, A.group)
-    tpr = 0
-    if A.nnz and n:
-        avg = A.nnz / n
-        tpr = 2 if avg <= 9 else 4 if avg <= 18 else 8 if avg <= 40 else 16 if avg <= 100 else 32
+    tpr = _tpr(A)
     x = torch.zeros(A.n_local, dtype=torch.float64, device=dev)
     p = torch.zeros(A.n_local, dtype=torch.float64, device=dev)
     r = b.clone()

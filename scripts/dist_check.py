@@ -81,6 +81,10 @@ assert np.abs(hist[:15] - info1.residuals[:15]).max() <= 1e-10 * hist[0]
 assert np.abs(hist[:m] - info1.residuals[:m]).max() <= 1e-5 * hist[0]
 err = float((xd - x1[go]).abs().max() / x1.abs().max())
 assert err <= 1e-9, err
+xh, infoh, kh, histh = pd.dist_cg_host(DS, bg[go].contiguous(), rtol=1e-10, maxiter=500)
+assert infoh == 0 and abs(kh - k) <= 1 and float((xh - xd).abs().max() / xd.abs().max()) <= 1e-9
+xm, infom, km, histm = pd.dist_cg(DS, bg[go].contiguous(), rtol=1e-14, maxiter=7)
+assert infom == 7 and km == 7 and len(histm) == 8
 if rank == 0:
     print(f"dist_cg: {k} iterations (single GPU {info1.iterations}), max rel diff {err:.1e}")
 dist.barrier()

@@ -128,6 +128,10 @@ int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
  *   a warp-shuffle segmented scan, in a fixed order (bit-reproducible).
  */
 int64_t pgb_csr_workspace_bytes(int64_t nc, int L, int64_t n_rows, int mode);
+/* Optional CUDA-event timing of the phases of the two-level symbolic_sort (off by default):
+ * out[0] radix sort of the incidences, [1] row offsets + max count, [2] per-row sort, [3] scan. */
+void pgb_set_profile(int on);
+void pgb_get_phase_ms(double* out, int n);
 int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell_dofs, int mode,
                           void* workspace, int64_t workspace_bytes, uint32_t* perm,
                           int64_t* nnz_host, void* stream);

@@ -32,6 +32,8 @@ _SIGS = {
     "pgb_local_size": (_i, [_i, _i]),
     "pgb_local_matrices": (_i, [_i, _i, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pgb_csr_workspace_bytes": (_l, [_l, _i, _l, _i]),
+    "pgb_set_profile": (None, [_i]),
+    "pgb_get_phase_ms": (None, [_p, _i]),
     "pgb_csr_symbolic_sort": (_i, [_l, _l, _i, _p, _i, _p, _l, _p, C.POINTER(C.c_int64), _p]),
     "pgb_csr_symbolic_finish": (_i, [_l, _l, _i, _i, _l, _p, _p, _i, _p, _p, _p]),
     "pgb_csr_numeric": (_i, [_l, _p, _p, _p, _p, _p]),

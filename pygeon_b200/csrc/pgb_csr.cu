@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) k_radix_hist(KeySrc<KeyT> src, uin
     uint32_t idx = base + i * SORT_BLOCK + threadIdx.x;
     if (idx < n) {
       uint32_t d = (uint32_t)(load_key(src, idx) >> shift) & (RADIX - 1);
-      atomicAdd(&h[d], 1u);
+      atomicAdd(&h[d], 1u);  // integer count: order independent (measured faster than match.any aggregation)
     }
   }
   __syncthreads();
@@ -319,11 +319,12 @@ __global__ void __launch_bounds__(256) k_row_starts(const uint32_t* __restrict__
                                                     uint32_t* __restrict__ row_start) {
   uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i >= n) return;
-  int64_t k = keys[i];
-  int64_t prev = (i == 0) ? -1 : (int64_t)keys[i - 1];
-  for (int64_t r = prev + 1; r <= k; ++r) row_start[r] = i;
+  uint32_t k = keys[i];
+  uint32_t prev = (i == 0) ? 0xffffffffu : keys[i - 1];
+  if (k != prev)
+    for (uint32_t r = prev + 1u; r <= k; ++r) row_start[r] = i;  // prev + 1 wraps to 0 for i == 0
   if (i == n - 1)
-    for (int64_t r = k + 1; r <= n_rows; ++r) row_start[r] = n;
+    for (int64_t r = (int64_t)k + 1; r <= n_rows; ++r) row_start[r] = n;
 }
 
 // max number of incidences of one dof (integer max: order independent)
@@ -642,6 +643,34 @@ int radix_sort(KeySrc<KeyT> src, uint32_t n, int total_bits, KeyT* kbuf[2], uint
   return 0;
 }
 
+// optional per-phase timing of the symbolic call (CUDA events on the caller's stream)
+bool g_profile = false;
+double g_phase_ms[8] = {0};
+struct PhaseTimer {
+  cudaEvent_t ev[8];
+  int n = 0;
+  cudaStream_t s;
+  explicit PhaseTimer(cudaStream_t st) : s(st) {}
+  void mark() {
+    if (!g_profile || n >= 8) return;
+    cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n], s);
+    ++n;
+  }
+  void finish() {
+    if (!g_profile) return;
+    for (int i = 0; i < 8; ++i) g_phase_ms[i] = 0.0;
+    if (n) cudaEventSynchronize(ev[n - 1]);
+    for (int i = 0; i + 1 < n; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      g_phase_ms[i] = ms;
+    }
+    for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+    n = 0;
+  }
+};
+
 constexpr int MODE_TWO_LEVEL = 0, MODE_FULL_SORT = 1, MODE_TWO_LEVEL_KEY64 = 2;
 bool g_force_key64 = false;  // mode 2: exercise the 64-bit-key row sort (tests)
 constexpr uint32_t MAX_ROW_CAND = 512;  // capacity of the largest k_rowsort instance
@@ -735,6 +764,13 @@ int launch_rowsort(uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row
 
 }  // namespace
 
+extern "C" void pgb_set_profile(int on) { g_profile = on != 0; }
+/* phases of the last two-level pgb_csr_symbolic_sort call [ms]: 0 radix sort of the incidences,
+ * 1 row offsets + max (incl. the host read), 2 per-row sort, 3 scan of the row counts */
+extern "C" void pgb_get_phase_ms(double* out, int n) {
+  for (int i = 0; i < n && i < 8; ++i) out[i] = g_phase_ms[i];
+}
+
 extern "C" int64_t pgb_csr_workspace_bytes(int64_t nc, int L, int64_t n_rows, int mode) {
   return ws_layout(nc * L * L, nc * L, n_rows, mode).total;
 }
@@ -775,7 +811,10 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     uint32_t* row_start = (uint32_t*)(ws + l.row_start);
     uint32_t* row_nnz = (uint32_t*)(ws + l.row_nnz);
     KeySrc<uint32_t> src{nullptr, cell_dofs, (uint32_t)L, (uint32_t)(L * L), cb};
+    PhaseTimer pt(s);
+    pt.mark();
     if (radix_sort<uint32_t>(src, (uint32_t)n_inc, cb, kbuf, pbuf, hist, parts, s)) return 1;
+    pt.mark();
     k_row_starts<<<pgb_grid(n_inc, 256), 256, 0, s>>>(kbuf[0], (uint32_t)n_inc, n_rows, row_start);
     k_max_row<<<(unsigned)(n_rows < 256 * 1184 ? pgb_grid(n_rows, 256) : 1184), 256, 0, s>>>(n_rows, row_start, meta + 3);
     PGB_LAUNCH_CHECK();
@@ -788,11 +827,15 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
       return 3;
     }
     PGB_CHECK(cudaMemsetAsync(row_nnz + n_rows, 0, 2 * sizeof(uint32_t), s));
+    pt.mark();
     if (launch_rowsort(max_inc * (uint32_t)L, L, n_rows, row_start, pbuf[0], cell_dofs, perm,
                        (int32_t*)(ws + l.ucol), (uint32_t*)(ws + l.useg), row_nnz, s))
       return 1;
+    pt.mark();
     if (scan_u32(row_nnz, (uint64_t)n_rows + 1, parts, nullptr, s)) return 1;
     PGB_CHECK(cudaMemcpyAsync(meta + 2, row_nnz + n_rows, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    pt.mark();
+    pt.finish();
   }
   uint32_t nnz32 = 0;
   PGB_CHECK(cudaMemcpyAsync(&nnz32, meta + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

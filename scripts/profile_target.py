@@ -22,11 +22,22 @@ sd = pg.structured_grid(3, n, device=dev)
 sd.compute_connectivity()
 raw = engine.RawGrid.upload(sd, dev, ridges=(space == "nedelec0"))
 raw.check = False
+import time
 for _ in range(reps):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     pack = engine.GridPack.from_raw(raw)
     plan = engine.symbolic(pack, space)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
     vals = engine.local_matrices(pack, kind)
     data = engine.numeric(plan, vals)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"cells {sd.num_cells} rows {plan.n_rows} nnz {plan.nnz}: pack+symbolic {1e3 * (t1 - t0):.2f} ms, "
+          f"local+numeric {1e3 * (t2 - t1):.2f} ms -> cold {sd.num_cells / (t2 - t0):.3g} cells/s, "
+          f"warm {sd.num_cells / (t2 - t1):.3g} cells/s, mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
+    del vals
 torch.cuda.synchronize()
 if cg_iters and space == "lagrange1":
     A = engine.DeviceCSR((plan.n_rows, plan.n_rows), plan.indptr, plan.indices, data)

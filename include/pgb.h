@@ -185,6 +185,26 @@ int pgb_cg_step_spmv(int64_t n, const void* indptr, int idx64, const int32_t* in
 int pgb_cg_step_xr(int64_t n, const double* p, const double* q, const double* dinv, double* x,
                    double* r, double* scratch, void* stream);
 
+/* MINRES step API, same idea (kernels of pgb_minres one by one; the host rotates the r1/r2/y and
+ * w buffers exactly as pgb_minres does).  mask bits of step_reduce: 1 = v.y, 2 = r2.y, 4 = x.x,
+ * 8 = r1.y (beta1^2), 16 = b.b; the reduced values sit at scratch[5*PGB_NPART + i]; the int `done`
+ * flag at scratch[5*PGB_NPART + 8]; (beta1^2, b.b) at scratch[5*PGB_NPART + 80]; the residual
+ * estimates (phibar) of iterations 1.. at scratch[5*PGB_NPART + 82 + itn]. */
+int64_t pgb_mr_scratch_doubles(int maxiter);
+int pgb_mr_step_reduce(double* scratch, int mask, int from_red, void* stream);
+int pgb_mr_step_init(int64_t n, const double* b, const double* q, double* r1, double* scratch,
+                     void* stream);
+int pgb_mr_step_start(int64_t n, const double* r1, double* v, double* w, double* w2, double rtol,
+                      double shift, int maxiter, double* scratch, void* stream);
+int pgb_mr_step_spmv(int64_t n, const void* indptr, int idx64, const int32_t* indices,
+                     const double* data, const double* v, double* y, const double* r1, int itn,
+                     int threads_per_row, double* scratch, void* stream);
+int pgb_mr_step_c(int64_t n, double* y, const double* r2, double* scratch, void* stream);
+int pgb_mr_step_scalars(int itn, int test_only, double* scratch, void* stream);
+int pgb_mr_step_d(int64_t n, double* v, double* w_old, const double* w_new, const double* r2,
+                  double* x, double* scratch, void* stream);
+int pgb_mr_state(const double* scratch, int* itn_host, int* istop_host, void* stream);
+
 int pgb_dot_partials(int64_t n, const double* x, const double* y, double* partials /*[PGB_NPART]*/,
                      void* stream);
 int pgb_reduce_partials(const double* partials, int count, double* out, void* stream);

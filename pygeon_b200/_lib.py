@@ -46,6 +46,15 @@ _SIGS = {
     "pgb_cg_step_p": (_i, [_l, _i, _p, _p, _p, _p, _p]),
     "pgb_cg_step_spmv": (_i, [_l, _p, _i, _p, _p, _p, _p, _i, _p, _p]),
     "pgb_cg_step_xr": (_i, [_l, _p, _p, _p, _p, _p, _p, _p]),
+    "pgb_mr_scratch_doubles": (_l, [_i]),
+    "pgb_mr_step_reduce": (_i, [_p, _i, _i, _p]),
+    "pgb_mr_step_init": (_i, [_l, _p, _p, _p, _p, _p]),
+    "pgb_mr_step_start": (_i, [_l, _p, _p, _p, _p, _d, _d, _i, _p, _p]),
+    "pgb_mr_step_spmv": (_i, [_l, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p]),
+    "pgb_mr_step_c": (_i, [_l, _p, _p, _p, _p]),
+    "pgb_mr_step_scalars": (_i, [_i, _i, _p, _p]),
+    "pgb_mr_step_d": (_i, [_l, _p, _p, _p, _p, _p, _p, _p]),
+    "pgb_mr_state": (_i, [_p, C.POINTER(_i), C.POINTER(_i), _p]),
     "pgb_dot_partials": (_i, [_l, _p, _p, _p, _p]),
     "pgb_reduce_partials": (_i, [_p, _i, _p, _p]),
     "pgb_axpby": (_i, [_l, _d, _p, _d, _p, _p]),

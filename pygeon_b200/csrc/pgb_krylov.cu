@@ -529,20 +529,20 @@ double avg_row(int64_t n, const void* indptr, int idx64, cudaStream_t s) {
 
 // ---- step API helpers (multi-GPU drivers): move partial sums to / from a contiguous buffer ------
 // red[i] = sum(parts_i) for the arrays selected by `mask`
-__global__ void __launch_bounds__(KB) k_parts_to_red(double* scratch, int mask) {
+__global__ void __launch_bounds__(KB) k_parts_to_red(double* scratch, int mask, int narr) {
   __shared__ double ws[KB / 32];
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < narr; ++i) {
     if (!((mask >> i) & 1)) continue;
     double s = sum_partials(scratch + (size_t)i * NPART, ws);
-    if (threadIdx.x == 0) scratch[4 * NPART + i] = s;
+    if (threadIdx.x == 0) scratch[(size_t)narr * NPART + i] = s;
   }
 }
 // parts_i = (red[i], 0, 0, ...) so that the fused kernels see the globally reduced value
-__global__ void __launch_bounds__(KB) k_red_to_parts(double* scratch, int mask) {
-  for (int i = 0; i < 4; ++i) {
+__global__ void __launch_bounds__(KB) k_red_to_parts(double* scratch, int mask, int narr) {
+  for (int i = 0; i < narr; ++i) {
     if (!((mask >> i) & 1)) continue;
     double* p = scratch + (size_t)i * NPART;
-    double v = scratch[4 * NPART + i];
+    double v = scratch[(size_t)narr * NPART + i];
     for (int j = threadIdx.x; j < NPART; j += KB) p[j] = (j == 0) ? v : 0.0;
   }
 }
@@ -771,8 +771,8 @@ extern "C" int pgb_cg_step_init(int64_t n, const double* b, const double* q, con
 
 /* mask bits: 1 = rr, 2 = rho, 4 = bb, 8 = pq.  to_red: parts -> scratch[4*NPART + i]; from_red: back. */
 extern "C" int pgb_cg_step_reduce(double* scratch, int mask, int from_red, void* stream) {
-  if (from_red) k_red_to_parts<<<1, KB, 0, (cudaStream_t)stream>>>(scratch, mask);
-  else k_parts_to_red<<<1, KB, 0, (cudaStream_t)stream>>>(scratch, mask);
+  if (from_red) k_red_to_parts<<<1, KB, 0, (cudaStream_t)stream>>>(scratch, mask, 4);
+  else k_parts_to_red<<<1, KB, 0, (cudaStream_t)stream>>>(scratch, mask, 4);
   PGB_LAUNCH_CHECK();
   return 0;
 }
@@ -801,5 +801,110 @@ extern "C" int pgb_cg_step_xr(int64_t n, const double* p, const double* q, const
   StepScratch t = step_scratch(scratch);
   k_cg_xr<<<vec_grid(n), KB, 0, (cudaStream_t)stream>>>(n, p, q, dinv, x, r, t.p_pq, t.p_rr, t.p_rho, t.sc);
   PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MINRES step API (same kernels as pgb_minres; the host rotates the r / w buffers exactly as
+// pgb_minres does).  scratch layout (doubles): [5*NPART partial arrays: alfa, beta, xx, b1, bb]
+// [8: red][8: done flag][64: scalars][2: (beta1^2, b.b)][maxiter+2: |r| estimates (phibar)].
+// mask bits for step_reduce: 1 = v.y (alfa), 2 = r2.y (beta^2), 4 = x.x, 8 = r1.y (beta1^2), 16 = b.b.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct MrScratch {
+  double *p_alfa, *p_beta, *p_xx, *p_b1, *p_bb, *red, *out2, *resid;
+  int* flag;
+  MinresScal* sc;
+};
+MrScratch mr_scratch(double* s) {
+  MrScratch t;
+  t.p_alfa = s;
+  t.p_beta = s + NPART;
+  t.p_xx = s + 2 * NPART;
+  t.p_b1 = s + 3 * NPART;
+  t.p_bb = s + 4 * NPART;
+  t.red = s + 5 * NPART;
+  t.flag = (int*)(s + 5 * NPART + 8);
+  t.sc = (MinresScal*)(s + 5 * NPART + 16);
+  t.out2 = s + 5 * NPART + 80;
+  t.resid = s + 5 * NPART + 82;
+  return t;
+}
+static_assert(sizeof(MinresScal) <= 64 * sizeof(double), "MinresScal must fit its scratch slot");
+}  // namespace
+
+extern "C" int64_t pgb_mr_scratch_doubles(int maxiter) { return 5 * (int64_t)NPART + 82 + maxiter + 2; }
+
+extern "C" int pgb_mr_step_reduce(double* scratch, int mask, int from_red, void* stream) {
+  if (from_red) k_red_to_parts<<<1, KB, 0, (cudaStream_t)stream>>>(scratch, mask, 5);
+  else k_parts_to_red<<<1, KB, 0, (cudaStream_t)stream>>>(scratch, mask, 5);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+/* r1 = b - q (q = A x0); partials beta1^2 and b.b */
+extern "C" int pgb_mr_step_init(int64_t n, const double* b, const double* q, double* r1, double* scratch,
+                                void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  MrScratch t = mr_scratch(scratch);
+  PGB_CHECK(cudaMemsetAsync(t.flag, 0, 8, s));
+  k_mr_init<<<vec_grid(n), KB, 0, s>>>(n, b, q, nullptr, r1, t.p_b1, t.p_bb);
+  k_dot<<<1, KB, 0, s>>>(0, b, b, t.p_xx);  // x.x = 0 for x0 = 0 (zero-fills the partial array)
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+/* after the all-reduce of (beta1^2, b.b): scalar state + v = r1/beta1, w = w2 = 0.
+ * scratch[5*NPART+80..81] = (beta1^2, b.b) for the host's early-exit tests. */
+extern "C" int pgb_mr_step_start(int64_t n, const double* r1, double* v, double* w, double* w2, double rtol,
+                                 double shift, int maxiter, double* scratch, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  MrScratch t = mr_scratch(scratch);
+  k_mr_setup<<<1, KB, 0, s>>>(t.sc, t.p_b1, t.p_bb, rtol, shift, maxiter, t.out2);
+  k_mr_start<<<vec_grid(n), KB, 0, s>>>(n, r1, nullptr, t.sc, v, w, w2);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_mr_step_spmv(int64_t n, const void* indptr, int idx64, const int32_t* indices,
+                                const double* data, const double* v, double* y, const double* r1, int itn,
+                                int threads_per_row, double* scratch, void* stream) {
+  MrScratch t = mr_scratch(scratch);
+  SpmvArgs a = {};
+  a.n = n; a.indptr = indptr; a.indices = indices; a.data = data;
+  a.x = v; a.y = y; a.parts = t.p_alfa; a.mr = t.sc; a.r1 = r1; a.itn = itn;
+  return launch_spmv<SPMV_MINRES>(a, idx64, threads_per_row > 0 ? threads_per_row : 4, (cudaStream_t)stream);
+}
+
+extern "C" int pgb_mr_step_c(int64_t n, double* y, const double* r2, double* scratch, void* stream) {
+  MrScratch t = mr_scratch(scratch);
+  k_mr_c<<<vec_grid(n), KB, 0, (cudaStream_t)stream>>>(n, y, r2, nullptr, t.p_alfa, t.p_beta, t.sc);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_mr_step_scalars(int itn, int test_only, double* scratch, void* stream) {
+  MrScratch t = mr_scratch(scratch);
+  k_mr_scalars<<<1, KB, 0, (cudaStream_t)stream>>>(itn, t.p_beta, t.p_xx, t.sc, t.resid, t.flag, test_only);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_mr_step_d(int64_t n, double* v, double* w_old, const double* w_new, const double* r2,
+                             double* x, double* scratch, void* stream) {
+  MrScratch t = mr_scratch(scratch);
+  k_mr_d<<<vec_grid(n), KB, 0, (cudaStream_t)stream>>>(n, v, w_old, w_new, r2, nullptr, x, t.p_xx, t.sc);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+/* (itn, istop) of the device-side state, after a stream synchronisation */
+extern "C" int pgb_mr_state(const double* scratch, int* itn_host, int* istop_host, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  MinresScal h;
+  PGB_CHECK(cudaMemcpyAsync(&h, scratch + 5 * NPART + 16, sizeof(h), cudaMemcpyDeviceToHost, s));
+  PGB_CHECK(cudaStreamSynchronize(s));
+  *itn_host = h.itn;
+  *istop_host = h.istop;
   return 0;
 }

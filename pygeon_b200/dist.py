@@ -90,6 +90,9 @@ def _dof_z_range(sd: SimplexGrid, space: str):
     if space == "p0":
         z = torch.arange(sd.num_cells, dtype=torch.int64) // (6 * n * n)
         return z, z + 1
+    if space == "darcy":  # RT0 x P0: face dofs then cell dofs
+        a, b = _dof_z_range(sd, "rt0"), _dof_z_range(sd, "p0")
+        return torch.cat([a[0], b[0]]), torch.cat([a[1], b[1]])
     raise KeyError(space)
 
 
@@ -120,6 +123,8 @@ def global_keys(sd: SimplexGrid, space: str) -> torch.Tensor:
         return st["edge_keys"].cpu() + (node_off << sh)
     if space == "p0":
         return torch.arange(sd.num_cells, dtype=torch.int64) + lay.z0 * 6 * n * n
+    if space == "darcy":
+        return torch.cat([global_keys(sd, "rt0"), global_keys(sd, "p0") + (1 << 60)])
     raise KeyError(space)
 
 
@@ -385,6 +390,86 @@ def dist_cg(A: DistCSR, b: torch.Tensor, *, rtol=1e-5, atol=0.0, maxiter=1000, c
         return x[:n], 0, iters, hist
     hist = np.concatenate([hist_d[:iters].cpu().numpy(), [float(np.sqrt(max(float(red[0].item()), 0.0)))]])
     return x[:n], int(maxiter), iters, hist
+
+
+def dist_minres(A: DistCSR, b: torch.Tensor, *, rtol=1e-5, shift=0.0, maxiter=1000, check_every=8):
+    """MINRES (Paige-Saunders, the recurrence and stopping tests of ``scipy.sparse.linalg.minres``)
+    on the row-distributed operator with the fused device kernels of the single-GPU driver
+    (``pgb_mr_step_*``): per iteration one halo exchange of ``v`` and three one-scalar all-reduces
+    (v.y, r2.y, x.x); all Lanczos / rotation scalars stay on the device.
+    Returns (x_owned, info, iterations, phibar history)."""
+    import ctypes as C
+
+    from ._lib import NPART, check, lib
+    from .engine import _stream
+
+    dev = b.device
+    n = A.n_owned
+    multi = dist.is_initialized() and dist.get_world_size(A.group) > 1
+    tpr = _tpr(A)
+    idx64 = 1 if A.indptr.dtype == torch.int64 else 0
+    scratch = torch.zeros(int(lib.pgb_mr_scratch_doubles(int(maxiter))), dtype=torch.float64, device=dev)
+    sp = scratch.data_ptr()
+    red = scratch[5 * NPART: 5 * NPART + 5]
+    flags = scratch[5 * NPART + 8: 5 * NPART + 9].view(torch.int32)
+    out2 = scratch[5 * NPART + 80: 5 * NPART + 82]
+    hist_d = scratch[5 * NPART + 82:]
+
+    def allreduce(lo, hi):
+        mask = sum(1 << i for i in range(lo, hi))
+        check(lib.pgb_mr_step_reduce(sp, mask, 0, _stream()))
+        if multi:
+            dist.all_reduce(red[lo:hi], group=A.group)
+        check(lib.pgb_mr_step_reduce(sp, mask, 1, _stream()))
+
+    f64 = dict(dtype=torch.float64, device=dev)
+    x = torch.zeros(max(n, 1), **f64)
+    v = torch.zeros(A.n_local, **f64)
+    rb = [torch.zeros(max(n, 1), **f64) for _ in range(3)]
+    wb = [torch.zeros(max(n, 1), **f64) for _ in range(2)]
+    check(lib.pgb_mr_step_init(n, b.data_ptr(), rb[2].data_ptr(), rb[0].data_ptr(), sp, _stream()))
+    allreduce(3, 5)
+    check(lib.pgb_mr_step_start(n, rb[0].data_ptr(), v.data_ptr(), wb[0].data_ptr(), wb[1].data_ptr(),
+                                float(rtol), float(shift), int(maxiter), sp, _stream()))
+    b1sq, bb = (float(t) for t in out2.cpu())
+    if b1sq == 0.0 or bb == 0.0:  # x0 = 0 solves the system / b == 0
+        return x[:n], 0, 0, np.zeros(0)
+    r1 = r2 = rb[0]
+    y, spare = rb[1], rb[2]
+    w_new, w_old = wb[0], wb[1]
+    itn = 0
+    while itn < maxiter:
+        if check_every and itn and itn % check_every == 0 and int(flags[0].item()):
+            break
+        itn += 1
+        halo_exchange(A, v)
+        check(lib.pgb_mr_step_spmv(n, A.indptr.data_ptr(), idx64, A.indices.data_ptr(), A.data.data_ptr(),
+                                   v.data_ptr(), y.data_ptr(), r1.data_ptr(), itn, tpr, sp, _stream()))
+        allreduce(0, 1)
+        check(lib.pgb_mr_step_c(n, y.data_ptr(), r2.data_ptr(), sp, _stream()))
+        allreduce(1, 2)
+        old_r1 = r1
+        r1, r2 = r2, y
+        y = spare if old_r1 is r1 else old_r1
+        check(lib.pgb_mr_step_scalars(itn, 0, sp, _stream()))
+        check(lib.pgb_mr_step_d(n, v.data_ptr(), w_old.data_ptr(), w_new.data_ptr(), r2.data_ptr(), x.data_ptr(),
+                                sp, _stream()))
+        allreduce(2, 3)
+        w_old, w_new = w_new, w_old
+    check(lib.pgb_mr_step_scalars(itn + 1, 1, sp, _stream()))
+    it_h, st_h = C.c_int(0), C.c_int(0)
+    check(lib.pgb_mr_state(sp, C.byref(it_h), C.byref(st_h), _stream()))
+    k = it_h.value
+    hist = hist_d[1: k + 1].cpu().numpy()
+    return x[:n], (int(maxiter) if st_h.value == 6 else 0), k, hist
+
+
+def assemble_darcy_slab(sd: SimplexGrid, data=None, keyword="unitary_data", group=None) -> DistCSR:
+    """Owned rows of the symmetrised mixed-Darcy system [[M, -B^T], [-B, 0]] on this rank's slab."""
+    from . import darcy
+
+    A = darcy.darcy_saddle_device(sd, data, keyword)
+    return build_dist_csr(A.indptr, A.indices, A.data, owned_mask(sd, "darcy"), global_keys(sd, "darcy"), group)
 
 
 def dist_cg_host(A: DistCSR, b: torch.Tensor, *, rtol=1e-5, atol=0.0, maxiter=1000):

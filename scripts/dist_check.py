@@ -87,6 +87,38 @@ xm, infom, km, histm = pd.dist_cg(DS, bg[go].contiguous(), rtol=1e-14, maxiter=7
 assert infom == 7 and km == 7 and len(histm) == 8
 if rank == 0:
     print(f"dist_cg: {k} iterations (single GPU {info1.iterations}), max rel diff {err:.1e}")
+# distributed MINRES on the symmetrised Darcy saddle system vs the single-GPU MINRES
+from pygeon_b200.solvers import minres_device
+
+DD = pd.assemble_darcy_slab(sd)
+A1 = pg.darcy_saddle_device(full)
+nf, ncg = full.num_faces, full.num_cells
+bg = torch.from_numpy(np.random.default_rng(1).normal(size=nf + ncg)).to(dev)
+keysd = DD.owned_keys.cpu()
+isf = keysd < (1 << 60)
+god = torch.empty(keysd.numel(), dtype=torch.int64)
+god[isf] = torch.searchsorted(full._structured["face_keys"], keysd[isf])
+god[~isf] = nf + (keysd[~isf] - (1 << 60))
+god = god.to(dev)
+cnt = torch.tensor([DD.n_owned], device=dev)
+dist.all_reduce(cnt)
+assert int(cnt.item()) == nf + ncg
+x1, i1 = minres_device(A1, bg, rtol=1e-9, maxiter=4000)
+xd, infod, kd, histd = pd.dist_minres(DD, bg[god].contiguous(), rtol=1e-9, maxiter=4000)
+assert infod == i1.info == 0, (infod, i1.info)
+assert abs(kd - i1.iterations) <= max(3, i1.iterations // 50), (kd, i1.iterations)
+mm = min(30, kd, i1.iterations)
+assert np.abs(histd[:mm] - i1.residuals[:mm]).max() <= 1e-9 * i1.residuals[0]
+# residual of the distributed solution measured with the single-GPU operator
+xfull = torch.zeros(nf + ncg, dtype=torch.float64, device=dev)
+xfull[god] = xd
+dist.all_reduce(xfull)
+A1s = sps.csr_array((A1.data.cpu().numpy(), A1.indices.cpu().numpy(), A1.indptr.cpu().numpy()), shape=A1.shape)
+res_d = np.linalg.norm(bg.cpu().numpy() - A1s @ xfull.cpu().numpy())
+res_1 = np.linalg.norm(bg.cpu().numpy() - A1s @ x1.cpu().numpy())
+assert res_d <= 10 * max(res_1, 1e-9 * float(bg.norm())), (res_d, res_1)
+if rank == 0:
+    print(f"dist_minres: {kd} iterations (single GPU {i1.iterations}), residual {res_d:.2e} vs {res_1:.2e}")
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:

@@ -369,7 +369,7 @@ def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
         if mode == 1:
             _lib.count(((2 * bits + 7) // 8) * 5 + 3)
         else:
-            _lib.count(((bits + 7) // 8) * 5 + 6)
+            _lib.count(((bits + 7) // 8) * 5 + 7)
         del ws
     plan = CsrPlan(n_rows, n_coo, nnz, perm, seg, indptr, indices)
     pack.plans[key] = plan

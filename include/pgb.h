@@ -95,10 +95,15 @@ enum {
   PGB_RT0_DIVDIV = 8,   /* RT0 stiff = cell_faces diag(w/|c|) cell_faces^T (hdiv.py:177-192 via
                            discretization.py:154-183); also Nedelec0 stiff in 2D     L = d+1 */
   PGB_BDM1_DIVDIV = 9,  /* BDM1 stiff, div = div_RT0 @ hstack([I]*d)/d (hdiv.py:353-371)  L = d(d+1) */
-  PGB_DARCY_SADDLE = 10 /* symmetrised mixed-Darcy block system [[M, -B^T], [-B, 0]] with M = RT0 mass,
+  PGB_DARCY_SADDLE = 10, /* symmetrised mixed-Darcy block system [[M, -B^T], [-B, 0]] with M = RT0 mass,
                            B = P0mass @ div (tutorials/fluid_flow/darcy.ipynb cell 10,
                            tests/patch_tests/test_laplacian_mixed.py:50), assembled in one pass:
                            local dofs = (faces of the cell, num_faces + cell)        L = d+2 */
+  PGB_L1_LUMPED = 11,   /* Lagrange1.assemble_lumped_matrix (discretization.py:91-110 with the lumped
+                           broken-P1 mass eye/(d+1), l2.py:472-483): diag w|c|/(d+1)  L = d+1 */
+  PGB_RT0_LUMPED = 12,  /* RT0.assemble_lumped_matrix (hdiv.py:140-175): diag sum_c (dist^T K dist)/|dist|
+                           / |f|, dist = face centre - cell centre                   L = d+1 */
+  PGB_BDM1_LUMPED = 13  /* BDM1 lumped: w|c| delta_jl/(d+1) t_aj^T K t_bl            L = d(d+1) */
 };
 int pgb_local_size(int kind, int dim); /* L */
 int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,

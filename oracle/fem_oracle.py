@@ -449,7 +449,75 @@ def local_bdm1_divdiv(sd, tabs, w, K):
     return A, dofs
 
 
+def local_lagrange1_lumped(sd, tabs, w, K):
+    """Pi^T kron(eye/(d+1), diag(|c| w)) Pi (discretization.py:91-110, l2.py:472-483): diag w|c|/(d+1)."""
+    d = sd.dim
+    _, vol, _ = local_geometry(sd, tabs)
+    return (w * vol)[:, None, None] * (np.eye(d + 1) / (d + 1))[None], tabs["opp"]
+
+
+def local_rt0_lumped(sd, tabs, w, K):
+    """RT0.assemble_lumped_matrix (hdiv.py:140-175): L_ff = sum_c (dist^T K dist)/|dist| / |f|,
+    dist = face centre - cell centre, K = the stored 3x3 tensor (unrotated, as in the reference)."""
+    d, nc = sd.dim, sd.num_cells
+    x = sd.nodes.T  # (nn, 3) ambient coordinates, as the reference uses face_centers / cell_centers
+    X = x[tabs["opp"]]  # (nc, d+1, 3)
+    cc = X.mean(axis=1)
+    A = np.zeros((nc, d + 1, d + 1))
+    for a in range(d + 1):
+        others = [t for t in range(d + 1) if t != a]
+        P = X[:, others, :]
+        dist = P.mean(axis=1) - cc
+        if d == 3:
+            area = 0.5 * np.linalg.norm(np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]), axis=1)
+        else:
+            area = np.linalg.norm(P[:, 1] - P[:, 0], axis=1)
+        q = np.einsum("ci,ijc,cj->c", dist, K, dist)
+        nd = np.linalg.norm(dist, axis=1)
+        A[:, a, a] = np.where(nd > 0, q / np.where(nd > 0, nd, 1.0), 0.0) / area
+    return A, tabs["faces"]
+
+
+def local_bdm1_lumped(sd, tabs, w, K):
+    """BDM1 lumped mass: Pi^T (kron(I_d, lumped P1) W(K)) Pi: w|c| delta_jl/(d+1) t_aj^T K t_bl."""
+    d = sd.dim
+    A, dofs = local_bdm1_mass(sd, tabs, w, K)
+    fnodes = tabs["fnodes"]
+    js = (fnodes[:, :, :, None] == tabs["opp"][:, None, None, :]).argmax(axis=3).reshape(sd.num_cells, -1)
+    same = js[:, :, None] == js[:, None, :]
+    # undo Mhat (2 on the diagonal blocks j == l, 1 elsewhere), apply delta_jl/(d+1)
+    return np.where(same, A / 2.0 * (d + 2), 0.0), dofs
+
+
+def port_lumped(space: str, sd, data=None, keyword="unitary_data", tabs=None):
+    """The reference's route: Pi.T @ M_lumped @ Pi (discretization.py:91-136); RT0 / Nedelec0 overrides."""
+    tabs = tabs or cell_tables(sd)
+    w, K = cell_data(sd, data, keyword)
+    d = sd.dim
+    if space == "rt0":
+        A, dofs = local_rt0_lumped(sd, tabs, w, K)
+        diag = np.zeros(sd.num_faces)
+        np.add.at(diag, dofs.ravel(), np.einsum("caa->ca", A).ravel())
+        return sps.diags_array(diag).tocsc()
+    if space == "nedelec0":
+        return sps.diags_array(np.asarray(port_mass(space, sd, data, keyword, tabs).sum(axis=0)).ravel()).tocsc()
+    lump = sps.kron(np.eye(d + 1) / (d + 1), sps.diags_array(sd.cell_volumes * w)).tocsc()
+    Pi = _PROJ[space](sd, tabs)
+    if space == "lagrange1":
+        M = lump
+    else:
+        R = np.asarray(sd.rotation_matrix, dtype=float)
+        Kr = np.tensordot(R.T, np.tensordot(R, K, (1, 0)), (0, 1))
+        tiled = np.tile(Kr, d + 1)
+        W = sps.block_array([[sps.diags_array(tiled[i, j]) for j in range(d)] for i in range(d)]).tocsc()
+        M = sps.kron(sps.eye_array(d), lump).tocsc() @ W
+    return (Pi.T @ M @ Pi).tocsc()
+
+
 _LOCAL = {
+    ("lagrange1", "lumped"): local_lagrange1_lumped,
+    ("rt0", "lumped"): local_rt0_lumped,
+    ("bdm1", "lumped"): local_bdm1_lumped,
     ("rt0", "stiff"): local_rt0_divdiv,
     ("bdm1", "stiff"): local_bdm1_divdiv,
     ("lagrange1", "mass"): local_lagrange1_mass,

@@ -39,6 +39,7 @@ FORMS = [
     ("lagrange1", "mass"), ("lagrange1", "stiff"), ("lagrange1", "gradgrad"),
     ("rt0", "mass"), ("rt0", "stiff"), ("bdm1", "mass"), ("bdm1", "stiff"),
     ("nedelec0", "mass"), ("nedelec0", "stiff"),
+    ("lagrange1", "lumped"), ("rt0", "lumped"), ("bdm1", "lumped"),
 ]
 
 
@@ -87,6 +88,9 @@ def main():
             if form == "mass":
                 ref = d.assemble_mass_matrix(g, data)
                 pat = fo.closed_form(space, "mass", g, data, "key", tabs)
+            elif form == "lumped":
+                ref = d.assemble_lumped_matrix(g, data)
+                pat = fo.closed_form(space, "lumped", g, data, "key", tabs)
             elif form == "gradgrad":
                 ref = d.assemble_grad_grad_matrix(g, data)
                 pat = fo.closed_form(space, "stiff", g, data, "key", tabs, rot2d=False)
@@ -99,6 +103,7 @@ def main():
             store[key + "_indices"] = refS.indices.astype(np.int32)
             store[key + "_data"] = refS.data
             store[key + "_refnnz"] = sps.csr_array(ref).nnz
+        store["nedelec0_lumped_diag"] = pg.Nedelec0("key").assemble_lumped_matrix(g, data).diagonal()
         d0 = pg.PwConstants("key").assemble_mass_matrix(g, data)
         store["p0_mass_diag"] = d0.diagonal()
         path = os.path.join(out_dir, name + ".npz")

@@ -31,6 +31,10 @@ def __getattr__(name):
         from . import darcy as _dz
 
         return getattr(_dz, name)
+    if name in ("DeviceLinearSystem",):
+        from . import device_system as _ds
+
+        return getattr(_ds, name)
     if name in ("DeviceCSR",):
         from . import engine as _e
 

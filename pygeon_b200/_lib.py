@@ -78,6 +78,9 @@ KIND = {
     "rt0_divdiv": 8,
     "bdm1_divdiv": 9,
     "darcy_saddle": 10,
+    "l1_lumped": 11,
+    "rt0_lumped": 12,
+    "bdm1_lumped": 13,
 }
 NPART = 1184
 

@@ -195,7 +195,7 @@ __device__ __forceinline__ void pair3(int e, int& p, int& q) {
 
 template <int KIND, int D>
 struct LocalSize {
-  static constexpr int L = (KIND == PGB_BDM1_MASS || KIND == PGB_BDM1_DIVDIV)   ? D * (D + 1)
+  static constexpr int L = (KIND == PGB_BDM1_MASS || KIND == PGB_BDM1_DIVDIV || KIND == PGB_BDM1_LUMPED) ? D * (D + 1)
                            : (KIND == PGB_N0_MASS || KIND == PGB_N0_CURLCURL) ? D * (D + 1) / 2
                            : (KIND == PGB_P0_MASS)                            ? 1
                            : (KIND == PGB_DARCY_SADDLE)                       ? D + 2
@@ -246,6 +246,63 @@ __global__ void __launch_bounds__(BLOCK) k_local(Params p) {
         emit((D + 1) * L + a, ba);
       }
       emit((D + 1) * L + (D + 1), 0.0);
+    } else if constexpr (KIND == PGB_L1_LUMPED) {
+      double wv = w * g.vol / (D + 1);
+#pragma unroll
+      for (int a = 0; a <= D; ++a)
+#pragma unroll
+        for (int b = 0; b <= D; ++b) emit(a * L + b, a == b ? wv : 0.0);
+    } else if constexpr (KIND == PGB_RT0_LUMPED) {
+      // face slot a = the face opposite node a: centre = mean of the other nodes, measure from them
+      double cc[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double m = 0;
+#pragma unroll
+        for (int t = 0; t <= D; ++t) m += g.X[t][i];
+        cc[i] = m / (D + 1);
+      }
+#pragma unroll
+      for (int a = 0; a <= D; ++a) {
+        double dist[D], o[D][D];  // o: the D nodes of the face
+        int k = 0;
+#pragma unroll
+        for (int t = 0; t <= D; ++t) {
+          if (t != a) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) o[k][i] = g.X[t][i];
+            ++k;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          double fc = 0;
+#pragma unroll
+          for (int t = 0; t < D; ++t) fc += o[t][i];
+          dist[i] = fc / D - cc[i];
+        }
+        double area;
+        if constexpr (D == 3) {
+          double u[3] = {o[1][0] - o[0][0], o[1][1] - o[0][1], o[1][2] - o[0][2]};
+          double v[3] = {o[2][0] - o[0][0], o[2][1] - o[0][1], o[2][2] - o[0][2]};
+          double cx = u[1] * v[2] - u[2] * v[1], cy = u[2] * v[0] - u[0] * v[2], cz = u[0] * v[1] - u[1] * v[0];
+          area = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+        } else {
+          double ux = o[1][0] - o[0][0], uy = o[1][1] - o[0][1];
+          area = sqrt(ux * ux + uy * uy);
+        }
+        double q = 0, nd = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          nd += dist[i] * dist[i];
+#pragma unroll
+          for (int j = 0; j < D; ++j) q += dist[i] * (HAS_K ? Kr[i][j] : (i == j ? 1.0 : 0.0)) * dist[j];
+        }
+        nd = sqrt(nd);
+        double val = (nd > 0.0) ? q / nd / area : 0.0;
+#pragma unroll
+        for (int b = 0; b <= D; ++b) emit(a * L + b, a == b ? val : 0.0);
+      }
     } else if constexpr (KIND == PGB_RT0_DIVDIV) {
       unsigned sb = p.sign_bits[c];
       double wv = w / g.vol;
@@ -344,7 +401,7 @@ __global__ void __launch_bounds__(BLOCK) k_local(Params p) {
           }
         }
       }
-    } else if constexpr (KIND == PGB_BDM1_MASS) {
+    } else if constexpr (KIND == PGB_BDM1_MASS || KIND == PGB_BDM1_LUMPED) {
       unsigned bits = p.aux_bits[c];
       unsigned sb = p.sign_bits[c];
       double T[L][D], KT[L][D];
@@ -374,6 +431,7 @@ __global__ void __launch_bounds__(BLOCK) k_local(Params p) {
 #pragma unroll
         for (int q = 0; q < L; ++q) {
           double m = (js[r] == js[q]) ? 2.0 * base : base;
+          if constexpr (KIND == PGB_BDM1_LUMPED) m = (js[r] == js[q]) ? 1.0 / (D + 1) : 0.0;
           emit(r * L + q, wv * m * dotd<D>(T[r], KT[q]));
         }
     }
@@ -417,6 +475,9 @@ int dispatch(int kind, const Params& p, cudaStream_t s) {
     case PGB_RT0_DIVDIV: return launch<PGB_RT0_DIVDIV, D>(p, s);
     case PGB_BDM1_DIVDIV: return launch<PGB_BDM1_DIVDIV, D>(p, s);
     case PGB_DARCY_SADDLE: return launch<PGB_DARCY_SADDLE, D>(p, s);
+    case PGB_L1_LUMPED: return launch<PGB_L1_LUMPED, D>(p, s);
+    case PGB_RT0_LUMPED: return launch<PGB_RT0_LUMPED, D>(p, s);
+    case PGB_BDM1_LUMPED: return launch<PGB_BDM1_LUMPED, D>(p, s);
   }
   pgb_set_error("pgb_local_matrices: unknown kind %d", kind);
   return 2;
@@ -427,6 +488,7 @@ int dispatch(int kind, const Params& p, cudaStream_t s) {
 extern "C" int pgb_local_size(int kind, int dim) {
   switch (kind) {
     case PGB_BDM1_MASS:
+    case PGB_BDM1_LUMPED:
     case PGB_BDM1_DIVDIV: return dim * (dim + 1);
     case PGB_N0_MASS:
     case PGB_N0_CURLCURL: return dim * (dim + 1) / 2;
@@ -443,9 +505,10 @@ extern "C" int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* 
   PGB_REQUIRE(dim == 2 || dim == 3, "pgb_local_matrices: dim must be 2 or 3");
   PGB_REQUIRE(cell_nodes && coords && vals, "pgb_local_matrices: null pointer");
   if (kind == PGB_RT0_MASS || kind == PGB_BDM1_MASS || kind == PGB_N0_CURLCURL ||
-      kind == PGB_RT0_DIVDIV || kind == PGB_BDM1_DIVDIV || kind == PGB_DARCY_SADDLE)
+      kind == PGB_RT0_DIVDIV || kind == PGB_BDM1_DIVDIV || kind == PGB_DARCY_SADDLE || kind == PGB_BDM1_LUMPED)
     PGB_REQUIRE(sign_bits, "pgb_local_matrices: sign_bits required");
-  if (kind == PGB_BDM1_MASS || kind == PGB_N0_MASS || (kind == PGB_N0_CURLCURL && dim == 3))
+  if (kind == PGB_BDM1_MASS || kind == PGB_BDM1_LUMPED || kind == PGB_N0_MASS ||
+      (kind == PGB_N0_CURLCURL && dim == 3))
     PGB_REQUIRE(aux_bits, "pgb_local_matrices: aux_bits required");
   if (nc == 0) return 0;
   Params p;

@@ -66,6 +66,24 @@ class Discretization(abc.ABC):
             return sps.csc_array((0, 0))
         return self.assemble_mass_matrix_device(sd, data).to_scipy("csc")
 
+    # ---- lumped mass -------------------------------------------------------------------
+    _lumped_diagonal = True
+
+    def assemble_lumped_matrix_device(self, sd, data: dict | None = None) -> engine.DeviceCSR:
+        w, K = self._coefficients(sd, data)
+        if self.tensor_order == SCALAR:
+            K = None
+        return engine.assemble_device(self._space, "lumped", sd, w, K)
+
+    def assemble_lumped_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
+        """Lumped mass (``discretization.py:91-110``; ``RT0`` override ``fem/hdiv.py:140-175``)."""
+        if self.ndof(sd) == 0:
+            return sps.csc_array((0, 0))
+        A = self.assemble_lumped_matrix_device(sd, data)
+        if self._lumped_diagonal:
+            return sps.diags_array(A.diagonal().cpu().numpy()).tocsc()
+        return A.to_scipy("csc")
+
     # ---- stiffness ---------------------------------------------------------------------
     def _stiff_form(self, sd) -> str:
         return "stiff"
@@ -194,6 +212,8 @@ class BDM1(Discretization):
     poly_order = 1
     tensor_order = VECTOR
     _space = "bdm1"
+
+    _lumped_diagonal = False  # couples the d dofs that sit at the same node of a cell
 
     def ndof(self, sd) -> int:
         return sd.face_nodes.nnz

@@ -313,6 +313,16 @@ class DeviceCSR:
         ip, ix, da = _to_host([self.indptr, self.indices, self.data])
         return cls((da, ix, ip), shape=self.shape)
 
+    def diagonal(self) -> torch.Tensor:
+        """Diagonal entries (every row of the structural patterns built here has one)."""
+        n = self.shape[0]
+        counts = (self.indptr[1:] - self.indptr[:-1]).to(torch.int64)
+        row_of = torch.repeat_interleave(torch.arange(n, device=self.data.device), counts)
+        mask = self.indices.to(torch.int64) == row_of
+        out = torch.zeros(n, dtype=torch.float64, device=self.data.device)
+        out[row_of[mask]] = self.data[mask]
+        return out
+
     @staticmethod
     def from_scipy(A, device=None) -> "DeviceCSR":
         dev = _device(device)
@@ -388,6 +398,9 @@ _FORMS = {
     ("rt0", "stiff"): "rt0_divdiv",
     ("bdm1", "stiff"): "bdm1_divdiv",
     ("darcy", "saddle"): "darcy_saddle",
+    ("lagrange1", "lumped"): "l1_lumped",
+    ("rt0", "lumped"): "rt0_lumped",
+    ("bdm1", "lumped"): "bdm1_lumped",
 }
 
 
@@ -398,7 +411,7 @@ def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None) -> torch
     aux = None
     if kind in ("n0_mass",) or (kind == "n0_curlcurl" and d == 3):
         aux = pack.edges()[1]
-    elif kind == "bdm1_mass":
+    elif kind in ("bdm1_mass", "bdm1_lumped"):
         aux = pack.bdm1()[1]
     with torch.cuda.device(dev):
         vals = out if out is not None else torch.empty((nc, L * L), dtype=torch.float64, device=dev)

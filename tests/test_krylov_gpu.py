@@ -176,3 +176,28 @@ def test_linear_system_multi_rhs():
     ls2.flag_ess_bc(sd.tags["domain_boundary_nodes"], np.zeros(n))
     x = ls2.solve(pg.cg_solver(rtol=1e-12))
     assert x.shape == (n, 2) and np.allclose(x[:, 1], 2 * x[:, 0], rtol=1e-9, atol=1e-12)
+
+
+def test_device_linear_system_matches_host():
+    """Assemble -> essential BC elimination -> CG entirely on the device equals the host
+    LinearSystem route (numerics/linear_system.py:64-94)."""
+    sd = pg.structured_grid(3, 7, perturb=0.1)
+    sd.compute_geometry()
+    A = pg.Lagrange1().assemble_stiff_matrix(sd)
+    Ad = pg.Lagrange1().assemble_stiff_matrix_device(sd)
+    rng = np.random.default_rng(3)
+    b = rng.normal(size=sd.num_nodes)
+    bd = sd.tags["domain_boundary_nodes"]
+    vals = rng.normal(size=sd.num_nodes)
+    ls = pg.LinearSystem(A, b)
+    ls.flag_ess_bc(bd, vals)
+    x_host = ls.solve()
+    dls = pg.DeviceLinearSystem(Ad, b)
+    dls.flag_ess_bc(bd, vals)
+    A0, b0, keep = dls.reduce_system()
+    A0h, b0h, _ = ls.reduce_system()
+    A0s = sps.csr_array((A0.data.cpu().numpy(), A0.indices.cpu().numpy(), A0.indptr.cpu().numpy()), shape=A0.shape)
+    assert abs(A0s - sps.csr_array(A0h)).max() <= 1e-14 * abs(A0h).max()
+    assert np.abs(b0.cpu().numpy() - b0h).max() <= 1e-13 * np.abs(b0h).max()
+    x, info = dls.solve("cg", rtol=1e-13, maxiter=2000)
+    assert info.info == 0 and np.abs(x.cpu().numpy() - x_host).max() <= 1e-9 * np.abs(x_host).max()

@@ -339,6 +339,8 @@ class DeviceCSR:
 
 
 symbolic_mode = 0  # 0 = two-level (default), 1 = full (row,col) radix sort; see include/pgb.h
+force_idx64 = False  # tests: emit int64 indptr even when nnz < 2^31
+overlap_streams = False  # optional: run K1 on a side stream next to the symbolic phase (no measurable gain on B200: both kernels fill the SMs)
 
 
 def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
@@ -368,7 +370,7 @@ def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
             check(rc)
             break
         nnz = int(nnz.value)
-        it = torch.int64 if nnz >= 2**31 else _I32
+        it = torch.int64 if (nnz >= 2**31 or force_idx64) else _I32
         indptr = torch.empty((n_rows + 1,), dtype=it, device=dev)
         indices = torch.empty((nnz,), dtype=_I32, device=dev)
         seg = torch.empty((nnz + 1,), dtype=_I32, device=dev)
@@ -460,6 +462,42 @@ def clear_cache(sd) -> None:
         delattr(sd, _CACHE_ATTR)
 
 
+_SIDE: dict = {}
+
+
+def assemble_on_pack(pack: GridPack, space: str, kind: str, wd=None, Kd=None):
+    """symbolic (cached per pack) + K1 + K2 numeric.  When the plan still has to be built, K1 - a
+    pure HBM streaming kernel - runs on a side stream concurrently with the symbolic phase, whose
+    dominant kernel (the per-row register sort) is issue bound and leaves the memory system idle."""
+    dev = pack.device
+    cached = ("plan", space) in pack.plans
+    if cached or not overlap_streams:
+        plan = symbolic(pack, space)
+        vals = local_matrices(pack, kind, wd, Kd)
+        return plan, numeric(plan, vals)
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream()
+        side = _SIDE.get(dev)
+        if side is None:
+            side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+        if kind in ("n0_mass", "n0_curlcurl"):
+            pack.edges()  # aux tables must exist before the side stream reads them
+        elif kind in ("bdm1_mass", "bdm1_lumped"):
+            pack.bdm1()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            vals = local_matrices(pack, kind, wd, Kd)
+            done = torch.cuda.Event()
+            done.record(side)
+        plan = symbolic(pack, space)
+        main.wait_event(done)
+        vals.record_stream(main)
+        data = numeric(plan, vals)
+    return plan, data
+
+
 def assemble_device(space: str, form: str, sd, w=None, K=None, device=None) -> DeviceCSR:
     """Full assembly on the device: pack (cached) -> K1 -> K2.  ``w``/``K`` are host numpy
     arrays in the reference's layout or None."""
@@ -468,9 +506,7 @@ def assemble_device(space: str, form: str, sd, w=None, K=None, device=None) -> D
     kind = _FORMS[(space, form)]
     wd = None if w is None else _to_dev(w, dev)
     Kd = None if K is None else _to_dev(K, dev)
-    plan = symbolic(pack, space)
-    vals = local_matrices(pack, kind, wd, Kd)
-    data = numeric(plan, vals)
+    plan, data = assemble_on_pack(pack, space, kind, wd, Kd)
     n = plan.n_rows
     return DeviceCSR((n, n), plan.indptr, plan.indices, data)
 

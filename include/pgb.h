@@ -164,11 +164,12 @@ int pgb_cg(int64_t n, const void* indptr, int idx64, const int32_t* indices, con
            const double* b, double* x, const double* dinv, double rtol, double atol, int maxiter,
            double* work, int* iters_host, int* info_host, double* resid_host, void* stream);
 
-/* Whole MINRES solve (Paige-Saunders as in scipy).  work: 6*n doubles. */
+/* Whole MINRES solve (Paige-Saunders as in scipy).  work: 6*n doubles.  dinv: optional positive
+ * diagonal preconditioner (the `M` of scipy.sparse.linalg.minres as an inverse diagonal) or NULL. */
 int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_t* indices,
-               const double* data, const double* b, double* x, double shift, double rtol,
-               int maxiter, double* work, int* iters_host, int* info_host, double* resid_host,
-               void* stream);
+               const double* data, const double* b, double* x, const double* dinv, double shift,
+               double rtol, int maxiter, double* work, int* iters_host, int* info_host,
+               double* resid_host, void* stream);
 
 /* Building blocks used by the multi-GPU drivers (halo exchange / allreduce happen between
  * them on the host side through NCCL). */

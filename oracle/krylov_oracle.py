@@ -50,8 +50,8 @@ def cg(A, b, x0=None, *, rtol=1e-5, atol=0.0, maxiter=None, dinv=None):
     return x, maxiter, maxiter, np.array(hist)
 
 
-def minres(A, b, x0=None, *, rtol=1e-5, shift=0.0, maxiter=None):
-    """scipy.sparse.linalg.minres restated (no preconditioner); returns
+def minres(A, b, x0=None, *, rtol=1e-5, shift=0.0, maxiter=None, dinv=None):
+    """scipy.sparse.linalg.minres restated (optional inverse-diagonal preconditioner); returns
     (x, info, iterations, phibar history)."""
     b = np.asarray(b, dtype=float)
     n = b.size
@@ -59,8 +59,9 @@ def minres(A, b, x0=None, *, rtol=1e-5, shift=0.0, maxiter=None):
         maxiter = 5 * n
     eps = np.finfo(float).eps
     x = np.zeros(n) if x0 is None else np.array(x0, dtype=float)
+    psolve = (lambda r: r) if dinv is None else (lambda r: dinv * r)
     r1 = b.copy() if x0 is None else b - A @ x
-    y = r1
+    y = psolve(r1)
     beta1 = np.dot(r1, y)
     if beta1 == 0:
         return x, 0, 0, np.zeros(0)
@@ -85,6 +86,7 @@ def minres(A, b, x0=None, *, rtol=1e-5, shift=0.0, maxiter=None):
         alfa = np.dot(v, y)
         y = y - (alfa / beta) * r2
         r1, r2 = r2, y
+        y = psolve(r2)
         oldb = beta
         beta = np.sqrt(np.dot(r2, y))
         tnorm2 += alfa**2 + oldb**2 + beta**2

@@ -27,7 +27,7 @@ def __getattr__(name):
         from . import solvers as _s
 
         return getattr(_s, name)
-    if name in ("darcy_saddle_device", "darcy_saddle_matrix"):
+    if name in ("darcy_saddle_device", "darcy_saddle_matrix", "darcy_block_jacobi"):
         from . import darcy as _dz
 
         return getattr(_dz, name)

@@ -39,7 +39,7 @@ _SIGS = {
     "pgb_csr_numeric": (_i, [_l, _p, _p, _p, _p, _p]),
     "pgb_spmv": (_i, [_l, _p, _i, _p, _p, _p, _p, _i, _p]),
     "pgb_cg": (_i, [_l, _p, _i, _p, _p, _p, _p, _p, _d, _d, _i, _p, C.POINTER(_i), C.POINTER(_i), _p, _p]),
-    "pgb_minres": (_i, [_l, _p, _i, _p, _p, _p, _p, _d, _d, _i, _p, C.POINTER(_i), C.POINTER(_i), _p, _p]),
+    "pgb_minres": (_i, [_l, _p, _i, _p, _p, _p, _p, _p, _d, _d, _i, _p, C.POINTER(_i), C.POINTER(_i), _p, _p]),
     "pgb_cg_scratch_doubles": (_l, [_i]),
     "pgb_cg_step_init": (_i, [_l, _p, _p, _p, _p, _d, _d, _p, _p]),
     "pgb_cg_step_reduce": (_i, [_p, _i, _i, _p]),

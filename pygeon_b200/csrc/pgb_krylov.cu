@@ -666,14 +666,13 @@ extern "C" int pgb_cg(int64_t n, const void* indptr, int idx64, const int32_t* i
 }
 
 extern "C" int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_t* indices,
-                          const double* data, const double* b, double* x, double shift, double rtol,
-                          int maxiter, double* work, int* iters_host, int* info_host,
+                          const double* data, const double* b, double* x, const double* dinv, double shift,
+                          double rtol, int maxiter, double* work, int* iters_host, int* info_host,
                           double* resid_host, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   PGB_REQUIRE(n > 0 && maxiter >= 0, "pgb_minres: bad arguments");
   if (ensure_scratch(maxiter)) return 1;
   Scratch& S = g_scr;
-  const double* dinv = nullptr;
   double* v = work;
   double* rb[3] = {work + n, work + 2 * n, work + 3 * n};  // r1, r2, y rotate
   double* wb[2] = {work + 4 * n, work + 5 * n};

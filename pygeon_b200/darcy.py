@@ -33,3 +33,22 @@ def darcy_saddle_matrix(sd, data: dict | None = None, keyword: str = UNITARY_DAT
     """Host copy (CSC).  For non-symmetric tensors the CSR arrays are reinterpreted as CSC exactly as
     for the mass matrices (see pgb.h, K1 note)."""
     return darcy_saddle_device(sd, data, keyword).to_scipy("csc")
+
+
+def darcy_block_jacobi(A: engine.DeviceCSR, num_faces: int):
+    """Inverse diagonal of the SPD block preconditioner diag(diag(M), diag(B diag(M)^-1 B^T)) for
+    the symmetrised saddle system (the natural scaling fix for SURVEY.md H5: ``B`` has entries
+    +-1/|c|, so unpreconditioned MINRES stagnates).  Index bookkeeping with torch, device resident."""
+    import torch
+
+    n = A.shape[0]
+    dev = A.data.device
+    d = A.diagonal()
+    du = d[:num_faces]
+    counts = (A.indptr[1:] - A.indptr[:-1]).to(torch.int64)
+    row_of = torch.repeat_interleave(torch.arange(n, device=dev), counts)
+    cols = A.indices.to(torch.int64)
+    sel = (row_of >= num_faces) & (cols < num_faces)  # entries of -B
+    dp = torch.zeros(n - num_faces, dtype=torch.float64, device=dev)
+    dp.index_add_(0, row_of[sel] - num_faces, A.data[sel] ** 2 / du[cols[sel]])
+    return 1.0 / torch.cat([du, dp])

@@ -57,7 +57,7 @@ def cg_device(A: DeviceCSR, b: torch.Tensor, x0=None, *, rtol=1e-5, atol=0.0, ma
     return x, SolveInfo(k, info.value, resid[: k + 1].copy())
 
 
-def minres_device(A: DeviceCSR, b: torch.Tensor, x0=None, *, rtol=1e-5, shift=0.0, maxiter=None):
+def minres_device(A: DeviceCSR, b: torch.Tensor, x0=None, *, rtol=1e-5, shift=0.0, maxiter=None, dinv=None):
     n = A.shape[0]
     dev = b.device
     if maxiter is None:
@@ -68,7 +68,7 @@ def minres_device(A: DeviceCSR, b: torch.Tensor, x0=None, *, rtol=1e-5, shift=0.
         resid = np.zeros(maxiter + 1)
         it, info = C.c_int(0), C.c_int(0)
         check(lib.pgb_minres(n, A.indptr.data_ptr(), A.idx64, A.indices.data_ptr(), A.data.data_ptr(),
-                             b.data_ptr(), x.data_ptr(), float(shift), float(rtol), int(maxiter),
+                             b.data_ptr(), x.data_ptr(), _ptr(dinv), float(shift), float(rtol), int(maxiter),
                              work.data_ptr(), C.byref(it), C.byref(info), resid.ctypes.data, _stream()))
         _lib.count(5 + 4 * it.value)
     k = it.value
@@ -104,11 +104,13 @@ def cg(A, b, x0=None, *, rtol=1e-5, atol=0.0, maxiter=None, M=None, device=None)
     return x, (info.info if isinstance(info, SolveInfo) else max(i.info for i in info))
 
 
-def minres(A, b, x0=None, *, rtol=1e-5, shift=0.0, maxiter=None, device=None):
-    """Drop-in for ``scipy.sparse.linalg.minres(A, b, ...)`` -> ``(x, info)``."""
+def minres(A, b, x0=None, *, rtol=1e-5, shift=0.0, maxiter=None, M=None, device=None):
+    """Drop-in for ``scipy.sparse.linalg.minres(A, b, ...)`` -> ``(x, info)``.  ``M`` may be a 1-D
+    array / tensor holding a positive inverse diagonal (Jacobi-type preconditioner)."""
     dev = _device(device)
     x0d = None if x0 is None else _vec(x0, dev)
-    x, info = _columns(lambda Ad, bd: minres_device(Ad, bd, x0d, rtol=rtol, shift=shift, maxiter=maxiter),
+    dinv = None if M is None else _vec(M if isinstance(M, torch.Tensor) else np.asarray(M), dev)
+    x, info = _columns(lambda Ad, bd: minres_device(Ad, bd, x0d, rtol=rtol, shift=shift, maxiter=maxiter, dinv=dinv),
                        A, b, dev)
     minres.last_info = info
     return x, (info.info if isinstance(info, SolveInfo) else max(i.info for i in info))

@@ -201,3 +201,27 @@ def test_device_linear_system_matches_host():
     assert np.abs(b0.cpu().numpy() - b0h).max() <= 1e-13 * np.abs(b0h).max()
     x, info = dls.solve("cg", rtol=1e-13, maxiter=2000)
     assert info.info == 0 and np.abs(x.cpu().numpy() - x_host).max() <= 1e-9 * np.abs(x_host).max()
+
+
+@pytest.mark.parametrize("dim,n", [(2, 12), (3, 4)])
+def test_preconditioned_minres_darcy(dim, n):
+    """Block-Jacobi preconditioned MINRES on the one-pass saddle system: same recurrence as scipy's
+    minres with M (oracle), and far fewer iterations than without."""
+    sd = pg.structured_grid(dim, n, perturb=0.1)
+    sd.compute_geometry()
+    Ad = pg.darcy_saddle_device(sd)
+    dinv = pg.darcy_block_jacobi(Ad, sd.num_faces)
+    A = Ad.to_scipy("csr")
+    b = np.random.default_rng(2).normal(size=A.shape[0])
+    x_o, info_o, k_o, hist_o = ko.minres(A, b, rtol=1e-10, maxiter=20000, dinv=dinv.cpu().numpy())
+    x_g, info_g = pg.minres(Ad, b, rtol=1e-10, maxiter=20000, M=dinv)
+    si = pg.minres.last_info
+    assert info_g == info_o == 0
+    assert abs(si.iterations - k_o) <= max(3, k_o // 50)
+    m = min(si.iterations, k_o, 40)
+    assert np.abs(si.residuals[:m] - hist_o[:m]).max() <= 1e-9 * hist_o[0]
+    _, _ = pg.minres(Ad, b, rtol=1e-10, maxiter=20000)
+    assert pg.minres.last_info.iterations > 2 * si.iterations
+    r = np.linalg.norm(b - A @ x_g)
+    r_o = np.linalg.norm(b - A @ x_o)
+    assert r <= 10 * r_o  # MINRES stops on |r| <= rtol |A| |x|: compare with the oracle, not with |b|

@@ -45,10 +45,15 @@ def test_cg_oracle_vs_scipy(dim, n, jacobi):
 
 
 @pytest.mark.parametrize("dim,n", [(2, 6), (3, 3)])
-def test_minres_oracle_vs_scipy(dim, n):
+@pytest.mark.parametrize("precond", [False, True])
+def test_minres_oracle_vs_scipy(dim, n, precond):
     A, b = darcy(dim, n)
     its = []
-    xs, info_s = spla.minres(A, b, rtol=1e-9, maxiter=4000, callback=lambda xk: its.append(1))
-    x, info, k, hist = ko.minres(A, b, rtol=1e-9, maxiter=4000)
+    dinv, M = None, None
+    if precond:
+        dinv = 1.0 / np.where(A.diagonal() > 0, A.diagonal(), 1.0 + np.arange(A.shape[0]) % 3)
+        M = spla.LinearOperator(A.shape, matvec=lambda v: dinv * v)
+    xs, info_s = spla.minres(A, b, rtol=1e-9, maxiter=4000, M=M, callback=lambda xk: its.append(1))
+    x, info, k, hist = ko.minres(A, b, rtol=1e-9, maxiter=4000, dinv=dinv)
     assert info == info_s and k == len(its)
     assert np.allclose(x, xs, rtol=1e-10, atol=1e-12)

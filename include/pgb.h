@@ -47,6 +47,9 @@ const char* pgb_last_error(void);
 int pgb_pack_cells(int dim, int64_t nc, const int32_t* cf_idx, const int8_t* cf_sgn,
                    const int32_t* fn_idx, int32_t* cell_nodes, uint8_t* sign_bits,
                    int32_t* err_flag, void* stream);
+/* cf_sgn / sign_bits of pgb_pack_cells may be NULL; the sign bits can then be produced later by
+ * pgb_pack_signs (Lagrange1 never needs them, so cell_faces.data is not even uploaded). */
+int pgb_pack_signs(int dim, int64_t nc, const int8_t* cf_sgn, uint8_t* sign_bits, void* stream);
 
 /* BDM1 dofs (fem/hdiv.py:474-480): dof of (face slot a, pos) = f_a + pos*nf, pos = slot of
  * the node in face_nodes.indices of f_a.  cell_dofs [nc*d*(d+1)], jslot_bits[nc]: 2 bits per

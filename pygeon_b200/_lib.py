@@ -25,6 +25,7 @@ _SIGS = {
     "pgb_version": (_i, []),
     "pgb_last_error": (C.c_char_p, []),
     "pgb_pack_cells": (_i, [_i, _l, _p, _p, _p, _p, _p, _p, _p]),
+    "pgb_pack_signs": (_i, [_i, _l, _p, _p, _p]),
     "pgb_pack_bdm1": (_i, [_i, _l, _l, _p, _p, _p, _p, _p, _p]),
     "pgb_pack_edges3d": (_i, [_l, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pgb_pack_edges2d": (_i, [_l, _p, _p, _p, _p, _p]),

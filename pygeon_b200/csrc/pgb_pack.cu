@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) k_pack_cells(int64_t nc, const int32_t* _
 #pragma unroll
   for (int a = 0; a <= D; ++a) {
     f[a] = cf_idx[c * (D + 1) + a];
-    if (cf_sgn[c * (D + 1) + a] < 0) bits |= 1u << a;
+    if (cf_sgn && cf_sgn[c * (D + 1) + a] < 0) bits |= 1u << a;
   }
 #pragma unroll
   for (int a = 0; a <= D; ++a)
@@ -62,8 +62,21 @@ __global__ void __launch_bounds__(256) k_pack_cells(int64_t nc, const int32_t* _
     bad |= !found;
     cell_nodes[c * (D + 1) + a] = (int32_t)opp;
   }
-  sign_bits[c] = (uint8_t)bits;
+  if (sign_bits) sign_bits[c] = (uint8_t)bits;
   if (bad) *err_flag = 1;
+}
+
+// sign bits alone (spaces that do not need them, e.g. Lagrange1, never upload cell_faces.data)
+template <int D>
+__global__ void __launch_bounds__(256) k_pack_signs(int64_t nc, const int8_t* __restrict__ cf_sgn,
+                                                    uint8_t* __restrict__ sign_bits) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  unsigned bits = 0;
+#pragma unroll
+  for (int a = 0; a <= D; ++a)
+    if (cf_sgn[c * (D + 1) + a] < 0) bits |= 1u << a;
+  sign_bits[c] = (uint8_t)bits;
 }
 
 // ---- BDM1 dofs -----------------------------------------------------------------------------
@@ -215,6 +228,16 @@ extern "C" int pgb_pack_cells(int dim, int64_t nc, const int32_t* cf_idx, const 
     k_pack_cells<3><<<pgb_grid(nc, 256), 256, 0, s>>>(nc, cf_idx, cf_sgn, fn_idx, cell_nodes, sign_bits, err_flag);
   else
     k_pack_cells<2><<<pgb_grid(nc, 256), 256, 0, s>>>(nc, cf_idx, cf_sgn, fn_idx, cell_nodes, sign_bits, err_flag);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_pack_signs(int dim, int64_t nc, const int8_t* cf_sgn, uint8_t* sign_bits, void* stream) {
+  PGB_REQUIRE(dim == 2 || dim == 3, "pgb_pack_signs: dim must be 2 or 3");
+  if (nc == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dim == 3) k_pack_signs<3><<<pgb_grid(nc, 256), 256, 0, s>>>(nc, cf_sgn, sign_bits);
+  else k_pack_signs<2><<<pgb_grid(nc, 256), 256, 0, s>>>(nc, cf_sgn, sign_bits);
   PGB_LAUNCH_CHECK();
   return 0;
 }

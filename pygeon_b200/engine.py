@@ -44,36 +44,56 @@ def _to_dev(arr: np.ndarray, dev, dtype=None) -> torch.Tensor:
     return t
 
 
-_STAGING: dict = {}
+class _PinnedPool:
+    """Pinned host blocks for results.  A block is handed out as the memory of the numpy arrays
+    returned to the caller (who owns them: the block is not reused while any array derived from it
+    is alive) and comes back to the pool through a weakref finalizer.  Page-locking costs
+    ~0.5 ms/MB, so recycling blocks is what makes device->host run at PCIe speed; a pageable
+    ``.cpu()`` manages ~2 GB/s on this platform."""
+
+    GRAIN = 1 << 22  # 4 MiB size classes
+
+    def __init__(self):
+        self.free: dict = {}
+
+    def take(self, nbytes: int) -> torch.Tensor:
+        cls = max((int(nbytes) + self.GRAIN - 1) // self.GRAIN, 1) * self.GRAIN
+        lst = self.free.get(cls)
+        if lst:
+            return lst.pop()
+        return torch.empty(cls, dtype=torch.uint8).pin_memory()
+
+    def give(self, blk: torch.Tensor) -> None:
+        lst = self.free.setdefault(blk.numel(), [])
+        if len(lst) < 4:
+            lst.append(blk)
 
 
-def _staging(nbytes: int, dev) -> torch.Tensor:
-    """Persistent pinned host buffer (grown geometrically), one per device."""
-    buf = _STAGING.get(dev)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8).pin_memory()
-        _STAGING[dev] = buf
-    return buf
+_POOL = _PinnedPool()
 
 
 def _to_host(tensors) -> list:
-    """Device tensors -> fresh numpy arrays via the pinned staging buffer."""
+    """Device tensors -> numpy arrays owned by the caller, backed by recycled pinned blocks."""
+    import weakref
+
     dev = tensors[0].device
-    sizes = [t.numel() * t.element_size() for t in tensors]
-    offs = np.concatenate([[0], np.cumsum([(s + 255) // 256 * 256 for s in sizes])])
-    stage = _staging(int(offs[-1]), dev)
-    views = []
+    views, blocks = [], []
     with torch.cuda.device(dev):
-        for t, o, sz in zip(tensors, offs[:-1], sizes):
-            v = stage[int(o): int(o) + sz].view(t.dtype)
-            v.copy_(t.contiguous().view(-1), non_blocking=True)
-            views.append(v)
+        for t in tensors:
+            nbytes = t.numel() * t.element_size()
+            blk = _POOL.take(nbytes)
+            view = blk[:nbytes].view(t.dtype).view(t.shape)
+            view.copy_(t, non_blocking=True)
+            views.append(view)
+            blocks.append(blk)
         torch.cuda.current_stream().synchronize()
     out = []
-    for t, v in zip(tensors, views):
-        h = torch.empty(t.shape, dtype=t.dtype)
-        h.view(-1).copy_(v)  # multi-threaded host memcpy into caller-owned memory
-        out.append(h.numpy())
+    for view, blk in zip(views, blocks):
+        arr = view.numpy()
+        # arr.base is the tensor object numpy holds on to; every array derived from `arr` keeps
+        # `arr` (hence arr.base) alive, so the block returns to the pool only when all are gone
+        weakref.finalize(arr.base, _POOL.give, blk)
+        out.append(arr)
     return out
 
 
@@ -100,7 +120,7 @@ class RawGrid:
     device: torch.device
     R: np.ndarray
     cf_idx: torch.Tensor
-    cf_sgn: torch.Tensor
+    cf_sgn: torch.Tensor | None  # uploaded on demand (need_signs): Lagrange1 never reads it
     fn_idx: torch.Tensor
     nodes: torch.Tensor
     fr_idx: torch.Tensor | None = None
@@ -111,7 +131,7 @@ class RawGrid:
     h2d_bytes: int = 0
 
     @staticmethod
-    def upload(sd, device=None, ridges: bool = False) -> "RawGrid":
+    def upload(sd, device=None, ridges: bool = False, signs: bool = False) -> "RawGrid":
         dev = _device(device)
         d = int(sd.dim)
         if d not in (2, 3):
@@ -127,13 +147,23 @@ class RawGrid:
         with torch.cuda.device(dev):
             raw = RawGrid(
                 d, nc, nf, nn, nf if d == 2 else int(getattr(sd, "num_ridges", 0)), dev, R,
-                _to_dev(cf.indices, dev, _I32), _sign_i8(_to_dev(cf.data, dev)),
+                _to_dev(cf.indices, dev, _I32), None,
                 _to_dev(fn.indices, dev, _I32), _to_dev(nodes_h, dev), _sd=sd,
             )
-        raw.h2d_bytes = cf.indices.nbytes + cf.data.nbytes + fn.indices.nbytes + nodes_h.nbytes
+        raw.h2d_bytes = cf.indices.nbytes + fn.indices.nbytes + nodes_h.nbytes
+        if signs:
+            raw.need_signs()
         if ridges:
             raw.need_ridges()
         return raw
+
+    def need_signs(self) -> None:
+        if self.cf_sgn is not None:
+            return
+        data = self._sd.cell_faces.data
+        with torch.cuda.device(self.device):
+            self.cf_sgn = _sign_i8(_to_dev(data, self.device))
+        self.h2d_bytes += data.nbytes
 
     def need_ridges(self) -> None:
         if self.fr_idx is not None:
@@ -174,7 +204,7 @@ class GridPack:
     cf_idx: torch.Tensor
     fn_idx: torch.Tensor
     cell_nodes: torch.Tensor
-    sign_bits: torch.Tensor
+    _sign_bits: torch.Tensor | None = None
     _raw: object = None
     _edges: tuple | None = None
     _bdm1: tuple | None = None
@@ -195,12 +225,14 @@ class GridPack:
             coords = torch.empty((nn, 4 if d == 3 else 2), dtype=torch.float64, device=dev)
             check(lib.pgb_prep_coords(d, nn, raw.nodes.data_ptr(), raw.R.ctypes.data, coords.data_ptr(), s))
             cell_nodes = torch.empty((nc, d + 1), dtype=_I32, device=dev)
-            sign_bits = torch.empty((nc,), dtype=torch.uint8, device=dev)
+            sign_bits = None
+            if raw.cf_sgn is not None:
+                sign_bits = torch.empty((nc,), dtype=torch.uint8, device=dev)
             err = torch.zeros((1,), dtype=_I32, device=dev)
             check(
                 lib.pgb_pack_cells(
-                    d, nc, raw.cf_idx.data_ptr(), raw.cf_sgn.data_ptr(), raw.fn_idx.data_ptr(),
-                    cell_nodes.data_ptr(), sign_bits.data_ptr(), err.data_ptr(), s,
+                    d, nc, raw.cf_idx.data_ptr(), _ptr(raw.cf_sgn), raw.fn_idx.data_ptr(),
+                    cell_nodes.data_ptr(), _ptr(sign_bits), err.data_ptr(), s,
                 )
             )
             _lib.count(2)
@@ -208,6 +240,19 @@ class GridPack:
                 raise NotImplementedError("Grid is not simplicial; cannot compute opposite node.")
         return GridPack(d, nc, nf, nn, raw.ne, dev, raw.R, coords, raw.cf_idx, raw.fn_idx, cell_nodes,
                         sign_bits, _raw=raw)
+
+    @property
+    def sign_bits(self) -> torch.Tensor:
+        """bit a set <=> cell_faces sign of face slot a is -1 (uploads cell_faces.data on first use)."""
+        if self._sign_bits is None:
+            raw = self._raw
+            raw.need_signs()
+            with torch.cuda.device(self.device):
+                bits = torch.empty((self.nc,), dtype=torch.uint8, device=self.device)
+                check(lib.pgb_pack_signs(self.dim, self.nc, raw.cf_sgn.data_ptr(), bits.data_ptr(), _stream()))
+                _lib.count(1)
+            self._sign_bits = bits
+        return self._sign_bits
 
     # -- Nedelec0 tables ----------------------------------------------------------------
     def edges(self):
@@ -411,6 +456,9 @@ def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None) -> torch
     d, nc, dev = pack.dim, pack.nc, pack.device
     L = int(lib.pgb_local_size(KIND[kind], d))
     aux = None
+    needs_sign = kind in ("rt0_mass", "bdm1_mass", "bdm1_lumped", "n0_curlcurl", "rt0_divdiv", "bdm1_divdiv",
+                          "darcy_saddle")
+    sign_bits = pack.sign_bits if needs_sign else None
     if kind in ("n0_mass",) or (kind == "n0_curlcurl" and d == 3):
         aux = pack.edges()[1]
     elif kind in ("bdm1_mass", "bdm1_lumped"):
@@ -419,7 +467,7 @@ def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None) -> torch
         vals = out if out is not None else torch.empty((nc, L * L), dtype=torch.float64, device=dev)
         check(
             lib.pgb_local_matrices(
-                KIND[kind], d, nc, pack.cell_nodes.data_ptr(), pack.sign_bits.data_ptr(), _ptr(aux),
+                KIND[kind], d, nc, pack.cell_nodes.data_ptr(), _ptr(sign_bits), _ptr(aux),
                 pack.coords.data_ptr(), _ptr(K), pack.R.ctypes.data, _ptr(w), vals.data_ptr(), _stream(),
             )
         )

@@ -297,10 +297,12 @@ def run_ours(args):
     passes = (bits + 7) // 8  # radix passes of the incidence transpose (32-bit keys)
     n_inc = nc * 4
     b_local = nc * (16 + 128) + 32 * nn
-    b_numeric = n_coo * 12 + (nnz + 1) * 4 + nnz * 8
+    # row-gather numeric over the sliced-ELL plan: value 8 B + slot 1 B per COO entry, incidence id
+    # 4 B per L entries, slice pointers / indptr, data 8 B per entry
+    b_numeric = n_coo * 9 + n_inc * 4 + 8 * nn + nnz * 8
     b_sort_pass = n_inc * 16  # the scatter kernel moves each (key, payload) once in and once out
     # per-row sort: read sorted incidences + row offsets, write perm, unique cols / run starts
-    b_rowsort = n_inc * 4 + n_inc * 4 + 8 * nn + n_coo * 4 + nnz * 8  # + the cell->dof table, read once
+    b_rowsort = n_inc * 4 + n_inc * 4 + 8 * nn + n_coo * 1 + nnz * 4  # incidences + cell->dof table in, slots + unique cols out
     b_step_algo = nc * 16 + 32 * nn + n_coo * 0 + nnz * 12 + 4 * (nn + 1)  # read grid once, write CSR once
     kern = {
         "local_matrices": {"ms": wl, "gbs": b_local / wl / 1e6, "bytes": b_local},

@@ -319,13 +319,24 @@ class GridPack:
 # --------------------------------------------------------------------------------------
 @dataclass
 class CsrPlan:
+    """Result of the symbolic phase, reusable by every operator of a space on the grid.
+
+    mode 0 (two level): ``ell_ptr, ell_inc, ell_slots`` drive the row-gather numeric kernel;
+    mode 1 (full sort): ``perm, seg`` drive the segmented-reduce numeric kernel."""
+
     n_rows: int
     n_coo: int
     nnz: int
-    perm: torch.Tensor  # uint32 stored as int32
-    seg: torch.Tensor
+    L: int
+    mode: int
     indptr: torch.Tensor
     indices: torch.Tensor
+    perm: torch.Tensor | None = None  # mode 1: uint32 stored as int32
+    seg: torch.Tensor | None = None
+    ell_ptr: torch.Tensor | None = None  # mode 0: sliced-ELL transpose of the incidence lists
+    ell_inc: torch.Tensor | None = None
+    ell_slots: torch.Tensor | None = None
+    max_row_nnz: int = 0
 
 
 @dataclass
@@ -389,28 +400,35 @@ overlap_streams = False  # optional: run K1 on a side stream next to the symboli
 
 
 def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
-    """Sort-by-(row,col) of the cell->dof incidences: pattern + gather permutation."""
+    """Sort-by-(row,col) of the cell->dof incidences: CSR pattern + the gather plan."""
     mode = symbolic_mode if mode is None else mode
     key = ("plan", space)
     if key in pack.plans:
         return pack.plans[key]
     dofs, n_rows = pack.dofs(space)
     nc, L = int(dofs.shape[0]), int(dofs.shape[1])
-    n_coo = nc * L * L
+    n_coo, n_inc = nc * L * L, nc * L
     dev = pack.device
     with torch.cuda.device(dev):
         s = _stream()
         dofs = dofs.contiguous()
-        perm = torch.empty((max(n_coo, 1),), dtype=_I32, device=dev)
         while True:
             ws_bytes = int(lib.pgb_csr_workspace_bytes(nc, L, n_rows, mode))
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-            nnz = C.c_int64(0)
+            if mode == 1:
+                first = torch.empty((max(n_coo, 1),), dtype=_I32, device=dev)  # perm
+                slots = row_start = None
+            else:
+                first = torch.empty((max(n_inc, 1),), dtype=_I32, device=dev)  # inc_sorted
+                slots = torch.empty((max(n_coo, 1),), dtype=torch.uint8, device=dev)
+                row_start = torch.empty((n_rows + 1,), dtype=_I32, device=dev)
+            nnz, mx = C.c_int64(0), C.c_int(0)
             rc = lib.pgb_csr_symbolic_sort(n_rows, nc, L, dofs.data_ptr(), mode, ws.data_ptr(), ws_bytes,
-                                           perm.data_ptr(), C.byref(nnz), s)
-            if rc == 3 and mode == 0:  # a dof shared by too many cells for the register sort
+                                           first.data_ptr(), _ptr(slots), _ptr(row_start), C.byref(nnz),
+                                           C.byref(mx), s)
+            if rc == 3 and mode != 1:  # a dof shared by too many cells / a row too long for the register sort
                 mode = 1
-                del ws
+                del ws, first, slots, row_start
                 continue
             check(rc)
             break
@@ -418,17 +436,35 @@ def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
         it = torch.int64 if (nnz >= 2**31 or force_idx64) else _I32
         indptr = torch.empty((n_rows + 1,), dtype=it, device=dev)
         indices = torch.empty((nnz,), dtype=_I32, device=dev)
-        seg = torch.empty((nnz + 1,), dtype=_I32, device=dev)
-        check(lib.pgb_csr_symbolic_finish(n_rows, nc, L, mode, nnz, ws.data_ptr(), indptr.data_ptr(),
-                                          1 if it == torch.int64 else 0, indices.data_ptr(),
-                                          seg.data_ptr(), s))
+        seg = torch.empty((nnz + 1,), dtype=_I32, device=dev) if mode == 1 else None
+        check(lib.pgb_csr_symbolic_finish(n_rows, nc, L, mode, nnz, ws.data_ptr(), _ptr(row_start),
+                                          indptr.data_ptr(), 1 if it == torch.int64 else 0, indices.data_ptr(),
+                                          _ptr(seg), s))
         bits = max(1, int(n_rows - 1).bit_length()) if n_rows > 1 else 1
         if mode == 1:
             _lib.count(((2 * bits + 7) // 8) * 5 + 3)
         else:
             _lib.count(((bits + 7) // 8) * 5 + 7)
         del ws
-    plan = CsrPlan(n_rows, n_coo, nnz, perm, seg, indptr, indices)
+    if mode == 1:
+        plan = CsrPlan(n_rows, n_coo, nnz, L, 1, indptr, indices, perm=first, seg=seg)
+    else:
+        with torch.cuda.device(dev):
+            n_sl = (n_rows + 31) // 32
+            ell_ptr = torch.empty((n_sl + 1,), dtype=_I32, device=dev)
+            sws = torch.empty((2048,), dtype=_I32, device=dev)
+            tot = C.c_int64(0)
+            check(lib.pgb_csr_ell_ptr(n_rows, row_start.data_ptr(), ell_ptr.data_ptr(), sws.data_ptr(),
+                                      C.byref(tot), s))
+            tot = int(tot.value)
+            sw = (L + 3) // 4
+            ell_inc = torch.empty((max(tot * 32, 1),), dtype=_I32, device=dev)
+            ell_slots = torch.empty((max(tot * 32 * sw, 1),), dtype=_I32, device=dev)
+            check(lib.pgb_csr_ell_build(n_rows, L, row_start.data_ptr(), first.data_ptr(), slots.data_ptr(),
+                                        ell_ptr.data_ptr(), ell_inc.data_ptr(), ell_slots.data_ptr(), s))
+            _lib.count(5)
+        plan = CsrPlan(n_rows, n_coo, nnz, L, 0, indptr, indices, ell_ptr=ell_ptr, ell_inc=ell_inc,
+                       ell_slots=ell_slots, max_row_nnz=int(mx.value))
     pack.plans[key] = plan
     return plan
 
@@ -476,12 +512,18 @@ def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None) -> torch
 
 
 def numeric(plan: CsrPlan, vals: torch.Tensor, out=None) -> torch.Tensor:
-    """K2 numeric phase: gather through the permutation + segmented reduce."""
+    """K2 numeric phase: local values -> CSR data through the plan (fixed summation order)."""
     dev = vals.device
     with torch.cuda.device(dev):
         data = out if out is not None else torch.empty((plan.nnz,), dtype=torch.float64, device=dev)
-        check(lib.pgb_csr_numeric(plan.nnz, plan.perm.data_ptr(), plan.seg.data_ptr(), vals.data_ptr(),
-                                  data.data_ptr(), _stream()))
+        if plan.mode == 1:
+            check(lib.pgb_csr_numeric(plan.nnz, plan.perm.data_ptr(), plan.seg.data_ptr(), vals.data_ptr(),
+                                      data.data_ptr(), _stream()))
+        else:
+            check(lib.pgb_csr_numeric_ell(plan.n_rows, plan.L, plan.max_row_nnz, plan.ell_ptr.data_ptr(),
+                                          plan.ell_inc.data_ptr(), plan.ell_slots.data_ptr(),
+                                          plan.indptr.data_ptr(), 1 if plan.indptr.dtype == torch.int64 else 0,
+                                          vals.data_ptr(), data.data_ptr(), _stream()))
         _lib.count(1)
     return data
 

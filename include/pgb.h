@@ -112,10 +112,14 @@ enum {
   PGB_BDM1_LUMPED = 13  /* BDM1 lumped: w|c| delta_jl/(d+1) t_aj^T K t_bl            L = d(d+1) */
 };
 int pgb_local_size(int kind, int dim); /* L */
+/* dst_pos (nullable): [nc*L] destination row of every local row (the inc_pos of a mode-0 plan);
+ * local row a of cell c is then written to vals[dst_pos[c*L+a]*LP .. +L) instead of
+ * vals[(c*L+a)*L .. +L), with the row pitch LP = L rounded up to even (16-byte aligned rows; vals
+ * then holds nc*L*LP doubles, the slots array of the plan nc*L*LP bytes). */
 int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
                        const uint8_t* sign_bits, const uint32_t* aux_bits, const double* coords,
-                       const double* K, const double* R_host, const double* w, double* vals,
-                       void* stream);
+                       const double* K, const double* R_host, const double* w, const uint32_t* dst_pos,
+                       double* vals, void* stream);
 
 /* ---- K2: COO -> CSR, deterministic, no floating-point atomics --------------------
  * Replaces scipy's COO->CSC constructor and SpGEMM duplicate summation
@@ -124,8 +128,9 @@ int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
  *
  * Two symbolic algorithms produce the same CSR pattern (indptr, indices):
  *   mode 0 (two level, default): (1) stable LSD radix sort of the nc*L incidences (cell, a) by
- *     dof id (32-bit keys) = the transpose of the cell->dof table: inc_sorted [nc*L] (incidence
- *     ids cell*L + a in (dof, cell) order) and row_start [n_rows+1]; (2) one sub-warp per row
+ *     dof id (32-bit keys) = the transpose of the cell->dof table; returned as inc_pos [nc*L]
+ *     (position of incidence cell*L + a in (dof, cell) order: where K1 must put that local row)
+ *     and row_start [n_rows+1]; (2) one sub-warp per row
  *     gathers the row's candidate columns, sorts them with a register bitonic network, removes
  *     duplicates and records for every candidate the index of its column inside the row
  *     (slots [nc*L*L] uint8, slots[(row_start[r] + q)*L + b]); (3) a scan of the row counts and a
@@ -135,14 +140,14 @@ int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
  *   mode 1 (full sort): stable LSD radix sort of all nc*L*L packed (row,col) keys (64-bit) with
  *     the COO position as payload (perm [n_coo]), then head-flag compaction (seg [nnz+1]).
  * symbolic_sort: workspace of pgb_csr_workspace_bytes(nc, L, n_rows, mode) bytes.
- *   perm_or_inc: perm (mode 1) or inc_sorted (mode 0).  nnz_host / max_row_nnz_host are returned
+ *   perm_or_inc: perm (mode 1) or inc_pos (mode 0).  nnz_host / max_row_nnz_host are returned
  *   after a stream synchronisation.
  * symbolic_finish: indptr (int32 if idx64==0 else int64) [n_rows+1], indices [nnz]; mode 1 also
  *   seg [nnz+1] (start of each entry's run in perm).
- * numeric_ell (mode 0 plans): one thread per row walks the row's incident cells in ascending cell
- *   order through a sliced-ELL copy of the incidence lists, reads each contiguous local row of
- *   vals with vector loads (one 32-byte sector for L = 4) and adds it into per-row accumulators
- *   in shared memory.  9 B read per COO entry.
+ * numeric_rows (mode 0 plans): K1 has written every local row to its row-sorted position
+ *   (pgb_local_matrices with dst_pos = inc_pos), so a CSR row owns a contiguous block of vals_t;
+ *   one thread per row streams it with 256-bit loads and adds each value into the accumulator of
+ *   its column slot in shared memory.  No gathers; 9 B read per COO entry.
  * numeric (mode 1 plans): data[k] = sum over its run of vals[perm[.]]: lane-sequential partial
  *   sums combined by a warp-shuffle segmented scan.
  * Both sum in a fixed order (bit-reproducible, no floating-point atomics).
@@ -159,17 +164,10 @@ int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell
 int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mode, int64_t nnz,
                             const void* workspace, const uint32_t* row_start, void* indptr, int idx64,
                             int32_t* indices, uint32_t* seg, void* stream);
-/* mode 0 plans: sliced-ELL transpose of the incidence lists (slices of 32 rows padded to their
- * longest row) and the row-gather numeric kernel.  ell_ptr [ceil(n_rows/32) + 1] (scan_ws: 8 KB);
- * ell_inc [total*32], ell_slots [total*32*ceil(L/4)] with total = *total_host. */
-int pgb_csr_ell_ptr(int64_t n_rows, const uint32_t* row_start, uint32_t* ell_ptr, void* scan_ws,
-                    int64_t* total_host, void* stream);
-int pgb_csr_ell_build(int64_t n_rows, int L, const uint32_t* row_start, const uint32_t* inc_sorted,
-                      const uint8_t* slots, const uint32_t* ell_ptr, uint32_t* ell_inc,
-                      uint32_t* ell_slots, void* stream);
-int pgb_csr_numeric_ell(int64_t n_rows, int L, int max_row_nnz, const uint32_t* ell_ptr,
-                        const uint32_t* ell_inc, const uint32_t* ell_slots, const void* indptr, int idx64,
-                        const double* vals, double* data, void* stream);
+/* mode 0 plans: vals_t holds the local rows in row-sorted order (K1 called with dst_pos = inc_pos). */
+int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, const uint32_t* row_start,
+                         const uint8_t* slots, const void* indptr, int idx64, const double* vals_t,
+                         double* data, void* stream);
 int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t* seg, const double* vals,
                     double* data, void* stream);
 

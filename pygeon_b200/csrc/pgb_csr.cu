@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
                                                  int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz,
                                                  uint32_t* __restrict__ max_nnz) {
   constexpr int N = G * ITEMS;
+  constexpr int LP = L + (L & 1);
   constexpr bool K32 = sizeof(KeyT) == 4;
   constexpr int EB = (N <= 8) ? 3 : (N <= 16) ? 4 : (N <= 32) ? 5 : (N <= 64) ? 6 : (N <= 128) ? 7 : (N <= 256) ? 8 : 9;
   constexpr int CSH = K32 ? EB : 32;  // column shift inside the key
@@ -450,7 +451,8 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
         ucol_tmp[base + run] = (int32_t)(key[i] >> CSH);
       }
       uint32_t e0 = (uint32_t)key[i] & ((1u << EB) - 1u);  // position before sorting
-      slots[base + e0] = (uint8_t)run;
+      uint32_t q0 = e0 / L;
+      slots[(uint64_t)(rs + q0) * LP + (e0 - q0 * L)] = (uint8_t)run;  // row pitch LP = L rounded up to even
     }
   }
   if (live && gl == 0) row_nnz[r] = (uint32_t)total;
@@ -483,133 +485,94 @@ __global__ void __launch_bounds__(256) k_compact(int64_t n_rows, int L, const ui
   for (uint32_t k = gl; k < cnt; k += 8) indices[o0 + k] = ucol_tmp[base + k];
 }
 
-// ---- numeric, row-gather form over a sliced-ELL transpose (plans of the two-level symbolic) ------
-// The segmented-reduce kernel below issues one 8-byte gather per COO entry; each is its own L1
-// wavefront, and at ~1 wavefront / clock / SM that (not HBM) bounds it.  Here ONE THREAD owns one
-// matrix row and walks the row's incident (cell, a) pairs in ascending cell order: it reads the
-// contiguous local row vals[cell][a][0..L) with 16-byte vector loads (one 32-byte sector for L = 4)
-// and adds each value into the row's accumulator of that column, kept in shared memory as
-// acc[slot][thread] (conflict-free).  To make the per-row lists coalesced they are stored in
-// sliced-ELL form: rows are grouped in slices of 32 (one warp), a slice is padded to its longest
-// row, and entry i of the 32 rows is contiguous: ell_inc[(ell_ptr[s] + i)*32 + lane] = incidence id
-// (0xffffffff = padding), ell_slots[((ell_ptr[s] + i)*SW + w)*32 + lane] = the uint8 column slots of
-// that incidence, four per word.  Sequential in cell order => the oracle's summation order,
-// bit-reproducible, no atomics.  Reads per COO entry: 8 B value + 1 B slot + 4/L B incidence id.
-constexpr uint32_t ELL_PAD = 0xffffffffu;
-
-__global__ void __launch_bounds__(256) k_ell_widths(int64_t n_rows, const uint32_t* __restrict__ row_start,
-                                                    uint32_t* __restrict__ width) {
-  // one warp per slice of 32 rows
-  const int lane = threadIdx.x & 31;
-  const int64_t sl = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
-  const int64_t r = sl * 32 + lane;
-  uint32_t m = (r < n_rows) ? row_start[r + 1] - row_start[r] : 0u;
-  m = __reduce_max_sync(FULL, m);
-  if (lane == 0 && sl * 32 < n_rows + 32) width[sl] = (sl * 32 < n_rows) ? m : 0u;
+// ---- numeric over row-sorted local rows (plans of the two-level symbolic) ------------------------
+// With such a plan K1 writes local row a of cell c straight to position inc_pos[c*L + a] of vals_t,
+// i.e. grouped by matrix row in ascending cell order (the order of the incidence transpose).  A CSR
+// row r then owns the CONTIGUOUS block vals_t[row_start[r]*L .. row_start[r+1]*L) and the uint8
+// column slots at the same positions.  One thread per row streams its block with 256-bit loads
+// (every 64-byte HBM atom is consumed, no gathers at all) and adds each value into the row's
+// accumulator acc[slot][thread] in shared memory (conflict-free).  Sequential in cell order => the
+// oracle's summation order, bit-reproducible, no atomics.  Reads per COO entry: 8 B + 1 B.
+__global__ void __launch_bounds__(256) k_inc_pos(uint32_t n_inc, const uint32_t* __restrict__ inc_sorted,
+                                                 uint32_t* __restrict__ inc_pos) {
+  uint32_t p = blockIdx.x * 256u + threadIdx.x;
+  if (p < n_inc) inc_pos[inc_sorted[p]] = p;
 }
 
 template <int L>
-__global__ void __launch_bounds__(256) k_ell_build(int64_t n_rows, const uint32_t* __restrict__ row_start,
-                                                   const uint32_t* __restrict__ inc_sorted,
-                                                   const uint8_t* __restrict__ slots, const uint32_t* __restrict__ ell_ptr,
-                                                   uint32_t* __restrict__ ell_inc, uint32_t* __restrict__ ell_slots) {
-  constexpr int SW = (L + 3) / 4;
-  const int lane = threadIdx.x & 31;
-  const int64_t sl = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
-  if (sl * 32 >= n_rows) return;
-  const int64_t r = sl * 32 + lane;
-  const uint64_t p0 = ell_ptr[sl];
-  const uint32_t W = ell_ptr[sl + 1] - ell_ptr[sl];
-  uint32_t rs = 0, m = 0;
-  if (r < n_rows) {
-    rs = row_start[r];
-    m = row_start[r + 1] - rs;
-  }
-  for (uint32_t i = 0; i < W; ++i) {
-    uint32_t inc = ELL_PAD;
-    uint32_t w[SW];
-#pragma unroll
-    for (int q = 0; q < SW; ++q) w[q] = 0u;
-    if (i < m) {
-      inc = inc_sorted[rs + i];
-      const uint8_t* sp = slots + (uint64_t)(rs + i) * L;
-#pragma unroll
-      for (int b = 0; b < L; ++b) w[b >> 2] |= (uint32_t)sp[b] << (8 * (b & 3));
-    }
-    ell_inc[(p0 + i) * 32 + lane] = inc;
-#pragma unroll
-    for (int q = 0; q < SW; ++q) ell_slots[((p0 + i) * SW + q) * 32 + lane] = w[q];
-  }
-}
-
-template <int L>
-__device__ __forceinline__ void load_local_row(const double* __restrict__ vals, uint32_t inc, double (&v)[L]) {
-  const double* p = vals + (uint64_t)inc * L;
+__device__ __forceinline__ void load_row(const double* __restrict__ p, double (&v)[L]) {
   if constexpr (L % 4 == 0) {
-    // 256-bit loads (LDG.E.256 on sm_100): one request per 32-byte sector
 #pragma unroll
-    for (int b = 0; b < L; b += 4)
+    for (int b = 0; b < L; b += 4)  // LDG.E.256
       asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
                    : "=d"(v[b]), "=d"(v[b + 1]), "=d"(v[b + 2]), "=d"(v[b + 3])
                    : "l"(p + b));
   } else if constexpr (L % 2 == 0) {
 #pragma unroll
     for (int b = 0; b < L; b += 2) {
-      double2 t = *reinterpret_cast<const double2*>(p + b);
+      double2 t = __ldg(reinterpret_cast<const double2*>(p + b));
       v[b] = t.x;
       v[b + 1] = t.y;
     }
   } else {
 #pragma unroll
-    for (int b = 0; b < L; ++b) v[b] = p[b];
+    for (int b = 0; b < L; ++b) v[b] = __ldg(p + b);
+  }
+}
+
+template <int L>
+__device__ __forceinline__ void load_slots(const uint8_t* __restrict__ p, uint32_t (&sl)[L]) {
+  if constexpr (L % 4 == 0) {
+#pragma unroll
+    for (int b = 0; b < L; b += 4) {
+      uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + b));
+      sl[b] = w & 0xffu;
+      sl[b + 1] = (w >> 8) & 0xffu;
+      sl[b + 2] = (w >> 16) & 0xffu;
+      sl[b + 3] = w >> 24;
+    }
+  } else if constexpr (L % 2 == 0) {
+#pragma unroll
+    for (int b = 0; b < L; b += 2) {
+      uint32_t w = __ldg(reinterpret_cast<const uint16_t*>(p + b));
+      sl[b] = w & 0xffu;
+      sl[b + 1] = w >> 8;
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < L; ++b) sl[b] = __ldg(p + b);
   }
 }
 
 template <int L, int BLK, typename IP>
-__global__ void __launch_bounds__(BLK) k_numeric_ell(int64_t n_rows, const uint32_t* __restrict__ ell_ptr,
-                                                     const uint32_t* __restrict__ ell_inc,
-                                                     const uint32_t* __restrict__ ell_slots,
-                                                     const IP* __restrict__ indptr, const double* __restrict__ vals,
-                                                     double* __restrict__ data) {
-  constexpr int SW = (L + 3) / 4;
-  constexpr int U = (L <= 4) ? 4 : 2;  // incidences in flight per thread
+__global__ void __launch_bounds__(BLK) k_numeric_t(int64_t n_rows, const uint32_t* __restrict__ row_start,
+                                                   const uint8_t* __restrict__ slots, const IP* __restrict__ indptr,
+                                                   const double* __restrict__ vals_t, double* __restrict__ data) {
+  constexpr int U = (L <= 4) ? 4 : 2;  // local rows in flight per thread (8 measured slower)
+  constexpr int LP = L + (L & 1);      // row pitch (values and slots)
   extern __shared__ double acc[];    // [slot][thread]
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int64_t r = (int64_t)blockIdx.x * BLK + tid;
-  const int64_t sl = r >> 5;
-  const bool live = r < n_rows;
-  if (sl * 32 >= n_rows) return;  // whole warp out of range
-  const uint64_t p0 = ell_ptr[sl];
-  const uint32_t W = ell_ptr[sl + 1] - ell_ptr[sl];
-  IP o0 = 0;
-  uint32_t cnt = 0;
-  if (live) {
-    o0 = indptr[r];
-    cnt = (uint32_t)(indptr[r + 1] - o0);
-  }
+  if (r >= n_rows) return;
+  const uint32_t rs = row_start[r], re = row_start[r + 1];
+  const IP o0 = indptr[r];
+  const uint32_t cnt = (uint32_t)(indptr[r + 1] - o0);
   for (uint32_t s2 = 0; s2 < cnt; ++s2) acc[s2 * BLK + tid] = 0.0;
-  for (uint32_t i0 = 0; i0 < W; i0 += U) {
-    uint32_t inc[U], sw[U][SW];
-    double v[U][L];
+  for (uint32_t q0 = rs; q0 < re; q0 += U) {
+    double v[U][LP];
+    uint32_t sl[U][LP];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const bool in = i0 + u < W;
-      inc[u] = in ? ell_inc[(p0 + i0 + u) * 32 + lane] : ELL_PAD;
-#pragma unroll
-      for (int q = 0; q < SW; ++q) sw[u][q] = in ? ell_slots[((p0 + i0 + u) * SW + q) * 32 + lane] : 0u;
+      if (q0 + u < re) {
+        load_row<LP>(vals_t + (uint64_t)(q0 + u) * LP, v[u]);
+        load_slots<LP>(slots + (uint64_t)(q0 + u) * LP, sl[u]);
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (inc[u] != ELL_PAD) load_local_row<L>(vals, inc[u], v[u]);
-    }
+      if (q0 + u < re) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (inc[u] != ELL_PAD) {
-#pragma unroll
-        for (int b = 0; b < L; ++b) {
-          uint32_t s2 = (sw[u][b >> 2] >> (8 * (b & 3))) & 0xffu;
-          acc[s2 * BLK + tid] += v[u][b];
-        }
+        for (int b = 0; b < L; ++b) acc[sl[u][b] * BLK + tid] += v[u][b];
       }
     }
   }
@@ -806,7 +769,7 @@ struct WsLayout {
   // full sort
   int64_t keys_a, keys_b, perm_b;
   // two level
-  int64_t ikeys_a, ikeys_b, ipay_b, row_nnz, ucol;
+  int64_t ikeys_a, ikeys_b, ipay_a, ipay_b, row_nnz, ucol;
   // shared
   int64_t hist, parts, meta, total;
 };
@@ -827,6 +790,7 @@ WsLayout ws_layout(int64_t n_coo, int64_t n_inc, int64_t n_rows, int mode) {
   } else {
     l.ikeys_a = o;   o += al(n_inc * 4);
     l.ikeys_b = o;   o += al(n_inc * 4);
+    l.ipay_a = o;    o += al(n_inc * 4);
     l.ipay_b = o;    o += al(n_inc * 4);
     l.row_nnz = o;   o += al((n_rows + 2) * 4);
     l.ucol = o;      o += al(n_coo * 4);
@@ -889,40 +853,38 @@ int launch_rowsort(uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row
 }
 
 template <int L, int BLK, typename IP>
-int launch_numeric_ell_t(int64_t n_rows, int caps, const uint32_t* ell_ptr, const uint32_t* ell_inc,
-                         const uint32_t* ell_slots, const void* indptr, const double* vals, double* data,
-                         cudaStream_t s) {
+int launch_numeric_t_b(int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots, const void* indptr,
+                       const double* vals_t, double* data, cudaStream_t s) {
   size_t smem = (size_t)caps * BLK * sizeof(double);
   static size_t attr = 48 * 1024;
   if (smem > attr) {
-    PGB_CHECK(cudaFuncSetAttribute(k_numeric_ell<L, BLK, IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PGB_CHECK(cudaFuncSetAttribute(k_numeric_t<L, BLK, IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  k_numeric_ell<L, BLK, IP><<<(unsigned)pgb_cdiv(n_rows, BLK), BLK, smem, s>>>(n_rows, ell_ptr, ell_inc, ell_slots,
-                                                                               (const IP*)indptr, vals, data);
+  k_numeric_t<L, BLK, IP><<<(unsigned)pgb_cdiv(n_rows, BLK), BLK, smem, s>>>(n_rows, row_start, slots,
+                                                                             (const IP*)indptr, vals_t, data);
   PGB_LAUNCH_CHECK();
   return 0;
 }
 
 template <int L, typename IP>
-int launch_numeric_ell_l(int64_t n_rows, int caps, const uint32_t* ell_ptr, const uint32_t* ell_inc,
-                         const uint32_t* ell_slots, const void* indptr, const double* vals, double* data,
-                         cudaStream_t s) {
-  if (caps <= 200) return launch_numeric_ell_t<L, 128, IP>(n_rows, caps, ell_ptr, ell_inc, ell_slots, indptr, vals, data, s);
-  return launch_numeric_ell_t<L, 64, IP>(n_rows, caps, ell_ptr, ell_inc, ell_slots, indptr, vals, data, s);
+int launch_numeric_t_l(int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots, const void* indptr,
+                       const double* vals_t, double* data, cudaStream_t s) {
+  if (caps <= 200) return launch_numeric_t_b<L, 128, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+  return launch_numeric_t_b<L, 64, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
 }
 
 template <typename IP>
-int launch_numeric_ell(int L, int64_t n_rows, int caps, const uint32_t* ell_ptr, const uint32_t* ell_inc,
-                       const uint32_t* ell_slots, const void* indptr, const double* vals, double* data, cudaStream_t s) {
+int launch_numeric_t(int L, int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots,
+                     const void* indptr, const double* vals_t, double* data, cudaStream_t s) {
   switch (L) {
-    case 3: return launch_numeric_ell_l<3, IP>(n_rows, caps, ell_ptr, ell_inc, ell_slots, indptr, vals, data, s);
-    case 4: return launch_numeric_ell_l<4, IP>(n_rows, caps, ell_ptr, ell_inc, ell_slots, indptr, vals, data, s);
-    case 5: return launch_numeric_ell_l<5, IP>(n_rows, caps, ell_ptr, ell_inc, ell_slots, indptr, vals, data, s);
-    case 6: return launch_numeric_ell_l<6, IP>(n_rows, caps, ell_ptr, ell_inc, ell_slots, indptr, vals, data, s);
-    case 12: return launch_numeric_ell_l<12, IP>(n_rows, caps, ell_ptr, ell_inc, ell_slots, indptr, vals, data, s);
+    case 3: return launch_numeric_t_l<3, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+    case 4: return launch_numeric_t_l<4, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+    case 5: return launch_numeric_t_l<5, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+    case 6: return launch_numeric_t_l<6, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+    case 12: return launch_numeric_t_l<12, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
   }
-  pgb_set_error("pgb_csr_numeric_ell: unsupported local size %d", L);
+  pgb_set_error("pgb_csr_numeric_rows: unsupported local size %d", L);
   return 2;
 }
 
@@ -977,13 +939,14 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
   } else {
     PGB_REQUIRE(slots && row_start, "pgb_csr_symbolic_sort: slots / row_start required in two-level mode");
     uint32_t* kbuf[2] = {(uint32_t*)(ws + l.ikeys_a), (uint32_t*)(ws + l.ikeys_b)};
-    uint32_t* pbuf[2] = {perm_or_inc, (uint32_t*)(ws + l.ipay_b)};  // sorted incidences land in the caller's array
+    uint32_t* pbuf[2] = {(uint32_t*)(ws + l.ipay_a), (uint32_t*)(ws + l.ipay_b)};  // pbuf[0]: sorted incidences
     uint32_t* row_nnz = (uint32_t*)(ws + l.row_nnz);
     KeySrc<uint32_t> src{nullptr, cell_dofs, (uint32_t)L, (uint32_t)(L * L), cb};
     PhaseTimer pt(s);
     pt.mark();
     if (radix_sort<uint32_t>(src, (uint32_t)n_inc, cb, kbuf, pbuf, hist, parts, s)) return 1;
     pt.mark();
+    k_inc_pos<<<pgb_grid(n_inc, 256), 256, 0, s>>>((uint32_t)n_inc, pbuf[0], perm_or_inc);  // inverse permutation
     k_row_starts<<<pgb_grid(n_inc, 256), 256, 0, s>>>(kbuf[0], (uint32_t)n_inc, n_rows, row_start);
     k_max_row<<<(unsigned)(n_rows < 256 * 1184 ? pgb_grid(n_rows, 256) : 1184), 256, 0, s>>>(n_rows, row_start, meta + 3);
     PGB_LAUNCH_CHECK();
@@ -1057,50 +1020,15 @@ extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mo
   return 0;
 }
 
-/* sliced-ELL transpose of the incidence lists: widths of the 32-row slices, scanned into ell_ptr
- * [n_slices + 1]; *total_host = ell_ptr[n_slices] (synchronises the stream). */
-extern "C" int pgb_csr_ell_ptr(int64_t n_rows, const uint32_t* row_start, uint32_t* ell_ptr, void* scan_ws,
-                               int64_t* total_host, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  const int64_t n_sl = pgb_cdiv(n_rows, 32);
-  k_ell_widths<<<pgb_grid((n_sl + 1) * 32, 256), 256, 0, s>>>(n_rows, row_start, ell_ptr);
-  PGB_LAUNCH_CHECK();
-  PGB_CHECK(cudaMemsetAsync(ell_ptr + n_sl, 0, sizeof(uint32_t), s));
-  if (scan_u32(ell_ptr, (uint64_t)n_sl + 1, (uint32_t*)scan_ws, nullptr, s)) return 1;
-  uint32_t tot = 0;
-  PGB_CHECK(cudaMemcpyAsync(&tot, ell_ptr + n_sl, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  PGB_CHECK(cudaStreamSynchronize(s));
-  *total_host = (int64_t)tot;
-  return 0;
-}
-
-extern "C" int pgb_csr_ell_build(int64_t n_rows, int L, const uint32_t* row_start, const uint32_t* inc_sorted,
-                                 const uint8_t* slots, const uint32_t* ell_ptr, uint32_t* ell_inc,
-                                 uint32_t* ell_slots, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
+extern "C" int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, const uint32_t* row_start,
+                                    const uint8_t* slots, const void* indptr, int idx64, const double* vals_t,
+                                    double* data, void* stream) {
   if (n_rows == 0) return 0;
-  unsigned grid = pgb_grid(pgb_cdiv(n_rows, 32) * 32, 256);
-  switch (L) {
-    case 3: k_ell_build<3><<<grid, 256, 0, s>>>(n_rows, row_start, inc_sorted, slots, ell_ptr, ell_inc, ell_slots); break;
-    case 4: k_ell_build<4><<<grid, 256, 0, s>>>(n_rows, row_start, inc_sorted, slots, ell_ptr, ell_inc, ell_slots); break;
-    case 5: k_ell_build<5><<<grid, 256, 0, s>>>(n_rows, row_start, inc_sorted, slots, ell_ptr, ell_inc, ell_slots); break;
-    case 6: k_ell_build<6><<<grid, 256, 0, s>>>(n_rows, row_start, inc_sorted, slots, ell_ptr, ell_inc, ell_slots); break;
-    case 12: k_ell_build<12><<<grid, 256, 0, s>>>(n_rows, row_start, inc_sorted, slots, ell_ptr, ell_inc, ell_slots); break;
-    default: pgb_set_error("pgb_csr_ell_build: unsupported local size %d", L); return 2;
-  }
-  PGB_LAUNCH_CHECK();
-  return 0;
-}
-
-extern "C" int pgb_csr_numeric_ell(int64_t n_rows, int L, int max_row_nnz, const uint32_t* ell_ptr,
-                                   const uint32_t* ell_inc, const uint32_t* ell_slots, const void* indptr, int idx64,
-                                   const double* vals, double* data, void* stream) {
-  if (n_rows == 0) return 0;
-  PGB_REQUIRE(max_row_nnz >= 0 && max_row_nnz <= 255, "pgb_csr_numeric_ell: max_row_nnz out of range");
+  PGB_REQUIRE(max_row_nnz >= 0 && max_row_nnz <= 255, "pgb_csr_numeric_rows: max_row_nnz out of range");
   cudaStream_t s = (cudaStream_t)stream;
   int caps = max_row_nnz < 1 ? 1 : max_row_nnz;
-  return idx64 ? launch_numeric_ell<int64_t>(L, n_rows, caps, ell_ptr, ell_inc, ell_slots, indptr, vals, data, s)
-               : launch_numeric_ell<int32_t>(L, n_rows, caps, ell_ptr, ell_inc, ell_slots, indptr, vals, data, s);
+  return idx64 ? launch_numeric_t<int64_t>(L, n_rows, caps, row_start, slots, indptr, vals_t, data, s)
+               : launch_numeric_t<int32_t>(L, n_rows, caps, row_start, slots, indptr, vals_t, data, s);
 }
 
 extern "C" int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t* seg,

@@ -321,7 +321,8 @@ class GridPack:
 class CsrPlan:
     """Result of the symbolic phase, reusable by every operator of a space on the grid.
 
-    mode 0 (two level): ``ell_ptr, ell_inc, ell_slots`` drive the row-gather numeric kernel;
+    mode 0 (two level): K1 writes the local rows to ``inc_pos`` (row-sorted order) and the
+    streaming numeric kernel reduces them through ``row_start`` / ``slots``;
     mode 1 (full sort): ``perm, seg`` drive the segmented-reduce numeric kernel."""
 
     n_rows: int
@@ -333,9 +334,9 @@ class CsrPlan:
     indices: torch.Tensor
     perm: torch.Tensor | None = None  # mode 1: uint32 stored as int32
     seg: torch.Tensor | None = None
-    ell_ptr: torch.Tensor | None = None  # mode 0: sliced-ELL transpose of the incidence lists
-    ell_inc: torch.Tensor | None = None
-    ell_slots: torch.Tensor | None = None
+    inc_pos: torch.Tensor | None = None  # mode 0: row-sorted position of every local row (for K1)
+    row_start: torch.Tensor | None = None
+    slots: torch.Tensor | None = None
     max_row_nnz: int = 0
 
 
@@ -396,7 +397,6 @@ class DeviceCSR:
 
 symbolic_mode = 0  # 0 = two-level (default), 1 = full (row,col) radix sort; see include/pgb.h
 force_idx64 = False  # tests: emit int64 indptr even when nnz < 2^31
-overlap_streams = False  # optional: run K1 on a side stream next to the symbolic phase (no measurable gain on B200: both kernels fill the SMs)
 
 
 def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
@@ -419,8 +419,8 @@ def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
                 first = torch.empty((max(n_coo, 1),), dtype=_I32, device=dev)  # perm
                 slots = row_start = None
             else:
-                first = torch.empty((max(n_inc, 1),), dtype=_I32, device=dev)  # inc_sorted
-                slots = torch.empty((max(n_coo, 1),), dtype=torch.uint8, device=dev)
+                first = torch.empty((max(n_inc, 1),), dtype=_I32, device=dev)  # inc_pos
+                slots = torch.zeros((max(n_inc * (L + (L & 1)), 1),), dtype=torch.uint8, device=dev)
                 row_start = torch.empty((n_rows + 1,), dtype=_I32, device=dev)
             nnz, mx = C.c_int64(0), C.c_int(0)
             rc = lib.pgb_csr_symbolic_sort(n_rows, nc, L, dofs.data_ptr(), mode, ws.data_ptr(), ws_bytes,
@@ -449,22 +449,8 @@ def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
     if mode == 1:
         plan = CsrPlan(n_rows, n_coo, nnz, L, 1, indptr, indices, perm=first, seg=seg)
     else:
-        with torch.cuda.device(dev):
-            n_sl = (n_rows + 31) // 32
-            ell_ptr = torch.empty((n_sl + 1,), dtype=_I32, device=dev)
-            sws = torch.empty((2048,), dtype=_I32, device=dev)
-            tot = C.c_int64(0)
-            check(lib.pgb_csr_ell_ptr(n_rows, row_start.data_ptr(), ell_ptr.data_ptr(), sws.data_ptr(),
-                                      C.byref(tot), s))
-            tot = int(tot.value)
-            sw = (L + 3) // 4
-            ell_inc = torch.empty((max(tot * 32, 1),), dtype=_I32, device=dev)
-            ell_slots = torch.empty((max(tot * 32 * sw, 1),), dtype=_I32, device=dev)
-            check(lib.pgb_csr_ell_build(n_rows, L, row_start.data_ptr(), first.data_ptr(), slots.data_ptr(),
-                                        ell_ptr.data_ptr(), ell_inc.data_ptr(), ell_slots.data_ptr(), s))
-            _lib.count(5)
-        plan = CsrPlan(n_rows, n_coo, nnz, L, 0, indptr, indices, ell_ptr=ell_ptr, ell_inc=ell_inc,
-                       ell_slots=ell_slots, max_row_nnz=int(mx.value))
+        plan = CsrPlan(n_rows, n_coo, nnz, L, 0, indptr, indices, inc_pos=first, row_start=row_start,
+                       slots=slots, max_row_nnz=int(mx.value))
     pack.plans[key] = plan
     return plan
 
@@ -487,8 +473,10 @@ _FORMS = {
 }
 
 
-def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None) -> torch.Tensor:
-    """K1: vals (nc, L*L) on the device.  ``w`` (nc,) / ``K`` (3,3,nc) are device tensors or None."""
+def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None, plan: "CsrPlan | None" = None) -> torch.Tensor:
+    """K1: vals (nc, L*L) on the device.  ``w`` (nc,) / ``K`` (3,3,nc) are device tensors or None.
+    With a mode-0 ``plan`` the local rows are written in the plan's row-sorted order (what
+    :func:`numeric` expects for that plan); without, in plain [cell][a][b] order."""
     d, nc, dev = pack.dim, pack.nc, pack.device
     L = int(lib.pgb_local_size(KIND[kind], d))
     aux = None
@@ -500,11 +488,14 @@ def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None) -> torch
     elif kind in ("bdm1_mass", "bdm1_lumped"):
         aux = pack.bdm1()[1]
     with torch.cuda.device(dev):
-        vals = out if out is not None else torch.empty((nc, L * L), dtype=torch.float64, device=dev)
+        rowmajor = plan is not None and plan.mode == 0
+        pitch = L + (L & 1) if rowmajor else L  # row-sorted layout: rows padded to an even length
+        vals = out if out is not None else torch.empty((nc, L * pitch), dtype=torch.float64, device=dev)
         check(
             lib.pgb_local_matrices(
                 KIND[kind], d, nc, pack.cell_nodes.data_ptr(), _ptr(sign_bits), _ptr(aux),
-                pack.coords.data_ptr(), _ptr(K), pack.R.ctypes.data, _ptr(w), vals.data_ptr(), _stream(),
+                pack.coords.data_ptr(), _ptr(K), pack.R.ctypes.data, _ptr(w),
+                _ptr(plan.inc_pos) if (plan is not None and plan.mode == 0) else 0, vals.data_ptr(), _stream(),
             )
         )
         _lib.count(1)
@@ -520,10 +511,10 @@ def numeric(plan: CsrPlan, vals: torch.Tensor, out=None) -> torch.Tensor:
             check(lib.pgb_csr_numeric(plan.nnz, plan.perm.data_ptr(), plan.seg.data_ptr(), vals.data_ptr(),
                                       data.data_ptr(), _stream()))
         else:
-            check(lib.pgb_csr_numeric_ell(plan.n_rows, plan.L, plan.max_row_nnz, plan.ell_ptr.data_ptr(),
-                                          plan.ell_inc.data_ptr(), plan.ell_slots.data_ptr(),
-                                          plan.indptr.data_ptr(), 1 if plan.indptr.dtype == torch.int64 else 0,
-                                          vals.data_ptr(), data.data_ptr(), _stream()))
+            check(lib.pgb_csr_numeric_rows(plan.n_rows, plan.L, plan.max_row_nnz, plan.row_start.data_ptr(),
+                                           plan.slots.data_ptr(), plan.indptr.data_ptr(),
+                                           1 if plan.indptr.dtype == torch.int64 else 0,
+                                           vals.data_ptr(), data.data_ptr(), _stream()))
         _lib.count(1)
     return data
 
@@ -556,36 +547,10 @@ _SIDE: dict = {}
 
 
 def assemble_on_pack(pack: GridPack, space: str, kind: str, wd=None, Kd=None):
-    """symbolic (cached per pack) + K1 + K2 numeric.  When the plan still has to be built, K1 - a
-    pure HBM streaming kernel - runs on a side stream concurrently with the symbolic phase, whose
-    dominant kernel (the per-row register sort) is issue bound and leaves the memory system idle."""
-    dev = pack.device
-    cached = ("plan", space) in pack.plans
-    if cached or not overlap_streams:
-        plan = symbolic(pack, space)
-        vals = local_matrices(pack, kind, wd, Kd)
-        return plan, numeric(plan, vals)
-    with torch.cuda.device(dev):
-        main = torch.cuda.current_stream()
-        side = _SIDE.get(dev)
-        if side is None:
-            side = _SIDE[dev] = torch.cuda.Stream(device=dev)
-        if kind in ("n0_mass", "n0_curlcurl"):
-            pack.edges()  # aux tables must exist before the side stream reads them
-        elif kind in ("bdm1_mass", "bdm1_lumped"):
-            pack.bdm1()
-        ready = torch.cuda.Event()
-        ready.record(main)
-        with torch.cuda.stream(side):
-            side.wait_event(ready)
-            vals = local_matrices(pack, kind, wd, Kd)
-            done = torch.cuda.Event()
-            done.record(side)
-        plan = symbolic(pack, space)
-        main.wait_event(done)
-        vals.record_stream(main)
-        data = numeric(plan, vals)
-    return plan, data
+    """symbolic (cached per pack) -> K1 (writing the local rows where the plan wants them) -> K2."""
+    plan = symbolic(pack, space)
+    vals = local_matrices(pack, kind, wd, Kd, plan=plan)
+    return plan, numeric(plan, vals)
 
 
 def assemble_device(space: str, form: str, sd, w=None, K=None, device=None) -> DeviceCSR:

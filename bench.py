@@ -35,8 +35,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# (profiles/r1_ncu_full.txt; config #2, L1 stiffness on 128^3)
-TRAFFIC = {"k_rowsort": 1.678e9, "local_matrices": 1.822e9, "csr_numeric": 2.813e9}
+# (profiles/r1_ncu_full.txt; config #2, L1 stiffness on 128^3; k_rowsort, k_local, k_numeric_t)
+TRAFFIC = {"k_rowsort": 0.805e9, "local_matrices": 2.029e9, "csr_numeric": 2.070e9}
 
 METRIC = "cells assembled/s into CSR"
 UNIT = "cells/s"
@@ -216,7 +216,7 @@ def run_ours(args):
         e[1].record()
         plan = engine.symbolic(pack, "lagrange1")
         e[2].record()
-        vals = engine.local_matrices(pack, "l1_stiff")
+        vals = engine.local_matrices(pack, "l1_stiff", plan=plan)
         e[3].record()
         data = engine.numeric(plan, vals)
         e[4].record()
@@ -251,16 +251,16 @@ def run_ours(args):
         # ---- warm steps (plan reused) ------------------------------------------------------
         pack = engine.GridPack.from_raw(raw)
         plan = engine.symbolic(pack, "lagrange1")
-        vals = torch.empty((nc, 16), dtype=torch.float64, device=dev)
+        vals = torch.empty((nc, 16), dtype=torch.float64, device=dev)  # L = 4: pitch 4
         out = torch.empty((plan.nnz,), dtype=torch.float64, device=dev)
         for _ in range(3):
-            engine.numeric(plan, engine.local_matrices(pack, "l1_stiff", out=vals), out=out)
+            engine.numeric(plan, engine.local_matrices(pack, "l1_stiff", out=vals, plan=plan), out=out)
         w0, w1, w2 = ev(), ev(), ev()
         wl, wn = 0.0, 0.0
         torch.cuda.synchronize()
         for _ in range(args.steps):
             w0.record()
-            engine.local_matrices(pack, "l1_stiff", out=vals)
+            engine.local_matrices(pack, "l1_stiff", out=vals, plan=plan)
             w1.record()
             engine.numeric(plan, vals, out=out)
             w2.record()
@@ -296,11 +296,13 @@ def run_ours(args):
     bits = max(1, int(nn - 1).bit_length())
     passes = (bits + 7) // 8  # radix passes of the incidence transpose (32-bit keys)
     n_inc = nc * 4
-    b_local = nc * (16 + 128) + 32 * nn
-    b_numeric = n_coo * 12 + (nnz + 1) * 4 + nnz * 8
+    b_local = nc * (16 + 16 + 128) + 32 * nn  # node ids + destination rows + values; coords once per node
+    # streaming numeric over the row-sorted local rows: value 8 B + slot 1 B per COO entry, row
+    # offsets + indptr 8 B per row, data 8 B per entry
+    b_numeric = n_coo * 9 + 8 * nn + nnz * 8
     b_sort_pass = n_inc * 16  # the scatter kernel moves each (key, payload) once in and once out
     # per-row sort: read sorted incidences + row offsets, write perm, unique cols / run starts
-    b_rowsort = n_inc * 4 + n_inc * 4 + 8 * nn + n_coo * 4 + nnz * 8  # + the cell->dof table, read once
+    b_rowsort = n_inc * 4 + n_inc * 4 + 8 * nn + n_coo * 1 + nnz * 4  # incidences + cell->dof table in, slots + unique cols out
     b_step_algo = nc * 16 + 32 * nn + n_coo * 0 + nnz * 12 + 4 * (nn + 1)  # read grid once, write CSR once
     kern = {
         "local_matrices": {"ms": wl, "gbs": b_local / wl / 1e6, "bytes": b_local},
@@ -321,7 +323,7 @@ def run_ours(args):
 
     # ---- CG on the assembled operator (S + M, SPD, same pattern) --------------------------------
     S = engine.DeviceCSR((nn, nn), plan.indptr, plan.indices, out.clone())
-    Mv = engine.numeric(plan, engine.local_matrices(pack, "l1_mass", out=vals))
+    Mv = engine.numeric(plan, engine.local_matrices(pack, "l1_mass", out=vals, plan=plan))
     S.data += Mv
     b = torch.ones(nn, dtype=torch.float64, device=dev)
     cg_iters = args.cg_iters

@@ -29,6 +29,9 @@ extern "C" {
 
 int pgb_version(void);
 const char* pgb_last_error(void);
+/* cudaLimitMaxL2FetchGranularity hint (32 / 64 / 128 bytes) for the current device. */
+int pgb_set_l2_fetch_granularity(int bytes);
+int pgb_get_l2_fetch_granularity(void);
 
 /* ---- grid packing ------------------------------------------------------------
  * Replaces Grid.compute_opposite_nodes (grids/grid.py:279-309),
@@ -109,31 +112,45 @@ enum {
   PGB_BDM1_LUMPED = 13  /* BDM1 lumped: w|c| delta_jl/(d+1) t_aj^T K t_bl            L = d(d+1) */
 };
 int pgb_local_size(int kind, int dim); /* L */
+/* dst_pos (nullable): [nc*L] destination row of every local row (the inc_pos of a mode-0 plan);
+ * local row a of cell c is then written to vals[dst_pos[c*L+a]*LP .. +L) instead of
+ * vals[(c*L+a)*L .. +L), with the row pitch LP = L rounded up to even (16-byte aligned rows; vals
+ * then holds nc*L*LP doubles, the slots array of the plan nc*L*LP bytes). */
 int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
                        const uint8_t* sign_bits, const uint32_t* aux_bits, const double* coords,
-                       const double* K, const double* R_host, const double* w, double* vals,
-                       void* stream);
+                       const double* K, const double* R_host, const double* w, const uint32_t* dst_pos,
+                       double* vals, void* stream);
 
 /* ---- K2: COO -> CSR, deterministic, no floating-point atomics --------------------
  * Replaces scipy's COO->CSC constructor and SpGEMM duplicate summation
  * (e.g. fem/hdiv.py:509, fem/hcurl.py:291, fem/h1.py:237, discretization.py:136).
  * COO entry i = cell*L*L + a*L + b has row cell_dofs[cell*L+a], col cell_dofs[cell*L+b].
  *
- * Two symbolic algorithms produce the same arrays:
+ * Two symbolic algorithms produce the same CSR pattern (indptr, indices):
  *   mode 0 (two level, default): (1) stable LSD radix sort of the nc*L incidences (cell, a) by
- *     dof id (32-bit keys) = the transpose of the cell->dof table; (2) one sub-warp per row
- *     gathers the row's candidates (col, src), sorts them with a register bitonic network and
- *     removes duplicate columns; (3) a scan of the row counts and a compaction.  Needs every dof
- *     to be shared by at most 512/L cells; otherwise returns 3 and the caller retries with mode 1.
+ *     dof id (32-bit keys) = the transpose of the cell->dof table; returned as inc_pos [nc*L]
+ *     (position of incidence cell*L + a in (dof, cell) order: where K1 must put that local row)
+ *     and row_start [n_rows+1]; (2) one sub-warp per row
+ *     gathers the row's candidate columns, sorts them with a register bitonic network, removes
+ *     duplicates and records for every candidate the index of its column inside the row
+ *     (slots [nc*L*L] uint8, slots[(row_start[r] + q)*L + b]); (3) a scan of the row counts and a
+ *     compaction.  Needs every dof to be shared by at most 512/L cells and every row to have at
+ *     most 255 entries; otherwise returns 3 and the caller retries with mode 1.
+ *     (mode 2 = mode 0 with 64-bit keys forced in the row sort; for tests.)
  *   mode 1 (full sort): stable LSD radix sort of all nc*L*L packed (row,col) keys (64-bit) with
- *     the COO position as payload, then head-flag compaction.
+ *     the COO position as payload (perm [n_coo]), then head-flag compaction (seg [nnz+1]).
  * symbolic_sort: workspace of pgb_csr_workspace_bytes(nc, L, n_rows, mode) bytes.
- *   perm [n_coo] out: COO positions in sorted order.  nnz_host: number of distinct keys
- *   (the call synchronises the stream to return it).
- * symbolic_finish: indptr (int32 if idx64==0 else int64) [n_rows+1], indices [nnz],
- *   seg [nnz+1]: start of each entry's run in perm.
- * numeric: data[k] = sum over its run of vals[perm[.]]: lane-sequential partial sums combined by
- *   a warp-shuffle segmented scan, in a fixed order (bit-reproducible).
+ *   perm_or_inc: perm (mode 1) or inc_pos (mode 0).  nnz_host / max_row_nnz_host are returned
+ *   after a stream synchronisation.
+ * symbolic_finish: indptr (int32 if idx64==0 else int64) [n_rows+1], indices [nnz]; mode 1 also
+ *   seg [nnz+1] (start of each entry's run in perm).
+ * numeric_rows (mode 0 plans): K1 has written every local row to its row-sorted position
+ *   (pgb_local_matrices with dst_pos = inc_pos), so a CSR row owns a contiguous block of vals_t;
+ *   one thread per row streams it with 256-bit loads and adds each value into the accumulator of
+ *   its column slot in shared memory.  No gathers; 9 B read per COO entry.
+ * numeric (mode 1 plans): data[k] = sum over its run of vals[perm[.]]: lane-sequential partial
+ *   sums combined by a warp-shuffle segmented scan.
+ * Both sum in a fixed order (bit-reproducible, no floating-point atomics).
  */
 int64_t pgb_csr_workspace_bytes(int64_t nc, int L, int64_t n_rows, int mode);
 /* Optional CUDA-event timing of the phases of the two-level symbolic_sort (off by default):
@@ -141,11 +158,16 @@ int64_t pgb_csr_workspace_bytes(int64_t nc, int L, int64_t n_rows, int mode);
 void pgb_set_profile(int on);
 void pgb_get_phase_ms(double* out, int n);
 int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell_dofs, int mode,
-                          void* workspace, int64_t workspace_bytes, uint32_t* perm,
-                          int64_t* nnz_host, void* stream);
+                          void* workspace, int64_t workspace_bytes, uint32_t* perm_or_inc,
+                          uint8_t* slots, uint32_t* row_start, int64_t* nnz_host,
+                          int* max_row_nnz_host, void* stream);
 int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mode, int64_t nnz,
-                            const void* workspace, void* indptr, int idx64, int32_t* indices,
-                            uint32_t* seg, void* stream);
+                            const void* workspace, const uint32_t* row_start, void* indptr, int idx64,
+                            int32_t* indices, uint32_t* seg, void* stream);
+/* mode 0 plans: vals_t holds the local rows in row-sorted order (K1 called with dst_pos = inc_pos). */
+int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, const uint32_t* row_start,
+                         const uint8_t* slots, const void* indptr, int idx64, const double* vals_t,
+                         double* data, void* stream);
 int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t* seg, const double* vals,
                     double* data, void* stream);
 

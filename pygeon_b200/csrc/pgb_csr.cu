@@ -346,19 +346,23 @@ __global__ void __launch_bounds__(256) k_max_row(int64_t n_rows, const uint32_t*
   }
 }
 
-// KeyT = uint32_t: key = (col << log2(N)) | e with e the candidate's position before sorting (the
-// incidences of a row are in ascending cell order, so e orders ties exactly like src = inc*L + b);
-// used whenever n_rows * N fits in 32 bits.  KeyT = uint64_t: key = (col << 32) | src.
+// Key = (col << CSH) | e0 with e0 the candidate's position in the row before sorting
+// (e0 = q*L + b for the q-th incidence of the row and local column b).  KeyT = uint32_t
+// (CSH = log2 N) whenever n_rows * N fits in 32 bits, else uint64_t (CSH = 32).
+// Output per row: the sorted unique columns (scratch, compacted later), and for every candidate
+// the index of its column among them ("slot", uint8): slots[(row_start[r] + q)*L + b].
 template <int G, int ITEMS, int L, typename KeyT>
 __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t* __restrict__ row_start,
                                                  const uint32_t* __restrict__ inc_sorted,
-                                                 const int32_t* __restrict__ dofs, uint32_t* __restrict__ perm,
-                                                 int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ useg_tmp,
-                                                 uint32_t* __restrict__ row_nnz) {
+                                                 const int32_t* __restrict__ dofs, uint8_t* __restrict__ slots,
+                                                 int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz,
+                                                 uint32_t* __restrict__ max_nnz) {
   constexpr int N = G * ITEMS;
+  constexpr int LP = L + (L & 1);
   constexpr bool K32 = sizeof(KeyT) == 4;
   constexpr int EB = (N <= 8) ? 3 : (N <= 16) ? 4 : (N <= 32) ? 5 : (N <= 64) ? 6 : (N <= 128) ? 7 : (N <= 256) ? 8 : 9;
   constexpr int CSH = K32 ? EB : 32;  // column shift inside the key
+  __shared__ uint32_t wmax[8];
   const int lane = threadIdx.x & 31;
   const int gl = lane % G;  // lane within the group
   const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
@@ -379,10 +383,9 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
     key[i] = (KeyT) ~(KeyT)0;
     if (e < ncand) {
       uint32_t q = e / L, b = e - q * L;
-      uint32_t inc = inc_sorted[rs + q];
-      uint32_t cell = inc / L;
+      uint32_t cell = inc_sorted[rs + q] / L;
       uint32_t col = (uint32_t)__ldg(dofs + (int64_t)cell * L + b);
-      key[i] = ((KeyT)col << CSH) | (KeyT)(K32 ? e : inc * L + b);
+      key[i] = ((KeyT)col << CSH) | (KeyT)e;
     }
   }
   // bitonic sort, ascending, N elements spread over G lanes
@@ -438,55 +441,142 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
     if (gl >= d) inc_ += t;
   }
   int total = __shfl_sync(FULL, inc_, (lane - gl) + G - 1);
-  int rank = inc_ - cnt;
+  int run = inc_ - cnt - 1;  // index of the run that is open when this lane starts
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     uint32_t e = gl * ITEMS + i;
     if (e < ncand) {
-      uint32_t src;
-      if (K32) {
-        uint32_t e0 = (uint32_t)key[i] & ((1u << EB) - 1u);  // position before sorting
-        uint32_t q = e0 / L, b = e0 - q * L;
-        src = inc_sorted[rs + q] * L + b;
-      } else {
-        src = (uint32_t)key[i];
-      }
-      perm[base + e] = src;
       if ((heads >> i) & 1u) {
-        ucol_tmp[base + rank] = (int32_t)(key[i] >> CSH);
-        useg_tmp[base + rank] = base + e;
-        ++rank;
+        ++run;
+        ucol_tmp[base + run] = (int32_t)(key[i] >> CSH);
       }
+      uint32_t e0 = (uint32_t)key[i] & ((1u << EB) - 1u);  // position before sorting
+      uint32_t q0 = e0 / L;
+      slots[(uint64_t)(rs + q0) * LP + (e0 - q0 * L)] = (uint8_t)run;  // row pitch LP = L rounded up to even
     }
   }
   if (live && gl == 0) row_nnz[r] = (uint32_t)total;
+  // largest row (integer max: order independent)
+  uint32_t mx = __reduce_max_sync(FULL, (uint32_t)total);
+  if (lane == 0) wmax[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; ++q) mx = wmax[q] > mx ? wmax[q] : mx;
+    atomicMax(max_nnz, mx);
+  }
 }
 
-// row_nnz has been exclusively scanned in place (row_off); copy each row's unique columns / run
-// starts from their scratch position to the final CSR arrays.
+// row_nnz has been exclusively scanned in place (row_off): copy each row's unique columns from
+// their scratch position to the final CSR arrays.
 template <typename IP>
 __global__ void __launch_bounds__(256) k_compact(int64_t n_rows, int L, const uint32_t* __restrict__ row_start,
                                                  const uint32_t* __restrict__ row_off,
-                                                 const int32_t* __restrict__ ucol_tmp,
-                                                 const uint32_t* __restrict__ useg_tmp, IP* __restrict__ indptr,
-                                                 int32_t* __restrict__ indices, uint32_t* __restrict__ seg,
-                                                 uint32_t n_coo) {
+                                                 const int32_t* __restrict__ ucol_tmp, IP* __restrict__ indptr,
+                                                 int32_t* __restrict__ indices) {
   // 8 lanes per row
   const int gl = threadIdx.x & 7;
   const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
   if (r > n_rows) return;
   uint32_t o0 = row_off[r];
   if (gl == 0) indptr[r] = (IP)o0;
-  if (r == n_rows) {
-    if (gl == 0) seg[o0] = n_coo;
-    return;
-  }
+  if (r == n_rows) return;
   uint32_t cnt = row_off[r + 1] - o0;
   uint32_t base = row_start[r] * (uint32_t)L;
-  for (uint32_t k = gl; k < cnt; k += 8) {
-    indices[o0 + k] = ucol_tmp[base + k];
-    seg[o0 + k] = useg_tmp[base + k];
+  for (uint32_t k = gl; k < cnt; k += 8) indices[o0 + k] = ucol_tmp[base + k];
+}
+
+// ---- numeric over row-sorted local rows (plans of the two-level symbolic) ------------------------
+// With such a plan K1 writes local row a of cell c straight to position inc_pos[c*L + a] of vals_t,
+// i.e. grouped by matrix row in ascending cell order (the order of the incidence transpose).  A CSR
+// row r then owns the CONTIGUOUS block vals_t[row_start[r]*L .. row_start[r+1]*L) and the uint8
+// column slots at the same positions.  One thread per row streams its block with 256-bit loads
+// (every 64-byte HBM atom is consumed, no gathers at all) and adds each value into the row's
+// accumulator acc[slot][thread] in shared memory (conflict-free).  Sequential in cell order => the
+// oracle's summation order, bit-reproducible, no atomics.  Reads per COO entry: 8 B + 1 B.
+__global__ void __launch_bounds__(256) k_inc_pos(uint32_t n_inc, const uint32_t* __restrict__ inc_sorted,
+                                                 uint32_t* __restrict__ inc_pos) {
+  uint32_t p = blockIdx.x * 256u + threadIdx.x;
+  if (p < n_inc) inc_pos[inc_sorted[p]] = p;
+}
+
+template <int L>
+__device__ __forceinline__ void load_row(const double* __restrict__ p, double (&v)[L]) {
+  if constexpr (L % 4 == 0) {
+#pragma unroll
+    for (int b = 0; b < L; b += 4)  // LDG.E.256
+      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                   : "=d"(v[b]), "=d"(v[b + 1]), "=d"(v[b + 2]), "=d"(v[b + 3])
+                   : "l"(p + b));
+  } else if constexpr (L % 2 == 0) {
+#pragma unroll
+    for (int b = 0; b < L; b += 2) {
+      double2 t = __ldg(reinterpret_cast<const double2*>(p + b));
+      v[b] = t.x;
+      v[b + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < L; ++b) v[b] = __ldg(p + b);
   }
+}
+
+template <int L>
+__device__ __forceinline__ void load_slots(const uint8_t* __restrict__ p, uint32_t (&sl)[L]) {
+  if constexpr (L % 4 == 0) {
+#pragma unroll
+    for (int b = 0; b < L; b += 4) {
+      uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + b));
+      sl[b] = w & 0xffu;
+      sl[b + 1] = (w >> 8) & 0xffu;
+      sl[b + 2] = (w >> 16) & 0xffu;
+      sl[b + 3] = w >> 24;
+    }
+  } else if constexpr (L % 2 == 0) {
+#pragma unroll
+    for (int b = 0; b < L; b += 2) {
+      uint32_t w = __ldg(reinterpret_cast<const uint16_t*>(p + b));
+      sl[b] = w & 0xffu;
+      sl[b + 1] = w >> 8;
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < L; ++b) sl[b] = __ldg(p + b);
+  }
+}
+
+template <int L, int BLK, typename IP>
+__global__ void __launch_bounds__(BLK) k_numeric_t(int64_t n_rows, const uint32_t* __restrict__ row_start,
+                                                   const uint8_t* __restrict__ slots, const IP* __restrict__ indptr,
+                                                   const double* __restrict__ vals_t, double* __restrict__ data) {
+  constexpr int U = (L <= 4) ? 4 : 2;  // local rows in flight per thread (8 measured slower)
+  constexpr int LP = L + (L & 1);      // row pitch (values and slots)
+  extern __shared__ double acc[];    // [slot][thread]
+  const int tid = threadIdx.x;
+  const int64_t r = (int64_t)blockIdx.x * BLK + tid;
+  if (r >= n_rows) return;
+  const uint32_t rs = row_start[r], re = row_start[r + 1];
+  const IP o0 = indptr[r];
+  const uint32_t cnt = (uint32_t)(indptr[r + 1] - o0);
+  for (uint32_t s2 = 0; s2 < cnt; ++s2) acc[s2 * BLK + tid] = 0.0;
+  for (uint32_t q0 = rs; q0 < re; q0 += U) {
+    double v[U][LP];
+    uint32_t sl[U][LP];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (q0 + u < re) {
+        load_row<LP>(vals_t + (uint64_t)(q0 + u) * LP, v[u]);
+        load_slots<LP>(slots + (uint64_t)(q0 + u) * LP, sl[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (q0 + u < re) {
+#pragma unroll
+        for (int b = 0; b < L; ++b) acc[sl[u][b] * BLK + tid] += v[u][b];
+      }
+    }
+  }
+  for (uint32_t s2 = 0; s2 < cnt; ++s2) data[o0 + s2] = acc[s2 * BLK + tid];
 }
 
 // ---- numeric: lane-sequential partial sums + warp-shuffle segmented scan ------------------------
@@ -679,7 +769,7 @@ struct WsLayout {
   // full sort
   int64_t keys_a, keys_b, perm_b;
   // two level
-  int64_t ikeys_a, ikeys_b, ipay_a, ipay_b, row_start, row_nnz, ucol, useg;
+  int64_t ikeys_a, ikeys_b, ipay_a, ipay_b, row_nnz, ucol;
   // shared
   int64_t hist, parts, meta, total;
 };
@@ -690,7 +780,7 @@ WsLayout ws_layout(int64_t n_coo, int64_t n_inc, int64_t n_rows, int mode) {
   int64_t o = 0;
   int64_t nsort = (mode == MODE_FULL_SORT) ? n_coo : n_inc;
   int64_t ntiles = pgb_cdiv(nsort > 0 ? nsort : 1, SORT_TILE);
-  l.meta = o;  o += 256;  // uint32: [0] mode, [1] cb, [2] nnz, [3] max incidences per row
+  l.meta = o;  o += 256;  // uint32: [0] mode, [1] cb, [2] nnz, [3] max incidences per row, [4] max row nnz
   l.parts = o; o += al(2048 * 4);
   l.hist = o;  o += al(ntiles * RADIX * 4);
   if (mode == MODE_FULL_SORT) {
@@ -702,10 +792,8 @@ WsLayout ws_layout(int64_t n_coo, int64_t n_inc, int64_t n_rows, int mode) {
     l.ikeys_b = o;   o += al(n_inc * 4);
     l.ipay_a = o;    o += al(n_inc * 4);
     l.ipay_b = o;    o += al(n_inc * 4);
-    l.row_start = o; o += al((n_rows + 2) * 4);
     l.row_nnz = o;   o += al((n_rows + 2) * 4);
     l.ucol = o;      o += al(n_coo * 4);
-    l.useg = o;      o += al(n_coo * 4);
   }
   l.total = o;
   return l;
@@ -725,33 +813,35 @@ ChunkGrid chunk_grid(int64_t n) {
 
 template <int G, int ITEMS, typename KeyT>
 int launch_rowsort_l(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
-                     uint32_t* perm, int32_t* ucol, uint32_t* useg, uint32_t* row_nnz, cudaStream_t s) {
+                     uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
   unsigned grid = pgb_grid(n_rows * G, 256);
+#define PGB_RL(LL) k_rowsort<G, ITEMS, LL, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz)
   switch (L) {
-    case 3: k_rowsort<G, ITEMS, 3, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
-    case 4: k_rowsort<G, ITEMS, 4, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
-    case 5: k_rowsort<G, ITEMS, 5, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
-    case 6: k_rowsort<G, ITEMS, 6, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
-    case 12: k_rowsort<G, ITEMS, 12, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz); break;
+    case 3: PGB_RL(3); break;
+    case 4: PGB_RL(4); break;
+    case 5: PGB_RL(5); break;
+    case 6: PGB_RL(6); break;
+    case 12: PGB_RL(12); break;
     default: pgb_set_error("k_rowsort: unsupported local size %d", L); return 2;
   }
+#undef PGB_RL
   PGB_LAUNCH_CHECK();
   return 0;
 }
 
 template <int G, int ITEMS>
 int launch_rowsort_k(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
-                     uint32_t* perm, int32_t* ucol, uint32_t* useg, uint32_t* row_nnz, cudaStream_t s) {
+                     uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
   // 32-bit keys when (col, position-in-row) fits strictly below the padding value 0xffffffff
   if ((uint64_t)n_rows * (uint64_t)(G * ITEMS) <= 0xffffffffull && !g_force_key64)
-    return launch_rowsort_l<G, ITEMS, uint32_t>(L, n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz, s);
-  return launch_rowsort_l<G, ITEMS, uint64_t>(L, n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz, s);
+    return launch_rowsort_l<G, ITEMS, uint32_t>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
+  return launch_rowsort_l<G, ITEMS, uint64_t>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
 }
 
 int launch_rowsort(uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc,
-                   const int32_t* dofs, uint32_t* perm, int32_t* ucol, uint32_t* useg, uint32_t* row_nnz,
+                   const int32_t* dofs, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
                    cudaStream_t s) {
-#define PGB_RS(G, I) return launch_rowsort_k<G, I>(L, n_rows, row_start, inc, dofs, perm, ucol, useg, row_nnz, s)
+#define PGB_RS(G, I) return launch_rowsort_k<G, I>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s)
   if (max_cand <= 8) PGB_RS(4, 2);
   if (max_cand <= 16) PGB_RS(8, 2);
   if (max_cand <= 32) PGB_RS(8, 4);
@@ -760,6 +850,42 @@ int launch_rowsort(uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row
   if (max_cand <= 256) PGB_RS(32, 8);
   PGB_RS(32, 16);
 #undef PGB_RS
+}
+
+template <int L, int BLK, typename IP>
+int launch_numeric_t_b(int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots, const void* indptr,
+                       const double* vals_t, double* data, cudaStream_t s) {
+  size_t smem = (size_t)caps * BLK * sizeof(double);
+  static size_t attr = 48 * 1024;
+  if (smem > attr) {
+    PGB_CHECK(cudaFuncSetAttribute(k_numeric_t<L, BLK, IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  k_numeric_t<L, BLK, IP><<<(unsigned)pgb_cdiv(n_rows, BLK), BLK, smem, s>>>(n_rows, row_start, slots,
+                                                                             (const IP*)indptr, vals_t, data);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int L, typename IP>
+int launch_numeric_t_l(int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots, const void* indptr,
+                       const double* vals_t, double* data, cudaStream_t s) {
+  if (caps <= 200) return launch_numeric_t_b<L, 128, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+  return launch_numeric_t_b<L, 64, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+}
+
+template <typename IP>
+int launch_numeric_t(int L, int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots,
+                     const void* indptr, const double* vals_t, double* data, cudaStream_t s) {
+  switch (L) {
+    case 3: return launch_numeric_t_l<3, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+    case 4: return launch_numeric_t_l<4, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+    case 5: return launch_numeric_t_l<5, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+    case 6: return launch_numeric_t_l<6, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+    case 12: return launch_numeric_t_l<12, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+  }
+  pgb_set_error("pgb_csr_numeric_rows: unsupported local size %d", L);
+  return 2;
 }
 
 }  // namespace
@@ -776,8 +902,9 @@ extern "C" int64_t pgb_csr_workspace_bytes(int64_t nc, int L, int64_t n_rows, in
 }
 
 extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell_dofs, int mode,
-                                     void* workspace, int64_t workspace_bytes, uint32_t* perm,
-                                     int64_t* nnz_host, void* stream) {
+                                     void* workspace, int64_t workspace_bytes, uint32_t* perm_or_inc,
+                                     uint8_t* slots, uint32_t* row_start, int64_t* nnz_host,
+                                     int* max_row_nnz_host, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n_coo = nc * L * L, n_inc = nc * L;
   PGB_REQUIRE(mode >= 0 && mode <= 2, "pgb_csr_symbolic_sort: bad mode");
@@ -787,18 +914,22 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
   WsLayout l = ws_layout(n_coo, n_inc, n_rows, mode);
   PGB_REQUIRE(workspace_bytes >= l.total, "pgb_csr_symbolic_sort: workspace too small");
   *nnz_host = 0;
+  if (max_row_nnz_host) *max_row_nnz_host = 0;
   char* ws = (char*)workspace;
   uint32_t* meta = (uint32_t*)(ws + l.meta);
   uint32_t* parts = (uint32_t*)(ws + l.parts);
   uint32_t* hist = (uint32_t*)(ws + l.hist);
   const int cb = bits_for(n_rows);
-  uint32_t m[4] = {(uint32_t)mode, (uint32_t)cb, 0u, 0u};
+  uint32_t m[5] = {(uint32_t)mode, (uint32_t)cb, 0u, 0u, 0u};
   PGB_CHECK(cudaMemcpyAsync(meta, m, sizeof(m), cudaMemcpyHostToDevice, s));
-  if (n_coo == 0) return 0;
+  if (n_coo == 0) {
+    if (mode != MODE_FULL_SORT) PGB_CHECK(cudaMemsetAsync(row_start, 0, sizeof(uint32_t) * (n_rows + 1), s));
+    return 0;
+  }
 
   if (mode == MODE_FULL_SORT) {
     uint64_t* kbuf[2] = {(uint64_t*)(ws + l.keys_a), (uint64_t*)(ws + l.keys_b)};
-    uint32_t* pbuf[2] = {perm, (uint32_t*)(ws + l.perm_b)};
+    uint32_t* pbuf[2] = {perm_or_inc, (uint32_t*)(ws + l.perm_b)};
     KeySrc<uint64_t> src{nullptr, cell_dofs, (uint32_t)L, (uint32_t)(L * L), cb};
     if (radix_sort<uint64_t>(src, (uint32_t)n_coo, 2 * cb, kbuf, pbuf, hist, parts, s)) return 1;
     ChunkGrid cg = chunk_grid(n_coo);
@@ -806,15 +937,16 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     k_scan_parts<<<1, 256, 0, s>>>(parts, (int)cg.g, meta + 2);
     PGB_LAUNCH_CHECK();
   } else {
+    PGB_REQUIRE(slots && row_start, "pgb_csr_symbolic_sort: slots / row_start required in two-level mode");
     uint32_t* kbuf[2] = {(uint32_t*)(ws + l.ikeys_a), (uint32_t*)(ws + l.ikeys_b)};
-    uint32_t* pbuf[2] = {(uint32_t*)(ws + l.ipay_a), (uint32_t*)(ws + l.ipay_b)};
-    uint32_t* row_start = (uint32_t*)(ws + l.row_start);
+    uint32_t* pbuf[2] = {(uint32_t*)(ws + l.ipay_a), (uint32_t*)(ws + l.ipay_b)};  // pbuf[0]: sorted incidences
     uint32_t* row_nnz = (uint32_t*)(ws + l.row_nnz);
     KeySrc<uint32_t> src{nullptr, cell_dofs, (uint32_t)L, (uint32_t)(L * L), cb};
     PhaseTimer pt(s);
     pt.mark();
     if (radix_sort<uint32_t>(src, (uint32_t)n_inc, cb, kbuf, pbuf, hist, parts, s)) return 1;
     pt.mark();
+    k_inc_pos<<<pgb_grid(n_inc, 256), 256, 0, s>>>((uint32_t)n_inc, pbuf[0], perm_or_inc);  // inverse permutation
     k_row_starts<<<pgb_grid(n_inc, 256), 256, 0, s>>>(kbuf[0], (uint32_t)n_inc, n_rows, row_start);
     k_max_row<<<(unsigned)(n_rows < 256 * 1184 ? pgb_grid(n_rows, 256) : 1184), 256, 0, s>>>(n_rows, row_start, meta + 3);
     PGB_LAUNCH_CHECK();
@@ -828,8 +960,8 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     }
     PGB_CHECK(cudaMemsetAsync(row_nnz + n_rows, 0, 2 * sizeof(uint32_t), s));
     pt.mark();
-    if (launch_rowsort(max_inc * (uint32_t)L, L, n_rows, row_start, pbuf[0], cell_dofs, perm,
-                       (int32_t*)(ws + l.ucol), (uint32_t*)(ws + l.useg), row_nnz, s))
+    if (launch_rowsort(max_inc * (uint32_t)L, L, n_rows, row_start, pbuf[0], cell_dofs, slots,
+                       (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s))
       return 1;
     pt.mark();
     if (scan_u32(row_nnz, (uint64_t)n_rows + 1, parts, nullptr, s)) return 1;
@@ -837,16 +969,21 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     pt.mark();
     pt.finish();
   }
-  uint32_t nnz32 = 0;
-  PGB_CHECK(cudaMemcpyAsync(&nnz32, meta + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  uint32_t out2[3] = {0, 0, 0};
+  PGB_CHECK(cudaMemcpyAsync(out2, meta + 2, sizeof(out2), cudaMemcpyDeviceToHost, s));
   PGB_CHECK(cudaStreamSynchronize(s));
-  *nnz_host = (int64_t)nnz32;
+  *nnz_host = (int64_t)out2[0];
+  if (max_row_nnz_host) *max_row_nnz_host = (int)out2[2];
+  if (mode != MODE_FULL_SORT && out2[2] > 255u) {
+    pgb_set_error("pgb_csr_symbolic_sort: a row has %u entries (> 255, the uint8 slot range); use mode 1", out2[2]);
+    return 3;
+  }
   return 0;
 }
 
 extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mode, int64_t nnz,
-                                       const void* workspace, void* indptr, int idx64, int32_t* indices,
-                                       uint32_t* seg, void* stream) {
+                                       const void* workspace, const uint32_t* row_start, void* indptr, int idx64,
+                                       int32_t* indices, uint32_t* seg, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n_coo = nc * L * L, n_inc = nc * L;
   if (n_coo == 0) {
@@ -859,6 +996,7 @@ extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mo
   const char* ws = (const char*)workspace;
   const int cb = bits_for(n_rows);
   if (mode == MODE_FULL_SORT) {
+    PGB_REQUIRE(seg, "pgb_csr_symbolic_finish: seg required in mode 1");
     const uint64_t* keys = (const uint64_t*)(ws + l.keys_a);
     const uint32_t* parts = (const uint32_t*)(ws + l.parts);
     ChunkGrid cg = chunk_grid(n_coo);
@@ -869,20 +1007,28 @@ extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mo
       k_emit_unique<int32_t><<<(unsigned)cg.g, 256, 0, s>>>(keys, (uint64_t)n_coo, cg.chunk, parts, cb, n_rows,
                                                             (uint32_t)nnz, (int32_t*)indptr, indices, seg);
   } else {
-    const uint32_t* row_start = (const uint32_t*)(ws + l.row_start);
+    PGB_REQUIRE(row_start, "pgb_csr_symbolic_finish: row_start required in two-level mode");
     const uint32_t* row_off = (const uint32_t*)(ws + l.row_nnz);
     const int32_t* ucol = (const int32_t*)(ws + l.ucol);
-    const uint32_t* useg = (const uint32_t*)(ws + l.useg);
     unsigned grid = pgb_grid((n_rows + 1) * 8, 256);
     if (idx64)
-      k_compact<int64_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, useg, (int64_t*)indptr, indices,
-                                              seg, (uint32_t)n_coo);
+      k_compact<int64_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, (int64_t*)indptr, indices);
     else
-      k_compact<int32_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, useg, (int32_t*)indptr, indices,
-                                              seg, (uint32_t)n_coo);
+      k_compact<int32_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, (int32_t*)indptr, indices);
   }
   PGB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, const uint32_t* row_start,
+                                    const uint8_t* slots, const void* indptr, int idx64, const double* vals_t,
+                                    double* data, void* stream) {
+  if (n_rows == 0) return 0;
+  PGB_REQUIRE(max_row_nnz >= 0 && max_row_nnz <= 255, "pgb_csr_numeric_rows: max_row_nnz out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  int caps = max_row_nnz < 1 ? 1 : max_row_nnz;
+  return idx64 ? launch_numeric_t<int64_t>(L, n_rows, caps, row_start, slots, indptr, vals_t, data, s)
+               : launch_numeric_t<int32_t>(L, n_rows, caps, row_start, slots, indptr, vals_t, data, s);
 }
 
 extern "C" int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t* seg,

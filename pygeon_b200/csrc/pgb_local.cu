@@ -21,6 +21,7 @@ struct Params {
   const double* coords;
   const double* K;
   const double* w;
+  const uint32_t* dst_pos;  // nullable: destination row of every local row (row-sorted layout)
   double* vals;
   double R[9];
   int r_ident;
@@ -214,11 +215,36 @@ __global__ void __launch_bounds__(BLOCK) k_local(Params p) {
   const int64_t c = c0 + tid;
   const bool live = c < p.nc;
 
+  // Row-sorted output (p.dst_pos): every kind emits its values in row-major order, so a local row
+  // is complete when k % L == L-1; it is then stored with vector stores (STG.E.256 for L % 4 == 0)
+  // at its destination row.  Otherwise: shared-memory staging + coalesced stream-out.
+  // Rows are stored with pitch LP = L rounded up to even, so that they are 16-byte aligned.
+  const bool rowmajor = p.dst_pos != nullptr;
+  constexpr int LP = L + (L & 1);
+  double rowbuf[LP];
+  if constexpr (LP != L) rowbuf[LP - 1] = 0.0;
+  auto flush_row = [&](int row) {
+    double* dst = p.vals + (uint64_t)p.dst_pos[c * L + row] * LP;
+    if constexpr (LP % 4 == 0) {
+#pragma unroll
+      for (int b = 0; b < LP; b += 4)
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst + b), "d"(rowbuf[b]), "d"(rowbuf[b + 1]),
+                     "d"(rowbuf[b + 2]), "d"(rowbuf[b + 3])
+                     : "memory");
+    } else {
+#pragma unroll
+      for (int b = 0; b < LP; b += 2) *reinterpret_cast<double2*>(dst + b) = make_double2(rowbuf[b], rowbuf[b + 1]);
+    }
+  };
   auto emit = [&](int k, double v) {
-    if constexpr (STAGED)
+    if (rowmajor) {
+      rowbuf[k % L] = v;
+      if (k % L == L - 1) flush_row(k / L);
+    } else if constexpr (STAGED) {
       tile[k * (BLOCK + 1) + tid] = v;
-    else
+    } else {
       p.vals[c * LL + k] = v;
+    }
   };
 
   if (live) {
@@ -241,10 +267,10 @@ __global__ void __launch_bounds__(BLOCK) k_local(Params p) {
       for (int a = 0; a <= D; ++a) {
 #pragma unroll
         for (int b = 0; b <= D; ++b) emit(a * L + b, A[a][b]);
-        double ba = ((sb >> a) & 1u) ? bv : -bv;  // -B^T entry: -(s_a w/|c|)
-        emit(a * L + (D + 1), ba);
-        emit((D + 1) * L + a, ba);
+        emit(a * L + (D + 1), ((sb >> a) & 1u) ? bv : -bv);  // -B^T entry: -(s_a w/|c|)
       }
+#pragma unroll
+      for (int a = 0; a <= D; ++a) emit((D + 1) * L + a, ((sb >> a) & 1u) ? bv : -bv);  // -B row
       emit((D + 1) * L + (D + 1), 0.0);
     } else if constexpr (KIND == PGB_L1_LUMPED) {
       double wv = w * g.vol / (D + 1);
@@ -437,7 +463,7 @@ __global__ void __launch_bounds__(BLOCK) k_local(Params p) {
     }
   }
 
-  if constexpr (STAGED) {
+  if (STAGED && !rowmajor) {
     __syncthreads();
     int64_t rem = p.nc - c0;
     int nb = rem < BLOCK ? (int)rem : BLOCK;
@@ -501,7 +527,7 @@ extern "C" int pgb_local_size(int kind, int dim) {
 extern "C" int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
                                   const uint8_t* sign_bits, const uint32_t* aux_bits,
                                   const double* coords, const double* K, const double* R_host,
-                                  const double* w, double* vals, void* stream) {
+                                  const double* w, const uint32_t* dst_pos, double* vals, void* stream) {
   PGB_REQUIRE(dim == 2 || dim == 3, "pgb_local_matrices: dim must be 2 or 3");
   PGB_REQUIRE(cell_nodes && coords && vals, "pgb_local_matrices: null pointer");
   if (kind == PGB_RT0_MASS || kind == PGB_BDM1_MASS || kind == PGB_N0_CURLCURL ||
@@ -519,6 +545,7 @@ extern "C" int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* 
   p.coords = coords;
   p.K = K;
   p.w = w;
+  p.dst_pos = dst_pos;
   p.vals = vals;
   bool ident = true;
   for (int i = 0; i < 9; ++i) {

@@ -319,13 +319,25 @@ class GridPack:
 # --------------------------------------------------------------------------------------
 @dataclass
 class CsrPlan:
+    """Result of the symbolic phase, reusable by every operator of a space on the grid.
+
+    mode 0 (two level): K1 writes the local rows to ``inc_pos`` (row-sorted order) and the
+    streaming numeric kernel reduces them through ``row_start`` / ``slots``;
+    mode 1 (full sort): ``perm, seg`` drive the segmented-reduce numeric kernel."""
+
     n_rows: int
     n_coo: int
     nnz: int
-    perm: torch.Tensor  # uint32 stored as int32
-    seg: torch.Tensor
+    L: int
+    mode: int
     indptr: torch.Tensor
     indices: torch.Tensor
+    perm: torch.Tensor | None = None  # mode 1: uint32 stored as int32
+    seg: torch.Tensor | None = None
+    inc_pos: torch.Tensor | None = None  # mode 0: row-sorted position of every local row (for K1)
+    row_start: torch.Tensor | None = None
+    slots: torch.Tensor | None = None
+    max_row_nnz: int = 0
 
 
 @dataclass
@@ -385,32 +397,38 @@ class DeviceCSR:
 
 symbolic_mode = 0  # 0 = two-level (default), 1 = full (row,col) radix sort; see include/pgb.h
 force_idx64 = False  # tests: emit int64 indptr even when nnz < 2^31
-overlap_streams = False  # optional: run K1 on a side stream next to the symbolic phase (no measurable gain on B200: both kernels fill the SMs)
 
 
 def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
-    """Sort-by-(row,col) of the cell->dof incidences: pattern + gather permutation."""
+    """Sort-by-(row,col) of the cell->dof incidences: CSR pattern + the gather plan."""
     mode = symbolic_mode if mode is None else mode
     key = ("plan", space)
     if key in pack.plans:
         return pack.plans[key]
     dofs, n_rows = pack.dofs(space)
     nc, L = int(dofs.shape[0]), int(dofs.shape[1])
-    n_coo = nc * L * L
+    n_coo, n_inc = nc * L * L, nc * L
     dev = pack.device
     with torch.cuda.device(dev):
         s = _stream()
         dofs = dofs.contiguous()
-        perm = torch.empty((max(n_coo, 1),), dtype=_I32, device=dev)
         while True:
             ws_bytes = int(lib.pgb_csr_workspace_bytes(nc, L, n_rows, mode))
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-            nnz = C.c_int64(0)
+            if mode == 1:
+                first = torch.empty((max(n_coo, 1),), dtype=_I32, device=dev)  # perm
+                slots = row_start = None
+            else:
+                first = torch.empty((max(n_inc, 1),), dtype=_I32, device=dev)  # inc_pos
+                slots = torch.zeros((max(n_inc * (L + (L & 1)), 1),), dtype=torch.uint8, device=dev)
+                row_start = torch.empty((n_rows + 1,), dtype=_I32, device=dev)
+            nnz, mx = C.c_int64(0), C.c_int(0)
             rc = lib.pgb_csr_symbolic_sort(n_rows, nc, L, dofs.data_ptr(), mode, ws.data_ptr(), ws_bytes,
-                                           perm.data_ptr(), C.byref(nnz), s)
-            if rc == 3 and mode == 0:  # a dof shared by too many cells for the register sort
+                                           first.data_ptr(), _ptr(slots), _ptr(row_start), C.byref(nnz),
+                                           C.byref(mx), s)
+            if rc == 3 and mode != 1:  # a dof shared by too many cells / a row too long for the register sort
                 mode = 1
-                del ws
+                del ws, first, slots, row_start
                 continue
             check(rc)
             break
@@ -418,17 +436,21 @@ def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
         it = torch.int64 if (nnz >= 2**31 or force_idx64) else _I32
         indptr = torch.empty((n_rows + 1,), dtype=it, device=dev)
         indices = torch.empty((nnz,), dtype=_I32, device=dev)
-        seg = torch.empty((nnz + 1,), dtype=_I32, device=dev)
-        check(lib.pgb_csr_symbolic_finish(n_rows, nc, L, mode, nnz, ws.data_ptr(), indptr.data_ptr(),
-                                          1 if it == torch.int64 else 0, indices.data_ptr(),
-                                          seg.data_ptr(), s))
+        seg = torch.empty((nnz + 1,), dtype=_I32, device=dev) if mode == 1 else None
+        check(lib.pgb_csr_symbolic_finish(n_rows, nc, L, mode, nnz, ws.data_ptr(), _ptr(row_start),
+                                          indptr.data_ptr(), 1 if it == torch.int64 else 0, indices.data_ptr(),
+                                          _ptr(seg), s))
         bits = max(1, int(n_rows - 1).bit_length()) if n_rows > 1 else 1
         if mode == 1:
             _lib.count(((2 * bits + 7) // 8) * 5 + 3)
         else:
             _lib.count(((bits + 7) // 8) * 5 + 7)
         del ws
-    plan = CsrPlan(n_rows, n_coo, nnz, perm, seg, indptr, indices)
+    if mode == 1:
+        plan = CsrPlan(n_rows, n_coo, nnz, L, 1, indptr, indices, perm=first, seg=seg)
+    else:
+        plan = CsrPlan(n_rows, n_coo, nnz, L, 0, indptr, indices, inc_pos=first, row_start=row_start,
+                       slots=slots, max_row_nnz=int(mx.value))
     pack.plans[key] = plan
     return plan
 
@@ -451,8 +473,10 @@ _FORMS = {
 }
 
 
-def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None) -> torch.Tensor:
-    """K1: vals (nc, L*L) on the device.  ``w`` (nc,) / ``K`` (3,3,nc) are device tensors or None."""
+def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None, plan: "CsrPlan | None" = None) -> torch.Tensor:
+    """K1: vals (nc, L*L) on the device.  ``w`` (nc,) / ``K`` (3,3,nc) are device tensors or None.
+    With a mode-0 ``plan`` the local rows are written in the plan's row-sorted order (what
+    :func:`numeric` expects for that plan); without, in plain [cell][a][b] order."""
     d, nc, dev = pack.dim, pack.nc, pack.device
     L = int(lib.pgb_local_size(KIND[kind], d))
     aux = None
@@ -464,11 +488,14 @@ def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None) -> torch
     elif kind in ("bdm1_mass", "bdm1_lumped"):
         aux = pack.bdm1()[1]
     with torch.cuda.device(dev):
-        vals = out if out is not None else torch.empty((nc, L * L), dtype=torch.float64, device=dev)
+        rowmajor = plan is not None and plan.mode == 0
+        pitch = L + (L & 1) if rowmajor else L  # row-sorted layout: rows padded to an even length
+        vals = out if out is not None else torch.empty((nc, L * pitch), dtype=torch.float64, device=dev)
         check(
             lib.pgb_local_matrices(
                 KIND[kind], d, nc, pack.cell_nodes.data_ptr(), _ptr(sign_bits), _ptr(aux),
-                pack.coords.data_ptr(), _ptr(K), pack.R.ctypes.data, _ptr(w), vals.data_ptr(), _stream(),
+                pack.coords.data_ptr(), _ptr(K), pack.R.ctypes.data, _ptr(w),
+                _ptr(plan.inc_pos) if (plan is not None and plan.mode == 0) else 0, vals.data_ptr(), _stream(),
             )
         )
         _lib.count(1)
@@ -476,12 +503,18 @@ def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None) -> torch
 
 
 def numeric(plan: CsrPlan, vals: torch.Tensor, out=None) -> torch.Tensor:
-    """K2 numeric phase: gather through the permutation + segmented reduce."""
+    """K2 numeric phase: local values -> CSR data through the plan (fixed summation order)."""
     dev = vals.device
     with torch.cuda.device(dev):
         data = out if out is not None else torch.empty((plan.nnz,), dtype=torch.float64, device=dev)
-        check(lib.pgb_csr_numeric(plan.nnz, plan.perm.data_ptr(), plan.seg.data_ptr(), vals.data_ptr(),
-                                  data.data_ptr(), _stream()))
+        if plan.mode == 1:
+            check(lib.pgb_csr_numeric(plan.nnz, plan.perm.data_ptr(), plan.seg.data_ptr(), vals.data_ptr(),
+                                      data.data_ptr(), _stream()))
+        else:
+            check(lib.pgb_csr_numeric_rows(plan.n_rows, plan.L, plan.max_row_nnz, plan.row_start.data_ptr(),
+                                           plan.slots.data_ptr(), plan.indptr.data_ptr(),
+                                           1 if plan.indptr.dtype == torch.int64 else 0,
+                                           vals.data_ptr(), data.data_ptr(), _stream()))
         _lib.count(1)
     return data
 
@@ -514,36 +547,10 @@ _SIDE: dict = {}
 
 
 def assemble_on_pack(pack: GridPack, space: str, kind: str, wd=None, Kd=None):
-    """symbolic (cached per pack) + K1 + K2 numeric.  When the plan still has to be built, K1 - a
-    pure HBM streaming kernel - runs on a side stream concurrently with the symbolic phase, whose
-    dominant kernel (the per-row register sort) is issue bound and leaves the memory system idle."""
-    dev = pack.device
-    cached = ("plan", space) in pack.plans
-    if cached or not overlap_streams:
-        plan = symbolic(pack, space)
-        vals = local_matrices(pack, kind, wd, Kd)
-        return plan, numeric(plan, vals)
-    with torch.cuda.device(dev):
-        main = torch.cuda.current_stream()
-        side = _SIDE.get(dev)
-        if side is None:
-            side = _SIDE[dev] = torch.cuda.Stream(device=dev)
-        if kind in ("n0_mass", "n0_curlcurl"):
-            pack.edges()  # aux tables must exist before the side stream reads them
-        elif kind in ("bdm1_mass", "bdm1_lumped"):
-            pack.bdm1()
-        ready = torch.cuda.Event()
-        ready.record(main)
-        with torch.cuda.stream(side):
-            side.wait_event(ready)
-            vals = local_matrices(pack, kind, wd, Kd)
-            done = torch.cuda.Event()
-            done.record(side)
-        plan = symbolic(pack, space)
-        main.wait_event(done)
-        vals.record_stream(main)
-        data = numeric(plan, vals)
-    return plan, data
+    """symbolic (cached per pack) -> K1 (writing the local rows where the plan wants them) -> K2."""
+    plan = symbolic(pack, space)
+    vals = local_matrices(pack, kind, wd, Kd, plan=plan)
+    return plan, numeric(plan, vals)
 
 
 def assemble_device(space: str, form: str, sd, w=None, K=None, device=None) -> DeviceCSR:

@@ -39,7 +39,7 @@ for rep in range(2):
     pack = engine.GridPack.from_raw(raw)
     plan = engine.symbolic(pack, "darcy")
     e[1].record()
-    vals = engine.local_matrices(pack, "darcy_saddle")
+    vals = engine.local_matrices(pack, "darcy_saddle", plan=plan)
     e[2].record()
     data = engine.numeric(plan, vals)
     e[3].record()

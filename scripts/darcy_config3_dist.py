@@ -49,7 +49,7 @@ for rep in range(3):
     pack = engine.GridPack.from_raw(raw)
     plan = engine.symbolic(pack, "darcy")
     e[1].record()
-    data = engine.numeric(plan, engine.local_matrices(pack, "darcy_saddle"))
+    data = engine.numeric(plan, engine.local_matrices(pack, "darcy_saddle", plan=plan))
     e[2].record()
     barrier()
     t = torch.tensor([e[0].elapsed_time(e[2]), e[1].elapsed_time(e[2])], dtype=torch.float64, device=dev)

@@ -30,7 +30,7 @@ for _ in range(reps):
     plan = engine.symbolic(pack, space)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    vals = engine.local_matrices(pack, kind)
+    vals = engine.local_matrices(pack, kind, plan=plan)
     data = engine.numeric(plan, vals)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
@@ -41,7 +41,7 @@ for _ in range(reps):
 torch.cuda.synchronize()
 if cg_iters and space == "lagrange1":
     A = engine.DeviceCSR((plan.n_rows, plan.n_rows), plan.indptr, plan.indices, data)
-    A.data += engine.numeric(plan, engine.local_matrices(pack, "l1_mass"))
+    A.data += engine.numeric(plan, engine.local_matrices(pack, "l1_mass", plan=plan))
     b = torch.ones(plan.n_rows, dtype=torch.float64, device=dev)
     x, info = cg_device(A, b, rtol=0.0, maxiter=cg_iters)
     torch.cuda.synchronize()

@@ -28,7 +28,7 @@ for dim, n in ((2, 7), (3, 3)):
     for mode in (1, 2):
         pack = engine.GridPack.from_grid(sd)
         plan = engine.symbolic(pack, "nedelec0", mode=mode)
-        engine.numeric(plan, engine.local_matrices(pack, "n0_mass"))
+        engine.numeric(plan, engine.local_matrices(pack, "n0_mass", plan=plan))
     S = pg.Lagrange1().assemble_stiff_matrix(sd) + pg.Lagrange1().assemble_mass_matrix(sd)
     b = np.ones(sd.num_nodes)
     pg.cg(S, b, rtol=1e-10, maxiter=200)

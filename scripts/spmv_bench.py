@@ -15,7 +15,7 @@ for space, kind, n in (("lagrange1", "l1_stiff", 128), ("rt0", "rt0_mass", 96), 
     raw = engine.RawGrid.upload(sd, dev, ridges=(space == "nedelec0"))
     pack = engine.GridPack.from_raw(raw)
     plan = engine.symbolic(pack, space)
-    data = engine.numeric(plan, engine.local_matrices(pack, kind))
+    data = engine.numeric(plan, engine.local_matrices(pack, kind, plan=plan))
     nr, nnz = plan.n_rows, plan.nnz
     x = torch.randn(nr, dtype=torch.float64, device=dev)
     y = torch.empty_like(x)

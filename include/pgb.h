@@ -114,8 +114,8 @@ enum {
 int pgb_local_size(int kind, int dim); /* L */
 /* dst_pos (nullable): [nc*L] destination row of every local row (the inc_pos of a mode-0 plan);
  * local row a of cell c is then written to vals[dst_pos[c*L+a]*LP .. +L) instead of
- * vals[(c*L+a)*L .. +L), with the row pitch LP = L rounded up to even (16-byte aligned rows; vals
- * then holds nc*L*LP doubles, the slots array of the plan nc*L*LP bytes). */
+ * vals[(c*L+a)*L .. +L), with the row pitch LP = L rounded up to a multiple of 4 (rows are whole
+ * 32-byte sectors; vals then holds nc*L*LP doubles, the slots array of the plan nc*L*LP bytes). */
 int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
                        const uint8_t* sign_bits, const uint32_t* aux_bits, const double* coords,
                        const double* K, const double* R_host, const double* w, const uint32_t* dst_pos,

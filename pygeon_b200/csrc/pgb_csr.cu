@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
                                                  int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz,
                                                  uint32_t* __restrict__ max_nnz) {
   constexpr int N = G * ITEMS;
-  constexpr int LP = L + (L & 1);
+  constexpr int LP = (L + 3) & ~3;
   constexpr bool K32 = sizeof(KeyT) == 4;
   constexpr int EB = (N <= 8) ? 3 : (N <= 16) ? 4 : (N <= 32) ? 5 : (N <= 64) ? 6 : (N <= 128) ? 7 : (N <= 256) ? 8 : 9;
   constexpr int CSH = K32 ? EB : 32;  // column shift inside the key
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
       }
       uint32_t e0 = (uint32_t)key[i] & ((1u << EB) - 1u);  // position before sorting
       uint32_t q0 = e0 / L;
-      slots[(uint64_t)(rs + q0) * LP + (e0 - q0 * L)] = (uint8_t)run;  // row pitch LP = L rounded up to even
+      slots[(uint64_t)(rs + q0) * LP + (e0 - q0 * L)] = (uint8_t)run;  // row pitch LP = L rounded up to a multiple of 4
     }
   }
   if (live && gl == 0) row_nnz[r] = (uint32_t)total;
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(BLK) k_numeric_t(int64_t n_rows, const uint32_
                                                    const uint8_t* __restrict__ slots, const IP* __restrict__ indptr,
                                                    const double* __restrict__ vals_t, double* __restrict__ data) {
   constexpr int U = (L <= 4) ? 4 : 2;  // local rows in flight per thread (8 measured slower)
-  constexpr int LP = L + (L & 1);      // row pitch (values and slots)
+  constexpr int LP = (L + 3) & ~3;      // row pitch (values and slots)
   extern __shared__ double acc[];    // [slot][thread]
   const int tid = threadIdx.x;
   const int64_t r = (int64_t)blockIdx.x * BLK + tid;

@@ -420,7 +420,7 @@ def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
                 slots = row_start = None
             else:
                 first = torch.empty((max(n_inc, 1),), dtype=_I32, device=dev)  # inc_pos
-                slots = torch.zeros((max(n_inc * (L + (L & 1)), 1),), dtype=torch.uint8, device=dev)
+                slots = torch.zeros((max(n_inc * ((L + 3) & ~3), 1),), dtype=torch.uint8, device=dev)
                 row_start = torch.empty((n_rows + 1,), dtype=_I32, device=dev)
             nnz, mx = C.c_int64(0), C.c_int(0)
             rc = lib.pgb_csr_symbolic_sort(n_rows, nc, L, dofs.data_ptr(), mode, ws.data_ptr(), ws_bytes,
@@ -489,7 +489,7 @@ def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None, plan: "C
         aux = pack.bdm1()[1]
     with torch.cuda.device(dev):
         rowmajor = plan is not None and plan.mode == 0
-        pitch = L + (L & 1) if rowmajor else L  # row-sorted layout: rows padded to an even length
+        pitch = ((L + 3) & ~3) if rowmajor else L  # row-sorted layout: rows padded to whole 32-byte sectors
         vals = out if out is not None else torch.empty((nc, L * pitch), dtype=torch.float64, device=dev)
         check(
             lib.pgb_local_matrices(

@@ -565,7 +565,11 @@ __global__ void __launch_bounds__(256) k_rowhash(int64_t n_rows, const uint32_t*
 #pragma unroll
   for (int k = 0; k < HASH_SIZE / 32; ++k) tkey[k * 32 + lane] = HASH_EMPTY;
   __syncwarp();
-  // candidates, strided: e = i*32 + lane; insert their columns
+  // candidates, strided: e = i*32 + lane; insert their columns.  Every incident cell contributes
+  // the row's own dof once (the worst same-address conflict): it is inserted by lane 0 alone.
+  const uint32_t hdiag = hash_col((uint32_t)r);
+  if (lane == 0 && ncand) tkey[hdiag] = (uint32_t)r;
+  __syncwarp();
   uint32_t hpos[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) {
@@ -576,6 +580,10 @@ __global__ void __launch_bounds__(256) k_rowhash(int64_t n_rows, const uint32_t*
       uint32_t cell = inc_sorted[rs + q] / L;
       uint32_t col = (uint32_t)__ldg(dofs + (int64_t)cell * L + b);
       uint32_t h = hash_col(col);
+      if (col == (uint32_t)r) {
+        hpos[i] = hdiag;
+        continue;
+      }
       while (true) {
         uint32_t old = atomicCAS(&tkey[h], HASH_EMPTY, col);
         if (old == HASH_EMPTY || old == col) break;

@@ -136,7 +136,11 @@ int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
  *     (slots [nc*L*L] uint8, slots[(row_start[r] + q)*L + b]); (3) a scan of the row counts and a
  *     compaction.  Needs every dof to be shared by at most 512/L cells and every row to have at
  *     most 255 entries; otherwise returns 3 and the caller retries with mode 1.
- *     (mode 2 = mode 0 with 64-bit keys forced in the row sort; for tests.)
+ *     Rows with 33..256 candidates are deduplicated through a shared-memory hash table first, so
+ *     that only their distinct columns are sorted (k_rowhash); shorter / longer rows use the
+ *     bitonic network on all candidates (k_rowsort).
+ *     (mode 2 = mode 0 with 64-bit keys forced in the row sort, mode 3 = mode 0 with the bitonic
+ *     row sort forced; for tests.)
  *   mode 1 (full sort): stable LSD radix sort of all nc*L*L packed (row,col) keys (64-bit) with
  *     the COO position as payload (perm [n_coo]), then head-flag compaction (seg [nnz+1]).
  * symbolic_sort: workspace of pgb_csr_workspace_bytes(nc, L, n_rows, mode) bytes.

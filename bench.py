@@ -36,7 +36,7 @@ if ROOT not in sys.path:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/r1_ncu_full.txt; config #2, L1 stiffness on 128^3; k_rowsort, k_local, k_numeric_t)
-TRAFFIC = {"k_rowsort": 0.805e9, "local_matrices": 2.029e9, "csr_numeric": 2.070e9}
+TRAFFIC = {"k_rowsort": 0.800e9, "local_matrices": 2.029e9, "csr_numeric": 2.070e9}
 
 METRIC = "cells assembled/s into CSR"
 UNIT = "cells/s"
@@ -315,7 +315,8 @@ def run_ours(args):
                                 "gbs": passes * (b_sort_pass + 4 * n_inc) / max(ph[0], 1e-9) / 1e6},
         "symbolic_row_offsets": {"ms": float(ph[1])},
         "symbolic_rowsort": {"ms": float(ph[2]), "bytes": b_rowsort, "gbs": b_rowsort / max(ph[2], 1e-9) / 1e6,
-                             "note": "register bitonic network: issue-bound (ncu sm throughput ~89%), not HBM-bound"},
+                             "note": "k_rowhash: shared-memory hash dedupe + register bitonic sort of the distinct "
+                                     "columns; issue / shared-memory bound, not HBM-bound"},
         "symbolic_scan": {"ms": float(ph[3])},
     }
     for k in ("local_matrices", "csr_numeric"):
@@ -404,12 +405,12 @@ def run_ours(args):
     dom = max(("symbolic", "local", "numeric", "pack"), key=lambda k: phases[k])
     if dom == "symbolic":
         # dominant kernel of the cold step: k_rowsort (one launch per step)
-        roof = {"bound": "hbm", "kernel": "k_rowsort (per-row register bitonic sort of the symbolic phase)",
+        roof = {"bound": "hbm", "kernel": "k_rowhash (per-row dedupe + sort of the symbolic phase)",
                 "achieved": kern["symbolic_rowsort"]["gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "traffic": TRAFFIC.get("k_rowsort"),
-                "note": "this kernel is instruction-issue bound (sm throughput 89% in ncu), so its HBM fraction is "
-                        "low by construction; the HBM-bound kernels are in `kernels` (local_matrices, csr_numeric) "
-                        "and `solve`"}
+                "note": "largest single kernel of the cold step; it is issue / shared-memory bound (ncu), so its "
+                        "HBM fraction is low by construction; the HBM-bound kernels are in `kernels` "
+                        "(local_matrices, csr_numeric) and `solve`"}
     else:
         key = "local_matrices" if dom == "local" else "csr_numeric"
         roof = {"bound": "hbm", "kernel": key, "achieved": kern[key]["gbs"], "peak": hbm_peak, "unit": "GB/s",

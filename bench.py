@@ -294,26 +294,25 @@ def run_ours(args):
 
     # ---- roofline bookkeeping (algorithmic bytes) --------------------------
     bits = max(1, int(nn - 1).bit_length())
-    passes = (bits + 7) // 8  # radix passes of the incidence transpose (32-bit keys)
     n_inc = nc * 4
     b_local = nc * (16 + 16 + 128) + 32 * nn  # node ids + destination rows + values; coords once per node
     # streaming numeric over the row-sorted local rows: value 8 B + slot 1 B per COO entry, row
     # offsets + indptr 8 B per row, data 8 B per entry
     b_numeric = n_coo * 9 + 8 * nn + nnz * 8
-    b_sort_pass = n_inc * 16  # the scatter kernel moves each (key, payload) once in and once out
+    # counting transpose: dofs in twice, ranks out + in, placed incidences out + in, sorted incidences + inc_pos out
+    b_transpose = n_inc * (4 + 4 + 1 + 1 + 4 + 4 + 4 + 4) + 12 * nn
     # per-row sort: read sorted incidences + row offsets, write perm, unique cols / run starts
     b_rowsort = n_inc * 4 + n_inc * 4 + 8 * nn + n_coo * 1 + nnz * 4  # incidences + cell->dof table in, slots + unique cols out
     b_step_algo = nc * 16 + 32 * nn + n_coo * 0 + nnz * 12 + 4 * (nn + 1)  # read grid once, write CSR once
     kern = {
         "local_matrices": {"ms": wl, "gbs": b_local / wl / 1e6, "bytes": b_local},
         "csr_numeric": {"ms": wn, "gbs": b_numeric / wn / 1e6, "bytes": b_numeric},
-        "symbolic_total": {"ms": phases["symbolic"], "radix_passes": passes,
-                           "bytes": passes * (b_sort_pass + 4 * n_inc) + b_rowsort + 16 * nnz,
-                           "gbs": (passes * (b_sort_pass + 4 * n_inc) + b_rowsort + 16 * nnz) / phases["symbolic"] / 1e6},
+        "symbolic_total": {"ms": phases["symbolic"],
+                           "bytes": b_transpose + b_rowsort + 16 * nnz,
+                           "gbs": (b_transpose + b_rowsort + 16 * nnz) / phases["symbolic"] / 1e6},
         "pack": {"ms": phases["pack"]},
-        "symbolic_radix_sort": {"ms": float(ph[0]), "passes": passes, "bytes": passes * (b_sort_pass + 4 * n_inc),
-                                "gbs": passes * (b_sort_pass + 4 * n_inc) / max(ph[0], 1e-9) / 1e6},
-        "symbolic_row_offsets": {"ms": float(ph[1])},
+        "symbolic_count_scan": {"ms": float(ph[0]), "note": "k_inc_count (integer atomics) + scan + max + host read"},
+        "symbolic_place_rowcanon": {"ms": float(ph[1]), "note": "k_inc_place + k_row_canon (per-row sort of the incidences)"},
         "symbolic_rowsort": {"ms": float(ph[2]), "bytes": b_rowsort, "gbs": b_rowsort / max(ph[2], 1e-9) / 1e6,
                              "note": "k_rowhash: shared-memory hash dedupe + register bitonic sort of the distinct "
                                      "columns; issue / shared-memory bound, not HBM-bound"},

@@ -346,6 +346,117 @@ __global__ void __launch_bounds__(256) k_max_row(int64_t n_rows, const uint32_t*
   }
 }
 
+// bitonic sort of N = G*NPL keys held by a group of G consecutive lanes (element e = lane*NPL + i,
+// `lane` = lane index inside the group)
+template <int NPL, int G = 32>
+__device__ __forceinline__ void warp_bitonic_u32(uint32_t (&key)[NPL], int lane) {
+  constexpr int N = G * NPL;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= NPL) {
+        const int lj = j / NPL;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          uint32_t other = __shfl_xor_sync(FULL, key[i], lj);
+          int e = lane * NPL + i;
+          bool lower = (e & j) == 0, asc = (e & k) == 0;
+          uint32_t mn = min(key[i], other), mx = max(key[i], other);
+          key[i] = (lower == asc) ? mn : mx;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          if ((i & j) == 0) {
+            int e = lane * NPL + i;
+            bool asc = (e & k) == 0;
+            uint32_t a = key[i], b = key[i | j];
+            bool sw = asc ? (a > b) : (a < b);
+            key[i] = sw ? b : a;
+            key[i | j] = sw ? a : b;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- incidence transpose by counting (default) ---------------------------------------------------
+// (1) k_inc_count: cnt[dof] += 1 for every incidence; the value the integer atomic returns is kept
+//     as a provisional rank inside the row (it depends on the execution order, the counts do not).
+// (2) exclusive scan of cnt -> row_start.
+// (3) k_inc_place: incidence i goes to row_start[dof] + rank  (a permutation of the row's block).
+// (4) k_row_canon: every row sorts its (short) incidence list ascending, which is exactly the order
+//     a stable sort by dof produces: inc_sorted / inc_pos are bit-identical to the radix path and
+//     to themselves from run to run.  The floating-point summation order downstream is therefore
+//     fixed; the atomics only ever touch integer counters.
+__global__ void __launch_bounds__(256) k_inc_count(uint32_t n_inc, const int32_t* __restrict__ dofs,
+                                                   uint32_t* __restrict__ cnt, uint8_t* __restrict__ rank) {
+  const uint32_t i0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+  if (i0 >= n_inc) return;
+  if (i0 + 4 <= n_inc) {
+    int4 d = *reinterpret_cast<const int4*>(dofs + i0);
+    uint32_t r0 = atomicAdd(cnt + d.x, 1u), r1 = atomicAdd(cnt + d.y, 1u);
+    uint32_t r2 = atomicAdd(cnt + d.z, 1u), r3 = atomicAdd(cnt + d.w, 1u);
+    uchar4 o;
+    o.x = (uint8_t)min(r0, 255u), o.y = (uint8_t)min(r1, 255u);
+    o.z = (uint8_t)min(r2, 255u), o.w = (uint8_t)min(r3, 255u);
+    *reinterpret_cast<uchar4*>(rank + i0) = o;
+  } else {
+    for (uint32_t i = i0; i < n_inc; ++i) rank[i] = (uint8_t)min(atomicAdd(cnt + dofs[i], 1u), 255u);
+  }
+}
+
+// valid when every dof has at most 256 incidences (ranks did not saturate)
+__global__ void __launch_bounds__(256) k_inc_place(uint32_t n_inc, const int32_t* __restrict__ dofs,
+                                                   const uint32_t* __restrict__ row_start,
+                                                   const uint8_t* __restrict__ rank, uint32_t* __restrict__ inc_tmp) {
+  const uint32_t i0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+  if (i0 >= n_inc) return;
+  if (i0 + 4 <= n_inc) {
+    int4 d = *reinterpret_cast<const int4*>(dofs + i0);
+    uchar4 k = *reinterpret_cast<const uchar4*>(rank + i0);
+    uint32_t p0 = __ldg(row_start + d.x) + k.x, p1 = __ldg(row_start + d.y) + k.y;
+    uint32_t p2 = __ldg(row_start + d.z) + k.z, p3 = __ldg(row_start + d.w) + k.w;
+    inc_tmp[p0] = i0;
+    inc_tmp[p1] = i0 + 1;
+    inc_tmp[p2] = i0 + 2;
+    inc_tmp[p3] = i0 + 3;
+  } else {
+    for (uint32_t i = i0; i < n_inc; ++i) inc_tmp[row_start[dofs[i]] + rank[i]] = i;
+  }
+}
+
+// G lanes per row, NPL incidences per lane (capacity G*NPL)
+template <int G, int NPL>
+__global__ void __launch_bounds__(256) k_row_canon(int64_t n_rows, const uint32_t* __restrict__ row_start,
+                                                   const uint32_t* __restrict__ inc_tmp,
+                                                   uint32_t* __restrict__ inc_sorted, uint32_t* __restrict__ inc_pos) {
+  const int gl = threadIdx.x & (G - 1);
+  const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
+  uint32_t rs = 0, cnt = 0;
+  if (r < n_rows) {
+    rs = row_start[r];
+    cnt = row_start[r + 1] - rs;
+  }
+  uint32_t k[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    uint32_t e = (uint32_t)(i * G + gl);  // any initial placement will do: coalesced
+    k[i] = (e < cnt) ? inc_tmp[rs + e] : 0xffffffffu;
+  }
+  warp_bitonic_u32<NPL, G>(k, gl);
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    uint32_t e = (uint32_t)(gl * NPL + i);
+    if (e < cnt) {
+      inc_sorted[rs + e] = k[i];
+      inc_pos[k[i]] = rs + e;
+    }
+  }
+}
+
 // Key = (col << CSH) | e0 with e0 the candidate's position in the row before sorting
 // (e0 = q*L + b for the q-th incidence of the row and local column b).  KeyT = uint32_t
 // (CSH = log2 N) whenever n_rows * N fits in 32 bits, else uint64_t (CSH = 32).
@@ -477,40 +588,6 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
 // before the insert was measured slower: 1.89 ms vs 1.55 ms on config #2.)
 constexpr int HASH_SIZE = 256;
 constexpr uint32_t HASH_EMPTY = 0xffffffffu;
-
-template <int NPL>
-__device__ __forceinline__ void warp_bitonic_u32(uint32_t (&key)[NPL], int lane) {
-  constexpr int N = 32 * NPL;
-#pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= NPL) {
-        const int lj = j / NPL;
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          uint32_t other = __shfl_xor_sync(FULL, key[i], lj);
-          int e = lane * NPL + i;
-          bool lower = (e & j) == 0, asc = (e & k) == 0;
-          uint32_t mn = min(key[i], other), mx = max(key[i], other);
-          key[i] = (lower == asc) ? mn : mx;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          if ((i & j) == 0) {
-            int e = lane * NPL + i;
-            bool asc = (e & k) == 0;
-            uint32_t a = key[i], b = key[i | j];
-            bool sw = asc ? (a > b) : (a < b);
-            key[i] = sw ? b : a;
-            key[i | j] = sw ? a : b;
-          }
-        }
-      }
-    }
-  }
-}
 
 __device__ __forceinline__ uint32_t hash_col(uint32_t c) { return (c * 2654435761u) >> 24; }
 
@@ -921,7 +998,7 @@ struct PhaseTimer {
   }
 };
 
-constexpr int MODE_TWO_LEVEL = 0, MODE_FULL_SORT = 1, MODE_TWO_LEVEL_KEY64 = 2;
+constexpr int MODE_TWO_LEVEL = 0, MODE_FULL_SORT = 1, MODE_TWO_LEVEL_KEY64 = 2, MODE_TWO_LEVEL_RADIX = 4;
 bool g_force_key64 = false;  // mode 2: exercise the 64-bit-key row sort (tests)
 constexpr uint32_t MAX_ROW_CAND = 512;  // capacity of the largest k_rowsort instance
 
@@ -1093,7 +1170,7 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
                                      int* max_row_nnz_host, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n_coo = nc * L * L, n_inc = nc * L;
-  PGB_REQUIRE(mode >= 0 && mode <= 3, "pgb_csr_symbolic_sort: bad mode");
+  PGB_REQUIRE(mode >= 0 && mode <= 4, "pgb_csr_symbolic_sort: bad mode");
   g_force_key64 = (mode == MODE_TWO_LEVEL_KEY64);
   g_force_bitonic = (mode == 3);
   PGB_REQUIRE(n_coo < ((int64_t)1 << 32) - SORT_TILE, "pgb_csr_symbolic_sort: n_coo must be < 2^32");
@@ -1131,18 +1208,45 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     KeySrc<uint32_t> src{nullptr, cell_dofs, (uint32_t)L, (uint32_t)(L * L), cb};
     PhaseTimer pt(s);
     pt.mark();
-    if (radix_sort<uint32_t>(src, (uint32_t)n_inc, cb, kbuf, pbuf, hist, parts, s)) return 1;
-    pt.mark();
-    k_inc_pos<<<pgb_grid(n_inc, 256), 256, 0, s>>>((uint32_t)n_inc, pbuf[0], perm_or_inc);  // inverse permutation
-    k_row_starts<<<pgb_grid(n_inc, 256), 256, 0, s>>>(kbuf[0], (uint32_t)n_inc, n_rows, row_start);
-    k_max_row<<<(unsigned)(n_rows < 256 * 1184 ? pgb_grid(n_rows, 256) : 1184), 256, 0, s>>>(n_rows, row_start, meta + 3);
-    PGB_LAUNCH_CHECK();
     uint32_t max_inc = 0;
-    PGB_CHECK(cudaMemcpyAsync(&max_inc, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    PGB_CHECK(cudaStreamSynchronize(s));
-    if (max_inc * (uint32_t)L > MAX_ROW_CAND) {
-      pgb_set_error("pgb_csr_symbolic_sort: a dof is shared by %u cells (> %u candidates per row); "
-                    "use mode 1 (full sort)", max_inc, MAX_ROW_CAND);
+    if (mode == MODE_TWO_LEVEL_RADIX) {
+      if (radix_sort<uint32_t>(src, (uint32_t)n_inc, cb, kbuf, pbuf, hist, parts, s)) return 1;
+      pt.mark();
+      k_inc_pos<<<pgb_grid(n_inc, 256), 256, 0, s>>>((uint32_t)n_inc, pbuf[0], perm_or_inc);  // inverse permutation
+      k_row_starts<<<pgb_grid(n_inc, 256), 256, 0, s>>>(kbuf[0], (uint32_t)n_inc, n_rows, row_start);
+      k_max_row<<<(unsigned)(n_rows < 256 * 1184 ? pgb_grid(n_rows, 256) : 1184), 256, 0, s>>>(n_rows, row_start, meta + 3);
+      PGB_LAUNCH_CHECK();
+      PGB_CHECK(cudaMemcpyAsync(&max_inc, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      PGB_CHECK(cudaStreamSynchronize(s));
+    } else {
+      // counting transpose: counts -> row_start, provisional ranks in kbuf[0] (bytes)
+      uint8_t* rank = (uint8_t*)kbuf[0];
+      PGB_CHECK(cudaMemsetAsync(row_start, 0, sizeof(uint32_t) * (n_rows + 1), s));
+      k_inc_count<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank);
+      PGB_LAUNCH_CHECK();
+      if (scan_u32(row_start, (uint64_t)n_rows + 1, parts, nullptr, s)) return 1;
+      k_max_row<<<(unsigned)(n_rows < 256 * 1184 ? pgb_grid(n_rows, 256) : 1184), 256, 0, s>>>(n_rows, row_start, meta + 3);
+      PGB_LAUNCH_CHECK();
+      PGB_CHECK(cudaMemcpyAsync(&max_inc, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      PGB_CHECK(cudaStreamSynchronize(s));
+      pt.mark();
+      if (max_inc <= 256u) {
+        k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, pbuf[1]);
+#define PGB_RC(G, N) k_row_canon<G, N><<<pgb_grid(n_rows * G, 256), 256, 0, s>>>(n_rows, row_start, pbuf[1], pbuf[0], perm_or_inc)
+        if (max_inc <= 4) PGB_RC(4, 1);
+        else if (max_inc <= 8) PGB_RC(8, 1);
+        else if (max_inc <= 16) PGB_RC(16, 1);
+        else if (max_inc <= 32) PGB_RC(32, 1);
+        else if (max_inc <= 64) PGB_RC(32, 2);
+        else if (max_inc <= 128) PGB_RC(32, 4);
+        else PGB_RC(32, 8);
+#undef PGB_RC
+        PGB_LAUNCH_CHECK();
+      }
+    }
+    if (max_inc * (uint32_t)L > MAX_ROW_CAND || max_inc > 256u) {
+      pgb_set_error("pgb_csr_symbolic_sort: a dof is shared by %u cells (> %u candidates per row or > 256 "
+                    "cells); use mode 1 (full sort)", max_inc, MAX_ROW_CAND);
       return 3;
     }
     PGB_CHECK(cudaMemsetAsync(row_nnz + n_rows, 0, 2 * sizeof(uint32_t), s));

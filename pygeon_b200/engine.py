@@ -443,8 +443,10 @@ def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
         bits = max(1, int(n_rows - 1).bit_length()) if n_rows > 1 else 1
         if mode == 1:
             _lib.count(((2 * bits + 7) // 8) * 5 + 3)
-        else:
+        elif mode == 4:
             _lib.count(((bits + 7) // 8) * 5 + 7)
+        else:
+            _lib.count(13)  # count, 3 scan, max, place, canon, row sort, 3 scan, compact (+1 memset)
         del ws
     if mode == 1:
         plan = CsrPlan(n_rows, n_coo, nnz, L, 1, indptr, indices, perm=first, seg=seg)

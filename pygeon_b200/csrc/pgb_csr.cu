@@ -580,118 +580,161 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
 // ---- per-row dedupe by hashing (rows with 33..256 candidates) -----------------------------------
 // The bitonic network above sorts ALL candidates of a row although only the distinct columns need
 // ordering (a P1 node row of the Kuhn mesh has 96 candidates but ~15 distinct columns).  Here one
-// warp per row inserts the candidate columns into a 256-entry open-addressing table in shared
-// memory (atomicCAS on integers: the resulting SET is order independent), compacts the distinct
-// columns, sorts only those (1, 2 or 8 per lane) and hands every candidate the rank of its column
-// through the table.  Output identical to k_rowsort (sorted unique columns + uint8 slot per
-// candidate), tested bit for bit.  (Merging equal columns of a 32-candidate chunk with match.any
-// before the insert was measured slower: 1.89 ms vs 1.55 ms on config #2.)
-constexpr int HASH_SIZE = 256;
+// warp per row
+//   (1) loads the row's incidences (in the arbitrary order k_inc_place left them), sorts them
+//       ascending (= the canonical (dof, cell) order) and records inc_pos: the work of k_row_canon;
+//   (2) every lane loads the dof row of its incident cell with vector loads and inserts the L
+//       columns into an open-addressing table in shared memory (atomicCAS on integers: the
+//       resulting SET is order independent);
+//   (3) compacts the distinct columns, sorts only those and hands every candidate the rank of its
+//       column through the table; a lane writes the LP slot bytes of its incidence as whole words.
+// Output identical to k_rowsort (sorted unique columns + uint8 slot per candidate), tested bit for
+// bit.  (Merging equal columns with match.any before the insert was measured slower.)
 constexpr uint32_t HASH_EMPTY = 0xffffffffu;
 
-__device__ __forceinline__ uint32_t hash_col(uint32_t c) { return (c * 2654435761u) >> 24; }
+template <int HS>
+__device__ __forceinline__ uint32_t hash_col(uint32_t c) {
+  return (c * 2654435761u) >> (32 - (HS == 64 ? 6 : HS == 128 ? 7 : HS == 256 ? 8 : 9));
+}
 
 // sort the nu distinct columns held in ucols[0..nu) (shared memory), write them back sorted and
 // store every column's rank in tslot at the column's table position
-template <int NPL>
-__device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint32_t* tkey, uint32_t* tslot, int lane) {
+template <int NPL, int HS>
+__device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint32_t* tkey, uint8_t* tslot, int lane) {
   uint32_t k[NPL];
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
     int e = lane * NPL + i;
     k[i] = (e < nu) ? ucols[e] : HASH_EMPTY;
   }
-  warp_bitonic_u32<NPL>(k, lane);
   __syncwarp();
+  warp_bitonic_u32<NPL>(k, lane);
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
     int e = lane * NPL + i;
     if (e < nu) {
       ucols[e] = k[i];
-      uint32_t h = hash_col(k[i]);
-      while (tkey[h] != k[i]) h = (h + 1) & (HASH_SIZE - 1);
-      tslot[h] = (uint32_t)e;
+      uint32_t h = hash_col<HS>(k[i]);
+      while (tkey[h] != k[i]) h = (h + 1) & (HS - 1);
+      tslot[h] = (uint8_t)e;
     }
   }
   __syncwarp();
 }
 
-template <int CPL, int L>
+// dof row of one cell, vector loads where the row pitch allows
+template <int L>
+__device__ __forceinline__ void load_dofs(const int32_t* __restrict__ p, uint32_t (&d)[L]) {
+  if constexpr (L % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < L / 4; ++j) {
+      int4 t = __ldg(reinterpret_cast<const int4*>(p) + j);
+      d[4 * j] = (uint32_t)t.x, d[4 * j + 1] = (uint32_t)t.y, d[4 * j + 2] = (uint32_t)t.z, d[4 * j + 3] = (uint32_t)t.w;
+    }
+  } else if constexpr (L % 2 == 0) {
+#pragma unroll
+    for (int j = 0; j < L / 2; ++j) {
+      int2 t = __ldg(reinterpret_cast<const int2*>(p) + j);
+      d[2 * j] = (uint32_t)t.x, d[2 * j + 1] = (uint32_t)t.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < L; ++j) d[j] = (uint32_t)__ldg(p + j);
+  }
+}
+
+// NPL incidences per lane (row capacity 32*NPL incidences), table of HS entries (at most 3/4 full)
+template <int NPL, int L, int HS>
 __global__ void __launch_bounds__(256) k_rowhash(int64_t n_rows, const uint32_t* __restrict__ row_start,
-                                                 const uint32_t* __restrict__ inc_sorted,
-                                                 const int32_t* __restrict__ dofs, uint8_t* __restrict__ slots,
-                                                 int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz,
-                                                 uint32_t* __restrict__ max_nnz) {
+                                                 const uint32_t* __restrict__ inc_tmp,
+                                                 const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos,
+                                                 uint8_t* __restrict__ slots, int32_t* __restrict__ ucol_tmp,
+                                                 uint32_t* __restrict__ row_nnz, uint32_t* __restrict__ max_nnz) {
   constexpr int LP = (L + 3) & ~3;
-  __shared__ uint32_t s_key[8][HASH_SIZE];
-  __shared__ uint32_t s_slot[8][HASH_SIZE];
-  __shared__ uint32_t s_ucol[8][HASH_SIZE];
+  __shared__ uint32_t s_key[8][HS];
+  __shared__ uint32_t s_ucol[8][HS];
+  __shared__ uint8_t s_slot[8][HS];
   __shared__ uint32_t wmax[8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t r = (int64_t)blockIdx.x * 8 + w;
   uint32_t* tkey = s_key[w];
-  uint32_t* tslot = s_slot[w];
+  uint8_t* tslot = s_slot[w];
   uint32_t* ucols = s_ucol[w];
-  uint32_t rs = 0, re = 0;
+  uint32_t rs = 0, cnt = 0;
   if (r < n_rows) {
     rs = row_start[r];
-    re = row_start[r + 1];
+    cnt = row_start[r + 1] - rs;
   }
-  const uint32_t ncand = (re - rs) * L;
-  const uint32_t base = rs * L;
+  uint32_t inc[NPL];
 #pragma unroll
-  for (int k = 0; k < HASH_SIZE / 32; ++k) tkey[k * 32 + lane] = HASH_EMPTY;
-  __syncwarp();
-  // candidates, strided: e = i*32 + lane; insert their columns.  Every incident cell contributes
-  // the row's own dof once (the worst same-address conflict): it is inserted by lane 0 alone.
-  const uint32_t hdiag = hash_col((uint32_t)r);
-  if (lane == 0 && ncand) tkey[hdiag] = (uint32_t)r;
-  __syncwarp();
-  uint32_t hpos[CPL];
+  for (int i = 0; i < NPL; ++i) {
+    uint32_t e = (uint32_t)(i * 32 + lane);
+    inc[i] = (e < cnt) ? inc_tmp[rs + e] : 0xffffffffu;
+  }
 #pragma unroll
-  for (int i = 0; i < CPL; ++i) {
-    uint32_t e = i * 32 + lane;
-    hpos[i] = 0;
-    if (e < ncand) {
-      uint32_t q = e / L, b = e - q * L;
-      uint32_t cell = inc_sorted[rs + q] / L;
-      uint32_t col = (uint32_t)__ldg(dofs + (int64_t)cell * L + b);
-      uint32_t h = hash_col(col);
-      if (col == (uint32_t)r) {
-        hpos[i] = hdiag;
-        continue;
+  for (int k = 0; k < HS / 32; ++k) tkey[k * 32 + lane] = HASH_EMPTY;
+  warp_bitonic_u32<NPL>(inc, lane);  // canonical order: ascending incidence = ascending (cell, a)
+  // Every incident cell contributes the row's own dof once (the worst same-address conflict): it is
+  // inserted by lane 0 alone.
+  const uint32_t hdiag = hash_col<HS>((uint32_t)r);
+  if (lane == 0 && cnt) tkey[hdiag] = (uint32_t)r;
+  __syncwarp();
+  uint16_t hpos[NPL][L];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const uint32_t e = (uint32_t)(lane * NPL + i);
+    if (e < cnt) {
+      inc_pos[inc[i]] = rs + e;
+      uint32_t d[L];
+      load_dofs<L>(dofs + (int64_t)(inc[i] / L) * L, d);
+#pragma unroll
+      for (int b = 0; b < L; ++b) {
+        const uint32_t col = d[b];
+        uint32_t h = hdiag;
+        if (col != (uint32_t)r) {
+          h = hash_col<HS>(col);
+          while (true) {
+            uint32_t old = atomicCAS(&tkey[h], HASH_EMPTY, col);
+            if (old == HASH_EMPTY || old == col) break;
+            h = (h + 1) & (HS - 1);
+          }
+        }
+        hpos[i][b] = (uint16_t)h;
       }
-      while (true) {
-        uint32_t old = atomicCAS(&tkey[h], HASH_EMPTY, col);
-        if (old == HASH_EMPTY || old == col) break;
-        h = (h + 1) & (HASH_SIZE - 1);
-      }
-      hpos[i] = h;
     }
   }
   __syncwarp();
   // compact the distinct columns
   int nu = 0;
 #pragma unroll
-  for (int k = 0; k < HASH_SIZE / 32; ++k) {
+  for (int k = 0; k < HS / 32; ++k) {
     uint32_t v = tkey[k * 32 + lane];
     unsigned m = __ballot_sync(FULL, v != HASH_EMPTY);
     if (v != HASH_EMPTY) ucols[nu + __popc(m & ((1u << lane) - 1u))] = v;
     nu += __popc(m);
   }
   __syncwarp();
-  if (nu <= 32) sort_uniques<1>(ucols, nu, tkey, tslot, lane);
-  else if (nu <= 64) sort_uniques<2>(ucols, nu, tkey, tslot, lane);
-  else sort_uniques<8>(ucols, nu, tkey, tslot, lane);
-  // slots of the candidates, sorted distinct columns of the row
+  if (nu <= 32) sort_uniques<1, HS>(ucols, nu, tkey, tslot, lane);
+  else if (nu <= 64) sort_uniques<2, HS>(ucols, nu, tkey, tslot, lane);
+  else if (HS <= 128 || nu <= 128) sort_uniques<4, HS>(ucols, nu, tkey, tslot, lane);
+  else sort_uniques<8, HS>(ucols, nu, tkey, tslot, lane);
+  // slots of the candidates: the LP bytes of one incidence as whole words
 #pragma unroll
-  for (int i = 0; i < CPL; ++i) {
-    uint32_t e = i * 32 + lane;
-    if (e < ncand) {
-      uint32_t q = e / L, b = e - q * L;
-      slots[(uint64_t)(rs + q) * LP + b] = (uint8_t)tslot[hpos[i]];
+  for (int i = 0; i < NPL; ++i) {
+    const uint32_t e = (uint32_t)(lane * NPL + i);
+    if (e < cnt) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(slots + (uint64_t)(rs + e) * LP);
+#pragma unroll
+      for (int j = 0; j < LP / 4; ++j) {
+        uint32_t wv = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (4 * j + t < L) wv |= (uint32_t)tslot[hpos[i][4 * j + t]] << (8 * t);
+        dst[j] = wv;
+      }
     }
   }
+  const uint32_t base = rs * L;
   for (int e = lane; e < nu; e += 32) ucol_tmp[base + e] = (int32_t)ucols[e];
   if (r < n_rows && lane == 0) row_nnz[r] = (uint32_t)nu;
   if (lane == 0) wmax[w] = (uint32_t)nu;
@@ -1075,11 +1118,12 @@ int launch_rowsort_k(int L, int64_t n_rows, const uint32_t* row_start, const uin
   return launch_rowsort_l<G, ITEMS, uint64_t>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
 }
 
-template <int CPL>
-int launch_rowhash(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
-                   uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
+template <int NPL, int HS>
+int launch_rowhash_l(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs,
+                     uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
+                     cudaStream_t s) {
   unsigned grid = (unsigned)pgb_cdiv(n_rows, 8);
-#define PGB_RH(LL) k_rowhash<CPL, LL><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz)
+#define PGB_RH(LL) k_rowhash<NPL, LL, HS><<<grid, 256, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz)
   switch (L) {
     case 3: PGB_RH(3); break;
     case 4: PGB_RH(4); break;
@@ -1093,17 +1137,30 @@ int launch_rowhash(int L, int64_t n_rows, const uint32_t* row_start, const uint3
   return 0;
 }
 
+// fused canonical sort of the incidences + hash dedupe; inc_tmp: the row blocks in any order
+int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row_start,
+                   const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
+                   uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
+#define PGB_RHL(N, H) return launch_rowhash_l<N, H>(L, n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, s)
+  if (max_inc <= 32) {
+    if (max_cand <= 96) PGB_RHL(1, 128);
+    PGB_RHL(1, 512);
+  }
+  if (max_cand <= 96) PGB_RHL(4, 128);
+  PGB_RHL(4, 512);
+#undef PGB_RHL
+}
+
 bool g_force_bitonic = false;  // mode 3: always use the bitonic row sort (tests)
+
+// rows with many candidates but few distinct columns: dedupe by hashing, sort only the distinct ones
+bool rowhash_applies(uint32_t max_inc, uint32_t max_cand) {
+  return !g_force_bitonic && !g_force_key64 && max_cand > 32 && max_cand <= 256 && max_inc <= 128;
+}
 
 int launch_rowsort(uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc,
                    const int32_t* dofs, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
                    cudaStream_t s) {
-  // rows with many candidates but few distinct columns: dedupe by hashing, sort only the distinct ones
-  if (!g_force_bitonic && !g_force_key64 && max_cand > 32 && max_cand <= 256) {
-    if (max_cand <= 64) return launch_rowhash<2>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
-    if (max_cand <= 128) return launch_rowhash<4>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
-    return launch_rowhash<8>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
-  }
 #define PGB_RS(G, I) return launch_rowsort_k<G, I>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s)
   if (max_cand <= 8) PGB_RS(4, 2);
   if (max_cand <= 16) PGB_RS(8, 2);
@@ -1209,6 +1266,7 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     PhaseTimer pt(s);
     pt.mark();
     uint32_t max_inc = 0;
+    const uint32_t* inc_rows = pbuf[0];
     if (mode == MODE_TWO_LEVEL_RADIX) {
       if (radix_sort<uint32_t>(src, (uint32_t)n_inc, cb, kbuf, pbuf, hist, parts, s)) return 1;
       pt.mark();
@@ -1230,17 +1288,21 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
       PGB_CHECK(cudaMemcpyAsync(&max_inc, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       PGB_CHECK(cudaStreamSynchronize(s));
       pt.mark();
-      if (max_inc <= 256u) {
+      if (max_inc <= 256u && max_inc * (uint32_t)L <= MAX_ROW_CAND) {
         k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, pbuf[1]);
+        inc_rows = pbuf[1];  // row blocks, each in arbitrary order
+        if (!rowhash_applies(max_inc, max_inc * (uint32_t)L)) {  // k_rowhash sorts them itself
 #define PGB_RC(G, N) k_row_canon<G, N><<<pgb_grid(n_rows * G, 256), 256, 0, s>>>(n_rows, row_start, pbuf[1], pbuf[0], perm_or_inc)
-        if (max_inc <= 4) PGB_RC(4, 1);
-        else if (max_inc <= 8) PGB_RC(8, 1);
-        else if (max_inc <= 16) PGB_RC(16, 1);
-        else if (max_inc <= 32) PGB_RC(32, 1);
-        else if (max_inc <= 64) PGB_RC(32, 2);
-        else if (max_inc <= 128) PGB_RC(32, 4);
-        else PGB_RC(32, 8);
+          if (max_inc <= 4) PGB_RC(4, 1);
+          else if (max_inc <= 8) PGB_RC(8, 1);
+          else if (max_inc <= 16) PGB_RC(16, 1);
+          else if (max_inc <= 32) PGB_RC(32, 1);
+          else if (max_inc <= 64) PGB_RC(32, 2);
+          else if (max_inc <= 128) PGB_RC(32, 4);
+          else PGB_RC(32, 8);
 #undef PGB_RC
+          inc_rows = pbuf[0];
+        }
         PGB_LAUNCH_CHECK();
       }
     }
@@ -1251,9 +1313,14 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     }
     PGB_CHECK(cudaMemsetAsync(row_nnz + n_rows, 0, 2 * sizeof(uint32_t), s));
     pt.mark();
-    if (launch_rowsort(max_inc * (uint32_t)L, L, n_rows, row_start, pbuf[0], cell_dofs, slots,
-                       (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s))
+    if (rowhash_applies(max_inc, max_inc * (uint32_t)L)) {
+      if (launch_rowhash(max_inc, max_inc * (uint32_t)L, L, n_rows, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
+                         (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s))
+        return 1;
+    } else if (launch_rowsort(max_inc * (uint32_t)L, L, n_rows, row_start, inc_rows, cell_dofs, slots,
+                              (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s)) {
       return 1;
+    }
     pt.mark();
     if (scan_u32(row_nnz, (uint64_t)n_rows + 1, parts, nullptr, s)) return 1;
     PGB_CHECK(cudaMemcpyAsync(meta + 2, row_nnz + n_rows, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));

@@ -446,7 +446,7 @@ def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
         elif mode == 4:
             _lib.count(((bits + 7) // 8) * 5 + 7)
         else:
-            _lib.count(13)  # count, 3 scan, max, place, canon, row sort, 3 scan, compact (+1 memset)
+            _lib.count(12)  # count, 3 scan, max, place, (canon,) row sort|hash, 3 scan, compact (+memsets)
         del ws
     if mode == 1:
         plan = CsrPlan(n_rows, n_coo, nnz, L, 1, indptr, indices, perm=first, seg=seg)

@@ -348,9 +348,33 @@ __global__ void __launch_bounds__(256) k_max_row(int64_t n_rows, const uint32_t*
 
 // bitonic sort of N = G*NPL keys held by a group of G consecutive lanes (element e = lane*NPL + i,
 // `lane` = lane index inside the group)
+// one key per lane: the all-ascending form of the network (the first step of every merge pairs
+// lane i with its mirror i ^ (k-1)), so that min / max is decided by ONE compile-time bit of the
+// lane index: a stage is SHFL + predicate + VIMNMX
+template <int G>
+__device__ __forceinline__ uint32_t group_bitonic1_u32(uint32_t key, int lane) {
+#pragma unroll
+  for (int k = 2; k <= G; k <<= 1) {
+    {
+      uint32_t other = __shfl_xor_sync(FULL, key, k - 1);
+      key = (lane & (k >> 1)) ? max(key, other) : min(key, other);
+    }
+#pragma unroll
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      uint32_t other = __shfl_xor_sync(FULL, key, j);
+      key = (lane & j) ? max(key, other) : min(key, other);
+    }
+  }
+  return key;
+}
+
 template <int NPL, int G = 32>
 __device__ __forceinline__ void warp_bitonic_u32(uint32_t (&key)[NPL], int lane) {
   constexpr int N = G * NPL;
+  if constexpr (NPL == 1) {
+    key[0] = group_bitonic1_u32<G>(key[0], lane);
+    return;
+  }
 #pragma unroll
   for (int k = 2; k <= N; k <<= 1) {
 #pragma unroll
@@ -599,7 +623,7 @@ __device__ __forceinline__ uint32_t hash_col(uint32_t c) {
 
 // sort the nu distinct columns held in ucols[0..nu) (shared memory), write them back sorted and
 // store every column's rank in tslot at the column's table position
-template <int NPL, int HS>
+template <int NPL, int HS, int G = 32>
 __device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint32_t* tkey, uint8_t* tslot, int lane) {
   uint32_t k[NPL];
 #pragma unroll
@@ -608,7 +632,7 @@ __device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint
     k[i] = (e < nu) ? ucols[e] : HASH_EMPTY;
   }
   __syncwarp();
-  warp_bitonic_u32<NPL>(k, lane);
+  warp_bitonic_u32<NPL, G>(k, lane & (G - 1));  // G < 32: nu <= G, the other groups sort padding
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
     int e = lane * NPL + i;
@@ -645,7 +669,7 @@ __device__ __forceinline__ void load_dofs(const int32_t* __restrict__ p, uint32_
 
 // NPL incidences per lane (row capacity 32*NPL incidences), table of HS entries (at most 3/4 full)
 template <int NPL, int L, int HS>
-__global__ void __launch_bounds__(256) k_rowhash(int64_t n_rows, const uint32_t* __restrict__ row_start,
+__global__ void __launch_bounds__(256, (NPL == 1 && L <= 6) ? (HS <= 128 ? 8 : 5) : 1) k_rowhash(int64_t n_rows, const uint32_t* __restrict__ row_start,
                                                  const uint32_t* __restrict__ inc_tmp,
                                                  const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos,
                                                  uint8_t* __restrict__ slots, int32_t* __restrict__ ucol_tmp,
@@ -714,7 +738,8 @@ __global__ void __launch_bounds__(256) k_rowhash(int64_t n_rows, const uint32_t*
     nu += __popc(m);
   }
   __syncwarp();
-  if (nu <= 32) sort_uniques<1, HS>(ucols, nu, tkey, tslot, lane);
+  if (nu <= 16) sort_uniques<1, HS, 16>(ucols, nu, tkey, tslot, lane);
+  else if (nu <= 32) sort_uniques<1, HS>(ucols, nu, tkey, tslot, lane);
   else if (nu <= 64) sort_uniques<2, HS>(ucols, nu, tkey, tslot, lane);
   else if (HS <= 128 || nu <= 128) sort_uniques<4, HS>(ucols, nu, tkey, tslot, lane);
   else sort_uniques<8, HS>(ucols, nu, tkey, tslot, lane);

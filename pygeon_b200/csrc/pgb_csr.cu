@@ -601,6 +601,157 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
   }
 }
 
+// dof row of one cell, vector loads where the row pitch allows
+template <int L>
+__device__ __forceinline__ void load_dofs(const int32_t* __restrict__ p, uint32_t (&d)[L]) {
+  if constexpr (L % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < L / 4; ++j) {
+      int4 t = __ldg(reinterpret_cast<const int4*>(p) + j);
+      d[4 * j] = (uint32_t)t.x, d[4 * j + 1] = (uint32_t)t.y, d[4 * j + 2] = (uint32_t)t.z, d[4 * j + 3] = (uint32_t)t.w;
+    }
+  } else if constexpr (L % 2 == 0) {
+#pragma unroll
+    for (int j = 0; j < L / 2; ++j) {
+      int2 t = __ldg(reinterpret_cast<const int2*>(p) + j);
+      d[2 * j] = (uint32_t)t.x, d[2 * j + 1] = (uint32_t)t.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < L; ++j) d[j] = (uint32_t)__ldg(p + j);
+  }
+}
+
+// ---- short rows: one THREAD per row ---------------------------------------------------------------
+// Rows of face / cell / face-node dofs have a handful of incident cells (RT0: 2, P0: 1, BDM1: 2), i.e.
+// 5..32 candidate columns.  A sorting network over registers needs no shuffles, no shared memory and
+// no predicates (a compare-exchange is two VIMNMX), and neighbouring threads own neighbouring rows,
+// so the row offsets, the incidences, the slot bytes and the unique columns are all accessed in
+// contiguous runs across the warp.  The thread also puts its (at most MI) incidences into canonical
+// order and records inc_pos, like k_rowhash.  Output identical to k_rowsort.
+template <int N, typename KeyT>
+__device__ __forceinline__ void reg_bitonic(KeyT (&a)[N]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int p = i ^ (k - 1);
+      if (i < p) {
+        KeyT lo = a[i] < a[p] ? a[i] : a[p], hi = a[i] < a[p] ? a[p] : a[i];
+        a[i] = lo, a[p] = hi;
+      }
+    }
+#pragma unroll
+    for (int j = k >> 2; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int p = i ^ j;
+        if (i < p) {
+          KeyT lo = a[i] < a[p] ? a[i] : a[p], hi = a[i] < a[p] ? a[p] : a[i];
+          a[i] = lo, a[p] = hi;
+        }
+      }
+    }
+  }
+}
+
+// Block-compacted output: the 128 rows of a block stage their unique columns back to back in shared
+// memory (row order) and their slot bytes at the block-relative incidence position; both are then
+// written with coalesced stores: the columns to ucol_tmp[row_start[first]*L ...) (k_compact knows
+// this layout through meta[5]), the slot bytes to their final place.
+constexpr int ROWTHREAD_BLOCK = 128;
+
+template <int MI, int L, int N, typename KeyT>
+__global__ void __launch_bounds__(ROWTHREAD_BLOCK) k_rowthread(int64_t n_rows, const uint32_t* __restrict__ row_start,
+                                                               const uint32_t* __restrict__ inc_tmp,
+                                                               const int32_t* __restrict__ dofs,
+                                                               uint32_t* __restrict__ inc_pos, uint8_t* __restrict__ slots,
+                                                               int32_t* __restrict__ ucol_tmp,
+                                                               uint32_t* __restrict__ row_nnz,
+                                                               uint32_t* __restrict__ max_nnz) {
+  static_assert(MI * L <= N, "network too small");
+  constexpr int LP = (L + 3) & ~3;
+  constexpr int B = ROWTHREAD_BLOCK;
+  constexpr bool K32 = sizeof(KeyT) == 4;
+  constexpr int EB = (N <= 8) ? 3 : (N <= 16) ? 4 : 5;
+  constexpr int CSH = K32 ? EB : 32;
+  __shared__ uint32_t s_u[B * MI * L];
+  __shared__ __align__(16) uint8_t s_sl[B * MI * LP];
+  __shared__ uint32_t s_w[B / 32], s_m[B / 32], s_rs0;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t r = (int64_t)blockIdx.x * B + tid;
+  uint32_t rs = 0, cnt = 0;
+  if (r < n_rows) {
+    rs = row_start[r];
+    cnt = row_start[r + 1] - rs;
+  }
+  if (tid == 0) s_rs0 = rs;
+  for (int j = tid; j < B * MI * LP / 4; j += B) reinterpret_cast<uint32_t*>(s_sl)[j] = 0u;
+  uint32_t inc[MI];
+#pragma unroll
+  for (int q = 0; q < MI; ++q) inc[q] = ((uint32_t)q < cnt) ? inc_tmp[rs + q] : 0xffffffffu;
+  if constexpr (MI > 1) reg_bitonic<MI, uint32_t>(inc);
+  KeyT key[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) key[i] = (KeyT) ~(KeyT)0;
+#pragma unroll
+  for (int q = 0; q < MI; ++q) {
+    if ((uint32_t)q < cnt) {
+      inc_pos[inc[q]] = rs + q;
+      uint32_t d[L];
+      load_dofs<L>(dofs + (int64_t)(inc[q] / L) * L, d);
+#pragma unroll
+      for (int b = 0; b < L; ++b) key[q * L + b] = ((KeyT)d[b] << CSH) | (KeyT)(q * L + b);
+    }
+  }
+  reg_bitonic<N, KeyT>(key);
+  const uint32_t ncand = cnt * L;
+  // number of distinct columns, block-exclusive scan
+  uint32_t total = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if ((uint32_t)i < ncand) total += (i == 0 || (uint32_t)(key[i] >> CSH) != (uint32_t)(key[i > 0 ? i - 1 : 0] >> CSH)) ? 1u : 0u;
+  uint32_t incl = warp_incl_scan(total);
+  uint32_t mx = __reduce_max_sync(FULL, total);
+  if (lane == 31) s_w[w] = incl;
+  if (lane == 0) s_m[w] = mx;
+  __syncthreads();  // s_rs0, s_w, s_m, zeroed s_sl
+  uint32_t off = incl - total, btotal = 0;
+#pragma unroll
+  for (int i = 0; i < B / 32; ++i) {
+    if (i < w) off += s_w[i];
+    btotal += s_w[i];
+  }
+  const uint32_t rs0 = s_rs0;
+  int run = -1;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    if ((uint32_t)i < ncand) {
+      const uint32_t col = (uint32_t)(key[i] >> CSH);
+      if (i == 0 || col != (uint32_t)(key[i > 0 ? i - 1 : 0] >> CSH)) {
+        ++run;
+        s_u[off + run] = col;
+      }
+      const uint32_t e0 = (uint32_t)key[i] & ((1u << EB) - 1u);
+      const uint32_t q0 = e0 / L;
+      s_sl[(rs - rs0 + q0) * LP + (e0 - q0 * L)] = (uint8_t)run;
+    }
+  }
+  if (r < n_rows) row_nnz[r] = total;
+  __syncthreads();
+  // coalesced write-out
+  const int64_t r_end = ((int64_t)blockIdx.x + 1) * B < n_rows ? ((int64_t)blockIdx.x + 1) * B : n_rows;
+  const uint32_t ninc = row_start[r_end] - rs0;
+  for (uint32_t j = tid; j < btotal; j += B) ucol_tmp[(uint64_t)rs0 * L + j] = (int32_t)s_u[j];
+  uint32_t* sl_out = reinterpret_cast<uint32_t*>(slots + (uint64_t)rs0 * LP);
+  for (uint32_t j = tid; j < ninc * (LP / 4); j += B) sl_out[j] = reinterpret_cast<const uint32_t*>(s_sl)[j];
+  if (tid == 0) {
+    uint32_t m = s_m[0];
+    for (int q = 1; q < B / 32; ++q) m = s_m[q] > m ? s_m[q] : m;
+    atomicMax(max_nnz, m);
+  }
+}
+
 // ---- per-row dedupe by hashing (rows with 33..256 candidates) -----------------------------------
 // The bitonic network above sorts ALL candidates of a row although only the distinct columns need
 // ordering (a P1 node row of the Kuhn mesh has 96 candidates but ~15 distinct columns).  Here one
@@ -644,27 +795,6 @@ __device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint
     }
   }
   __syncwarp();
-}
-
-// dof row of one cell, vector loads where the row pitch allows
-template <int L>
-__device__ __forceinline__ void load_dofs(const int32_t* __restrict__ p, uint32_t (&d)[L]) {
-  if constexpr (L % 4 == 0) {
-#pragma unroll
-    for (int j = 0; j < L / 4; ++j) {
-      int4 t = __ldg(reinterpret_cast<const int4*>(p) + j);
-      d[4 * j] = (uint32_t)t.x, d[4 * j + 1] = (uint32_t)t.y, d[4 * j + 2] = (uint32_t)t.z, d[4 * j + 3] = (uint32_t)t.w;
-    }
-  } else if constexpr (L % 2 == 0) {
-#pragma unroll
-    for (int j = 0; j < L / 2; ++j) {
-      int2 t = __ldg(reinterpret_cast<const int2*>(p) + j);
-      d[2 * j] = (uint32_t)t.x, d[2 * j + 1] = (uint32_t)t.y;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < L; ++j) d[j] = (uint32_t)__ldg(p + j);
-  }
 }
 
 // NPL incidences per lane (row capacity 32*NPL incidences), table of HS entries (at most 3/4 full)
@@ -776,8 +906,8 @@ __global__ void __launch_bounds__(256, (NPL == 1 && L <= 6) ? (HS <= 128 ? 8 : 5
 template <typename IP>
 __global__ void __launch_bounds__(256) k_compact(int64_t n_rows, int L, const uint32_t* __restrict__ row_start,
                                                  const uint32_t* __restrict__ row_off,
-                                                 const int32_t* __restrict__ ucol_tmp, IP* __restrict__ indptr,
-                                                 int32_t* __restrict__ indices) {
+                                                 const int32_t* __restrict__ ucol_tmp, const uint32_t* __restrict__ meta,
+                                                 IP* __restrict__ indptr, int32_t* __restrict__ indices) {
   // 8 lanes per row
   const int gl = threadIdx.x & 7;
   const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
@@ -786,7 +916,16 @@ __global__ void __launch_bounds__(256) k_compact(int64_t n_rows, int L, const ui
   if (gl == 0) indptr[r] = (IP)o0;
   if (r == n_rows) return;
   uint32_t cnt = row_off[r + 1] - o0;
-  uint32_t base = row_start[r] * (uint32_t)L;
+  // scratch position of the row's columns: per row (k_rowsort / k_rowhash), or back to back inside
+  // groups of meta[5] rows (k_rowthread)
+  const uint32_t grp = meta[5];
+  uint64_t base;
+  if (grp) {
+    const int64_t first = r - r % (int64_t)grp;
+    base = (uint64_t)row_start[first] * (uint32_t)L + (o0 - row_off[first]);
+  } else {
+    base = (uint64_t)row_start[r] * (uint32_t)L;
+  }
   for (uint32_t k = gl; k < cnt; k += 8) indices[o0 + k] = ucol_tmp[base + k];
 }
 
@@ -1085,7 +1224,8 @@ WsLayout ws_layout(int64_t n_coo, int64_t n_inc, int64_t n_rows, int mode) {
   int64_t o = 0;
   int64_t nsort = (mode == MODE_FULL_SORT) ? n_coo : n_inc;
   int64_t ntiles = pgb_cdiv(nsort > 0 ? nsort : 1, SORT_TILE);
-  l.meta = o;  o += 256;  // uint32: [0] mode, [1] cb, [2] nnz, [3] max incidences per row, [4] max row nnz
+  l.meta = o;  o += 256;  // uint32: [0] mode, [1] cb, [2] nnz, [3] max incidences per row, [4] max row nnz,
+                          // [5] rows per group of the unique-column scratch (0: one segment per row)
   l.parts = o; o += al(2048 * 4);
   l.hist = o;  o += al(ntiles * RADIX * 4);
   if (mode == MODE_FULL_SORT) {
@@ -1178,6 +1318,43 @@ int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, int64_t n_rows, c
 
 bool g_force_bitonic = false;  // mode 3: always use the bitonic row sort (tests)
 
+template <int MI, int L, int N>
+int launch_rowthread_k(int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs,
+                       uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
+                       cudaStream_t s) {
+  unsigned grid = (unsigned)pgb_cdiv(n_rows, ROWTHREAD_BLOCK);
+  if ((uint64_t)n_rows * (uint64_t)N <= 0xffffffffull && !g_force_key64)
+    k_rowthread<MI, L, N, uint32_t><<<grid, ROWTHREAD_BLOCK, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz);
+  else
+    k_rowthread<MI, L, N, uint64_t><<<grid, ROWTHREAD_BLOCK, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+// rows with at most 8 incidences and 32 candidates: one thread per row (k_rowthread)
+bool rowthread_applies(uint32_t max_inc, uint32_t max_cand) {
+  if (g_force_bitonic || max_inc == 0 || max_inc > 8) return false;
+  const uint32_t mi = max_inc <= 1 ? 1 : max_inc <= 2 ? 2 : max_inc <= 4 ? 4 : 8;  // network of the incidences
+  return mi * (max_cand / max_inc) <= 32;
+}
+
+int launch_rowthread(uint32_t max_inc, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp,
+                     const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz,
+                     uint32_t* max_nnz, cudaStream_t s) {
+  const int mi = max_inc <= 1 ? 1 : max_inc <= 2 ? 2 : max_inc <= 4 ? 4 : 8;
+#define PGB_RT(MI, LL, N) \
+  if (L == LL && mi == MI)  \
+    return launch_rowthread_k<MI, LL, N>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, s)
+  PGB_RT(1, 3, 8);  PGB_RT(2, 3, 8);  PGB_RT(4, 3, 16); PGB_RT(8, 3, 32);
+  PGB_RT(1, 4, 8);  PGB_RT(2, 4, 8);  PGB_RT(4, 4, 16); PGB_RT(8, 4, 32);
+  PGB_RT(1, 5, 8);  PGB_RT(2, 5, 16); PGB_RT(4, 5, 32);
+  PGB_RT(1, 6, 8);  PGB_RT(2, 6, 16); PGB_RT(4, 6, 32);
+  PGB_RT(1, 12, 16); PGB_RT(2, 12, 32);
+#undef PGB_RT
+  pgb_set_error("k_rowthread: unsupported local size %d / %u incidences", L, max_inc);
+  return 2;
+}
+
 // rows with many candidates but few distinct columns: dedupe by hashing, sort only the distinct ones
 bool rowhash_applies(uint32_t max_inc, uint32_t max_cand) {
   return !g_force_bitonic && !g_force_key64 && max_cand > 32 && max_cand <= 256 && max_inc <= 128;
@@ -1266,7 +1443,7 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
   uint32_t* parts = (uint32_t*)(ws + l.parts);
   uint32_t* hist = (uint32_t*)(ws + l.hist);
   const int cb = bits_for(n_rows);
-  uint32_t m[5] = {(uint32_t)mode, (uint32_t)cb, 0u, 0u, 0u};
+  uint32_t m[6] = {(uint32_t)mode, (uint32_t)cb, 0u, 0u, 0u, 0u};
   PGB_CHECK(cudaMemcpyAsync(meta, m, sizeof(m), cudaMemcpyHostToDevice, s));
   if (n_coo == 0) {
     if (mode != MODE_FULL_SORT) PGB_CHECK(cudaMemsetAsync(row_start, 0, sizeof(uint32_t) * (n_rows + 1), s));
@@ -1316,7 +1493,8 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
       if (max_inc <= 256u && max_inc * (uint32_t)L <= MAX_ROW_CAND) {
         k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, pbuf[1]);
         inc_rows = pbuf[1];  // row blocks, each in arbitrary order
-        if (!rowhash_applies(max_inc, max_inc * (uint32_t)L)) {  // k_rowhash sorts them itself
+        if (!rowhash_applies(max_inc, max_inc * (uint32_t)L) &&
+            !rowthread_applies(max_inc, max_inc * (uint32_t)L)) {  // those kernels sort the row blocks themselves
 #define PGB_RC(G, N) k_row_canon<G, N><<<pgb_grid(n_rows * G, 256), 256, 0, s>>>(n_rows, row_start, pbuf[1], pbuf[0], perm_or_inc)
           if (max_inc <= 4) PGB_RC(4, 1);
           else if (max_inc <= 8) PGB_RC(8, 1);
@@ -1338,7 +1516,13 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     }
     PGB_CHECK(cudaMemsetAsync(row_nnz + n_rows, 0, 2 * sizeof(uint32_t), s));
     pt.mark();
-    if (rowhash_applies(max_inc, max_inc * (uint32_t)L)) {
+    if (rowthread_applies(max_inc, max_inc * (uint32_t)L)) {
+      const uint32_t grp = ROWTHREAD_BLOCK;
+      PGB_CHECK(cudaMemcpyAsync(meta + 5, &grp, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+      if (launch_rowthread(max_inc, L, n_rows, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
+                           (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s))
+        return 1;
+    } else if (rowhash_applies(max_inc, max_inc * (uint32_t)L)) {
       if (launch_rowhash(max_inc, max_inc * (uint32_t)L, L, n_rows, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
                          (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s))
         return 1;
@@ -1393,11 +1577,12 @@ extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mo
     PGB_REQUIRE(row_start, "pgb_csr_symbolic_finish: row_start required in two-level mode");
     const uint32_t* row_off = (const uint32_t*)(ws + l.row_nnz);
     const int32_t* ucol = (const int32_t*)(ws + l.ucol);
+    const uint32_t* meta = (const uint32_t*)(ws + l.meta);
     unsigned grid = pgb_grid((n_rows + 1) * 8, 256);
     if (idx64)
-      k_compact<int64_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, (int64_t*)indptr, indices);
+      k_compact<int64_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, meta, (int64_t*)indptr, indices);
     else
-      k_compact<int32_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, (int32_t*)indptr, indices);
+      k_compact<int32_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, meta, (int32_t*)indptr, indices);
   }
   PGB_LAUNCH_CHECK();
   return 0;

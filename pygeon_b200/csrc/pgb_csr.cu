@@ -368,6 +368,9 @@ __device__ __forceinline__ uint32_t group_bitonic1_u32(uint32_t key, int lane) {
   return key;
 }
 
+// NPL keys per lane, element e = lane*NPL + i: same all-ascending network; steps with partner
+// distance >= NPL go through shuffles (the mirror step exchanges key[i] with key[NPL-1-i] of the
+// partner lane), the others are compare-exchanges between registers of one lane
 template <int NPL, int G = 32>
 __device__ __forceinline__ void warp_bitonic_u32(uint32_t (&key)[NPL], int lane) {
   constexpr int N = G * NPL;
@@ -377,28 +380,40 @@ __device__ __forceinline__ void warp_bitonic_u32(uint32_t (&key)[NPL], int lane)
   }
 #pragma unroll
   for (int k = 2; k <= N; k <<= 1) {
+    if (k <= NPL) {  // mirror step inside the lane
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = 0; i < NPL; ++i) {
+        const int p = i ^ (k - 1);
+        if (i < p) {
+          uint32_t lo = min(key[i], key[p]), hi = max(key[i], key[p]);
+          key[i] = lo, key[p] = hi;
+        }
+      }
+    } else {
+      const int lj = k / NPL - 1;
+      uint32_t other[NPL];
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) other[i] = __shfl_xor_sync(FULL, key[NPL - 1 - i], lj);
+      const bool up = (lane & (k / NPL / 2)) != 0;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) key[i] = up ? max(key[i], other[i]) : min(key[i], other[i]);
+    }
+#pragma unroll
+    for (int j = k >> 2; j > 0; j >>= 1) {
       if (j >= NPL) {
         const int lj = j / NPL;
+        const bool up = (lane & lj) != 0;
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
           uint32_t other = __shfl_xor_sync(FULL, key[i], lj);
-          int e = lane * NPL + i;
-          bool lower = (e & j) == 0, asc = (e & k) == 0;
-          uint32_t mn = min(key[i], other), mx = max(key[i], other);
-          key[i] = (lower == asc) ? mn : mx;
+          key[i] = up ? max(key[i], other) : min(key[i], other);
         }
       } else {
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
           if ((i & j) == 0) {
-            int e = lane * NPL + i;
-            bool asc = (e & k) == 0;
-            uint32_t a = key[i], b = key[i | j];
-            bool sw = asc ? (a > b) : (a < b);
-            key[i] = sw ? b : a;
-            key[i | j] = sw ? a : b;
+            uint32_t lo = min(key[i], key[i | j]), hi = max(key[i], key[i | j]);
+            key[i] = lo, key[i | j] = hi;
           }
         }
       }
@@ -673,7 +688,7 @@ __global__ void __launch_bounds__(ROWTHREAD_BLOCK) k_rowthread(int64_t n_rows, c
   constexpr int LP = (L + 3) & ~3;
   constexpr int B = ROWTHREAD_BLOCK;
   constexpr bool K32 = sizeof(KeyT) == 4;
-  constexpr int EB = (N <= 8) ? 3 : (N <= 16) ? 4 : 5;
+  constexpr int EB = (N <= 8) ? 3 : (N <= 16) ? 4 : (N <= 32) ? 5 : 6;
   constexpr int CSH = K32 ? EB : 32;
   __shared__ uint32_t s_u[B * MI * L];
   __shared__ __align__(16) uint8_t s_sl[B * MI * LP];
@@ -772,21 +787,22 @@ __device__ __forceinline__ uint32_t hash_col(uint32_t c) {
   return (c * 2654435761u) >> (32 - (HS == 64 ? 6 : HS == 128 ? 7 : HS == 256 ? 8 : 9));
 }
 
-// sort the nu distinct columns held in ucols[0..nu) (shared memory), write them back sorted and
-// store every column's rank in tslot at the column's table position
-template <int NPL, int HS, int G = 32>
-__device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint32_t* tkey, uint8_t* tslot, int lane) {
-  uint32_t k[NPL];
+// sort the nu distinct columns of every group (ucols[0..nu), shared memory; NPU per lane of the
+// group, G*NPU >= the largest nu of the warp), write them back sorted and store every column's rank
+// in tslot at the column's table position.  Called by all lanes of the warp.
+template <int NPU, int HS, int G>
+__device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint32_t* tkey, uint8_t* tslot, int gl) {
+  uint32_t k[NPU];
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    int e = lane * NPL + i;
+  for (int i = 0; i < NPU; ++i) {
+    int e = gl * NPU + i;
     k[i] = (e < nu) ? ucols[e] : HASH_EMPTY;
   }
   __syncwarp();
-  warp_bitonic_u32<NPL, G>(k, lane & (G - 1));  // G < 32: nu <= G, the other groups sort padding
+  warp_bitonic_u32<NPU, G>(k, gl);
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    int e = lane * NPL + i;
+  for (int i = 0; i < NPU; ++i) {
+    int e = gl * NPU + i;
     if (e < nu) {
       ucols[e] = k[i];
       uint32_t h = hash_col<HS>(k[i]);
@@ -797,23 +813,26 @@ __device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint
   __syncwarp();
 }
 
-// NPL incidences per lane (row capacity 32*NPL incidences), table of HS entries (at most 3/4 full)
-template <int NPL, int L, int HS>
-__global__ void __launch_bounds__(256, (NPL == 1 && L <= 6) ? (HS <= 128 ? 8 : 5) : 1) k_rowhash(int64_t n_rows, const uint32_t* __restrict__ row_start,
-                                                 const uint32_t* __restrict__ inc_tmp,
-                                                 const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos,
-                                                 uint8_t* __restrict__ slots, int32_t* __restrict__ ucol_tmp,
-                                                 uint32_t* __restrict__ row_nnz, uint32_t* __restrict__ max_nnz) {
+// G lanes per row (256/G rows per block), NPL incidences per lane (row capacity G*NPL incidences),
+// table of HS entries per row (at most 3/4 full)
+template <int G, int NPL, int L, int HS>
+__global__ void __launch_bounds__(256, (NPL == 1 && L <= 6) ? ((256 / G) * HS * 9 <= 20000 ? 8 : 5) : 1)
+k_rowhash(int64_t n_rows, const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ inc_tmp,
+          const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos, uint8_t* __restrict__ slots,
+          int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz, uint32_t* __restrict__ max_nnz) {
   constexpr int LP = (L + 3) & ~3;
-  __shared__ uint32_t s_key[8][HS];
-  __shared__ uint32_t s_ucol[8][HS];
-  __shared__ uint8_t s_slot[8][HS];
+  constexpr int RPB = 256 / G;  // rows per block
+  __shared__ uint32_t s_key[RPB][HS];
+  __shared__ uint32_t s_ucol[RPB][HS];
+  __shared__ uint8_t s_slot[RPB][HS];
   __shared__ uint32_t wmax[8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t r = (int64_t)blockIdx.x * 8 + w;
-  uint32_t* tkey = s_key[w];
-  uint8_t* tslot = s_slot[w];
-  uint32_t* ucols = s_ucol[w];
+  const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
+  const int g = threadIdx.x / G;
+  const int64_t r = (int64_t)blockIdx.x * RPB + g;
+  uint32_t* tkey = s_key[g];
+  uint8_t* tslot = s_slot[g];
+  uint32_t* ucols = s_ucol[g];
   uint32_t rs = 0, cnt = 0;
   if (r < n_rows) {
     rs = row_start[r];
@@ -822,21 +841,22 @@ __global__ void __launch_bounds__(256, (NPL == 1 && L <= 6) ? (HS <= 128 ? 8 : 5
   uint32_t inc[NPL];
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
-    uint32_t e = (uint32_t)(i * 32 + lane);
+    uint32_t e = (uint32_t)(i * G + gl);
     inc[i] = (e < cnt) ? inc_tmp[rs + e] : 0xffffffffu;
   }
 #pragma unroll
-  for (int k = 0; k < HS / 32; ++k) tkey[k * 32 + lane] = HASH_EMPTY;
-  warp_bitonic_u32<NPL>(inc, lane);  // canonical order: ascending incidence = ascending (cell, a)
+  for (int k = 0; k < HS / G; ++k) tkey[k * G + gl] = HASH_EMPTY;
+  warp_bitonic_u32<NPL, G>(inc, gl);  // canonical order: ascending incidence = ascending (cell, a)
   // Every incident cell contributes the row's own dof once (the worst same-address conflict): it is
-  // inserted by lane 0 alone.
+  // inserted by the first lane alone.
   const uint32_t hdiag = hash_col<HS>((uint32_t)r);
-  if (lane == 0 && cnt) tkey[hdiag] = (uint32_t)r;
+  __syncwarp();
+  if (gl == 0 && cnt) tkey[hdiag] = (uint32_t)r;
   __syncwarp();
   uint16_t hpos[NPL][L];
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
-    const uint32_t e = (uint32_t)(lane * NPL + i);
+    const uint32_t e = (uint32_t)(gl * NPL + i);
     if (e < cnt) {
       inc_pos[inc[i]] = rs + e;
       uint32_t d[L];
@@ -858,25 +878,30 @@ __global__ void __launch_bounds__(256, (NPL == 1 && L <= 6) ? (HS <= 128 ? 8 : 5
     }
   }
   __syncwarp();
-  // compact the distinct columns
+  // compact the distinct columns of the group's table
   int nu = 0;
+  const uint32_t gmask = (G == 32) ? FULL : ((1u << (G & 31)) - 1u);
 #pragma unroll
-  for (int k = 0; k < HS / 32; ++k) {
-    uint32_t v = tkey[k * 32 + lane];
-    unsigned m = __ballot_sync(FULL, v != HASH_EMPTY);
-    if (v != HASH_EMPTY) ucols[nu + __popc(m & ((1u << lane) - 1u))] = v;
+  for (int k = 0; k < HS / G; ++k) {
+    uint32_t v = tkey[k * G + gl];
+    unsigned m = (__ballot_sync(FULL, v != HASH_EMPTY) >> gbase) & gmask;
+    if (v != HASH_EMPTY) ucols[nu + __popc(m & ((1u << gl) - 1u))] = v;
     nu += __popc(m);
   }
   __syncwarp();
-  if (nu <= 16) sort_uniques<1, HS, 16>(ucols, nu, tkey, tslot, lane);
-  else if (nu <= 32) sort_uniques<1, HS>(ucols, nu, tkey, tslot, lane);
-  else if (nu <= 64) sort_uniques<2, HS>(ucols, nu, tkey, tslot, lane);
-  else if (HS <= 128 || nu <= 128) sort_uniques<4, HS>(ucols, nu, tkey, tslot, lane);
-  else sort_uniques<8, HS>(ucols, nu, tkey, tslot, lane);
+  // sort them; the network size is chosen for the longest row of the warp, so that the warp stays converged
+  const int nu_w = (G == 32) ? nu : (int)__reduce_max_sync(FULL, (unsigned)nu);
+  if (G >= 16 && nu_w <= 16) sort_uniques<1, HS, 16>(ucols, nu, tkey, tslot, lane & 15);
+  else if (nu_w <= G) sort_uniques<1, HS, G>(ucols, nu, tkey, tslot, gl);
+  else if (nu_w <= 2 * G) sort_uniques<2, HS, G>(ucols, nu, tkey, tslot, gl);
+  else if (nu_w <= 4 * G) sort_uniques<4, HS, G>(ucols, nu, tkey, tslot, gl);
+  else if (HS * 3 / 4 <= 8 * G || nu_w <= 8 * G) sort_uniques<8, HS, G>(ucols, nu, tkey, tslot, gl);
+  else if (HS * 3 / 4 <= 16 * G || nu_w <= 16 * G) sort_uniques<16, HS, G>(ucols, nu, tkey, tslot, gl);
+  else sort_uniques<32, HS, G>(ucols, nu, tkey, tslot, gl);
   // slots of the candidates: the LP bytes of one incidence as whole words
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
-    const uint32_t e = (uint32_t)(lane * NPL + i);
+    const uint32_t e = (uint32_t)(gl * NPL + i);
     if (e < cnt) {
       uint32_t* dst = reinterpret_cast<uint32_t*>(slots + (uint64_t)(rs + e) * LP);
 #pragma unroll
@@ -890,9 +915,10 @@ __global__ void __launch_bounds__(256, (NPL == 1 && L <= 6) ? (HS <= 128 ? 8 : 5
     }
   }
   const uint32_t base = rs * L;
-  for (int e = lane; e < nu; e += 32) ucol_tmp[base + e] = (int32_t)ucols[e];
-  if (r < n_rows && lane == 0) row_nnz[r] = (uint32_t)nu;
-  if (lane == 0) wmax[w] = (uint32_t)nu;
+  for (int e = gl; e < nu; e += G) ucol_tmp[base + e] = (int32_t)ucols[e];
+  if (r < n_rows && gl == 0) row_nnz[r] = (uint32_t)nu;
+  const uint32_t mxw = __reduce_max_sync(FULL, (unsigned)nu);
+  if (lane == 0) wmax[w] = mxw;
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t mx = wmax[0];
@@ -1283,12 +1309,12 @@ int launch_rowsort_k(int L, int64_t n_rows, const uint32_t* row_start, const uin
   return launch_rowsort_l<G, ITEMS, uint64_t>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
 }
 
-template <int NPL, int HS>
+template <int G, int NPL, int HS>
 int launch_rowhash_l(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs,
                      uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
                      cudaStream_t s) {
-  unsigned grid = (unsigned)pgb_cdiv(n_rows, 8);
-#define PGB_RH(LL) k_rowhash<NPL, LL, HS><<<grid, 256, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz)
+  unsigned grid = (unsigned)pgb_cdiv(n_rows, 256 / G);
+#define PGB_RH(LL) k_rowhash<G, NPL, LL, HS><<<grid, 256, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz)
   switch (L) {
     case 3: PGB_RH(3); break;
     case 4: PGB_RH(4); break;
@@ -1302,17 +1328,26 @@ int launch_rowhash_l(int L, int64_t n_rows, const uint32_t* row_start, const uin
   return 0;
 }
 
-// fused canonical sort of the incidences + hash dedupe; inc_tmp: the row blocks in any order
+// fused canonical sort of the incidences + hash dedupe; inc_tmp: the row blocks in any order.
+// Lanes per row from the largest incidence count, table size from the largest candidate count.
 int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row_start,
                    const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
                    uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
-#define PGB_RHL(N, H) return launch_rowhash_l<N, H>(L, n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, s)
-  if (max_inc <= 32) {
-    if (max_cand <= 96) PGB_RHL(1, 128);
-    PGB_RHL(1, 512);
+#define PGB_RHL(G, N, H) return launch_rowhash_l<G, N, H>(L, n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, s)
+  if (max_inc <= 8) {
+    if (max_cand <= 48) PGB_RHL(8, 1, 64);
+    PGB_RHL(8, 1, 128);  // max_cand <= 96 (L <= 12)
   }
-  if (max_cand <= 96) PGB_RHL(4, 128);
-  PGB_RHL(4, 512);
+  if (max_inc <= 16) {
+    if (max_cand <= 96) PGB_RHL(16, 1, 128);
+    PGB_RHL(16, 1, 256);  // max_cand <= 192
+  }
+  if (max_inc <= 32) {
+    if (max_cand <= 96) PGB_RHL(32, 1, 128);
+    PGB_RHL(32, 1, 512);
+  }
+  if (max_cand <= 96) PGB_RHL(32, 4, 128);
+  PGB_RHL(32, 4, 512);
 #undef PGB_RHL
 }
 
@@ -1331,11 +1366,11 @@ int launch_rowthread_k(int64_t n_rows, const uint32_t* row_start, const uint32_t
   return 0;
 }
 
-// rows with at most 8 incidences and 32 candidates: one thread per row (k_rowthread)
+// rows with at most 8 incidences and 64 candidates: one thread per row (k_rowthread)
 bool rowthread_applies(uint32_t max_inc, uint32_t max_cand) {
   if (g_force_bitonic || max_inc == 0 || max_inc > 8) return false;
   const uint32_t mi = max_inc <= 1 ? 1 : max_inc <= 2 ? 2 : max_inc <= 4 ? 4 : 8;  // network of the incidences
-  return mi * (max_cand / max_inc) <= 32;
+  return mi * (max_cand / max_inc) <= 64;
 }
 
 int launch_rowthread(uint32_t max_inc, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp,
@@ -1347,9 +1382,9 @@ int launch_rowthread(uint32_t max_inc, int L, int64_t n_rows, const uint32_t* ro
     return launch_rowthread_k<MI, LL, N>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, s)
   PGB_RT(1, 3, 8);  PGB_RT(2, 3, 8);  PGB_RT(4, 3, 16); PGB_RT(8, 3, 32);
   PGB_RT(1, 4, 8);  PGB_RT(2, 4, 8);  PGB_RT(4, 4, 16); PGB_RT(8, 4, 32);
-  PGB_RT(1, 5, 8);  PGB_RT(2, 5, 16); PGB_RT(4, 5, 32);
-  PGB_RT(1, 6, 8);  PGB_RT(2, 6, 16); PGB_RT(4, 6, 32);
-  PGB_RT(1, 12, 16); PGB_RT(2, 12, 32);
+  PGB_RT(1, 5, 8);  PGB_RT(2, 5, 16); PGB_RT(4, 5, 32); PGB_RT(8, 5, 64);
+  PGB_RT(1, 6, 8);  PGB_RT(2, 6, 16); PGB_RT(4, 6, 32); PGB_RT(8, 6, 64);
+  PGB_RT(1, 12, 16); PGB_RT(2, 12, 32); PGB_RT(4, 12, 64);
 #undef PGB_RT
   pgb_set_error("k_rowthread: unsupported local size %d / %u incidences", L, max_inc);
   return 2;

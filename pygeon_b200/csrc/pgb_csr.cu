@@ -8,6 +8,9 @@
 // No floating-point atomics anywhere; the only atomics are shared-memory integer counters of the
 // digit histogram (their result is order independent), so pattern and values are bit-reproducible.
 #include "pgb_common.cuh"
+#include "pgb_rows.cuh"
+
+using namespace pgb_rows;
 
 namespace {
 
@@ -17,7 +20,6 @@ constexpr int SORT_BLOCK = 256;
 constexpr int SORT_WARPS = SORT_BLOCK / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_BLOCK * SORT_ITEMS;  // 4096 keys per block
-constexpr unsigned FULL = 0xffffffffu;
 
 constexpr int SCAN_G = PGB_NPART;  // chunks of the two-level scans (<= 2048)
 
@@ -67,16 +69,6 @@ __global__ void __launch_bounds__(SORT_BLOCK) k_radix_hist(KeySrc<KeyT> src, uin
 }
 
 // ---- two-level exclusive scan over uint32 (reduce / scan partials / apply) -------------------
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
-  int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t t = __shfl_up_sync(FULL, v, d);
-    if (lane >= d) v += t;
-  }
-  return v;
-}
-
 // exclusive scan of one value per thread over a 256-thread block; returns exclusive prefix,
 // total in `total`.  ws: 8 uint32 of shared memory.
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* ws, uint32_t& total) {
@@ -346,81 +338,6 @@ __global__ void __launch_bounds__(256) k_max_row(int64_t n_rows, const uint32_t*
   }
 }
 
-// bitonic sort of N = G*NPL keys held by a group of G consecutive lanes (element e = lane*NPL + i,
-// `lane` = lane index inside the group)
-// one key per lane: the all-ascending form of the network (the first step of every merge pairs
-// lane i with its mirror i ^ (k-1)), so that min / max is decided by ONE compile-time bit of the
-// lane index: a stage is SHFL + predicate + VIMNMX
-template <int G>
-__device__ __forceinline__ uint32_t group_bitonic1_u32(uint32_t key, int lane) {
-#pragma unroll
-  for (int k = 2; k <= G; k <<= 1) {
-    {
-      uint32_t other = __shfl_xor_sync(FULL, key, k - 1);
-      key = (lane & (k >> 1)) ? max(key, other) : min(key, other);
-    }
-#pragma unroll
-    for (int j = k >> 2; j > 0; j >>= 1) {
-      uint32_t other = __shfl_xor_sync(FULL, key, j);
-      key = (lane & j) ? max(key, other) : min(key, other);
-    }
-  }
-  return key;
-}
-
-// NPL keys per lane, element e = lane*NPL + i: same all-ascending network; steps with partner
-// distance >= NPL go through shuffles (the mirror step exchanges key[i] with key[NPL-1-i] of the
-// partner lane), the others are compare-exchanges between registers of one lane
-template <int NPL, int G = 32>
-__device__ __forceinline__ void warp_bitonic_u32(uint32_t (&key)[NPL], int lane) {
-  constexpr int N = G * NPL;
-  if constexpr (NPL == 1) {
-    key[0] = group_bitonic1_u32<G>(key[0], lane);
-    return;
-  }
-#pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
-    if (k <= NPL) {  // mirror step inside the lane
-#pragma unroll
-      for (int i = 0; i < NPL; ++i) {
-        const int p = i ^ (k - 1);
-        if (i < p) {
-          uint32_t lo = min(key[i], key[p]), hi = max(key[i], key[p]);
-          key[i] = lo, key[p] = hi;
-        }
-      }
-    } else {
-      const int lj = k / NPL - 1;
-      uint32_t other[NPL];
-#pragma unroll
-      for (int i = 0; i < NPL; ++i) other[i] = __shfl_xor_sync(FULL, key[NPL - 1 - i], lj);
-      const bool up = (lane & (k / NPL / 2)) != 0;
-#pragma unroll
-      for (int i = 0; i < NPL; ++i) key[i] = up ? max(key[i], other[i]) : min(key[i], other[i]);
-    }
-#pragma unroll
-    for (int j = k >> 2; j > 0; j >>= 1) {
-      if (j >= NPL) {
-        const int lj = j / NPL;
-        const bool up = (lane & lj) != 0;
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          uint32_t other = __shfl_xor_sync(FULL, key[i], lj);
-          key[i] = up ? max(key[i], other) : min(key[i], other);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          if ((i & j) == 0) {
-            uint32_t lo = min(key[i], key[i | j]), hi = max(key[i], key[i | j]);
-            key[i] = lo, key[i | j] = hi;
-          }
-        }
-      }
-    }
-  }
-}
-
 // ---- incidence transpose by counting (default) ---------------------------------------------------
 // (1) k_inc_count: cnt[dof] += 1 for every incidence; the value the integer atomic returns is kept
 //     as a provisional rank inside the row (it depends on the execution order, the counts do not).
@@ -493,437 +410,6 @@ __global__ void __launch_bounds__(256) k_row_canon(int64_t n_rows, const uint32_
       inc_sorted[rs + e] = k[i];
       inc_pos[k[i]] = rs + e;
     }
-  }
-}
-
-// Key = (col << CSH) | e0 with e0 the candidate's position in the row before sorting
-// (e0 = q*L + b for the q-th incidence of the row and local column b).  KeyT = uint32_t
-// (CSH = log2 N) whenever n_rows * N fits in 32 bits, else uint64_t (CSH = 32).
-// Output per row: the sorted unique columns (scratch, compacted later), and for every candidate
-// the index of its column among them ("slot", uint8): slots[(row_start[r] + q)*L + b].
-template <int G, int ITEMS, int L, typename KeyT>
-__global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t* __restrict__ row_start,
-                                                 const uint32_t* __restrict__ inc_sorted,
-                                                 const int32_t* __restrict__ dofs, uint8_t* __restrict__ slots,
-                                                 int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz,
-                                                 uint32_t* __restrict__ max_nnz) {
-  constexpr int N = G * ITEMS;
-  constexpr int LP = (L + 3) & ~3;
-  constexpr bool K32 = sizeof(KeyT) == 4;
-  constexpr int EB = (N <= 8) ? 3 : (N <= 16) ? 4 : (N <= 32) ? 5 : (N <= 64) ? 6 : (N <= 128) ? 7 : (N <= 256) ? 8 : 9;
-  constexpr int CSH = K32 ? EB : 32;  // column shift inside the key
-  __shared__ uint32_t wmax[8];
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % G;  // lane within the group
-  const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
-  const bool live = r < n_rows;
-  uint32_t rs = 0, re = 0;
-  if (live) {
-    rs = row_start[r];
-    re = row_start[r + 1];
-  }
-  const uint32_t ncand = (re - rs) * L;
-  const uint32_t base = rs * L;
-
-  // gather candidates, blocked layout: element e = gl*ITEMS + i
-  KeyT key[ITEMS];
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    uint32_t e = gl * ITEMS + i;
-    key[i] = (KeyT) ~(KeyT)0;
-    if (e < ncand) {
-      uint32_t q = e / L, b = e - q * L;
-      uint32_t cell = inc_sorted[rs + q] / L;
-      uint32_t col = (uint32_t)__ldg(dofs + (int64_t)cell * L + b);
-      key[i] = ((KeyT)col << CSH) | (KeyT)e;
-    }
-  }
-  // bitonic sort, ascending, N elements spread over G lanes
-#pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= ITEMS) {
-        const int lj = j / ITEMS;
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-          KeyT other = __shfl_xor_sync(FULL, key[i], lj);
-          int e = gl * ITEMS + i;
-          bool lower = (e & j) == 0;
-          bool asc = (e & k) == 0;
-          KeyT mn = key[i] < other ? key[i] : other;
-          KeyT mx = key[i] < other ? other : key[i];
-          key[i] = (lower == asc) ? mn : mx;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-          if ((i & j) == 0) {
-            int e = gl * ITEMS + i;
-            bool asc = (e & k) == 0;
-            KeyT a = key[i], b = key[i | j];
-            bool sw = asc ? (a > b) : (a < b);
-            key[i] = sw ? b : a;
-            key[i | j] = sw ? a : b;
-          }
-        }
-      }
-    }
-  }
-  // unique columns: head(e) = e == 0 || col(e) != col(e-1)
-  uint32_t prev_last = (uint32_t)(__shfl_up_sync(FULL, key[ITEMS - 1], 1) >> CSH);
-  uint32_t heads = 0;  // bit i set: element i of this lane starts a run
-  int cnt = 0;
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    uint32_t e = gl * ITEMS + i;
-    uint32_t col = (uint32_t)(key[i] >> CSH);
-    uint32_t pc = (i == 0) ? prev_last : (uint32_t)(key[i - 1] >> CSH);
-    bool h = (e < ncand) && (e == 0 || col != pc);
-    heads |= (h ? 1u : 0u) << i;
-    cnt += h;
-  }
-  // exclusive scan of cnt over the G lanes of the group
-  int inc_ = cnt;
-#pragma unroll
-  for (int d = 1; d < G; d <<= 1) {
-    int t = __shfl_up_sync(FULL, inc_, d);
-    if (gl >= d) inc_ += t;
-  }
-  int total = __shfl_sync(FULL, inc_, (lane - gl) + G - 1);
-  int run = inc_ - cnt - 1;  // index of the run that is open when this lane starts
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    uint32_t e = gl * ITEMS + i;
-    if (e < ncand) {
-      if ((heads >> i) & 1u) {
-        ++run;
-        ucol_tmp[base + run] = (int32_t)(key[i] >> CSH);
-      }
-      uint32_t e0 = (uint32_t)key[i] & ((1u << EB) - 1u);  // position before sorting
-      uint32_t q0 = e0 / L;
-      slots[(uint64_t)(rs + q0) * LP + (e0 - q0 * L)] = (uint8_t)run;  // row pitch LP = L rounded up to a multiple of 4
-    }
-  }
-  if (live && gl == 0) row_nnz[r] = (uint32_t)total;
-  // largest row (integer max: order independent)
-  uint32_t mx = __reduce_max_sync(FULL, (uint32_t)total);
-  if (lane == 0) wmax[threadIdx.x >> 5] = mx;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int q = 1; q < 8; ++q) mx = wmax[q] > mx ? wmax[q] : mx;
-    atomicMax(max_nnz, mx);
-  }
-}
-
-// dof row of one cell, vector loads where the row pitch allows
-template <int L>
-__device__ __forceinline__ void load_dofs(const int32_t* __restrict__ p, uint32_t (&d)[L]) {
-  if constexpr (L % 4 == 0) {
-#pragma unroll
-    for (int j = 0; j < L / 4; ++j) {
-      int4 t = __ldg(reinterpret_cast<const int4*>(p) + j);
-      d[4 * j] = (uint32_t)t.x, d[4 * j + 1] = (uint32_t)t.y, d[4 * j + 2] = (uint32_t)t.z, d[4 * j + 3] = (uint32_t)t.w;
-    }
-  } else if constexpr (L % 2 == 0) {
-#pragma unroll
-    for (int j = 0; j < L / 2; ++j) {
-      int2 t = __ldg(reinterpret_cast<const int2*>(p) + j);
-      d[2 * j] = (uint32_t)t.x, d[2 * j + 1] = (uint32_t)t.y;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < L; ++j) d[j] = (uint32_t)__ldg(p + j);
-  }
-}
-
-// ---- short rows: one THREAD per row ---------------------------------------------------------------
-// Rows of face / cell / face-node dofs have a handful of incident cells (RT0: 2, P0: 1, BDM1: 2), i.e.
-// 5..32 candidate columns.  A sorting network over registers needs no shuffles, no shared memory and
-// no predicates (a compare-exchange is two VIMNMX), and neighbouring threads own neighbouring rows,
-// so the row offsets, the incidences, the slot bytes and the unique columns are all accessed in
-// contiguous runs across the warp.  The thread also puts its (at most MI) incidences into canonical
-// order and records inc_pos, like k_rowhash.  Output identical to k_rowsort.
-template <int N, typename KeyT>
-__device__ __forceinline__ void reg_bitonic(KeyT (&a)[N]) {
-#pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const int p = i ^ (k - 1);
-      if (i < p) {
-        KeyT lo = a[i] < a[p] ? a[i] : a[p], hi = a[i] < a[p] ? a[p] : a[i];
-        a[i] = lo, a[p] = hi;
-      }
-    }
-#pragma unroll
-    for (int j = k >> 2; j > 0; j >>= 1) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        const int p = i ^ j;
-        if (i < p) {
-          KeyT lo = a[i] < a[p] ? a[i] : a[p], hi = a[i] < a[p] ? a[p] : a[i];
-          a[i] = lo, a[p] = hi;
-        }
-      }
-    }
-  }
-}
-
-// Block-compacted output: the 128 rows of a block stage their unique columns back to back in shared
-// memory (row order) and their slot bytes at the block-relative incidence position; both are then
-// written with coalesced stores: the columns to ucol_tmp[row_start[first]*L ...) (k_compact knows
-// this layout through meta[5]), the slot bytes to their final place.
-constexpr int ROWTHREAD_BLOCK = 128;
-
-template <int MI, int L, int N, typename KeyT>
-__global__ void __launch_bounds__(ROWTHREAD_BLOCK) k_rowthread(int64_t n_rows, const uint32_t* __restrict__ row_start,
-                                                               const uint32_t* __restrict__ inc_tmp,
-                                                               const int32_t* __restrict__ dofs,
-                                                               uint32_t* __restrict__ inc_pos, uint8_t* __restrict__ slots,
-                                                               int32_t* __restrict__ ucol_tmp,
-                                                               uint32_t* __restrict__ row_nnz,
-                                                               uint32_t* __restrict__ max_nnz) {
-  static_assert(MI * L <= N, "network too small");
-  constexpr int LP = (L + 3) & ~3;
-  constexpr int B = ROWTHREAD_BLOCK;
-  constexpr bool K32 = sizeof(KeyT) == 4;
-  constexpr int EB = (N <= 8) ? 3 : (N <= 16) ? 4 : (N <= 32) ? 5 : 6;
-  constexpr int CSH = K32 ? EB : 32;
-  __shared__ uint32_t s_u[B * MI * L];
-  __shared__ __align__(16) uint8_t s_sl[B * MI * LP];
-  __shared__ uint32_t s_w[B / 32], s_m[B / 32], s_rs0;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int64_t r = (int64_t)blockIdx.x * B + tid;
-  uint32_t rs = 0, cnt = 0;
-  if (r < n_rows) {
-    rs = row_start[r];
-    cnt = row_start[r + 1] - rs;
-  }
-  if (tid == 0) s_rs0 = rs;
-  for (int j = tid; j < B * MI * LP / 4; j += B) reinterpret_cast<uint32_t*>(s_sl)[j] = 0u;
-  uint32_t inc[MI];
-#pragma unroll
-  for (int q = 0; q < MI; ++q) inc[q] = ((uint32_t)q < cnt) ? inc_tmp[rs + q] : 0xffffffffu;
-  if constexpr (MI > 1) reg_bitonic<MI, uint32_t>(inc);
-  KeyT key[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) key[i] = (KeyT) ~(KeyT)0;
-#pragma unroll
-  for (int q = 0; q < MI; ++q) {
-    if ((uint32_t)q < cnt) {
-      inc_pos[inc[q]] = rs + q;
-      uint32_t d[L];
-      load_dofs<L>(dofs + (int64_t)(inc[q] / L) * L, d);
-#pragma unroll
-      for (int b = 0; b < L; ++b) key[q * L + b] = ((KeyT)d[b] << CSH) | (KeyT)(q * L + b);
-    }
-  }
-  reg_bitonic<N, KeyT>(key);
-  const uint32_t ncand = cnt * L;
-  // number of distinct columns, block-exclusive scan
-  uint32_t total = 0;
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-    if ((uint32_t)i < ncand) total += (i == 0 || (uint32_t)(key[i] >> CSH) != (uint32_t)(key[i > 0 ? i - 1 : 0] >> CSH)) ? 1u : 0u;
-  uint32_t incl = warp_incl_scan(total);
-  uint32_t mx = __reduce_max_sync(FULL, total);
-  if (lane == 31) s_w[w] = incl;
-  if (lane == 0) s_m[w] = mx;
-  __syncthreads();  // s_rs0, s_w, s_m, zeroed s_sl
-  uint32_t off = incl - total, btotal = 0;
-#pragma unroll
-  for (int i = 0; i < B / 32; ++i) {
-    if (i < w) off += s_w[i];
-    btotal += s_w[i];
-  }
-  const uint32_t rs0 = s_rs0;
-  int run = -1;
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    if ((uint32_t)i < ncand) {
-      const uint32_t col = (uint32_t)(key[i] >> CSH);
-      if (i == 0 || col != (uint32_t)(key[i > 0 ? i - 1 : 0] >> CSH)) {
-        ++run;
-        s_u[off + run] = col;
-      }
-      const uint32_t e0 = (uint32_t)key[i] & ((1u << EB) - 1u);
-      const uint32_t q0 = e0 / L;
-      s_sl[(rs - rs0 + q0) * LP + (e0 - q0 * L)] = (uint8_t)run;
-    }
-  }
-  if (r < n_rows) row_nnz[r] = total;
-  __syncthreads();
-  // coalesced write-out
-  const int64_t r_end = ((int64_t)blockIdx.x + 1) * B < n_rows ? ((int64_t)blockIdx.x + 1) * B : n_rows;
-  const uint32_t ninc = row_start[r_end] - rs0;
-  for (uint32_t j = tid; j < btotal; j += B) ucol_tmp[(uint64_t)rs0 * L + j] = (int32_t)s_u[j];
-  uint32_t* sl_out = reinterpret_cast<uint32_t*>(slots + (uint64_t)rs0 * LP);
-  for (uint32_t j = tid; j < ninc * (LP / 4); j += B) sl_out[j] = reinterpret_cast<const uint32_t*>(s_sl)[j];
-  if (tid == 0) {
-    uint32_t m = s_m[0];
-    for (int q = 1; q < B / 32; ++q) m = s_m[q] > m ? s_m[q] : m;
-    atomicMax(max_nnz, m);
-  }
-}
-
-// ---- per-row dedupe by hashing (rows with 33..256 candidates) -----------------------------------
-// The bitonic network above sorts ALL candidates of a row although only the distinct columns need
-// ordering (a P1 node row of the Kuhn mesh has 96 candidates but ~15 distinct columns).  Here one
-// warp per row
-//   (1) loads the row's incidences (in the arbitrary order k_inc_place left them), sorts them
-//       ascending (= the canonical (dof, cell) order) and records inc_pos: the work of k_row_canon;
-//   (2) every lane loads the dof row of its incident cell with vector loads and inserts the L
-//       columns into an open-addressing table in shared memory (atomicCAS on integers: the
-//       resulting SET is order independent);
-//   (3) compacts the distinct columns, sorts only those and hands every candidate the rank of its
-//       column through the table; a lane writes the LP slot bytes of its incidence as whole words.
-// Output identical to k_rowsort (sorted unique columns + uint8 slot per candidate), tested bit for
-// bit.  (Merging equal columns with match.any before the insert was measured slower.)
-constexpr uint32_t HASH_EMPTY = 0xffffffffu;
-
-template <int HS>
-__device__ __forceinline__ uint32_t hash_col(uint32_t c) {
-  return (c * 2654435761u) >> (32 - (HS == 64 ? 6 : HS == 128 ? 7 : HS == 256 ? 8 : 9));
-}
-
-// sort the nu distinct columns of every group (ucols[0..nu), shared memory; NPU per lane of the
-// group, G*NPU >= the largest nu of the warp), write them back sorted and store every column's rank
-// in tslot at the column's table position.  Called by all lanes of the warp.
-template <int NPU, int HS, int G>
-__device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint32_t* tkey, uint8_t* tslot, int gl) {
-  uint32_t k[NPU];
-#pragma unroll
-  for (int i = 0; i < NPU; ++i) {
-    int e = gl * NPU + i;
-    k[i] = (e < nu) ? ucols[e] : HASH_EMPTY;
-  }
-  __syncwarp();
-  warp_bitonic_u32<NPU, G>(k, gl);
-#pragma unroll
-  for (int i = 0; i < NPU; ++i) {
-    int e = gl * NPU + i;
-    if (e < nu) {
-      ucols[e] = k[i];
-      uint32_t h = hash_col<HS>(k[i]);
-      while (tkey[h] != k[i]) h = (h + 1) & (HS - 1);
-      tslot[h] = (uint8_t)e;
-    }
-  }
-  __syncwarp();
-}
-
-// G lanes per row (256/G rows per block), NPL incidences per lane (row capacity G*NPL incidences),
-// table of HS entries per row (at most 3/4 full)
-template <int G, int NPL, int L, int HS>
-__global__ void __launch_bounds__(256, (NPL == 1 && L <= 6) ? ((256 / G) * HS * 9 <= 20000 ? 8 : 5) : 1)
-k_rowhash(int64_t n_rows, const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ inc_tmp,
-          const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos, uint8_t* __restrict__ slots,
-          int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz, uint32_t* __restrict__ max_nnz) {
-  constexpr int LP = (L + 3) & ~3;
-  constexpr int RPB = 256 / G;  // rows per block
-  __shared__ uint32_t s_key[RPB][HS];
-  __shared__ uint32_t s_ucol[RPB][HS];
-  __shared__ uint8_t s_slot[RPB][HS];
-  __shared__ uint32_t wmax[8];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
-  const int g = threadIdx.x / G;
-  const int64_t r = (int64_t)blockIdx.x * RPB + g;
-  uint32_t* tkey = s_key[g];
-  uint8_t* tslot = s_slot[g];
-  uint32_t* ucols = s_ucol[g];
-  uint32_t rs = 0, cnt = 0;
-  if (r < n_rows) {
-    rs = row_start[r];
-    cnt = row_start[r + 1] - rs;
-  }
-  uint32_t inc[NPL];
-#pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    uint32_t e = (uint32_t)(i * G + gl);
-    inc[i] = (e < cnt) ? inc_tmp[rs + e] : 0xffffffffu;
-  }
-#pragma unroll
-  for (int k = 0; k < HS / G; ++k) tkey[k * G + gl] = HASH_EMPTY;
-  warp_bitonic_u32<NPL, G>(inc, gl);  // canonical order: ascending incidence = ascending (cell, a)
-  // Every incident cell contributes the row's own dof once (the worst same-address conflict): it is
-  // inserted by the first lane alone.
-  const uint32_t hdiag = hash_col<HS>((uint32_t)r);
-  __syncwarp();
-  if (gl == 0 && cnt) tkey[hdiag] = (uint32_t)r;
-  __syncwarp();
-  uint16_t hpos[NPL][L];
-#pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    const uint32_t e = (uint32_t)(gl * NPL + i);
-    if (e < cnt) {
-      inc_pos[inc[i]] = rs + e;
-      uint32_t d[L];
-      load_dofs<L>(dofs + (int64_t)(inc[i] / L) * L, d);
-#pragma unroll
-      for (int b = 0; b < L; ++b) {
-        const uint32_t col = d[b];
-        uint32_t h = hdiag;
-        if (col != (uint32_t)r) {
-          h = hash_col<HS>(col);
-          while (true) {
-            uint32_t old = atomicCAS(&tkey[h], HASH_EMPTY, col);
-            if (old == HASH_EMPTY || old == col) break;
-            h = (h + 1) & (HS - 1);
-          }
-        }
-        hpos[i][b] = (uint16_t)h;
-      }
-    }
-  }
-  __syncwarp();
-  // compact the distinct columns of the group's table
-  int nu = 0;
-  const uint32_t gmask = (G == 32) ? FULL : ((1u << (G & 31)) - 1u);
-#pragma unroll
-  for (int k = 0; k < HS / G; ++k) {
-    uint32_t v = tkey[k * G + gl];
-    unsigned m = (__ballot_sync(FULL, v != HASH_EMPTY) >> gbase) & gmask;
-    if (v != HASH_EMPTY) ucols[nu + __popc(m & ((1u << gl) - 1u))] = v;
-    nu += __popc(m);
-  }
-  __syncwarp();
-  // sort them; the network size is chosen for the longest row of the warp, so that the warp stays converged
-  const int nu_w = (G == 32) ? nu : (int)__reduce_max_sync(FULL, (unsigned)nu);
-  if (G >= 16 && nu_w <= 16) sort_uniques<1, HS, 16>(ucols, nu, tkey, tslot, lane & 15);
-  else if (nu_w <= G) sort_uniques<1, HS, G>(ucols, nu, tkey, tslot, gl);
-  else if (nu_w <= 2 * G) sort_uniques<2, HS, G>(ucols, nu, tkey, tslot, gl);
-  else if (nu_w <= 4 * G) sort_uniques<4, HS, G>(ucols, nu, tkey, tslot, gl);
-  else if (HS * 3 / 4 <= 8 * G || nu_w <= 8 * G) sort_uniques<8, HS, G>(ucols, nu, tkey, tslot, gl);
-  else if (HS * 3 / 4 <= 16 * G || nu_w <= 16 * G) sort_uniques<16, HS, G>(ucols, nu, tkey, tslot, gl);
-  else sort_uniques<32, HS, G>(ucols, nu, tkey, tslot, gl);
-  // slots of the candidates: the LP bytes of one incidence as whole words
-#pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    const uint32_t e = (uint32_t)(gl * NPL + i);
-    if (e < cnt) {
-      uint32_t* dst = reinterpret_cast<uint32_t*>(slots + (uint64_t)(rs + e) * LP);
-#pragma unroll
-      for (int j = 0; j < LP / 4; ++j) {
-        uint32_t wv = 0;
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-          if (4 * j + t < L) wv |= (uint32_t)tslot[hpos[i][4 * j + t]] << (8 * t);
-        dst[j] = wv;
-      }
-    }
-  }
-  const uint32_t base = rs * L;
-  for (int e = gl; e < nu; e += G) ucol_tmp[base + e] = (int32_t)ucols[e];
-  if (r < n_rows && gl == 0) row_nnz[r] = (uint32_t)nu;
-  const uint32_t mxw = __reduce_max_sync(FULL, (unsigned)nu);
-  if (lane == 0) wmax[w] = mxw;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t mx = wmax[0];
-    for (int q = 1; q < 8; ++q) mx = wmax[q] > mx ? wmax[q] : mx;
-    atomicMax(max_nnz, mx);
   }
 }
 
@@ -1232,7 +718,6 @@ struct PhaseTimer {
 };
 
 constexpr int MODE_TWO_LEVEL = 0, MODE_FULL_SORT = 1, MODE_TWO_LEVEL_KEY64 = 2, MODE_TWO_LEVEL_RADIX = 4;
-bool g_force_key64 = false;  // mode 2: exercise the 64-bit-key row sort (tests)
 constexpr uint32_t MAX_ROW_CAND = 512;  // capacity of the largest k_rowsort instance
 
 struct WsLayout {
@@ -1282,132 +767,6 @@ ChunkGrid chunk_grid(int64_t n) {
   return {g, chunk};
 }
 
-template <int G, int ITEMS, typename KeyT>
-int launch_rowsort_l(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
-                     uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
-  unsigned grid = pgb_grid(n_rows * G, 256);
-#define PGB_RL(LL) k_rowsort<G, ITEMS, LL, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz)
-  switch (L) {
-    case 3: PGB_RL(3); break;
-    case 4: PGB_RL(4); break;
-    case 5: PGB_RL(5); break;
-    case 6: PGB_RL(6); break;
-    case 12: PGB_RL(12); break;
-    default: pgb_set_error("k_rowsort: unsupported local size %d", L); return 2;
-  }
-#undef PGB_RL
-  PGB_LAUNCH_CHECK();
-  return 0;
-}
-
-template <int G, int ITEMS>
-int launch_rowsort_k(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
-                     uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
-  // 32-bit keys when (col, position-in-row) fits strictly below the padding value 0xffffffff
-  if ((uint64_t)n_rows * (uint64_t)(G * ITEMS) <= 0xffffffffull && !g_force_key64)
-    return launch_rowsort_l<G, ITEMS, uint32_t>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
-  return launch_rowsort_l<G, ITEMS, uint64_t>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
-}
-
-template <int G, int NPL, int HS>
-int launch_rowhash_l(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs,
-                     uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
-                     cudaStream_t s) {
-  unsigned grid = (unsigned)pgb_cdiv(n_rows, 256 / G);
-#define PGB_RH(LL) k_rowhash<G, NPL, LL, HS><<<grid, 256, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz)
-  switch (L) {
-    case 3: PGB_RH(3); break;
-    case 4: PGB_RH(4); break;
-    case 5: PGB_RH(5); break;
-    case 6: PGB_RH(6); break;
-    case 12: PGB_RH(12); break;
-    default: pgb_set_error("k_rowhash: unsupported local size %d", L); return 2;
-  }
-#undef PGB_RH
-  PGB_LAUNCH_CHECK();
-  return 0;
-}
-
-// fused canonical sort of the incidences + hash dedupe; inc_tmp: the row blocks in any order.
-// Lanes per row from the largest incidence count, table size from the largest candidate count.
-int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row_start,
-                   const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
-                   uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
-#define PGB_RHL(G, N, H) return launch_rowhash_l<G, N, H>(L, n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, s)
-  if (max_inc <= 8) {
-    if (max_cand <= 48) PGB_RHL(8, 1, 64);
-    PGB_RHL(8, 1, 128);  // max_cand <= 96 (L <= 12)
-  }
-  if (max_inc <= 16) {
-    if (max_cand <= 96) PGB_RHL(16, 1, 128);
-    PGB_RHL(16, 1, 256);  // max_cand <= 192
-  }
-  if (max_inc <= 32) {
-    if (max_cand <= 96) PGB_RHL(32, 1, 128);
-    PGB_RHL(32, 1, 512);
-  }
-  if (max_cand <= 96) PGB_RHL(32, 4, 128);
-  PGB_RHL(32, 4, 512);
-#undef PGB_RHL
-}
-
-bool g_force_bitonic = false;  // mode 3: always use the bitonic row sort (tests)
-
-template <int MI, int L, int N>
-int launch_rowthread_k(int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs,
-                       uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
-                       cudaStream_t s) {
-  unsigned grid = (unsigned)pgb_cdiv(n_rows, ROWTHREAD_BLOCK);
-  if ((uint64_t)n_rows * (uint64_t)N <= 0xffffffffull && !g_force_key64)
-    k_rowthread<MI, L, N, uint32_t><<<grid, ROWTHREAD_BLOCK, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz);
-  else
-    k_rowthread<MI, L, N, uint64_t><<<grid, ROWTHREAD_BLOCK, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz);
-  PGB_LAUNCH_CHECK();
-  return 0;
-}
-
-// rows with at most 8 incidences and 64 candidates: one thread per row (k_rowthread)
-bool rowthread_applies(uint32_t max_inc, uint32_t max_cand) {
-  if (g_force_bitonic || max_inc == 0 || max_inc > 8) return false;
-  const uint32_t mi = max_inc <= 1 ? 1 : max_inc <= 2 ? 2 : max_inc <= 4 ? 4 : 8;  // network of the incidences
-  return mi * (max_cand / max_inc) <= 64;
-}
-
-int launch_rowthread(uint32_t max_inc, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp,
-                     const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz,
-                     uint32_t* max_nnz, cudaStream_t s) {
-  const int mi = max_inc <= 1 ? 1 : max_inc <= 2 ? 2 : max_inc <= 4 ? 4 : 8;
-#define PGB_RT(MI, LL, N) \
-  if (L == LL && mi == MI)  \
-    return launch_rowthread_k<MI, LL, N>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, s)
-  PGB_RT(1, 3, 8);  PGB_RT(2, 3, 8);  PGB_RT(4, 3, 16); PGB_RT(8, 3, 32);
-  PGB_RT(1, 4, 8);  PGB_RT(2, 4, 8);  PGB_RT(4, 4, 16); PGB_RT(8, 4, 32);
-  PGB_RT(1, 5, 8);  PGB_RT(2, 5, 16); PGB_RT(4, 5, 32); PGB_RT(8, 5, 64);
-  PGB_RT(1, 6, 8);  PGB_RT(2, 6, 16); PGB_RT(4, 6, 32); PGB_RT(8, 6, 64);
-  PGB_RT(1, 12, 16); PGB_RT(2, 12, 32); PGB_RT(4, 12, 64);
-#undef PGB_RT
-  pgb_set_error("k_rowthread: unsupported local size %d / %u incidences", L, max_inc);
-  return 2;
-}
-
-// rows with many candidates but few distinct columns: dedupe by hashing, sort only the distinct ones
-bool rowhash_applies(uint32_t max_inc, uint32_t max_cand) {
-  return !g_force_bitonic && !g_force_key64 && max_cand > 32 && max_cand <= 256 && max_inc <= 128;
-}
-
-int launch_rowsort(uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc,
-                   const int32_t* dofs, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
-                   cudaStream_t s) {
-#define PGB_RS(G, I) return launch_rowsort_k<G, I>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s)
-  if (max_cand <= 8) PGB_RS(4, 2);
-  if (max_cand <= 16) PGB_RS(8, 2);
-  if (max_cand <= 32) PGB_RS(8, 4);
-  if (max_cand <= 64) PGB_RS(16, 4);
-  if (max_cand <= 128) PGB_RS(32, 4);
-  if (max_cand <= 256) PGB_RS(32, 8);
-  PGB_RS(32, 16);
-#undef PGB_RS
-}
 
 template <int L, int BLK, typename IP>
 int launch_numeric_t_b(int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots, const void* indptr,
@@ -1552,10 +911,8 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     PGB_CHECK(cudaMemsetAsync(row_nnz + n_rows, 0, 2 * sizeof(uint32_t), s));
     pt.mark();
     if (rowthread_applies(max_inc, max_inc * (uint32_t)L)) {
-      const uint32_t grp = ROWTHREAD_BLOCK;
-      PGB_CHECK(cudaMemcpyAsync(meta + 5, &grp, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
       if (launch_rowthread(max_inc, L, n_rows, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
-                           (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s))
+                           (int32_t*)(ws + l.ucol), row_nnz, meta + 4, meta + 5, s))
         return 1;
     } else if (rowhash_applies(max_inc, max_inc * (uint32_t)L)) {
       if (launch_rowhash(max_inc, max_inc * (uint32_t)L, L, n_rows, row_start, inc_rows, cell_dofs, perm_or_inc, slots,

@@ -30,6 +30,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, "pgb_common.cuh"), os.path.join(CSRC, "pgb_rows.cuh"), os.path.join(INCLUDE, "pgb.h")]
+    srcs = [os.path.join(CSRC, src) for src in SOURCES]
+    if not force and not _stale(LIB, srcs + headers):
+        return LIB  # e.g. on a GPU box: the library travels, the object files do not
     objs, procs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

@@ -1,12 +1,17 @@
 // K2: deterministic COO -> CSR.
 //
-// symbolic  : stable LSD radix sort (8-bit digits) of the packed (row,col) keys with the COO
-//             position as payload, then a head-flag compaction that emits indptr / indices /
-//             run offsets.  Keys of the first pass are generated on the fly from cell_dofs.
-// numeric   : data[k] = sum of vals[perm[p]] over the run of entry k, by a warp-shuffle
-//             segmented scan in a fixed order.
-// No floating-point atomics anywhere; the only atomics are shared-memory integer counters of the
-// digit histogram (their result is order independent), so pattern and values are bit-reproducible.
+// symbolic (default, two level): transpose of the cell->dof table by counting (k_inc_count, scan,
+//             k_inc_place), then one row kernel (pgb_rowthread.cu / pgb_rowhash.cu / pgb_rowsort.cu)
+//             that sorts each row's incidences, finds the sorted distinct columns and the slot of
+//             every candidate; scan of the row counts; k_compact.
+// symbolic (fallback, mode 1): stable LSD radix sort (8-bit digits) of the packed (row,col) keys
+//             with the COO position as payload, then a head-flag compaction that emits indptr /
+//             indices / run offsets.  Keys of the first pass are generated on the fly.
+// numeric   : k_numeric_t streams the row-sorted local rows (two-level plans); k_numeric reduces
+//             vals[perm[p]] over the run of every entry with a warp-shuffle segmented scan (mode 1).
+// No floating-point atomics anywhere.  Integer atomics (counters, histogram bins, hash keys, max) are
+// used only where the result that reaches the output does not depend on their order, so pattern
+// and values are bit-reproducible.
 #include "pgb_common.cuh"
 #include "pgb_rows.cuh"
 

@@ -167,6 +167,10 @@ int64_t pgb_csr_workspace_bytes(int64_t nc, int L, int64_t n_rows, int mode);
  * [2] per-row kernel, [3] scan of the row counts. */
 void pgb_set_profile(int on);
 void pgb_get_phase_ms(double* out, int n);
+/* Name of the per-row kernel the last two-level pgb_csr_symbolic_sort launched, e.g.
+ * "k_rowthread<2,4,8,u32>" (template arguments as in the source); "" before the first call or
+ * after a mode-1 call.  For tests and profiles. */
+const char* pgb_csr_last_row_kernel(void);
 int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell_dofs, int mode,
                           void* workspace, int64_t workspace_bytes, uint32_t* perm_or_inc,
                           uint8_t* slots, uint32_t* row_start, int64_t* nnz_host,

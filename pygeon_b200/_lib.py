@@ -24,6 +24,7 @@ _p, _i, _l, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _SIGS = {
     "pgb_version": (_i, []),
     "pgb_last_error": (C.c_char_p, []),
+    "pgb_csr_last_row_kernel": (C.c_char_p, []),
     "pgb_set_l2_fetch_granularity": (_i, [_i]),
     "pgb_get_l2_fetch_granularity": (_i, []),
     "pgb_pack_cells": (_i, [_i, _l, _p, _p, _p, _p, _p, _p, _p]),

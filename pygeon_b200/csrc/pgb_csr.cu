@@ -812,6 +812,7 @@ int launch_numeric_t(int L, int64_t n_rows, int caps, const uint32_t* row_start,
 }  // namespace
 
 extern "C" void pgb_set_profile(int on) { g_profile = on != 0; }
+extern "C" const char* pgb_csr_last_row_kernel(void) { return g_row_kernel; }
 /* phases of the last two-level pgb_csr_symbolic_sort call [ms]: 0 radix sort of the incidences,
  * 1 row offsets + max (incl. the host read), 2 per-row sort, 3 scan of the row counts */
 extern "C" void pgb_get_phase_ms(double* out, int n) {
@@ -835,6 +836,7 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
   PGB_REQUIRE(n_rows > 0 && n_rows < ((int64_t)1 << 31), "pgb_csr_symbolic_sort: n_rows out of range");
   WsLayout l = ws_layout(n_coo, n_inc, n_rows, mode);
   PGB_REQUIRE(workspace_bytes >= l.total, "pgb_csr_symbolic_sort: workspace too small");
+  g_row_kernel[0] = 0;
   *nnz_host = 0;
   if (max_row_nnz_host) *max_row_nnz_host = 0;
   char* ws = (char*)workspace;

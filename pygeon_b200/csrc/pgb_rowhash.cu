@@ -169,6 +169,7 @@ template <int G, int NPL, int HS>
 int launch_rowhash_l(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs,
                      uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
                      cudaStream_t s) {
+  snprintf(g_row_kernel, sizeof(g_row_kernel), "k_rowhash<%d,%d,%d,%d>", G, NPL, L, HS);
   unsigned grid = (unsigned)pgb_cdiv(n_rows, 256 / G);
 #define PGB_RH(LL) k_rowhash<G, NPL, LL, HS><<<grid, 256, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz)
   switch (L) {
@@ -195,10 +196,7 @@ int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, int64_t n_rows, c
                    const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
                    uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
 #define PGB_RHL(G, N, H) return launch_rowhash_l<G, N, H>(L, n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, s)
-  if (max_inc <= 8) {
-    if (max_cand <= 48) PGB_RHL(8, 1, 64);
-    PGB_RHL(8, 1, 128);  // max_cand <= 96 (L <= 12)
-  }
+  if (max_inc <= 8) PGB_RHL(8, 1, 128);  // 65..96 candidates (fewer go to k_rowthread)
   if (max_inc <= 16) {
     if (max_cand <= 96) PGB_RHL(16, 1, 128);
     PGB_RHL(16, 1, 256);  // max_cand <= 192
@@ -207,8 +205,7 @@ int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, int64_t n_rows, c
     if (max_cand <= 96) PGB_RHL(32, 1, 128);
     PGB_RHL(32, 1, 512);
   }
-  if (max_cand <= 96) PGB_RHL(32, 4, 128);
-  PGB_RHL(32, 4, 512);
+  PGB_RHL(32, 4, 512);  // more than 32 incidences: more than 96 candidates
 #undef PGB_RHL
 }
 

@@ -7,6 +7,9 @@ namespace pgb_rows {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// name of the row kernel launched last (pgb_csr_last_row_kernel)
+extern char g_row_kernel[64];
+
 // test switches (pgb_csr_symbolic_sort modes 2 and 3)
 extern bool g_force_key64;    // 64-bit (col, position) keys in the row sorts
 extern bool g_force_bitonic;  // always k_rowsort

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t*
 template <int G, int ITEMS, typename KeyT>
 int launch_rowsort_l(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
                      uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
+  snprintf(g_row_kernel, sizeof(g_row_kernel), "k_rowsort<%d,%d,%d,%s>", G, ITEMS, L, sizeof(KeyT) == 4 ? "u32" : "u64");
   unsigned grid = pgb_grid(n_rows * G, 256);
 #define PGB_RL(LL) k_rowsort<G, ITEMS, LL, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz)
   switch (L) {
@@ -159,6 +160,7 @@ namespace pgb_rows {
 
 bool g_force_key64 = false;
 bool g_force_bitonic = false;
+char g_row_kernel[64] = "";
 
 int launch_rowsort(uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc,
                    const int32_t* dofs, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,

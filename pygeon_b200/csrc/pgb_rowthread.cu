@@ -146,7 +146,9 @@ int launch_rowthread_k(int64_t n_rows, const uint32_t* row_start, const uint32_t
   const uint32_t grp = B;  // k_compact: the unique columns are stored back to back in groups of B rows
   PGB_CHECK(cudaMemcpyAsync(meta_grp, &grp, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   unsigned grid = (unsigned)pgb_cdiv(n_rows, B);
-  if ((uint64_t)n_rows * (uint64_t)N <= 0xffffffffull && !g_force_key64)
+  const bool k32 = (uint64_t)n_rows * (uint64_t)N <= 0xffffffffull && !g_force_key64;
+  snprintf(g_row_kernel, sizeof(g_row_kernel), "k_rowthread<%d,%d,%d,%s>", MI, L, N, k32 ? "u32" : "u64");
+  if (k32)
     k_rowthread<MI, L, N, uint32_t><<<grid, B, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz);
   else
     k_rowthread<MI, L, N, uint64_t><<<grid, B, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz);

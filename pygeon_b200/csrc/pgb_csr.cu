@@ -446,6 +446,24 @@ __global__ void __launch_bounds__(256) k_compact(int64_t n_rows, int L, const ui
   for (uint32_t k = gl; k < cnt; k += 8) indices[o0 + k] = ucol_tmp[base + k];
 }
 
+// scratch written by k_rowthread: the distinct columns of every group of `grp` consecutive rows are
+// already back to back, so the compaction is one contiguous copy per group
+template <typename IP>
+__global__ void __launch_bounds__(256) k_compact_groups(int64_t n_rows, int L, uint32_t grp,
+                                                        const uint32_t* __restrict__ row_start,
+                                                        const uint32_t* __restrict__ row_off,
+                                                        const int32_t* __restrict__ ucol_tmp, IP* __restrict__ indptr,
+                                                        int32_t* __restrict__ indices) {
+  const int64_t first = (int64_t)blockIdx.x * grp;
+  const int64_t last = first + grp < n_rows ? first + grp : n_rows;
+  const uint64_t src0 = (uint64_t)row_start[first] * (uint32_t)L;
+  const uint32_t dst0 = row_off[first];
+  const uint32_t len = row_off[last] - dst0;
+  for (uint32_t j = threadIdx.x; j < len; j += 256) indices[dst0 + j] = ucol_tmp[src0 + j];
+  for (int64_t r = first + threadIdx.x; r < last; r += 256) indptr[r] = (IP)row_off[r];
+  if (last == n_rows && threadIdx.x == 0) indptr[n_rows] = (IP)row_off[n_rows];
+}
+
 // ---- numeric over row-sorted local rows (plans of the two-level symbolic) ------------------------
 // With such a plan K1 writes local row a of cell c straight to position inc_pos[c*L + a] of vals_t,
 // i.e. grouped by matrix row in ascending cell order (the order of the incidence transpose).  A CSR
@@ -977,11 +995,22 @@ extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mo
     const uint32_t* row_off = (const uint32_t*)(ws + l.row_nnz);
     const int32_t* ucol = (const int32_t*)(ws + l.ucol);
     const uint32_t* meta = (const uint32_t*)(ws + l.meta);
-    unsigned grid = pgb_grid((n_rows + 1) * 8, 256);
-    if (idx64)
-      k_compact<int64_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, meta, (int64_t*)indptr, indices);
-    else
-      k_compact<int32_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, meta, (int32_t*)indptr, indices);
+    uint32_t grp = 0;  // layout of the scratch: meta[5] rows per group (k_rowthread) or one segment per row
+    PGB_CHECK(cudaMemcpyAsync(&grp, meta + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PGB_CHECK(cudaStreamSynchronize(s));
+    if (grp) {
+      unsigned grid = (unsigned)pgb_cdiv(n_rows, (int64_t)grp);
+      if (idx64)
+        k_compact_groups<int64_t><<<grid, 256, 0, s>>>(n_rows, L, grp, row_start, row_off, ucol, (int64_t*)indptr, indices);
+      else
+        k_compact_groups<int32_t><<<grid, 256, 0, s>>>(n_rows, L, grp, row_start, row_off, ucol, (int32_t*)indptr, indices);
+    } else {
+      unsigned grid = pgb_grid((n_rows + 1) * 8, 256);
+      if (idx64)
+        k_compact<int64_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, meta, (int64_t*)indptr, indices);
+      else
+        k_compact<int32_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, meta, (int32_t*)indptr, indices);
+    }
   }
   PGB_LAUNCH_CHECK();
   return 0;

@@ -50,7 +50,10 @@ def _oracle(dofs, n_rows, vals):
 CASES = [
     # L, nc, n_rows, hub, row kernel expected in mode 0 (prefix of pgb_csr_last_row_kernel())
     (3, 4000, 9000, 1, "k_rowthread<"),       # k_rowthread MI<=4
-    (3, 4000, 3000, 8, "k_rowthread<8,3,32"),       # k_rowthread MI=8
+    (3, 4000, 3000, 8, "k_rowthread<8,3,32"),
+    (3, 4001, 3000, 8, "k_rowthread<8,3,32"),   # nc*L not a multiple of 4: scalar tails of k_inc_count / k_inc_place
+    (5, 2999, 3100, 8, "k_rowthread<8,5,64"),
+    (3, 130, 131, 3, "k_rowthread<"),           # a single block, ragged last group       # k_rowthread MI=8
     (3, 6000, 2500, 16, "k_rowthread<16,3,64"),      # k_rowthread MI=16, 48 keys
     (3, 6000, 2500, 30, "k_rowhash<32,1,3,128>"),      # k_rowhash 32 lanes, table 128
     (3, 6000, 2500, 80, "k_rowhash<32,4,3,512>"),      # k_rowhash 32 lanes x 4, table 512

@@ -64,7 +64,10 @@ class Discretization(abc.ABC):
         """``(Pi.T @ M @ Pi).tocsc()`` of ``discretization.py:65-89,112-136``."""
         if self.ndof(sd) == 0:
             return sps.csc_array((0, 0))
-        return self.assemble_mass_matrix_device(sd, data).to_scipy("csc")
+        w, K = self._coefficients(sd, data)
+        if self.tensor_order == SCALAR:
+            K = None
+        return engine.assemble_host(self._space, "mass", sd, w, K)
 
     # ---- lumped mass -------------------------------------------------------------------
     _lumped_diagonal = True
@@ -98,7 +101,11 @@ class Discretization(abc.ABC):
     def assemble_stiff_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
         """``(B.T @ A @ B).tocsc()`` of ``discretization.py:154-183``."""
         self.get_range_discr_class(sd.dim)  # raises like the reference when there is none
-        return self.assemble_stiff_matrix_device(sd, data).to_scipy("csc")
+        w, K = self._coefficients(sd, data)
+        form = self._stiff_form(sd)
+        if form in ("stiff2d",) or self._space in ("rt0", "bdm1"):
+            K = None
+        return engine.assemble_host(self._space, form, sd, w, K)
 
     @abc.abstractmethod
     def assemble_diff_matrix(self, sd) -> sps.csc_array: ...

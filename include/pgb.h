@@ -178,10 +178,12 @@ int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell
 int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mode, int64_t nnz,
                             const void* workspace, const uint32_t* row_start, void* indptr, int idx64,
                             int32_t* indices, uint32_t* seg, void* stream);
-/* mode 0 plans: vals_t holds the local rows in row-sorted order (K1 called with dst_pos = inc_pos). */
+/* mode 0 plans: vals_t holds the local rows in row-sorted order (K1 called with dst_pos = inc_pos).
+ * flags bit 0: transpose the rows' entries through shared memory and write them with coalesced
+ * stores (faster when nnz is comparable to n_coo; same values either way). */
 int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, const uint32_t* row_start,
                          const uint8_t* slots, const void* indptr, int idx64, const double* vals_t,
-                         double* data, void* stream);
+                         double* data, int flags, void* stream);
 int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t* seg, const double* vals,
                     double* data, void* stream);
 

@@ -523,19 +523,36 @@ __device__ __forceinline__ void load_slots(const uint8_t* __restrict__ p, uint32
   }
 }
 
-template <int L, int BLK, typename IP>
-__global__ void __launch_bounds__(BLK) k_numeric_t(int64_t n_rows, const uint32_t* __restrict__ row_start,
+// STAGED: the row's entries are transposed through a second shared-memory buffer and written with
+// coalesced stores (a per-thread store costs one L1 wavefront per lane: rows are 8*cnt bytes apart).
+// Pays when the matrix has about as many entries as COO candidates (RT0, BDM1, N0, the Darcy saddle:
+// 5-15 % faster); for P1 in 3D (6.3 candidates per entry) the doubled shared memory takes L1 capacity
+// away from the loads and the kernel gets 20 % slower, so the caller chooses (flags bit 0).
+// (Fetching the slot bytes of 4 local rows with one 16-byte load, rounds aligned to 16 bytes of the
+// slot array, was measured slower for every space.)
+template <int L, int BLK, typename IP, bool STAGED>
+__global__ void __launch_bounds__(BLK) k_numeric_t(int64_t n_rows, int caps, const uint32_t* __restrict__ row_start,
                                                    const uint8_t* __restrict__ slots, const IP* __restrict__ indptr,
                                                    const double* __restrict__ vals_t, double* __restrict__ data) {
   constexpr int U = (L <= 4) ? 4 : 2;  // local rows in flight per thread (8 measured slower)
   constexpr int LP = (L + 3) & ~3;      // row pitch (values and slots)
-  extern __shared__ double acc[];    // [slot][thread]
+  extern __shared__ double smem[];
+  double* acc = smem;  // [slot][thread]
+  __shared__ IP s_o0;
   const int tid = threadIdx.x;
-  const int64_t r = (int64_t)blockIdx.x * BLK + tid;
-  if (r >= n_rows) return;
-  const uint32_t rs = row_start[r], re = row_start[r + 1];
-  const IP o0 = indptr[r];
-  const uint32_t cnt = (uint32_t)(indptr[r + 1] - o0);
+  const int64_t r0 = (int64_t)blockIdx.x * BLK;
+  const int64_t r = r0 + tid;
+  const bool live = r < n_rows;
+  if constexpr (!STAGED)
+    if (!live) return;
+  uint32_t rs = 0, re = 0, cnt = 0;
+  IP o0 = 0;
+  if (live) {
+    rs = row_start[r];
+    re = row_start[r + 1];
+    o0 = indptr[r];
+    cnt = (uint32_t)(indptr[r + 1] - o0);
+  }
   for (uint32_t s2 = 0; s2 < cnt; ++s2) acc[s2 * BLK + tid] = 0.0;
   for (uint32_t q0 = rs; q0 < re; q0 += U) {
     double v[U][LP];
@@ -555,7 +572,20 @@ __global__ void __launch_bounds__(BLK) k_numeric_t(int64_t n_rows, const uint32_
       }
     }
   }
-  for (uint32_t s2 = 0; s2 < cnt; ++s2) data[o0 + s2] = acc[s2 * BLK + tid];
+  if constexpr (!STAGED) {
+    for (uint32_t s2 = 0; s2 < cnt; ++s2) data[o0 + s2] = acc[s2 * BLK + tid];
+  } else {
+    double* outs = smem + (size_t)caps * BLK;  // the block's entries in CSR order
+    if (tid == 0) s_o0 = o0;
+    __syncthreads();
+    const IP ob = s_o0;
+    const uint32_t off = (uint32_t)(o0 - ob);
+    for (uint32_t s2 = 0; s2 < cnt; ++s2) outs[off + s2] = acc[s2 * BLK + tid];
+    __syncthreads();
+    const int64_t r1 = r0 + BLK < n_rows ? r0 + BLK : n_rows;
+    const uint32_t total = (uint32_t)(indptr[r1] - ob);
+    for (uint32_t j = tid; j < total; j += BLK) data[ob + j] = outs[j];
+  }
 }
 
 // ---- numeric: lane-sequential partial sums + warp-shuffle segmented scan ------------------------
@@ -791,37 +821,45 @@ ChunkGrid chunk_grid(int64_t n) {
 }
 
 
-template <int L, int BLK, typename IP>
+template <int L, int BLK, typename IP, bool STAGED>
 int launch_numeric_t_b(int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots, const void* indptr,
                        const double* vals_t, double* data, cudaStream_t s) {
-  size_t smem = (size_t)caps * BLK * sizeof(double);
+  size_t smem = (STAGED ? 2 : 1) * (size_t)caps * BLK * sizeof(double);  // accumulators (+ output staging)
   static size_t attr = 48 * 1024;
   if (smem > attr) {
-    PGB_CHECK(cudaFuncSetAttribute(k_numeric_t<L, BLK, IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PGB_CHECK(cudaFuncSetAttribute(k_numeric_t<L, BLK, IP, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
     attr = smem;
   }
-  k_numeric_t<L, BLK, IP><<<(unsigned)pgb_cdiv(n_rows, BLK), BLK, smem, s>>>(n_rows, row_start, slots,
-                                                                             (const IP*)indptr, vals_t, data);
+  k_numeric_t<L, BLK, IP, STAGED><<<(unsigned)pgb_cdiv(n_rows, BLK), BLK, smem, s>>>(
+      n_rows, caps, row_start, slots, (const IP*)indptr, vals_t, data);
   PGB_LAUNCH_CHECK();
   return 0;
 }
 
 template <int L, typename IP>
-int launch_numeric_t_l(int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots, const void* indptr,
-                       const double* vals_t, double* data, cudaStream_t s) {
-  if (caps <= 200) return launch_numeric_t_b<L, 128, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
-  return launch_numeric_t_b<L, 64, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+int launch_numeric_t_l(int64_t n_rows, int caps, bool staged, const uint32_t* row_start, const uint8_t* slots,
+                       const void* indptr, const double* vals_t, double* data, cudaStream_t s) {
+#define PGB_NT(B, S) return launch_numeric_t_b<L, B, IP, S>(n_rows, caps, row_start, slots, indptr, vals_t, data, s)
+  if (staged) {
+    if (caps <= 48) PGB_NT(128, true);
+    if (caps <= 100) PGB_NT(64, true);
+    PGB_NT(32, true);
+  }
+  if (caps <= 200) PGB_NT(128, false);
+  PGB_NT(64, false);
+#undef PGB_NT
 }
 
 template <typename IP>
-int launch_numeric_t(int L, int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots,
+int launch_numeric_t(int L, int64_t n_rows, int caps, bool staged, const uint32_t* row_start, const uint8_t* slots,
                      const void* indptr, const double* vals_t, double* data, cudaStream_t s) {
   switch (L) {
-    case 3: return launch_numeric_t_l<3, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
-    case 4: return launch_numeric_t_l<4, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
-    case 5: return launch_numeric_t_l<5, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
-    case 6: return launch_numeric_t_l<6, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
-    case 12: return launch_numeric_t_l<12, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+    case 3: return launch_numeric_t_l<3, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
+    case 4: return launch_numeric_t_l<4, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
+    case 5: return launch_numeric_t_l<5, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
+    case 6: return launch_numeric_t_l<6, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
+    case 12: return launch_numeric_t_l<12, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
   }
   pgb_set_error("pgb_csr_numeric_rows: unsupported local size %d", L);
   return 2;
@@ -1018,13 +1056,14 @@ extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mo
 
 extern "C" int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, const uint32_t* row_start,
                                     const uint8_t* slots, const void* indptr, int idx64, const double* vals_t,
-                                    double* data, void* stream) {
+                                    double* data, int flags, void* stream) {
   if (n_rows == 0) return 0;
   PGB_REQUIRE(max_row_nnz >= 0 && max_row_nnz <= 255, "pgb_csr_numeric_rows: max_row_nnz out of range");
   cudaStream_t s = (cudaStream_t)stream;
   int caps = max_row_nnz < 1 ? 1 : max_row_nnz;
-  return idx64 ? launch_numeric_t<int64_t>(L, n_rows, caps, row_start, slots, indptr, vals_t, data, s)
-               : launch_numeric_t<int32_t>(L, n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+  const bool staged = (flags & 1) != 0;
+  return idx64 ? launch_numeric_t<int64_t>(L, n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s)
+               : launch_numeric_t<int32_t>(L, n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
 }
 
 extern "C" int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t* seg,

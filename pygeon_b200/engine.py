@@ -576,10 +576,13 @@ def numeric(plan: CsrPlan, vals: torch.Tensor, out=None) -> torch.Tensor:
             check(lib.pgb_csr_numeric(plan.nnz, plan.perm.data_ptr(), plan.seg.data_ptr(), vals.data_ptr(),
                                       data.data_ptr(), _stream()))
         else:
+            # coalesced output through shared memory when the matrix has about as many entries as
+            # COO candidates (RT0, BDM1, N0, Darcy); not for P1 in 3D (6 candidates per entry)
+            staged = 1 if 3 * plan.nnz > plan.n_coo else 0
             check(lib.pgb_csr_numeric_rows(plan.n_rows, plan.L, plan.max_row_nnz, plan.row_start.data_ptr(),
                                            plan.slots.data_ptr(), plan.indptr.data_ptr(),
                                            1 if plan.indptr.dtype == torch.int64 else 0,
-                                           vals.data_ptr(), data.data_ptr(), _stream()))
+                                           vals.data_ptr(), data.data_ptr(), staged, _stream()))
         _lib.count(1)
     return data
 

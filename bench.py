@@ -7,8 +7,8 @@ Workload at N=1: BASELINE.json configs[1] - pg.Lagrange1 stiffness on the 128^3 
 tetrahedral unit cube (12 582 912 tets), followed by CG iterations on the assembled operator.
 
 A *step* is one complete assembly of that matrix into CSR with NOTHING cached: grid packing
-(node-opposite-face tables, coordinates), the symbolic phase (radix sort by (row, col), pattern),
-the per-cell local matrices and the segmented reduce.  ``value`` = cells/s with the grid's raw
+(node-opposite-face tables, coordinates), the symbolic phase (incidence transpose + per-row sort of the
+distinct columns = the sort by (row, col); pattern), the per-cell local matrices and the ordered reduce.  ``value`` = cells/s with the grid's raw
 arrays already resident in HBM; ``e2e`` = the same through the public
 ``pg.Lagrange1().assemble_stiff_matrix(sd)`` call with host (pinned) grid arrays in and a host
 scipy matrix out, host<->device copies inside the timed region.  ``warm`` (symbolic plan reused, the
@@ -35,8 +35,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# (profiles/r1_ncu_full.txt; config #2, L1 stiffness on 128^3; k_rowsort, k_local, k_numeric_t)
-TRAFFIC = {"k_rowsort": 0.800e9, "local_matrices": 2.029e9, "csr_numeric": 2.070e9}
+# (profiles/r1_ncu_full.txt; config #2, L1 stiffness on 128^3; k_rowhash, k_local, k_numeric_t)
+NOMINAL_HBM_GBS = 8000.0  # north_star's nominal HBM3e figure; the measured copy peak is what `frac` uses
+TRAFFIC = {"k_rowhash": 1.048e9, "local_matrices": 2.027e9, "csr_numeric": 2.069e9}
 
 METRIC = "cells assembled/s into CSR"
 UNIT = "cells/s"
@@ -294,33 +295,35 @@ def run_ours(args):
 
     # ---- roofline bookkeeping (algorithmic bytes) --------------------------
     bits = max(1, int(nn - 1).bit_length())
-    passes = (bits + 7) // 8  # radix passes of the incidence transpose (32-bit keys)
     n_inc = nc * 4
     b_local = nc * (16 + 16 + 128) + 32 * nn  # node ids + destination rows + values; coords once per node
     # streaming numeric over the row-sorted local rows: value 8 B + slot 1 B per COO entry, row
     # offsets + indptr 8 B per row, data 8 B per entry
     b_numeric = n_coo * 9 + 8 * nn + nnz * 8
-    b_sort_pass = n_inc * 16  # the scatter kernel moves each (key, payload) once in and once out
-    # per-row sort: read sorted incidences + row offsets, write perm, unique cols / run starts
-    b_rowsort = n_inc * 4 + n_inc * 4 + 8 * nn + n_coo * 1 + nnz * 4  # incidences + cell->dof table in, slots + unique cols out
+    # counting transpose: dofs in twice, ranks out + in, placed incidences out + in, sorted incidences + inc_pos out
+    b_transpose = n_inc * (4 + 4 + 1 + 1 + 4 + 4 + 4 + 4) + 12 * nn
+    # k_rowhash: row blocks of incidences + row offsets + the cell->dof table in; inc_pos, slot bytes,
+    # unique columns + row counts out
+    b_rowsort = n_inc * 4 + 8 * nn + nc * 16 + n_inc * 4 + n_coo * 1 + nnz * 4 + 4 * nn
     b_step_algo = nc * 16 + 32 * nn + n_coo * 0 + nnz * 12 + 4 * (nn + 1)  # read grid once, write CSR once
     kern = {
         "local_matrices": {"ms": wl, "gbs": b_local / wl / 1e6, "bytes": b_local},
         "csr_numeric": {"ms": wn, "gbs": b_numeric / wn / 1e6, "bytes": b_numeric},
-        "symbolic_total": {"ms": phases["symbolic"], "radix_passes": passes,
-                           "bytes": passes * (b_sort_pass + 4 * n_inc) + b_rowsort + 16 * nnz,
-                           "gbs": (passes * (b_sort_pass + 4 * n_inc) + b_rowsort + 16 * nnz) / phases["symbolic"] / 1e6},
+        "symbolic_total": {"ms": phases["symbolic"],
+                           "bytes": b_transpose + b_rowsort + 16 * nnz,
+                           "gbs": (b_transpose + b_rowsort + 16 * nnz) / phases["symbolic"] / 1e6},
         "pack": {"ms": phases["pack"]},
-        "symbolic_radix_sort": {"ms": float(ph[0]), "passes": passes, "bytes": passes * (b_sort_pass + 4 * n_inc),
-                                "gbs": passes * (b_sort_pass + 4 * n_inc) / max(ph[0], 1e-9) / 1e6},
-        "symbolic_row_offsets": {"ms": float(ph[1])},
+        "symbolic_count_scan": {"ms": float(ph[0]), "note": "k_inc_count (integer atomics) + scan + max + host read"},
+        "symbolic_place_rowcanon": {"ms": float(ph[1]), "note": "k_inc_place + k_row_canon (per-row sort of the incidences)"},
         "symbolic_rowsort": {"ms": float(ph[2]), "bytes": b_rowsort, "gbs": b_rowsort / max(ph[2], 1e-9) / 1e6,
-                             "note": "k_rowhash: shared-memory hash dedupe + register bitonic sort of the distinct "
-                                     "columns; issue / shared-memory bound, not HBM-bound"},
+                             "note": "k_rowhash: canonical sort of the row's incidences, shared-memory hash dedupe, "
+                                     "register bitonic sort of the distinct columns; issue / LSU bound (ncu: SM 76 %, "
+                                     "DRAM 14 %), not HBM-bound"},
         "symbolic_scan": {"ms": float(ph[3])},
     }
     for k in ("local_matrices", "csr_numeric"):
         kern[k]["frac"] = kern[k]["gbs"] / hbm_peak
+        kern[k]["frac_nominal_8tbs"] = kern[k]["gbs"] / NOMINAL_HBM_GBS
 
     # ---- CG on the assembled operator (S + M, SPD, same pattern) --------------------------------
     S = engine.DeviceCSR((nn, nn), plan.indptr, plan.indices, out.clone())
@@ -404,10 +407,10 @@ def run_ours(args):
 
     dom = max(("symbolic", "local", "numeric", "pack"), key=lambda k: phases[k])
     if dom == "symbolic":
-        # dominant kernel of the cold step: k_rowsort (one launch per step)
+        # dominant kernel of the cold step: k_rowhash (one launch per step)
         roof = {"bound": "hbm", "kernel": "k_rowhash (per-row dedupe + sort of the symbolic phase)",
                 "achieved": kern["symbolic_rowsort"]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "traffic": TRAFFIC.get("k_rowsort"),
+                "traffic": TRAFFIC.get("k_rowhash"),
                 "note": "largest single kernel of the cold step; it is issue / shared-memory bound (ncu), so its "
                         "HBM fraction is low by construction; the HBM-bound kernels are in `kernels` "
                         "(local_matrices, csr_numeric) and `solve`"}
@@ -417,6 +420,8 @@ def run_ours(args):
                 "traffic": TRAFFIC.get(key)}
     roof["frac"] = roof["achieved"] / hbm_peak
     roof["peak_source"] = peak_src
+    roof["frac_nominal_8tbs"] = roof["achieved"] / NOMINAL_HBM_GBS  # both denominators
+    solve["frac_nominal_8tbs"] = solve["gbs"] / (NOMINAL_HBM_GBS * world)
 
     value = world * nc_owned / (ms_step * 1e-3)
     line = {

@@ -127,20 +127,24 @@ int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
  * COO entry i = cell*L*L + a*L + b has row cell_dofs[cell*L+a], col cell_dofs[cell*L+b].
  *
  * Two symbolic algorithms produce the same CSR pattern (indptr, indices):
- *   mode 0 (two level, default): (1) stable LSD radix sort of the nc*L incidences (cell, a) by
- *     dof id (32-bit keys) = the transpose of the cell->dof table; returned as inc_pos [nc*L]
- *     (position of incidence cell*L + a in (dof, cell) order: where K1 must put that local row)
- *     and row_start [n_rows+1]; (2) one sub-warp per row
- *     gathers the row's candidate columns, sorts them with a register bitonic network, removes
- *     duplicates and records for every candidate the index of its column inside the row
- *     (slots [nc*L*L] uint8, slots[(row_start[r] + q)*L + b]); (3) a scan of the row counts and a
- *     compaction.  Needs every dof to be shared by at most 512/L cells and every row to have at
- *     most 255 entries; otherwise returns 3 and the caller retries with mode 1.
- *     Rows with 33..256 candidates are deduplicated through a shared-memory hash table first, so
- *     that only their distinct columns are sorted (k_rowhash); shorter / longer rows use the
- *     bitonic network on all candidates (k_rowsort).
- *     (mode 2 = mode 0 with 64-bit keys forced in the row sort, mode 3 = mode 0 with the bitonic
- *     row sort forced; for tests.)
+ *   mode 0 (two level, default): (1) transpose of the cell->dof table by counting: integer
+ *     atomicAdd per incidence (cell, a) on its dof's counter, scan -> row_start [n_rows+1], every
+ *     incidence dropped into its row block; the per-row kernel of step (2) sorts each block
+ *     ascending, i.e. into the order of a stable sort by dof id, so everything downstream is
+ *     independent of the order in which the atomics ran.  Returned: inc_pos [nc*L] (position of
+ *     incidence cell*L + a in (dof, cell) order: where K1 must put that local row) and row_start.
+ *     (2) per row: gather the candidate columns of the incident cells, find the sorted distinct
+ *     columns and record for every candidate the index of its column inside the row
+ *     (slots, uint8, slots[(row_start[r] + q)*LP + b], LP = L rounded up to a multiple of 4).
+ *     Three kernels, picked from the largest incidence / candidate count of a row: one thread per
+ *     row with a register sorting network (<= 16 incidences, <= 64 candidates), a group of 8..32
+ *     lanes per row with a shared-memory hash dedupe (<= 256 candidates), a sub-warp bitonic sort
+ *     of all candidates (<= 512).  (3) a scan of the row counts and a compaction.
+ *     Needs every dof to be shared by at most min(256, 512/L) cells and every row to have at most
+ *     255 entries; otherwise returns 3 and the caller retries with mode 1.
+ *     Test modes: 2 = 64-bit (col, position) keys forced in the row sorts, 3 = the sub-warp bitonic
+ *     row sort forced, 4 = step (1) by a stable LSD radix sort of the incidences (32-bit keys)
+ *     instead of counting.  All give bit-identical inc_pos / slots / pattern.
  *   mode 1 (full sort): stable LSD radix sort of all nc*L*L packed (row,col) keys (64-bit) with
  *     the COO position as payload (perm [n_coo]), then head-flag compaction (seg [nnz+1]).
  * symbolic_sort: workspace of pgb_csr_workspace_bytes(nc, L, n_rows, mode) bytes.
@@ -158,9 +162,15 @@ int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
  */
 int64_t pgb_csr_workspace_bytes(int64_t nc, int L, int64_t n_rows, int mode);
 /* Optional CUDA-event timing of the phases of the two-level symbolic_sort (off by default):
- * out[0] radix sort of the incidences, [1] row offsets + max count, [2] per-row sort, [3] scan. */
+ * out[0] counting (k_inc_count, scan, max, host read; mode 4: the radix sort), [1] placement of the
+ * incidences (+ k_row_canon when the row kernel does not sort them itself; mode 4: row offsets),
+ * [2] per-row kernel, [3] scan of the row counts. */
 void pgb_set_profile(int on);
 void pgb_get_phase_ms(double* out, int n);
+/* Name of the per-row kernel the last two-level pgb_csr_symbolic_sort launched, e.g.
+ * "k_rowthread<2,4,8,u32>" (template arguments as in the source); "" before the first call or
+ * after a mode-1 call.  For tests and profiles. */
+const char* pgb_csr_last_row_kernel(void);
 int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell_dofs, int mode,
                           void* workspace, int64_t workspace_bytes, uint32_t* perm_or_inc,
                           uint8_t* slots, uint32_t* row_start, int64_t* nnz_host,
@@ -168,10 +178,12 @@ int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell
 int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mode, int64_t nnz,
                             const void* workspace, const uint32_t* row_start, void* indptr, int idx64,
                             int32_t* indices, uint32_t* seg, void* stream);
-/* mode 0 plans: vals_t holds the local rows in row-sorted order (K1 called with dst_pos = inc_pos). */
+/* mode 0 plans: vals_t holds the local rows in row-sorted order (K1 called with dst_pos = inc_pos).
+ * flags bit 0: transpose the rows' entries through shared memory and write them with coalesced
+ * stores (faster when nnz is comparable to n_coo; same values either way). */
 int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, const uint32_t* row_start,
                          const uint8_t* slots, const void* indptr, int idx64, const double* vals_t,
-                         double* data, void* stream);
+                         double* data, int flags, void* stream);
 int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t* seg, const double* vals,
                     double* data, void* stream);
 

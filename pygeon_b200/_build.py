@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libpgb.so")
-SOURCES = ["pgb_api.cu", "pgb_pack.cu", "pgb_local.cu", "pgb_csr.cu", "pgb_krylov.cu"]
+SOURCES = ["pgb_api.cu", "pgb_pack.cu", "pgb_local.cu", "pgb_csr.cu", "pgb_rowsort.cu", "pgb_rowthread.cu",
+           "pgb_rowhash.cu", "pgb_krylov.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", f"-I{INCLUDE}", f"-I{CSRC}",
@@ -28,7 +29,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(CSRC, "pgb_common.cuh"), os.path.join(INCLUDE, "pgb.h")]
+    headers = [os.path.join(CSRC, "pgb_common.cuh"), os.path.join(CSRC, "pgb_rows.cuh"), os.path.join(INCLUDE, "pgb.h")]
+    srcs = [os.path.join(CSRC, src) for src in SOURCES]
+    if not force and not _stale(LIB, srcs + headers):
+        return LIB  # e.g. on a GPU box: the library travels, the object files do not
     objs, procs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

@@ -24,6 +24,7 @@ _p, _i, _l, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _SIGS = {
     "pgb_version": (_i, []),
     "pgb_last_error": (C.c_char_p, []),
+    "pgb_csr_last_row_kernel": (C.c_char_p, []),
     "pgb_set_l2_fetch_granularity": (_i, [_i]),
     "pgb_get_l2_fetch_granularity": (_i, []),
     "pgb_pack_cells": (_i, [_i, _l, _p, _p, _p, _p, _p, _p, _p]),
@@ -39,7 +40,7 @@ _SIGS = {
     "pgb_get_phase_ms": (None, [_p, _i]),
     "pgb_csr_symbolic_sort": (_i, [_l, _l, _i, _p, _i, _p, _l, _p, _p, _p, C.POINTER(C.c_int64), C.POINTER(_i), _p]),
     "pgb_csr_symbolic_finish": (_i, [_l, _l, _i, _i, _l, _p, _p, _p, _i, _p, _p, _p]),
-    "pgb_csr_numeric_rows": (_i, [_l, _i, _i, _p, _p, _p, _i, _p, _p, _p]),
+    "pgb_csr_numeric_rows": (_i, [_l, _i, _i, _p, _p, _p, _i, _p, _p, _i, _p]),
     "pgb_csr_numeric": (_i, [_l, _p, _p, _p, _p, _p]),
     "pgb_spmv": (_i, [_l, _p, _i, _p, _p, _p, _p, _i, _p]),
     "pgb_cg": (_i, [_l, _p, _i, _p, _p, _p, _p, _p, _d, _d, _i, _p, C.POINTER(_i), C.POINTER(_i), _p, _p]),

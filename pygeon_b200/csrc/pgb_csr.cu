@@ -1,13 +1,21 @@
 // K2: deterministic COO -> CSR.
 //
-// symbolic  : stable LSD radix sort (8-bit digits) of the packed (row,col) keys with the COO
-//             position as payload, then a head-flag compaction that emits indptr / indices /
-//             run offsets.  Keys of the first pass are generated on the fly from cell_dofs.
-// numeric   : data[k] = sum of vals[perm[p]] over the run of entry k, by a warp-shuffle
-//             segmented scan in a fixed order.
-// No floating-point atomics anywhere; the only atomics are shared-memory integer counters of the
-// digit histogram (their result is order independent), so pattern and values are bit-reproducible.
+// symbolic (default, two level): transpose of the cell->dof table by counting (k_inc_count, scan,
+//             k_inc_place), then one row kernel (pgb_rowthread.cu / pgb_rowhash.cu / pgb_rowsort.cu)
+//             that sorts each row's incidences, finds the sorted distinct columns and the slot of
+//             every candidate; scan of the row counts; k_compact.
+// symbolic (fallback, mode 1): stable LSD radix sort (8-bit digits) of the packed (row,col) keys
+//             with the COO position as payload, then a head-flag compaction that emits indptr /
+//             indices / run offsets.  Keys of the first pass are generated on the fly.
+// numeric   : k_numeric_t streams the row-sorted local rows (two-level plans); k_numeric reduces
+//             vals[perm[p]] over the run of every entry with a warp-shuffle segmented scan (mode 1).
+// No floating-point atomics anywhere.  Integer atomics (counters, histogram bins, hash keys, max) are
+// used only where the result that reaches the output does not depend on their order, so pattern
+// and values are bit-reproducible.
 #include "pgb_common.cuh"
+#include "pgb_rows.cuh"
+
+using namespace pgb_rows;
 
 namespace {
 
@@ -17,7 +25,6 @@ constexpr int SORT_BLOCK = 256;
 constexpr int SORT_WARPS = SORT_BLOCK / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_BLOCK * SORT_ITEMS;  // 4096 keys per block
-constexpr unsigned FULL = 0xffffffffu;
 
 constexpr int SCAN_G = PGB_NPART;  // chunks of the two-level scans (<= 2048)
 
@@ -67,16 +74,6 @@ __global__ void __launch_bounds__(SORT_BLOCK) k_radix_hist(KeySrc<KeyT> src, uin
 }
 
 // ---- two-level exclusive scan over uint32 (reduce / scan partials / apply) -------------------
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
-  int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t t = __shfl_up_sync(FULL, v, d);
-    if (lane >= d) v += t;
-  }
-  return v;
-}
-
 // exclusive scan of one value per thread over a 256-thread block; returns exclusive prefix,
 // total in `total`.  ws: 8 uint32 of shared memory.
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* ws, uint32_t& total) {
@@ -346,283 +343,78 @@ __global__ void __launch_bounds__(256) k_max_row(int64_t n_rows, const uint32_t*
   }
 }
 
-// Key = (col << CSH) | e0 with e0 the candidate's position in the row before sorting
-// (e0 = q*L + b for the q-th incidence of the row and local column b).  KeyT = uint32_t
-// (CSH = log2 N) whenever n_rows * N fits in 32 bits, else uint64_t (CSH = 32).
-// Output per row: the sorted unique columns (scratch, compacted later), and for every candidate
-// the index of its column among them ("slot", uint8): slots[(row_start[r] + q)*L + b].
-template <int G, int ITEMS, int L, typename KeyT>
-__global__ void __launch_bounds__(256) k_rowsort(int64_t n_rows, const uint32_t* __restrict__ row_start,
-                                                 const uint32_t* __restrict__ inc_sorted,
-                                                 const int32_t* __restrict__ dofs, uint8_t* __restrict__ slots,
-                                                 int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz,
-                                                 uint32_t* __restrict__ max_nnz) {
-  constexpr int N = G * ITEMS;
-  constexpr int LP = (L + 3) & ~3;
-  constexpr bool K32 = sizeof(KeyT) == 4;
-  constexpr int EB = (N <= 8) ? 3 : (N <= 16) ? 4 : (N <= 32) ? 5 : (N <= 64) ? 6 : (N <= 128) ? 7 : (N <= 256) ? 8 : 9;
-  constexpr int CSH = K32 ? EB : 32;  // column shift inside the key
-  __shared__ uint32_t wmax[8];
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % G;  // lane within the group
+// ---- incidence transpose by counting (default) ---------------------------------------------------
+// (1) k_inc_count: cnt[dof] += 1 for every incidence; the value the integer atomic returns is kept
+//     as a provisional rank inside the row (it depends on the execution order, the counts do not).
+// (2) exclusive scan of cnt -> row_start.
+// (3) k_inc_place: incidence i goes to row_start[dof] + rank  (a permutation of the row's block).
+// (4) k_row_canon: every row sorts its (short) incidence list ascending, which is exactly the order
+//     a stable sort by dof produces: inc_sorted / inc_pos are bit-identical to the radix path and
+//     to themselves from run to run.  The floating-point summation order downstream is therefore
+//     fixed; the atomics only ever touch integer counters.
+__global__ void __launch_bounds__(256) k_inc_count(uint32_t n_inc, const int32_t* __restrict__ dofs,
+                                                   uint32_t* __restrict__ cnt, uint8_t* __restrict__ rank) {
+  const uint32_t i0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+  if (i0 >= n_inc) return;
+  if (i0 + 4 <= n_inc) {
+    int4 d = *reinterpret_cast<const int4*>(dofs + i0);
+    uint32_t r0 = atomicAdd(cnt + d.x, 1u), r1 = atomicAdd(cnt + d.y, 1u);
+    uint32_t r2 = atomicAdd(cnt + d.z, 1u), r3 = atomicAdd(cnt + d.w, 1u);
+    uchar4 o;
+    o.x = (uint8_t)min(r0, 255u), o.y = (uint8_t)min(r1, 255u);
+    o.z = (uint8_t)min(r2, 255u), o.w = (uint8_t)min(r3, 255u);
+    *reinterpret_cast<uchar4*>(rank + i0) = o;
+  } else {
+    for (uint32_t i = i0; i < n_inc; ++i) rank[i] = (uint8_t)min(atomicAdd(cnt + dofs[i], 1u), 255u);
+  }
+}
+
+// valid when every dof has at most 256 incidences (ranks did not saturate)
+__global__ void __launch_bounds__(256) k_inc_place(uint32_t n_inc, const int32_t* __restrict__ dofs,
+                                                   const uint32_t* __restrict__ row_start,
+                                                   const uint8_t* __restrict__ rank, uint32_t* __restrict__ inc_tmp) {
+  const uint32_t i0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+  if (i0 >= n_inc) return;
+  if (i0 + 4 <= n_inc) {
+    int4 d = *reinterpret_cast<const int4*>(dofs + i0);
+    uchar4 k = *reinterpret_cast<const uchar4*>(rank + i0);
+    uint32_t p0 = __ldg(row_start + d.x) + k.x, p1 = __ldg(row_start + d.y) + k.y;
+    uint32_t p2 = __ldg(row_start + d.z) + k.z, p3 = __ldg(row_start + d.w) + k.w;
+    inc_tmp[p0] = i0;
+    inc_tmp[p1] = i0 + 1;
+    inc_tmp[p2] = i0 + 2;
+    inc_tmp[p3] = i0 + 3;
+  } else {
+    for (uint32_t i = i0; i < n_inc; ++i) inc_tmp[row_start[dofs[i]] + rank[i]] = i;
+  }
+}
+
+// G lanes per row, NPL incidences per lane (capacity G*NPL)
+template <int G, int NPL>
+__global__ void __launch_bounds__(256) k_row_canon(int64_t n_rows, const uint32_t* __restrict__ row_start,
+                                                   const uint32_t* __restrict__ inc_tmp,
+                                                   uint32_t* __restrict__ inc_sorted, uint32_t* __restrict__ inc_pos) {
+  const int gl = threadIdx.x & (G - 1);
   const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
-  const bool live = r < n_rows;
-  uint32_t rs = 0, re = 0;
-  if (live) {
+  uint32_t rs = 0, cnt = 0;
+  if (r < n_rows) {
     rs = row_start[r];
-    re = row_start[r + 1];
+    cnt = row_start[r + 1] - rs;
   }
-  const uint32_t ncand = (re - rs) * L;
-  const uint32_t base = rs * L;
-
-  // gather candidates, blocked layout: element e = gl*ITEMS + i
-  KeyT key[ITEMS];
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    uint32_t e = gl * ITEMS + i;
-    key[i] = (KeyT) ~(KeyT)0;
-    if (e < ncand) {
-      uint32_t q = e / L, b = e - q * L;
-      uint32_t cell = inc_sorted[rs + q] / L;
-      uint32_t col = (uint32_t)__ldg(dofs + (int64_t)cell * L + b);
-      key[i] = ((KeyT)col << CSH) | (KeyT)e;
-    }
-  }
-  // bitonic sort, ascending, N elements spread over G lanes
-#pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= ITEMS) {
-        const int lj = j / ITEMS;
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-          KeyT other = __shfl_xor_sync(FULL, key[i], lj);
-          int e = gl * ITEMS + i;
-          bool lower = (e & j) == 0;
-          bool asc = (e & k) == 0;
-          KeyT mn = key[i] < other ? key[i] : other;
-          KeyT mx = key[i] < other ? other : key[i];
-          key[i] = (lower == asc) ? mn : mx;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-          if ((i & j) == 0) {
-            int e = gl * ITEMS + i;
-            bool asc = (e & k) == 0;
-            KeyT a = key[i], b = key[i | j];
-            bool sw = asc ? (a > b) : (a < b);
-            key[i] = sw ? b : a;
-            key[i | j] = sw ? a : b;
-          }
-        }
-      }
-    }
-  }
-  // unique columns: head(e) = e == 0 || col(e) != col(e-1)
-  uint32_t prev_last = (uint32_t)(__shfl_up_sync(FULL, key[ITEMS - 1], 1) >> CSH);
-  uint32_t heads = 0;  // bit i set: element i of this lane starts a run
-  int cnt = 0;
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    uint32_t e = gl * ITEMS + i;
-    uint32_t col = (uint32_t)(key[i] >> CSH);
-    uint32_t pc = (i == 0) ? prev_last : (uint32_t)(key[i - 1] >> CSH);
-    bool h = (e < ncand) && (e == 0 || col != pc);
-    heads |= (h ? 1u : 0u) << i;
-    cnt += h;
-  }
-  // exclusive scan of cnt over the G lanes of the group
-  int inc_ = cnt;
-#pragma unroll
-  for (int d = 1; d < G; d <<= 1) {
-    int t = __shfl_up_sync(FULL, inc_, d);
-    if (gl >= d) inc_ += t;
-  }
-  int total = __shfl_sync(FULL, inc_, (lane - gl) + G - 1);
-  int run = inc_ - cnt - 1;  // index of the run that is open when this lane starts
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    uint32_t e = gl * ITEMS + i;
-    if (e < ncand) {
-      if ((heads >> i) & 1u) {
-        ++run;
-        ucol_tmp[base + run] = (int32_t)(key[i] >> CSH);
-      }
-      uint32_t e0 = (uint32_t)key[i] & ((1u << EB) - 1u);  // position before sorting
-      uint32_t q0 = e0 / L;
-      slots[(uint64_t)(rs + q0) * LP + (e0 - q0 * L)] = (uint8_t)run;  // row pitch LP = L rounded up to a multiple of 4
-    }
-  }
-  if (live && gl == 0) row_nnz[r] = (uint32_t)total;
-  // largest row (integer max: order independent)
-  uint32_t mx = __reduce_max_sync(FULL, (uint32_t)total);
-  if (lane == 0) wmax[threadIdx.x >> 5] = mx;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int q = 1; q < 8; ++q) mx = wmax[q] > mx ? wmax[q] : mx;
-    atomicMax(max_nnz, mx);
-  }
-}
-
-// ---- per-row dedupe by hashing (rows with 33..256 candidates) -----------------------------------
-// The bitonic network above sorts ALL candidates of a row although only the distinct columns need
-// ordering (a P1 node row of the Kuhn mesh has 96 candidates but ~15 distinct columns).  Here one
-// warp per row inserts the candidate columns into a 256-entry open-addressing table in shared
-// memory (atomicCAS on integers: the resulting SET is order independent), compacts the distinct
-// columns, sorts only those (1, 2 or 8 per lane) and hands every candidate the rank of its column
-// through the table.  Output identical to k_rowsort (sorted unique columns + uint8 slot per
-// candidate), tested bit for bit.  (Merging equal columns of a 32-candidate chunk with match.any
-// before the insert was measured slower: 1.89 ms vs 1.55 ms on config #2.)
-constexpr int HASH_SIZE = 256;
-constexpr uint32_t HASH_EMPTY = 0xffffffffu;
-
-template <int NPL>
-__device__ __forceinline__ void warp_bitonic_u32(uint32_t (&key)[NPL], int lane) {
-  constexpr int N = 32 * NPL;
-#pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= NPL) {
-        const int lj = j / NPL;
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          uint32_t other = __shfl_xor_sync(FULL, key[i], lj);
-          int e = lane * NPL + i;
-          bool lower = (e & j) == 0, asc = (e & k) == 0;
-          uint32_t mn = min(key[i], other), mx = max(key[i], other);
-          key[i] = (lower == asc) ? mn : mx;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          if ((i & j) == 0) {
-            int e = lane * NPL + i;
-            bool asc = (e & k) == 0;
-            uint32_t a = key[i], b = key[i | j];
-            bool sw = asc ? (a > b) : (a < b);
-            key[i] = sw ? b : a;
-            key[i | j] = sw ? a : b;
-          }
-        }
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ uint32_t hash_col(uint32_t c) { return (c * 2654435761u) >> 24; }
-
-// sort the nu distinct columns held in ucols[0..nu) (shared memory), write them back sorted and
-// store every column's rank in tslot at the column's table position
-template <int NPL>
-__device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint32_t* tkey, uint32_t* tslot, int lane) {
   uint32_t k[NPL];
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
-    int e = lane * NPL + i;
-    k[i] = (e < nu) ? ucols[e] : HASH_EMPTY;
+    uint32_t e = (uint32_t)(i * G + gl);  // any initial placement will do: coalesced
+    k[i] = (e < cnt) ? inc_tmp[rs + e] : 0xffffffffu;
   }
-  warp_bitonic_u32<NPL>(k, lane);
-  __syncwarp();
+  warp_bitonic_u32<NPL, G>(k, gl);
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
-    int e = lane * NPL + i;
-    if (e < nu) {
-      ucols[e] = k[i];
-      uint32_t h = hash_col(k[i]);
-      while (tkey[h] != k[i]) h = (h + 1) & (HASH_SIZE - 1);
-      tslot[h] = (uint32_t)e;
+    uint32_t e = (uint32_t)(gl * NPL + i);
+    if (e < cnt) {
+      inc_sorted[rs + e] = k[i];
+      inc_pos[k[i]] = rs + e;
     }
-  }
-  __syncwarp();
-}
-
-template <int CPL, int L>
-__global__ void __launch_bounds__(256) k_rowhash(int64_t n_rows, const uint32_t* __restrict__ row_start,
-                                                 const uint32_t* __restrict__ inc_sorted,
-                                                 const int32_t* __restrict__ dofs, uint8_t* __restrict__ slots,
-                                                 int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz,
-                                                 uint32_t* __restrict__ max_nnz) {
-  constexpr int LP = (L + 3) & ~3;
-  __shared__ uint32_t s_key[8][HASH_SIZE];
-  __shared__ uint32_t s_slot[8][HASH_SIZE];
-  __shared__ uint32_t s_ucol[8][HASH_SIZE];
-  __shared__ uint32_t wmax[8];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t r = (int64_t)blockIdx.x * 8 + w;
-  uint32_t* tkey = s_key[w];
-  uint32_t* tslot = s_slot[w];
-  uint32_t* ucols = s_ucol[w];
-  uint32_t rs = 0, re = 0;
-  if (r < n_rows) {
-    rs = row_start[r];
-    re = row_start[r + 1];
-  }
-  const uint32_t ncand = (re - rs) * L;
-  const uint32_t base = rs * L;
-#pragma unroll
-  for (int k = 0; k < HASH_SIZE / 32; ++k) tkey[k * 32 + lane] = HASH_EMPTY;
-  __syncwarp();
-  // candidates, strided: e = i*32 + lane; insert their columns.  Every incident cell contributes
-  // the row's own dof once (the worst same-address conflict): it is inserted by lane 0 alone.
-  const uint32_t hdiag = hash_col((uint32_t)r);
-  if (lane == 0 && ncand) tkey[hdiag] = (uint32_t)r;
-  __syncwarp();
-  uint32_t hpos[CPL];
-#pragma unroll
-  for (int i = 0; i < CPL; ++i) {
-    uint32_t e = i * 32 + lane;
-    hpos[i] = 0;
-    if (e < ncand) {
-      uint32_t q = e / L, b = e - q * L;
-      uint32_t cell = inc_sorted[rs + q] / L;
-      uint32_t col = (uint32_t)__ldg(dofs + (int64_t)cell * L + b);
-      uint32_t h = hash_col(col);
-      if (col == (uint32_t)r) {
-        hpos[i] = hdiag;
-        continue;
-      }
-      while (true) {
-        uint32_t old = atomicCAS(&tkey[h], HASH_EMPTY, col);
-        if (old == HASH_EMPTY || old == col) break;
-        h = (h + 1) & (HASH_SIZE - 1);
-      }
-      hpos[i] = h;
-    }
-  }
-  __syncwarp();
-  // compact the distinct columns
-  int nu = 0;
-#pragma unroll
-  for (int k = 0; k < HASH_SIZE / 32; ++k) {
-    uint32_t v = tkey[k * 32 + lane];
-    unsigned m = __ballot_sync(FULL, v != HASH_EMPTY);
-    if (v != HASH_EMPTY) ucols[nu + __popc(m & ((1u << lane) - 1u))] = v;
-    nu += __popc(m);
-  }
-  __syncwarp();
-  if (nu <= 32) sort_uniques<1>(ucols, nu, tkey, tslot, lane);
-  else if (nu <= 64) sort_uniques<2>(ucols, nu, tkey, tslot, lane);
-  else sort_uniques<8>(ucols, nu, tkey, tslot, lane);
-  // slots of the candidates, sorted distinct columns of the row
-#pragma unroll
-  for (int i = 0; i < CPL; ++i) {
-    uint32_t e = i * 32 + lane;
-    if (e < ncand) {
-      uint32_t q = e / L, b = e - q * L;
-      slots[(uint64_t)(rs + q) * LP + b] = (uint8_t)tslot[hpos[i]];
-    }
-  }
-  for (int e = lane; e < nu; e += 32) ucol_tmp[base + e] = (int32_t)ucols[e];
-  if (r < n_rows && lane == 0) row_nnz[r] = (uint32_t)nu;
-  if (lane == 0) wmax[w] = (uint32_t)nu;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t mx = wmax[0];
-    for (int q = 1; q < 8; ++q) mx = wmax[q] > mx ? wmax[q] : mx;
-    atomicMax(max_nnz, mx);
   }
 }
 
@@ -631,8 +423,8 @@ __global__ void __launch_bounds__(256) k_rowhash(int64_t n_rows, const uint32_t*
 template <typename IP>
 __global__ void __launch_bounds__(256) k_compact(int64_t n_rows, int L, const uint32_t* __restrict__ row_start,
                                                  const uint32_t* __restrict__ row_off,
-                                                 const int32_t* __restrict__ ucol_tmp, IP* __restrict__ indptr,
-                                                 int32_t* __restrict__ indices) {
+                                                 const int32_t* __restrict__ ucol_tmp, const uint32_t* __restrict__ meta,
+                                                 IP* __restrict__ indptr, int32_t* __restrict__ indices) {
   // 8 lanes per row
   const int gl = threadIdx.x & 7;
   const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
@@ -641,8 +433,35 @@ __global__ void __launch_bounds__(256) k_compact(int64_t n_rows, int L, const ui
   if (gl == 0) indptr[r] = (IP)o0;
   if (r == n_rows) return;
   uint32_t cnt = row_off[r + 1] - o0;
-  uint32_t base = row_start[r] * (uint32_t)L;
+  // scratch position of the row's columns: per row (k_rowsort / k_rowhash), or back to back inside
+  // groups of meta[5] rows (k_rowthread)
+  const uint32_t grp = meta[5];
+  uint64_t base;
+  if (grp) {
+    const int64_t first = r - r % (int64_t)grp;
+    base = (uint64_t)row_start[first] * (uint32_t)L + (o0 - row_off[first]);
+  } else {
+    base = (uint64_t)row_start[r] * (uint32_t)L;
+  }
   for (uint32_t k = gl; k < cnt; k += 8) indices[o0 + k] = ucol_tmp[base + k];
+}
+
+// scratch written by k_rowthread: the distinct columns of every group of `grp` consecutive rows are
+// already back to back, so the compaction is one contiguous copy per group
+template <typename IP>
+__global__ void __launch_bounds__(256) k_compact_groups(int64_t n_rows, int L, uint32_t grp,
+                                                        const uint32_t* __restrict__ row_start,
+                                                        const uint32_t* __restrict__ row_off,
+                                                        const int32_t* __restrict__ ucol_tmp, IP* __restrict__ indptr,
+                                                        int32_t* __restrict__ indices) {
+  const int64_t first = (int64_t)blockIdx.x * grp;
+  const int64_t last = first + grp < n_rows ? first + grp : n_rows;
+  const uint64_t src0 = (uint64_t)row_start[first] * (uint32_t)L;
+  const uint32_t dst0 = row_off[first];
+  const uint32_t len = row_off[last] - dst0;
+  for (uint32_t j = threadIdx.x; j < len; j += 256) indices[dst0 + j] = ucol_tmp[src0 + j];
+  for (int64_t r = first + threadIdx.x; r < last; r += 256) indptr[r] = (IP)row_off[r];
+  if (last == n_rows && threadIdx.x == 0) indptr[n_rows] = (IP)row_off[n_rows];
 }
 
 // ---- numeric over row-sorted local rows (plans of the two-level symbolic) ------------------------
@@ -704,19 +523,36 @@ __device__ __forceinline__ void load_slots(const uint8_t* __restrict__ p, uint32
   }
 }
 
-template <int L, int BLK, typename IP>
-__global__ void __launch_bounds__(BLK) k_numeric_t(int64_t n_rows, const uint32_t* __restrict__ row_start,
+// STAGED: the row's entries are transposed through a second shared-memory buffer and written with
+// coalesced stores (a per-thread store costs one L1 wavefront per lane: rows are 8*cnt bytes apart).
+// Pays when the matrix has about as many entries as COO candidates (RT0, BDM1, N0, the Darcy saddle:
+// 5-15 % faster); for P1 in 3D (6.3 candidates per entry) the doubled shared memory takes L1 capacity
+// away from the loads and the kernel gets 20 % slower, so the caller chooses (flags bit 0).
+// (Fetching the slot bytes of 4 local rows with one 16-byte load, rounds aligned to 16 bytes of the
+// slot array, was measured slower for every space.)
+template <int L, int BLK, typename IP, bool STAGED>
+__global__ void __launch_bounds__(BLK) k_numeric_t(int64_t n_rows, int caps, const uint32_t* __restrict__ row_start,
                                                    const uint8_t* __restrict__ slots, const IP* __restrict__ indptr,
                                                    const double* __restrict__ vals_t, double* __restrict__ data) {
   constexpr int U = (L <= 4) ? 4 : 2;  // local rows in flight per thread (8 measured slower)
   constexpr int LP = (L + 3) & ~3;      // row pitch (values and slots)
-  extern __shared__ double acc[];    // [slot][thread]
+  extern __shared__ double smem[];
+  double* acc = smem;  // [slot][thread]
+  __shared__ IP s_o0;
   const int tid = threadIdx.x;
-  const int64_t r = (int64_t)blockIdx.x * BLK + tid;
-  if (r >= n_rows) return;
-  const uint32_t rs = row_start[r], re = row_start[r + 1];
-  const IP o0 = indptr[r];
-  const uint32_t cnt = (uint32_t)(indptr[r + 1] - o0);
+  const int64_t r0 = (int64_t)blockIdx.x * BLK;
+  const int64_t r = r0 + tid;
+  const bool live = r < n_rows;
+  if constexpr (!STAGED)
+    if (!live) return;
+  uint32_t rs = 0, re = 0, cnt = 0;
+  IP o0 = 0;
+  if (live) {
+    rs = row_start[r];
+    re = row_start[r + 1];
+    o0 = indptr[r];
+    cnt = (uint32_t)(indptr[r + 1] - o0);
+  }
   for (uint32_t s2 = 0; s2 < cnt; ++s2) acc[s2 * BLK + tid] = 0.0;
   for (uint32_t q0 = rs; q0 < re; q0 += U) {
     double v[U][LP];
@@ -736,7 +572,20 @@ __global__ void __launch_bounds__(BLK) k_numeric_t(int64_t n_rows, const uint32_
       }
     }
   }
-  for (uint32_t s2 = 0; s2 < cnt; ++s2) data[o0 + s2] = acc[s2 * BLK + tid];
+  if constexpr (!STAGED) {
+    for (uint32_t s2 = 0; s2 < cnt; ++s2) data[o0 + s2] = acc[s2 * BLK + tid];
+  } else {
+    double* outs = smem + (size_t)caps * BLK;  // the block's entries in CSR order
+    if (tid == 0) s_o0 = o0;
+    __syncthreads();
+    const IP ob = s_o0;
+    const uint32_t off = (uint32_t)(o0 - ob);
+    for (uint32_t s2 = 0; s2 < cnt; ++s2) outs[off + s2] = acc[s2 * BLK + tid];
+    __syncthreads();
+    const int64_t r1 = r0 + BLK < n_rows ? r0 + BLK : n_rows;
+    const uint32_t total = (uint32_t)(indptr[r1] - ob);
+    for (uint32_t j = tid; j < total; j += BLK) data[ob + j] = outs[j];
+  }
 }
 
 // ---- numeric: lane-sequential partial sums + warp-shuffle segmented scan ------------------------
@@ -921,8 +770,7 @@ struct PhaseTimer {
   }
 };
 
-constexpr int MODE_TWO_LEVEL = 0, MODE_FULL_SORT = 1, MODE_TWO_LEVEL_KEY64 = 2;
-bool g_force_key64 = false;  // mode 2: exercise the 64-bit-key row sort (tests)
+constexpr int MODE_TWO_LEVEL = 0, MODE_FULL_SORT = 1, MODE_TWO_LEVEL_KEY64 = 2, MODE_TWO_LEVEL_RADIX = 4;
 constexpr uint32_t MAX_ROW_CAND = 512;  // capacity of the largest k_rowsort instance
 
 struct WsLayout {
@@ -940,7 +788,8 @@ WsLayout ws_layout(int64_t n_coo, int64_t n_inc, int64_t n_rows, int mode) {
   int64_t o = 0;
   int64_t nsort = (mode == MODE_FULL_SORT) ? n_coo : n_inc;
   int64_t ntiles = pgb_cdiv(nsort > 0 ? nsort : 1, SORT_TILE);
-  l.meta = o;  o += 256;  // uint32: [0] mode, [1] cb, [2] nnz, [3] max incidences per row, [4] max row nnz
+  l.meta = o;  o += 256;  // uint32: [0] mode, [1] cb, [2] nnz, [3] max incidences per row, [4] max row nnz,
+                          // [5] rows per group of the unique-column scratch (0: one segment per row)
   l.parts = o; o += al(2048 * 4);
   l.hist = o;  o += al(ntiles * RADIX * 4);
   if (mode == MODE_FULL_SORT) {
@@ -971,104 +820,46 @@ ChunkGrid chunk_grid(int64_t n) {
   return {g, chunk};
 }
 
-template <int G, int ITEMS, typename KeyT>
-int launch_rowsort_l(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
-                     uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
-  unsigned grid = pgb_grid(n_rows * G, 256);
-#define PGB_RL(LL) k_rowsort<G, ITEMS, LL, KeyT><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz)
-  switch (L) {
-    case 3: PGB_RL(3); break;
-    case 4: PGB_RL(4); break;
-    case 5: PGB_RL(5); break;
-    case 6: PGB_RL(6); break;
-    case 12: PGB_RL(12); break;
-    default: pgb_set_error("k_rowsort: unsupported local size %d", L); return 2;
-  }
-#undef PGB_RL
-  PGB_LAUNCH_CHECK();
-  return 0;
-}
 
-template <int G, int ITEMS>
-int launch_rowsort_k(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
-                     uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
-  // 32-bit keys when (col, position-in-row) fits strictly below the padding value 0xffffffff
-  if ((uint64_t)n_rows * (uint64_t)(G * ITEMS) <= 0xffffffffull && !g_force_key64)
-    return launch_rowsort_l<G, ITEMS, uint32_t>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
-  return launch_rowsort_l<G, ITEMS, uint64_t>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
-}
-
-template <int CPL>
-int launch_rowhash(int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
-                   uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
-  unsigned grid = (unsigned)pgb_cdiv(n_rows, 8);
-#define PGB_RH(LL) k_rowhash<CPL, LL><<<grid, 256, 0, s>>>(n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz)
-  switch (L) {
-    case 3: PGB_RH(3); break;
-    case 4: PGB_RH(4); break;
-    case 5: PGB_RH(5); break;
-    case 6: PGB_RH(6); break;
-    case 12: PGB_RH(12); break;
-    default: pgb_set_error("k_rowhash: unsupported local size %d", L); return 2;
-  }
-#undef PGB_RH
-  PGB_LAUNCH_CHECK();
-  return 0;
-}
-
-bool g_force_bitonic = false;  // mode 3: always use the bitonic row sort (tests)
-
-int launch_rowsort(uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc,
-                   const int32_t* dofs, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
-                   cudaStream_t s) {
-  // rows with many candidates but few distinct columns: dedupe by hashing, sort only the distinct ones
-  if (!g_force_bitonic && !g_force_key64 && max_cand > 32 && max_cand <= 256) {
-    if (max_cand <= 64) return launch_rowhash<2>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
-    if (max_cand <= 128) return launch_rowhash<4>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
-    return launch_rowhash<8>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
-  }
-#define PGB_RS(G, I) return launch_rowsort_k<G, I>(L, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s)
-  if (max_cand <= 8) PGB_RS(4, 2);
-  if (max_cand <= 16) PGB_RS(8, 2);
-  if (max_cand <= 32) PGB_RS(8, 4);
-  if (max_cand <= 64) PGB_RS(16, 4);
-  if (max_cand <= 128) PGB_RS(32, 4);
-  if (max_cand <= 256) PGB_RS(32, 8);
-  PGB_RS(32, 16);
-#undef PGB_RS
-}
-
-template <int L, int BLK, typename IP>
+template <int L, int BLK, typename IP, bool STAGED>
 int launch_numeric_t_b(int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots, const void* indptr,
                        const double* vals_t, double* data, cudaStream_t s) {
-  size_t smem = (size_t)caps * BLK * sizeof(double);
+  size_t smem = (STAGED ? 2 : 1) * (size_t)caps * BLK * sizeof(double);  // accumulators (+ output staging)
   static size_t attr = 48 * 1024;
   if (smem > attr) {
-    PGB_CHECK(cudaFuncSetAttribute(k_numeric_t<L, BLK, IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PGB_CHECK(cudaFuncSetAttribute(k_numeric_t<L, BLK, IP, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
     attr = smem;
   }
-  k_numeric_t<L, BLK, IP><<<(unsigned)pgb_cdiv(n_rows, BLK), BLK, smem, s>>>(n_rows, row_start, slots,
-                                                                             (const IP*)indptr, vals_t, data);
+  k_numeric_t<L, BLK, IP, STAGED><<<(unsigned)pgb_cdiv(n_rows, BLK), BLK, smem, s>>>(
+      n_rows, caps, row_start, slots, (const IP*)indptr, vals_t, data);
   PGB_LAUNCH_CHECK();
   return 0;
 }
 
 template <int L, typename IP>
-int launch_numeric_t_l(int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots, const void* indptr,
-                       const double* vals_t, double* data, cudaStream_t s) {
-  if (caps <= 200) return launch_numeric_t_b<L, 128, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
-  return launch_numeric_t_b<L, 64, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+int launch_numeric_t_l(int64_t n_rows, int caps, bool staged, const uint32_t* row_start, const uint8_t* slots,
+                       const void* indptr, const double* vals_t, double* data, cudaStream_t s) {
+#define PGB_NT(B, S) return launch_numeric_t_b<L, B, IP, S>(n_rows, caps, row_start, slots, indptr, vals_t, data, s)
+  if (staged) {
+    if (caps <= 48) PGB_NT(128, true);
+    if (caps <= 100) PGB_NT(64, true);
+    PGB_NT(32, true);
+  }
+  if (caps <= 200) PGB_NT(128, false);
+  PGB_NT(64, false);
+#undef PGB_NT
 }
 
 template <typename IP>
-int launch_numeric_t(int L, int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots,
+int launch_numeric_t(int L, int64_t n_rows, int caps, bool staged, const uint32_t* row_start, const uint8_t* slots,
                      const void* indptr, const double* vals_t, double* data, cudaStream_t s) {
   switch (L) {
-    case 3: return launch_numeric_t_l<3, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
-    case 4: return launch_numeric_t_l<4, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
-    case 5: return launch_numeric_t_l<5, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
-    case 6: return launch_numeric_t_l<6, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
-    case 12: return launch_numeric_t_l<12, IP>(n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+    case 3: return launch_numeric_t_l<3, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
+    case 4: return launch_numeric_t_l<4, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
+    case 5: return launch_numeric_t_l<5, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
+    case 6: return launch_numeric_t_l<6, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
+    case 12: return launch_numeric_t_l<12, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
   }
   pgb_set_error("pgb_csr_numeric_rows: unsupported local size %d", L);
   return 2;
@@ -1077,6 +868,7 @@ int launch_numeric_t(int L, int64_t n_rows, int caps, const uint32_t* row_start,
 }  // namespace
 
 extern "C" void pgb_set_profile(int on) { g_profile = on != 0; }
+extern "C" const char* pgb_csr_last_row_kernel(void) { return g_row_kernel; }
 /* phases of the last two-level pgb_csr_symbolic_sort call [ms]: 0 radix sort of the incidences,
  * 1 row offsets + max (incl. the host read), 2 per-row sort, 3 scan of the row counts */
 extern "C" void pgb_get_phase_ms(double* out, int n) {
@@ -1093,13 +885,14 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
                                      int* max_row_nnz_host, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n_coo = nc * L * L, n_inc = nc * L;
-  PGB_REQUIRE(mode >= 0 && mode <= 3, "pgb_csr_symbolic_sort: bad mode");
+  PGB_REQUIRE(mode >= 0 && mode <= 4, "pgb_csr_symbolic_sort: bad mode");
   g_force_key64 = (mode == MODE_TWO_LEVEL_KEY64);
   g_force_bitonic = (mode == 3);
   PGB_REQUIRE(n_coo < ((int64_t)1 << 32) - SORT_TILE, "pgb_csr_symbolic_sort: n_coo must be < 2^32");
   PGB_REQUIRE(n_rows > 0 && n_rows < ((int64_t)1 << 31), "pgb_csr_symbolic_sort: n_rows out of range");
   WsLayout l = ws_layout(n_coo, n_inc, n_rows, mode);
   PGB_REQUIRE(workspace_bytes >= l.total, "pgb_csr_symbolic_sort: workspace too small");
+  g_row_kernel[0] = 0;
   *nnz_host = 0;
   if (max_row_nnz_host) *max_row_nnz_host = 0;
   char* ws = (char*)workspace;
@@ -1107,7 +900,7 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
   uint32_t* parts = (uint32_t*)(ws + l.parts);
   uint32_t* hist = (uint32_t*)(ws + l.hist);
   const int cb = bits_for(n_rows);
-  uint32_t m[5] = {(uint32_t)mode, (uint32_t)cb, 0u, 0u, 0u};
+  uint32_t m[6] = {(uint32_t)mode, (uint32_t)cb, 0u, 0u, 0u, 0u};
   PGB_CHECK(cudaMemcpyAsync(meta, m, sizeof(m), cudaMemcpyHostToDevice, s));
   if (n_coo == 0) {
     if (mode != MODE_FULL_SORT) PGB_CHECK(cudaMemsetAsync(row_start, 0, sizeof(uint32_t) * (n_rows + 1), s));
@@ -1131,25 +924,67 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     KeySrc<uint32_t> src{nullptr, cell_dofs, (uint32_t)L, (uint32_t)(L * L), cb};
     PhaseTimer pt(s);
     pt.mark();
-    if (radix_sort<uint32_t>(src, (uint32_t)n_inc, cb, kbuf, pbuf, hist, parts, s)) return 1;
-    pt.mark();
-    k_inc_pos<<<pgb_grid(n_inc, 256), 256, 0, s>>>((uint32_t)n_inc, pbuf[0], perm_or_inc);  // inverse permutation
-    k_row_starts<<<pgb_grid(n_inc, 256), 256, 0, s>>>(kbuf[0], (uint32_t)n_inc, n_rows, row_start);
-    k_max_row<<<(unsigned)(n_rows < 256 * 1184 ? pgb_grid(n_rows, 256) : 1184), 256, 0, s>>>(n_rows, row_start, meta + 3);
-    PGB_LAUNCH_CHECK();
     uint32_t max_inc = 0;
-    PGB_CHECK(cudaMemcpyAsync(&max_inc, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    PGB_CHECK(cudaStreamSynchronize(s));
-    if (max_inc * (uint32_t)L > MAX_ROW_CAND) {
-      pgb_set_error("pgb_csr_symbolic_sort: a dof is shared by %u cells (> %u candidates per row); "
-                    "use mode 1 (full sort)", max_inc, MAX_ROW_CAND);
+    const uint32_t* inc_rows = pbuf[0];
+    if (mode == MODE_TWO_LEVEL_RADIX) {
+      if (radix_sort<uint32_t>(src, (uint32_t)n_inc, cb, kbuf, pbuf, hist, parts, s)) return 1;
+      pt.mark();
+      k_inc_pos<<<pgb_grid(n_inc, 256), 256, 0, s>>>((uint32_t)n_inc, pbuf[0], perm_or_inc);  // inverse permutation
+      k_row_starts<<<pgb_grid(n_inc, 256), 256, 0, s>>>(kbuf[0], (uint32_t)n_inc, n_rows, row_start);
+      k_max_row<<<(unsigned)(n_rows < 256 * 1184 ? pgb_grid(n_rows, 256) : 1184), 256, 0, s>>>(n_rows, row_start, meta + 3);
+      PGB_LAUNCH_CHECK();
+      PGB_CHECK(cudaMemcpyAsync(&max_inc, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      PGB_CHECK(cudaStreamSynchronize(s));
+    } else {
+      // counting transpose: counts -> row_start, provisional ranks in kbuf[0] (bytes)
+      uint8_t* rank = (uint8_t*)kbuf[0];
+      PGB_CHECK(cudaMemsetAsync(row_start, 0, sizeof(uint32_t) * (n_rows + 1), s));
+      k_inc_count<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank);
+      PGB_LAUNCH_CHECK();
+      if (scan_u32(row_start, (uint64_t)n_rows + 1, parts, nullptr, s)) return 1;
+      k_max_row<<<(unsigned)(n_rows < 256 * 1184 ? pgb_grid(n_rows, 256) : 1184), 256, 0, s>>>(n_rows, row_start, meta + 3);
+      PGB_LAUNCH_CHECK();
+      PGB_CHECK(cudaMemcpyAsync(&max_inc, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      PGB_CHECK(cudaStreamSynchronize(s));
+      pt.mark();
+      if (max_inc <= 256u && max_inc * (uint32_t)L <= MAX_ROW_CAND) {
+        k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, pbuf[1]);
+        inc_rows = pbuf[1];  // row blocks, each in arbitrary order
+        if (!rowhash_applies(max_inc, max_inc * (uint32_t)L) &&
+            !rowthread_applies(max_inc, max_inc * (uint32_t)L)) {  // those kernels sort the row blocks themselves
+#define PGB_RC(G, N) k_row_canon<G, N><<<pgb_grid(n_rows * G, 256), 256, 0, s>>>(n_rows, row_start, pbuf[1], pbuf[0], perm_or_inc)
+          if (max_inc <= 4) PGB_RC(4, 1);
+          else if (max_inc <= 8) PGB_RC(8, 1);
+          else if (max_inc <= 16) PGB_RC(16, 1);
+          else if (max_inc <= 32) PGB_RC(32, 1);
+          else if (max_inc <= 64) PGB_RC(32, 2);
+          else if (max_inc <= 128) PGB_RC(32, 4);
+          else PGB_RC(32, 8);
+#undef PGB_RC
+          inc_rows = pbuf[0];
+        }
+        PGB_LAUNCH_CHECK();
+      }
+    }
+    if (max_inc * (uint32_t)L > MAX_ROW_CAND || max_inc > 256u) {
+      pgb_set_error("pgb_csr_symbolic_sort: a dof is shared by %u cells (> %u candidates per row or > 256 "
+                    "cells); use mode 1 (full sort)", max_inc, MAX_ROW_CAND);
       return 3;
     }
     PGB_CHECK(cudaMemsetAsync(row_nnz + n_rows, 0, 2 * sizeof(uint32_t), s));
     pt.mark();
-    if (launch_rowsort(max_inc * (uint32_t)L, L, n_rows, row_start, pbuf[0], cell_dofs, slots,
-                       (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s))
+    if (rowthread_applies(max_inc, max_inc * (uint32_t)L)) {
+      if (launch_rowthread(max_inc, L, n_rows, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
+                           (int32_t*)(ws + l.ucol), row_nnz, meta + 4, meta + 5, s))
+        return 1;
+    } else if (rowhash_applies(max_inc, max_inc * (uint32_t)L)) {
+      if (launch_rowhash(max_inc, max_inc * (uint32_t)L, L, n_rows, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
+                         (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s))
+        return 1;
+    } else if (launch_rowsort(max_inc * (uint32_t)L, L, n_rows, row_start, inc_rows, cell_dofs, slots,
+                              (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s)) {
       return 1;
+    }
     pt.mark();
     if (scan_u32(row_nnz, (uint64_t)n_rows + 1, parts, nullptr, s)) return 1;
     PGB_CHECK(cudaMemcpyAsync(meta + 2, row_nnz + n_rows, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
@@ -1197,11 +1032,23 @@ extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mo
     PGB_REQUIRE(row_start, "pgb_csr_symbolic_finish: row_start required in two-level mode");
     const uint32_t* row_off = (const uint32_t*)(ws + l.row_nnz);
     const int32_t* ucol = (const int32_t*)(ws + l.ucol);
-    unsigned grid = pgb_grid((n_rows + 1) * 8, 256);
-    if (idx64)
-      k_compact<int64_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, (int64_t*)indptr, indices);
-    else
-      k_compact<int32_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, (int32_t*)indptr, indices);
+    const uint32_t* meta = (const uint32_t*)(ws + l.meta);
+    uint32_t grp = 0;  // layout of the scratch: meta[5] rows per group (k_rowthread) or one segment per row
+    PGB_CHECK(cudaMemcpyAsync(&grp, meta + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PGB_CHECK(cudaStreamSynchronize(s));
+    if (grp) {
+      unsigned grid = (unsigned)pgb_cdiv(n_rows, (int64_t)grp);
+      if (idx64)
+        k_compact_groups<int64_t><<<grid, 256, 0, s>>>(n_rows, L, grp, row_start, row_off, ucol, (int64_t*)indptr, indices);
+      else
+        k_compact_groups<int32_t><<<grid, 256, 0, s>>>(n_rows, L, grp, row_start, row_off, ucol, (int32_t*)indptr, indices);
+    } else {
+      unsigned grid = pgb_grid((n_rows + 1) * 8, 256);
+      if (idx64)
+        k_compact<int64_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, meta, (int64_t*)indptr, indices);
+      else
+        k_compact<int32_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, meta, (int32_t*)indptr, indices);
+    }
   }
   PGB_LAUNCH_CHECK();
   return 0;
@@ -1209,13 +1056,14 @@ extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mo
 
 extern "C" int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, const uint32_t* row_start,
                                     const uint8_t* slots, const void* indptr, int idx64, const double* vals_t,
-                                    double* data, void* stream) {
+                                    double* data, int flags, void* stream) {
   if (n_rows == 0) return 0;
   PGB_REQUIRE(max_row_nnz >= 0 && max_row_nnz <= 255, "pgb_csr_numeric_rows: max_row_nnz out of range");
   cudaStream_t s = (cudaStream_t)stream;
   int caps = max_row_nnz < 1 ? 1 : max_row_nnz;
-  return idx64 ? launch_numeric_t<int64_t>(L, n_rows, caps, row_start, slots, indptr, vals_t, data, s)
-               : launch_numeric_t<int32_t>(L, n_rows, caps, row_start, slots, indptr, vals_t, data, s);
+  const bool staged = (flags & 1) != 0;
+  return idx64 ? launch_numeric_t<int64_t>(L, n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s)
+               : launch_numeric_t<int32_t>(L, n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
 }
 
 extern "C" int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t* seg,

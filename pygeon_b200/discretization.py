@@ -64,7 +64,10 @@ class Discretization(abc.ABC):
         """``(Pi.T @ M @ Pi).tocsc()`` of ``discretization.py:65-89,112-136``."""
         if self.ndof(sd) == 0:
             return sps.csc_array((0, 0))
-        return self.assemble_mass_matrix_device(sd, data).to_scipy("csc")
+        w, K = self._coefficients(sd, data)
+        if self.tensor_order == SCALAR:
+            K = None
+        return engine.assemble_host(self._space, "mass", sd, w, K)
 
     # ---- lumped mass -------------------------------------------------------------------
     _lumped_diagonal = True
@@ -98,13 +101,38 @@ class Discretization(abc.ABC):
     def assemble_stiff_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
         """``(B.T @ A @ B).tocsc()`` of ``discretization.py:154-183``."""
         self.get_range_discr_class(sd.dim)  # raises like the reference when there is none
-        return self.assemble_stiff_matrix_device(sd, data).to_scipy("csc")
+        w, K = self._coefficients(sd, data)
+        form = self._stiff_form(sd)
+        if form in ("stiff2d",) or self._space in ("rt0", "bdm1"):
+            K = None
+        return engine.assemble_host(self._space, form, sd, w, K)
+
+    def source_term(self, sd, func) -> np.ndarray:
+        """``assemble_mass_matrix(sd) @ interpolate(sd, func)`` (``discretization.py:221-235``)."""
+        return self.assemble_mass_matrix(sd) @ self.interpolate(sd, func)
+
+    def interpolate(self, sd, func) -> np.ndarray:
+        raise NotImplementedError
+
+    def assemble_nat_bc(self, sd, func, b_faces) -> np.ndarray:
+        raise NotImplementedError
 
     @abc.abstractmethod
     def assemble_diff_matrix(self, sd) -> sps.csc_array: ...
 
     @abc.abstractmethod
     def get_range_discr_class(self, dim: int) -> Type["Discretization"]: ...
+
+
+def _eval_points(func, pts: np.ndarray) -> list:
+    """``[func(x) for x in pts.T]`` — the reference evaluates user callables point by point
+    (e.g. ``fem/hdiv.py:208-212``); the results are returned as the reference would see them."""
+    return [func(x) for x in pts.T]
+
+
+def _boundary_faces(b_faces) -> np.ndarray:
+    b_faces = np.asarray(b_faces)
+    return np.where(b_faces)[0] if b_faces.dtype == bool else b_faces
 
 
 class PwConstants(Discretization):
@@ -135,6 +163,14 @@ class PwConstants(Discretization):
 
     def assemble_diff_matrix(self, sd) -> sps.csc_array:
         return sps.csc_array((0, self.ndof(sd)))
+
+    def interpolate(self, sd, func) -> np.ndarray:
+        """Cell integrals ``func(cell centre) * |c|`` (``fem/l2.py:390-406``)."""
+        return np.array([f * vol for f, vol in zip(_eval_points(func, sd.cell_centers), sd.cell_volumes)])
+
+    def assemble_nat_bc(self, sd, _func, _b_faces) -> np.ndarray:
+        """Discontinuous functions have no boundary trace: zero (``fem/l2.py:169-190``)."""
+        return np.zeros(self.ndof(sd))
 
     def get_range_discr_class(self, dim: int):
         raise NotImplementedError("There's no zero discretization in PyGeoN")
@@ -176,6 +212,26 @@ class Lagrange1(Discretization):
             case _:
                 raise ValueError("Dimension must be 0, 1, 2, or 3.")
 
+    def interpolate(self, sd, func) -> np.ndarray:
+        """Nodal values (``fem/h1.py:255-269``)."""
+        return np.array(_eval_points(func, sd.nodes))
+
+    def assemble_nat_bc(self, sd, func, b_faces) -> np.ndarray:
+        """``(v, g)`` on the boundary faces by the midpoint value spread over the face's nodes
+        (``fem/h1.py:271-302``); accumulated face by face in the order of ``b_faces``."""
+        b_faces = _boundary_faces(b_faces)
+        vals = np.zeros(self.ndof(sd))
+        if b_faces.size == 0:
+            return vals
+        fn = sd.face_nodes
+        g = np.array(_eval_points(func, sd.face_centers[:, b_faces]), dtype=float).reshape(b_faces.size)
+        cnt = fn.indptr[b_faces + 1] - fn.indptr[b_faces]
+        contrib = np.repeat(g * sd.face_areas[b_faces] / cnt, cnt)
+        starts = np.repeat(fn.indptr[b_faces], cnt)
+        within = np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        np.add.at(vals, fn.indices[starts + within], contrib)
+        return vals
+
     def get_range_discr_class(self, dim: int):
         match dim:
             case 3:
@@ -202,6 +258,23 @@ class RT0(Discretization):
         """``fem/hdiv.py:177-192``."""
         return sps.csc_array(sd.cell_faces.T)
 
+    def interpolate(self, sd, func) -> np.ndarray:
+        """Normal fluxes ``func(face centre) . n_f`` (``fem/hdiv.py:194-212``)."""
+        f = _eval_points(func, sd.face_centers)
+        return np.array([np.inner(np.asarray(v).flatten(), n) for v, n in zip(f, sd.face_normals.T)])
+
+    def assemble_nat_bc(self, sd, func, b_faces) -> np.ndarray:
+        """``(u . n, g)`` on the boundary: ``g(face centre)`` times the orientation of the face
+        w.r.t. its only cell (``fem/hdiv.py:214-241``)."""
+        b_faces = _boundary_faces(b_faces)
+        vals = np.zeros(self.ndof(sd))
+        if b_faces.size == 0:
+            return vals
+        sign = np.asarray(sd.cell_faces.tocsr()[b_faces, :].sum(axis=1)).ravel()
+        g = np.array(_eval_points(func, sd.face_centers[:, b_faces]), dtype=float).reshape(b_faces.size)
+        vals[b_faces] = g * sign
+        return vals
+
     def get_range_discr_class(self, _dim: int):
         return PwConstants
 
@@ -227,6 +300,29 @@ class BDM1(Discretization):
     def assemble_diff_matrix(self, sd) -> sps.csc_array:
         """``fem/hdiv.py:353-371``."""
         return (sps.csc_array(sd.cell_faces.T) @ self.proj_to_RT0(sd)).tocsc()
+
+    def interpolate(self, sd, func) -> np.ndarray:
+        """``n_f . func(node)`` for the d nodes of every face (``fem/hdiv.py:373-395``)."""
+        d, nf = sd.dim, sd.num_faces
+        fn = sd.face_nodes.indices.reshape(nf, d)
+        fvals = np.array([np.asarray(v).flatten() for v in _eval_points(func, sd.nodes)])  # (nn, 3)
+        vals = np.einsum("if,fji->jf", sd.face_normals, fvals[fn])  # (d, nf): pos-major
+        return vals.reshape(-1)
+
+    def assemble_nat_bc(self, sd, func, b_faces) -> np.ndarray:
+        """``(q . n, g)`` on the boundary with the P1 mass of the face (``fem/hdiv.py:397-436``)."""
+        b_faces = _boundary_faces(b_faces)
+        d, nf = sd.dim, sd.num_faces
+        vals = np.zeros(self.ndof(sd))
+        if b_faces.size == 0:
+            return vals
+        local_mass = (np.ones((d, d)) + np.eye(d)) / (d * (d + 1))  # PwLinears.assemble_local_mass(d - 1)
+        signs = sd.cell_faces @ np.ones(sd.num_cells)
+        fn = sd.face_nodes.indices.reshape(nf, d)[b_faces]  # (nb, d)
+        g = np.array(_eval_points(func, sd.nodes[:, fn.ravel()]), dtype=float).reshape(b_faces.size, d)
+        loc = signs[b_faces, None] * (g @ local_mass.T)  # (nb, d)
+        vals[(b_faces[:, None] + np.arange(d)[None, :] * nf).ravel()] = loc.ravel()
+        return vals
 
     def get_range_discr_class(self, _dim: int):
         return PwConstants
@@ -255,6 +351,16 @@ class Nedelec0(Discretization):
             case _:
                 diff = sps.csc_array((0, self.ndof(sd)))
         return diff.tocsc()
+
+    def interpolate(self, sd, func) -> np.ndarray:
+        """Tangential components at the edge midpoints (``fem/hcurl.py:146-164``)."""
+        edge_nodes = sd.ridge_peaks if sd.dim == 3 else sd.face_ridges
+        mid = sd.nodes @ abs(edge_nodes.astype(float)) / 2
+        f = _eval_points(func, mid)
+        return np.array([np.inner(np.asarray(v).flatten(), t) for v, t in zip(f, sd.edge_tangents.T)])
+
+    def assemble_nat_bc(self, sd, func, b_faces) -> np.ndarray:
+        raise NotImplementedError  # as the reference, fem/hcurl.py:108-126
 
     def assemble_lumped_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
         """Row sums of the mass matrix on the diagonal (``fem/hcurl.py:63-80``)."""

@@ -7,6 +7,7 @@ libpgb.so through :mod:`pygeon_b200._lib`.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -44,6 +45,37 @@ def _to_dev(arr: np.ndarray, dev, dtype=None) -> torch.Tensor:
     return t
 
 
+_SIDE: dict = {}
+# copy / compute overlap of the host-in / host-out path (PGB_OVERLAP=0 switches both off: debugging)
+overlap_upload = os.environ.get("PGB_OVERLAP", "1") != "0"    # `nodes` goes up on a side stream (pinned sources only)
+overlap_download = os.environ.get("PGB_OVERLAP", "1") != "0"  # the pattern comes down on a side stream while K1 / K2 run
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    """One extra stream per device for copies that may overlap the kernels of the current stream."""
+    key = torch.device(dev).index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(dev)
+    return _SIDE[key]
+
+
+def _to_dev_side(arr: np.ndarray, dev):
+    """Upload ``arr`` on the side stream when it is pinned, so that kernels which do not read it
+    need not wait for it.  Returns (tensor, event to wait for before the first read | None)."""
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if not overlap_upload or not t.is_pinned():
+        return t.to(dev, non_blocking=True), None
+    main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+    dst = torch.empty(t.shape, dtype=t.dtype, device=dev)
+    side.wait_stream(main)  # the block may have been used by earlier work of the current stream
+    with torch.cuda.stream(side):
+        dst.copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    dst.record_stream(side)
+    return dst, ev
+
+
 class _PinnedPool:
     """Pinned host blocks for results.  A block is handed out as the memory of the numpy arrays
     returned to the caller (who owns them: the block is not reused while any array derived from it
@@ -72,21 +104,31 @@ class _PinnedPool:
 _POOL = _PinnedPool()
 
 
-def _to_host(tensors) -> list:
-    """Device tensors -> numpy arrays owned by the caller, backed by recycled pinned blocks."""
-    import weakref
-
+def _d2h_start(tensors, stream=None):
+    """Queue device -> pinned-host copies of ``tensors`` on ``stream`` (default: the current one)."""
     dev = tensors[0].device
     views, blocks = [], []
     with torch.cuda.device(dev):
-        for t in tensors:
-            nbytes = t.numel() * t.element_size()
-            blk = _POOL.take(nbytes)
-            view = blk[:nbytes].view(t.dtype).view(t.shape)
-            view.copy_(t, non_blocking=True)
-            views.append(view)
-            blocks.append(blk)
-        torch.cuda.current_stream().synchronize()
+        st = stream if stream is not None else torch.cuda.current_stream()
+        with torch.cuda.stream(st):
+            for t in tensors:
+                nbytes = t.numel() * t.element_size()
+                blk = _POOL.take(nbytes)
+                view = blk[:nbytes].view(t.dtype).view(t.shape)
+                view.copy_(t, non_blocking=True)
+                if stream is not None:
+                    t.record_stream(st)
+                views.append(view)
+                blocks.append(blk)
+    return views, blocks, st
+
+
+def _d2h_finish(pending) -> list:
+    """Wait for the copies and hand the pinned blocks to the caller as numpy arrays."""
+    import weakref
+
+    views, blocks, st = pending
+    st.synchronize()
     out = []
     for view, blk in zip(views, blocks):
         arr = view.numpy()
@@ -95,6 +137,11 @@ def _to_host(tensors) -> list:
         weakref.finalize(arr.base, _POOL.give, blk)
         out.append(arr)
     return out
+
+
+def _to_host(tensors) -> list:
+    """Device tensors -> numpy arrays owned by the caller, backed by recycled pinned blocks."""
+    return _d2h_finish(_d2h_start(tensors))
 
 
 def _sign_i8(t: torch.Tensor) -> torch.Tensor:
@@ -129,6 +176,7 @@ class RawGrid:
     check: bool = True
     _sd: object = None
     h2d_bytes: int = 0
+    nodes_ready: object = None  # event of the side-stream upload of `nodes` (only K1 reads the coordinates)
 
     @staticmethod
     def upload(sd, device=None, ridges: bool = False, signs: bool = False) -> "RawGrid":
@@ -145,10 +193,11 @@ class RawGrid:
         R = np.ascontiguousarray(getattr(sd, "rotation_matrix", np.eye(d, 3)), dtype=np.float64)
         nodes_h = np.asarray(sd.nodes, dtype=np.float64)
         with torch.cuda.device(dev):
+            cf_idx, fn_idx = _to_dev(cf.indices, dev, _I32), _to_dev(fn.indices, dev, _I32)
+            nodes_d, ev = _to_dev_side(nodes_h, dev)  # last, and off the main stream: pack / symbolic do not wait
             raw = RawGrid(
                 d, nc, nf, nn, nf if d == 2 else int(getattr(sd, "num_ridges", 0)), dev, R,
-                _to_dev(cf.indices, dev, _I32), None,
-                _to_dev(fn.indices, dev, _I32), _to_dev(nodes_h, dev), _sd=sd,
+                cf_idx, None, fn_idx, nodes_d, _sd=sd, nodes_ready=ev,
             )
         raw.h2d_bytes = cf.indices.nbytes + fn.indices.nbytes + nodes_h.nbytes
         if signs:
@@ -200,7 +249,7 @@ class GridPack:
     ne: int
     device: torch.device
     R: np.ndarray
-    coords: torch.Tensor
+    _coords: torch.Tensor | None  # filled on first use (K1): see `coords`
     cf_idx: torch.Tensor
     fn_idx: torch.Tensor
     cell_nodes: torch.Tensor
@@ -222,8 +271,6 @@ class GridPack:
         dev, d, nc, nf, nn = raw.device, raw.dim, raw.nc, raw.nf, raw.nn
         with torch.cuda.device(dev):
             s = _stream()
-            coords = torch.empty((nn, 4 if d == 3 else 2), dtype=torch.float64, device=dev)
-            check(lib.pgb_prep_coords(d, nn, raw.nodes.data_ptr(), raw.R.ctypes.data, coords.data_ptr(), s))
             cell_nodes = torch.empty((nc, d + 1), dtype=_I32, device=dev)
             sign_bits = None
             if raw.cf_sgn is not None:
@@ -235,11 +282,27 @@ class GridPack:
                     cell_nodes.data_ptr(), _ptr(sign_bits), err.data_ptr(), s,
                 )
             )
-            _lib.count(2)
+            _lib.count(1)
             if raw.check and int(err.item()):
                 raise NotImplementedError("Grid is not simplicial; cannot compute opposite node.")
-        return GridPack(d, nc, nf, nn, raw.ne, dev, raw.R, coords, raw.cf_idx, raw.fn_idx, cell_nodes,
+        return GridPack(d, nc, nf, nn, raw.ne, dev, raw.R, None, raw.cf_idx, raw.fn_idx, cell_nodes,
                         sign_bits, _raw=raw)
+
+    @property
+    def coords(self) -> torch.Tensor:
+        """Rotated node coordinates (nn, 4 | 2) fp64.  Only K1 reads them, so they are prepared on
+        first use: the upload of ``nodes`` (side stream) overlaps the packing and the symbolic phase."""
+        if self._coords is None:
+            raw, d = self._raw, self.dim
+            with torch.cuda.device(self.device):
+                if raw.nodes_ready is not None:
+                    torch.cuda.current_stream().wait_event(raw.nodes_ready)
+                coords = torch.empty((self.nn, 4 if d == 3 else 2), dtype=torch.float64, device=self.device)
+                check(lib.pgb_prep_coords(d, self.nn, raw.nodes.data_ptr(), raw.R.ctypes.data, coords.data_ptr(),
+                                          _stream()))
+                _lib.count(1)
+            self._coords = coords
+        return self._coords
 
     @property
     def sign_bits(self) -> torch.Tensor:
@@ -443,8 +506,10 @@ def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
         bits = max(1, int(n_rows - 1).bit_length()) if n_rows > 1 else 1
         if mode == 1:
             _lib.count(((2 * bits + 7) // 8) * 5 + 3)
-        else:
+        elif mode == 4:
             _lib.count(((bits + 7) // 8) * 5 + 7)
+        else:
+            _lib.count(12)  # count, 3 scan, max, place, (canon,) row sort|hash, 3 scan, compact (+memsets)
         del ws
     if mode == 1:
         plan = CsrPlan(n_rows, n_coo, nnz, L, 1, indptr, indices, perm=first, seg=seg)
@@ -511,10 +576,13 @@ def numeric(plan: CsrPlan, vals: torch.Tensor, out=None) -> torch.Tensor:
             check(lib.pgb_csr_numeric(plan.nnz, plan.perm.data_ptr(), plan.seg.data_ptr(), vals.data_ptr(),
                                       data.data_ptr(), _stream()))
         else:
+            # coalesced output through shared memory when the matrix has about as many entries as
+            # COO candidates (RT0, BDM1, N0, Darcy); not for P1 in 3D (6 candidates per entry)
+            staged = 1 if 3 * plan.nnz > plan.n_coo else 0
             check(lib.pgb_csr_numeric_rows(plan.n_rows, plan.L, plan.max_row_nnz, plan.row_start.data_ptr(),
                                            plan.slots.data_ptr(), plan.indptr.data_ptr(),
                                            1 if plan.indptr.dtype == torch.int64 else 0,
-                                           vals.data_ptr(), data.data_ptr(), _stream()))
+                                           vals.data_ptr(), data.data_ptr(), staged, _stream()))
         _lib.count(1)
     return data
 
@@ -543,9 +611,6 @@ def clear_cache(sd) -> None:
         delattr(sd, _CACHE_ATTR)
 
 
-_SIDE: dict = {}
-
-
 def assemble_on_pack(pack: GridPack, space: str, kind: str, wd=None, Kd=None):
     """symbolic (cached per pack) -> K1 (writing the local rows where the plan wants them) -> K2."""
     plan = symbolic(pack, space)
@@ -564,6 +629,33 @@ def assemble_device(space: str, form: str, sd, w=None, K=None, device=None) -> D
     plan, data = assemble_on_pack(pack, space, kind, wd, Kd)
     n = plan.n_rows
     return DeviceCSR((n, n), plan.indptr, plan.indices, data)
+
+
+def assemble_host(space: str, form: str, sd, w=None, K=None, device=None, fmt: str = "csc"):
+    """The public host-in / host-out call: upload, assemble, download, with the copies overlapped
+    where the data flow allows it: ``nodes`` goes up on a side stream while the grid is packed and
+    the pattern is built (only K1 reads coordinates); indptr / indices come down on the side stream
+    while K1 and the numeric phase run; the values follow on the main stream."""
+    pack = get_pack(sd, device)
+    dev = pack.device
+    kind = _FORMS[(space, form)]
+    cls = sps.csc_array if fmt == "csc" else sps.csr_array
+    with torch.cuda.device(dev):
+        wd = None if w is None else _to_dev(w, dev)
+        Kd = None if K is None else _to_dev(K, dev)
+        plan = symbolic(pack, space)  # ends with a stream synchronisation: the pattern is complete
+        n = plan.n_rows
+        if n == 0 or plan.nnz == 0:
+            return DeviceCSR((n, n), plan.indptr, plan.indices, numeric(plan, local_matrices(pack, kind, wd, Kd, plan=plan))).to_scipy(fmt)
+        side = _side_stream(dev) if overlap_download else None
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+        pat = _d2h_start([plan.indptr, plan.indices], side)
+        data = numeric(plan, local_matrices(pack, kind, wd, Kd, plan=plan))
+        val = _d2h_start([data])
+        ip, ix = _d2h_finish(pat)
+        (da,) = _d2h_finish(val)
+    return cls((da, ix, ip), shape=(n, n))
 
 
 def cell_volumes_inverse_weighted(sd, w=None, device=None) -> torch.Tensor:

@@ -167,6 +167,40 @@ def test_patch_mixed_darcy_linear_pressure():
     assert np.abs(u + sd.face_normals[0]).max() < 1e-7
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("space", ["RT0", "BDM1"])
+def test_patch_linear_distribution_reference_script(dim, space):
+    """The reference's patch test, statement by statement (tests/patch_tests/
+    test_laplacian_mixed.py:27-70): saddle system from assemble_mass_matrix / assemble_diff_matrix,
+    natural boundary data from assemble_nat_bc, exact fields from interpolate."""
+    sd = pg.structured_grid(dim, 4 if dim == 2 else 3)
+    sd.compute_geometry()
+    discr_q, discr_p = getattr(pg, space)("flow"), pg.PwConstants("flow")
+
+    def q_func(_):
+        return np.array([-1, 2, 1 if dim == 3 else 0])
+
+    def p_func(x):
+        return -x @ q_func(x)
+
+    face_mass = discr_q.assemble_mass_matrix(sd)
+    cell_mass = discr_p.assemble_mass_matrix(sd, None)
+    div = cell_mass @ discr_q.assemble_diff_matrix(sd)
+    spp = sps.block_array([[face_mass, -div.T], [div, None]]).tocsc()
+    b_faces = sd.tags["domain_boundary_faces"]
+    bc_val = -discr_q.assemble_nat_bc(sd, p_func, b_faces)
+    rhs = np.zeros(spp.shape[0])
+    rhs[: bc_val.size] += bc_val
+    x = pg.LinearSystem(spp, rhs).solve()  # scipy spsolve, the reference's default
+    q, p = x[: bc_val.size], x[-discr_p.ndof(sd):]
+    assert np.allclose(p, discr_p.interpolate(sd, p_func))
+    assert np.allclose(q, discr_q.interpolate(sd, q_func))
+    # the same system, symmetrised, through GPU MINRES
+    sym = sps.block_array([[face_mass, -div.T], [-div, None]]).tocsc()
+    xs, info = pg.minres(sym, rhs, rtol=1e-13, maxiter=50000)
+    assert info == 0 and np.abs(xs - x).max() < 1e-6 * np.abs(x).max()
+
+
 def test_linear_system_multi_rhs():
     """b with several columns (tests/numerics/test_linear_system.py:9-24)."""
     sd, ls = poisson_system(2, 10)

@@ -91,3 +91,33 @@ def test_reference_element_matches(ref, dim):
     assert np.array_equal(a.nodes, b.nodes)
     assert np.array_equal(a.face_nodes.indices, b.face_nodes.indices)
     assert np.array_equal(a.cell_faces.toarray(), b.cell_faces.toarray())
+
+
+@pytest.mark.parametrize("dim,n,pert", [(2, 5, 0.2), (3, 3, 0.2)])
+def test_vectors_match_reference(ref, dim, n, pert):
+    """interpolate / assemble_nat_bc (host-side vector assemblies around the path)
+    against the reference's per-face Python loops (fem/hdiv.py:194-241,373-436, fem/h1.py:255-302,
+    fem/l2.py:390-406, fem/hcurl.py:146-164)."""
+    import pygeon_b200 as pgb
+
+    pg, pp = ref
+    sd = structured_grid(dim, n, perturb=pert)
+    sd.compute_geometry()
+    g = ref_loader.ref_grid(sd)
+    scal = lambda x: 1.0 + x[0] - 2.0 * x[1] + 0.5 * x[2] + x[0] * x[1]  # noqa: E731
+    vec = lambda x: np.array([x[1] + 1.0, -x[0] * x[2], 0.3 + x[2] if dim == 3 else 0.0])  # noqa: E731
+    b_faces = sd.tags["domain_boundary_faces"]
+    assert np.array_equal(b_faces, g.tags["domain_boundary_faces"])
+    idx = np.where(b_faces)[0][::-1].copy()  # also an index array, in another order
+    for name, f_int in (("PwConstants", scal), ("Lagrange1", scal), ("RT0", vec), ("BDM1", vec), ("Nedelec0", vec)):
+        ours, theirs = getattr(pgb, name)("k"), getattr(pg, name)("k")
+        if name == "Nedelec0" and dim == 2:
+            continue  # the reference's interpolate reads ridge_peaks, which is empty in 2D (hcurl.py:160)
+        assert np.allclose(ours.interpolate(sd, f_int), theirs.interpolate(g, f_int), rtol=1e-14, atol=1e-15), name
+        if name == "Nedelec0":
+            with pytest.raises(NotImplementedError):
+                ours.assemble_nat_bc(sd, scal, b_faces)
+            continue
+        for bf in (b_faces, idx):
+            a, b = ours.assemble_nat_bc(sd, scal, bf), theirs.assemble_nat_bc(g, scal, bf)
+            assert a.shape == b.shape and np.allclose(a, b, rtol=1e-14, atol=1e-15), name

@@ -1,0 +1,133 @@
+"""COO -> CSR on random cell->dof tables: every row kernel of the two-level symbolic phase
+(k_rowthread, k_rowhash with 8/16/32 lanes per row, k_rowsort, k_row_canon) and the full-sort
+fallback against a scipy oracle, through engine.symbolic / engine.numeric (ctypes -> C ABI).
+
+The tables have no geometry: `L` distinct dofs per cell drawn from a sliding window (locality as in
+a mesh) plus one hub dof shared by exactly `hub` cells, which sets the largest incidence count and
+therefore the kernel that pgb_csr_symbolic_sort picks."""
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+pytestmark = pytest.mark.gpu
+
+
+class _Table:
+    """Stand-in for engine.GridPack: just the cell->dof table of one 'space'."""
+
+    def __init__(self, dofs, n_rows, device):
+        self._dofs, self._n, self.device, self.plans = dofs, n_rows, device, {}
+
+    def dofs(self, space):
+        return self._dofs, self._n
+
+
+def _random_table(L, nc, n_rows, hub, seed):
+    rng = np.random.default_rng(seed)
+    W = L + 6
+    off = np.argsort(rng.random((nc, W)), axis=1)[:, :L] + 1  # L distinct offsets in [1, W]
+    start = rng.integers(1, n_rows - W - 1, size=nc)
+    dofs = (start[:, None] + off).astype(np.int32)  # never dof 0
+    cells = rng.choice(nc, size=hub, replace=False)
+    # the hub: dof 0 in exactly `hub` cells, whose other dofs come from a small set (a row may have at
+    # most 255 distinct columns in the two-level path)
+    dofs[cells] = (rng.integers(1, 40, size=hub)[:, None] + off[cells]).astype(np.int32)
+    dofs[cells, rng.integers(0, L, size=hub)] = 0
+    return dofs
+
+
+def _oracle(dofs, n_rows, vals):
+    nc, L = dofs.shape
+    rows = np.repeat(dofs, L, axis=1).ravel()
+    cols = np.tile(dofs, (1, L)).ravel()
+    A = sps.coo_array((vals.ravel(), (rows, cols)), shape=(n_rows, n_rows)).tocsr()
+    A.sum_duplicates()
+    A.sort_indices()
+    return A
+
+
+CASES = [
+    # L, nc, n_rows, hub, row kernel expected in mode 0 (prefix of pgb_csr_last_row_kernel())
+    (3, 4000, 9000, 1, "k_rowthread<"),       # k_rowthread MI<=4
+    (3, 4000, 3000, 8, "k_rowthread<8,3,32"),
+    (3, 4001, 3000, 8, "k_rowthread<8,3,32"),   # nc*L not a multiple of 4: scalar tails of k_inc_count / k_inc_place
+    (5, 2999, 3100, 8, "k_rowthread<8,5,64"),
+    (3, 130, 131, 3, "k_rowthread<"),           # a single block, ragged last group       # k_rowthread MI=8
+    (3, 6000, 2500, 16, "k_rowthread<16,3,64"),      # k_rowthread MI=16, 48 keys
+    (3, 6000, 2500, 30, "k_rowhash<32,1,3,128>"),      # k_rowhash 32 lanes, table 128
+    (3, 6000, 2500, 80, "k_rowhash<32,4,3,512>"),      # k_rowhash 32 lanes x 4, table 512
+    (3, 6000, 2500, 150, "k_rowsort<32,16,3"),     # k_row_canon + k_rowsort (450 candidates)
+    (3, 6000, 2500, 200, ""),     # > 512 candidates: full-sort fallback
+    (4, 3000, 9000, 2, "k_rowthread<"),       # k_rowthread MI=2
+    (4, 3000, 4000, 4, "k_rowthread<"),
+    (4, 5000, 2500, 16, "k_rowthread<16,4,64"),      # k_rowthread MI=16, 64 keys
+    (4, 5000, 2500, 24, "k_rowhash<32,1,4,128>"),      # k_rowhash 32 lanes, table 128
+    (4, 5000, 2500, 32, "k_rowhash<32,1,4,512>"),      # table 512
+    (4, 5000, 2500, 60, "k_rowhash<32,4,4,512>"),      # 32 lanes x 4
+    (4, 5000, 2500, 100, "k_rowsort<32,16,4"),     # k_rowsort
+    (5, 3000, 9000, 2, "k_rowthread<"),
+    (5, 3000, 3000, 8, "k_rowthread<8,5,64"),       # k_rowthread MI=8, 40 of 64 keys
+    (5, 4000, 2500, 12, "k_rowhash<16,1,5,128>"),      # k_rowhash 16 lanes, table 128
+    (5, 4000, 2500, 30, "k_rowhash<32,1,5,512>"),      # 32 lanes, table 512
+    (5, 4000, 2500, 50, "k_rowhash<32,4,5,512>"),      # 32 lanes x 4
+    (6, 3000, 9000, 2, "k_rowthread<"),
+    (6, 3000, 3500, 8, "k_rowthread<8,6,64"),       # k_rowthread MI=8, 48 of 64 keys
+    (6, 4000, 3000, 16, "k_rowhash<16,1,6,128>"),      # k_rowhash 16 lanes, table 128
+    (6, 4000, 3000, 40, "k_rowhash<32,4,6,512>"),      # 32 lanes x 4, table 512
+    (12, 2000, 9000, 1, "k_rowthread<"),
+    (12, 2000, 9000, 2, "k_rowthread<"),      # k_rowthread MI=2 (BDM1 in 3D)
+    (12, 2000, 9000, 4, "k_rowthread<4,12,64"),      # 48 of 64 keys
+    (12, 3000, 9000, 7, "k_rowhash<8,1,12,128>"),      # k_rowhash 8 lanes, table 128
+    (12, 3000, 6000, 14, "k_rowhash<16,1,12,256>"),     # 16 lanes, table 256
+    (12, 3000, 6000, 20, "k_rowhash<32,1,12,512>"),     # 32 lanes, table 512
+]
+
+
+@pytest.mark.parametrize("L,nc,n_rows,hub,kernel", CASES)
+def test_random_tables_all_modes(L, nc, n_rows, hub, kernel):
+    import torch
+
+    from pygeon_b200 import _lib, engine
+
+    dev = torch.device("cuda", 0)
+    dofs = _random_table(L, nc, n_rows, hub, seed=L * 1000 + hub)
+    counts = np.bincount(dofs.ravel(), minlength=n_rows)
+    assert counts[0] == hub
+    rng = np.random.default_rng(7)
+    vals = rng.uniform(0.5, 1.5, size=(nc, L, L))
+    ref = _oracle(dofs, n_rows, vals)
+    dd = torch.from_numpy(dofs).to(dev)
+    vd = torch.from_numpy(vals).to(dev)
+    LP = (L + 3) & ~3
+    first = None
+    for it, mode in enumerate((0, 0, 3, 4, 2, 1)):
+        plan = engine.symbolic(_Table(dd, n_rows, dev), "t", mode=mode)
+        used = _lib.lib.pgb_csr_last_row_kernel().decode()
+        if it == 0 and counts.max() == hub:  # the hub decides
+            assert (used.startswith(kernel) and kernel) or (kernel == "" and plan.mode == 1), used
+        if mode == 3 and plan.mode == 0:
+            assert used.startswith("k_rowsort<"), used
+        assert np.array_equal(plan.indptr.cpu().numpy(), ref.indptr), (mode, plan.mode)
+        assert np.array_equal(plan.indices.cpu().numpy(), ref.indices), (mode, plan.mode)
+        if plan.mode == 0:
+            # the local rows where K1 would put them: row (c, a) at inc_pos[c*L + a]
+            vt = torch.zeros((nc * L, LP), dtype=torch.float64, device=dev)
+            vt[plan.inc_pos.long(), :L] = vd.reshape(nc * L, L)
+            data = engine.numeric(plan, vt.reshape(nc, L * LP))
+            state = (plan.inc_pos.clone(), plan.slots.clone(), plan.row_start.clone())
+            if first is None:
+                first = state
+            else:  # bit-identical plans whatever the kernel / the order of the integer atomics
+                assert all(torch.equal(a, b) for a, b in zip(first, state)), mode
+            inc = np.argsort(plan.inc_pos.cpu().numpy().astype(np.int64), kind="stable")
+            rows_sorted = dofs.ravel()[inc]
+            assert np.all(np.diff(rows_sorted) >= 0)  # (dof, cell) order ...
+            same = rows_sorted[1:] == rows_sorted[:-1]
+            assert np.all(np.diff(inc)[same] > 0)  # ... ascending incidence inside a row
+        else:
+            data = engine.numeric(plan, vd.reshape(nc, L * L).contiguous())
+        err = np.abs(data.cpu().numpy() - ref.data).max()
+        assert err <= 1e-13 * np.abs(ref.data).max(), (mode, err)
+    if hub * L <= 512 and hub <= 256 and np.diff(ref.indptr).max() <= 255:
+        assert first is not None  # the two-level path did run

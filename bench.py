@@ -173,6 +173,9 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from pygeon_b200 import dist as pgd
+
+    numa_cpus = pgd.bind_to_gpu_numa(local) if os.environ.get("PGB_BIND_NUMA", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     hbm_peak, peak_src = peaks()
@@ -181,8 +184,6 @@ def run_ours(args):
     # ---- synthetic grid: connectivity generated on the device, host copy in pinned memory -----
     # N>1: rank r owns n cube layers of the n x n x (n*N) box and also evaluates the halo layer
     # above them (redundant compute, no communication during assembly)
-    from pygeon_b200 import dist as pgd
-
     lay = pgd.slab_layout(n, n * world, world, rank)
     sd = pgd.local_slab_grid(lay, device=dev)
     keep = []
@@ -437,7 +438,8 @@ def run_ours(args):
                  "note": "symbolic plan reused (K1 + K2 numeric only)"},
         "solve": solve,
         "e2e": {"value": world * nc_owned / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                "host_cpus_bound": len(numa_cpus) if numa_cpus else None},
         "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks.summary(),
     }
     print(json.dumps(line))

@@ -27,6 +27,34 @@ import torch.distributed as dist
 from .grid import SimplexGrid, structured_grid
 
 
+def bind_to_gpu_numa(device_index: int) -> list[int] | None:
+    """Pin the calling process to the CPUs NVML reports as local to the GPU, so that the pinned host
+    buffers it allocates afterwards (grid arrays, result blocks) live on the GPU's NUMA node.  With
+    one process per GPU this keeps every rank's PCIe traffic off the inter-socket link.  Returns the
+    CPU list, or None when NVML / the affinity call is unavailable (nothing is changed then)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        cpus = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------
 # structured slab partition
 # --------------------------------------------------------------------------------------

@@ -109,7 +109,12 @@ enum {
                            broken-P1 mass eye/(d+1), l2.py:472-483): diag w|c|/(d+1)  L = d+1 */
   PGB_RT0_LUMPED = 12,  /* RT0.assemble_lumped_matrix (hdiv.py:140-175): diag sum_c (dist^T K dist)/|dist|
                            / |f|, dist = face centre - cell centre                   L = d+1 */
-  PGB_BDM1_LUMPED = 13  /* BDM1 lumped: w|c| delta_jl/(d+1) t_aj^T K t_bl            L = d(d+1) */
+  PGB_BDM1_LUMPED = 13, /* BDM1 lumped: w|c| delta_jl/(d+1) t_aj^T K t_bl            L = d(d+1) */
+  PGB_L2_MASS = 14,     /* Lagrange2 mass (h1.py:352-392 through discretization.py:112-136): w|c| (phi_i, phi_j),
+                           phi = lambda_i(2 lambda_i - 1) for the d+1 nodes, 4 lambda_p lambda_q for the edges
+                           (p,q) = (0,1),(0,2)[,(0,3)],(1,2)[,(1,3),(2,3)]              L = (d+1) + d(d+1)/2 */
+  PGB_L2_STIFF = 15     /* Lagrange2 stiffness (h1.py:545-599): |c| sum_jl Mhat_jl grad phi_i(x_j)^T K
+                           grad phi_k(x_l); pg.WEIGHT is not read (as the reference)   L = (d+1) + d(d+1)/2 */
 };
 int pgb_local_size(int kind, int dim); /* L */
 /* dst_pos (nullable): [nc*L] destination row of every local row (the inc_pos of a mode-0 plan);

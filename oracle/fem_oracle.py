@@ -514,7 +514,92 @@ def port_lumped(space: str, sd, data=None, keyword="unitary_data", tabs=None):
     return (Pi.T @ M @ Pi).tocsc()
 
 
+# ---- Lagrange2 (the reference's per-cell Python loop, fem/h1.py:545-599) ----
+def lagrange2_pairs(d):
+    """Local edge -> (p, q) slot pairs, ``Lagrange2.get_local_edge_nodes`` (fem/h1.py:449-469)."""
+    return [(p, q) for p in range(d + 1) for q in range(p + 1, d + 1)]
+
+
+def lagrange2_dofs(sd, tabs):
+    """Cell -> dof table (nc, (d+1) + d(d+1)/2): the nodes in slot order, then ``num_nodes`` + the
+    edge the reference attaches to the local pair (p, q) of ``lagrange2_pairs`` order
+    (``get_edge_dof_indices`` fem/h1.py:507-543): in 2D the face opposite the third slot
+    (``faces[::-1]``); in 3D a purely index-based rule - the cell's six ridge ids sorted ascending
+    and permuted by [5, 4, 2, 3, 1, 0] ("experimentally, we always find the following numbering").
+    On grids whose ridges are numbered lexicographically by their end nodes and whose opposite
+    nodes come in descending order (all structured grids) that is the ridge joining the two
+    nodes; elsewhere (e.g. ``reference_element(3)``) it is not, and parity means following the rule."""
+    d, opp = sd.dim, tabs["opp"]
+    if d == 2:
+        edges = tabs["faces"][:, ::-1]
+    else:
+        eid, _ = local_edges(sd, tabs)
+        edges = np.sort(eid, axis=1)[:, [5, 4, 2, 3, 1, 0]]
+    return np.hstack([opp, sd.num_nodes + edges]).astype(np.int64)
+
+
+def lagrange2_local_mass(d):
+    """(phi_i, phi_j) on a d-simplex of measure 1, phi = lambda_i(2 lambda_i - 1) | 4 lambda_p lambda_q
+    (``Lagrange2.assemble_local_mass`` fem/h1.py:352-392), from the monomial integrals
+    d! prod(alpha_k!) / (d + |alpha|)!  (fem/h1.py:418-436)."""
+    from math import factorial
+
+    pairs = lagrange2_pairs(d)
+    n, ne = d + 1, len(pairs)
+    # basis functions as {exponent tuple: coefficient}
+    def mono(*idx):
+        a = [0] * n
+        for i in idx:
+            a[i] += 1
+        return tuple(a)
+
+    basis = [{mono(i, i): 2.0, mono(i): -1.0} for i in range(n)] + [{mono(p, q): 4.0} for p, q in pairs]
+
+    def integ(a):
+        return factorial(d) * np.prod([factorial(k) for k in a]) / factorial(d + sum(a))
+
+    M = np.zeros((n + ne, n + ne))
+    for i, bi in enumerate(basis):
+        for j, bj in enumerate(basis):
+            M[i, j] = sum(ci * cj * integ(tuple(x + y for x, y in zip(ai, aj))) for ai, ci in bi.items() for aj, cj in bj.items())
+    return M
+
+
+def local_lagrange2_mass(sd, tabs, w, K):
+    _, vol, _ = local_geometry(sd, tabs)
+    return (w * vol)[:, None, None] * lagrange2_local_mass(sd.dim)[None], lagrange2_dofs(sd, tabs)
+
+
+def local_lagrange2_stiff(sd, tabs, w, K):
+    """|c| sum_{j,l} Mhat_jl grad phi_i(x_j)^T K grad phi_k(x_l) with the P1 mass Mhat of the nodal
+    values of the (linear) gradients; grad phi_i(x_j) = (4 delta_ij - 1) g_i for a node,
+    4 (delta_jp g_q + delta_jq g_p) for the edge (p, q) (fem/h1.py:471-505, 545-599).  The
+    reference does not read pg.WEIGHT here."""
+    d = sd.dim
+    _, vol, G = local_geometry(sd, tabs)
+    # entry (i, k) = Psi_i^T K Psi_k with K itself (h1.py:585-587), unlike the projection-based
+    # spaces whose contraction produces K^T (rotated_tensor)
+    R = np.asarray(getattr(sd, "rotation_matrix", np.eye(d, 3)), dtype=float)
+    Kr = np.einsum("ia,abc,jb->cij", R, K, R)
+    pairs = lagrange2_pairs(d)
+    n, ne = d + 1, len(pairs)
+    nc = sd.num_cells
+    # nodal values of the gradients: Psi (nc, n+ne, n nodes, d)
+    Psi = np.zeros((nc, n + ne, n, d))
+    for i in range(n):
+        for j in range(n):
+            Psi[:, i, j, :] = (4.0 * (i == j) - 1.0) * G[:, i, :]
+    for e, (p_, q_) in enumerate(pairs):
+        Psi[:, n + e, p_, :] = 4.0 * G[:, q_, :]
+        Psi[:, n + e, q_, :] = 4.0 * G[:, p_, :]
+    mhat = (np.ones((n, n)) + np.eye(n)) / ((d + 1) * (d + 2))
+    A = np.einsum("jl,cijx,cxy,ckly->cik", mhat, Psi, Kr, Psi) * vol[:, None, None]
+    return A, lagrange2_dofs(sd, tabs)
+
+
 _LOCAL = {
+    ("lagrange2", "mass"): local_lagrange2_mass,
+    ("lagrange2", "stiff"): local_lagrange2_stiff,
     ("lagrange1", "lumped"): local_lagrange1_lumped,
     ("rt0", "lumped"): local_rt0_lumped,
     ("bdm1", "lumped"): local_bdm1_lumped,
@@ -533,6 +618,7 @@ NDOF = {
     "rt0": lambda sd: sd.num_faces,
     "bdm1": lambda sd: sd.dim * sd.num_faces,
     "nedelec0": lambda sd: sd.num_edges,
+    "lagrange2": lambda sd: sd.num_nodes + sd.num_edges,
 }
 
 

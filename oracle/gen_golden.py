@@ -40,6 +40,7 @@ FORMS = [
     ("rt0", "mass"), ("rt0", "stiff"), ("bdm1", "mass"), ("bdm1", "stiff"),
     ("nedelec0", "mass"), ("nedelec0", "stiff"),
     ("lagrange1", "lumped"), ("rt0", "lumped"), ("bdm1", "lumped"),
+    ("lagrange2", "mass"), ("lagrange2", "stiff"),
 ]
 
 
@@ -59,7 +60,8 @@ def main():
     pg, pp = ref_loader.load()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    cls = {"lagrange1": pg.Lagrange1, "rt0": pg.RT0, "bdm1": pg.BDM1, "nedelec0": pg.Nedelec0}
+    cls = {"lagrange1": pg.Lagrange1, "rt0": pg.RT0, "bdm1": pg.BDM1, "nedelec0": pg.Nedelec0,
+           "lagrange2": pg.Lagrange2}
     for name, dim, n, pert, mode in CASES:
         sd = reference_element(dim) if n == 0 else structured_grid(dim, n, perturb=pert, seed=1)
         sd.compute_geometry()

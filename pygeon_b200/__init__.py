@@ -15,7 +15,7 @@ from .params import SecondOrderTensor, get_cell_data, initialize_data
 
 def __getattr__(name):
     # lazy: these pull in libpgb.so
-    if name in ("Discretization", "Lagrange1", "RT0", "BDM1", "Nedelec0", "PwConstants"):
+    if name in ("Discretization", "Lagrange1", "Lagrange2", "RT0", "BDM1", "Nedelec0", "PwConstants"):
         from . import discretization as _d
 
         return getattr(_d, name)

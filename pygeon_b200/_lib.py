@@ -86,6 +86,8 @@ KIND = {
     "l1_lumped": 11,
     "rt0_lumped": 12,
     "bdm1_lumped": 13,
+    "l2_mass": 14,
+    "l2_stiff": 15,
 }
 NPART = 1184
 

@@ -194,12 +194,48 @@ __device__ __forceinline__ void pair3(int e, int& p, int& q) {
   q = Q[e];
 }
 
+// local edge e of a D-simplex joins slots (p, q): (0,1),(0,2)[,(0,3)],(1,2)[,(1,3),(2,3)]
+template <int D>
+__device__ __forceinline__ void pair_of(int e, int& p, int& q) {
+  if constexpr (D == 3) {
+    pair3(e, p, q);
+  } else {
+    constexpr int P[3] = {0, 0, 1};
+    constexpr int Q[3] = {1, 2, 2};
+    p = P[e];
+    q = Q[e];
+  }
+}
+
+// (phi_i, phi_j) of the P2 basis on a D-simplex of measure 1 (Lagrange2.assemble_local_mass,
+// h1.py:352-392): nodes first, then the edges in pair_of order
+template <int D>
+__device__ __forceinline__ double l2_mass_entry(int i, int j) {
+  constexpr int N = D + 1;
+  constexpr double nn_diag = (D == 2) ? 1.0 / 30 : 1.0 / 70, nn_off = (D == 2) ? -1.0 / 180 : 1.0 / 420;
+  constexpr double ne_adj = (D == 2) ? 0.0 : -1.0 / 105, ne_opp = (D == 2) ? -1.0 / 45 : -1.0 / 70;
+  constexpr double ee_diag = (D == 2) ? 8.0 / 45 : 8.0 / 105, ee_share = (D == 2) ? 4.0 / 45 : 4.0 / 105;
+  constexpr double ee_disj = 2.0 / 105;
+  if (i < N && j < N) return i == j ? nn_diag : nn_off;
+  if (i < N || j < N) {
+    int node = i < N ? i : j, p, q;
+    pair_of<D>((i < N ? j : i) - N, p, q);
+    return (node == p || node == q) ? ne_adj : ne_opp;
+  }
+  int p, q, r, s;
+  pair_of<D>(i - N, p, q);
+  pair_of<D>(j - N, r, s);
+  int common = (p == r) + (p == s) + (q == r) + (q == s);
+  return common == 2 ? ee_diag : common == 1 ? ee_share : ee_disj;
+}
+
 template <int KIND, int D>
 struct LocalSize {
   static constexpr int L = (KIND == PGB_BDM1_MASS || KIND == PGB_BDM1_DIVDIV || KIND == PGB_BDM1_LUMPED) ? D * (D + 1)
                            : (KIND == PGB_N0_MASS || KIND == PGB_N0_CURLCURL) ? D * (D + 1) / 2
                            : (KIND == PGB_P0_MASS)                            ? 1
                            : (KIND == PGB_DARCY_SADDLE)                       ? D + 2
+                           : (KIND == PGB_L2_MASS || KIND == PGB_L2_STIFF)    ? (D + 1) + D * (D + 1) / 2
                                                                               : D + 1;
 };
 
@@ -370,6 +406,54 @@ __global__ void __launch_bounds__(BLOCK) k_local(Params p) {
       for (int a = 0; a <= D; ++a)
 #pragma unroll
         for (int b = 0; b <= D; ++b) emit(a * L + b, wv * dotd<D>(Gv[a], KG[b]));
+    } else if constexpr (KIND == PGB_L2_MASS) {
+      double wv = w * g.vol;
+#pragma unroll
+      for (int i = 0; i < L; ++i)
+#pragma unroll
+        for (int j = 0; j < L; ++j) emit(i * L + j, wv * l2_mass_entry<D>(i, j));
+    } else if constexpr (KIND == PGB_L2_STIFF) {
+      // The gradients of the P2 basis are linear; their nodal values are combinations of the
+      // grad lambda, integrated with the P1 mass Mhat.  The reference's entry (i, k) is
+      // Psi_i^T K Psi_k; the CSR built here is handed to scipy as CSC, i.e. it must hold the
+      // transpose: the formulas below are evaluated with Gm[a][b] = grad lambda_b^T K grad lambda_a.
+      constexpr int N = D + 1;
+      double Gv[N][D], KG[N][D], Gm[N][N];
+#pragma unroll
+      for (int a = 0; a < N; ++a)
+#pragma unroll
+        for (int i = 0; i < D; ++i) Gv[a][i] = g.G[a][i];
+      apply_tensor<D, N, HAS_K>(Kr, Gv, KG);
+#pragma unroll
+      for (int a = 0; a < N; ++a)
+#pragma unroll
+        for (int b = 0; b < N; ++b) Gm[a][b] = g.vol * dotd<D>(Gv[b], KG[a]);
+      constexpr double c1 = 1.0 / N;
+#pragma unroll
+      for (int i = 0; i < L; ++i) {
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+          double v;
+          if (i < N && k < N) {
+            v = Gm[i][k] * (16.0 * mhat<D>(i, k) - 8.0 * c1 + 1.0);
+          } else if (i < N) {
+            int r, s;
+            pair_of<D>(k - N, r, s);
+            v = 4.0 * (Gm[i][s] * (4.0 * mhat<D>(i, r) - c1) + Gm[i][r] * (4.0 * mhat<D>(i, s) - c1));
+          } else if (k < N) {
+            int p_, q_;
+            pair_of<D>(i - N, p_, q_);
+            v = 4.0 * (Gm[q_][k] * (4.0 * mhat<D>(p_, k) - c1) + Gm[p_][k] * (4.0 * mhat<D>(q_, k) - c1));
+          } else {
+            int p_, q_, r, s;
+            pair_of<D>(i - N, p_, q_);
+            pair_of<D>(k - N, r, s);
+            v = 16.0 * (mhat<D>(p_, r) * Gm[q_][s] + mhat<D>(p_, s) * Gm[q_][r] + mhat<D>(q_, r) * Gm[p_][s] +
+                        mhat<D>(q_, s) * Gm[p_][r]);
+          }
+          emit(i * L + k, v);
+        }
+      }
     } else if constexpr (KIND == PGB_RT0_MASS) {
       double A[D + 1][D + 1];
       rt0_local<D, HAS_K>(g, Kr, p.sign_bits[c], w, A);
@@ -507,6 +591,8 @@ int dispatch(int kind, const Params& p, cudaStream_t s) {
     case PGB_L1_LUMPED: return launch<PGB_L1_LUMPED, D>(p, s);
     case PGB_RT0_LUMPED: return launch<PGB_RT0_LUMPED, D>(p, s);
     case PGB_BDM1_LUMPED: return launch<PGB_BDM1_LUMPED, D>(p, s);
+    case PGB_L2_MASS: return launch<PGB_L2_MASS, D>(p, s);
+    case PGB_L2_STIFF: return launch<PGB_L2_STIFF, D>(p, s);
   }
   pgb_set_error("pgb_local_matrices: unknown kind %d", kind);
   return 2;
@@ -523,6 +609,8 @@ extern "C" int pgb_local_size(int kind, int dim) {
     case PGB_N0_CURLCURL: return dim * (dim + 1) / 2;
     case PGB_P0_MASS: return 1;
     case PGB_DARCY_SADDLE: return dim + 2;
+    case PGB_L2_MASS:
+    case PGB_L2_STIFF: return (dim + 1) + dim * (dim + 1) / 2;
     default: return dim + 1;
   }
 }

@@ -177,6 +177,7 @@ int launch_rowhash_l(int L, int64_t n_rows, const uint32_t* row_start, const uin
     case 4: PGB_RH(4); break;
     case 5: PGB_RH(5); break;
     case 6: PGB_RH(6); break;
+    case 10: PGB_RH(10); break;
     case 12: PGB_RH(12); break;
     default: pgb_set_error("k_rowhash: unsupported local size %d", L); return 2;
   }

@@ -136,6 +136,7 @@ int launch_rowsort_l(int L, int64_t n_rows, const uint32_t* row_start, const uin
     case 4: PGB_RL(4); break;
     case 5: PGB_RL(5); break;
     case 6: PGB_RL(6); break;
+    case 10: PGB_RL(10); break;
     case 12: PGB_RL(12); break;
     default: pgb_set_error("k_rowsort: unsupported local size %d", L); return 2;
   }

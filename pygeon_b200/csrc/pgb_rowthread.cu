@@ -181,6 +181,7 @@ int launch_rowthread(uint32_t max_inc, int L, int64_t n_rows, const uint32_t* ro
   PGB_RT(1, 4, 8);  PGB_RT(2, 4, 8);  PGB_RT(4, 4, 16); PGB_RT(8, 4, 32); PGB_RT(16, 4, 64);
   PGB_RT(1, 5, 8);  PGB_RT(2, 5, 16); PGB_RT(4, 5, 32); PGB_RT(8, 5, 64);
   PGB_RT(1, 6, 8);  PGB_RT(2, 6, 16); PGB_RT(4, 6, 32); PGB_RT(8, 6, 64);
+  PGB_RT(1, 10, 16); PGB_RT(2, 10, 32); PGB_RT(4, 10, 64);
   PGB_RT(1, 12, 16); PGB_RT(2, 12, 32); PGB_RT(4, 12, 64);
 #undef PGB_RT
   pgb_set_error("k_rowthread: unsupported local size %d / %u incidences", L, max_inc);

@@ -244,6 +244,60 @@ class Lagrange1(Discretization):
                 raise NotImplementedError("There's no zero discretization in PyGeoN")
 
 
+class Lagrange2(Discretization):
+    """``fem/h1.py:326-800``: quadratic Lagrange elements, one dof per node and per edge
+    (edge dofs numbered ``num_nodes + edge id``).  The reference assembles the stiffness matrix in a
+    Python loop over the cells (``fem/h1.py:545-599``); here it goes through the same K1/K2 engine
+    as the lowest-order spaces (kinds ``PGB_L2_MASS`` / ``PGB_L2_STIFF``)."""
+
+    poly_order = 2
+    tensor_order = SCALAR
+    _space = "lagrange2"
+
+    def ndof(self, sd) -> int:
+        return sd.num_nodes + sd.num_edges
+
+    def assemble_stiff_matrix_device(self, sd, data: dict | None = None) -> engine.DeviceCSR:
+        _, K = self._coefficients(sd, data)
+        return engine.assemble_device(self._space, "stiff", sd, None, K)  # pg.WEIGHT is not read (h1.py:560-562)
+
+    def assemble_stiff_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
+        """``(K grad u, grad v)`` (``fem/h1.py:545-599``)."""
+        _, K = self._coefficients(sd, data)
+        return engine.assemble_host(self._space, "stiff", sd, None, K)
+
+    def assemble_diff_matrix(self, sd) -> sps.csc_array:
+        """Gradient into Nedelec1 (two dofs per edge), ``fem/h1.py:601-674`` (2D and 3D)."""
+        match sd.dim:
+            case 2:
+                edge_nodes, num_edges, second = sd.face_ridges, sd.num_faces, 1
+            case 3:
+                edge_nodes, num_edges, second = sd.ridge_peaks, sd.num_ridges, -1
+            case _:
+                raise ValueError("Dimension must be 2 or 3.")
+        edge_nodes = sps.csc_array(edge_nodes).astype(float)
+        d0 = edge_nodes.copy().T
+        d0.data[edge_nodes.data == -1] = -3
+        d0.data[edge_nodes.data == 1] = -1
+        diff_0 = sps.hstack((d0, 4 * sps.eye_array(num_edges)))
+        d1 = edge_nodes.copy().T
+        d1.data[edge_nodes.data == 1] = 3
+        d1.data[edge_nodes.data == -1] = 1
+        diff_1 = second * sps.hstack((d1, -4 * sps.eye_array(num_edges)))
+        return sps.vstack((diff_0, diff_1)).tocsc()
+
+    def interpolate(self, sd, func) -> np.ndarray:
+        """Values at the nodes, then at the edge midpoints (``fem/h1.py:722-753``)."""
+        if sd.dim == 2:
+            edge_coords = sd.face_centers
+        else:
+            edge_coords = sd.nodes @ abs(sd.ridge_peaks.astype(float)) / 2
+        return np.array(_eval_points(func, np.hstack((sd.nodes, edge_coords))))
+
+    def get_range_discr_class(self, dim: int):
+        raise NotImplementedError("Nedelec1 (the range of Lagrange2) is not part of this package")
+
+
 class RT0(Discretization):
     """``fem/hdiv.py:13-274``: one dof per face."""
 

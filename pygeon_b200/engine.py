@@ -258,6 +258,7 @@ class GridPack:
     _edges: tuple | None = None
     _bdm1: tuple | None = None
     _darcy: object = None
+    _l2: object = None
     plans: dict = field(default_factory=dict)
 
     @staticmethod
@@ -369,6 +370,14 @@ class GridPack:
             return self.edges()[0], self.ne
         if space == "bdm1":
             return self.bdm1()[0], d * self.nf
+        if space == "lagrange2":  # nodes in slot order, then num_nodes + edge (p, q), pairs in lexicographic order
+            if self._l2 is None:
+                if d == 2:  # edge (0,1),(0,2),(1,2) = the face opposite slot 2, 1, 0 (fem/h1.py:524-527)
+                    edges = self.cf_idx.view(self.nc, 3).flip(1)
+                else:  # the reference's index rule: sorted ridge ids of the cell, permuted (fem/h1.py:529-540)
+                    edges = torch.sort(self.edges()[0], dim=1).values[:, [5, 4, 2, 3, 1, 0]]
+                self._l2 = torch.cat([self.cell_nodes, edges + self.nn], dim=1).contiguous()
+            return self._l2, self.nn + self.ne
         if space == "darcy":  # RT0 x P0: faces of the cell, then num_faces + cell
             if self._darcy is None:
                 cells = torch.arange(self.nc, dtype=_I32, device=self.device) + self.nf
@@ -533,6 +542,8 @@ _FORMS = {
     ("bdm1", "stiff"): "bdm1_divdiv",
     ("darcy", "saddle"): "darcy_saddle",
     ("lagrange1", "lumped"): "l1_lumped",
+    ("lagrange2", "mass"): "l2_mass",
+    ("lagrange2", "stiff"): "l2_stiff",
     ("rt0", "lumped"): "rt0_lumped",
     ("bdm1", "lumped"): "bdm1_lumped",
 }

@@ -15,8 +15,8 @@ dev = torch.device("cuda", 0)
 sd = pg.structured_grid(3, n, device=dev)
 sd.compute_connectivity()
 for space, kind in (("lagrange1", "l1_stiff"), ("rt0", "rt0_mass"), ("nedelec0", "n0_mass"), ("bdm1", "bdm1_mass"),
-                    ("darcy", "darcy_saddle")):
-    raw = engine.RawGrid.upload(sd, dev, ridges=(space == "nedelec0"))
+                    ("darcy", "darcy_saddle"), ("lagrange2", "l2_stiff")):
+    raw = engine.RawGrid.upload(sd, dev, ridges=(space in ("nedelec0", "lagrange2")))
     raw.check = False
     cold, warm = [], []
     ph = np.zeros(4)

@@ -79,6 +79,10 @@ def test_oracle_matches_reference(ref, dim, n, pert, mode, which_grid):
               fo.closed_form(space, "stiff", G, data, "k", tabs))
     check(pg.Lagrange1("k").assemble_grad_grad_matrix(g, data), None,
           fo.closed_form("lagrange1", "stiff", G, data, "k", tabs, rot2d=False))
+    # Lagrange2: the reference loops over the cells in Python (h1.py:545-599)
+    for form in ("mass", "stiff"):
+        refm = getattr(pg.Lagrange2("k"), f"assemble_{form}_matrix")(g, data)
+        check(refm, None, fo.closed_form("lagrange2", form, G, data, "k", tabs))
     d0 = pg.PwConstants("k").assemble_mass_matrix(g, data).diagonal()
     assert np.allclose(fo.p0_mass(G, data, "k").diagonal(), d0, rtol=1e-14)
 
@@ -109,6 +113,10 @@ def test_vectors_match_reference(ref, dim, n, pert):
     b_faces = sd.tags["domain_boundary_faces"]
     assert np.array_equal(b_faces, g.tags["domain_boundary_faces"])
     idx = np.where(b_faces)[0][::-1].copy()  # also an index array, in another order
+    l2o, l2r = pgb.Lagrange2("k"), pg.Lagrange2("k")
+    assert l2o.ndof(sd) == l2r.ndof(g)
+    assert np.allclose(l2o.interpolate(sd, scal), l2r.interpolate(g, scal), rtol=1e-14, atol=1e-15)
+    assert abs(l2o.assemble_diff_matrix(sd) - l2r.assemble_diff_matrix(g)).max() == 0
     for name, f_int in (("PwConstants", scal), ("Lagrange1", scal), ("RT0", vec), ("BDM1", vec), ("Nedelec0", vec)):
         ours, theirs = getattr(pgb, name)("k"), getattr(pg, name)("k")
         if name == "Nedelec0" and dim == 2:

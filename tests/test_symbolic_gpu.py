@@ -75,6 +75,8 @@ CASES = [
     (6, 3000, 3500, 8, "k_rowthread<8,6,64"),       # k_rowthread MI=8, 48 of 64 keys
     (6, 4000, 3000, 16, "k_rowhash<16,1,6,128>"),      # k_rowhash 16 lanes, table 128
     (6, 4000, 3000, 40, "k_rowhash<32,4,6,512>"),      # 32 lanes x 4, table 512
+    (10, 2000, 9000, 2, "k_rowthread<"),        # Lagrange2 in 3D: edge rows ...
+    (10, 3000, 6000, 24, "k_rowhash<32,1,10,512>"),  # ... and node rows (240 candidates)
     (12, 2000, 9000, 1, "k_rowthread<"),
     (12, 2000, 9000, 2, "k_rowthread<"),      # k_rowthread MI=2 (BDM1 in 3D)
     (12, 2000, 9000, 4, "k_rowthread<4,12,64"),      # 48 of 64 keys

@@ -74,6 +74,11 @@ int pgb_pack_edges3d(int64_t nc, const int32_t* cf_idx, const int32_t* fr_idx,
 int pgb_pack_edges2d(int64_t nc, const int32_t* cf_idx, const int32_t* fr_idx,
                      const int32_t* cell_nodes, uint32_t* edge_bits, void* stream);
 
+/* Lagrange2 cell -> dof table [nc][(d+1) + d(d+1)/2]: nodes in slot order, then nn + the edge ids in
+ * the order of Lagrange2.get_edge_dof_indices (fem/h1.py:507-543).  cell_edges: [nc][3] face ids (2D,
+ * = cell_faces indices) or [nc][6] ridge ids of the cell in any order (3D, from pgb_pack_edges3d). */
+int pgb_pack_l2_dofs(int dim, int64_t nc, int64_t nn, const int32_t* cell_nodes,
+                     const int32_t* cell_edges, int32_t* dofs, void* stream);
 /* coords[nn][4] (3D, padded) or [nn][2] (2D) = R @ nodes, nodes given as (3, nn) row-major
  * (sd.nodes), R = sd.rotation_matrix (d x 3, host pointer). */
 int pgb_prep_coords(int dim, int64_t nn, const double* nodes, const double* R_host,

@@ -960,7 +960,16 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     uint32_t max_inc = 0;
     uint32_t* chunk_max_d = (uint32_t*)(ws + l.chunk);
     const int64_t n_chunks = pgb_cdiv(n_rows, CHUNK_ROWS);
-    std::vector<uint32_t> chunk_max((size_t)n_chunks);
+    // pinned staging for the two small device->host reads of this call (a pageable target costs an
+    // extra internal synchronisation)
+    static uint32_t* h_pin = nullptr;
+    static int64_t h_pin_cap = 0;
+    if (n_chunks + 1 > h_pin_cap) {
+      if (h_pin) cudaFreeHost(h_pin);
+      h_pin_cap = n_chunks + 1 + 1024;
+      PGB_CHECK(cudaMallocHost(&h_pin, sizeof(uint32_t) * h_pin_cap));
+    }
+    uint32_t* chunk_max = h_pin;
     const uint32_t* inc_rows = pbuf[0];
     const bool radix = (mode == MODE_TWO_LEVEL_RADIX);
     uint8_t* rank = (uint8_t*)kbuf[0];
@@ -978,9 +987,10 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     }
     k_chunk_max<<<(unsigned)n_chunks, 256, 0, s>>>(n_rows, row_start, chunk_max_d, meta + 3);
     PGB_LAUNCH_CHECK();
-    PGB_CHECK(cudaMemcpyAsync(&max_inc, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    PGB_CHECK(cudaMemcpyAsync(chunk_max.data(), chunk_max_d, sizeof(uint32_t) * n_chunks, cudaMemcpyDeviceToHost, s));
+    PGB_CHECK(cudaMemcpyAsync(h_pin + n_chunks, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PGB_CHECK(cudaMemcpyAsync(chunk_max, chunk_max_d, sizeof(uint32_t) * n_chunks, cudaMemcpyDeviceToHost, s));
     PGB_CHECK(cudaStreamSynchronize(s));
+    max_inc = h_pin[n_chunks];
     if (!radix) pt.mark();
     if (max_inc * (uint32_t)L > MAX_ROW_CAND || max_inc > 256u) {
       pgb_set_error("pgb_csr_symbolic_sort: a dof is shared by %u cells (> %u candidates per row or > 256 "
@@ -999,7 +1009,7 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     std::vector<RowRange>& rg = g_ranges;
     rg.clear();
     for (int64_t i = 0; i < n_chunks; ++i) {
-      const uint32_t m = chunk_max[(size_t)i] ? chunk_max[(size_t)i] : 1u;
+      const uint32_t m = chunk_max[i] ? chunk_max[i] : 1u;
       const int64_t r0 = i * CHUNK_ROWS, r1 = r0 + CHUNK_ROWS < n_rows ? r0 + CHUNK_ROWS : n_rows;
       if (!rg.empty() && rg.back().kind == kind_of(m) && bucket(rg.back().max_inc) == bucket(m)) {
         rg.back().r1 = r1;

@@ -54,7 +54,7 @@ __device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint
 // G lanes per row (256/G rows per block), NPL incidences per lane (row capacity G*NPL incidences),
 // table of HS entries per row (at most 3/4 full)
 template <int G, int NPL, int L, int HS>
-__global__ void __launch_bounds__(256, (NPL == 1 && L <= 6) ? ((256 / G) * HS * 9 <= 20000 ? 8 : 5) : 1)
+__global__ void __launch_bounds__(256, (NPL == 1 && L <= 6) ? ((256 / G) * HS * 9 <= 20000 ? 8 : 5) : (NPL == 1 ? 5 : 1))
 k_rowhash(int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ inc_tmp,
           const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos, uint8_t* __restrict__ slots,
           int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz, uint32_t* __restrict__ max_nnz) {

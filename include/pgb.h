@@ -74,6 +74,11 @@ int pgb_pack_edges3d(int64_t nc, const int32_t* cf_idx, const int32_t* fr_idx,
 int pgb_pack_edges2d(int64_t nc, const int32_t* cf_idx, const int32_t* fr_idx,
                      const int32_t* cell_nodes, uint32_t* edge_bits, void* stream);
 
+/* Lagrange2 cell -> dof table [nc][(d+1) + d(d+1)/2]: nodes in slot order, then nn + the edge ids in
+ * the order of Lagrange2.get_edge_dof_indices (fem/h1.py:507-543).  cell_edges: [nc][3] face ids (2D,
+ * = cell_faces indices) or [nc][6] ridge ids of the cell in any order (3D, from pgb_pack_edges3d). */
+int pgb_pack_l2_dofs(int dim, int64_t nc, int64_t nn, const int32_t* cell_nodes,
+                     const int32_t* cell_edges, int32_t* dofs, void* stream);
 /* coords[nn][4] (3D, padded) or [nn][2] (2D) = R @ nodes, nodes given as (3, nn) row-major
  * (sd.nodes), R = sd.rotation_matrix (d x 3, host pointer). */
 int pgb_prep_coords(int dim, int64_t nn, const double* nodes, const double* R_host,
@@ -141,7 +146,8 @@ int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
  *     (2) per row: gather the candidate columns of the incident cells, find the sorted distinct
  *     columns and record for every candidate the index of its column inside the row
  *     (slots, uint8, slots[(row_start[r] + q)*LP + b], LP = L rounded up to a multiple of 4).
- *     Three kernels, picked from the largest incidence / candidate count of a row: one thread per
+ *     Three kernels, picked per range of 4096-row chunks from the largest incidence / candidate
+ *     count of a row in the range (a few long rows do not slow the others down): one thread per
  *     row with a register sorting network (<= 16 incidences, <= 64 candidates), a group of 8..32
  *     lanes per row with a shared-memory hash dedupe (<= 256 candidates), a sub-warp bitonic sort
  *     of all candidates (<= 512).  (3) a scan of the row counts and a compaction.
@@ -155,7 +161,8 @@ int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
  * symbolic_sort: workspace of pgb_csr_workspace_bytes(nc, L, n_rows, mode) bytes.
  *   perm_or_inc: perm (mode 1) or inc_pos (mode 0).  nnz_host / max_row_nnz_host are returned
  *   after a stream synchronisation.
- * symbolic_finish: indptr (int32 if idx64==0 else int64) [n_rows+1], indices [nnz]; mode 1 also
+ * symbolic_finish: must be the next call after symbolic_sort on the same workspace (it reads the
+ *   row ranges chosen there).  indptr (int32 if idx64==0 else int64) [n_rows+1], indices [nnz]; mode 1 also
  *   seg [nnz+1] (start of each entry's run in perm).
  * numeric_rows (mode 0 plans): K1 has written every local row to its row-sorted position
  *   (pgb_local_matrices with dst_pos = inc_pos), so a CSR row owns a contiguous block of vals_t;
@@ -172,9 +179,9 @@ int64_t pgb_csr_workspace_bytes(int64_t nc, int L, int64_t n_rows, int mode);
  * [2] per-row kernel, [3] scan of the row counts. */
 void pgb_set_profile(int on);
 void pgb_get_phase_ms(double* out, int n);
-/* Name of the per-row kernel the last two-level pgb_csr_symbolic_sort launched, e.g.
- * "k_rowthread<2,4,8,u32>" (template arguments as in the source); "" before the first call or
- * after a mode-1 call.  For tests and profiles. */
+/* Names of the per-row kernels the last two-level pgb_csr_symbolic_sort launched, joined by '+',
+ * e.g. "k_rowhash<32,1,10,512>+k_rowthread<8,10,64,u32>" (template arguments as in the source);
+ * "" before the first call or after a mode-1 call.  For tests and profiles. */
 const char* pgb_csr_last_row_kernel(void);
 int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell_dofs, int mode,
                           void* workspace, int64_t workspace_bytes, uint32_t* perm_or_inc,

@@ -25,6 +25,7 @@ _SIGS = {
     "pgb_version": (_i, []),
     "pgb_last_error": (C.c_char_p, []),
     "pgb_csr_last_row_kernel": (C.c_char_p, []),
+    "pgb_pack_l2_dofs": (_i, [_i, _l, _l, _p, _p, _p, _p]),
     "pgb_set_l2_fetch_granularity": (_i, [_i]),
     "pgb_get_l2_fetch_granularity": (_i, []),
     "pgb_pack_cells": (_i, [_i, _l, _p, _p, _p, _p, _p, _p, _p]),

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "pgb.h"
 
 void pgb_set_error(const char* fmt, ...);

@@ -15,6 +15,8 @@
 #include "pgb_common.cuh"
 #include "pgb_rows.cuh"
 
+#include <vector>
+
 using namespace pgb_rows;
 
 namespace {
@@ -343,6 +345,30 @@ __global__ void __launch_bounds__(256) k_max_row(int64_t n_rows, const uint32_t*
   }
 }
 
+// largest incidence count of every chunk of CHUNK_ROWS rows (and of the matrix): the row kernel is
+// chosen per range of chunks, so that a few long rows do not put every row on the slow kernel
+constexpr int CHUNK_ROWS = 4096;  // multiple of ROWTHREAD_GROUP and of the rows per block of every row kernel
+__global__ void __launch_bounds__(256) k_chunk_max(int64_t n_rows, const uint32_t* __restrict__ row_start,
+                                                   uint32_t* __restrict__ chunk_max, uint32_t* __restrict__ max_count) {
+  __shared__ uint32_t ws[8];
+  const int64_t r0 = (int64_t)blockIdx.x * CHUNK_ROWS;
+  const int64_t r1 = r0 + CHUNK_ROWS < n_rows ? r0 + CHUNK_ROWS : n_rows;
+  uint32_t mx = 0;
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) {
+    uint32_t c = row_start[r + 1] - row_start[r];
+    mx = c > mx ? c : mx;
+  }
+  mx = __reduce_max_sync(FULL, mx);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) ws[w] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; ++q) mx = ws[q] > mx ? ws[q] : mx;
+    chunk_max[blockIdx.x] = mx;
+    atomicMax(max_count, mx);
+  }
+}
+
 // ---- incidence transpose by counting (default) ---------------------------------------------------
 // (1) k_inc_count: cnt[dof] += 1 for every incidence; the value the integer atomic returns is kept
 //     as a provisional rank inside the row (it depends on the execution order, the counts do not).
@@ -391,11 +417,11 @@ __global__ void __launch_bounds__(256) k_inc_place(uint32_t n_inc, const int32_t
 
 // G lanes per row, NPL incidences per lane (capacity G*NPL)
 template <int G, int NPL>
-__global__ void __launch_bounds__(256) k_row_canon(int64_t n_rows, const uint32_t* __restrict__ row_start,
+__global__ void __launch_bounds__(256) k_row_canon(int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start,
                                                    const uint32_t* __restrict__ inc_tmp,
                                                    uint32_t* __restrict__ inc_sorted, uint32_t* __restrict__ inc_pos) {
   const int gl = threadIdx.x & (G - 1);
-  const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
+  const int64_t r = row0 + ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;  // rows [row0, n_rows)
   uint32_t rs = 0, cnt = 0;
   if (r < n_rows) {
     rs = row_start[r];
@@ -420,42 +446,37 @@ __global__ void __launch_bounds__(256) k_row_canon(int64_t n_rows, const uint32_
 
 // row_nnz has been exclusively scanned in place (row_off): copy each row's unique columns from
 // their scratch position to the final CSR arrays.
+// Rows [row0, row1) whose distinct columns sit at ucol_tmp[row_start[r]*L ...) (k_rowsort / k_rowhash).
+// The range that ends the matrix also writes indptr[n_rows].
 template <typename IP>
-__global__ void __launch_bounds__(256) k_compact(int64_t n_rows, int L, const uint32_t* __restrict__ row_start,
+__global__ void __launch_bounds__(256) k_compact(int64_t row0, int64_t row1, int64_t n_rows, int L,
+                                                 const uint32_t* __restrict__ row_start,
                                                  const uint32_t* __restrict__ row_off,
-                                                 const int32_t* __restrict__ ucol_tmp, const uint32_t* __restrict__ meta,
-                                                 IP* __restrict__ indptr, int32_t* __restrict__ indices) {
+                                                 const int32_t* __restrict__ ucol_tmp, IP* __restrict__ indptr,
+                                                 int32_t* __restrict__ indices) {
   // 8 lanes per row
   const int gl = threadIdx.x & 7;
-  const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
-  if (r > n_rows) return;
+  const int64_t r = row0 + (((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3);
+  if (r > row1 || (r == row1 && row1 != n_rows)) return;
   uint32_t o0 = row_off[r];
   if (gl == 0) indptr[r] = (IP)o0;
   if (r == n_rows) return;
   uint32_t cnt = row_off[r + 1] - o0;
-  // scratch position of the row's columns: per row (k_rowsort / k_rowhash), or back to back inside
-  // groups of meta[5] rows (k_rowthread)
-  const uint32_t grp = meta[5];
-  uint64_t base;
-  if (grp) {
-    const int64_t first = r - r % (int64_t)grp;
-    base = (uint64_t)row_start[first] * (uint32_t)L + (o0 - row_off[first]);
-  } else {
-    base = (uint64_t)row_start[r] * (uint32_t)L;
-  }
+  const uint64_t base = (uint64_t)row_start[r] * (uint32_t)L;
   for (uint32_t k = gl; k < cnt; k += 8) indices[o0 + k] = ucol_tmp[base + k];
 }
 
-// scratch written by k_rowthread: the distinct columns of every group of `grp` consecutive rows are
-// already back to back, so the compaction is one contiguous copy per group
+// Rows [row0, row1) written by k_rowthread (row0 a multiple of the group size): the distinct columns
+// of every group of `grp` consecutive rows are already back to back, so the compaction is one
+// contiguous copy per group.
 template <typename IP>
-__global__ void __launch_bounds__(256) k_compact_groups(int64_t n_rows, int L, uint32_t grp,
+__global__ void __launch_bounds__(256) k_compact_groups(int64_t row0, int64_t row1, int64_t n_rows, int L, uint32_t grp,
                                                         const uint32_t* __restrict__ row_start,
                                                         const uint32_t* __restrict__ row_off,
                                                         const int32_t* __restrict__ ucol_tmp, IP* __restrict__ indptr,
                                                         int32_t* __restrict__ indices) {
-  const int64_t first = (int64_t)blockIdx.x * grp;
-  const int64_t last = first + grp < n_rows ? first + grp : n_rows;
+  const int64_t first = row0 + (int64_t)blockIdx.x * grp;
+  const int64_t last = first + grp < row1 ? first + grp : row1;
   const uint64_t src0 = (uint64_t)row_start[first] * (uint32_t)L;
   const uint32_t dst0 = row_off[first];
   const uint32_t len = row_off[last] - dst0;
@@ -770,6 +791,16 @@ struct PhaseTimer {
   }
 };
 
+// row ranges of the last two-level symbolic_sort and the kernel family each got; symbolic_finish
+// (called next, with the same workspace) compacts every range according to its scratch layout
+struct RowRange {
+  int64_t r0, r1;
+  uint32_t max_inc;
+  int kind;  // 0 k_rowthread (grouped scratch), 1 k_rowhash, 2 k_rowsort (one scratch segment per row)
+};
+std::vector<RowRange> g_ranges;
+const void* g_ranges_ws = nullptr;
+
 constexpr int MODE_TWO_LEVEL = 0, MODE_FULL_SORT = 1, MODE_TWO_LEVEL_KEY64 = 2, MODE_TWO_LEVEL_RADIX = 4;
 constexpr uint32_t MAX_ROW_CAND = 512;  // capacity of the largest k_rowsort instance
 
@@ -777,7 +808,7 @@ struct WsLayout {
   // full sort
   int64_t keys_a, keys_b, perm_b;
   // two level
-  int64_t ikeys_a, ikeys_b, ipay_a, ipay_b, row_nnz, ucol;
+  int64_t ikeys_a, ikeys_b, ipay_a, ipay_b, row_nnz, ucol, chunk;
   // shared
   int64_t hist, parts, meta, total;
 };
@@ -803,6 +834,7 @@ WsLayout ws_layout(int64_t n_coo, int64_t n_inc, int64_t n_rows, int mode) {
     l.ipay_b = o;    o += al(n_inc * 4);
     l.row_nnz = o;   o += al((n_rows + 2) * 4);
     l.ucol = o;      o += al(n_coo * 4);
+    l.chunk = o;     o += al((n_rows / CHUNK_ROWS + 2) * 4);
   }
   l.total = o;
   return l;
@@ -926,65 +958,115 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     PhaseTimer pt(s);
     pt.mark();
     uint32_t max_inc = 0;
+    uint32_t* chunk_max_d = (uint32_t*)(ws + l.chunk);
+    const int64_t n_chunks = pgb_cdiv(n_rows, CHUNK_ROWS);
+    // pinned staging for the two small device->host reads of this call (a pageable target costs an
+    // extra internal synchronisation)
+    static uint32_t* h_pin = nullptr;
+    static int64_t h_pin_cap = 0;
+    if (n_chunks + 1 > h_pin_cap) {
+      if (h_pin) cudaFreeHost(h_pin);
+      h_pin_cap = n_chunks + 1 + 1024;
+      PGB_CHECK(cudaMallocHost(&h_pin, sizeof(uint32_t) * h_pin_cap));
+    }
+    uint32_t* chunk_max = h_pin;
     const uint32_t* inc_rows = pbuf[0];
-    if (mode == MODE_TWO_LEVEL_RADIX) {
+    const bool radix = (mode == MODE_TWO_LEVEL_RADIX);
+    uint8_t* rank = (uint8_t*)kbuf[0];
+    if (radix) {
       if (radix_sort<uint32_t>(src, (uint32_t)n_inc, cb, kbuf, pbuf, hist, parts, s)) return 1;
       pt.mark();
       k_inc_pos<<<pgb_grid(n_inc, 256), 256, 0, s>>>((uint32_t)n_inc, pbuf[0], perm_or_inc);  // inverse permutation
       k_row_starts<<<pgb_grid(n_inc, 256), 256, 0, s>>>(kbuf[0], (uint32_t)n_inc, n_rows, row_start);
-      k_max_row<<<(unsigned)(n_rows < 256 * 1184 ? pgb_grid(n_rows, 256) : 1184), 256, 0, s>>>(n_rows, row_start, meta + 3);
-      PGB_LAUNCH_CHECK();
-      PGB_CHECK(cudaMemcpyAsync(&max_inc, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-      PGB_CHECK(cudaStreamSynchronize(s));
     } else {
       // counting transpose: counts -> row_start, provisional ranks in kbuf[0] (bytes)
-      uint8_t* rank = (uint8_t*)kbuf[0];
       PGB_CHECK(cudaMemsetAsync(row_start, 0, sizeof(uint32_t) * (n_rows + 1), s));
       k_inc_count<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank);
       PGB_LAUNCH_CHECK();
       if (scan_u32(row_start, (uint64_t)n_rows + 1, parts, nullptr, s)) return 1;
-      k_max_row<<<(unsigned)(n_rows < 256 * 1184 ? pgb_grid(n_rows, 256) : 1184), 256, 0, s>>>(n_rows, row_start, meta + 3);
-      PGB_LAUNCH_CHECK();
-      PGB_CHECK(cudaMemcpyAsync(&max_inc, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-      PGB_CHECK(cudaStreamSynchronize(s));
-      pt.mark();
-      if (max_inc <= 256u && max_inc * (uint32_t)L <= MAX_ROW_CAND) {
-        k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, pbuf[1]);
-        inc_rows = pbuf[1];  // row blocks, each in arbitrary order
-        if (!rowhash_applies(max_inc, max_inc * (uint32_t)L) &&
-            !rowthread_applies(max_inc, max_inc * (uint32_t)L)) {  // those kernels sort the row blocks themselves
-#define PGB_RC(G, N) k_row_canon<G, N><<<pgb_grid(n_rows * G, 256), 256, 0, s>>>(n_rows, row_start, pbuf[1], pbuf[0], perm_or_inc)
-          if (max_inc <= 4) PGB_RC(4, 1);
-          else if (max_inc <= 8) PGB_RC(8, 1);
-          else if (max_inc <= 16) PGB_RC(16, 1);
-          else if (max_inc <= 32) PGB_RC(32, 1);
-          else if (max_inc <= 64) PGB_RC(32, 2);
-          else if (max_inc <= 128) PGB_RC(32, 4);
-          else PGB_RC(32, 8);
-#undef PGB_RC
-          inc_rows = pbuf[0];
-        }
-        PGB_LAUNCH_CHECK();
-      }
     }
+    k_chunk_max<<<(unsigned)n_chunks, 256, 0, s>>>(n_rows, row_start, chunk_max_d, meta + 3);
+    PGB_LAUNCH_CHECK();
+    PGB_CHECK(cudaMemcpyAsync(h_pin + n_chunks, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PGB_CHECK(cudaMemcpyAsync(chunk_max, chunk_max_d, sizeof(uint32_t) * n_chunks, cudaMemcpyDeviceToHost, s));
+    PGB_CHECK(cudaStreamSynchronize(s));
+    max_inc = h_pin[n_chunks];
+    if (!radix) pt.mark();
     if (max_inc * (uint32_t)L > MAX_ROW_CAND || max_inc > 256u) {
       pgb_set_error("pgb_csr_symbolic_sort: a dof is shared by %u cells (> %u candidates per row or > 256 "
                     "cells); use mode 1 (full sort)", max_inc, MAX_ROW_CAND);
       return 3;
     }
+    // ranges of chunks that get the same row kernel
+    auto kind_of = [&](uint32_t m) {
+      return rowthread_applies(m, m * (uint32_t)L) ? 0 : rowhash_applies(m, m * (uint32_t)L) ? 1 : 2;
+    };
+    auto bucket = [](uint32_t m) {
+      uint32_t b = 1;
+      while (b < m) b <<= 1;
+      return b;
+    };
+    std::vector<RowRange>& rg = g_ranges;
+    rg.clear();
+    for (int64_t i = 0; i < n_chunks; ++i) {
+      const uint32_t m = chunk_max[i] ? chunk_max[i] : 1u;
+      const int64_t r0 = i * CHUNK_ROWS, r1 = r0 + CHUNK_ROWS < n_rows ? r0 + CHUNK_ROWS : n_rows;
+      if (!rg.empty() && rg.back().kind == kind_of(m) && bucket(rg.back().max_inc) == bucket(m)) {
+        rg.back().r1 = r1;
+        rg.back().max_inc = m > rg.back().max_inc ? m : rg.back().max_inc;
+      } else {
+        rg.push_back({r0, r1, m, kind_of(m)});
+      }
+    }
+    while (rg.size() > 64) {  // many alternations (scattered long rows): coarsen
+      std::vector<RowRange> c;
+      for (size_t i = 0; i < rg.size(); i += 2) {
+        RowRange x = rg[i];
+        if (i + 1 < rg.size()) {
+          x.r1 = rg[i + 1].r1;
+          x.max_inc = rg[i + 1].max_inc > x.max_inc ? rg[i + 1].max_inc : x.max_inc;
+        }
+        x.kind = kind_of(x.max_inc);
+        c.push_back(x);
+      }
+      rg.swap(c);
+    }
+    g_ranges_ws = workspace;
+    if (!radix) {
+      k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, pbuf[1]);
+      PGB_LAUNCH_CHECK();
+      inc_rows = pbuf[1];  // row blocks, each in arbitrary order
+      for (const RowRange& x : rg) {
+        if (x.kind != 2) continue;  // k_rowthread / k_rowhash sort the row blocks themselves
+        const int64_t nr = x.r1 - x.r0;
+        const uint32_t mi = x.max_inc;
+#define PGB_RC(G, N) k_row_canon<G, N><<<pgb_grid(nr * G, 256), 256, 0, s>>>(x.r0, x.r1, row_start, pbuf[1], pbuf[0], perm_or_inc)
+        if (mi <= 4) PGB_RC(4, 1);
+        else if (mi <= 8) PGB_RC(8, 1);
+        else if (mi <= 16) PGB_RC(16, 1);
+        else if (mi <= 32) PGB_RC(32, 1);
+        else if (mi <= 64) PGB_RC(32, 2);
+        else if (mi <= 128) PGB_RC(32, 4);
+        else PGB_RC(32, 8);
+#undef PGB_RC
+        PGB_LAUNCH_CHECK();
+      }
+    }
     PGB_CHECK(cudaMemsetAsync(row_nnz + n_rows, 0, 2 * sizeof(uint32_t), s));
     pt.mark();
-    if (rowthread_applies(max_inc, max_inc * (uint32_t)L)) {
-      if (launch_rowthread(max_inc, L, n_rows, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
-                           (int32_t*)(ws + l.ucol), row_nnz, meta + 4, meta + 5, s))
-        return 1;
-    } else if (rowhash_applies(max_inc, max_inc * (uint32_t)L)) {
-      if (launch_rowhash(max_inc, max_inc * (uint32_t)L, L, n_rows, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
-                         (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s))
-        return 1;
-    } else if (launch_rowsort(max_inc * (uint32_t)L, L, n_rows, row_start, inc_rows, cell_dofs, slots,
-                              (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s)) {
-      return 1;
+    for (const RowRange& x : rg) {
+      const uint32_t mi = x.max_inc, mc = x.max_inc * (uint32_t)L;
+      int rc;
+      if (x.kind == 0)
+        rc = launch_rowthread(mi, L, x.r0, x.r1, n_rows, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
+                              (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s);
+      else if (x.kind == 1)
+        rc = launch_rowhash(mi, mc, L, x.r0, x.r1, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
+                            (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s);
+      else
+        rc = launch_rowsort(mc, L, x.r0, x.r1, n_rows, row_start, pbuf[0], cell_dofs, slots, (int32_t*)(ws + l.ucol),
+                            row_nnz, meta + 4, s);
+      if (rc) return rc;
     }
     pt.mark();
     if (scan_u32(row_nnz, (uint64_t)n_rows + 1, parts, nullptr, s)) return 1;
@@ -1033,22 +1115,25 @@ extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mo
     PGB_REQUIRE(row_start, "pgb_csr_symbolic_finish: row_start required in two-level mode");
     const uint32_t* row_off = (const uint32_t*)(ws + l.row_nnz);
     const int32_t* ucol = (const int32_t*)(ws + l.ucol);
-    const uint32_t* meta = (const uint32_t*)(ws + l.meta);
-    uint32_t grp = 0;  // layout of the scratch: meta[5] rows per group (k_rowthread) or one segment per row
-    PGB_CHECK(cudaMemcpyAsync(&grp, meta + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    PGB_CHECK(cudaStreamSynchronize(s));
-    if (grp) {
-      unsigned grid = (unsigned)pgb_cdiv(n_rows, (int64_t)grp);
-      if (idx64)
-        k_compact_groups<int64_t><<<grid, 256, 0, s>>>(n_rows, L, grp, row_start, row_off, ucol, (int64_t*)indptr, indices);
-      else
-        k_compact_groups<int32_t><<<grid, 256, 0, s>>>(n_rows, L, grp, row_start, row_off, ucol, (int32_t*)indptr, indices);
-    } else {
-      unsigned grid = pgb_grid((n_rows + 1) * 8, 256);
-      if (idx64)
-        k_compact<int64_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, meta, (int64_t*)indptr, indices);
-      else
-        k_compact<int32_t><<<grid, 256, 0, s>>>(n_rows, L, row_start, row_off, ucol, meta, (int32_t*)indptr, indices);
+    PGB_REQUIRE(g_ranges_ws == workspace && !g_ranges.empty(),
+                "pgb_csr_symbolic_finish: must follow pgb_csr_symbolic_sort on the same workspace");
+    for (const RowRange& x : g_ranges) {
+      if (x.kind == 0) {
+        unsigned grid = (unsigned)pgb_cdiv(x.r1 - x.r0, (int64_t)ROWTHREAD_GROUP);
+        if (idx64)
+          k_compact_groups<int64_t><<<grid, 256, 0, s>>>(x.r0, x.r1, n_rows, L, ROWTHREAD_GROUP, row_start, row_off, ucol,
+                                                        (int64_t*)indptr, indices);
+        else
+          k_compact_groups<int32_t><<<grid, 256, 0, s>>>(x.r0, x.r1, n_rows, L, ROWTHREAD_GROUP, row_start, row_off, ucol,
+                                                        (int32_t*)indptr, indices);
+      } else {
+        unsigned grid = pgb_grid((x.r1 - x.r0 + 1) * 8, 256);
+        if (idx64)
+          k_compact<int64_t><<<grid, 256, 0, s>>>(x.r0, x.r1, n_rows, L, row_start, row_off, ucol, (int64_t*)indptr, indices);
+        else
+          k_compact<int32_t><<<grid, 256, 0, s>>>(x.r0, x.r1, n_rows, L, row_start, row_off, ucol, (int32_t*)indptr, indices);
+      }
+      PGB_LAUNCH_CHECK();
     }
   }
   PGB_LAUNCH_CHECK();

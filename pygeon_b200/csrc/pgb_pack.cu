@@ -276,6 +276,54 @@ extern "C" int pgb_pack_edges2d(int64_t nc, const int32_t* cf_idx, const int32_t
   return 0;
 }
 
+// Lagrange2 cell -> dof table: the cell's nodes in slot order, then num_nodes + the edge the
+// reference attaches to the local pair (p, q) (Lagrange2.get_edge_dof_indices, fem/h1.py:507-543):
+// 2D: the faces in reverse slot order; 3D: the six ridge ids sorted ascending, permuted [5,4,2,3,1,0].
+template <int D>
+__global__ void __launch_bounds__(256) k_pack_l2_dofs(int64_t nc, int32_t nn, const int32_t* __restrict__ cell_nodes,
+                                                      const int32_t* __restrict__ cell_edges,
+                                                      int32_t* __restrict__ dofs) {
+  constexpr int N = D + 1, E = D * (D + 1) / 2, L = N + E;
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  int32_t e[E];
+#pragma unroll
+  for (int k = 0; k < E; ++k) e[k] = cell_edges[c * E + k];
+  int32_t out[E];
+  if constexpr (D == 2) {
+    out[0] = e[2], out[1] = e[1], out[2] = e[0];
+  } else {
+    // sorting network for 6 keys (12 compare-exchanges)
+#define PGB_CE(i, j)              \
+  {                               \
+    int32_t lo = min(e[i], e[j]); \
+    int32_t hi = max(e[i], e[j]); \
+    e[i] = lo, e[j] = hi;         \
+  }
+    PGB_CE(0, 5) PGB_CE(1, 3) PGB_CE(2, 4) PGB_CE(1, 2) PGB_CE(3, 4) PGB_CE(0, 3) PGB_CE(2, 5) PGB_CE(0, 1)
+    PGB_CE(2, 3) PGB_CE(4, 5) PGB_CE(1, 2) PGB_CE(3, 4)
+#undef PGB_CE
+    out[0] = e[5], out[1] = e[4], out[2] = e[2], out[3] = e[3], out[4] = e[1], out[5] = e[0];
+  }
+#pragma unroll
+  for (int a = 0; a < N; ++a) dofs[c * L + a] = cell_nodes[c * N + a];
+#pragma unroll
+  for (int k = 0; k < E; ++k) dofs[c * L + N + k] = nn + out[k];
+}
+
+extern "C" int pgb_pack_l2_dofs(int dim, int64_t nc, int64_t nn, const int32_t* cell_nodes,
+                                const int32_t* cell_edges, int32_t* dofs, void* stream) {
+  PGB_REQUIRE(dim == 2 || dim == 3, "pgb_pack_l2_dofs: dim must be 2 or 3");
+  if (nc == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dim == 3)
+    k_pack_l2_dofs<3><<<pgb_grid(nc, 256), 256, 0, s>>>(nc, (int32_t)nn, cell_nodes, cell_edges, dofs);
+  else
+    k_pack_l2_dofs<2><<<pgb_grid(nc, 256), 256, 0, s>>>(nc, (int32_t)nn, cell_nodes, cell_edges, dofs);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int pgb_prep_coords(int dim, int64_t nn, const double* nodes, const double* R_host,
                                double* coords, void* stream) {
   PGB_REQUIRE(dim == 2 || dim == 3, "pgb_prep_coords: dim must be 2 or 3");

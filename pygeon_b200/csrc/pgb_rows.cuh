@@ -7,8 +7,9 @@ namespace pgb_rows {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-// name of the row kernel launched last (pgb_csr_last_row_kernel)
-extern char g_row_kernel[64];
+// names of the row kernels the last symbolic_sort launched, joined by '+' (pgb_csr_last_row_kernel)
+extern char g_row_kernel[256];
+void note_row_kernel(const char* name);
 
 // test switches (pgb_csr_symbolic_sort modes 2 and 3)
 extern bool g_force_key64;    // 64-bit (col, position) keys in the row sorts
@@ -123,18 +124,21 @@ __device__ __forceinline__ void load_dofs(const int32_t* __restrict__ p, uint32_
 
 
 // k_rowsort: bitonic sort of all candidates of a row by a sub-warp (pgb_rowsort.cu)
-int launch_rowsort(uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc,
-                   const int32_t* dofs, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
-                   cudaStream_t s);
+// All launchers work on the row range [row0, row1) (row0 a multiple of 128); n_rows = size of the
+// matrix (decides the key width).
+int launch_rowsort(uint32_t max_cand, int L, int64_t row0, int64_t row1, int64_t n_rows, const uint32_t* row_start,
+                   const uint32_t* inc, const int32_t* dofs, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz,
+                   uint32_t* max_nnz, cudaStream_t s);
 // k_rowthread: one thread per short row, register sorting network (pgb_rowthread.cu)
 bool rowthread_applies(uint32_t max_inc, uint32_t max_cand);
-int launch_rowthread(uint32_t max_inc, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp,
-                     const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz,
-                     uint32_t* max_nnz, uint32_t* meta_grp, cudaStream_t s);
+constexpr int ROWTHREAD_GROUP = 128;  // rows whose distinct columns k_rowthread stores back to back
+int launch_rowthread(uint32_t max_inc, int L, int64_t row0, int64_t row1, int64_t n_rows, const uint32_t* row_start,
+                     const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
+                     uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s);
 // k_rowhash: shared-memory hash dedupe by a group of lanes per row (pgb_rowhash.cu)
 bool rowhash_applies(uint32_t max_inc, uint32_t max_cand);
-int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, int64_t n_rows, const uint32_t* row_start,
-                   const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
+int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, int64_t row0, int64_t row1,
+                   const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
                    uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s);
 
 }  // namespace pgb_rows

@@ -44,11 +44,11 @@ __device__ __forceinline__ void reg_bitonic(KeyT (&a)[N]) {
 // this layout through meta[5]), the slot bytes to their final place.
 template <int N>
 struct RowThreadBlock {
-  static constexpr int value = N <= 64 ? 128 : 64;
+  static constexpr int value = 128;
 };
 
 template <int MI, int L, int N, typename KeyT>
-__global__ void __launch_bounds__(RowThreadBlock<N>::value) k_rowthread(int64_t n_rows, const uint32_t* __restrict__ row_start,
+__global__ void __launch_bounds__(RowThreadBlock<N>::value) k_rowthread(int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start,
                                                                const uint32_t* __restrict__ inc_tmp,
                                                                const int32_t* __restrict__ dofs,
                                                                uint32_t* __restrict__ inc_pos, uint8_t* __restrict__ slots,
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(RowThreadBlock<N>::value) k_rowthread(int64_t 
   __shared__ __align__(16) uint8_t s_sl[B * MI * LP];
   __shared__ uint32_t s_w[B / 32], s_m[B / 32], s_rs0;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int64_t r = (int64_t)blockIdx.x * B + tid;
+  const int64_t r = row0 + (int64_t)blockIdx.x * B + tid;  // rows [row0, n_rows), row0 a multiple of B
   uint32_t rs = 0, cnt = 0;
   if (r < n_rows) {
     rs = row_start[r];
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(RowThreadBlock<N>::value) k_rowthread(int64_t 
   if (r < n_rows) row_nnz[r] = total;
   __syncthreads();
   // coalesced write-out
-  const int64_t r_end = ((int64_t)blockIdx.x + 1) * B < n_rows ? ((int64_t)blockIdx.x + 1) * B : n_rows;
+  const int64_t r_end = row0 + ((int64_t)blockIdx.x + 1) * B < n_rows ? row0 + ((int64_t)blockIdx.x + 1) * B : n_rows;
   const uint32_t ninc = row_start[r_end] - rs0;
   for (uint32_t j = tid; j < btotal; j += B) ucol_tmp[(uint64_t)rs0 * L + j] = (int32_t)s_u[j];
   uint32_t* sl_out = reinterpret_cast<uint32_t*>(slots + (uint64_t)rs0 * LP);
@@ -139,19 +139,20 @@ __global__ void __launch_bounds__(RowThreadBlock<N>::value) k_rowthread(int64_t 
 }
 
 template <int MI, int L, int N>
-int launch_rowthread_k(int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs,
+int launch_rowthread_k(int64_t row0, int64_t row1, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs,
                        uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
-                       uint32_t* meta_grp, cudaStream_t s) {
+                       cudaStream_t s) {
   constexpr int B = RowThreadBlock<N>::value;
-  const uint32_t grp = B;  // k_compact: the unique columns are stored back to back in groups of B rows
-  PGB_CHECK(cudaMemcpyAsync(meta_grp, &grp, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-  unsigned grid = (unsigned)pgb_cdiv(n_rows, B);
+  static_assert(B == ROWTHREAD_GROUP, "k_compact_groups expects groups of ROWTHREAD_GROUP rows");
+  unsigned grid = (unsigned)pgb_cdiv(row1 - row0, B);
   const bool k32 = (uint64_t)n_rows * (uint64_t)N <= 0xffffffffull && !g_force_key64;
-  snprintf(g_row_kernel, sizeof(g_row_kernel), "k_rowthread<%d,%d,%d,%s>", MI, L, N, k32 ? "u32" : "u64");
+  char name[64];
+  snprintf(name, sizeof(name), "k_rowthread<%d,%d,%d,%s>", MI, L, N, k32 ? "u32" : "u64");
+  note_row_kernel(name);
   if (k32)
-    k_rowthread<MI, L, N, uint32_t><<<grid, B, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz);
+    k_rowthread<MI, L, N, uint32_t><<<grid, B, 0, s>>>(row0, row1, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz);
   else
-    k_rowthread<MI, L, N, uint64_t><<<grid, B, 0, s>>>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz);
+    k_rowthread<MI, L, N, uint64_t><<<grid, B, 0, s>>>(row0, row1, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz);
   PGB_LAUNCH_CHECK();
   return 0;
 }
@@ -170,13 +171,13 @@ bool rowthread_applies(uint32_t max_inc, uint32_t max_cand) {
   return mi * (max_cand / max_inc) <= 64;
 }
 
-int launch_rowthread(uint32_t max_inc, int L, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp,
+int launch_rowthread(uint32_t max_inc, int L, int64_t row0, int64_t row1, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp,
                      const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz,
-                     uint32_t* max_nnz, uint32_t* meta_grp, cudaStream_t s) {
+                     uint32_t* max_nnz, cudaStream_t s) {
   const int mi = max_inc <= 1 ? 1 : max_inc <= 2 ? 2 : max_inc <= 4 ? 4 : max_inc <= 8 ? 8 : 16;
 #define PGB_RT(MI, LL, N) \
   if (L == LL && mi == MI)  \
-    return launch_rowthread_k<MI, LL, N>(n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, meta_grp, s)
+    return launch_rowthread_k<MI, LL, N>(row0, row1, n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, s)
   PGB_RT(1, 3, 8);  PGB_RT(2, 3, 8);  PGB_RT(4, 3, 16); PGB_RT(8, 3, 32); PGB_RT(16, 3, 64);
   PGB_RT(1, 4, 8);  PGB_RT(2, 4, 8);  PGB_RT(4, 4, 16); PGB_RT(8, 4, 32); PGB_RT(16, 4, 64);
   PGB_RT(1, 5, 8);  PGB_RT(2, 5, 16); PGB_RT(4, 5, 32); PGB_RT(8, 5, 64);

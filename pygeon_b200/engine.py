@@ -372,11 +372,14 @@ class GridPack:
             return self.bdm1()[0], d * self.nf
         if space == "lagrange2":  # nodes in slot order, then num_nodes + edge (p, q), pairs in lexicographic order
             if self._l2 is None:
-                if d == 2:  # edge (0,1),(0,2),(1,2) = the face opposite slot 2, 1, 0 (fem/h1.py:524-527)
-                    edges = self.cf_idx.view(self.nc, 3).flip(1)
-                else:  # the reference's index rule: sorted ridge ids of the cell, permuted (fem/h1.py:529-540)
-                    edges = torch.sort(self.edges()[0], dim=1).values[:, [5, 4, 2, 3, 1, 0]]
-                self._l2 = torch.cat([self.cell_nodes, edges + self.nn], dim=1).contiguous()
+                ce = self.cf_idx if d == 2 else self.edges()[0]
+                with torch.cuda.device(self.device):
+                    L = (d + 1) + d * (d + 1) // 2
+                    out = torch.empty((self.nc, L), dtype=_I32, device=self.device)
+                    check(lib.pgb_pack_l2_dofs(d, self.nc, self.nn, self.cell_nodes.data_ptr(), ce.data_ptr(),
+                                               out.data_ptr(), _stream()))
+                    _lib.count(1)
+                self._l2 = out
             return self._l2, self.nn + self.ne
         if space == "darcy":  # RT0 x P0: faces of the cell, then num_faces + cell
             if self._darcy is None:

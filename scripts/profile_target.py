@@ -16,11 +16,11 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 space = sys.argv[2] if len(sys.argv) > 2 else "lagrange1"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 cg_iters = int(sys.argv[4]) if len(sys.argv) > 4 else 5
-kind = {"lagrange1": "l1_stiff", "rt0": "rt0_mass", "nedelec0": "n0_mass", "bdm1": "bdm1_mass", "darcy": "darcy_saddle"}[space]
+kind = {"lagrange1": "l1_stiff", "rt0": "rt0_mass", "nedelec0": "n0_mass", "bdm1": "bdm1_mass", "darcy": "darcy_saddle", "lagrange2": "l2_stiff"}[space]
 dev = torch.device("cuda", 0)
 sd = pg.structured_grid(3, n, device=dev)
 sd.compute_connectivity()
-raw = engine.RawGrid.upload(sd, dev, ridges=(space == "nedelec0"))
+raw = engine.RawGrid.upload(sd, dev, ridges=(space in ("nedelec0", "lagrange2")))
 raw.check = False
 import time
 for _ in range(reps):

@@ -129,3 +129,26 @@ def test_vectors_match_reference(ref, dim, n, pert):
         for bf in (b_faces, idx):
             a, b = ours.assemble_nat_bc(sd, scal, bf), theirs.assemble_nat_bc(g, scal, bf)
             assert a.shape == b.shape and np.allclose(a, b, rtol=1e-14, atol=1e-15), name
+
+
+@pytest.mark.parametrize("dim,npts", [(2, 120), (3, 60)])
+@pytest.mark.parametrize("mode", ["sym", "nonsym"])
+def test_oracle_matches_reference_unstructured(ref, dim, npts, mode):
+    """Delaunay meshes (varying node valence, faces / ridges in no lattice order): the closed forms,
+    including the Lagrange2 edge-dof index rule (h1.py:529-540), against the reference itself."""
+    from pgb_helpers import delaunay_grid
+
+    pg, pp = ref
+    sd = delaunay_grid(dim, npts, seed=3)
+    sd.compute_geometry()
+    g = ref_loader.ref_grid(sd)
+    data = _data(pg, pp, sd.num_cells, mode == "sym")
+    tabs = fo.cell_tables(sd)
+    cls = {"lagrange1": pg.Lagrange1, "rt0": pg.RT0, "bdm1": pg.BDM1, "nedelec0": pg.Nedelec0,
+           "lagrange2": pg.Lagrange2}
+    for space, c in cls.items():
+        for form in ("mass", "stiff"):
+            refm = sps.csr_array(getattr(c("k"), f"assemble_{form}_matrix")(g, data))
+            closed = fo.closed_form(space, form, sd, data, "k", tabs)
+            refS = fo.canonicalise(refm, closed)
+            assert np.abs(refS.data - closed.data).max() <= TOL * abs(refm).max(), (space, form)

@@ -395,23 +395,32 @@ __global__ void __launch_bounds__(256) k_inc_count(uint32_t n_inc, const int32_t
   }
 }
 
-// valid when every dof has at most 256 incidences (ranks did not saturate)
+// Ranks saturate at 255: the incidences of a dof beyond its first 255 draw their position from a
+// second counter (ovf [n_rows], zeroed; may be null when no dof has more than 255 incidences).
+__device__ __forceinline__ uint32_t place_pos(const uint32_t* __restrict__ row_start, uint32_t* __restrict__ ovf,
+                                              int32_t d, uint32_t rank) {
+  uint32_t p = __ldg(row_start + d) + rank;
+  if (rank == 255u && ovf) p += atomicAdd(ovf + d, 1u);
+  return p;
+}
+
 __global__ void __launch_bounds__(256) k_inc_place(uint32_t n_inc, const int32_t* __restrict__ dofs,
                                                    const uint32_t* __restrict__ row_start,
-                                                   const uint8_t* __restrict__ rank, uint32_t* __restrict__ inc_tmp) {
+                                                   const uint8_t* __restrict__ rank, uint32_t* __restrict__ ovf,
+                                                   uint32_t* __restrict__ inc_tmp) {
   const uint32_t i0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
   if (i0 >= n_inc) return;
   if (i0 + 4 <= n_inc) {
     int4 d = *reinterpret_cast<const int4*>(dofs + i0);
     uchar4 k = *reinterpret_cast<const uchar4*>(rank + i0);
-    uint32_t p0 = __ldg(row_start + d.x) + k.x, p1 = __ldg(row_start + d.y) + k.y;
-    uint32_t p2 = __ldg(row_start + d.z) + k.z, p3 = __ldg(row_start + d.w) + k.w;
+    uint32_t p0 = place_pos(row_start, ovf, d.x, k.x), p1 = place_pos(row_start, ovf, d.y, k.y);
+    uint32_t p2 = place_pos(row_start, ovf, d.z, k.z), p3 = place_pos(row_start, ovf, d.w, k.w);
     inc_tmp[p0] = i0;
     inc_tmp[p1] = i0 + 1;
     inc_tmp[p2] = i0 + 2;
     inc_tmp[p3] = i0 + 3;
   } else {
-    for (uint32_t i = i0; i < n_inc; ++i) inc_tmp[row_start[dofs[i]] + rank[i]] = i;
+    for (uint32_t i = i0; i < n_inc; ++i) inc_tmp[place_pos(row_start, ovf, dofs[i], rank[i])] = i;
   }
 }
 
@@ -796,7 +805,7 @@ struct PhaseTimer {
 struct RowRange {
   int64_t r0, r1;
   uint32_t max_inc;
-  int kind;  // 0 k_rowthread (grouped scratch), 1 k_rowhash, 2 k_rowsort (one scratch segment per row)
+  int kind;  // 0 k_rowthread (grouped scratch), 1 k_rowhash, 2 k_rowsort, 3 k_rowlong (one scratch segment per row)
 };
 std::vector<RowRange> g_ranges;
 const void* g_ranges_ws = nullptr;
@@ -992,13 +1001,16 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     PGB_CHECK(cudaStreamSynchronize(s));
     max_inc = h_pin[n_chunks];
     if (!radix) pt.mark();
-    if (max_inc * (uint32_t)L > MAX_ROW_CAND || max_inc > 256u) {
-      pgb_set_error("pgb_csr_symbolic_sort: a dof is shared by %u cells (> %u candidates per row or > 256 "
-                    "cells); use mode 1 (full sort)", max_inc, MAX_ROW_CAND);
+    // rows beyond the capacity of k_rowsort go to k_rowlong (counting transpose only)
+    const bool long_ok = !radix && !g_force_bitonic && !g_force_key64;
+    if (max_inc > (uint32_t)LONG_MAX_INC || (!long_ok && (max_inc * (uint32_t)L > MAX_ROW_CAND || max_inc > 256u))) {
+      pgb_set_error("pgb_csr_symbolic_sort: a dof is shared by %u cells (more than the row kernels take); "
+                    "use mode 1 (full sort)", max_inc);
       return 3;
     }
     // ranges of chunks that get the same row kernel
     auto kind_of = [&](uint32_t m) {
+      if (m * (uint32_t)L > MAX_ROW_CAND || m > 256u) return 3;  // k_rowlong
       return rowthread_applies(m, m * (uint32_t)L) ? 0 : rowhash_applies(m, m * (uint32_t)L) ? 1 : 2;
     };
     auto bucket = [](uint32_t m) {
@@ -1033,7 +1045,12 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     }
     g_ranges_ws = workspace;
     if (!radix) {
-      k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, pbuf[1]);
+      uint32_t* ovf = nullptr;
+      if (max_inc > 255u) {  // saturated ranks: second counter per dof (row_nnz is free until the row kernels run)
+        ovf = row_nnz;
+        PGB_CHECK(cudaMemsetAsync(ovf, 0, sizeof(uint32_t) * n_rows, s));
+      }
+      k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, ovf, pbuf[1]);
       PGB_LAUNCH_CHECK();
       inc_rows = pbuf[1];  // row blocks, each in arbitrary order
       for (const RowRange& x : rg) {
@@ -1063,6 +1080,9 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
       else if (x.kind == 1)
         rc = launch_rowhash(mi, mc, L, x.r0, x.r1, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
                             (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s);
+      else if (x.kind == 3)
+        rc = launch_rowlong(L, x.r0, x.r1, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
+                            (int32_t*)(ws + l.ucol), row_nnz, meta + 4, meta + 5, s);
       else
         rc = launch_rowsort(mc, L, x.r0, x.r1, n_rows, row_start, pbuf[0], cell_dofs, slots, (int32_t*)(ws + l.ucol),
                             row_nnz, meta + 4, s);
@@ -1074,13 +1094,14 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     pt.mark();
     pt.finish();
   }
-  uint32_t out2[3] = {0, 0, 0};
+  uint32_t out2[4] = {0, 0, 0, 0};  // nnz, max incidences, max row nnz, k_rowlong overflow (distinct columns of a row)
   PGB_CHECK(cudaMemcpyAsync(out2, meta + 2, sizeof(out2), cudaMemcpyDeviceToHost, s));
   PGB_CHECK(cudaStreamSynchronize(s));
   *nnz_host = (int64_t)out2[0];
   if (max_row_nnz_host) *max_row_nnz_host = (int)out2[2];
-  if (mode != MODE_FULL_SORT && out2[2] > 255u) {
-    pgb_set_error("pgb_csr_symbolic_sort: a row has %u entries (> 255, the uint8 slot range); use mode 1", out2[2]);
+  if (mode != MODE_FULL_SORT && (out2[2] > 255u || out2[3] > 255u)) {
+    pgb_set_error("pgb_csr_symbolic_sort: a row has %u entries (> 255, the uint8 slot range); use mode 1",
+                  out2[2] > out2[3] ? out2[2] : out2[3]);
     return 3;
   }
   return 0;

@@ -141,4 +141,11 @@ int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, int64_t row0, int
                    const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
                    uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s);
 
+// k_rowlong: one block per row, up to LONG_MAX_INC incident cells (pgb_rowlong.cu); inc_tmp: the row
+// blocks in any order.  *overflow_flag is raised when a row has more than 255 distinct columns.
+constexpr int LONG_MAX_INC = 2048;
+int launch_rowlong(int L, int64_t row0, int64_t row1, const uint32_t* row_start, const uint32_t* inc_tmp,
+                   const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz,
+                   uint32_t* max_nnz, uint32_t* overflow_flag, cudaStream_t s);
+
 }  // namespace pgb_rows

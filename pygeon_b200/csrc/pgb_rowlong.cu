@@ -37,7 +37,7 @@ __device__ __forceinline__ void block_bitonic(uint32_t* a, uint32_t n) {
 }
 
 template <int L>
-__global__ void __launch_bounds__(256) k_rowlong(int64_t row0, const uint32_t* __restrict__ row_start,
+__global__ void __launch_bounds__(256) k_rowlong(const uint32_t* __restrict__ rows, int64_t row0, const uint32_t* __restrict__ row_start,
                                                  const uint32_t* __restrict__ inc_tmp,
                                                  const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos,
                                                  uint8_t* __restrict__ slots, int32_t* __restrict__ ucol_tmp,
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_rowlong(int64_t row0, const uint32_t* _
   __shared__ uint32_t s_u[256];
   __shared__ uint32_t s_nu;
   const int tid = threadIdx.x;
-  const int64_t r = row0 + blockIdx.x;
+  const int64_t r = rows ? (int64_t)rows[blockIdx.x] : row0 + blockIdx.x;
   const uint32_t rs = row_start[r], cnt = row_start[r + 1] - rs;
   uint32_t n2 = 32;
   while (n2 < cnt) n2 <<= 1;
@@ -116,14 +116,15 @@ __global__ void __launch_bounds__(256) k_rowlong(int64_t row0, const uint32_t* _
 
 namespace pgb_rows {
 
-int launch_rowlong(int L, int64_t row0, int64_t row1, const uint32_t* row_start, const uint32_t* inc_tmp,
+int launch_rowlong(int L, const uint32_t* rows, int64_t row0, int64_t row1, const uint32_t* row_start, const uint32_t* inc_tmp,
                    const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz,
                    uint32_t* max_nnz, uint32_t* overflow_flag, cudaStream_t s) {
   char name[64];
   snprintf(name, sizeof(name), "k_rowlong<%d>", L);
   note_row_kernel(name);
+  if (row1 <= row0) return 0;
   unsigned grid = (unsigned)(row1 - row0);
-#define PGB_RLG(LL) k_rowlong<LL><<<grid, 256, 0, s>>>(row0, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, overflow_flag)
+#define PGB_RLG(LL) k_rowlong<LL><<<grid, 256, 0, s>>>(rows, row0, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, overflow_flag)
   switch (L) {
     case 3: PGB_RLG(3); break;
     case 4: PGB_RLG(4); break;

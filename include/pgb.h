@@ -146,13 +146,14 @@ int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
  *     (2) per row: gather the candidate columns of the incident cells, find the sorted distinct
  *     columns and record for every candidate the index of its column inside the row
  *     (slots, uint8, slots[(row_start[r] + q)*LP + b], LP = L rounded up to a multiple of 4).
- *     Three kernels, picked per range of 4096-row chunks from the largest incidence / candidate
- *     count of a row in the range (a few long rows do not slow the others down): one thread per
+ *     Four kernels, picked by row length (per range of 4096-row chunks, or per size-class row list
+ *     when long rows are scattered; a few long rows do not slow the others down): one thread per
  *     row with a register sorting network (<= 16 incidences, <= 64 candidates), a group of 8..32
  *     lanes per row with a shared-memory hash dedupe (<= 256 candidates), a sub-warp bitonic sort
- *     of all candidates (<= 512).  (3) a scan of the row counts and a compaction.
- *     Needs every dof to be shared by at most min(256, 512/L) cells and every row to have at most
- *     255 entries; otherwise returns 3 and the caller retries with mode 1.
+ *     of all candidates (<= 512), one block per row (<= 2048 incidences).  (3) a scan of the row
+ *     counts and a compaction.
+ *     Needs every dof to be shared by at most 2048 cells and every row to have at most 255
+ *     entries; otherwise returns 3 and the caller retries with mode 1.
  *     Test modes: 2 = 64-bit (col, position) keys forced in the row sorts, 3 = the sub-warp bitonic
  *     row sort forced, 4 = step (1) by a stable LSD radix sort of the incidences (32-bit keys)
  *     instead of counting.  All give bit-identical inc_pos / slots / pattern.

@@ -345,27 +345,62 @@ __global__ void __launch_bounds__(256) k_max_row(int64_t n_rows, const uint32_t*
   }
 }
 
-// largest incidence count of every chunk of CHUNK_ROWS rows (and of the matrix): the row kernel is
-// chosen per range of chunks, so that a few long rows do not put every row on the slow kernel
-constexpr int CHUNK_ROWS = 4096;  // multiple of ROWTHREAD_GROUP and of the rows per block of every row kernel
+// Largest incidence count of every chunk of CHUNK_ROWS rows (and of the matrix), and how many rows of
+// the chunk fall into each size class (class k: 2^(k-1) < incidences <= 2^k; k = 0: at most one).
+// Chunks whose rows are all short go to k_rowthread as a contiguous range; the rows of the other
+// chunks are gathered into one row list per size class, so that every row gets the cheapest kernel
+// that takes it, wherever the long rows are.
+constexpr int CHUNK_ROWS = 4096;  // multiple of ROWTHREAD_GROUP
+constexpr int NCLS = 12;          // size classes up to 2^11 = LONG_MAX_INC incidences
+__device__ __forceinline__ int size_class(uint32_t cnt) { return cnt <= 1u ? 0 : 32 - __clz(cnt - 1u); }
+
 __global__ void __launch_bounds__(256) k_chunk_max(int64_t n_rows, const uint32_t* __restrict__ row_start,
-                                                   uint32_t* __restrict__ chunk_max, uint32_t* __restrict__ max_count) {
+                                                   uint32_t* __restrict__ chunk_max, uint32_t* __restrict__ chunk_hist,
+                                                   uint32_t* __restrict__ chunk_cmax, uint32_t* __restrict__ max_count) {
   __shared__ uint32_t ws[8];
+  __shared__ uint32_t hist[NCLS], cmax[NCLS];
+  if (threadIdx.x < NCLS) hist[threadIdx.x] = 0, cmax[threadIdx.x] = 0;
+  __syncthreads();
   const int64_t r0 = (int64_t)blockIdx.x * CHUNK_ROWS;
   const int64_t r1 = r0 + CHUNK_ROWS < n_rows ? r0 + CHUNK_ROWS : n_rows;
   uint32_t mx = 0;
   for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) {
     uint32_t c = row_start[r + 1] - row_start[r];
     mx = c > mx ? c : mx;
+    int k = size_class(c);
+    k = k < NCLS ? k : NCLS - 1;
+    atomicAdd(&hist[k], 1u);  // integer count / max: order independent
+    atomicMax(&cmax[k], c);
   }
   mx = __reduce_max_sync(FULL, mx);
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) ws[w] = mx;
   __syncthreads();
+  if (threadIdx.x < NCLS) {
+    chunk_hist[(int64_t)blockIdx.x * NCLS + threadIdx.x] = hist[threadIdx.x];
+    chunk_cmax[(int64_t)blockIdx.x * NCLS + threadIdx.x] = cmax[threadIdx.x];
+  }
   if (threadIdx.x == 0) {
     for (int q = 1; q < 8; ++q) mx = ws[q] > mx ? ws[q] : mx;
     chunk_max[blockIdx.x] = mx;
     atomicMax(max_count, mx);
+  }
+}
+
+// Scatter the rows of the listed chunks into the per-class row lists.  start[chunk*NCLS + k]: where
+// the class-k rows of the chunk begin in `list` (0xffffffff in [chunk*NCLS]: chunk not listed).  The
+// order inside a (chunk, class) block is arbitrary: every row kernel writes to row-owned locations.
+__global__ void __launch_bounds__(256) k_row_lists(int64_t n_rows, const uint32_t* __restrict__ row_start,
+                                                   const uint32_t* __restrict__ start, uint32_t* __restrict__ list) {
+  __shared__ uint32_t pos[NCLS];
+  if (start[(int64_t)blockIdx.x * NCLS] == 0xffffffffu) return;
+  if (threadIdx.x < NCLS) pos[threadIdx.x] = start[(int64_t)blockIdx.x * NCLS + threadIdx.x];
+  __syncthreads();
+  const int64_t r0 = (int64_t)blockIdx.x * CHUNK_ROWS;
+  const int64_t r1 = r0 + CHUNK_ROWS < n_rows ? r0 + CHUNK_ROWS : n_rows;
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) {
+    int k = size_class(row_start[r + 1] - row_start[r]);
+    list[atomicAdd(&pos[k < NCLS ? k : NCLS - 1], 1u)] = (uint32_t)r;
   }
 }
 
@@ -395,35 +430,46 @@ __global__ void __launch_bounds__(256) k_inc_count(uint32_t n_inc, const int32_t
   }
 }
 
-// valid when every dof has at most 256 incidences (ranks did not saturate)
+// Ranks saturate at 255: the incidences of a dof beyond its first 255 draw their position from a
+// second counter (ovf [n_rows], zeroed; may be null when no dof has more than 255 incidences).
+__device__ __forceinline__ uint32_t place_pos(const uint32_t* __restrict__ row_start, uint32_t* __restrict__ ovf,
+                                              int32_t d, uint32_t rank) {
+  uint32_t p = __ldg(row_start + d) + rank;
+  if (rank == 255u && ovf) p += atomicAdd(ovf + d, 1u);
+  return p;
+}
+
 __global__ void __launch_bounds__(256) k_inc_place(uint32_t n_inc, const int32_t* __restrict__ dofs,
                                                    const uint32_t* __restrict__ row_start,
-                                                   const uint8_t* __restrict__ rank, uint32_t* __restrict__ inc_tmp) {
+                                                   const uint8_t* __restrict__ rank, uint32_t* __restrict__ ovf,
+                                                   uint32_t* __restrict__ inc_tmp) {
   const uint32_t i0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
   if (i0 >= n_inc) return;
   if (i0 + 4 <= n_inc) {
     int4 d = *reinterpret_cast<const int4*>(dofs + i0);
     uchar4 k = *reinterpret_cast<const uchar4*>(rank + i0);
-    uint32_t p0 = __ldg(row_start + d.x) + k.x, p1 = __ldg(row_start + d.y) + k.y;
-    uint32_t p2 = __ldg(row_start + d.z) + k.z, p3 = __ldg(row_start + d.w) + k.w;
+    uint32_t p0 = place_pos(row_start, ovf, d.x, k.x), p1 = place_pos(row_start, ovf, d.y, k.y);
+    uint32_t p2 = place_pos(row_start, ovf, d.z, k.z), p3 = place_pos(row_start, ovf, d.w, k.w);
     inc_tmp[p0] = i0;
     inc_tmp[p1] = i0 + 1;
     inc_tmp[p2] = i0 + 2;
     inc_tmp[p3] = i0 + 3;
   } else {
-    for (uint32_t i = i0; i < n_inc; ++i) inc_tmp[row_start[dofs[i]] + rank[i]] = i;
+    for (uint32_t i = i0; i < n_inc; ++i) inc_tmp[place_pos(row_start, ovf, dofs[i], rank[i])] = i;
   }
 }
 
 // G lanes per row, NPL incidences per lane (capacity G*NPL)
 template <int G, int NPL>
-__global__ void __launch_bounds__(256) k_row_canon(int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start,
+__global__ void __launch_bounds__(256) k_row_canon(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows,
+                                                   const uint32_t* __restrict__ row_start,
                                                    const uint32_t* __restrict__ inc_tmp,
                                                    uint32_t* __restrict__ inc_sorted, uint32_t* __restrict__ inc_pos) {
   const int gl = threadIdx.x & (G - 1);
-  const int64_t r = row0 + ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;  // rows [row0, n_rows)
+  bool live;
+  const int64_t r = pick_row(rows, row0, n_rows, ((int64_t)blockIdx.x * 256 + threadIdx.x) / G, live);
   uint32_t rs = 0, cnt = 0;
-  if (r < n_rows) {
+  if (live) {
     rs = row_start[r];
     cnt = row_start[r + 1] - rs;
   }
@@ -796,7 +842,8 @@ struct PhaseTimer {
 struct RowRange {
   int64_t r0, r1;
   uint32_t max_inc;
-  int kind;  // 0 k_rowthread (grouped scratch), 1 k_rowhash, 2 k_rowsort (one scratch segment per row)
+  int kind;  // 0: k_rowthread range (grouped scratch); 1: rows handled through the size-class lists (one scratch
+             // segment per row)
 };
 std::vector<RowRange> g_ranges;
 const void* g_ranges_ws = nullptr;
@@ -808,7 +855,7 @@ struct WsLayout {
   // full sort
   int64_t keys_a, keys_b, perm_b;
   // two level
-  int64_t ikeys_a, ikeys_b, ipay_a, ipay_b, row_nnz, ucol, chunk;
+  int64_t ikeys_a, ikeys_b, ipay_a, ipay_b, row_nnz, ucol, chunk, rowlist;
   // shared
   int64_t hist, parts, meta, total;
 };
@@ -834,7 +881,8 @@ WsLayout ws_layout(int64_t n_coo, int64_t n_inc, int64_t n_rows, int mode) {
     l.ipay_b = o;    o += al(n_inc * 4);
     l.row_nnz = o;   o += al((n_rows + 2) * 4);
     l.ucol = o;      o += al(n_coo * 4);
-    l.chunk = o;     o += al((n_rows / CHUNK_ROWS + 2) * 4);
+    l.chunk = o;     o += al((n_rows / CHUNK_ROWS + 2) * (1 + 3 * NCLS) * 4);  // max, class histogram, class maxima, list starts
+    l.rowlist = o;   o += al(n_rows * 4);
   }
   l.total = o;
   return l;
@@ -960,16 +1008,25 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     uint32_t max_inc = 0;
     uint32_t* chunk_max_d = (uint32_t*)(ws + l.chunk);
     const int64_t n_chunks = pgb_cdiv(n_rows, CHUNK_ROWS);
-    // pinned staging for the two small device->host reads of this call (a pageable target costs an
-    // extra internal synchronisation)
+    // pinned staging for the small device->host / host->device transfers of this call (a pageable
+    // buffer costs an extra internal synchronisation): [0, nch) chunk maxima, [nch] the global
+    // maximum, then nch*NCLS class counts, nch*NCLS class maxima, nch*NCLS list starts
     static uint32_t* h_pin = nullptr;
     static int64_t h_pin_cap = 0;
-    if (n_chunks + 1 > h_pin_cap) {
+    const int64_t h_need = n_chunks * (1 + 3 * NCLS) + 1;
+    if (h_need > h_pin_cap) {
       if (h_pin) cudaFreeHost(h_pin);
-      h_pin_cap = n_chunks + 1 + 1024;
+      h_pin_cap = h_need + 4096;
       PGB_CHECK(cudaMallocHost(&h_pin, sizeof(uint32_t) * h_pin_cap));
     }
     uint32_t* chunk_max = h_pin;
+    uint32_t* chunk_hist = h_pin + n_chunks + 1;
+    uint32_t* chunk_cmax = chunk_hist + n_chunks * NCLS;
+    uint32_t* list_start = chunk_cmax + n_chunks * NCLS;
+    uint32_t* chunk_hist_d = chunk_max_d + n_chunks + 1;
+    uint32_t* chunk_cmax_d = chunk_hist_d + n_chunks * NCLS;
+    uint32_t* list_start_d = chunk_cmax_d + n_chunks * NCLS;
+    uint32_t* row_list = (uint32_t*)(ws + l.rowlist);
     const uint32_t* inc_rows = pbuf[0];
     const bool radix = (mode == MODE_TWO_LEVEL_RADIX);
     uint8_t* rank = (uint8_t*)kbuf[0];
@@ -985,68 +1042,153 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
       PGB_LAUNCH_CHECK();
       if (scan_u32(row_start, (uint64_t)n_rows + 1, parts, nullptr, s)) return 1;
     }
-    k_chunk_max<<<(unsigned)n_chunks, 256, 0, s>>>(n_rows, row_start, chunk_max_d, meta + 3);
+    k_chunk_max<<<(unsigned)n_chunks, 256, 0, s>>>(n_rows, row_start, chunk_max_d, chunk_hist_d, chunk_cmax_d, meta + 3);
     PGB_LAUNCH_CHECK();
     PGB_CHECK(cudaMemcpyAsync(h_pin + n_chunks, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PGB_CHECK(cudaMemcpyAsync(chunk_max, chunk_max_d, sizeof(uint32_t) * n_chunks, cudaMemcpyDeviceToHost, s));
+    PGB_CHECK(cudaMemcpyAsync(chunk_hist, chunk_hist_d, sizeof(uint32_t) * n_chunks * NCLS * 2, cudaMemcpyDeviceToHost, s));  // counts + maxima
     PGB_CHECK(cudaStreamSynchronize(s));
     max_inc = h_pin[n_chunks];
     if (!radix) pt.mark();
-    if (max_inc * (uint32_t)L > MAX_ROW_CAND || max_inc > 256u) {
-      pgb_set_error("pgb_csr_symbolic_sort: a dof is shared by %u cells (> %u candidates per row or > 256 "
-                    "cells); use mode 1 (full sort)", max_inc, MAX_ROW_CAND);
+    // rows beyond the capacity of k_rowsort go to k_rowlong (counting transpose only)
+    const bool long_ok = !radix && !g_force_bitonic && !g_force_key64;
+    if (max_inc > (uint32_t)LONG_MAX_INC || (!long_ok && (max_inc * (uint32_t)L > MAX_ROW_CAND || max_inc > 256u))) {
+      pgb_set_error("pgb_csr_symbolic_sort: a dof is shared by %u cells (more than the row kernels take); "
+                    "use mode 1 (full sort)", max_inc);
       return 3;
     }
-    // ranges of chunks that get the same row kernel
-    auto kind_of = [&](uint32_t m) {
-      return rowthread_applies(m, m * (uint32_t)L) ? 0 : rowhash_applies(m, m * (uint32_t)L) ? 1 : 2;
+    // Work items.  Chunks of short rows: contiguous ranges for k_rowthread.  The other chunks: either
+    // contiguous ranges, each with the kernel its longest row needs, or - when the long rows are
+    // scattered, so that almost every chunk has one - one row list per size class gathered from all of
+    // them.  A rough cost model (candidates per row x a factor per kernel family) decides.
+    struct Item {
+      const uint32_t* rows;  // row list (then r0 = 0) or null
+      int64_t r0, r1;
+      uint32_t bound;  // largest incidence count
+      int kind;        // 0 k_rowthread, 1 k_rowhash, 2 k_rowsort, 3 k_rowlong
     };
     auto bucket = [](uint32_t m) {
       uint32_t b = 1;
       while (b < m) b <<= 1;
       return b;
     };
+    auto kind_of = [&](uint32_t m) {  // kernel family for rows of at most m incidences (not k_rowthread)
+      if (rowhash_applies(m, m * (uint32_t)L)) return 1;
+      if (m * (uint32_t)L <= MAX_ROW_CAND && m <= 256u) return 2;
+      return 3;
+    };
+    auto cost_of = [&](uint32_t m) {
+      const double mc = (double)m * L;
+      const int k = kind_of(m);
+      const double f = k == 3 ? 20.0 : k == 2 ? 6.0 : m > 32u ? 4.0 : mc > 96.0 ? 2.0 : 1.0;
+      return mc * f;
+    };
+    std::vector<char> ckind((size_t)n_chunks);  // 0: k_rowthread range, 1: other
+    for (int64_t i = 0; i < n_chunks; ++i) {
+      const uint32_t m = chunk_max[i] ? chunk_max[i] : 1u;
+      ckind[(size_t)i] = rowthread_applies(m, m * (uint32_t)L) ? 0 : 1;
+    }
+    {  // many short k_rowthread ranges between other chunks would cost a launch each
+      int64_t nrange = 1;
+      for (int64_t i = 1; i < n_chunks; ++i) nrange += ckind[(size_t)i] != ckind[(size_t)i - 1];
+      if (nrange > 64) {
+        for (int64_t i = 0; i < n_chunks;) {
+          int64_t j = i;
+          while (j < n_chunks && ckind[(size_t)j] == ckind[(size_t)i]) ++j;
+          if (ckind[(size_t)i] == 0 && j - i < 8)
+            for (int64_t q = i; q < j; ++q) ckind[(size_t)q] = 1;
+          i = j;
+        }
+      }
+    }
+    uint32_t cls_total[NCLS] = {0}, cls_max[NCLS] = {0};  // rows / largest incidence count per size class
+    double cost_ranges = 0.0, cost_lists = 0.0;
+    for (int64_t i = 0; i < n_chunks; ++i) {
+      if (!ckind[(size_t)i]) continue;
+      const int64_t r0 = i * CHUNK_ROWS, r1 = r0 + CHUNK_ROWS < n_rows ? r0 + CHUNK_ROWS : n_rows;
+      cost_ranges += (double)(r1 - r0) * cost_of(chunk_max[i] ? chunk_max[i] : 1u);
+      for (int k = 0; k < NCLS; ++k) {
+        cls_total[k] += chunk_hist[i * NCLS + k];
+        cls_max[k] = chunk_cmax[i * NCLS + k] > cls_max[k] ? chunk_cmax[i * NCLS + k] : cls_max[k];
+      }
+    }
+    for (int k = 0; k < NCLS; ++k) cost_lists += (double)cls_total[k] * cost_of(cls_max[k] ? cls_max[k] : 1u);
+    const bool use_lists = cost_ranges > 1.25 * cost_lists;
+    // ranges (for the launches below and for symbolic_finish)
     std::vector<RowRange>& rg = g_ranges;
     rg.clear();
     for (int64_t i = 0; i < n_chunks; ++i) {
       const uint32_t m = chunk_max[i] ? chunk_max[i] : 1u;
       const int64_t r0 = i * CHUNK_ROWS, r1 = r0 + CHUNK_ROWS < n_rows ? r0 + CHUNK_ROWS : n_rows;
-      if (!rg.empty() && rg.back().kind == kind_of(m) && bucket(rg.back().max_inc) == bucket(m)) {
+      const int kind = ckind[(size_t)i];
+      const bool same_kernel = (kind && use_lists) || bucket(rg.empty() ? 0u : rg.back().max_inc) == bucket(m);
+      if (!rg.empty() && rg.back().kind == kind && same_kernel) {
         rg.back().r1 = r1;
         rg.back().max_inc = m > rg.back().max_inc ? m : rg.back().max_inc;
       } else {
-        rg.push_back({r0, r1, m, kind_of(m)});
+        rg.push_back({r0, r1, m, kind});
       }
     }
-    while (rg.size() > 64) {  // many alternations (scattered long rows): coarsen
+    if (!use_lists && rg.size() > 64) {  // bound the number of launches: merge neighbouring non-thread ranges
       std::vector<RowRange> c;
-      for (size_t i = 0; i < rg.size(); i += 2) {
-        RowRange x = rg[i];
-        if (i + 1 < rg.size()) {
-          x.r1 = rg[i + 1].r1;
-          x.max_inc = rg[i + 1].max_inc > x.max_inc ? rg[i + 1].max_inc : x.max_inc;
+      for (const RowRange& x : rg) {
+        if (!c.empty() && c.back().kind && x.kind) {
+          c.back().r1 = x.r1;
+          c.back().max_inc = x.max_inc > c.back().max_inc ? x.max_inc : c.back().max_inc;
+        } else {
+          c.push_back(x);
         }
-        x.kind = kind_of(x.max_inc);
-        c.push_back(x);
       }
       rg.swap(c);
     }
     g_ranges_ws = workspace;
+    std::vector<Item> items;
+    for (const RowRange& x : rg) {
+      if (x.kind == 0) items.push_back({nullptr, x.r0, x.r1, x.max_inc, 0});
+      else if (!use_lists) items.push_back({nullptr, x.r0, x.r1, x.max_inc, kind_of(x.max_inc)});
+    }
+    if (use_lists) {
+      uint32_t cls_base[NCLS + 1] = {0}, run[NCLS];
+      for (int k = 0; k < NCLS; ++k) cls_base[k + 1] = cls_base[k] + cls_total[k];
+      for (int k = 0; k < NCLS; ++k) run[k] = cls_base[k];
+      for (int64_t i = 0; i < n_chunks; ++i) {
+        if (!ckind[(size_t)i]) {
+          list_start[i * NCLS] = 0xffffffffu;
+          continue;
+        }
+        for (int k = 0; k < NCLS; ++k) {
+          list_start[i * NCLS + k] = run[k];
+          run[k] += chunk_hist[i * NCLS + k];
+        }
+      }
+      PGB_CHECK(cudaMemcpyAsync(list_start_d, list_start, sizeof(uint32_t) * n_chunks * NCLS, cudaMemcpyHostToDevice, s));
+      k_row_lists<<<(unsigned)n_chunks, 256, 0, s>>>(n_rows, row_start, list_start_d, row_list);
+      PGB_LAUNCH_CHECK();
+      for (int k = NCLS - 1; k >= 0; --k) {  // longest rows first
+        if (!cls_total[k]) continue;
+        const uint32_t bound = cls_max[k] ? cls_max[k] : 1u;
+        items.push_back({row_list + cls_base[k], 0, (int64_t)cls_total[k], bound, kind_of(bound)});
+      }
+    }
     if (!radix) {
-      k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, pbuf[1]);
+      uint32_t* ovf = nullptr;
+      if (max_inc > 255u) {  // saturated ranks: second counter per dof (row_nnz is free until the row kernels run)
+        ovf = row_nnz;
+        PGB_CHECK(cudaMemsetAsync(ovf, 0, sizeof(uint32_t) * n_rows, s));
+      }
+      k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, ovf, pbuf[1]);
       PGB_LAUNCH_CHECK();
       inc_rows = pbuf[1];  // row blocks, each in arbitrary order
-      for (const RowRange& x : rg) {
-        if (x.kind != 2) continue;  // k_rowthread / k_rowhash sort the row blocks themselves
+      for (const Item& x : items) {
+        if (x.kind != 2) continue;  // only k_rowsort needs sorted row blocks
         const int64_t nr = x.r1 - x.r0;
-        const uint32_t mi = x.max_inc;
-#define PGB_RC(G, N) k_row_canon<G, N><<<pgb_grid(nr * G, 256), 256, 0, s>>>(x.r0, x.r1, row_start, pbuf[1], pbuf[0], perm_or_inc)
-        if (mi <= 4) PGB_RC(4, 1);
-        else if (mi <= 8) PGB_RC(8, 1);
-        else if (mi <= 16) PGB_RC(16, 1);
-        else if (mi <= 32) PGB_RC(32, 1);
-        else if (mi <= 64) PGB_RC(32, 2);
-        else if (mi <= 128) PGB_RC(32, 4);
+#define PGB_RC(G, N) k_row_canon<G, N><<<pgb_grid(nr * G, 256), 256, 0, s>>>(x.rows, x.r0, x.r1, row_start, pbuf[1], pbuf[0], perm_or_inc)
+        if (x.bound <= 4) PGB_RC(4, 1);
+        else if (x.bound <= 8) PGB_RC(8, 1);
+        else if (x.bound <= 16) PGB_RC(16, 1);
+        else if (x.bound <= 32) PGB_RC(32, 1);
+        else if (x.bound <= 64) PGB_RC(32, 2);
+        else if (x.bound <= 128) PGB_RC(32, 4);
         else PGB_RC(32, 8);
 #undef PGB_RC
         PGB_LAUNCH_CHECK();
@@ -1054,18 +1196,27 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     }
     PGB_CHECK(cudaMemsetAsync(row_nnz + n_rows, 0, 2 * sizeof(uint32_t), s));
     pt.mark();
-    for (const RowRange& x : rg) {
-      const uint32_t mi = x.max_inc, mc = x.max_inc * (uint32_t)L;
+    for (const Item& x : items) {
+      const uint32_t mc = x.bound * (uint32_t)L;
+      int32_t* ucol = (int32_t*)(ws + l.ucol);
       int rc;
-      if (x.kind == 0)
-        rc = launch_rowthread(mi, L, x.r0, x.r1, n_rows, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
-                              (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s);
-      else if (x.kind == 1)
-        rc = launch_rowhash(mi, mc, L, x.r0, x.r1, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
-                            (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s);
-      else
-        rc = launch_rowsort(mc, L, x.r0, x.r1, n_rows, row_start, pbuf[0], cell_dofs, slots, (int32_t*)(ws + l.ucol),
-                            row_nnz, meta + 4, s);
+      switch (x.kind) {
+        case 0:
+          rc = launch_rowthread(x.bound, L, x.r0, x.r1, n_rows, row_start, inc_rows, cell_dofs, perm_or_inc, slots, ucol,
+                                row_nnz, meta + 4, s);
+          break;
+        case 1:
+          rc = launch_rowhash(x.bound, mc, L, x.rows, x.r0, x.r1, row_start, inc_rows, cell_dofs, perm_or_inc, slots, ucol,
+                              row_nnz, meta + 4, s);
+          break;
+        case 2:
+          rc = launch_rowsort(mc, L, x.rows, x.r0, x.r1, n_rows, row_start, pbuf[0], cell_dofs, slots, ucol, row_nnz,
+                              meta + 4, s);
+          break;
+        default:
+          rc = launch_rowlong(L, x.rows, x.r0, x.r1, row_start, inc_rows, cell_dofs, perm_or_inc, slots, ucol, row_nnz,
+                              meta + 4, meta + 5, s);
+      }
       if (rc) return rc;
     }
     pt.mark();
@@ -1074,13 +1225,14 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     pt.mark();
     pt.finish();
   }
-  uint32_t out2[3] = {0, 0, 0};
+  uint32_t out2[4] = {0, 0, 0, 0};  // nnz, max incidences, max row nnz, k_rowlong overflow (distinct columns of a row)
   PGB_CHECK(cudaMemcpyAsync(out2, meta + 2, sizeof(out2), cudaMemcpyDeviceToHost, s));
   PGB_CHECK(cudaStreamSynchronize(s));
   *nnz_host = (int64_t)out2[0];
   if (max_row_nnz_host) *max_row_nnz_host = (int)out2[2];
-  if (mode != MODE_FULL_SORT && out2[2] > 255u) {
-    pgb_set_error("pgb_csr_symbolic_sort: a row has %u entries (> 255, the uint8 slot range); use mode 1", out2[2]);
+  if (mode != MODE_FULL_SORT && (out2[2] > 255u || out2[3] > 255u)) {
+    pgb_set_error("pgb_csr_symbolic_sort: a row has %u entries (> 255, the uint8 slot range); use mode 1",
+                  out2[2] > out2[3] ? out2[2] : out2[3]);
     return 3;
   }
   return 0;

@@ -55,7 +55,7 @@ __device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint
 // table of HS entries per row (at most 3/4 full)
 template <int G, int NPL, int L, int HS>
 __global__ void __launch_bounds__(256, (NPL == 1 && L <= 6) ? ((256 / G) * HS * 9 <= 20000 ? 8 : 5) : (NPL == 1 ? 5 : 1))
-k_rowhash(int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ inc_tmp,
+k_rowhash(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ inc_tmp,
           const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos, uint8_t* __restrict__ slots,
           int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz, uint32_t* __restrict__ max_nnz) {
   constexpr int LP = (L + 3) & ~3;
@@ -67,12 +67,13 @@ k_rowhash(int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start, 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
   const int g = threadIdx.x / G;
-  const int64_t r = row0 + (int64_t)blockIdx.x * RPB + g;  // rows [row0, n_rows)
+  bool live;
+  const int64_t r = pick_row(rows, row0, n_rows, (int64_t)blockIdx.x * RPB + g, live);
   uint32_t* tkey = s_key[g];
   uint8_t* tslot = s_slot[g];
   uint32_t* ucols = s_ucol[g];
   uint32_t rs = 0, cnt = 0;
-  if (r < n_rows) {
+  if (live) {
     rs = row_start[r];
     cnt = row_start[r + 1] - rs;
   }
@@ -154,7 +155,7 @@ k_rowhash(int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start, 
   }
   const uint32_t base = rs * L;
   for (int e = gl; e < nu; e += G) ucol_tmp[base + e] = (int32_t)ucols[e];
-  if (r < n_rows && gl == 0) row_nnz[r] = (uint32_t)nu;
+  if (live && gl == 0) row_nnz[r] = (uint32_t)nu;
   const uint32_t mxw = __reduce_max_sync(FULL, (unsigned)nu);
   if (lane == 0) wmax[w] = mxw;
   __syncthreads();
@@ -166,14 +167,14 @@ k_rowhash(int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start, 
 }
 
 template <int G, int NPL, int HS>
-int launch_rowhash_l(int L, int64_t row0, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs,
+int launch_rowhash_l(int L, const uint32_t* rows, int64_t row0, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs,
                      uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
                      cudaStream_t s) {
   char name[64];
   snprintf(name, sizeof(name), "k_rowhash<%d,%d,%d,%d>", G, NPL, L, HS);
   note_row_kernel(name);
   unsigned grid = (unsigned)pgb_cdiv(n_rows - row0, 256 / G);
-#define PGB_RH(LL) k_rowhash<G, NPL, LL, HS><<<grid, 256, 0, s>>>(row0, n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz)
+#define PGB_RH(LL) k_rowhash<G, NPL, LL, HS><<<grid, 256, 0, s>>>(rows, row0, n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz)
   switch (L) {
     case 3: PGB_RH(3); break;
     case 4: PGB_RH(4); break;
@@ -195,10 +196,11 @@ namespace pgb_rows {
 
 // fused canonical sort of the incidences + hash dedupe; inc_tmp: the row blocks in any order.
 // Lanes per row from the largest incidence count, table size from the largest candidate count.
-int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, int64_t row0, int64_t n_rows, const uint32_t* row_start,
+int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, const uint32_t* rows, int64_t row0, int64_t n_rows,
+                   const uint32_t* row_start,
                    const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
                    uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
-#define PGB_RHL(G, N, H) return launch_rowhash_l<G, N, H>(L, row0, n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, s)
+#define PGB_RHL(G, N, H) return launch_rowhash_l<G, N, H>(L, rows, row0, n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, s)
   if (max_inc <= 8) PGB_RHL(8, 1, 128);  // 65..96 candidates (fewer go to k_rowthread)
   if (max_inc <= 16) {
     if (max_cand <= 96) PGB_RHL(16, 1, 128);

@@ -123,12 +123,22 @@ __device__ __forceinline__ void load_dofs(const int32_t* __restrict__ p, uint32_
 }
 
 
+// i-th row of a launch: row0 + i of the range [row0, row1), or rows[i], i < row1 - row0, when the
+// launch works on a row list (rows of one size class picked from anywhere in the matrix)
+__device__ __forceinline__ int64_t pick_row(const uint32_t* __restrict__ rows, int64_t row0, int64_t row1, int64_t i,
+                                            bool& live) {
+  live = row0 + i < row1;
+  if (!rows) return row0 + i;
+  return live ? (int64_t)rows[i] : 0;
+}
+
 // k_rowsort: bitonic sort of all candidates of a row by a sub-warp (pgb_rowsort.cu)
 // All launchers work on the row range [row0, row1) (row0 a multiple of 128); n_rows = size of the
 // matrix (decides the key width).
-int launch_rowsort(uint32_t max_cand, int L, int64_t row0, int64_t row1, int64_t n_rows, const uint32_t* row_start,
-                   const uint32_t* inc, const int32_t* dofs, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz,
-                   uint32_t* max_nnz, cudaStream_t s);
+// rows (nullable): row list of row1 - row0 entries (then row0 must be 0).
+int launch_rowsort(uint32_t max_cand, int L, const uint32_t* rows, int64_t row0, int64_t row1, int64_t n_rows,
+                   const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs, uint8_t* slots, int32_t* ucol,
+                   uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s);
 // k_rowthread: one thread per short row, register sorting network (pgb_rowthread.cu)
 bool rowthread_applies(uint32_t max_inc, uint32_t max_cand);
 constexpr int ROWTHREAD_GROUP = 128;  // rows whose distinct columns k_rowthread stores back to back
@@ -137,8 +147,15 @@ int launch_rowthread(uint32_t max_inc, int L, int64_t row0, int64_t row1, int64_
                      uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s);
 // k_rowhash: shared-memory hash dedupe by a group of lanes per row (pgb_rowhash.cu)
 bool rowhash_applies(uint32_t max_inc, uint32_t max_cand);
-int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, int64_t row0, int64_t row1,
+int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, const uint32_t* rows, int64_t row0, int64_t row1,
                    const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
                    uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s);
+
+// k_rowlong: one block per row, up to LONG_MAX_INC incident cells (pgb_rowlong.cu); inc_tmp: the row
+// blocks in any order.  *overflow_flag is raised when a row has more than 255 distinct columns.
+constexpr int LONG_MAX_INC = 2048;
+int launch_rowlong(int L, const uint32_t* rows, int64_t row0, int64_t row1, const uint32_t* row_start, const uint32_t* inc_tmp,
+                   const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz,
+                   uint32_t* max_nnz, uint32_t* overflow_flag, cudaStream_t s);
 
 }  // namespace pgb_rows

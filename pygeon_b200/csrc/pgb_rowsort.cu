@@ -11,7 +11,7 @@ using namespace pgb_rows;
 // Output per row: the sorted unique columns (scratch, compacted later), and for every candidate
 // the index of its column among them ("slot", uint8): slots[(row_start[r] + q)*L + b].
 template <int G, int ITEMS, int L, typename KeyT>
-__global__ void __launch_bounds__(256) k_rowsort(int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start,
+__global__ void __launch_bounds__(256) k_rowsort(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start,
                                                  const uint32_t* __restrict__ inc_sorted,
                                                  const int32_t* __restrict__ dofs, uint8_t* __restrict__ slots,
                                                  int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz,
@@ -24,8 +24,8 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t row0, int64_t n_rows, c
   __shared__ uint32_t wmax[8];
   const int lane = threadIdx.x & 31;
   const int gl = lane % G;  // lane within the group
-  const int64_t r = row0 + ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;  // rows [row0, n_rows)
-  const bool live = r < n_rows;
+  bool live;
+  const int64_t r = pick_row(rows, row0, n_rows, ((int64_t)blockIdx.x * 256 + threadIdx.x) / G, live);
   uint32_t rs = 0, re = 0;
   if (live) {
     rs = row_start[r];
@@ -126,13 +126,13 @@ __global__ void __launch_bounds__(256) k_rowsort(int64_t row0, int64_t n_rows, c
 }
 
 template <int G, int ITEMS, typename KeyT>
-int launch_rowsort_l(int L, int64_t row0, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
+int launch_rowsort_l(int L, const uint32_t* rows, int64_t row0, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
                      uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
   char name[64];
   snprintf(name, sizeof(name), "k_rowsort<%d,%d,%d,%s>", G, ITEMS, L, sizeof(KeyT) == 4 ? "u32" : "u64");
   note_row_kernel(name);
   unsigned grid = pgb_grid((n_rows - row0) * G, 256);
-#define PGB_RL(LL) k_rowsort<G, ITEMS, LL, KeyT><<<grid, 256, 0, s>>>(row0, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz)
+#define PGB_RL(LL) k_rowsort<G, ITEMS, LL, KeyT><<<grid, 256, 0, s>>>(rows, row0, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz)
   switch (L) {
     case 3: PGB_RL(3); break;
     case 4: PGB_RL(4); break;
@@ -148,12 +148,12 @@ int launch_rowsort_l(int L, int64_t row0, int64_t n_rows, const uint32_t* row_st
 }
 
 template <int G, int ITEMS>
-int launch_rowsort_k(int L, int64_t row0, int64_t row1, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
+int launch_rowsort_k(int L, const uint32_t* rows, int64_t row0, int64_t row1, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc, const int32_t* dofs,
                      uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s) {
   // 32-bit keys when (col, position-in-row) fits strictly below the padding value 0xffffffff
   if ((uint64_t)n_rows * (uint64_t)(G * ITEMS) <= 0xffffffffull && !g_force_key64)
-    return launch_rowsort_l<G, ITEMS, uint32_t>(L, row0, row1, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
-  return launch_rowsort_l<G, ITEMS, uint64_t>(L, row0, row1, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
+    return launch_rowsort_l<G, ITEMS, uint32_t>(L, rows, row0, row1, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
+  return launch_rowsort_l<G, ITEMS, uint64_t>(L, rows, row0, row1, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s);
 }
 
 
@@ -170,10 +170,11 @@ void note_row_kernel(const char* name) {
   snprintf(g_row_kernel + len, sizeof(g_row_kernel) - len, "%s%s", len ? "+" : "", name);
 }
 
-int launch_rowsort(uint32_t max_cand, int L, int64_t row0, int64_t row1, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc,
+int launch_rowsort(uint32_t max_cand, int L, const uint32_t* rows, int64_t row0, int64_t row1, int64_t n_rows,
+                   const uint32_t* row_start, const uint32_t* inc,
                    const int32_t* dofs, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
                    cudaStream_t s) {
-#define PGB_RS(G, I) return launch_rowsort_k<G, I>(L, row0, row1, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s)
+#define PGB_RS(G, I) return launch_rowsort_k<G, I>(L, rows, row0, row1, n_rows, row_start, inc, dofs, slots, ucol, row_nnz, max_nnz, s)
   if (max_cand <= 8) PGB_RS(4, 2);
   if (max_cand <= 16) PGB_RS(8, 2);
   if (max_cand <= 32) PGB_RS(8, 4);

@@ -58,7 +58,10 @@ CASES = [
     (3, 6000, 2500, 30, "k_rowhash<32,1,3,128>"),      # k_rowhash 32 lanes, table 128
     (3, 6000, 2500, 80, "k_rowhash<32,4,3,512>"),      # k_rowhash 32 lanes x 4, table 512
     (3, 6000, 2500, 150, "k_rowsort<32,16,3"),     # k_row_canon + k_rowsort (450 candidates)
-    (3, 6000, 2500, 200, ""),     # > 512 candidates: full-sort fallback
+    (3, 6000, 2500, 200, "k_rowlong<3>"),  # > 512 candidates: one block per row
+    (3, 6000, 2500, 300, "k_rowlong<3>"),  # > 255 incidences: saturated ranks take the overflow counter
+    (4, 9000, 2500, 700, "k_rowlong<4>"),
+    (3, 9000, 2500, 2100, ""),             # > 2048 incidences: full-sort fallback
     (4, 3000, 9000, 2, "k_rowthread<"),       # k_rowthread MI=2
     (4, 3000, 4000, 4, "k_rowthread<"),
     (4, 5000, 2500, 16, "k_rowthread<16,4,64"),      # k_rowthread MI=16, 64 keys
@@ -131,5 +134,5 @@ def test_random_tables_all_modes(L, nc, n_rows, hub, kernel):
             data = engine.numeric(plan, vd.reshape(nc, L * L).contiguous())
         err = np.abs(data.cpu().numpy() - ref.data).max()
         assert err <= 1e-13 * np.abs(ref.data).max(), (mode, err)
-    if hub * L <= 512 and hub <= 256 and np.diff(ref.indptr).max() <= 255:
+    if hub <= 2048 and np.diff(ref.indptr).max() <= 255:
         assert first is not None  # the two-level path did run

@@ -549,8 +549,10 @@ template <int L>
 __device__ __forceinline__ void load_row(const double* __restrict__ p, double (&v)[L]) {
   if constexpr (L % 4 == 0) {
 #pragma unroll
-    for (int b = 0; b < L; b += 4)  // LDG.E.256
-      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+    // LDG.E.256, read once: no L1 allocation (P1 128^3: 0.50 -> 0.43 ms, N0 1.97 -> 1.62 ms).  The same
+    // hint on the narrow loads (slot words here, SpMV values / indices, K1 ids) is 20-140 % SLOWER.
+    for (int b = 0; b < L; b += 4)
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
                    : "=d"(v[b]), "=d"(v[b + 1]), "=d"(v[b + 2]), "=d"(v[b + 3])
                    : "l"(p + b));
   } else if constexpr (L % 2 == 0) {

@@ -84,6 +84,39 @@ int pgb_pack_l2_dofs(int dim, int64_t nc, int64_t nn, const int32_t* cell_nodes,
 int pgb_prep_coords(int dim, int64_t nn, const double* nodes, const double* R_host,
                     double* coords, void* stream);
 
+/* ---- grid connectivity / geometry on the device --------------
+ * Ridges of a 3D simplicial grid, replacing Grid._compute_ridges_3d (grids/grid.py:149-216):
+ * ridges = the distinct sorted node pairs of all faces numbered lexicographically
+ * (coo sum_duplicates order, grid.py:187-198); face f holds the ridges (n0,n1), (n1,n2), (n2,n0) of
+ * its node order in face_nodes.indices with orientation sign(next - prev) (grid.py:172-182).
+ *   face_nodes      [nf][3]   face_nodes.indices
+ *   face_ridges     [nf][3]   out: face_ridges.indices (slot order = face node order)
+ *   face_ridge_sign [nf][3]   out: face_ridges.data as int8
+ *   ridge_peaks     [3*nf][2] out (capacity): ridge_peaks.indices = (lo, hi) node of every ridge
+ *                             (ridge_peaks.data = (-1, +1)); the first *num_ridges_host rows are valid
+ * Synchronises the stream (the ridge count is returned to the host).  Error (return 2) when a face
+ * repeats a node or a node id lies outside [0, num_nodes). */
+int64_t pgb_ridges3d_workspace_bytes(int64_t nf);
+int pgb_ridges3d(int64_t nf, int64_t num_nodes, const int32_t* face_nodes, int32_t* face_ridges,
+                 int8_t* face_ridge_sign, int32_t* ridge_peaks, int64_t* num_ridges_host,
+                 void* workspace, int64_t workspace_bytes, void* stream);
+/* Metric quantities of pp.Grid.compute_geometry for simplices (called from grids/grid.py:59), all
+ * (3, n) row-major like the grid attributes: face_normals (tied to the stored node order: 2D
+ * (t_y, -t_x, 0), 3D (x1-x0) x (x2-x0) / 2), face_areas, face_centers, cell_centers, cell_volumes.
+ * cell_nodes = the table of pgb_pack_cells.  cf_sgn may be NULL; otherwise *err_flag is set to 1 when
+ * a cell_faces sign is not the side of the cell the normal points to. */
+int pgb_grid_geometry(int dim, int64_t nc, int64_t nf, int64_t nn, const double* nodes,
+                      const int32_t* cf_idx, const int8_t* cf_sgn, const int32_t* fn_idx,
+                      const int32_t* cell_nodes, double* face_normals, double* face_areas,
+                      double* face_centers, double* cell_centers, double* cell_volumes,
+                      int32_t* err_flag, void* stream);
+/* Grid.compute_edge_properties (grids/grid.py:311-337): edge_tangents (3, ne) = nodes @ edge_nodes,
+ * edge_lengths.  edge_nodes [ne][2] = ridge_peaks.indices (3D) / face_ridges.indices (2D);
+ * edge_signs [ne][2] = the matching .data as int8, or NULL for (-1, +1). */
+int pgb_edge_geometry(int64_t ne, int64_t nn, const double* nodes, const int32_t* edge_nodes,
+                      const int8_t* edge_signs, double* edge_tangents, double* edge_lengths,
+                      void* stream);
+
 /* ---- K1: per-cell local matrices ------------------------------------------------
  * One thread per cell, fp64.  vals is [nc][L*L] row-major (local row a, local col b).
  * Replaces the implicit local matrices of Discretization._assemble_inner_product

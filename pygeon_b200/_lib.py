@@ -34,6 +34,10 @@ _SIGS = {
     "pgb_pack_edges3d": (_i, [_l, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pgb_pack_edges2d": (_i, [_l, _p, _p, _p, _p, _p]),
     "pgb_prep_coords": (_i, [_i, _l, _p, _p, _p, _p]),
+    "pgb_ridges3d_workspace_bytes": (_l, [_l]),
+    "pgb_ridges3d": (_i, [_l, _l, _p, _p, _p, _p, C.POINTER(C.c_int64), _p, _l, _p]),
+    "pgb_grid_geometry": (_i, [_i, _l, _l, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pgb_edge_geometry": (_i, [_l, _l, _p, _p, _p, _p, _p, _p]),
     "pgb_local_size": (_i, [_i, _i]),
     "pgb_local_matrices": (_i, [_i, _i, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pgb_csr_workspace_bytes": (_l, [_l, _i, _l, _i]),

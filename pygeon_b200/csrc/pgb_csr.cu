@@ -1315,3 +1315,113 @@ extern "C" int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t
   PGB_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- grid connectivity: ridges of a 3D simplicial grid (grids/grid.py:149-216) --------------------
+// The reference numbers the ridges (edges) as the distinct sorted node pairs of all faces in
+// lexicographic order (coo.sum_duplicates() of A[lo, hi], grid.py:187-198) and gives face f the
+// ridges (n0,n1), (n1,n2), (n2,n0) of its node order with orientation sign(next - prev)
+// (grid.py:172-182).  Here: one packed key (lo << cb | hi) per (face, slot), the stable LSD radix
+// sort of this file with the position as payload, head flags + exclusive scan = ridge id.
+namespace {
+
+__global__ void __launch_bounds__(256) k_ridge_keys(uint32_t n, const int32_t* __restrict__ fn, int cb,
+                                                    uint64_t* __restrict__ keys, int8_t* __restrict__ sign,
+                                                    int32_t num_nodes, int32_t* __restrict__ err) {
+  uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= n) return;
+  uint32_t f = i / 3u, j = i - 3u * f;
+  int32_t a = fn[i];
+  int32_t b = fn[3u * f + (j == 2u ? 0u : j + 1u)];
+  if (a == b || a < 0 || b < 0 || a >= num_nodes || b >= num_nodes) *err = 1;  // degenerate face / id out of range
+  uint32_t lo = (uint32_t)min(a, b), hi = (uint32_t)max(a, b);
+  keys[i] = ((uint64_t)lo << cb) | (uint64_t)hi;
+  sign[i] = (int8_t)((b > a) - (b < a));
+}
+
+__global__ void __launch_bounds__(256) k_ridge_heads(uint32_t n, const uint64_t* __restrict__ keys,
+                                                     uint32_t* __restrict__ head) {
+  uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i < n) head[i] = is_head(keys, i) ? 1u : 0u;
+}
+
+// head_ex[i] = number of heads before position i  =>  ridge id of position i = head_ex[i] - !is_head(i)
+__global__ void __launch_bounds__(256) k_ridge_emit(uint32_t n, const uint64_t* __restrict__ keys,
+                                                    const uint32_t* __restrict__ pos,
+                                                    const uint32_t* __restrict__ head_ex, int cb,
+                                                    int32_t* __restrict__ face_ridges,
+                                                    int32_t* __restrict__ ridge_peaks) {
+  uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = keys[i];
+  const bool h = (i == 0) || keys[i - 1] != k;
+  const uint32_t id = head_ex[i] - (h ? 0u : 1u);
+  face_ridges[pos[i]] = (int32_t)id;
+  if (h) {
+    ridge_peaks[2 * (uint64_t)id] = (int32_t)(k >> cb);
+    ridge_peaks[2 * (uint64_t)id + 1] = (int32_t)(k & ((1ull << cb) - 1));
+  }
+}
+
+struct RidgeWs {
+  int64_t keys_a, keys_b, pay_a, pay_b, hist, parts, meta, total;
+};
+RidgeWs ridge_ws(int64_t n) {
+  auto al = [](int64_t x) { return (x + 255) / 256 * 256; };
+  RidgeWs l = {};
+  int64_t o = 0;
+  l.meta = o;   o += 256;  // [0] number of ridges, [1] error flag
+  l.parts = o;  o += al(2048 * 4);
+  l.hist = o;   o += al(pgb_cdiv(n > 0 ? n : 1, SORT_TILE) * RADIX * 4);
+  l.keys_a = o; o += al(n * 8);
+  l.keys_b = o; o += al(n * 8);
+  l.pay_a = o;  o += al(n * 4);
+  l.pay_b = o;  o += al(n * 4);
+  l.total = o;
+  return l;
+}
+
+}  // namespace
+
+extern "C" int64_t pgb_ridges3d_workspace_bytes(int64_t nf) { return ridge_ws(3 * nf).total; }
+
+extern "C" int pgb_ridges3d(int64_t nf, int64_t num_nodes, const int32_t* face_nodes, int32_t* face_ridges,
+                            int8_t* face_ridge_sign, int32_t* ridge_peaks, int64_t* num_ridges_host,
+                            void* workspace, int64_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = 3 * nf;
+  *num_ridges_host = 0;
+  if (nf == 0) return 0;
+  PGB_REQUIRE(n < ((int64_t)1 << 32) - SORT_TILE, "pgb_ridges3d: 3*num_faces must be < 2^32");
+  PGB_REQUIRE(num_nodes > 0 && num_nodes < ((int64_t)1 << 31), "pgb_ridges3d: num_nodes out of range");
+  RidgeWs l = ridge_ws(n);
+  PGB_REQUIRE(workspace_bytes >= l.total, "pgb_ridges3d: workspace too small");
+  char* ws = (char*)workspace;
+  uint32_t* meta = (uint32_t*)(ws + l.meta);
+  uint32_t* parts = (uint32_t*)(ws + l.parts);
+  uint32_t* hist = (uint32_t*)(ws + l.hist);
+  uint64_t* kbuf[2] = {(uint64_t*)(ws + l.keys_a), (uint64_t*)(ws + l.keys_b)};
+  uint32_t* pbuf[2] = {(uint32_t*)(ws + l.pay_a), (uint32_t*)(ws + l.pay_b)};
+  const int cb = bits_for(num_nodes);
+  const int passes = (2 * cb + RADIX_BITS - 1) / RADIX_BITS;
+  PGB_CHECK(cudaMemsetAsync(meta, 0, 256, s));
+  // the first pass reads its keys from the buffer the last pass does NOT write into
+  uint64_t* keys_in = kbuf[(passes % 2 == 1) ? 1 : 0];
+  const unsigned g = pgb_grid(n, 256);
+  k_ridge_keys<<<g, 256, 0, s>>>((uint32_t)n, face_nodes, cb, keys_in, face_ridge_sign, (int32_t)num_nodes,
+                                 (int32_t*)(meta + 1));
+  PGB_LAUNCH_CHECK();
+  KeySrc<uint64_t> src{keys_in, nullptr, 0u, 0u, cb};
+  if (radix_sort<uint64_t>(src, (uint32_t)n, 2 * cb, kbuf, pbuf, hist, parts, s)) return 1;
+  uint32_t* head = pbuf[1];  // free after the sort (sorted keys / positions are in kbuf[0] / pbuf[0])
+  k_ridge_heads<<<g, 256, 0, s>>>((uint32_t)n, kbuf[0], head);
+  PGB_LAUNCH_CHECK();
+  if (scan_u32(head, (uint64_t)n, parts, meta, s)) return 1;
+  k_ridge_emit<<<g, 256, 0, s>>>((uint32_t)n, kbuf[0], pbuf[0], head, cb, face_ridges, ridge_peaks);
+  PGB_LAUNCH_CHECK();
+  uint32_t m[2] = {0, 0};
+  PGB_CHECK(cudaMemcpyAsync(m, meta, sizeof(m), cudaMemcpyDeviceToHost, s));
+  PGB_CHECK(cudaStreamSynchronize(s));
+  PGB_REQUIRE(m[1] == 0, "pgb_ridges3d: a face repeats a node or holds a node id outside [0, num_nodes)");
+  *num_ridges_host = (int64_t)m[0];
+  return 0;
+}

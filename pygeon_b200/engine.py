@@ -218,6 +218,10 @@ class RawGrid:
         if self.fr_idx is not None:
             return
         sd, dev, d = self._sd, self.device, self.dim
+        cached = getattr(sd, "_device_ridges", None)  # left by SimplexGrid.compute_*(device=...)
+        if d == 3 and cached is not None and cached[0].device == dev and cached[2].shape[0] == self.ne:
+            self.fr_idx, self.fr_sgn, self.rp_idx = (t.reshape(-1) for t in cached)
+            return
         fr = sd.face_ridges
         with torch.cuda.device(dev):
             if d == 2:

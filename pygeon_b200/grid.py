@@ -92,19 +92,25 @@ class SimplexGrid:
     def num_cell_nodes(self) -> np.ndarray:
         return np.diff(self.cell_nodes().indptr)
 
-    def compute_connectivity(self) -> None:
+    def compute_connectivity(self, device=None) -> None:
         """Ridges / peaks only (no metric quantities): what the assembly engine reads besides
-        ``nodes``, ``cell_faces`` and ``face_nodes``.  Cheap enough for 10^8-cell grids."""
+        ``nodes``, ``cell_faces`` and ``face_nodes``.  Cheap enough for 10^8-cell grids.
+        With a CUDA ``device`` the ridges of an unstructured 3D grid are numbered by
+        ``pgb_ridges3d`` (:mod:`pygeon_b200.connectivity`) instead of numpy."""
         self.rotation_matrix = np.eye(self.dim, AMBIENT_DIM)
         self.tags.setdefault("domain_boundary_faces", np.bincount(self.cell_faces.indices, minlength=self.num_faces) == 1)
-        self._compute_ridges()
+        self._compute_ridges(device)
         self.num_edges = self.num_faces if self.dim == 2 else self.num_ridges
 
-    def compute_geometry(self) -> None:
-        """Geometry + ridges/peaks + edge properties (``grid.py:39-64``)."""
+    def compute_geometry(self, device=None) -> None:
+        """Geometry + ridges/peaks + edge properties (``grid.py:39-64``).  With a CUDA ``device``
+        every step runs in libpgb.so kernels (:mod:`pygeon_b200.connectivity`) and only the results
+        come back to the host attributes; without one, numpy."""
         d = self.dim
         if d not in (2, 3):
             raise NotImplementedError("SimplexGrid supports dim 2 and 3")
+        if device is not None:
+            return self._compute_geometry_device(device)
         x = self.nodes
         if np.any(np.diff(self.face_nodes.indptr) != d):
             raise NotImplementedError("faces must be simplices")
@@ -149,9 +155,73 @@ class SimplexGrid:
         self._compute_edge_properties()
         self._geometry_done = True
 
+    def _compute_geometry_device(self, device) -> None:
+        from . import connectivity, engine
+
+        d, nc, nf = self.dim, self.num_cells, self.num_faces
+        if np.any(self.nodes[d:, :]):
+            raise NotImplementedError("tilted grids need pp.map_geometry (not available)")
+        self.rotation_matrix = np.eye(d, AMBIENT_DIM)
+        raw = engine.RawGrid.upload(self, device, signs=True)
+        pack = engine.GridPack.from_raw(raw)  # NotImplementedError for non-simplicial grids
+        dev = raw.device
+        with torch.cuda.device(dev):
+            if raw.nodes_ready is not None:
+                torch.cuda.current_stream().wait_event(raw.nodes_ready)
+            cf, fn = raw.cf_idx.view(nc, d + 1), raw.fn_idx.view(nf, d)
+            geo = connectivity.geometry(d, raw.nodes, cf, raw.cf_sgn.view(nc, d + 1), fn, pack.cell_nodes)
+            bnd = torch.bincount(raw.cf_idx.long(), minlength=nf) == 1
+            bn = torch.zeros(self.num_nodes, dtype=torch.bool, device=dev)
+            bn[fn[bnd].reshape(-1).long()] = True
+            for k, v in geo.items():
+                setattr(self, k, v.cpu().numpy())
+            self.tags["domain_boundary_faces"] = bnd.cpu().numpy()
+            self.tags["domain_boundary_nodes"] = bn.cpu().numpy()
+        self.tags["tip_faces"] = np.zeros(nf, dtype=bool)
+        self.tags["fracture_faces"] = np.zeros(nf, dtype=bool)
+        self._compute_ridges(dev)
+        with torch.cuda.device(dev):
+            if d == 2:
+                en, es = raw.fn_idx.view(nf, 2), _i8(self.face_ridges.data, dev).view(nf, 2)
+            else:
+                dr = getattr(self, "_device_ridges", None)  # absent for the structured generators
+                en = dr[2] if dr is not None else engine._to_dev(self.ridge_peaks.indices, dev, torch.int32).view(-1, 2)
+                es = None
+            t, ln = connectivity.edge_geometry(raw.nodes, en, es)
+            self.edge_tangents, self.edge_lengths = t.cpu().numpy(), ln.cpu().numpy()
+            self.num_edges = self.edge_lengths.size
+            self.mesh_size = float(ln.mean().item()) if ln.numel() else 0.0
+        self._geometry_done = True
+
     # ------------------------------------------------------------------ pg.Grid
-    def _compute_ridges(self) -> None:
+    def _compute_ridges_device(self, device) -> None:
+        """3D ridges through ``pgb_ridges3d``; keeps the device tensors for the assembly engine
+        (``RawGrid.need_ridges`` then uploads nothing)."""
+        from . import connectivity, engine
+
+        dev = engine._device(device)
+        if np.any(np.diff(self.face_nodes.indptr) != 3):
+            raise NotImplementedError("faces must be simplices")
+        with torch.cuda.device(dev):
+            fn = engine._to_dev(self.face_nodes.indices, dev, torch.int32).view(self.num_faces, 3)
+            fr, fs, rp = connectivity.ridges3d(fn, self.num_nodes)
+            self._device_ridges = (fr, fs, rp)
+            bnd = engine._to_dev(self.tags["domain_boundary_faces"], dev)
+            br = torch.zeros(rp.shape[0], dtype=torch.bool, device=dev)
+            br[fr[bnd].reshape(-1).long()] = True
+            fr_h, fs_h, rp_h, br_h = fr.cpu().numpy(), fs.cpu().numpy(), rp.cpu().numpy(), br.cpu().numpy()
+        self.num_peaks = self.num_nodes
+        self.num_ridges = rp_h.shape[0]
+        self.ridge_peaks = _csc_from_rows(rp_h, np.tile(np.array([-1, 1]), rp_h.shape[0]).reshape(-1, 2), self.num_nodes)
+        self.face_ridges = _csc_from_rows(fr_h, fs_h.astype(int), self.num_ridges)
+        self.tags["tip_peaks"] = np.zeros(self.num_peaks, dtype=bool)
+        self.tags["tip_ridges"] = np.zeros(self.num_ridges, dtype=bool)
+        self.tags["domain_boundary_ridges"] = br_h
+
+    def _compute_ridges(self, device=None) -> None:
         d = self.dim
+        if device is not None and d == 3 and not getattr(self, "_structured", None):
+            return self._compute_ridges_device(device)
         if d == 2:
             self.num_peaks = 0
             self.num_ridges = self.num_nodes
@@ -389,6 +459,10 @@ def structured_connectivity(dim: int, n: int, device="cpu", nz: int | None = Non
         out["face_ridges"] = torch.stack(fr, dim=1).to(torch.int32).contiguous()
         out["face_ridge_sign"] = torch.stack(fs, dim=1).contiguous()
     return out
+
+
+def _i8(data: np.ndarray, dev) -> torch.Tensor:
+    return torch.from_numpy(np.sign(np.asarray(data)).astype(np.int8)).to(dev)
 
 
 def _csc_from_rows(idx: np.ndarray, data: np.ndarray, nrows: int) -> sps.csc_array:

@@ -15,6 +15,7 @@ SOURCES = ["pgb_api.cu", "pgb_pack.cu", "pgb_local.cu", "pgb_csr.cu", "pgb_rowso
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", f"-I{INCLUDE}", f"-I{CSRC}",
+    *os.environ.get("PGB_NVCC_EXTRA", "").split(),  # A/B builds of a tuning macro (-DPGB_...)
 ]
 
 

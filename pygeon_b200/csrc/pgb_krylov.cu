@@ -16,6 +16,10 @@ namespace {
 constexpr int KB = 256;  // threads per block for all Krylov kernels
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NPART = PGB_NPART;
+#ifndef PGB_VU
+#define PGB_VU 4
+#endif
+constexpr int VU = PGB_VU;  // grid strides whose loads a vector kernel issues before it computes
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -40,6 +44,39 @@ __device__ __forceinline__ double sum_partials(const double* __restrict__ parts,
   double s = 0;
   for (int i = threadIdx.x; i < NPART; i += KB) s += parts[i];
   return block_sum(s, ws);
+}
+
+// N sums at once: the same per-value order as block_sum / sum_partials (bit-identical results), but
+// one pair of barriers and overlapped loads instead of N of each.  ws: N * KB/32 doubles.
+template <int N>
+__device__ __forceinline__ void block_sum_n(double (&v)[N], double* ws) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = warp_sum(v[j]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) ws[j * (KB / 32) + w] = v[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < KB / 32; ++i) s += ws[j * (KB / 32) + i];
+    v[j] = s;
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void sum_partials_n(const double* const (&parts)[N], double (&out)[N], double* ws) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) out[j] = 0;
+  for (int i = threadIdx.x; i < NPART; i += KB) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) out[j] += parts[j][i];
+  }
+  block_sum_n<N>(out, ws);
 }
 
 __device__ __forceinline__ void write_partial(double* parts, double v) {
@@ -262,11 +299,12 @@ __global__ void __launch_bounds__(KB) k_cg_p(int64_t n, int k, const double* __r
                                              const double* __restrict__ dinv, double* __restrict__ p,
                                              const double* p_rr, const double* p_rho, const double* p_bb,
                                              CgScal* sc, double* resid, volatile int* host_flag) {
-  __shared__ double ws[KB / 32];
+  __shared__ double ws[3 * (KB / 32)];
   if (sc->done) return;
-  double rr = sum_partials(p_rr, ws);
-  double rho = sum_partials(p_rho, ws);
-  double bb = sum_partials(p_bb, ws);
+  const double* const parts[3] = {p_rr, p_rho, p_bb};
+  double red[3];
+  sum_partials_n<3>(parts, red, ws);
+  const double rr = red[0], rho = red[1], bb = red[2];
   double rnorm = sqrt(rr);
   double atol = fmax(sc->atol_user, sc->rtol * sqrt(bb));
   bool done = rnorm < atol;
@@ -284,9 +322,25 @@ __global__ void __launch_bounds__(KB) k_cg_p(int64_t n, int k, const double* __r
   }
   if (done) return;
   double beta = (k > 0) ? rho / sc->rho_prev : 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB) {
-    double z = dinv ? dinv[i] * r[i] : r[i];
-    p[i] = (k > 0) ? z + beta * p[i] : z;
+  const int64_t st = (int64_t)gridDim.x * KB;
+  for (int64_t i0 = (int64_t)blockIdx.x * KB + threadIdx.x; i0 < n; i0 += VU * st) {
+    double rv[VU], pv[VU], dv[VU];
+#pragma unroll
+    for (int u = 0; u < VU; ++u) {  // all loads of VU grid strides first (memory-level parallelism)
+      const int64_t i = i0 + u * st;
+      const bool ok = i < n;
+      rv[u] = ok ? r[i] : 0.0;
+      pv[u] = (ok && k > 0) ? p[i] : 0.0;
+      dv[u] = (ok && dinv) ? dinv[i] : 1.0;
+    }
+#pragma unroll
+    for (int u = 0; u < VU; ++u) {
+      const int64_t i = i0 + u * st;
+      if (i < n) {
+        double z = dinv ? dv[u] * rv[u] : rv[u];
+        p[i] = (k > 0) ? z + beta * pv[u] : z;
+      }
+    }
   }
 }
 
@@ -296,20 +350,41 @@ __global__ void __launch_bounds__(KB) k_cg_xr(int64_t n, const double* __restric
                                               double* __restrict__ r, const double* p_pq, double* p_rr,
                                               double* p_rho, CgScal* sc) {
   __shared__ double ws[KB / 32];
+  __shared__ double ws2[2 * (KB / 32)];
   if (sc->done) return;
   double pq = sum_partials(p_pq, ws);
   double rho_cur = sc->rho;
   double alpha = rho_cur / pq;
   double rr = 0, rho = 0;
-  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB) {
-    x[i] += alpha * p[i];
-    double ri = r[i] - alpha * q[i];
-    r[i] = ri;
-    rr += ri * ri;
-    rho += ri * (dinv ? dinv[i] * ri : ri);
+  const int64_t st = (int64_t)gridDim.x * KB;
+  for (int64_t i0 = (int64_t)blockIdx.x * KB + threadIdx.x; i0 < n; i0 += VU * st) {
+    double pv[VU], qv[VU], xv[VU], rv[VU], dv[VU];
+#pragma unroll
+    for (int u = 0; u < VU; ++u) {
+      const int64_t i = i0 + u * st;
+      const bool ok = i < n;
+      pv[u] = ok ? p[i] : 0.0;
+      qv[u] = ok ? q[i] : 0.0;
+      xv[u] = ok ? x[i] : 0.0;
+      rv[u] = ok ? r[i] : 0.0;
+      dv[u] = (ok && dinv) ? dinv[i] : 1.0;
+    }
+#pragma unroll
+    for (int u = 0; u < VU; ++u) {  // same per-thread summation order as a plain grid-stride loop
+      const int64_t i = i0 + u * st;
+      if (i < n) {
+        x[i] = xv[u] + alpha * pv[u];
+        double ri = rv[u] - alpha * qv[u];
+        r[i] = ri;
+        rr += ri * ri;
+        rho += ri * (dinv ? dv[u] * ri : ri);
+      }
+    }
   }
-  write_partial(p_rr, block_sum(rr, ws));
-  write_partial(p_rho, block_sum(rho, ws));
+  double red[2] = {rr, rho};
+  block_sum_n<2>(red, ws2);
+  write_partial(p_rr, red[0]);
+  write_partial(p_rho, red[1]);
   if (blockIdx.x == 0 && threadIdx.x == 0) sc->rho_prev = rho_cur;
 }
 
@@ -354,10 +429,26 @@ __global__ void __launch_bounds__(KB) k_mr_c(int64_t n, double* __restrict__ y, 
   double alfa = sum_partials(p_alfa, ws);
   double c = alfa / sc->beta;
   double bt = 0;
-  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB) {
-    double yi = y[i] - c * r2[i];
-    y[i] = yi;
-    bt += yi * (dinv ? dinv[i] * yi : yi);
+  const int64_t st = (int64_t)gridDim.x * KB;
+  for (int64_t i0 = (int64_t)blockIdx.x * KB + threadIdx.x; i0 < n; i0 += VU * st) {
+    double yv[VU], r2v[VU], dv[VU];
+#pragma unroll
+    for (int u = 0; u < VU; ++u) {
+      const int64_t i = i0 + u * st;
+      const bool ok = i < n;
+      yv[u] = ok ? y[i] : 0.0;
+      r2v[u] = ok ? r2[i] : 0.0;
+      dv[u] = (ok && dinv) ? dinv[i] : 1.0;
+    }
+#pragma unroll
+    for (int u = 0; u < VU; ++u) {
+      const int64_t i = i0 + u * st;
+      if (i < n) {
+        double yi = yv[u] - c * r2v[u];
+        y[i] = yi;
+        bt += yi * (dinv ? dv[u] * yi : yi);
+      }
+    }
   }
   write_partial(p_beta, block_sum(bt, ws));
   if (blockIdx.x == 0 && threadIdx.x == 0) sc->alfa = alfa;
@@ -454,13 +545,32 @@ __global__ void __launch_bounds__(KB) k_mr_d(int64_t n, double* __restrict__ v, 
   if (sc->done) return;
   double oldeps = sc->oldeps, delta = sc->delta, denom = sc->denom, phi = sc->phi, ib = sc->inv_beta;
   double xx = 0;
-  for (int64_t i = (int64_t)blockIdx.x * KB + threadIdx.x; i < n; i += (int64_t)gridDim.x * KB) {
-    double wn = (v[i] - oldeps * w1[i] - delta * w2[i]) * denom;
-    w1[i] = wn;
-    double xi = x[i] + phi * wn;
-    x[i] = xi;
-    xx += xi * xi;
-    v[i] = (dinv ? dinv[i] * r2[i] : r2[i]) * ib;
+  const int64_t st = (int64_t)gridDim.x * KB;
+  for (int64_t i0 = (int64_t)blockIdx.x * KB + threadIdx.x; i0 < n; i0 += VU * st) {
+    double vv[VU], w1v[VU], w2v[VU], r2v[VU], xv[VU], dv[VU];
+#pragma unroll
+    for (int u = 0; u < VU; ++u) {
+      const int64_t i = i0 + u * st;
+      const bool ok = i < n;
+      vv[u] = ok ? v[i] : 0.0;
+      w1v[u] = ok ? w1[i] : 0.0;
+      w2v[u] = ok ? w2[i] : 0.0;
+      r2v[u] = ok ? r2[i] : 0.0;
+      xv[u] = ok ? x[i] : 0.0;
+      dv[u] = (ok && dinv) ? dinv[i] : 1.0;
+    }
+#pragma unroll
+    for (int u = 0; u < VU; ++u) {
+      const int64_t i = i0 + u * st;
+      if (i < n) {
+        double wn = (vv[u] - oldeps * w1v[u] - delta * w2v[u]) * denom;
+        w1[i] = wn;
+        double xi = xv[u] + phi * wn;
+        x[i] = xi;
+        xx += xi * xi;
+        v[i] = (dinv ? dv[u] * r2v[u] : r2v[u]) * ib;
+      }
+    }
   }
   write_partial(p_xx, block_sum(xx, ws));
 }

@@ -79,6 +79,13 @@ int pgb_pack_edges2d(int64_t nc, const int32_t* cf_idx, const int32_t* fr_idx,
  * = cell_faces indices) or [nc][6] ridge ids of the cell in any order (3D, from pgb_pack_edges3d). */
 int pgb_pack_l2_dofs(int dim, int64_t nc, int64_t nn, const int32_t* cell_nodes,
                      const int32_t* cell_edges, int32_t* dofs, void* stream);
+/* RT1 cell -> dof table [nc][d(d+2)] in the reference's local order (RT1.local_dofs_of_cell +
+ * reorder_faces, fem/hdiv.py:534-552,629-674): with the cell's nodes ranked by ascending id, dof
+ * q < d(d+1) = (face opposite the node of rank d - q % (d+1)) + (q / (d+1)) * nf, then
+ * d*nf + k*nc + c for k < d.  aux_bits[c]: bits 2r..2r+1 = face slot whose opposite node has rank r,
+ * bit 8+r = 1 when the cell_faces sign of that face is -1. */
+int pgb_pack_rt1(int dim, int64_t nc, int64_t nf, const int32_t* cf_idx, const int32_t* cell_nodes,
+                 const uint8_t* sign_bits, int32_t* cell_dofs, uint32_t* aux_bits, void* stream);
 /* coords[nn][4] (3D, padded) or [nn][2] (2D) = R @ nodes, nodes given as (3, nn) row-major
  * (sd.nodes), R = sd.rotation_matrix (d x 3, host pointer). */
 int pgb_prep_coords(int dim, int64_t nn, const double* nodes, const double* R_host,
@@ -151,8 +158,12 @@ enum {
   PGB_L2_MASS = 14,     /* Lagrange2 mass (h1.py:352-392 through discretization.py:112-136): w|c| (phi_i, phi_j),
                            phi = lambda_i(2 lambda_i - 1) for the d+1 nodes, 4 lambda_p lambda_q for the edges
                            (p,q) = (0,1),(0,2)[,(0,3)],(1,2)[,(1,3),(2,3)]              L = (d+1) + d(d+1)/2 */
-  PGB_L2_STIFF = 15     /* Lagrange2 stiffness (h1.py:545-599): |c| sum_jl Mhat_jl grad phi_i(x_j)^T K
+  PGB_L2_STIFF = 15,    /* Lagrange2 stiffness (h1.py:545-599): |c| sum_jl Mhat_jl grad phi_i(x_j)^T K
                            grad phi_k(x_l); pg.WEIGHT is not read (as the reference)   L = (d+1) + d(d+1)/2 */
+  PGB_RT1_MASS = 16     /* RT1 mass (hdiv.py:555-621, a Python loop over the cells): |c| Psi (M2 x K) Psi^T with the
+                           P2 local mass M2 and the nodal values Psi of the basis (hdiv.py:676-744), evaluated as a
+                           constant contraction of the Gram matrix of the cell's edge vectors (pgb_rt1_table.cuh);
+                           pg.WEIGHT is not read; aux_bits from pgb_pack_rt1            L = d(d+2) */
 };
 int pgb_local_size(int kind, int dim); /* L */
 /* dst_pos (nullable): [nc*L] destination row of every local row (the inc_pos of a mode-0 plan);

@@ -597,7 +597,99 @@ def local_lagrange2_stiff(sd, tabs, w, K):
     return A, lagrange2_dofs(sd, tabs)
 
 
+# ---- RT1 (the reference's per-cell Python loop, fem/hdiv.py:555-760) --------
+def rt1_point_coefficients(d):
+    """Nodal values of the RT1 basis of one cell as combinations of the cell's node positions:
+    ``c[p, j, n]`` = coefficient of ``x_n`` in the value of local basis function ``p`` at P2 point
+    ``j`` (the d+1 nodes, then the edges in ``lagrange2_pairs`` order), before the factor
+    ``s_p / (d |c|)``.  Local nodes are the cell's nodes in ascending id ("rank"), local dof
+    ``q < d(d+1)`` sits at node ``i = q // d`` of the face opposite node ``j = (d(d+1)-1-q) % (d+1)``
+    and the last d dofs are the cell functions of nodes 0..d-1 (``RT1.eval_basis_functions``,
+    fem/hdiv.py:676-744).  Closed form of the reference's construction: with t = x_i - x_j the face
+    function is t at node i, t/2 + (x_o - x_i)/4 on the edges {i, o}, o != j, -(x_o - x_j)/4 on the
+    edges {j, o}, o != i, and 0 elsewhere (in particular on the edge {i, j}); the cell function of node
+    m is (x_o - x_m)/4 on every edge {m, o}."""
+    n = d + 1
+    pairs = lagrange2_pairs(d)
+    P, L = n + len(pairs), d * (d + 2)
+    c = np.zeros((L, P, n))
+    for q in range(d * n):
+        i, j = q // d, (d * n - 1 - q) % n
+        c[q, i, i] += 1.0
+        c[q, i, j] -= 1.0
+        for e, (a, b) in enumerate(pairs):
+            if i in (a, b) and j not in (a, b):
+                o = b if a == i else a
+                c[q, n + e, i] += 0.5 - 0.25
+                c[q, n + e, j] -= 0.5
+                c[q, n + e, o] += 0.25
+            elif j in (a, b) and i not in (a, b):
+                o = b if a == j else a
+                c[q, n + e, o] -= 0.25
+                c[q, n + e, j] += 0.25
+    for m in range(d):
+        for e, (a, b) in enumerate(pairs):
+            if m in (a, b):
+                o = b if a == m else a
+                c[d * n + m, n + e, o] += 0.25
+                c[d * n + m, n + e, m] -= 0.25
+    return c
+
+
+def rt1_gram_table(d):
+    """``C[p, q, n, n']`` (n, n' = 1..d): A_pq = s_p s_q / (d^2 |c|) * sum C[p,q,n,n'] Q[n,n'] with
+    Q[n,n'] = (K y_n) . y_n', y_n = x_n - x_0.  The table the CUDA kernel is generated from
+    (``oracle/gen_rt1_table.py``); the n = 0 terms drop out because every value is a combination of
+    differences of node positions."""
+    c = rt1_point_coefficients(d)
+    assert np.abs(c.sum(axis=2)).max() < 1e-15
+    M2 = lagrange2_local_mass(d)
+    return np.einsum("jl,pjn,qlm->pqnm", M2, c, c)[:, :, 1:, 1:]
+
+
+def rt1_rank_tables(sd, tabs):
+    """Per cell, in rank order (ascending node id): node ids ``(nc, d+1)``, and for the face opposite
+    each node its id and sign (``RT1.reorder_faces`` fem/hdiv.py:629-674 lists the faces by
+    DESCENDING opposite node; here index r = the face opposite the node of rank r)."""
+    order = np.argsort(tabs["opp"], axis=1, kind="stable")
+    take = lambda a: np.take_along_axis(a, order, axis=1)  # noqa: E731
+    return take(tabs["opp"]), take(tabs["faces"]), take(tabs["signs"])
+
+
+def rt1_dofs(sd, tabs):
+    """``RT1.local_dofs_of_cell`` (fem/hdiv.py:534-552): dof q < d(d+1) = face opposite rank
+    d - q % (d+1), copy q // (d+1); then d*num_faces + k*num_cells + c."""
+    d, nc, nf = sd.dim, sd.num_cells, sd.num_faces
+    _, faces, _ = rt1_rank_tables(sd, tabs)
+    q = np.arange(d * (d + 1))
+    face_dofs = faces[:, d - q % (d + 1)] + (q // (d + 1)) * nf
+    cell_dofs = d * nf + np.arange(d)[None, :] * nc + np.arange(nc)[:, None]
+    return np.hstack([face_dofs, cell_dofs]).astype(np.int64)
+
+
+def local_rt1_mass(sd, tabs, w, K):
+    """|c| Psi (M2 x K) Psi^T with the P2 local mass M2 (fem/hdiv.py:555-621); entry (p, q) =
+    sum_jl M2_jl Psi_pj^T K Psi_ql with K itself; pg.WEIGHT is not read."""
+    d, nc = sd.dim, sd.num_cells
+    R = np.asarray(getattr(sd, "rotation_matrix", np.eye(d, 3)), dtype=float)
+    Kr = np.einsum("ia,abc,jb->cij", R, K, R)
+    nodes, _, signs = rt1_rank_tables(sd, tabs)
+    X = (R @ sd.nodes).T[nodes]  # (nc, d+1, d) in rank order
+    E = X[:, 1:, :] - X[:, :1, :]
+    vol = np.abs(np.linalg.det(E)) / (2.0 if d == 2 else 6.0)
+    c = rt1_point_coefficients(d)
+    Psi = np.einsum("pjn,cnx->cpjx", c, X)  # (nc, L, P, d)
+    q = np.arange(d * (d + 1))
+    s = np.ones((nc, d * (d + 2)))
+    s[:, : d * (d + 1)] = signs[:, (d * (d + 1) - 1 - q) % (d + 1)]
+    Psi *= (s / (d * vol)[:, None])[:, :, None, None]
+    M2 = lagrange2_local_mass(d)
+    A = np.einsum("jl,cpjx,cxy,cqly->cpq", M2, Psi, Kr, Psi) * vol[:, None, None]
+    return A, rt1_dofs(sd, tabs)
+
+
 _LOCAL = {
+    ("rt1", "mass"): local_rt1_mass,
     ("lagrange2", "mass"): local_lagrange2_mass,
     ("lagrange2", "stiff"): local_lagrange2_stiff,
     ("lagrange1", "lumped"): local_lagrange1_lumped,
@@ -619,6 +711,7 @@ NDOF = {
     "bdm1": lambda sd: sd.dim * sd.num_faces,
     "nedelec0": lambda sd: sd.num_edges,
     "lagrange2": lambda sd: sd.num_nodes + sd.num_edges,
+    "rt1": lambda sd: sd.dim * (sd.num_faces + sd.num_cells),
 }
 
 

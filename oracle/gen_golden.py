@@ -40,7 +40,7 @@ FORMS = [
     ("rt0", "mass"), ("rt0", "stiff"), ("bdm1", "mass"), ("bdm1", "stiff"),
     ("nedelec0", "mass"), ("nedelec0", "stiff"),
     ("lagrange1", "lumped"), ("rt0", "lumped"), ("bdm1", "lumped"),
-    ("lagrange2", "mass"), ("lagrange2", "stiff"),
+    ("lagrange2", "mass"), ("lagrange2", "stiff"), ("rt1", "mass"),
 ]
 
 
@@ -61,7 +61,7 @@ def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     cls = {"lagrange1": pg.Lagrange1, "rt0": pg.RT0, "bdm1": pg.BDM1, "nedelec0": pg.Nedelec0,
-           "lagrange2": pg.Lagrange2}
+           "lagrange2": pg.Lagrange2, "rt1": pg.RT1}
     for name, dim, n, pert, mode in CASES:
         sd = reference_element(dim) if n == 0 else structured_grid(dim, n, perturb=pert, seed=1)
         sd.compute_geometry()
@@ -105,6 +105,14 @@ def main():
             store[key + "_indices"] = refS.indices.astype(np.int32)
             store[key + "_data"] = refS.data
             store[key + "_refnnz"] = sps.csr_array(ref).nnz
+        # RT1 pieces assembled on the host around the path: divergence, lumped matrix
+        rt1 = pg.RT1("key")
+        for nm, mat in (("rt1_diff", rt1.assemble_diff_matrix(g)), ("rt1_lumped", rt1.assemble_lumped_matrix(g, data))):
+            mat = sps.csr_array(mat)
+            mat.sum_duplicates()
+            mat.sort_indices()
+            store[nm + "_indptr"], store[nm + "_indices"], store[nm + "_data"] = mat.indptr, mat.indices, mat.data
+            store[nm + "_shape"] = np.array(mat.shape)
         store["nedelec0_lumped_diag"] = pg.Nedelec0("key").assemble_lumped_matrix(g, data).diagonal()
         d0 = pg.PwConstants("key").assemble_mass_matrix(g, data)
         store["p0_mass_diag"] = d0.diagonal()

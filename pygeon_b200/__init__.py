@@ -1,7 +1,7 @@
 """B200-native FEM assembly-and-solve hot path behind PyGeoN's operator API.
 
 ``import pygeon_b200 as pg`` gives the reference's names for the path this package covers:
-``pg.Lagrange1, pg.RT0, pg.BDM1, pg.Nedelec0, pg.PwConstants, pg.LinearSystem`` and the parameter
+``pg.Lagrange1, pg.Lagrange2, pg.RT0, pg.BDM1, pg.RT1, pg.Nedelec0, pg.PwConstants, pg.LinearSystem`` and the parameter
 constants, plus the GPU ``solver`` callables ``pg.cg_solver`` / ``pg.minres_solver``.
 
 Importing the package never touches CUDA; the first assemble/solve call loads ``libpgb.so``
@@ -15,7 +15,7 @@ from .params import SecondOrderTensor, get_cell_data, initialize_data
 
 def __getattr__(name):
     # lazy: these pull in libpgb.so
-    if name in ("Discretization", "Lagrange1", "Lagrange2", "RT0", "BDM1", "Nedelec0", "PwConstants"):
+    if name in ("Discretization", "Lagrange1", "Lagrange2", "RT0", "BDM1", "RT1", "Nedelec0", "PwConstants"):
         from . import discretization as _d
 
         return getattr(_d, name)

@@ -33,6 +33,7 @@ _SIGS = {
     "pgb_pack_bdm1": (_i, [_i, _l, _l, _p, _p, _p, _p, _p, _p]),
     "pgb_pack_edges3d": (_i, [_l, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pgb_pack_edges2d": (_i, [_l, _p, _p, _p, _p, _p]),
+    "pgb_pack_rt1": (_i, [_i, _l, _l, _p, _p, _p, _p, _p, _p]),
     "pgb_prep_coords": (_i, [_i, _l, _p, _p, _p, _p]),
     "pgb_ridges3d_workspace_bytes": (_l, [_l]),
     "pgb_ridges3d": (_i, [_l, _l, _p, _p, _p, _p, C.POINTER(C.c_int64), _p, _l, _p]),
@@ -93,6 +94,7 @@ KIND = {
     "bdm1_lumped": 13,
     "l2_mass": 14,
     "l2_stiff": 15,
+    "rt1_mass": 16,
 }
 NPART = 1184
 

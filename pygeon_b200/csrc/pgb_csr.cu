@@ -941,7 +941,9 @@ int launch_numeric_t(int L, int64_t n_rows, int caps, bool staged, const uint32_
     case 4: return launch_numeric_t_l<4, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
     case 5: return launch_numeric_t_l<5, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
     case 6: return launch_numeric_t_l<6, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
+    case 8: return launch_numeric_t_l<8, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
     case 10: return launch_numeric_t_l<10, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
+    case 15: return launch_numeric_t_l<15, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
     case 12: return launch_numeric_t_l<12, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
   }
   pgb_set_error("pgb_csr_numeric_rows: unsupported local size %d", L);

@@ -8,6 +8,7 @@
 //
 // Closed forms: SURVEY.md section 8(a); each kind cites the reference code it replaces in pgb.h.
 #include "pgb_common.cuh"
+#include "pgb_rt1_table.cuh"
 
 namespace {
 
@@ -236,6 +237,7 @@ struct LocalSize {
                            : (KIND == PGB_P0_MASS)                            ? 1
                            : (KIND == PGB_DARCY_SADDLE)                       ? D + 2
                            : (KIND == PGB_L2_MASS || KIND == PGB_L2_STIFF)    ? (D + 1) + D * (D + 1) / 2
+                           : (KIND == PGB_RT1_MASS)                           ? D * (D + 2)
                                                                               : D + 1;
 };
 
@@ -454,6 +456,51 @@ __global__ void __launch_bounds__(BLOCK) k_local(Params p) {
           emit(i * L + k, v);
         }
       }
+    } else if constexpr (KIND == PGB_RT1_MASS) {
+      // Nodes in rank order (ascending id), Gram matrix Q[n][m] = (K y_n) . y_m of the edge vectors
+      // y_n = x_n - x_0, then the constant contraction of pgb_rt1_table.cuh.  The reference's entry
+      // (p, q) is Psi_p^T K Psi_q; the CSR built here is read as CSC, i.e. it holds the transpose,
+      // which is what (K y_n) . y_m (instead of y_n . K y_m) produces.
+      constexpr int N = D + 1;
+      const unsigned bits = p.aux_bits[c];
+      double Xr[N][D];
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        const unsigned slot = (bits >> (2 * r)) & 3u;
+#pragma unroll
+        for (int a = 0; a < N; ++a)
+          if (slot == (unsigned)a) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) Xr[r][i] = g.X[a][i];
+          }
+      }
+      double Y[D][D], KY[D][D], Q[D][D];
+#pragma unroll
+      for (int n = 0; n < D; ++n)
+#pragma unroll
+        for (int i = 0; i < D; ++i) Y[n][i] = Xr[n + 1][i] - Xr[0][i];
+      apply_tensor<D, D, HAS_K>(Kr, Y, KY);
+#pragma unroll
+      for (int n = 0; n < D; ++n)
+#pragma unroll
+        for (int m = 0; m < D; ++m) Q[n][m] = dotd<D>(KY[n], Y[m]);
+      const double scale = 1.0 / (D * D * g.vol);
+#pragma unroll
+      for (int pp = 0; pp < L; ++pp) {
+        // sign of the face the dof lives on (cell functions: +)
+        const bool negp = pp < D * N && ((bits >> (8 + (D * N - 1 - pp) % N)) & 1u);
+        const double sp = negp ? -scale : scale;
+#pragma unroll
+        for (int qq = 0; qq < L; ++qq) {
+          const bool negq = qq < D * N && ((bits >> (8 + (D * N - 1 - qq) % N)) & 1u);
+          double v = 0.0;
+#pragma unroll
+          for (int n = 0; n < D; ++n)
+#pragma unroll
+            for (int m = 0; m < D; ++m) v += pgb_rt1::table<D>()[((pp * L + qq) * D + n) * D + m] * Q[n][m];
+          emit(pp * L + qq, negq ? -(sp * v) : sp * v);
+        }
+      }
     } else if constexpr (KIND == PGB_RT0_MASS) {
       double A[D + 1][D + 1];
       rt0_local<D, HAS_K>(g, Kr, p.sign_bits[c], w, A);
@@ -593,6 +640,7 @@ int dispatch(int kind, const Params& p, cudaStream_t s) {
     case PGB_BDM1_LUMPED: return launch<PGB_BDM1_LUMPED, D>(p, s);
     case PGB_L2_MASS: return launch<PGB_L2_MASS, D>(p, s);
     case PGB_L2_STIFF: return launch<PGB_L2_STIFF, D>(p, s);
+    case PGB_RT1_MASS: return launch<PGB_RT1_MASS, D>(p, s);
   }
   pgb_set_error("pgb_local_matrices: unknown kind %d", kind);
   return 2;
@@ -611,6 +659,7 @@ extern "C" int pgb_local_size(int kind, int dim) {
     case PGB_DARCY_SADDLE: return dim + 2;
     case PGB_L2_MASS:
     case PGB_L2_STIFF: return (dim + 1) + dim * (dim + 1) / 2;
+    case PGB_RT1_MASS: return dim * (dim + 2);
     default: return dim + 1;
   }
 }
@@ -625,7 +674,7 @@ extern "C" int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* 
       kind == PGB_RT0_DIVDIV || kind == PGB_BDM1_DIVDIV || kind == PGB_DARCY_SADDLE || kind == PGB_BDM1_LUMPED)
     PGB_REQUIRE(sign_bits, "pgb_local_matrices: sign_bits required");
   if (kind == PGB_BDM1_MASS || kind == PGB_BDM1_LUMPED || kind == PGB_N0_MASS ||
-      (kind == PGB_N0_CURLCURL && dim == 3))
+      (kind == PGB_N0_CURLCURL && dim == 3) || kind == PGB_RT1_MASS)
     PGB_REQUIRE(aux_bits, "pgb_local_matrices: aux_bits required");
   if (nc == 0) return 0;
   Params p;

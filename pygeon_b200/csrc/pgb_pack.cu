@@ -324,6 +324,56 @@ extern "C" int pgb_pack_l2_dofs(int dim, int64_t nc, int64_t nn, const int32_t* 
   return 0;
 }
 
+// RT1 dofs: rank the cell's nodes by id (slot a = node opposite face slot a), see pgb.h
+template <int D>
+__global__ void __launch_bounds__(256) k_pack_rt1(int64_t nc, int32_t nf, const int32_t* __restrict__ cf_idx,
+                                                  const int32_t* __restrict__ cell_nodes,
+                                                  const uint8_t* __restrict__ sign_bits, int32_t* __restrict__ dofs,
+                                                  uint32_t* __restrict__ aux) {
+  constexpr int N = D + 1, L = D * (D + 2);
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  int32_t node[N], face[N];
+#pragma unroll
+  for (int a = 0; a < N; ++a) {
+    node[a] = cell_nodes[c * N + a];
+    face[a] = cf_idx[c * N + a];
+  }
+  const unsigned sb = sign_bits[c];
+  int32_t face_of_rank[N];
+  unsigned bits = 0;
+#pragma unroll
+  for (int a = 0; a < N; ++a) {
+    int r = 0;
+#pragma unroll
+    for (int b = 0; b < N; ++b) r += (node[b] < node[a]) ? 1 : 0;
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+      if (q == r) face_of_rank[q] = face[a];
+    bits |= (unsigned)a << (2 * r);
+    bits |= ((sb >> a) & 1u) << (8 + r);
+  }
+  aux[c] = bits;
+#pragma unroll
+  for (int q = 0; q < D * N; ++q) dofs[c * L + q] = face_of_rank[D - q % N] + (q / N) * nf;
+#pragma unroll
+  for (int k = 0; k < D; ++k) dofs[c * L + D * N + k] = (int32_t)((int64_t)D * nf + (int64_t)k * nc + c);
+}
+
+extern "C" int pgb_pack_rt1(int dim, int64_t nc, int64_t nf, const int32_t* cf_idx, const int32_t* cell_nodes,
+                            const uint8_t* sign_bits, int32_t* cell_dofs, uint32_t* aux_bits, void* stream) {
+  PGB_REQUIRE(dim == 2 || dim == 3, "pgb_pack_rt1: dim must be 2 or 3");
+  PGB_REQUIRE((int64_t)dim * (nf + nc) < ((int64_t)1 << 31), "pgb_pack_rt1: dof ids exceed int32");
+  if (nc == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dim == 3)
+    k_pack_rt1<3><<<pgb_grid(nc, 256), 256, 0, s>>>(nc, (int32_t)nf, cf_idx, cell_nodes, sign_bits, cell_dofs, aux_bits);
+  else
+    k_pack_rt1<2><<<pgb_grid(nc, 256), 256, 0, s>>>(nc, (int32_t)nf, cf_idx, cell_nodes, sign_bits, cell_dofs, aux_bits);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int pgb_prep_coords(int dim, int64_t nn, const double* nodes, const double* R_host,
                                double* coords, void* stream) {
   PGB_REQUIRE(dim == 2 || dim == 3, "pgb_prep_coords: dim must be 2 or 3");

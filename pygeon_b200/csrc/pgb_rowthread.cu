@@ -184,6 +184,8 @@ int launch_rowthread(uint32_t max_inc, int L, int64_t row0, int64_t row1, int64_
   PGB_RT(1, 6, 8);  PGB_RT(2, 6, 16); PGB_RT(4, 6, 32); PGB_RT(8, 6, 64);
   PGB_RT(1, 10, 16); PGB_RT(2, 10, 32); PGB_RT(4, 10, 64);
   PGB_RT(1, 12, 16); PGB_RT(2, 12, 32); PGB_RT(4, 12, 64);
+  PGB_RT(1, 8, 8);   PGB_RT(2, 8, 16);  PGB_RT(4, 8, 32);   // RT1 in 2D
+  PGB_RT(1, 15, 16); PGB_RT(2, 15, 32); PGB_RT(4, 15, 64);  // RT1 in 3D
 #undef PGB_RT
   pgb_set_error("k_rowthread: unsupported local size %d / %u incidences", L, max_inc);
   return 2;

@@ -382,6 +382,124 @@ class BDM1(Discretization):
         return PwConstants
 
 
+class RT1(Discretization):
+    """``fem/hdiv.py:512-1028``: Raviart-Thomas elements of order 1, d dofs per face (numbered like
+    BDM1: ``f + k * num_faces``) and d per cell (``d * num_faces + k * num_cells + c``).  The reference
+    assembles the mass matrix in a Python loop over the cells (``fem/hdiv.py:555-621``); here it goes
+    through the K1/K2 engine (kind ``PGB_RT1_MASS``, local 8 x 8 / 15 x 15 blocks).  The divergence,
+    the lumped cell block and the interpolation are O(num_cells) vectorised host code."""
+
+    poly_order = 2
+    tensor_order = VECTOR
+    _space = "rt1"
+    _lumped_diagonal = False
+
+    def ndof(self, sd) -> int:
+        return sd.dim * (sd.num_faces + sd.num_cells)
+
+    # ---- tables in the reference's local order (reorder_faces, fem/hdiv.py:629-674) -------------
+    @staticmethod
+    def _rank_tables(sd):
+        """Per cell: node ids ascending ``(nc, d+1)``, and faces / signs listed by DESCENDING opposite
+        node (``faces_loc``, ``signs_loc`` of the reference)."""
+        d, nc = sd.dim, sd.num_cells
+        opp = np.asarray(sd.compute_opposite_nodes().data).reshape(nc, d + 1)
+        faces = sd.cell_faces.indices.reshape(nc, d + 1)
+        signs = np.asarray(sd.cell_faces.data, dtype=float).reshape(nc, d + 1)
+        sorter = np.argsort(opp, axis=1)[:, ::-1]
+        take = lambda a: np.take_along_axis(a, sorter, axis=1)  # noqa: E731
+        return np.sort(opp, axis=1), take(faces), take(signs)
+
+    def _cell_dofs(self, sd, faces_loc):
+        """``local_dofs_of_cell`` for all cells (``fem/hdiv.py:534-552``): (nc, d(d+2))."""
+        d, nc, nf = sd.dim, sd.num_cells, sd.num_faces
+        loc_face = np.tile(faces_loc, (1, d)) + np.repeat(np.arange(d), d + 1)[None, :] * nf
+        loc_cell = d * nf + nc * np.arange(d)[None, :] + np.arange(nc)[:, None]
+        return np.hstack((loc_face, loc_cell))
+
+    # ---- mass ------------------------------------------------------------------------------------
+    def assemble_mass_matrix_device(self, sd, data: dict | None = None) -> engine.DeviceCSR:
+        _, K = self._coefficients(sd, data)
+        return engine.assemble_device(self._space, "mass", sd, None, K)  # pg.WEIGHT is not read (hdiv.py:575-577)
+
+    def assemble_mass_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
+        """``(K^-1 u, v)`` (``fem/hdiv.py:555-621``)."""
+        _, K = self._coefficients(sd, data)
+        return engine.assemble_host(self._space, "mass", sd, None, K)
+
+    # ---- divergence into PwLinears ---------------------------------------------------------------
+    @staticmethod
+    def compute_local_div_matrix(dim: int) -> np.ndarray:
+        """``fem/hdiv.py:867-892``."""
+        opp_node = np.tile(np.arange(dim + 1), dim)[::-1]
+        loc_node = np.repeat(np.arange(dim + 1), dim)
+        face_div = np.ones((dim + 1, dim * (dim + 1)))
+        face_div[loc_node, np.arange(loc_node.size)] += dim + 1
+        face_div[opp_node, np.arange(loc_node.size)] -= dim + 1
+        cell_div = (dim + 1) * np.eye(dim + 1, dim) - 1
+        return np.hstack((face_div, cell_div))
+
+    def assemble_diff_matrix(self, sd) -> sps.csc_array:
+        """Divergence RT1 -> PwLinears (``fem/hdiv.py:813-865``), all cells at once."""
+        d, nc = sd.dim, sd.num_cells
+        loc_div = self.compute_local_div_matrix(d)  # (d+1, L)
+        _, faces_loc, signs_loc = self._rank_tables(sd)
+        L = d * (d + 2)
+        signs = np.ones((nc, L))
+        signs[:, : d * (d + 1)] = np.tile(signs_loc, (1, d))
+        div = loc_div[None, :, :] * (signs / (d * sd.cell_volumes[:, None]))[:, None, :]  # (nc, d+1, L)
+        cols = np.broadcast_to(self._cell_dofs(sd, faces_loc)[:, None, :], div.shape)
+        ran = nc * np.arange(d + 1)[None, :] + np.arange(nc)[:, None]  # PwLinears.local_dofs_of_cell (l2.py:38-49)
+        rows = np.broadcast_to(ran[:, :, None], div.shape)
+        return sps.csc_array((div.ravel(), (rows.ravel(), cols.ravel())))
+
+    # ---- lumped mass (Egger & Radu 2020; fem/hdiv.py:970-1028) --------------------------------------
+    def _basis_at_center(self, sd, nodes_loc):
+        """``eval_basis_functions_at_center`` for all cells: (nc, 3, d)."""
+        d = sd.dim
+        X = sd.nodes[:, nodes_loc]  # (3, nc, d+1)
+        basis = (X.sum(axis=2)[:, :, None] - (d + 1) * X[:, :, :d]) / ((d + 1) ** 2)
+        return np.transpose(basis, (1, 0, 2)) / (d * sd.cell_volumes)[:, None, None]
+
+    def assemble_lumped_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
+        d, nc = sd.dim, sd.num_cells
+        bdm1_lumped = BDM1(self.keyword).assemble_lumped_matrix(sd, data) / (d + 2)
+        _, K = self._coefficients(sd, data)
+        Kv = np.broadcast_to(np.eye(3)[:, :, None], (3, 3, nc)) if K is None else K
+        nodes_loc, _, _ = self._rank_tables(sd)
+        P = self._basis_at_center(sd, nodes_loc)  # (nc, 3, d)
+        A = np.einsum("cxi,xyc,cyj->cij", P, Kv, P) * (sd.cell_volumes * (d + 1) / (d + 2))[:, None, None]
+        loc = nc * np.arange(d)[None, :] + np.arange(nc)[:, None]
+        rows = np.broadcast_to(loc[:, :, None], A.shape)
+        cols = np.broadcast_to(loc[:, None, :], A.shape)
+        cell_block = sps.csc_array((A.ravel(), (rows.ravel(), cols.ravel())), shape=(nc * d, nc * d))
+        return sps.csc_array(sps.block_diag((bdm1_lumped, cell_block)))
+
+    # ---- vectors -----------------------------------------------------------------------------------
+    def interpolate(self, sd, func) -> np.ndarray:
+        """Face dofs as BDM1, cell dofs from d x d systems at the cell centres (``fem/hdiv.py:894-934``)."""
+        d, nc = sd.dim, sd.num_cells
+        interp_faces = BDM1().interpolate(sd, func)
+        nodes_loc = sd.cell_nodes().indices.reshape(nc, d + 1)
+        P = self._basis_at_center(sd, nodes_loc)
+        f = np.array([np.asarray(v, dtype=float).flatten() for v in _eval_points(func, sd.cell_centers)])  # (nc, 3)
+        coeff = np.linalg.solve(P[:, :d, :], f[:, :d, None])[:, :, 0]  # (nc, d)
+        return np.hstack((interp_faces, coeff.T.ravel()))
+
+    def assemble_nat_bc(self, sd, func, b_faces) -> np.ndarray:
+        """``fem/hdiv.py:936-957``: the BDM1 boundary term on the face dofs."""
+        vals = np.zeros(self.ndof(sd))
+        bdm1 = BDM1()
+        vals[: bdm1.ndof(sd)] = bdm1.assemble_nat_bc(sd, func, b_faces)
+        return vals
+
+    def assemble_stiff_matrix_device(self, sd, data=None):
+        self.get_range_discr_class(sd.dim)
+
+    def get_range_discr_class(self, _dim: int):
+        raise NotImplementedError("PwLinears (the range of RT1) is not part of this package")
+
+
 class Nedelec0(Discretization):
     """``fem/hcurl.py:11-180``: one dof per edge (ridge in 3D, face in 2D)."""
 

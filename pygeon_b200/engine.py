@@ -261,6 +261,7 @@ class GridPack:
     _raw: object = None
     _edges: tuple | None = None
     _bdm1: tuple | None = None
+    _rt1: tuple | None = None
     _darcy: object = None
     _l2: object = None
     plans: dict = field(default_factory=dict)
@@ -362,6 +363,19 @@ class GridPack:
             self._bdm1 = (dofs, bits)
         return self._bdm1
 
+    def rt1(self):
+        """(cell_dofs (nc, d(d+2)) int32 in the reference's local order, rank / sign bits (nc,))."""
+        if self._rt1 is None:
+            d, nc, dev = self.dim, self.nc, self.device
+            with torch.cuda.device(dev):
+                dofs = torch.empty((nc, d * (d + 2)), dtype=_I32, device=dev)
+                bits = torch.empty((nc,), dtype=_I32, device=dev)
+                check(lib.pgb_pack_rt1(d, nc, self.nf, self.cf_idx.data_ptr(), self.cell_nodes.data_ptr(),
+                                       self.sign_bits.data_ptr(), dofs.data_ptr(), bits.data_ptr(), _stream()))
+                _lib.count(1)
+            self._rt1 = (dofs, bits)
+        return self._rt1
+
     # -- dof tables per space --------------------------------------------------------------
     def dofs(self, space: str):
         """(cell_dofs (nc, L) int32 tensor, ndof)."""
@@ -374,6 +388,8 @@ class GridPack:
             return self.edges()[0], self.ne
         if space == "bdm1":
             return self.bdm1()[0], d * self.nf
+        if space == "rt1":
+            return self.rt1()[0], d * (self.nf + self.nc)
         if space == "lagrange2":  # nodes in slot order, then num_nodes + edge (p, q), pairs in lexicographic order
             if self._l2 is None:
                 ce = self.cf_idx if d == 2 else self.edges()[0]
@@ -553,6 +569,7 @@ _FORMS = {
     ("lagrange2", "stiff"): "l2_stiff",
     ("rt0", "lumped"): "rt0_lumped",
     ("bdm1", "lumped"): "bdm1_lumped",
+    ("rt1", "mass"): "rt1_mass",
 }
 
 
@@ -570,6 +587,8 @@ def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None, plan: "C
         aux = pack.edges()[1]
     elif kind in ("bdm1_mass", "bdm1_lumped"):
         aux = pack.bdm1()[1]
+    elif kind == "rt1_mass":
+        aux = pack.rt1()[1]
     with torch.cuda.device(dev):
         rowmajor = plan is not None and plan.mode == 0
         pitch = ((L + 3) & ~3) if rowmajor else L  # row-sorted layout: rows padded to whole 32-byte sectors

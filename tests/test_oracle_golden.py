@@ -10,7 +10,8 @@ from pygeon_b200.grid import reference_element
 
 FORMS = [("lagrange1", "mass"), ("lagrange1", "stiff"), ("lagrange1", "gradgrad"), ("rt0", "mass"),
          ("rt0", "stiff"), ("bdm1", "mass"), ("bdm1", "stiff"), ("nedelec0", "mass"), ("nedelec0", "stiff"),
-         ("lagrange1", "lumped"), ("rt0", "lumped"), ("bdm1", "lumped"), ("lagrange2", "mass"), ("lagrange2", "stiff")]
+         ("lagrange1", "lumped"), ("rt0", "lumped"), ("bdm1", "lumped"), ("lagrange2", "mass"), ("lagrange2", "stiff"),
+         ("rt1", "mass")]
 
 # --- known answers copied as data from the reference's tests (file:line in each id) ------------
 KNOWN = {
@@ -57,6 +58,20 @@ KNOWN = {
          [2, 0, -1, -1, 16, 4, -8, 4, -8, -8], [2, -1, 0, -1, 4, 16, -8, 4, -8, -8],
          [-6, 1, 1, -4, -8, -8, 24, -8, 4, 4], [2, -1, -1, 0, 4, 4, -8, 16, -8, -8],
          [-6, 1, -4, 1, -8, -8, 4, -8, 24, 4], [-6, -4, 1, 1, -8, -8, 4, -8, 4, 24]]) / 30,
+    # tests/discretizations/fem/hdiv/test_rt1.py:19-74
+    ("rt1", "mass", 2): np.array(
+        [[10, -2, 1, 2, -1, 5, 0, -2], [-2, 16, 4, -1, 5, -4, 0, 1], [1, 4, 16, 2, -4, 5, 0, 1],
+         [2, -1, 2, 10, -5, 1, 0, 2], [-1, 5, -4, -5, 22, -8, -3, -1], [5, -4, 5, 1, -8, 22, 3, -4],
+         [0, 0, 0, 0, -3, 3, 4, -2], [-2, 1, 1, 2, -1, -4, -2, 8]]) / 360,
+    ("rt1", "mass", 3): np.array(
+        [[24, -4, 1, -1, 6, -3, 11, -11, 6, -3, 0, 0, -2, -6, 4], [-4, 52, 8, -8, -1, 18, -10, 10, -1, 18, 0, 0, -2, 8, -3],
+         [1, 8, 52, 8, 4, -10, 18, 0, 1, 0, 18, -10, 2, 3, -8], [-1, -8, 8, 52, -1, 0, 0, 18, -4, 10, -10, 18, -2, -3, -3],
+         [6, -1, 4, -1, 24, -11, 3, 0, 6, 0, 3, -11, -2, 4, -6], [-3, 18, -10, 0, -11, 64, -20, 10, 0, 18, -10, 4, -7, 4, 10],
+         [11, -10, 18, 0, 3, -20, 64, -4, 0, -10, 18, -10, 7, -10, -4], [-11, 10, 0, 18, 0, 10, -4, 64, -3, 20, -10, 18, -7, 10, -7],
+         [6, -1, 1, -4, 6, 0, 0, -3, 24, -11, 11, -3, -2, 4, 4], [-3, 18, 0, 10, 0, 18, -10, 20, -11, 64, -4, 10, -7, 4, -7],
+         [0, 0, 18, -10, 3, -10, 18, -10, 11, -4, 64, -20, 7, 7, -4], [0, 0, -10, 18, -11, 4, -10, 18, -3, 10, -20, 64, -7, -7, 10],
+         [-2, -2, 2, -2, -2, -7, 7, -7, -2, -7, 7, -7, 12, -4, -4], [-6, 8, 3, -3, 4, 4, -10, 10, 4, 4, 7, -7, -4, 32, -14],
+         [4, -3, -8, -3, -6, 10, -4, -7, 4, -7, -4, 10, -4, -14, 32]]) / 1260,
 }
 
 
@@ -67,8 +82,8 @@ def test_known_answer_reference_element(key, route):
     sd = reference_element(dim)
     sd.compute_geometry()
     if route == "port":
-        if space == "lagrange2":
-            pytest.skip("no scipy-route port for Lagrange2: the reference itself is a per-cell loop (h1.py:545-599)")
+        if space in ("lagrange2", "rt1"):
+            pytest.skip("no scipy-route port for Lagrange2 / RT1: the reference itself is a per-cell loop (h1.py:545-599, hdiv.py:555-621)")
         A = fo.port_mass(space, sd) if form == "mass" else fo.port_stiff(space, sd)
     else:
         A = fo.closed_form(space, form, sd)
@@ -87,7 +102,7 @@ def test_closed_form_matches_golden(golden, space, form):
     assert np.abs(A.data - ref.data).max() <= 1e-12 * scale
 
 
-@pytest.mark.parametrize("space,form", [f for f in FORMS if f[1] != "gradgrad" and f[0] != "lagrange2"])
+@pytest.mark.parametrize("space,form", [f for f in FORMS if f[1] != "gradgrad" and f[0] not in ("lagrange2", "rt1")])
 def test_port_matches_golden(golden, space, form):
     ref = golden.matrix(space, form)
     if form == "lumped":

@@ -83,6 +83,8 @@ def test_oracle_matches_reference(ref, dim, n, pert, mode, which_grid):
     for form in ("mass", "stiff"):
         refm = getattr(pg.Lagrange2("k"), f"assemble_{form}_matrix")(g, data)
         check(refm, None, fo.closed_form("lagrange2", form, G, data, "k", tabs))
+    # RT1: per-cell Python loop in the reference (hdiv.py:555-621)
+    check(pg.RT1("k").assemble_mass_matrix(g, data), None, fo.closed_form("rt1", "mass", G, data, "k", tabs))
     d0 = pg.PwConstants("k").assemble_mass_matrix(g, data).diagonal()
     assert np.allclose(fo.p0_mass(G, data, "k").diagonal(), d0, rtol=1e-14)
 
@@ -117,7 +119,10 @@ def test_vectors_match_reference(ref, dim, n, pert):
     assert l2o.ndof(sd) == l2r.ndof(g)
     assert np.allclose(l2o.interpolate(sd, scal), l2r.interpolate(g, scal), rtol=1e-14, atol=1e-15)
     assert abs(l2o.assemble_diff_matrix(sd) - l2r.assemble_diff_matrix(g)).max() == 0
-    for name, f_int in (("PwConstants", scal), ("Lagrange1", scal), ("RT0", vec), ("BDM1", vec), ("Nedelec0", vec)):
+    rt1o, rt1r = pgb.RT1("k"), pg.RT1("k")
+    assert rt1o.ndof(sd) == rt1r.ndof(g)
+    assert abs(rt1o.assemble_diff_matrix(sd) - rt1r.assemble_diff_matrix(g)).max() <= 1e-13 * n
+    for name, f_int in (("PwConstants", scal), ("Lagrange1", scal), ("RT0", vec), ("BDM1", vec), ("RT1", vec), ("Nedelec0", vec)):
         ours, theirs = getattr(pgb, name)("k"), getattr(pg, name)("k")
         if name == "Nedelec0" and dim == 2:
             continue  # the reference's interpolate reads ridge_peaks, which is empty in 2D (hcurl.py:160)

@@ -15,7 +15,9 @@ dev = torch.device("cuda", 0)
 sd = pg.structured_grid(3, n, device=dev)
 sd.compute_connectivity()
 for space, kind in (("lagrange1", "l1_stiff"), ("rt0", "rt0_mass"), ("nedelec0", "n0_mass"), ("bdm1", "bdm1_mass"),
-                    ("darcy", "darcy_saddle"), ("lagrange2", "l2_stiff")):
+                    ("darcy", "darcy_saddle"), ("lagrange2", "l2_stiff"), ("rt1", "rt1_mass")):
+    if len(sys.argv) > 2 and space not in sys.argv[2:]:
+        continue
     raw = engine.RawGrid.upload(sd, dev, ridges=(space in ("nedelec0", "lagrange2")))
     raw.check = False
     cold, warm = [], []

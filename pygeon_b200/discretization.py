@@ -48,9 +48,7 @@ class Discretization(abc.ABC):
     # ---- coefficients ------------------------------------------------------------------
     def _coefficients(self, sd, data):
         w = get_cell_data(sd, data, self.keyword, WEIGHT)
-        K = None
-        if self.tensor_order != SCALAR or True:
-            K = get_cell_data(sd, data, self.keyword, SECOND_ORDER_TENSOR)
+        K = get_cell_data(sd, data, self.keyword, SECOND_ORDER_TENSOR)
         return w, K
 
     # ---- mass --------------------------------------------------------------------------

@@ -61,3 +61,18 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("the oracle", "").replace("oracle for", ""), fn
+
+
+def test_ctypes_argument_counts_match_header():
+    """Every prototype in pgb.h has as many parameters as its ctypes signature (a mismatch would
+    corrupt the call silently: ctypes cannot check a C ABI)."""
+    from pygeon_b200 import _lib
+
+    text = open(os.path.join(ROOT, "include", "pgb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b(pgb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text)
+    assert len(protos) == len(_lib._SIGS)
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib._SIGS[name][1]), f"{name}: header has {n} parameters, ctypes table {len(_lib._SIGS[name][1])}"

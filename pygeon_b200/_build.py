@@ -30,7 +30,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(CSRC, "pgb_common.cuh"), os.path.join(CSRC, "pgb_rows.cuh"), os.path.join(INCLUDE, "pgb.h")]
+    headers = [os.path.join(CSRC, h) for h in ("pgb_common.cuh", "pgb_rows.cuh", "pgb_rt1_table.cuh")]
+    headers.append(os.path.join(INCLUDE, "pgb.h"))
     srcs = [os.path.join(CSRC, src) for src in SOURCES]
     if not force and not _stale(LIB, srcs + headers):
         return LIB  # e.g. on a GPU box: the library travels, the object files do not

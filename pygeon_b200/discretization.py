@@ -428,14 +428,17 @@ class RT1(Discretization):
     # ---- divergence into PwLinears ---------------------------------------------------------------
     @staticmethod
     def compute_local_div_matrix(dim: int) -> np.ndarray:
-        """``fem/hdiv.py:867-892``."""
-        opp_node = np.tile(np.arange(dim + 1), dim)[::-1]
-        loc_node = np.repeat(np.arange(dim + 1), dim)
-        face_div = np.ones((dim + 1, dim * (dim + 1)))
-        face_div[loc_node, np.arange(loc_node.size)] += dim + 1
-        face_div[opp_node, np.arange(loc_node.size)] -= dim + 1
-        cell_div = (dim + 1) * np.eye(dim + 1, dim) - 1
-        return np.hstack((face_div, cell_div))
+        """Nodal values (at the d+1 cell nodes, rows) of the divergence of the local basis (columns),
+        before the factor ``s / (d |c|)``: the face function at node i of the face opposite node j has
+        divergence ``1 + (d+1)(lambda_i - lambda_j)``, the cell function of node k
+        ``(d+1) lambda_k - 1`` (same values as ``fem/hdiv.py:867-892``)."""
+        n = dim + 1
+        q = np.arange(dim * n)
+        i, j = q // dim, (dim * n - 1 - q) % n  # local dof q <-> (node i, opposite node j)
+        r = np.arange(n)[:, None]
+        face = 1.0 + n * ((r == i[None, :]).astype(float) - (r == j[None, :]).astype(float))
+        cell = n * (r == np.arange(dim)[None, :]).astype(float) - 1.0
+        return np.hstack((face, cell))
 
     def assemble_diff_matrix(self, sd) -> sps.csc_array:
         """Divergence RT1 -> PwLinears (``fem/hdiv.py:813-865``), all cells at once."""

@@ -285,6 +285,33 @@ def build_dist_csr(indptr, indices, data, owned: torch.Tensor, keys: torch.Tenso
                    send_idx, recv_range, group)
 
 
+def interior_range(A: DistCSR) -> tuple[int, int]:
+    """Longest run ``[a, b)`` of consecutive owned rows without a ghost column.
+
+    In the slab numbering the rows that read ghost values sit at both ends of the owned block (the
+    planes shared with the lower / upper neighbour), so ``[a, b)`` holds nearly all rows: an SpMV over
+    it needs no halo data and can run while ``halo_exchange`` is in flight; the two interface ranges
+    ``[0, a)`` and ``[b, n_owned)`` follow.  (Pointer offsets are enough for a row-range SpMV: indptr
+    holds absolute positions.)  Not used by :func:`dist_spmv` yet, see DESIGN.md section 8."""
+    n = A.n_owned
+    if n == 0:
+        return 0, 0
+    ip = A.indptr.to(torch.int64)
+    lens = ip[1:] - ip[:-1]
+    row_of = torch.repeat_interleave(torch.arange(n, device=ip.device), lens)
+    touches = torch.zeros(n, dtype=torch.bool, device=ip.device)
+    touches[row_of[A.indices.to(torch.int64) >= n]] = True
+    if not bool(touches.any()):
+        return 0, n
+    # run lengths of the ghost-free rows: boundaries at the interface rows
+    bad = torch.nonzero(touches).flatten()
+    edges = torch.cat([bad.new_tensor([-1]), bad, bad.new_tensor([n])])
+    gaps = edges[1:] - edges[:-1] - 1
+    k = int(torch.argmax(gaps).item())
+    a = int(edges[k].item()) + 1
+    return a, a + int(gaps[k].item())
+
+
 def halo_exchange(A: DistCSR, x: torch.Tensor, comm_device=None) -> None:
     """Fill the ghost block ``x[n_owned:]`` with the owners' values (grouped isend/irecv)."""
     if not A.send_idx and not A.recv_range:

@@ -84,6 +84,14 @@ def _worker(rank, world, port, q):
             assert np.array_equal(x.numpy(), xg[gcol]), space
             y = loc @ x.numpy()
             assert np.abs(y - (Aglob @ xg)[gid_owned]).max() <= 1e-12 * np.abs(Aglob @ xg).max()
+            # interior range: no ghost column inside, every interface row outside, and it is the bulk
+            a, b = pd.interior_range(D)
+            ghost_rows = np.unique(loc.tocoo().row[loc.tocoo().col >= D.n_owned])
+            assert 0 <= a <= b <= D.n_owned
+            assert not np.any((ghost_rows >= a) & (ghost_rows < b)), space
+            if ghost_rows.size:
+                assert a == 0 or (a - 1) in ghost_rows
+                assert b == D.n_owned or b in ghost_rows
             # at most two neighbours for a slab partition
             assert set(D.send_idx) <= {rank - 1, rank + 1} and set(D.recv_range) <= {rank - 1, rank + 1}
         dist.barrier()

@@ -10,7 +10,8 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host;
  *   - the caller owns every buffer; the only allocations made here are the Krylov drivers'
- *     O(maxiter) residual history, a few KB of scalars and a mapped pinned stop flag;
+ *     residual history (at most PGB_RESID_CAP doubles per device), a few KB of scalars and a
+ *     mapped pinned stop flag;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*)
  *     unless stated otherwise; return value 0 = ok, non-zero = error with
  *     pgb_last_error() describing it (thread-local);
@@ -244,6 +245,40 @@ int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, const uint32_t*
 int pgb_csr_numeric(int64_t nnz, const uint32_t* perm, const uint32_t* seg, const double* vals,
                     double* data, void* stream);
 
+/* ---- system build around the assembled matrix, in HBM ----------------------
+ * Replaces the host SpGEMMs of LinearSystem.reduce_system (numerics/linear_system.py:64-77:
+ * R_0 @ A @ R_0.T with the restriction matrix of :115-127) and serves the owned-row extraction of the
+ * cell-partitioned multi-GPU path.  Count -> scan -> fill: scratch is O(rows), nothing per entry.
+ *   workspace: pgb_system_workspace_bytes(n) bytes for any call below working on n rows.
+ * pgb_mask_to_map: newid[i] = rank of i among the entries with mask[i] != 0, or -1 (nullable);
+ *   rows[rank] = i (nullable); *count_host = number kept (stream synchronised when non-NULL).
+ * pgb_csr_extract_symbolic: out row i = input row rows[i] (rows == NULL: row i), entries whose
+ *   column has col_map[col] < 0 dropped (col_map == NULL: keep all): writes the int64 row pointer
+ *   out_indptr[n_out + 1], *nnz_host after a synchronisation.
+ * pgb_csr_extract_fill: the kept entries in their original order, columns renumbered through col_map. */
+int64_t pgb_system_workspace_bytes(int64_t n);
+int pgb_mask_to_map(int64_t n, const uint8_t* mask, int32_t* newid, int32_t* rows, int64_t* count_host,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+int pgb_csr_extract_symbolic(int64_t n_out, const int32_t* rows, const void* indptr, int idx64,
+                             const int32_t* indices, const int32_t* col_map, int64_t* out_indptr,
+                             int64_t* nnz_host, void* workspace, int64_t workspace_bytes, void* stream);
+int pgb_csr_extract_fill(int64_t n_out, const int32_t* rows, const void* indptr, int idx64,
+                         const int32_t* indices, const double* data, const int32_t* col_map,
+                         const int64_t* out_indptr, int32_t* out_indices, double* out_data, void* stream);
+/* diag[r] = A[r][r] (0 when the row has no diagonal entry). */
+int pgb_csr_diagonal(int64_t n, const void* indptr, int idx64, const int32_t* indices, const double* data,
+                     double* diag, void* stream);
+/* Inverse diagonal of the SPD block preconditioner diag(diag(M), diag(B diag(M)^-1 B^T)) of the
+ * symmetrised Darcy saddle matrix [[M, -B^T], [-B, 0]] (rows < num_faces: fluxes); diag_work:
+ * num_faces doubles of scratch. */
+int pgb_darcy_block_jacobi(int64_t n, int64_t num_faces, const void* indptr, int idx64, const int32_t* indices,
+                           const double* data, double* diag_work, double* dinv, void* stream);
+/* out[i] = x[idx[i]] (+ a * y[idx[i]] when y != NULL): the restriction R v of linear_system.py:72-77 and
+ * the send-buffer packing of the halo exchange.  scatter_add: dst[idx[i]] += src[i] (distinct idx): R^T v. */
+int pgb_gather(int64_t n, const int32_t* idx, const double* x, const double* y, double a, double* out,
+               void* stream);
+int pgb_scatter_add(int64_t n, const int32_t* idx, const double* src, double* dst, void* stream);
+
 /* ---- K3: SpMV and fused Krylov steps ----------------------------------------------
  * The reference has no iterative solver (numerics/linear_system.py:79-94 takes any
  * `solver(A, b) -> x`); these implement the recurrences of scipy.sparse.linalg.cg / minres
@@ -254,10 +289,12 @@ int pgb_spmv(int64_t n_rows, const void* indptr, int idx64, const int32_t* indic
              const double* data, const double* x, double* y, int threads_per_row, void* stream);
 
 /* Whole CG solve on one GPU.  x (in: x0, out: solution), work: 3*n doubles.
- * dinv: optional Jacobi preconditioner (1/diag) or NULL.  resid_host[maxiter+1] (host, may be
- * NULL) receives ||r_k||_2 for k = 0..iters.  Stops when ||r|| <= max(atol, rtol*||b||), checked
- * every iteration like scipy.  Synchronises the stream.  *iters_host = iterations done,
- * *info_host = 0 converged / maxiter otherwise. */
+ * dinv: optional Jacobi preconditioner (1/diag) or NULL.  resid_host[min(maxiter+1, PGB_RESID_CAP)]
+ * (host, may be NULL) receives ||r_k||_2 for k = 0..iters (the first PGB_RESID_CAP of them: the
+ * history is bounded whatever maxiter is).  Stops when ||r|| <= max(atol, rtol*||b||), checked
+ * every iteration like scipy; b == 0 returns x = 0 at once (scipy: `return b, 0`).  Synchronises
+ * the stream.  *iters_host = iterations done, *info_host = 0 converged / maxiter otherwise. */
+#define PGB_RESID_CAP (1 << 20)
 int pgb_cg(int64_t n, const void* indptr, int idx64, const int32_t* indices, const double* data,
            const double* b, double* x, const double* dinv, double rtol, double atol, int maxiter,
            double* work, int* iters_host, int* info_host, double* resid_host, void* stream);

@@ -104,12 +104,14 @@ class Grid:
             e = x[:, cn_idx[:, 1]] - x[:, cn_idx[:, 0]]
             self.cell_volumes = np.linalg.norm(e, axis=0)
         elif d == 2:
+            # planar grid, possibly tilted in 3D: in-plane normal t x n_plane ((t_y, -t_x, 0) in the xy-plane)
             t = x[:, fn[:, 1]] - x[:, fn[:, 0]]
-            self.face_normals = np.vstack([t[1], -t[0], np.zeros(self.num_faces)])
+            n_plane = _plane_normal(x, cn_idx) if np.any(x[2]) else np.array([0.0, 0.0, 1.0])
+            self.face_normals = np.cross(t, n_plane[:, None], axis=0)
             self.face_areas = np.linalg.norm(t, axis=0)
             a = x[:, cn_idx[:, 1]] - x[:, cn_idx[:, 0]]
             b = x[:, cn_idx[:, 2]] - x[:, cn_idx[:, 0]]
-            self.cell_volumes = 0.5 * np.abs(a[0] * b[1] - a[1] * b[0])
+            self.cell_volumes = 0.5 * np.linalg.norm(np.cross(a, b, axis=0), axis=0)
         else:
             a = x[:, fn[:, 1]] - x[:, fn[:, 0]]
             b = x[:, fn[:, 2]] - x[:, fn[:, 0]]
@@ -131,6 +133,37 @@ class Grid:
         import copy as _copy
 
         return _copy.copy(self)
+
+
+def _plane_normal(x, cn_idx):
+    """Unit normal of the plane of a 2D grid embedded in 3D, oriented to the upper half space."""
+    a = x[:, cn_idx[0, 1]] - x[:, cn_idx[0, 0]]
+    b = x[:, cn_idx[0, 2]] - x[:, cn_idx[0, 0]]
+    n = np.cross(a, b)
+    n /= np.linalg.norm(n)
+    return -n if n[2] < 0 else n
+
+
+class map_geometry:  # namespace like porepy's module of that name
+    """`pp.map_geometry.map_grid`, restated from PorePy's published algorithm (PorePy itself is absent):
+    the rotation about `n x e_z` by the angle between the plane normal `n` and `e_z` (Rodrigues' formula);
+    the reference reads `R` and `keep_dims` from the tuple (grids/grid.py:366-368)."""
+
+    @staticmethod
+    def map_grid(g):
+        cn_idx = g.cell_nodes().indices.reshape(g.num_cells, g.dim + 1)
+        n = _plane_normal(g.nodes, cn_idx)
+        ez = np.array([0.0, 0.0, 1.0])
+        axis = np.cross(n, ez)
+        s, c = np.linalg.norm(axis), float(n @ ez)
+        if s < 1e-15:
+            R = np.eye(3)
+        else:
+            axis = axis / s
+            W = np.array([[0.0, -axis[2], axis[1]], [axis[2], 0.0, -axis[0]], [-axis[1], axis[0], 0.0]])
+            R = c * np.eye(3) + s * W + (1.0 - c) * np.outer(axis, axis)
+        keep = np.array([True, True, False])
+        return None, None, None, None, R, keep, None
 
 
 class MortarGrid:  # only used as a base class / in annotations

@@ -34,7 +34,20 @@ CASES = [
     ("tet2_pert_nonsym", 3, 2, 0.2, "nonsym"),
     ("tet3_lattice", 3, 3, 0.0, "default"),
     ("tet3_lattice_sym", 3, 3, 0.0, "sym"),
+    # 2D grid tilted in 3D: non-identity rotation_matrix (grids/grid.py:355-370, vec_l2.py:113-114, hdiv.py:493)
+    ("tri4_tilted_nonsym", 2, 4, 0.2, "nonsym", True),
+    ("tri3_tilted", 2, 3, 0.15, "default", True),
 ]
+
+
+def tilt(sd):
+    """Rigid motion of a planar grid into a generic plane of R^3 (fixed Euler angles + shift)."""
+    a, b, c = 0.4, -0.7, 0.3
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    sd.nodes = Rz @ Ry @ Rx @ sd.nodes + np.array([[0.1], [0.2], [0.3]])
+    return sd
 FORMS = [
     ("lagrange1", "mass"), ("lagrange1", "stiff"), ("lagrange1", "gradgrad"),
     ("rt0", "mass"), ("rt0", "stiff"), ("bdm1", "mass"), ("bdm1", "stiff"),
@@ -62,8 +75,13 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     cls = {"lagrange1": pg.Lagrange1, "rt0": pg.RT0, "bdm1": pg.BDM1, "nedelec0": pg.Nedelec0,
            "lagrange2": pg.Lagrange2, "rt1": pg.RT1}
-    for name, dim, n, pert, mode in CASES:
+    only = sys.argv[1:]
+    for name, dim, n, pert, mode, *tilted in CASES:
+        if only and name not in only:
+            continue
         sd = reference_element(dim) if n == 0 else structured_grid(dim, n, perturb=pert, seed=1)
+        if tilted and tilted[0]:
+            tilt(sd)
         sd.compute_geometry()
         g = ref_loader.ref_grid(sd)
         w, K = coefficients(sd.num_cells, mode)

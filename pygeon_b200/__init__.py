@@ -9,8 +9,18 @@ Importing the package never touches CUDA; the first assemble/solve call loads ``
 """
 
 from .constants import *  # noqa: F401,F403
-from .grid import SimplexGrid, structured_grid
-from .params import SecondOrderTensor, get_cell_data, initialize_data
+from . import bmat, numerics  # noqa: F401
+from .grid import SimplexGrid, reference_element, structured_grid, unit_grid  # noqa: F401
+from .md_grid import MixedDimensionalGrid, MortarGrid, as_mdg  # noqa: F401
+from .numerics.differentials import curl, div, grad  # noqa: F401
+from .numerics.innerproducts import (cell_mass, face_mass, lumped_cell_mass, lumped_face_mass,  # noqa: F401
+                                     lumped_peak_mass, lumped_ridge_mass, peak_mass, ridge_mass)
+from .numerics.projections import eval_at_cell_centers  # noqa: F401
+from .numerics.restrictions import remove_tip_dofs  # noqa: F401
+from .numerics.stiffness import cell_stiff, face_stiff, peak_stiff, ridge_stiff  # noqa: F401
+from .params import SecondOrderTensor, get_cell_data, initialize_data  # noqa: F401
+
+Grid = SimplexGrid  # the grid class of this package under the reference's name
 
 
 def __getattr__(name):

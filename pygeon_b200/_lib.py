@@ -48,6 +48,14 @@ _SIGS = {
     "pgb_csr_symbolic_finish": (_i, [_l, _l, _i, _i, _l, _p, _p, _p, _i, _p, _p, _p]),
     "pgb_csr_numeric_rows": (_i, [_l, _i, _i, _p, _p, _p, _i, _p, _p, _i, _p]),
     "pgb_csr_numeric": (_i, [_l, _p, _p, _p, _p, _p]),
+    "pgb_system_workspace_bytes": (_l, [_l]),
+    "pgb_mask_to_map": (_i, [_l, _p, _p, _p, C.POINTER(C.c_int64), _p, _l, _p]),
+    "pgb_csr_extract_symbolic": (_i, [_l, _p, _p, _i, _p, _p, _p, C.POINTER(C.c_int64), _p, _l, _p]),
+    "pgb_csr_extract_fill": (_i, [_l, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "pgb_csr_diagonal": (_i, [_l, _p, _i, _p, _p, _p, _p]),
+    "pgb_darcy_block_jacobi": (_i, [_l, _l, _p, _i, _p, _p, _p, _p, _p]),
+    "pgb_gather": (_i, [_l, _p, _p, _p, _d, _p, _p]),
+    "pgb_scatter_add": (_i, [_l, _p, _p, _p, _p]),
     "pgb_spmv": (_i, [_l, _p, _i, _p, _p, _p, _p, _i, _p]),
     "pgb_cg": (_i, [_l, _p, _i, _p, _p, _p, _p, _p, _d, _d, _i, _p, C.POINTER(_i), C.POINTER(_i), _p, _p]),
     "pgb_minres": (_i, [_l, _p, _i, _p, _p, _p, _p, _p, _d, _d, _i, _p, C.POINTER(_i), C.POINTER(_i), _p, _p]),

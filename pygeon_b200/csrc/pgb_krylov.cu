@@ -95,12 +95,12 @@ struct MinresScal {
   // per-iteration coefficients produced by the scalar kernel
   double alfa, oldeps, delta, denom, phi, inv_beta;
   double rtol, shift;
-  int itn, istop, pending, done, maxiter;
+  int itn, istop, pending, done, maxiter, resid_cap;
 };
 
 struct CgScal {
   double rho, rho_prev, atol_user, rtol, bnorm2;
-  int done, iters;
+  int done, iters, resid_cap;
 };
 
 enum { SPMV_PLAIN = 0, SPMV_CG = 1, SPMV_MINRES = 2 };
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(KB) k_cg_p(int64_t n, int k, const double* __r
   double atol = fmax(sc->atol_user, sc->rtol * sqrt(bb));
   bool done = rnorm < atol;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    resid[k] = rnorm;
+    if (k < sc->resid_cap) resid[k] = rnorm;
     sc->bnorm2 = bb;
     if (done) {
       sc->done = 1;
@@ -532,7 +532,7 @@ __global__ void k_mr_scalars(int itn, const double* p_beta, const double* p_xx, 
   sc->oldb = oldb;
   sc->beta = beta;
   sc->itn = itn;
-  resid[itn] = phibar;
+  if (itn < sc->resid_cap) resid[itn] = phibar;
 }
 
 // w = (v - oldeps w1 - delta w2) denom, stored over w1 (= w_{k-2}, dead afterwards); x += phi w;
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(KB) k_mr_d(int64_t n, double* __restrict__ v, 
 }
 
 __global__ void k_mr_setup(MinresScal* sc, const double* p_b1, const double* p_bb, double rtol, double shift,
-                           int maxiter, double* out2) {
+                           int maxiter, int resid_cap, double* out2) {
   __shared__ double ws[KB / 32];
   double b1 = sum_partials(p_b1, ws);
   double bb = sum_partials(p_bb, ws);
@@ -591,35 +591,50 @@ __global__ void k_mr_setup(MinresScal* sc, const double* p_b1, const double* p_b
   s.rtol = rtol;
   s.shift = shift;
   s.maxiter = maxiter;
+  s.resid_cap = resid_cap;
   *sc = s;
   out2[0] = b1;
   out2[1] = bb;
 }
 
-// small persistent scratch shared by the drivers
+// small persistent scratch shared by the drivers, one per (host thread, device)
 struct Scratch {
   int* flag_host = nullptr;  // mapped pinned
   int* flag_dev = nullptr;
   void* scal = nullptr;  // device, 1 KB
   double* parts = nullptr;  // device, 8 * NPART doubles
-  double* resid = nullptr;  // device
+  double* resid = nullptr;  // device: hist_cap history entries + 2 spare slots
   int resid_cap = 0;
 };
-thread_local Scratch g_scr;
+constexpr int MAX_DEV = 64;
+thread_local Scratch g_scr_dev[MAX_DEV];
 
-int ensure_scratch(int maxiter) {
-  Scratch& s = g_scr;
+// number of residual-history entries kept for a solve of at most `maxiter` iterations
+inline int hist_cap(int maxiter) {
+  int64_t want = (int64_t)maxiter + 2;
+  return (int)(want < PGB_RESID_CAP ? want : PGB_RESID_CAP);
+}
+
+int ensure_scratch(int maxiter, Scratch** out) {
+  int dev = 0;
+  PGB_CHECK(cudaGetDevice(&dev));
+  PGB_REQUIRE(dev >= 0 && dev < MAX_DEV, "device ordinal out of range");
+  Scratch& s = g_scr_dev[dev];
   if (!s.flag_host) {
     PGB_CHECK(cudaHostAlloc((void**)&s.flag_host, 64, cudaHostAllocMapped));
     PGB_CHECK(cudaHostGetDevicePointer((void**)&s.flag_dev, s.flag_host, 0));
     PGB_CHECK(cudaMalloc(&s.scal, 1024));
     PGB_CHECK(cudaMalloc((void**)&s.parts, sizeof(double) * 8 * NPART));
   }
-  if (s.resid_cap < maxiter + 2) {
+  const int cap = hist_cap(maxiter);
+  if (s.resid_cap < cap) {  // bounded by PGB_RESID_CAP (8 MB), whatever maxiter is
     if (s.resid) cudaFree(s.resid);
-    PGB_CHECK(cudaMalloc((void**)&s.resid, sizeof(double) * (size_t)(maxiter + 2)));
-    s.resid_cap = maxiter + 2;
+    s.resid = nullptr;
+    s.resid_cap = 0;
+    PGB_CHECK(cudaMalloc((void**)&s.resid, sizeof(double) * (size_t)(cap + 2)));
+    s.resid_cap = cap;
   }
+  *out = &s;
   return 0;
 }
 
@@ -714,8 +729,10 @@ extern "C" int pgb_cg(int64_t n, const void* indptr, int idx64, const int32_t* i
                       double* resid_host, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   PGB_REQUIRE(n > 0 && maxiter >= 0, "pgb_cg: bad arguments");
-  if (ensure_scratch(maxiter)) return 1;
-  Scratch& S = g_scr;
+  Scratch* Sp = nullptr;
+  if (int rc = ensure_scratch(maxiter, &Sp)) return rc;
+  Scratch& S = *Sp;
+  const int cap = hist_cap(maxiter);
   double* r = work;
   double* p = work + n;
   double* q = work + 2 * n;
@@ -724,10 +741,28 @@ extern "C" int pgb_cg(int64_t n, const void* indptr, int idx64, const int32_t* i
   CgScal h = {};
   h.atol_user = atol;
   h.rtol = rtol;
+  h.resid_cap = cap;
   *S.flag_host = 0;
   PGB_CHECK(cudaMemcpyAsync(sc, &h, sizeof(h), cudaMemcpyHostToDevice, s));
   const int tpr = pick_tpr(avg_row(n, indptr, idx64, s));
   const int vg = vec_grid(n);
+  if (iters_host) *iters_host = 0;
+  if (info_host) *info_host = 0;
+
+  // scipy returns b (= 0) at once for a zero right-hand side; without this test alpha = 0/0 and no
+  // later `rnorm < atol` can ever be true
+  double* bb_dev = S.resid + cap + 1;
+  k_dot<<<vg, KB, 0, s>>>(n, b, b, p_bb);
+  k_reduce<<<1, KB, 0, s>>>(p_bb, NPART, bb_dev);
+  PGB_LAUNCH_CHECK();
+  double bb_host = 1.0;
+  PGB_CHECK(cudaMemcpyAsync(&bb_host, bb_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
+  PGB_CHECK(cudaStreamSynchronize(s));
+  if (bb_host == 0.0) {
+    PGB_CHECK(cudaMemsetAsync(x, 0, sizeof(double) * n, s));
+    PGB_CHECK(cudaStreamSynchronize(s));
+    return 0;
+  }
 
   SpmvArgs a = {};
   a.n = n; a.indptr = indptr; a.indices = indices; a.data = data;
@@ -746,27 +781,24 @@ extern "C" int pgb_cg(int64_t n, const void* indptr, int idx64, const int32_t* i
     PGB_LAUNCH_CHECK();
     ++launched;
   }
-  // final residual record (also catches convergence exactly at maxiter for the history)
+  // final residual (also catches convergence exactly at maxiter for the history)
+  double* rr_dev = S.resid + cap;
   if (launched == maxiter) {
-    k_reduce<<<1, KB, 0, s>>>(p_rr, NPART, S.resid + maxiter + 1);
+    k_reduce<<<1, KB, 0, s>>>(p_rr, NPART, rr_dev);
     PGB_LAUNCH_CHECK();
   }
   PGB_CHECK(cudaMemcpyAsync(&h, sc, sizeof(h), cudaMemcpyDeviceToHost, s));
   PGB_CHECK(cudaStreamSynchronize(s));
-  int iters = h.iters;
-  if (h.bnorm2 == 0.0) {  // scipy: return b (= 0)
-    PGB_CHECK(cudaMemsetAsync(x, 0, sizeof(double) * n, s));
-    iters = 0;
-    h.done = 1;
-  }
+  const int iters = h.iters;
   if (iters_host) *iters_host = iters;
   if (info_host) *info_host = h.done ? 0 : maxiter;
-  if (resid_host) {
+  if (resid_host) {  // ||r_k|| for k = 0..iters, truncated to the first PGB_RESID_CAP entries
     int cnt = h.done ? iters + 1 : iters;
+    if (cnt > cap) cnt = cap;
     if (cnt > 0) PGB_CHECK(cudaMemcpyAsync(resid_host, S.resid, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s));
-    if (!h.done && launched == maxiter) {
+    if (!h.done && launched == maxiter && iters < cap) {
       double rr = 0;
-      PGB_CHECK(cudaMemcpyAsync(&rr, S.resid + maxiter + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+      PGB_CHECK(cudaMemcpyAsync(&rr, rr_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
       PGB_CHECK(cudaStreamSynchronize(s));
       resid_host[iters] = sqrt(rr);
     }
@@ -781,8 +813,10 @@ extern "C" int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_
                           double* resid_host, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   PGB_REQUIRE(n > 0 && maxiter >= 0, "pgb_minres: bad arguments");
-  if (ensure_scratch(maxiter)) return 1;
-  Scratch& S = g_scr;
+  Scratch* Sp = nullptr;
+  if (int rc = ensure_scratch(maxiter, &Sp)) return rc;
+  Scratch& S = *Sp;
+  const int cap = hist_cap(maxiter);
   double* v = work;
   double* rb[3] = {work + n, work + 2 * n, work + 3 * n};  // r1, r2, y rotate
   double* wb[2] = {work + 4 * n, work + 5 * n};
@@ -799,7 +833,7 @@ extern "C" int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_
   a.x = x; a.y = rb[2];
   if (launch_spmv<SPMV_PLAIN>(a, idx64, tpr, s)) return 1;
   k_mr_init<<<vg, KB, 0, s>>>(n, b, rb[2], dinv, rb[0], p_b1, p_bb);
-  k_mr_setup<<<1, KB, 0, s>>>(sc, p_b1, p_bb, rtol, shift, maxiter, out2);
+  k_mr_setup<<<1, KB, 0, s>>>(sc, p_b1, p_bb, rtol, shift, maxiter, cap, out2);
   PGB_LAUNCH_CHECK();
   double hb[2];
   PGB_CHECK(cudaMemcpyAsync(hb, out2, sizeof(hb), cudaMemcpyDeviceToHost, s));
@@ -848,8 +882,9 @@ extern "C" int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_
   PGB_CHECK(cudaStreamSynchronize(s));
   if (iters_host) *iters_host = h.itn;
   if (info_host) *info_host = (h.istop == 6) ? maxiter : 0;
-  if (resid_host && h.itn > 0) {
-    PGB_CHECK(cudaMemcpyAsync(resid_host, S.resid + 1, sizeof(double) * h.itn, cudaMemcpyDeviceToHost, s));
+  if (resid_host && h.itn > 0) {  // phibar of iterations 1.., truncated to PGB_RESID_CAP - 1 entries
+    const int cnt = h.itn < cap - 1 ? h.itn : cap - 1;
+    PGB_CHECK(cudaMemcpyAsync(resid_host, S.resid + 1, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s));
     PGB_CHECK(cudaStreamSynchronize(s));
   }
   return 0;
@@ -862,7 +897,7 @@ extern "C" int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_
 // scratch layout (doubles): [4*NPART partial arrays: rr, rho, bb, pq][8: red][8: flag][16: scalars]
 // [maxiter+2: residual history];  pgb_cg_scratch_doubles(maxiter) gives the size.
 // ---------------------------------------------------------------------------------------------
-extern "C" int64_t pgb_cg_scratch_doubles(int maxiter) { return 4 * (int64_t)NPART + 32 + maxiter + 2; }
+extern "C" int64_t pgb_cg_scratch_doubles(int maxiter) { return 4 * (int64_t)NPART + 32 + hist_cap(maxiter); }
 
 extern "C" int pgb_cg_step_init(int64_t n, const double* b, const double* q, const double* dinv, double* r,
                                 double rtol, double atol, double* scratch, void* stream) {
@@ -871,6 +906,7 @@ extern "C" int pgb_cg_step_init(int64_t n, const double* b, const double* q, con
   CgScal h = {};
   h.atol_user = atol;
   h.rtol = rtol;
+  h.resid_cap = PGB_RESID_CAP;  // the caller sized the scratch with pgb_cg_scratch_doubles(maxiter)
   PGB_CHECK(cudaMemsetAsync(t.flag, 0, 8, s));
   PGB_CHECK(cudaMemcpyAsync(t.sc, &h, sizeof(h), cudaMemcpyHostToDevice, s));
   k_cg_init<<<vec_grid(n), KB, 0, s>>>(n, b, q, dinv, r, t.p_rr, t.p_rho, t.p_bb);
@@ -942,7 +978,7 @@ MrScratch mr_scratch(double* s) {
 static_assert(sizeof(MinresScal) <= 64 * sizeof(double), "MinresScal must fit its scratch slot");
 }  // namespace
 
-extern "C" int64_t pgb_mr_scratch_doubles(int maxiter) { return 5 * (int64_t)NPART + 82 + maxiter + 2; }
+extern "C" int64_t pgb_mr_scratch_doubles(int maxiter) { return 5 * (int64_t)NPART + 82 + hist_cap(maxiter); }
 
 extern "C" int pgb_mr_step_reduce(double* scratch, int mask, int from_red, void* stream) {
   if (from_red) k_red_to_parts<<<1, KB, 0, (cudaStream_t)stream>>>(scratch, mask, 5);
@@ -969,7 +1005,7 @@ extern "C" int pgb_mr_step_start(int64_t n, const double* r1, double* v, double*
                                  double shift, int maxiter, double* scratch, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   MrScratch t = mr_scratch(scratch);
-  k_mr_setup<<<1, KB, 0, s>>>(t.sc, t.p_b1, t.p_bb, rtol, shift, maxiter, t.out2);
+  k_mr_setup<<<1, KB, 0, s>>>(t.sc, t.p_b1, t.p_bb, rtol, shift, maxiter, hist_cap(maxiter), t.out2);
   k_mr_start<<<vec_grid(n), KB, 0, s>>>(n, r1, nullptr, t.sc, v, w, w2);
   PGB_LAUNCH_CHECK();
   return 0;

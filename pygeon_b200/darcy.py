@@ -20,35 +20,37 @@ import scipy.sparse as sps
 
 from . import engine
 from .constants import SECOND_ORDER_TENSOR, UNITARY_DATA, WEIGHT
-from .params import get_cell_data
+from .params import coefficient
 
 
 def darcy_saddle_device(sd, data: dict | None = None, keyword: str = UNITARY_DATA) -> engine.DeviceCSR:
-    w = get_cell_data(sd, data, keyword, WEIGHT)
-    K = get_cell_data(sd, data, keyword, SECOND_ORDER_TENSOR)
+    w = coefficient(sd, data, keyword, WEIGHT)
+    K = coefficient(sd, data, keyword, SECOND_ORDER_TENSOR)
     return engine.assemble_device("darcy", "saddle", sd, w, K)
 
 
 def darcy_saddle_matrix(sd, data: dict | None = None, keyword: str = UNITARY_DATA) -> sps.csc_array:
     """Host copy (CSC).  For non-symmetric tensors the CSR arrays are reinterpreted as CSC exactly as
     for the mass matrices (see pgb.h, K1 note)."""
-    return darcy_saddle_device(sd, data, keyword).to_scipy("csc")
+    w = coefficient(sd, data, keyword, WEIGHT)
+    K = coefficient(sd, data, keyword, SECOND_ORDER_TENSOR)
+    return engine.assemble_host("darcy", "saddle", sd, w, K)
 
 
 def darcy_block_jacobi(A: engine.DeviceCSR, num_faces: int):
     """Inverse diagonal of the SPD block preconditioner diag(diag(M), diag(B diag(M)^-1 B^T)) for
     the symmetrised saddle system (the natural scaling fix for SURVEY.md H5: ``B`` has entries
-    +-1/|c|, so unpreconditioned MINRES stagnates).  Index bookkeeping with torch, device resident."""
+    +-1/|c|, so unpreconditioned MINRES stagnates).  One pass over the matrix in HBM
+    (``pgb_darcy_block_jacobi``), scratch = one vector."""
     import torch
+
+    from ._lib import check, lib
 
     n = A.shape[0]
     dev = A.data.device
-    d = A.diagonal()
-    du = d[:num_faces]
-    counts = (A.indptr[1:] - A.indptr[:-1]).to(torch.int64)
-    row_of = torch.repeat_interleave(torch.arange(n, device=dev), counts)
-    cols = A.indices.to(torch.int64)
-    sel = (row_of >= num_faces) & (cols < num_faces)  # entries of -B
-    dp = torch.zeros(n - num_faces, dtype=torch.float64, device=dev)
-    dp.index_add_(0, row_of[sel] - num_faces, A.data[sel] ** 2 / du[cols[sel]])
-    return 1.0 / torch.cat([du, dp])
+    with torch.cuda.device(dev):
+        work = torch.empty(num_faces, dtype=torch.float64, device=dev)
+        dinv = torch.empty(n, dtype=torch.float64, device=dev)
+        check(lib.pgb_darcy_block_jacobi(n, num_faces, A.indptr.data_ptr(), A.idx64, A.indices.data_ptr(),
+                                         A.data.data_ptr(), work.data_ptr(), dinv.data_ptr(), engine._stream()))
+    return dinv

@@ -2,10 +2,10 @@
 
 ``LinearSystem.reduce_system`` (``numerics/linear_system.py:64-77``) eliminates the essential
 dofs on the host with two scipy SpGEMMs (``R @ A @ R.T``); at 10^8 cells that forces a round trip
-of a multi-GB matrix.  Here the same reduction is done on the matrix where it lives (HBM): rows
-and columns of the kept dofs are selected and renumbered, ``b_0 = R (b - A ess)`` uses the SpMV
-kernel, and the reduced system goes straight to the GPU Krylov drivers.  torch is used for the
-index bookkeeping (masks, prefix sums, compaction); the arithmetic (SpMV, CG/MINRES) is libpgb.
+of a multi-GB matrix.  Here the same reduction runs where the matrix lives: ``pgb_mask_to_map``
+numbers the free dofs, ``pgb_csr_extract_*`` select their rows and columns (count -> scan -> fill,
+O(n) scratch), ``b_0 = R (b - A ess)`` is one SpMV + one gather, and the reduced system goes
+straight to the GPU Krylov drivers.
 """
 
 from __future__ import annotations
@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from ._lib import check, lib
-from .engine import DeviceCSR, _stream, _to_dev
+from .engine import DeviceCSR, _stream, _to_dev, mask_to_map
 from .solvers import cg_device, minres_device
 
 
@@ -42,40 +42,23 @@ class DeviceLinearSystem:
     def flag_ess_bc(self, is_ess_dof, ess_vals) -> None:
         m = _as_dev(is_ess_dof, self.device, torch.bool)
         v = _as_dev(ess_vals, self.device, torch.float64)
-        self.is_dof[m] = False
-        self.ess_vals[m] += v[m]
+        self.is_dof &= ~m
+        self.ess_vals += torch.where(m, v, torch.zeros_like(v))
 
     def reduce_system(self):
-        """(A_0, b_0, kept indices): rows/columns of the free dofs, rhs corrected by the essential
-        values.  Valid for the symmetric-pattern matrices of this package (CSR == CSC pattern)."""
+        """(A_0, b_0, kept dof ids): rows / columns of the free dofs, right-hand side corrected by
+        the essential values."""
         A, dev = self.A, self.device
         n = A.shape[0]
-        keep = torch.nonzero(self.is_dof).flatten()
+        newid, keep = mask_to_map(self.is_dof)
         n0 = int(keep.numel())
-        # b_0 = R (b - A ess)
-        y = torch.empty(n, dtype=torch.float64, device=dev)
+        y = A.matvec(self.ess_vals)  # A ess
+        b0 = torch.empty(n0, dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
-            check(lib.pgb_spmv(n, A.indptr.data_ptr(), A.idx64, A.indices.data_ptr(), A.data.data_ptr(),
-                               self.ess_vals.data_ptr(), y.data_ptr(), 0, _stream()))
+            check(lib.pgb_gather(n0, keep.data_ptr(), self.b.data_ptr(), y.data_ptr(), -1.0, b0.data_ptr(), _stream()))
             _lib.count(1)
-        b0 = (self.b - y)[keep].contiguous()
-        # select rows, then drop the eliminated columns
-        newid = torch.full((n,), -1, dtype=torch.int64, device=dev)
-        newid[keep] = torch.arange(n0, device=dev)
-        ip = A.indptr.to(torch.int64)
-        lens = ip[keep + 1] - ip[keep]
-        row_of = torch.repeat_interleave(torch.arange(n0, device=dev), lens)
-        start = torch.zeros(n0 + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(lens, 0, out=start[1:])
-        pos = ip[keep][row_of] + (torch.arange(int(start[-1].item()), device=dev) - start[:-1][row_of])
-        cols = newid[A.indices[pos].to(torch.int64)]
-        ok = cols >= 0
-        cols, vals, row_of = cols[ok], A.data[pos][ok], row_of[ok]
-        counts = torch.bincount(row_of, minlength=n0)
-        indptr = torch.zeros(n0 + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(counts, 0, out=indptr[1:])
-        it = torch.int64 if int(indptr[-1].item()) >= 2**31 else torch.int32
-        A0 = DeviceCSR((n0, n0), indptr.to(it), cols.to(torch.int32).contiguous(), vals.contiguous())
+        del y
+        A0 = A.extract(keep, newid, n0)
         return A0, b0, keep
 
     def solve(self, solver: str = "cg", **kw):
@@ -84,5 +67,7 @@ class DeviceLinearSystem:
         fn = {"cg": cg_device, "minres": minres_device}[solver]
         x0, info = fn(A0, b0, **kw)
         x = self.ess_vals.clone()
-        x[keep] += x0
+        with torch.cuda.device(self.device):
+            check(lib.pgb_scatter_add(int(keep.numel()), keep.data_ptr(), x0.data_ptr(), x.data_ptr(), _stream()))
+            _lib.count(1)
         return x, info

@@ -23,7 +23,7 @@ import scipy.sparse as sps
 
 from . import engine
 from .constants import SCALAR, SECOND_ORDER_TENSOR, UNITARY_DATA, VECTOR, WEIGHT
-from .params import get_cell_data
+from .params import coefficient
 
 
 class Discretization(abc.ABC):
@@ -47,8 +47,8 @@ class Discretization(abc.ABC):
 
     # ---- coefficients ------------------------------------------------------------------
     def _coefficients(self, sd, data):
-        w = get_cell_data(sd, data, self.keyword, WEIGHT)
-        K = get_cell_data(sd, data, self.keyword, SECOND_ORDER_TENSOR)
+        w = coefficient(sd, data, self.keyword, WEIGHT)
+        K = coefficient(sd, data, self.keyword, SECOND_ORDER_TENSOR)
         return w, K
 
     # ---- mass --------------------------------------------------------------------------
@@ -80,10 +80,11 @@ class Discretization(abc.ABC):
         """Lumped mass (``discretization.py:91-110``; ``RT0`` override ``fem/hdiv.py:140-175``)."""
         if self.ndof(sd) == 0:
             return sps.csc_array((0, 0))
-        A = self.assemble_lumped_matrix_device(sd, data)
         if self._lumped_diagonal:
+            A = self.assemble_lumped_matrix_device(sd, data)
             return sps.diags_array(A.diagonal().cpu().numpy()).tocsc()
-        return A.to_scipy("csc")
+        w, K = self._coefficients(sd, data)
+        return engine.assemble_host(self._space, "lumped", sd, w, K)
 
     # ---- stiffness ---------------------------------------------------------------------
     def _stiff_form(self, sd) -> str:
@@ -144,7 +145,7 @@ class PwConstants(Discretization):
         return sd.num_cells
 
     def assemble_mass_diagonal_device(self, sd, data: dict | None = None):
-        w = get_cell_data(sd, data, self.keyword, WEIGHT)
+        w = coefficient(sd, data, self.keyword, WEIGHT)
         return engine.cell_volumes_inverse_weighted(sd, w)
 
     def assemble_mass_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
@@ -194,7 +195,8 @@ class Lagrange1(Discretization):
 
     def assemble_grad_grad_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
         """``(K grad u, grad v)`` (``fem/h1.py:39-63``)."""
-        return self.assemble_grad_grad_matrix_device(sd, data).to_scipy("csc")
+        w, K = self._coefficients(sd, data)
+        return engine.assemble_host(self._space, "stiff", sd, w, K)
 
     def assemble_diff_matrix(self, sd) -> sps.csc_array:
         """``fem/h1.py:152-179``."""

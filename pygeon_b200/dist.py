@@ -343,10 +343,10 @@ def assemble_slab(space: str, form: str, sd: SimplexGrid, data=None, keyword="un
     """Assemble the owned rows of ``space``/``form`` on this rank's slab grid (owned + halo cells)."""
     from . import engine
     from .constants import SECOND_ORDER_TENSOR, WEIGHT
-    from .params import get_cell_data
+    from .params import coefficient
 
-    w = get_cell_data(sd, data, keyword, WEIGHT)
-    K = get_cell_data(sd, data, keyword, SECOND_ORDER_TENSOR)
+    w = coefficient(sd, data, keyword, WEIGHT)
+    K = coefficient(sd, data, keyword, SECOND_ORDER_TENSOR)
     if space == "lagrange1":
         K = None if form == "mass" else K
     A = engine.assemble_device(space, form, sd, w, K)

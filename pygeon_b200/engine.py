@@ -443,6 +443,10 @@ class DeviceCSR:
     indptr: torch.Tensor
     indices: torch.Tensor
     data: torch.Tensor
+    # True: the matrix equals its transpose (symmetric coefficient tensor), so the arrays may be read
+    # as CSR or CSC alike.  False: the arrays are the CSR arrays of the matrix (what SpMV / CG /
+    # MINRES / reduce_system consume); a CSC host copy then needs a real transposition.
+    symmetric: bool = True
 
     @property
     def nnz(self) -> int:
@@ -463,17 +467,37 @@ class DeviceCSR:
         if self.shape[0] == 0:
             return cls(self.shape)
         ip, ix, da = _to_host([self.indptr, self.indices, self.data])
+        if fmt == "csc" and not self.symmetric:  # arrays are CSR of a non-symmetric matrix
+            return sps.csr_array((da, ix, ip), shape=self.shape).tocsc()
         return cls((da, ix, ip), shape=self.shape)
 
     def diagonal(self) -> torch.Tensor:
-        """Diagonal entries (every row of the structural patterns built here has one)."""
+        """Diagonal entries (``pgb_csr_diagonal``; 0 for a row without one)."""
         n = self.shape[0]
-        counts = (self.indptr[1:] - self.indptr[:-1]).to(torch.int64)
-        row_of = torch.repeat_interleave(torch.arange(n, device=self.data.device), counts)
-        mask = self.indices.to(torch.int64) == row_of
-        out = torch.zeros(n, dtype=torch.float64, device=self.data.device)
-        out[row_of[mask]] = self.data[mask]
+        dev = self.data.device
+        out = torch.empty(n, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pgb_csr_diagonal(n, self.indptr.data_ptr(), self.idx64, self.indices.data_ptr(),
+                                       self.data.data_ptr(), out.data_ptr(), _stream()))
+            _lib.count(1)
         return out
+
+    def matvec(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """``A @ x`` on the device (``pgb_spmv``)."""
+        n = self.shape[0]
+        y = torch.empty(n, dtype=torch.float64, device=self.data.device) if out is None else out
+        with torch.cuda.device(self.data.device):
+            check(lib.pgb_spmv(n, self.indptr.data_ptr(), self.idx64, self.indices.data_ptr(), self.data.data_ptr(),
+                               x.data_ptr(), y.data_ptr(), 0, _stream()))
+            _lib.count(1)
+        return y
+
+    def extract(self, rows: torch.Tensor | None, col_map: torch.Tensor | None, n_cols: int) -> "DeviceCSR":
+        """Rows ``rows`` (int32 ids, None = all) with the columns renumbered through ``col_map`` (int32,
+        -1 = dropped, None = unchanged): count -> scan -> fill kernels, O(rows) scratch."""
+        rows_out = self.shape[0] if rows is None else int(rows.numel())
+        ip, ix, da = extract_rows(self.indptr, self.indices, self.data, rows, col_map)
+        return DeviceCSR((rows_out, n_cols), ip, ix, da, symmetric=self.symmetric)
 
     @staticmethod
     def from_scipy(A, device=None) -> "DeviceCSR":
@@ -487,7 +511,52 @@ class DeviceCSR:
             _to_dev(A.indptr, dev, it),
             _to_dev(A.indices, dev, _I32),
             _to_dev(A.data.astype(np.float64, copy=False), dev),
+            symmetric=False,  # unknown: the arrays are CSR, a CSC copy is made by transposition
         )
+
+
+def mask_to_map(mask: torch.Tensor, want_newid: bool = True):
+    """(newid int32 (n,) with -1 for dropped entries | None, kept ids int32 (count,)) of a bool mask
+    (``pgb_mask_to_map``)."""
+    dev = mask.device
+    n = int(mask.numel())
+    m8 = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else (mask != 0).view(torch.uint8)
+    with torch.cuda.device(dev):
+        s = _stream()
+        ws_bytes = int(lib.pgb_system_workspace_bytes(n))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        cnt = C.c_int64(0)
+        check(lib.pgb_mask_to_map(n, m8.data_ptr(), 0, 0, C.byref(cnt), ws.data_ptr(), ws_bytes, s))
+        newid = torch.empty(n, dtype=_I32, device=dev) if want_newid else None
+        rows = torch.empty(int(cnt.value), dtype=_I32, device=dev)
+        check(lib.pgb_mask_to_map(n, m8.data_ptr(), _ptr(newid), rows.data_ptr(), None, ws.data_ptr(), ws_bytes, s))
+        _lib.count(7)
+    return newid, rows
+
+
+def extract_rows(indptr, indices, data, rows, col_map):
+    """``pgb_csr_extract_symbolic`` + ``pgb_csr_extract_fill``: (indptr, indices, data) of the selected rows."""
+    dev = indices.device
+    n_out = int(indptr.numel()) - 1 if rows is None else int(rows.numel())
+    idx64 = 1 if indptr.dtype == torch.int64 else 0
+    with torch.cuda.device(dev):
+        s = _stream()
+        ws_bytes = int(lib.pgb_system_workspace_bytes(n_out))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ip = torch.empty(n_out + 1, dtype=torch.int64, device=dev)
+        nnz = C.c_int64(0)
+        check(lib.pgb_csr_extract_symbolic(n_out, _ptr(rows), indptr.data_ptr(), idx64, indices.data_ptr(),
+                                           _ptr(col_map), ip.data_ptr(), C.byref(nnz), ws.data_ptr(), ws_bytes, s))
+        del ws
+        nnz = int(nnz.value)
+        ix = torch.empty(nnz, dtype=_I32, device=dev)
+        da = torch.empty(nnz, dtype=torch.float64, device=dev)
+        check(lib.pgb_csr_extract_fill(n_out, _ptr(rows), indptr.data_ptr(), idx64, indices.data_ptr(),
+                                       data.data_ptr(), _ptr(col_map), ip.data_ptr(), ix.data_ptr(), da.data_ptr(), s))
+        _lib.count(5)
+        if nnz < 2**31 and not force_idx64:
+            ip = ip.to(_I32)
+    return ip, ix, da
 
 
 symbolic_mode = 0  # 0 = two-level (default), 1 = full (row,col) radix sort; see include/pgb.h
@@ -655,17 +724,31 @@ def assemble_on_pack(pack: GridPack, space: str, kind: str, wd=None, Kd=None):
     return plan, numeric(plan, vals)
 
 
+def tensor_is_symmetric(K) -> bool:
+    """True when every (3, 3) block of ``K`` (3, 3, nc) equals its transpose."""
+    return K is None or all(np.array_equal(K[i, j], K[j, i]) for i, j in ((0, 1), (0, 2), (1, 2)))
+
+
 def assemble_device(space: str, form: str, sd, w=None, K=None, device=None) -> DeviceCSR:
     """Full assembly on the device: pack (cached) -> K1 -> K2.  ``w``/``K`` are host numpy
-    arrays in the reference's layout or None."""
+    arrays in the reference's layout or None.
+
+    The result is consumed as **CSR** on the device (SpMV, CG, MINRES, ``reduce_system``).  K1 builds
+    ``A[a][b] = u_a^T (R K R^T) u_b`` whose CSR arrays are the CSC arrays of the reference's matrix
+    (its contraction yields ``R K^T R^T``, fem/vec_l2.py:113-114; pgb.h K1 note), so a
+    non-symmetric tensor goes in transposed here: the arrays are then the CSR arrays of the
+    reference's matrix itself."""
     pack = get_pack(sd, device)
     dev = pack.device
     kind = _FORMS[(space, form)]
+    sym = tensor_is_symmetric(K)
+    if not sym:
+        K = np.ascontiguousarray(np.transpose(K, (1, 0, 2)))
     wd = None if w is None else _to_dev(w, dev)
     Kd = None if K is None else _to_dev(K, dev)
     plan, data = assemble_on_pack(pack, space, kind, wd, Kd)
     n = plan.n_rows
-    return DeviceCSR((n, n), plan.indptr, plan.indices, data)
+    return DeviceCSR((n, n), plan.indptr, plan.indices, data, symmetric=sym)
 
 
 def assemble_host(space: str, form: str, sd, w=None, K=None, device=None, fmt: str = "csc"):
@@ -677,6 +760,8 @@ def assemble_host(space: str, form: str, sd, w=None, K=None, device=None, fmt: s
     dev = pack.device
     kind = _FORMS[(space, form)]
     cls = sps.csc_array if fmt == "csc" else sps.csr_array
+    if fmt != "csc" and not tensor_is_symmetric(K):  # CSR of the reference matrix: see assemble_device
+        K = np.ascontiguousarray(np.transpose(K, (1, 0, 2)))
     with torch.cuda.device(dev):
         wd = None if w is None else _to_dev(w, dev)
         Kd = None if K is None else _to_dev(K, dev)

@@ -118,15 +118,15 @@ class SimplexGrid:
         self.face_centers = x[:, fn].mean(axis=2)
         cni = self.cell_node_table()
         self.cell_centers = x[:, cni].mean(axis=2)
-        if np.any(x[d:, :]):
-            raise NotImplementedError("tilted grids need pp.map_geometry (not available)")
-        self.rotation_matrix = np.eye(d, AMBIENT_DIM)
+        self.compute_rotation_matrix()
         if d == 2:
+            # in-plane normal of the stored node order: t x n_plane (= (t_y, -t_x, 0) in the xy-plane)
+            R = self.rotation_matrix
             t = x[:, fn[:, 1]] - x[:, fn[:, 0]]
-            self.face_normals = np.vstack([t[1], -t[0], np.zeros(self.num_faces)])
+            self.face_normals = np.cross(t, np.cross(R[0], R[1])[:, None], axis=0)
             a = x[:, cni[:, 1]] - x[:, cni[:, 0]]
             b = x[:, cni[:, 2]] - x[:, cni[:, 0]]
-            self.cell_volumes = 0.5 * np.abs(a[0] * b[1] - a[1] * b[0])
+            self.cell_volumes = 0.5 * np.linalg.norm(np.cross(a, b, axis=0), axis=0)
         else:
             a = x[:, fn[:, 1]] - x[:, fn[:, 0]]
             b = x[:, fn[:, 2]] - x[:, fn[:, 0]]
@@ -155,12 +155,47 @@ class SimplexGrid:
         self._compute_edge_properties()
         self._geometry_done = True
 
+    def compute_rotation_matrix(self) -> None:
+        """``rotation_matrix`` (dim x 3, orthonormal rows): maps the grid's plane to the xy-plane
+        (``grids/grid.py:355-370``).  The reference takes it from ``pp.map_geometry.map_grid`` (PorePy,
+        absent here): the rotation about ``n x e_z`` by the angle between the plane normal ``n`` and
+        ``e_z`` (Rodrigues' formula), of which the first ``dim`` rows are kept.  Restated here; every
+        matrix assembled from it only depends on the plane, not on the in-plane basis."""
+        d = self.dim
+        if d == 3 or not np.any(self.nodes[d:, :]):
+            self.rotation_matrix = np.eye(d, AMBIENT_DIM)
+            return
+        if d != 2:
+            raise NotImplementedError("only 2D grids embedded in 3D are supported")
+        x = self.nodes
+        fn = self.face_nodes.indices.reshape(self.num_faces, 2)
+        cf = self.cell_faces.indices.reshape(self.num_cells, 3)
+        # normal of the largest-area corner of the first cell; the sign convention follows that cell
+        tri = np.unique(fn[cf[0]].ravel())
+        nvec = np.cross(x[:, tri[1]] - x[:, tri[0]], x[:, tri[2]] - x[:, tri[0]])
+        nvec = nvec / np.linalg.norm(nvec)
+        if nvec[2] < 0:
+            nvec = -nvec
+        ez = np.array([0.0, 0.0, 1.0])
+        axis = np.cross(nvec, ez)
+        s, c = np.linalg.norm(axis), float(nvec @ ez)
+        if s < 1e-15:
+            R = np.eye(3)
+        else:
+            axis /= s
+            W = np.array([[0.0, -axis[2], axis[1]], [axis[2], 0.0, -axis[0]], [-axis[1], axis[0], 0.0]])
+            R = c * np.eye(3) + s * W + (1.0 - c) * np.outer(axis, axis)
+        planar = R @ (x - x[:, :1])
+        if np.abs(planar[2]).max() > 1e-10 * max(np.abs(planar).max(), 1e-300):
+            raise ValueError("the nodes of a 2D grid must lie in one plane")
+        self.rotation_matrix = R[:2]
+
     def _compute_geometry_device(self, device) -> None:
         from . import connectivity, engine
 
         d, nc, nf = self.dim, self.num_cells, self.num_faces
         if np.any(self.nodes[d:, :]):
-            raise NotImplementedError("tilted grids need pp.map_geometry (not available)")
+            raise NotImplementedError("device geometry supports axis-aligned grids; use compute_geometry() for tilted ones")
         self.rotation_matrix = np.eye(d, AMBIENT_DIM)
         raw = engine.RawGrid.upload(self, device, signs=True)
         pack = engine.GridPack.from_raw(raw)  # NotImplementedError for non-simplicial grids
@@ -509,6 +544,20 @@ def structured_grid(dim: int, n: int, perturb: float = 0.0, seed: int = 0, devic
     keep = ("face_ridges", "face_ridge_sign", "ridge_peaks", "face_keys", "edge_keys", "key_bits", "cell_nodes")
     sd._structured = {k: con[k] for k in con if k in keep}
     sd._structured.update(n=n, nz=(n if nz is None else nz), z0=z0)
+    return sd
+
+
+def unit_grid(dim: int, mesh_size: float, as_mdg: bool = True, structured: bool = True, **kwargs):
+    """``pg.unit_grid(dim, mesh_size, as_mdg=..., structured=True)`` (``grids/create_grid.py:115-156``):
+    the structured simplicial unit square / cube with ``round(1 / mesh_size)`` cells per side.  The
+    unstructured (gmsh) branch of the reference is not available."""
+    if not structured:
+        raise NotImplementedError("unstructured grids need gmsh; use structured=True")
+    sd = structured_grid(dim, max(int(np.round(1.0 / mesh_size)), 1), **kwargs)
+    if as_mdg:
+        from .md_grid import as_mdg as _as_mdg
+
+        return _as_mdg(sd)
     return sd
 
 

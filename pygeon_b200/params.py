@@ -9,9 +9,10 @@ from __future__ import annotations
 
 import numpy as np
 
-from .constants import PARAMETERS, SECOND_ORDER_TENSOR, WEIGHT
+from .constants import (AMBIENT_DIM, MATRIX, NORMAL_DIFFUSIVITY, PARAMETERS, SCALAR, SECOND_ORDER_TENSOR, VECTOR,
+                        VECTOR_FIELD, WEIGHT)
 
-data_default = {SECOND_ORDER_TENSOR: 1, WEIGHT: 1}
+data_default = {SECOND_ORDER_TENSOR: 1, VECTOR_FIELD: np.zeros(AMBIENT_DIM), WEIGHT: 1, NORMAL_DIFFUSIVITY: 1}
 
 
 class SecondOrderTensor:
@@ -39,17 +40,35 @@ def initialize_data(data: dict, keyword: str, specified_parameters: dict | None 
     return data
 
 
-def get_cell_data(sd, data, keyword: str, param: str):
-    """Raw parameter value, or the default (``params/data.py:91-103``).  Returns
+def _lookup(data, keyword: str, param: str):
+    if not data or PARAMETERS not in data or keyword not in data[PARAMETERS]:
+        return data_default[param]
+    return data[PARAMETERS][keyword].get(param, data_default[param])
+
+
+def get_cell_data(sd, data, keyword: str, param: str, tensor_order: int = SCALAR):
+    """``pg.get_cell_data`` (``params/data.py:61-118``): the parameter stored under
+    ``data[PARAMETERS][keyword][param]`` or its default; scalars are broadcast to one value per cell
+    (wrapped in a :class:`SecondOrderTensor` for ``tensor_order == MATRIX``), a single vector is
+    repeated for every cell when ``tensor_order == VECTOR``.  ``sd`` may be a mortar grid."""
+    value = _lookup(data, keyword, param)
+    if isinstance(value, np.ScalarType):
+        value = np.full(sd.num_cells, value)
+        if tensor_order == MATRIX:
+            value = SecondOrderTensor(value)
+    if isinstance(value, np.ndarray) and tensor_order == VECTOR and value.ndim == 1:
+        value = np.tile(value.reshape(-1, 1), (1, sd.num_cells))
+    return value
+
+
+def coefficient(sd, data, keyword: str, param: str):
+    """The engine's view of a coefficient: ``None`` when it has its default value (nothing is
+    uploaded, the kernels use 1 / identity), otherwise a validated float64 array.  Returns
 
     * for ``WEIGHT``: ``None`` (all ones) or a float64 array (nc,)
     * for ``SECOND_ORDER_TENSOR``: ``None`` (identity) or a float64 array (3, 3, nc)
     """
-    if not data or PARAMETERS not in data or keyword not in data[PARAMETERS]:
-        params = {}
-    else:
-        params = data[PARAMETERS][keyword]
-    value = params.get(param, data_default[param])
+    value = _lookup(data, keyword, param)
     nc = sd.num_cells
     if param == WEIGHT:
         if np.isscalar(value):

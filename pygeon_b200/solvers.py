@@ -38,41 +38,55 @@ def _vec(b, dev) -> torch.Tensor:
     return _to_dev(np.ascontiguousarray(b, dtype=np.float64), dev)
 
 
+RESID_CAP = 1 << 20  # PGB_RESID_CAP: residual-history entries kept per solve
+_INT_MAX = 2**31 - 1
+
+
+def _maxiter(maxiter, default: int) -> int:
+    """scipy's default (``10 n`` for cg, ``5 n`` for minres) clamped to the C ABI's ``int``; an explicit
+    value outside that range is an error, not a silent wrap-around."""
+    if maxiter is None:
+        return min(int(default), _INT_MAX)
+    maxiter = int(maxiter)
+    if not 0 <= maxiter <= _INT_MAX:
+        raise ValueError(f"maxiter = {maxiter} does not fit the C ABI's int")
+    return maxiter
+
+
 def cg_device(A: DeviceCSR, b: torch.Tensor, x0=None, *, rtol=1e-5, atol=0.0, maxiter=None, dinv=None):
-    """CG on device tensors.  Returns ``(x, SolveInfo)``; ``info`` is 0 or ``maxiter`` like scipy."""
+    """CG on device tensors.  Returns ``(x, SolveInfo)``; ``info`` is 0 or ``maxiter`` like scipy.
+    ``SolveInfo.residuals`` holds at most ``RESID_CAP`` entries (the first ones)."""
     n = A.shape[0]
     dev = b.device
-    if maxiter is None:
-        maxiter = 10 * n
+    maxiter = _maxiter(maxiter, 10 * n)
     with torch.cuda.device(dev):
         x = torch.zeros(n, dtype=torch.float64, device=dev) if x0 is None else x0.clone()
         work = torch.empty(3 * n, dtype=torch.float64, device=dev)
-        resid = np.zeros(maxiter + 1)
+        resid = np.zeros(min(maxiter + 1, RESID_CAP))
         it, info = C.c_int(0), C.c_int(0)
         check(lib.pgb_cg(n, A.indptr.data_ptr(), A.idx64, A.indices.data_ptr(), A.data.data_ptr(),
                          b.data_ptr(), x.data_ptr(), _ptr(dinv), float(rtol), float(atol), int(maxiter),
                          work.data_ptr(), C.byref(it), C.byref(info), resid.ctypes.data, _stream()))
         _lib.count(2 + 3 * it.value)
     k = it.value
-    return x, SolveInfo(k, info.value, resid[: k + 1].copy())
+    return x, SolveInfo(k, info.value, resid[: min(k + 1, resid.size)].copy())
 
 
 def minres_device(A: DeviceCSR, b: torch.Tensor, x0=None, *, rtol=1e-5, shift=0.0, maxiter=None, dinv=None):
     n = A.shape[0]
     dev = b.device
-    if maxiter is None:
-        maxiter = 5 * n
+    maxiter = _maxiter(maxiter, 5 * n)
     with torch.cuda.device(dev):
         x = torch.zeros(n, dtype=torch.float64, device=dev) if x0 is None else x0.clone()
         work = torch.empty(6 * n, dtype=torch.float64, device=dev)
-        resid = np.zeros(maxiter + 1)
+        resid = np.zeros(min(maxiter + 1, RESID_CAP))
         it, info = C.c_int(0), C.c_int(0)
         check(lib.pgb_minres(n, A.indptr.data_ptr(), A.idx64, A.indices.data_ptr(), A.data.data_ptr(),
                              b.data_ptr(), x.data_ptr(), _ptr(dinv), float(shift), float(rtol), int(maxiter),
                              work.data_ptr(), C.byref(it), C.byref(info), resid.ctypes.data, _stream()))
         _lib.count(5 + 4 * it.value)
     k = it.value
-    return x, SolveInfo(k, info.value, resid[:k].copy())
+    return x, SolveInfo(k, info.value, resid[: min(k, resid.size)].copy())
 
 
 def _columns(fn, A, b, device):
@@ -116,21 +130,41 @@ def minres(A, b, x0=None, *, rtol=1e-5, shift=0.0, maxiter=None, M=None, device=
     return x, (info.info if isinstance(info, SolveInfo) else max(i.info for i in info))
 
 
-def cg_solver(**kw):
-    """``solver`` callable for ``LinearSystem.solve``: ``ls.solve(cg_solver(rtol=1e-10))``."""
+def _make_solver(kind: str, host_fn, dev_fn, kw: dict):
+    """``solver`` callable for ``LinearSystem.solve``.  Called as ``solver(A, b)`` it behaves like any
+    scipy-style solver; ``pg.LinearSystem`` recognises ``pgb_kind`` and keeps the elimination of the
+    essential dofs and the solve on the device (``linear_system.py:79-94`` is the host version)."""
+    device = kw.pop("device", None)
 
     def solver(A, b):
-        x, info = cg(A, b, **kw)
-        solver.info = cg.last_info
+        x, _ = host_fn(A, b, device=device, **kw)
+        solver.info = host_fn.last_info
         return x
 
+    def pgb_solve(A0, b0, keep, dls):
+        dkw = dict(kw)
+        M = dkw.pop("M", None)
+        if M is not None:  # inverse diagonal over all dofs or over the free ones
+            M = _vec(M if isinstance(M, torch.Tensor) else np.asarray(M), b0.device)
+            dkw["dinv"] = M[keep.long()] if M.numel() != b0.numel() else M
+        x0, info = dev_fn(A0, b0, **dkw)
+        x = dls.ess_vals.clone()
+        with torch.cuda.device(b0.device):
+            check(lib.pgb_scatter_add(int(keep.numel()), keep.data_ptr(), x0.data_ptr(), x.data_ptr(), _stream()))
+            _lib.count(1)
+        return x, info
+
+    solver.pgb_kind = kind
+    solver.pgb_device = device
+    solver.pgb_solve = pgb_solve
+    solver.info = None
     return solver
+
+
+def cg_solver(**kw):
+    """``ls.solve(pg.cg_solver(rtol=1e-10))``: CG with scipy's recurrence and stopping rule."""
+    return _make_solver("cg", cg, cg_device, dict(kw))
 
 
 def minres_solver(**kw):
-    def solver(A, b):
-        x, info = minres(A, b, **kw)
-        solver.info = minres.last_info
-        return x
-
-    return solver
+    return _make_solver("minres", minres, minres_device, dict(kw))

@@ -6,7 +6,7 @@ import scipy.sparse as sps
 
 import pygeon_b200 as pg
 from pygeon_b200.linear_system import LinearSystem, create_restriction
-from pygeon_b200.params import get_cell_data
+from pygeon_b200.params import coefficient as get_cell_data
 
 
 def test_get_cell_data_defaults_and_broadcast():

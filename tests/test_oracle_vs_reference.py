@@ -16,6 +16,30 @@ TOL = 1e-12
 GRIDS = [(2, 4, 0.2), (3, 3, 0.2), (3, 4, 0.0), (2, 8, 0.0)]
 
 
+@pytest.mark.parametrize("mode", ["default", "sym", "nonsym"])
+def test_oracle_matches_reference_on_tilted_grid(ref, mode):
+    """Non-identity rotation_matrix (grids/grid.py:355-370; used at vec_l2.py:113-114, hdiv.py:493,
+    hcurl.py:276): a 2D grid moved rigidly into a generic plane of R^3, on the reference pg.Grid."""
+    from oracle.gen_golden import tilt
+
+    pg, pp = ref
+    sd = tilt(structured_grid(2, 4, perturb=0.2))
+    sd.compute_geometry()
+    g = ref_loader.ref_grid(sd)
+    assert np.abs(g.rotation_matrix - np.eye(2, 3)).max() > 0.1
+    assert np.allclose(g.rotation_matrix, sd.rotation_matrix, atol=1e-15)
+    data = None if mode == "default" else _data(pg, pp, sd.num_cells, mode == "sym")
+    cls = {"lagrange1": pg.Lagrange1, "rt0": pg.RT0, "bdm1": pg.BDM1, "nedelec0": pg.Nedelec0}
+    for G in (g, sd):
+        tabs = fo.cell_tables(G)
+        for space, c in cls.items():
+            for form, fn in (("mass", "assemble_mass_matrix"), ("stiff", "assemble_stiff_matrix")):
+                refm = sps.csr_array(getattr(c("k"), fn)(g, data))
+                closed = fo.closed_form(space, form, G, data, "k", tabs)
+                refS = fo.canonicalise(refm, closed)
+                assert np.abs(refS.data - closed.data).max() <= TOL * abs(refm).max()
+
+
 @pytest.fixture(scope="module")
 def ref():
     return ref_loader.load()

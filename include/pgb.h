@@ -306,7 +306,50 @@ int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_t* indices,
                double rtol, int maxiter, double* work, int* iters_host, int* info_host,
                double* resid_host, void* stream);
 
-/* Building blocks used by the multi-GPU drivers (halo exchange / allreduce happen between
+/* ---- K4: row-distributed CG / MINRES over NVLink peer memory (one process per GPU, one node) --------
+ * The reference has no distributed path; these are the multi-GPU form of pgb_cg /
+ * pgb_minres for the cell-partitioned systems of SURVEY 8(e).  The halo exchange and the global sums are
+ * done BY THE KRYLOV KERNELS through peer-mapped memory (P2P stores + sequence flags), see pgb_dist.cu.
+ *
+ * Communicator: every rank calls pgb_comm_create (allocates an arena of arena_bytes + a header of flags
+ * with cudaMalloc and exports it as a cudaIpcMemHandle_t), the caller exchanges the handles
+ * (pgb_comm_handle_bytes() bytes each, e.g. with torch.distributed.all_gather) and passes all of them, in
+ * rank order, to pgb_comm_connect.  arena_bytes must be the same on every rank.
+ *
+ * System layout: the local vector is [n_owned owned | pad | n_ghost ghosts], the ghost block starting at
+ * ghost_start (a multiple of 16 entries); columns of the CSR rows use that numbering.  Halo: for send
+ * peer s, the owned entries send_idx[send_off[s] .. send_off[s+1]) go to entries
+ * [send_dst[s], send_dst[s] + count) of the peer's local vector (= its ghost_start + the start of this
+ * rank's block there).  recv_peer lists the ranks this rank receives from.  Rows [interior_lo,
+ * interior_hi) have no ghost column: they are multiplied while the halo is in flight.
+ * x0 = 0; x: n_owned entries out.  b == 0 returns x = 0, iterations 0 (scipy).  All ranks must call with
+ * the same rtol / atol / maxiter; they stop at the same iteration (the scalars are bit-identical).
+ * Returns 4 when a wait on a peer timed out. */
+int pgb_comm_create(int rank, int world, int64_t arena_bytes, void** comm_out);
+int pgb_comm_handle_bytes(void);
+int pgb_comm_get_handle(void* comm, void* handle_out_host);
+int pgb_comm_connect(void* comm, const void* all_handles_host);
+void* pgb_comm_arena(void* comm);
+int64_t pgb_comm_arena_bytes(void* comm);
+int pgb_comm_barrier(void* comm, void* stream);
+int pgb_comm_destroy(void* comm);
+/* work: 2 * n_owned doubles.  The arena must hold 2 vectors of ghost_start + n_ghost doubles (the
+ * search direction is double buffered), at byte offsets 0 and arena_bytes / 2. */
+int pgb_dist_cg(void* comm, int64_t n_owned, int64_t ghost_start, int64_t n_ghost, const void* indptr, int idx64,
+                const int32_t* indices, const double* data, const double* b, const double* dinv, double* x,
+                double* work, int nsend, const int* send_peer_host, const int64_t* send_off_host,
+                const int64_t* send_dst_host, const int32_t* send_idx, int nrecv, const int* recv_peer_host,
+                int64_t interior_lo, int64_t interior_hi, int threads_per_row, double rtol, double atol,
+                int maxiter, int* iters_host, int* info_host, double* resid_host, void* stream);
+/* work: 5 * n_owned doubles; the arena holds the Lanczos vector (ghost_start + n_ghost doubles). */
+int pgb_dist_minres(void* comm, int64_t n_owned, int64_t ghost_start, int64_t n_ghost, const void* indptr,
+                    int idx64, const int32_t* indices, const double* data, const double* b, const double* dinv,
+                    double* x, double* work, int nsend, const int* send_peer_host, const int64_t* send_off_host,
+                    const int64_t* send_dst_host, const int32_t* send_idx, int nrecv, const int* recv_peer_host,
+                    int64_t interior_lo, int64_t interior_hi, int threads_per_row, double shift, double rtol,
+                    int maxiter, int* iters_host, int* info_host, double* resid_host, void* stream);
+
+/* Building blocks used by the NCCL multi-GPU drivers (halo exchange / allreduce happen between
  * them on the host side through NCCL). */
 /* CG step API: the fused kernels of pgb_cg one by one, so that a multi-GPU driver can interleave
  * the halo exchange (before step_spmv) and the all-reduce of the partial sums (step_reduce with

@@ -721,17 +721,23 @@ def local_matrices(space, form, sd, data=None, keyword="unitary_data", tabs=None
     return _LOCAL[(space, form)](sd, tabs, w, K, **kw)
 
 
-def closed_form(space, form, sd, data=None, keyword="unitary_data", tabs=None, **kw) -> sps.csr_array:
+def closed_form(space, form, sd, data=None, keyword="unitary_data", tabs=None, fast=False, **kw) -> sps.csr_array:
     """Structural-pattern CSR (sorted, int32, explicit zeros kept) from local matrices.
 
     Duplicates are summed in COO order = ascending cell id (the order the CUDA
-    segmented reduce uses), so values agree to the last few ulps.
+    segmented reduce uses), so values agree to the last few ulps.  ``fast=True`` lets scipy's
+    COO -> CSR constructor do the duplicate summation (same pattern, explicit zeros kept, summation
+    order unspecified: values agree to rounding) - for grids with 10^7 cells and more.
     """
     A, dofs = local_matrices(space, form, sd, data, keyword, tabs, **kw)
     n = NDOF[space](sd)
     L = dofs.shape[1]
     rows = np.broadcast_to(dofs[:, :, None], A.shape).ravel()
     cols = np.broadcast_to(dofs[:, None, :], A.shape).ravel()
+    if fast:
+        M = sps.coo_array((A.ravel(), (rows, cols)), shape=(n, n)).tocsr()
+        M.sort_indices()
+        return M
     return coo_to_csr(rows, cols, A.ravel(), n)
 
 
@@ -746,9 +752,7 @@ def coo_to_csr(rows, cols, vals, n) -> sps.csr_array:
     data = np.add.reduceat(vals[order], seg) if ks.size else np.zeros(0)
     ukey = ks[seg]
     r, c = ukey // n, ukey % n
-    indptr = np.zeros(n + 1, dtype=np.int64)
-    np.add.at(indptr, r + 1, 1)
-    indptr = np.cumsum(indptr)
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=n))]).astype(np.int64)
     it = np.int32 if ukey.size < 2**31 else np.int64
     return sps.csr_array((data, c.astype(np.int32), indptr.astype(it)), shape=(n, n))
 

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libpgb.so")
 SOURCES = ["pgb_api.cu", "pgb_pack.cu", "pgb_local.cu", "pgb_csr.cu", "pgb_rowsort.cu", "pgb_rowthread.cu",
-           "pgb_rowhash.cu", "pgb_rowlong.cu", "pgb_krylov.cu", "pgb_geometry.cu", "pgb_system.cu"]
+           "pgb_rowhash.cu", "pgb_rowlong.cu", "pgb_krylov.cu", "pgb_geometry.cu", "pgb_system.cu", "pgb_dist.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", f"-I{INCLUDE}", f"-I{CSRC}",
@@ -30,7 +30,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("pgb_common.cuh", "pgb_rows.cuh", "pgb_rt1_table.cuh")]
+    headers = [os.path.join(CSRC, h) for h in ("pgb_common.cuh", "pgb_rows.cuh", "pgb_rt1_table.cuh", "pgb_krylov.cuh")]
     headers.append(os.path.join(INCLUDE, "pgb.h"))
     srcs = [os.path.join(CSRC, src) for src in SOURCES]
     if not force and not _stale(LIB, srcs + headers):

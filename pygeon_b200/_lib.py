@@ -59,6 +59,18 @@ _SIGS = {
     "pgb_spmv": (_i, [_l, _p, _i, _p, _p, _p, _p, _i, _p]),
     "pgb_cg": (_i, [_l, _p, _i, _p, _p, _p, _p, _p, _d, _d, _i, _p, C.POINTER(_i), C.POINTER(_i), _p, _p]),
     "pgb_minres": (_i, [_l, _p, _i, _p, _p, _p, _p, _p, _d, _d, _i, _p, C.POINTER(_i), C.POINTER(_i), _p, _p]),
+    "pgb_comm_create": (_i, [_i, _i, _l, C.POINTER(C.c_void_p)]),
+    "pgb_comm_handle_bytes": (_i, []),
+    "pgb_comm_get_handle": (_i, [_p, _p]),
+    "pgb_comm_connect": (_i, [_p, _p]),
+    "pgb_comm_arena": (C.c_void_p, [_p]),
+    "pgb_comm_arena_bytes": (_l, [_p]),
+    "pgb_comm_barrier": (_i, [_p, _p]),
+    "pgb_comm_destroy": (_i, [_p]),
+    "pgb_dist_cg": (_i, [_p, _l, _l, _l, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _l, _l, _i,
+                         _d, _d, _i, C.POINTER(_i), C.POINTER(_i), _p, _p]),
+    "pgb_dist_minres": (_i, [_p, _l, _l, _l, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _l, _l, _i,
+                             _d, _d, _i, C.POINTER(_i), C.POINTER(_i), _p, _p]),
     "pgb_cg_scratch_doubles": (_l, [_i]),
     "pgb_cg_step_init": (_i, [_l, _p, _p, _p, _p, _d, _d, _p, _p]),
     "pgb_cg_step_reduce": (_i, [_p, _i, _i, _p]),

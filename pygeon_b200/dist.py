@@ -174,10 +174,28 @@ class DistCSR:
     send_idx: dict = field(default_factory=dict)  # peer -> indices into the owned block
     recv_range: dict = field(default_factory=dict)  # peer -> (start, count) inside the ghost block
     group: object = None
+    send_dst: dict = field(default_factory=dict)  # peer -> first entry of this rank's block in the peer's local vector
+    n_local_max: int = 0  # largest local vector length over the ranks (sizes the peer-memory arena)
+    _peer: object = None  # PeerComm + flattened halo description, built on first use
+    _interior: tuple | None = None
+
+    @property
+    def ghost_start(self) -> int:
+        """First ghost entry of a local vector: the owned block padded to a multiple of 16 doubles, so that
+        no 128-byte line holds owned and ghost entries together (peers store into the ghost block while the
+        interior rows of the SpMV are already reading owned entries)."""
+        return (self.n_owned + 15) // 16 * 16
 
     @property
     def n_local(self) -> int:
-        return self.n_owned + self.n_ghost
+        return self.ghost_start + self.n_ghost
+
+    def column_ids(self) -> torch.Tensor:
+        """Local grid id of every local column (length ``n_local``; -1 in the padding)."""
+        ids = torch.full((self.n_local,), -1, dtype=torch.int64, device=self.owned_local.device)
+        ids[: self.n_owned] = self.owned_local
+        ids[self.ghost_start:] = self.ghost_local
+        return ids
 
     @property
     def nnz(self) -> int:
@@ -207,27 +225,40 @@ def build_dist_csr(indptr, indices, data, owned: torch.Tensor, keys: torch.Tenso
     ``indptr / indices / data``: CSR over all local dofs (torch tensors, any device);
     ``owned``: bool mask over local dofs; ``keys``: partition-independent int64 key per local dof.
     ``comm_device``: device of the tensors handed to the collectives (cuda for nccl, cpu for gloo).
-    """
+    On a CUDA device the rows are selected and renumbered by the extraction kernels
+    (``pgb_mask_to_map`` / ``pgb_csr_extract_*``: O(rows) scratch); the torch version below serves the
+    CPU (gloo) tests of the partition logic."""
     dev = indices.device
     comm_device = dev if comm_device is None else torch.device(comm_device)
     owned = owned.to(dev)
     keys = keys.to(dev)
     n_local = owned.numel()
-    own = torch.nonzero(owned).flatten()
-    n_owned = int(own.numel())
-    ip = indptr.to(torch.int64)
-    lens = ip[own + 1] - ip[own]
-    new_ip = torch.zeros(n_owned + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(lens, 0, out=new_ip[1:])
-    nnz = int(new_ip[-1].item())
-    # positions of the kept entries in the old arrays
-    row_of = torch.repeat_interleave(torch.arange(n_owned, device=dev), lens)
-    pos = ip[own][row_of] + (torch.arange(nnz, device=dev) - new_ip[:-1][row_of])
-    cols = indices[pos].to(torch.int64)
-    vals = data[pos]
-    # ghost columns: referenced, not owned
-    ref = torch.zeros(n_local, dtype=torch.bool, device=dev)
-    ref[cols] = True
+    cuda = dev.type == "cuda"
+    if cuda:
+        from . import engine
+
+        _, own32 = engine.mask_to_map(owned, want_newid=False)
+        own = own32.long()
+        n_owned = int(own.numel())
+        # referenced columns of the owned rows: one pass with the identity map, then a flag scatter
+        ip0, cols0, _ = engine.extract_rows(indptr, indices, data, own32, None)
+        ref = torch.zeros(n_local, dtype=torch.bool, device=dev)
+        ref[cols0.long()] = True
+        del ip0, cols0
+    else:
+        own = torch.nonzero(owned).flatten()
+        n_owned = int(own.numel())
+        ip = indptr.to(torch.int64)
+        lens = ip[own + 1] - ip[own]
+        new_ip = torch.zeros(n_owned + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(lens, 0, out=new_ip[1:])
+        nnz = int(new_ip[-1].item())
+        row_of = torch.repeat_interleave(torch.arange(n_owned, device=dev), lens)
+        pos = ip[own][row_of] + (torch.arange(nnz, device=dev) - new_ip[:-1][row_of])
+        cols = indices[pos].to(torch.int64)
+        vals = data[pos]
+        ref = torch.zeros(n_local, dtype=torch.bool, device=dev)
+        ref[cols] = True
     ghost = torch.nonzero(ref & ~owned).flatten()
     gkeys = keys[ghost]
 
@@ -275,14 +306,30 @@ def build_dist_csr(indptr, indices, data, owned: torch.Tensor, keys: torch.Tenso
                 recv_range[q] = (start, cnt)
     elif ghost.numel():
         raise RuntimeError("ghost dofs in a single-rank run")
-    # renumber the columns
-    newid = torch.full((n_local,), -1, dtype=torch.int64, device=dev)
-    newid[own] = torch.arange(n_owned, device=dev)
-    newid[ghost] = n_owned + torch.arange(ghost.numel(), device=dev)
-    ncols = newid[cols]
-    it = torch.int64 if nnz >= 2**31 else torch.int32
-    return DistCSR(n_owned, int(ghost.numel()), new_ip.to(it), ncols.to(torch.int32), vals, own, ghost, okeys,
-                   send_idx, recv_range, group)
+    # renumber the columns: [owned | pad to a multiple of 16 | ghosts]
+    gstart = (n_owned + 15) // 16 * 16
+    newid = torch.full((n_local,), -1, dtype=torch.int32, device=dev)
+    newid[own] = torch.arange(n_owned, device=dev, dtype=torch.int32)
+    newid[ghost] = gstart + torch.arange(ghost.numel(), device=dev, dtype=torch.int32)
+    if cuda:
+        new_ip, ncols, vals = engine.extract_rows(indptr, indices, data, own32, newid)
+    else:
+        ncols = newid[cols].to(torch.int32)
+        it = torch.int64 if nnz >= 2**31 else torch.int32
+        new_ip = new_ip.to(it)
+    A = DistCSR(n_owned, int(ghost.numel()), new_ip, ncols, vals, own, ghost, okeys, send_idx, recv_range, group)
+    # where this rank's values land in each peer's local vector, and the arena size all ranks agree on
+    A.n_local_max = A.n_local
+    if world > 1:
+        info = [None] * world
+        dist.all_gather_object(info, {"n_local": A.n_local, "gstart": gstart, "recv": recv_range}, group=group)
+        A.n_local_max = max(i["n_local"] for i in info)
+        for q in send_idx:
+            start, cnt = info[q]["recv"][rank]
+            if cnt != int(send_idx[q].numel()):
+                raise RuntimeError("halo plan mismatch between sender and receiver")
+            A.send_dst[q] = info[q]["gstart"] + start
+    return A
 
 
 def interior_range(A: DistCSR) -> tuple[int, int]:
@@ -300,7 +347,7 @@ def interior_range(A: DistCSR) -> tuple[int, int]:
     lens = ip[1:] - ip[:-1]
     row_of = torch.repeat_interleave(torch.arange(n, device=ip.device), lens)
     touches = torch.zeros(n, dtype=torch.bool, device=ip.device)
-    touches[row_of[A.indices.to(torch.int64) >= n]] = True
+    touches[row_of[A.indices.to(torch.int64) >= A.ghost_start]] = True
     if not bool(touches.any()):
         return 0, n
     # run lengths of the ghost-free rows: boundaries at the interface rows
@@ -319,7 +366,7 @@ def halo_exchange(A: DistCSR, x: torch.Tensor, comm_device=None) -> None:
     cdev = x.device if comm_device is None else torch.device(comm_device)
     ops, recvs, keep = [], [], []
     for q, (start, cnt) in sorted(A.recv_range.items()):
-        view = x[A.n_owned + start: A.n_owned + start + cnt]
+        view = x[A.ghost_start + start: A.ghost_start + start + cnt]
         if view.device == cdev:
             buf = view
         else:
@@ -517,6 +564,266 @@ def dist_minres(A: DistCSR, b: torch.Tensor, *, rtol=1e-5, shift=0.0, maxiter=10
     k = it_h.value
     hist = hist_d[1: k + 1].cpu().numpy()
     return x[:n], (int(maxiter) if st_h.value == 6 else 0), k, hist
+
+
+# --------------------------------------------------------------------------------------
+# NVLink peer-memory transport (pgb_dist.cu): halo stores and global sums inside the Krylov kernels
+# --------------------------------------------------------------------------------------
+class PeerComm:
+    """Arena + flag header of this rank, exported to / mapped from the other ranks of the node through
+    CUDA IPC handles (exchanged with one ``all_gather``).  ``arena_bytes`` must agree on all ranks."""
+
+    def __init__(self, arena_bytes: int, group=None, device=None) -> None:
+        import ctypes as C
+
+        from ._lib import check, lib
+
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.pgb_comm_create(self.rank, self.world, int(arena_bytes), C.byref(h)))
+            self.handle = h
+            if self.world > 1:
+                nb = int(lib.pgb_comm_handle_bytes())
+                buf = (C.c_ubyte * nb)()
+                check(lib.pgb_comm_get_handle(h, buf))
+                mine = torch.tensor(list(buf), dtype=torch.uint8, device=self.device)
+                allh = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(allh, mine, group=group)
+                flat = torch.cat(allh).cpu().numpy().tobytes()
+                check(lib.pgb_comm_connect(h, flat))
+                dist.barrier(group=group)  # every rank has mapped every arena before anyone stores into one
+        self.arena_bytes = int(lib.pgb_comm_arena_bytes(h))
+
+    def close(self) -> None:
+        from ._lib import lib
+
+        if self.handle is not None:
+            torch.cuda.synchronize(self.device)
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self.group)  # nobody is still storing into a peer's arena
+            lib.pgb_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # best effort: no collective here
+        try:
+            from ._lib import lib
+
+            if getattr(self, "handle", None) is not None:
+                lib.pgb_comm_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class _PeerPlan:
+    """Flattened halo description in the form pgb_dist_cg / pgb_dist_minres take."""
+
+    def __init__(self, A: DistCSR) -> None:
+        import ctypes as C
+
+        dev = A.data.device
+        speers = sorted(A.send_idx)
+        rpeers = sorted(A.recv_range)
+        offs = [0]
+        for q in speers:
+            offs.append(offs[-1] + int(A.send_idx[q].numel()))
+        self.nsend, self.nrecv = len(speers), len(rpeers)
+        self.send_peer = (C.c_int * max(self.nsend, 1))(*speers)
+        self.send_off = (C.c_int64 * (self.nsend + 1))(*offs)
+        self.send_dst = (C.c_int64 * max(self.nsend, 1))(*[int(A.send_dst[q]) for q in speers])
+        self.recv_peer = (C.c_int * max(self.nrecv, 1))(*rpeers)
+        self.send_idx = (torch.cat([A.send_idx[q] for q in speers]).to(torch.int32).contiguous() if speers
+                         else torch.zeros(1, dtype=torch.int32, device=dev))
+        self.halo_bytes = 8 * offs[-1]
+
+
+def peer_setup(A: DistCSR) -> None:
+    """Communicator (sized for the double-buffered CG direction), halo plan and interior range of ``A``."""
+    if A._peer is None:
+        nbytes = 2 * ((A.n_local_max * 8 + 255) // 256 * 256)
+        A._peer = (PeerComm(nbytes, A.group, A.data.device), _PeerPlan(A))
+        A._interior = interior_range(A)
+
+
+def peer_release(A: DistCSR) -> None:
+    if A._peer is not None:
+        A._peer[0].close()
+        A._peer = None
+
+
+def _peer_solve(fn_name: str, A: DistCSR, b: torch.Tensor, dinv, work_vectors: int, extra: tuple, maxiter: int):
+    import ctypes as C
+
+    from . import _lib
+    from ._lib import check, lib
+    from .engine import _ptr, _stream
+    from .solvers import RESID_CAP, _maxiter
+
+    peer_setup(A)
+    comm, plan = A._peer
+    dev = b.device
+    n = A.n_owned
+    maxiter = _maxiter(maxiter, 10 * max(n, 1))
+    lo, hi = A._interior
+    x = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    work = torch.empty(work_vectors * max(n, 1), dtype=torch.float64, device=dev)
+    resid = np.zeros(min(maxiter + 1, RESID_CAP))
+    it, info = C.c_int(0), C.c_int(0)
+    idx64 = 1 if A.indptr.dtype == torch.int64 else 0
+    with torch.cuda.device(dev):
+        if comm.world > 1:
+            dist.barrier(group=A.group)  # ranks enter the solve together (the device waits are bounded)
+        check(getattr(lib, fn_name)(
+            comm.handle, n, A.ghost_start, A.n_ghost, A.indptr.data_ptr(), idx64, A.indices.data_ptr(),
+            A.data.data_ptr(), b.data_ptr(), _ptr(dinv), x.data_ptr(), work.data_ptr(), plan.nsend, plan.send_peer,
+            plan.send_off, plan.send_dst, plan.send_idx.data_ptr(), plan.nrecv, plan.recv_peer, lo, hi, _tpr(A),
+            *extra, int(maxiter), C.byref(it), C.byref(info), resid.ctypes.data, _stream()))
+        _lib.count(2 + 3 * it.value)
+    return x[:n], info.value, it.value, resid
+
+
+def dist_cg_peer(A: DistCSR, b: torch.Tensor, *, rtol=1e-5, atol=0.0, maxiter=1000, dinv=None):
+    """CG on the row-distributed operator with the halo exchange and the global sums done by the Krylov
+    kernels over NVLink peer memory (``pgb_dist_cg``): 3 kernel launches per iteration, no NCCL call, the
+    halo in flight under the interior rows of the SpMV.  Same recurrence and stopping rule as
+    ``scipy.sparse.linalg.cg`` with ``x0 = 0``.  Returns (x_owned, info, iterations, residual norms)."""
+    x, info, k, resid = _peer_solve("pgb_dist_cg", A, b, dinv, 2, (float(rtol), float(atol)), maxiter)
+    return x, info, k, resid[: min(k + 1, resid.size)].copy()
+
+
+def dist_minres_peer(A: DistCSR, b: torch.Tensor, *, rtol=1e-5, shift=0.0, maxiter=1000, dinv=None):
+    """MINRES (``pgb_dist_minres``), the peer-memory counterpart of :func:`dist_minres`.
+    Returns (x_owned, info, iterations, phibar history)."""
+    x, info, k, resid = _peer_solve("pgb_dist_minres", A, b, dinv, 5, (float(shift), float(rtol)), maxiter)
+    return x, info, k, resid[: min(k, resid.size)].copy()
+
+
+def self_check(n: int = 6, nz: int = 10, device=None, group=None) -> dict:
+    """Distributed parity on a small box, run by every rank (tests, ``bench.py --gpus N``):
+
+    * the rows this rank owns, assembled on its slab, equal the same rows of the single-GPU assembly of
+      the whole box (P1 stiffness, RT0 mass, Nedelec0 mass, Darcy saddle);
+    * distributed CG (P1 stiffness + mass) and MINRES (Darcy saddle) over NVLink peer memory and over NCCL
+      reproduce the single-GPU drivers' iteration counts and iterates.
+
+    Returns {"ok": bool, "max_row_err": ..., "cg": {...}, "minres": {...}} (identical on all ranks)."""
+    import scipy.sparse as sps
+
+    from . import darcy, discretization as D_, engine
+    from .solvers import cg_device, minres_device
+
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    full = structured_grid(3, n, nz=nz, perturb=0.1)
+    full.compute_geometry()
+    lay = slab_layout(n, nz, world, rank)
+    sd = local_slab_grid(lay, geometry=False)
+    # same perturbed coordinates as the box: local nodes are a contiguous z-range of the global ones
+    m2 = (n + 1) ** 2
+    sd.nodes = full.nodes[:, lay.z0 * m2: lay.z0 * m2 + sd.num_nodes].copy()
+    sd.compute_connectivity()
+    out = {"world": world, "grid": f"{n}x{n}x{nz}", "max_row_err": 0.0}
+
+    def gids(space, keys):
+        keys = keys.cpu()
+        if space == "lagrange1":
+            return keys.numpy()
+        if space == "darcy":
+            nf = full.num_faces
+            f = keys < (1 << 60)
+            g = np.empty(keys.numel(), dtype=np.int64)
+            g[f.numpy()] = torch.searchsorted(full._structured["face_keys"].cpu(), keys[f]).numpy()
+            g[~f.numpy()] = (keys[~f] - (1 << 60)).numpy() + nf
+            return g
+        table = full._structured["face_keys" if space == "rt0" else "edge_keys"].cpu()
+        return torch.searchsorted(table, keys).numpy()
+
+    def rows_match(space, Dm, Ag):
+        go = gids(space, Dm.owned_keys)
+        keys = global_keys(sd, space)
+        cid = Dm.column_ids().cpu()
+        valid = (cid >= 0).numpy()
+        gcol = np.zeros(Dm.n_local, dtype=np.int64)
+        gcol[valid] = gids(space, keys[cid[cid >= 0]])
+        loc = sps.csr_array((Dm.data.cpu().numpy(), Dm.indices.cpu().numpy(), Dm.indptr.cpu().numpy()),
+                            shape=(Dm.n_owned, Dm.n_local))
+        P = sps.csr_array((valid.astype(float), (np.arange(Dm.n_local), gcol)), shape=(Dm.n_local, Ag.shape[1]))
+        return go, float(abs(loc @ P - Ag[go]).max() / abs(Ag).max())
+
+    systems = {}
+    for space, form, cls in (("lagrange1", "stiff", D_.Lagrange1), ("rt0", "mass", D_.RT0),
+                             ("nedelec0", "mass", D_.Nedelec0), ("darcy", "saddle", None)):
+        if space == "darcy":
+            Dm = assemble_darcy_slab(sd, group=group)
+            Ag = darcy.darcy_saddle_device(full).to_scipy("csr")
+        else:
+            Dm = assemble_slab(space, form, sd, group=group)
+            Ad = cls().assemble_stiff_matrix_device(full) if form == "stiff" else cls().assemble_mass_matrix_device(full)
+            Ag = Ad.to_scipy("csr")
+        go, err = rows_match(space, Dm, Ag)
+        out["max_row_err"] = max(out["max_row_err"], err)
+        systems[space] = (Dm, Ag, go)
+
+    def agree(xd, go, xs):
+        return float(np.abs(xd.cpu().numpy() - xs[go]).max() / max(np.abs(xs).max(), 1e-300))
+
+    def hist_err(h, href, m=30):
+        m = min(m, len(h), len(href))
+        return float(np.abs(np.asarray(h[:m]) - np.asarray(href[:m])).max() / max(abs(href[0]), 1e-300)) if m else 0.0
+
+    def run(fn, Dm, bo, go, xs, href, **kw):
+        r = fn(Dm, bo, **kw)
+        return {"iters": int(r[2]), "info": int(r[1]), "x_err": agree(r[0], go, xs), "hist_err": hist_err(r[3], href)}
+
+    # CG on S + M (SPD), right-hand side from a global seeded vector
+    Dm, S, go = systems["lagrange1"]
+    Mloc = assemble_slab("lagrange1", "mass", sd, group=group)
+    Dm.data += Mloc.data  # same pattern, same extraction order
+    Ag = S + D_.Lagrange1().assemble_mass_matrix_device(full).to_scipy("csr")
+    bg = np.random.default_rng(7).normal(size=Ag.shape[0])
+    xs, si = cg_device(engine.DeviceCSR.from_scipy(Ag, dev), torch.from_numpy(bg).to(dev), rtol=1e-10, maxiter=2000)
+    xs = xs.cpu().numpy()
+    bo = torch.from_numpy(bg[go]).to(dev)
+    out["cg"] = {"single_gpu_iters": int(si.iterations),
+                 "peer": run(dist_cg_peer, Dm, bo, go, xs, si.residuals, rtol=1e-10, maxiter=2000),
+                 "nccl": run(dist_cg, Dm, bo, go, xs, si.residuals, rtol=1e-10, maxiter=2000)}
+    peer_release(Dm)
+    # MINRES on the symmetrised saddle system: block-Jacobi preconditioned over peer memory (iterates
+    # compared), plain over NCCL (badly conditioned: the first 30 residual estimates are compared)
+    Dm, Ag, go = systems["darcy"]
+    Afull = engine.DeviceCSR.from_scipy(Ag, dev)
+    dinv = darcy.darcy_block_jacobi(Afull, full.num_faces)
+    bg = np.random.default_rng(8).normal(size=Ag.shape[0])
+    bd = torch.from_numpy(bg).to(dev)
+    bo = torch.from_numpy(bg[go]).to(dev)
+    xs, si = minres_device(Afull, bd, rtol=1e-10, maxiter=20000, dinv=dinv)
+    dio = dinv[torch.from_numpy(go).to(dev)].contiguous()
+    out["minres"] = {"single_gpu_iters": int(si.iterations),
+                     "peer": run(dist_minres_peer, Dm, bo, go, xs.cpu().numpy(), si.residuals, rtol=1e-10,
+                                 maxiter=20000, dinv=dio)}
+    xs2, si2 = minres_device(Afull, bd, rtol=1e-8, maxiter=20000)
+    out["minres"]["single_gpu_iters_plain"] = int(si2.iterations)
+    out["minres"]["nccl"] = run(dist_minres, Dm, bo, go, xs2.cpu().numpy(), si2.residuals, rtol=1e-8, maxiter=20000)
+    peer_release(Dm)
+    ok = out["max_row_err"] <= 1e-13
+    for k, t, ref_it, xtol in (("cg", "peer", "single_gpu_iters", 1e-7), ("cg", "nccl", "single_gpu_iters", 1e-7),
+                               ("minres", "peer", "single_gpu_iters", 1e-6),
+                               ("minres", "nccl", "single_gpu_iters_plain", None)):
+        r, its = out[k][t], out[k][ref_it]
+        ok = ok and r["info"] == 0 and r["hist_err"] <= 1e-8 and abs(r["iters"] - its) <= max(3, its // 20)
+        if xtol is not None:
+            ok = ok and r["x_err"] <= xtol
+    if world > 1:
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        ok = bool(flag.item())
+    out["ok"] = ok
+    return out
 
 
 def assemble_darcy_slab(sd: SimplexGrid, data=None, keyword="unitary_data", group=None) -> DistCSR:

@@ -65,9 +65,14 @@ def _worker(rank, world, port, q):
             assert np.array_equal(cat, np.arange(Aglob.shape[0])), space
             # rows equal the global rows
             loc = sps.csr_array((D.data.numpy(), D.indices.numpy(), D.indptr.numpy()), shape=(D.n_owned, D.n_local))
-            colkeys = torch.cat([keys[D.owned_local], keys[D.ghost_local]])
-            gcol = _global_ids(full, space, colkeys)
-            P = sps.csr_array((np.ones(D.n_local), (np.arange(D.n_local), gcol)), shape=(D.n_local, Aglob.shape[1]))
+            cid = D.column_ids()
+            valid = (cid >= 0).numpy()  # the owned block is padded to a multiple of 16 entries
+            assert D.ghost_start % 16 == 0 and D.n_owned <= D.ghost_start < D.n_owned + 16
+            assert valid.sum() == D.n_owned + D.n_ghost and not valid[D.n_owned: D.ghost_start].any()
+            gcol = np.zeros(D.n_local, dtype=np.int64)
+            gcol[valid] = _global_ids(full, space, keys[cid[cid >= 0]])
+            P = sps.csr_array((valid.astype(float), (np.arange(D.n_local), gcol)), shape=(D.n_local, Aglob.shape[1]))
+            assert valid[np.unique(loc.indices)].all()  # no entry points into the padding
             rows_glob = Aglob[gid_owned]
             diff = abs(loc @ P - rows_glob).max()
             assert diff <= 1e-13 * abs(Aglob).max(), (space, diff)
@@ -81,12 +86,20 @@ def _worker(rank, world, port, q):
             x = torch.zeros(D.n_local, dtype=torch.float64)
             x[: D.n_owned] = torch.from_numpy(xg[gid_owned])
             pd.halo_exchange(D, x)
-            assert np.array_equal(x.numpy(), xg[gcol]), space
+            assert np.array_equal(x.numpy()[valid], xg[gcol[valid]]), space
+            # the plan for direct stores into the peers' vectors (NVLink path): where my values land
+            lands = [None] * world
+            dist.all_gather_object(lands, {q: (D.send_dst[q], keys[D.owned_local][D.send_idx[q]]) for q in D.send_idx})
+            for src, plan in enumerate(lands):
+                if rank in plan:
+                    dst, ks = plan[rank]
+                    assert torch.equal(keys[cid[dst: dst + ks.numel()]], ks), (space, src)
+            assert D.n_local_max >= D.n_local
             y = loc @ x.numpy()
             assert np.abs(y - (Aglob @ xg)[gid_owned]).max() <= 1e-12 * np.abs(Aglob @ xg).max()
             # interior range: no ghost column inside, every interface row outside, and it is the bulk
             a, b = pd.interior_range(D)
-            ghost_rows = np.unique(loc.tocoo().row[loc.tocoo().col >= D.n_owned])
+            ghost_rows = np.unique(loc.tocoo().row[loc.tocoo().col >= D.ghost_start])
             assert 0 <= a <= b <= D.n_owned
             assert not np.any((ghost_rows >= a) & (ghost_rows < b)), space
             if ghost_rows.size:

@@ -1,23 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the FEM assembly-and-solve hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--ncube NCUBE]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3] [--ncube NCUBE]
 
-Workload at N=1: BASELINE.json configs[1] - pg.Lagrange1 stiffness on the 128^3 structured
-tetrahedral unit cube (12 582 912 tets), followed by CG iterations on the assembled operator.
+Workloads
+  --config 2 (default at N = 1): BASELINE configs[1] - pg.Lagrange1 stiffness on the 128^3 structured
+      tetrahedral unit cube (12 582 912 tets) per GPU, CG iterations on the assembled operator
+      (weak scaling when N > 1: 128^3 per GPU).
+  --config 3 (default at N > 1): BASELINE configs[2], the north-star scaling case - mixed Darcy RT0/P0
+      saddle-point system on the 256^3 tetrahedral cube (100 663 296 tets, 302 M unknowns), cell
+      partitioned in z-slabs over the N GPUs (STRONG scaling: the same 100 M tets at every N), one-pass
+      assembly per rank + distributed MINRES over NVLink peer memory.  `--config 3 --gpus 1` runs the same
+      workload on one GPU (93.5 GiB).
 
-A *step* is one complete assembly of that matrix into CSR with NOTHING cached: grid packing
-(node-opposite-face tables, coordinates), the symbolic phase (incidence transpose + per-row sort of the
-distinct columns = the sort by (row, col); pattern), the per-cell local matrices and the ordered reduce.  ``value`` = cells/s with the grid's raw
-arrays already resident in HBM; ``e2e`` = the same through the public
-``pg.Lagrange1().assemble_stiff_matrix(sd)`` call with host (pinned) grid arrays in and a host
-scipy matrix out, host<->device copies inside the timed region.  ``warm`` (symbolic plan reused, the
-analogue of the reference's cached projection, hdiv.py:255) and ``solve`` (CG GB/s) are reported
-beside it.  ``--impl reference`` / ``cpu_baseline`` time the oracle's port of the reference's
-scipy algorithm on the host cores (a bounded sample of the same workload).
+A *step* is one complete (cold) assembly into CSR with NOTHING cached: grid packing, the symbolic phase
+(incidence transpose + per-row sort = the sort by (row, col); pattern), the per-cell local matrices and
+the ordered reduce.  `value` = cells/s with the grid's raw arrays already resident in HBM; `e2e` = the
+same through the public call (`pg.Lagrange1().assemble_stiff_matrix(sd)` / `pg.darcy_saddle_matrix(sd)`)
+with host (pinned) grid arrays in and a host scipy matrix out, host<->device copies inside the timed
+region.  `--impl reference` / `cpu_baseline` time the UNMODIFIED reference package staged in
+baseline/_ref (kind "reference"; the oracle's port of its algorithm, kind "port", only when the staged
+copy is absent) on the host cores, on a bounded sample of the workload that the line names.
 
-Timing: CUDA events on the launching stream, W>=3 warm-up steps, inputs far larger than L2
-(working set of a step is > 5 GB), max over ranks, clocks sampled during the timed region.
+Timing: CUDA events on the launching stream, W >= 3 warm-up steps, inputs far larger than L2 (the working
+set of a step is > 5 GB), max over ranks, clocks sampled during the timed region.
 """
 
 from __future__ import annotations
@@ -27,16 +33,15 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# (profiles/r1_ncu_full.txt; config #2, L1 stiffness on 128^3; k_rowhash, k_local, k_numeric_t)
 NOMINAL_HBM_GBS = 8000.0  # north_star's nominal HBM3e figure; the measured copy peak is what `frac` uses
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/: config #2, L1 stiffness on 128^3)
 TRAFFIC = {"k_rowhash": 1.048e9, "local_matrices": 2.027e9, "csr_numeric": 2.069e9}
 
 METRIC = "cells assembled/s into CSR"
@@ -55,7 +60,7 @@ def peaks():
 # clocks
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    """`nvidia-smi -lms 100` in the background for the duration of the timed region."""
+    """`nvidia-smi -lms 20` in the background for the duration of the timed region."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
@@ -67,7 +72,8 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)  # first samples before the timed region starts
         except Exception:
             self.proc = None
         return self
@@ -75,7 +81,7 @@ class ClockSampler:
     def __exit__(self, *a):
         if self.proc is None:
             return
-        time.sleep(0.25)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -95,60 +101,138 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
+def count_launches(fn) -> int | None:
+    """Kernel launches of one call of ``fn``, counted by CUPTI (torch.profiler sees every kernel of the
+    process, including libpgb.so's).  None when the profiler is unavailable."""
+    try:
+        import torch
+        from torch.profiler import ProfilerActivity, profile
+
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        n = 0
+        for e in prof.events():
+            if e.device_type is not None and "cuda" in str(e.device_type).lower() and "memcpy" not in e.name.lower() \
+                    and "memset" not in e.name.lower():
+                n += 1
+        return n or None
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle's port of the reference algorithm on host cores
+# reference arm / CPU baseline
 # ----------------------------------------------------------------------------------------------
-def cpu_sample_grid(n_sample):
+def load_reference():
+    """(pg_ref, pp_standin, kind): the unmodified reference from baseline/_ref (staged by
+    scripts/stage_reference.py; travels to the GPU box) with the porepy stand-in, else (None, None, 'port')."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "pygeon")):
+        return None, None, "port"
+    for p in (ref_dir, os.path.join(ROOT, "oracle", "_standins")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    try:
+        import porepy as pp
+        import pygeon as rpg
+
+        return rpg, pp, "reference"
+    except Exception as e:  # pragma: no cover
+        print(f"bench: staged reference failed to import ({e!r}); using the oracle port", file=sys.stderr)
+        return None, None, "port"
+
+
+def cpu_workload(config: int, n_sample: int):
+    """(step function -> matrix, cells, description, kind) of the CPU arm on an n_sample^3 Kuhn-tet cube."""
+    import scipy.sparse as sps
+
     import pygeon_b200 as pg
 
+    rpg, pp, kind = load_reference()
     sd = pg.structured_grid(3, n_sample)
-    sd.compute_geometry()
-    return sd
+    if kind == "reference":
+        g = rpg.Grid(3, sd.nodes.copy(), sd.face_nodes.copy(), sd.cell_faces.copy(), "bench")
+        g.compute_geometry()
+        if config == 2:
+            step = lambda: rpg.Lagrange1().assemble_stiff_matrix(g)  # noqa: E731  discretization.py:154-183
+        else:
+            def step():  # darcy.ipynb cell 10 / test_laplacian_mixed.py:50
+                M = rpg.RT0().assemble_mass_matrix(g)
+                B = rpg.PwConstants().assemble_mass_matrix(g) @ rpg.RT0().assemble_diff_matrix(g)
+                return sps.block_array([[M, -B.T], [B, None]]).tocsc()
+        what = "unmodified reference (baseline/_ref, porepy stand-in)"
+    else:
+        from oracle import fem_oracle as fo
+
+        sd.compute_geometry()
+        if config == 2:
+            step = lambda: fo.port_stiff("lagrange1", sd)  # noqa: E731
+        else:
+            def step():
+                M = fo.port_mass("rt0", sd)
+                B = sps.diags_array(1.0 / sd.cell_volumes) @ sd.cell_faces.T
+                return sps.block_array([[M, -B.T], [B, None]]).tocsc()
+        what = "oracle port of the reference algorithm (baseline/_ref absent)"
+    name = "pg.Lagrange1().assemble_stiff_matrix" if config == 2 else "RT0 mass + P0 mass @ div + block_array (Darcy saddle)"
+    return step, sd.num_cells, f"{name} on {n_sample}^3 structured tet cube ({sd.num_cells} tets); {what}", kind
 
 
-def cpu_step(sd):
-    """One reference-algorithm assembly of the workload's matrix (Lagrange1 stiffness:
-    Nedelec0 mass through Pi.T M Pi, then B.T A B; discretization.py:112-136,154-183)."""
-    from oracle import fem_oracle as fo
-
-    t = time.perf_counter()
-    A = fo.port_stiff("lagrange1", sd)
-    return time.perf_counter() - t, A
+def time_cpu(step, max_steps: int, budget_s: float):
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max(max_steps, 1):
+        t = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t)
+        if time.perf_counter() - t_start + times[-1] > budget_s:
+            break
+    return times
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_s = args.cpu_n
-    sd = cpu_sample_grid(n_s)
-    for _ in range(min(args.warmup, 1)):
-        cpu_step(sd)
-    times = [cpu_step(sd)[0] for _ in range(max(min(args.steps, 5), 1))]  # bounded: <= 5 samples of ~3-6 s
+    cfg = args.config
+    step, cells, what, kind = cpu_workload(cfg, args.cpu_n)
+    if args.warmup > 0:
+        step()
+    times = time_cpu(step, args.steps, budget_s=150.0)
     dt = sum(times) / len(times)
-    v = sd.num_cells / dt
-    sample = f"Lagrange1 stiffness on {n_s}^3 structured tet cube ({sd.num_cells} tets) per step; scipy SpGEMM is single-threaded"
+    v = cells / dt
+    full = workload_config(cfg, args.n if cfg == 2 else args.n3, args.gpus)
+    conf = {"workload": what + " per step; scipy sparse kernels are single-threaded",
+            "n_per_side": args.cpu_n, "cells": cells, "extrapolated_to": full["workload"],
+            "note": "CPU throughput is flat or falling with size (SURVEY section 6), so cells/s measured on the "
+                    "sample is an upper bound for the full workload; 5 kB/tet of host RAM rules out the full size"}
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.n, args.gpus),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "host_cpus": os.cpu_count()},
+        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak" if cfg == 2 else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": kind, "sample": what, "host_cpus": os.cpu_count()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(n, gpus):
-    return {"workload": f"pg.Lagrange1 stiffness (K=I, w=1) on {n}^3 structured Kuhn-tet unit cube "
-                        f"({6 * n ** 3} tets, {(n + 1) ** 3} nodes) per GPU; BASELINE configs[1]",
-            "n_per_side": n, "cells_per_gpu": 6 * n ** 3, "parallelism": f"cell-partitioned x{gpus}",
-            "l2": "inputs larger than L2 (step working set > 5 GB)"}
+def workload_config(cfg, n, gpus):
+    if cfg == 2:
+        return {"workload": f"pg.Lagrange1 stiffness (K=I, w=1) on {n}^3 structured Kuhn-tet unit cube "
+                            f"({6 * n ** 3} tets, {(n + 1) ** 3} nodes) per GPU; BASELINE configs[1]",
+                "n_per_side": n, "cells_per_gpu": 6 * n ** 3, "parallelism": f"cell-partitioned x{gpus}",
+                "l2": "inputs larger than L2 (step working set > 5 GB)"}
+    return {"workload": f"mixed Darcy RT0/P0 saddle system [[M,-B^T],[-B,0]] on {n}^3 structured Kuhn-tet cube "
+                        f"({6 * n ** 3} tets, {12 * n ** 3 + 6 * n ** 2 + 6 * n ** 3} unknowns), one-pass assembly + MINRES; "
+                        f"BASELINE configs[2], the same cells at every GPU count",
+            "n_per_side": n, "cells_total": 6 * n ** 3, "parallelism": f"cell-partitioned z-slabs x{gpus}",
+            "l2": "inputs larger than L2 (step working set > 10 GB per GPU)"}
 
 
 # ----------------------------------------------------------------------------------------------
-# our arm
+# helpers of our arm
 # ----------------------------------------------------------------------------------------------
 def pinned_view(arr):
     import numpy as np
@@ -158,34 +242,7 @@ def pinned_view(arr):
     return t.numpy(), t
 
 
-def run_ours(args):
-    import numpy as np
-    import scipy.sparse as sps
-    import torch
-    import torch.distributed as dist
-
-    import pygeon_b200 as pg
-    from pygeon_b200 import _lib, engine
-    from pygeon_b200.solvers import cg_device
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    from pygeon_b200 import dist as pgd
-
-    numa_cpus = pgd.bind_to_gpu_numa(local) if os.environ.get("PGB_BIND_NUMA", "1") != "0" else None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    hbm_peak, peak_src = peaks()
-    n = args.n
-
-    # ---- synthetic grid: connectivity generated on the device, host copy in pinned memory -----
-    # N>1: rank r owns n cube layers of the n x n x (n*N) box and also evaluates the halo layer
-    # above them (redundant compute, no communication during assembly)
-    lay = pgd.slab_layout(n, n * world, world, rank)
-    sd = pgd.local_slab_grid(lay, device=dev)
+def pin_grid(sd):
     keep = []
     for mat in (sd.cell_faces, sd.face_nodes):
         mat.indices, t1 = pinned_view(mat.indices)
@@ -193,22 +250,117 @@ def run_ours(args):
         keep += [t1, t2]
     sd.nodes, t3 = pinned_view(sd.nodes)
     keep.append(t3)
+    return keep
+
+
+class Ctx:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        from pygeon_b200 import dist as pgd
+
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.numa_cpus = pgd.bind_to_gpu_numa(self.local) if os.environ.get("PGB_BIND_NUMA", "1") != "0" else None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.hbm_peak, self.peak_src = peaks()
+        self.torch, self.dist = torch, dist
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def fractions(gbs, hbm_peak, world=1):
+    return {"gbs": gbs, "frac": gbs / (hbm_peak * world), "frac_nominal_8tbs": gbs / (NOMINAL_HBM_GBS * world)}
+
+
+def cpu_baseline_leg(args, cfg):
+    step, cells, what, kind = cpu_workload(cfg, args.cpu_n)
+    times = time_cpu(step, 1, budget_s=60.0)
+    dt = times[0]
+    return {"value": cells / dt, "unit": UNIT, "cores": 1, "kind": kind, "host_cpus": os.cpu_count(),
+            "sample": f"one call of {what}: {dt:.1f} s"}
+
+
+def verify_config2(A, sd):
+    """Full CSR of the benchmarked matrix against the oracle's closed form (bit-exact pattern, 1e-12 values)."""
+    import numpy as np
+
+    from oracle import fem_oracle as fo
+
+    t = time.perf_counter()
+    ref = fo.closed_form("lagrange1", "stiff", sd, fast=True).tocsc()
+    ref.sort_indices()
+    ok = (A.shape == ref.shape and A.nnz == ref.nnz and np.array_equal(A.indptr, ref.indptr)
+          and np.array_equal(A.indices, ref.indices))
+    err = float(np.abs(A.data - ref.data).max() / np.abs(ref.data).max()) if ok else None
+    ok = ok and err <= 1e-12
+    return {"parity_at_config": "ok" if ok else "FAILED", "max_rel_err": err, "nnz": int(ref.nnz),
+            "checked": "indptr, indices bit-exact; values 1e-12 * max|A| against oracle/fem_oracle.closed_form",
+            "oracle_s": time.perf_counter() - t}
+
+
+# ----------------------------------------------------------------------------------------------
+# config #2: P1 stiffness, 128^3 per GPU
+# ----------------------------------------------------------------------------------------------
+def run_config2(args, cx: Ctx):
+    import ctypes as C
+
+    import numpy as np
+
+    import pygeon_b200 as pg
+    from pygeon_b200 import _lib, engine
+    from pygeon_b200 import dist as pgd
+    from pygeon_b200.solvers import cg_device
+
+    torch, dist, dev, world, rank = cx.torch, cx.dist, cx.dev, cx.world, cx.rank
+    hbm_peak = cx.hbm_peak
+    n = args.n
+    dist_parity = pgd.self_check(6, 4 * world + 2) if world > 1 else None
+
+    # N>1: rank r owns n cube layers of the n x n x (n*N) box and also evaluates the halo layer above them
+    lay = pgd.slab_layout(n, n * world, world, rank)
+    sd = pgd.local_slab_grid(lay, device=dev)
+    keep = pin_grid(sd)
     nc, nn = sd.num_cells, sd.num_nodes
     nc_owned = 6 * n * n * lay.nz_owned
     disc = pg.Lagrange1()
-
     raw = engine.RawGrid.upload(sd, dev)
     raw.check = False  # no device->host validity read inside the device-resident step
     torch.cuda.synchronize()
-
-    def ev():
-        return torch.cuda.Event(enable_timing=True)
-
+    ev = cx.ev
     phase_names = ["pack", "symbolic", "local", "numeric"]
 
     def device_step(record=None):
-        """One cold assembly through the product path (engine.assemble_on_pack); the per-phase split
-        (`phases_ms`) is measured in separate steps with CUDA events between the phases."""
         if record is None:
             pack = engine.GridPack.from_raw(raw)
             return engine.assemble_on_pack(pack, "lagrange1", "l1_stiff")
@@ -225,35 +377,27 @@ def run_ours(args):
         record.append(e)
         return plan, data
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident cold steps ---------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         plan, data = device_step()
-    barrier()
-    launches0 = _lib.launches()
+    cx.barrier()
+    launches_per_step = count_launches(device_step)
     rec = []
     start, stop = ev(), ev()
-    with ClockSampler(local) as clocks:
-        barrier()
+    with ClockSampler(cx.local) as clocks:
+        cx.barrier()
         start.record()
         for _ in range(args.steps):
             plan, data = device_step()
         stop.record()
-        barrier()
+        cx.barrier()
         ms_total = start.elapsed_time(stop)
-        launches_timed = _lib.launches() - launches0
         for _ in range(min(args.steps, 5)):  # serialised steps, only for the per-phase attribution
             device_step(rec)
         torch.cuda.synchronize()
         # ---- warm steps (plan reused) ------------------------------------------------------
         pack = engine.GridPack.from_raw(raw)
         plan = engine.symbolic(pack, "lagrange1")
-        vals = torch.empty((nc, 16), dtype=torch.float64, device=dev)  # L = 4: pitch 4
+        vals = torch.empty((nc, 16), dtype=torch.float64, device=dev)
         out = torch.empty((plan.nnz,), dtype=torch.float64, device=dev)
         for _ in range(3):
             engine.numeric(plan, engine.local_matrices(pack, "l1_stiff", out=vals, plan=plan), out=out)
@@ -271,9 +415,6 @@ def run_ours(args):
             wn += w1.elapsed_time(w2)
         wl /= args.steps
         wn /= args.steps
-        # ---- per-phase split of the symbolic call (library-side CUDA events), outside the timed steps
-        import ctypes as C
-
         _lib.lib.pgb_set_profile(1)
         ph = np.zeros(4)
         for _ in range(3):
@@ -282,12 +423,7 @@ def run_ours(args):
             _lib.lib.pgb_get_phase_ms(buf, 4)
             ph += np.array(list(buf)) / 3
         _lib.lib.pgb_set_profile(0)
-    launches = launches_timed
-    ms_step = ms_total / args.steps
-    if world > 1:
-        t = torch.tensor([ms_step], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step = float(t.item())
+    ms_step = cx.max_over_ranks(ms_total / args.steps)
     phases = {k: 0.0 for k in phase_names}
     for e in rec:
         for i, k in enumerate(phase_names):
@@ -295,44 +431,32 @@ def run_ours(args):
     nnz, n_coo = plan.nnz, plan.n_coo
 
     # ---- roofline bookkeeping (algorithmic bytes) --------------------------
-    bits = max(1, int(nn - 1).bit_length())
     n_inc = nc * 4
-    b_local = nc * (16 + 16 + 128) + 32 * nn  # node ids + destination rows + values; coords once per node
-    # streaming numeric over the row-sorted local rows: value 8 B + slot 1 B per COO entry, row
-    # offsets + indptr 8 B per row, data 8 B per entry
+    b_local = nc * (16 + 16 + 128) + 32 * nn
     b_numeric = n_coo * 9 + 8 * nn + nnz * 8
-    # counting transpose: dofs in twice, ranks out + in, placed incidences out + in, sorted incidences + inc_pos out
     b_transpose = n_inc * (4 + 4 + 1 + 1 + 4 + 4 + 4 + 4) + 12 * nn
-    # k_rowhash: row blocks of incidences + row offsets + the cell->dof table in; inc_pos, slot bytes,
-    # unique columns + row counts out
     b_rowsort = n_inc * 4 + 8 * nn + nc * 16 + n_inc * 4 + n_coo * 1 + nnz * 4 + 4 * nn
-    b_step_algo = nc * 16 + 32 * nn + n_coo * 0 + nnz * 12 + 4 * (nn + 1)  # read grid once, write CSR once
+    b_step_algo = nc * 16 + 32 * nn + nnz * 12 + 4 * (nn + 1)
     kern = {
-        "local_matrices": {"ms": wl, "gbs": b_local / wl / 1e6, "bytes": b_local},
-        "csr_numeric": {"ms": wn, "gbs": b_numeric / wn / 1e6, "bytes": b_numeric},
-        "symbolic_total": {"ms": phases["symbolic"],
-                           "bytes": b_transpose + b_rowsort + 16 * nnz,
+        "local_matrices": {"ms": wl, "bytes": b_local, **fractions(b_local / wl / 1e6, hbm_peak)},
+        "csr_numeric": {"ms": wn, "bytes": b_numeric, **fractions(b_numeric / wn / 1e6, hbm_peak)},
+        "symbolic_total": {"ms": phases["symbolic"], "bytes": b_transpose + b_rowsort + 16 * nnz,
                            "gbs": (b_transpose + b_rowsort + 16 * nnz) / phases["symbolic"] / 1e6},
         "pack": {"ms": phases["pack"]},
-        "symbolic_count_scan": {"ms": float(ph[0]), "note": "k_inc_count (integer atomics) + scan + max + host read"},
-        "symbolic_place_rowcanon": {"ms": float(ph[1]), "note": "k_inc_place + k_row_canon (per-row sort of the incidences)"},
+        "symbolic_count_scan": {"ms": float(ph[0])},
+        "symbolic_place_rowcanon": {"ms": float(ph[1])},
         "symbolic_rowsort": {"ms": float(ph[2]), "bytes": b_rowsort, "gbs": b_rowsort / max(ph[2], 1e-9) / 1e6,
-                             "note": "k_rowhash: canonical sort of the row's incidences, shared-memory hash dedupe, "
-                                     "register bitonic sort of the distinct columns; issue / LSU bound (ncu: SM 76 %, "
-                                     "DRAM 14 %), not HBM-bound"},
+                             "kernel": _lib.lib.pgb_csr_last_row_kernel().decode()},
         "symbolic_scan": {"ms": float(ph[3])},
     }
-    for k in ("local_matrices", "csr_numeric"):
-        kern[k]["frac"] = kern[k]["gbs"] / hbm_peak
-        kern[k]["frac_nominal_8tbs"] = kern[k]["gbs"] / NOMINAL_HBM_GBS
 
     # ---- CG on the assembled operator (S + M, SPD, same pattern) --------------------------------
     S = engine.DeviceCSR((nn, nn), plan.indptr, plan.indices, out.clone())
     Mv = engine.numeric(plan, engine.local_matrices(pack, "l1_mass", out=vals, plan=plan))
     S.data += Mv
-    b = torch.ones(nn, dtype=torch.float64, device=dev)
     cg_iters = args.cg_iters
     if world == 1:
+        b = torch.ones(nn, dtype=torch.float64, device=dev)
         cg_device(S, b, rtol=0.0, atol=0.0, maxiter=5)
         torch.cuda.synchronize()
         c0, c1 = ev(), ev()
@@ -343,108 +467,257 @@ def run_ours(args):
         cg_ms = c0.elapsed_time(c1) / max(info.iterations, 1)
         b_cg = 12 * nnz + 4 * (nn + 1) + 88 * nn
         solve = {"solver": "cg (device-resident recurrence, pgb_cg)", "iters": info.iterations, "ms_per_iter": cg_ms,
-                 "gbs": b_cg / cg_ms / 1e6, "frac": b_cg / cg_ms / 1e6 / hbm_peak, "bytes_per_iter": b_cg,
-                 "n": nn, "nnz": nnz, "note": "vectors (17 MB each) are L2 resident at this size"}
+                 "bytes_per_iter": b_cg, **fractions(b_cg / cg_ms / 1e6, hbm_peak), "n": nn, "nnz": nnz,
+                 "note": "vectors (17 MB each) are L2 resident at this size"}
     else:
         D = pgd.build_dist_csr(S.indptr, S.indices, S.data, pgd.owned_mask(sd, "lagrange1"),
                                pgd.global_keys(sd, "lagrange1"))
         bo = torch.ones(D.n_owned, dtype=torch.float64, device=dev)
-        pgd.dist_cg(D, bo, rtol=0.0, atol=0.0, maxiter=3)
-        barrier()
-        c0, c1 = ev(), ev()
-        c0.record()
-        xo, _, its, _ = pgd.dist_cg(D, bo, rtol=0.0, atol=0.0, maxiter=cg_iters)
-        c1.record()
-        barrier()
-        t = torch.tensor([c0.elapsed_time(c1) / max(its, 1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        cg_ms = float(t.item())
-        bl = torch.tensor([12.0 * D.nnz + 4 * (D.n_owned + 1) + 88 * D.n_owned], dtype=torch.float64, device=dev)
-        dist.all_reduce(bl)
-        b_cg = float(bl.item())
+        solve = {}
+        for name, fn in (("peer", pgd.dist_cg_peer), ("nccl", pgd.dist_cg)):
+            fn(D, bo, rtol=0.0, atol=0.0, maxiter=3)
+            cx.barrier()
+            c0, c1 = ev(), ev()
+            c0.record()
+            _, _, its, _ = fn(D, bo, rtol=0.0, atol=0.0, maxiter=cg_iters)
+            c1.record()
+            cx.barrier()
+            ms = cx.max_over_ranks(c0.elapsed_time(c1) / max(its, 1))
+            b_cg = cx.sum_over_ranks(12.0 * D.nnz + 4 * (D.n_owned + 1) + 88 * D.n_owned)
+            solve[name] = {"iters": its, "ms_per_iter": ms, "bytes_per_iter": b_cg,
+                           **fractions(b_cg / ms / 1e6, hbm_peak, world)}
         halo = sum(int(v.numel()) for v in D.send_idx.values()) * 8
-        solve = {"solver": "cg (row-distributed; fused device-scalar kernels, NCCL halo exchange + 2 small all-reduces per iteration)",
-                 "iters": its, "ms_per_iter": cg_ms, "gbs": b_cg / cg_ms / 1e6,
-                 "frac": b_cg / cg_ms / 1e6 / (hbm_peak * world), "bytes_per_iter": b_cg,
-                 "halo_bytes_sent_per_iter_rank0": halo, "n_owned_rank0": D.n_owned}
+        solve.update({"solver": "cg, row-distributed: 'peer' = halo stores + global sums inside the Krylov kernels over "
+                                "NVLink peer memory (pgb_dist_cg, 3 launches / iteration); 'nccl' = grouped send/recv + "
+                                "2 all-reduces per iteration",
+                      "halo_bytes_sent_per_iter_rank0": halo, "n_owned_rank0": D.n_owned,
+                      **{k: solve["peer"][k] for k in ("ms_per_iter", "gbs", "frac", "frac_nominal_8tbs")}})
+        pgd.peer_release(D)
 
     # ---- end to end through the public API (host arrays in, scipy matrix out) -------------------
     e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(3):  # warm-up: also fills the pinned result pool (page-locking costs ~0.5 ms/MB once)
+    for _ in range(3):
         engine.clear_cache(sd)
         A = disc.assemble_stiff_matrix(sd)
     engine.clear_cache(sd)
-    barrier()
+    cx.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         engine.clear_cache(sd)
         A = disc.assemble_stiff_matrix(sd)
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = cx.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     h2d = raw.h2d_bytes
     d2h = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes
     assert A.shape == (nn, nn) and A.nnz == nnz
+    verify = None
+    if rank == 0 and world == 1 and args.verify:
+        verify = verify_config2(A, sd)
     cells_note = (f"{nc} cells evaluated per rank of which {nc_owned} owned "
                   f"(halo layer is redundant work and is not counted)")
-
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
-    # ---- CPU baseline (oracle port of the reference algorithm), rank 0 at N=1 only ---------------
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        sds = cpu_sample_grid(args.cpu_n)
-        dt, Aref = cpu_step(sds)
-        cpu = {"value": sds.num_cells / dt, "unit": UNIT, "cores": 1, "kind": "port",
-               "host_cpus": os.cpu_count(),
-               "sample": f"one Lagrange1 stiffness assembly on {args.cpu_n}^3 ({sds.num_cells} tets), "
-                         f"{dt:.1f} s; scipy sparse kernels are single-threaded"}
-
+    cpu = cpu_baseline_leg(args, 2) if (world == 1 and not args.no_cpu) else None
     dom = max(("symbolic", "local", "numeric", "pack"), key=lambda k: phases[k])
-    if dom == "symbolic":
-        # dominant kernel of the cold step: k_rowhash (one launch per step)
-        roof = {"bound": "hbm", "kernel": "k_rowhash (per-row dedupe + sort of the symbolic phase)",
-                "achieved": kern["symbolic_rowsort"]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "traffic": TRAFFIC.get("k_rowhash"),
-                "note": "largest single kernel of the cold step; it is issue / shared-memory bound (ncu), so its "
-                        "HBM fraction is low by construction; the HBM-bound kernels are in `kernels` "
-                        "(local_matrices, csr_numeric) and `solve`"}
-    else:
-        key = "local_matrices" if dom == "local" else "csr_numeric"
-        roof = {"bound": "hbm", "kernel": key, "achieved": kern[key]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "traffic": TRAFFIC.get(key)}
-    roof["frac"] = roof["achieved"] / hbm_peak
-    roof["peak_source"] = peak_src
-    roof["frac_nominal_8tbs"] = roof["achieved"] / NOMINAL_HBM_GBS  # both denominators
-    solve["frac_nominal_8tbs"] = solve["gbs"] / (NOMINAL_HBM_GBS * world)
-
+    # the dominant single kernel of the cold step
+    cand = {"k_rowhash (per-row dedupe + sort of the symbolic phase)": (kern["symbolic_rowsort"]["ms"], kern["symbolic_rowsort"]["gbs"], "k_rowhash"),
+            "k_local<L1_STIFF,3> (K1)": (wl, kern["local_matrices"]["gbs"], "local_matrices"),
+            "k_numeric_t<4,128> (K2 numeric)": (wn, kern["csr_numeric"]["gbs"], "csr_numeric")}
+    kname = max(cand, key=lambda k: cand[k][0])
+    roof = {"bound": "hbm", "kernel": kname, "achieved": cand[kname][1], "peak": hbm_peak, "unit": "GB/s",
+            "frac": cand[kname][1] / hbm_peak, "frac_nominal_8tbs": cand[kname][1] / NOMINAL_HBM_GBS,
+            "traffic": TRAFFIC.get(cand[kname][2]), "peak_source": cx.peak_src,
+            "dominant_phase": dom,
+            "kernels": {"K1_local_matrices": kern["local_matrices"], "K2_csr_numeric": kern["csr_numeric"],
+                        "K3_cg_iteration": {k: solve[k] for k in ("ms_per_iter", "gbs", "frac", "frac_nominal_8tbs")},
+                        "symbolic_row_kernel": kern["symbolic_rowsort"]},
+            "note": "achieved = algorithmic bytes / CUDA-event time of the kernel; K1 / K2 / K3 are the HBM-bound "
+                    "kernels (fractions against the measured copy peak and the nominal 8 TB/s)"}
     value = world * nc_owned / (ms_step * 1e-3)
+    conf = workload_config(2, n, world)
+    if verify:
+        conf["parity_at_config"] = verify["parity_at_config"]
+    if dist_parity:
+        conf["dist_parity"] = "ok" if dist_parity["ok"] else "FAILED"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, world),
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
         "roofline": roof,
-        "step_algorithmic": {"bytes": b_step_algo, "gbs": b_step_algo / ms_step / 1e6,
-                             "frac": b_step_algo / ms_step / 1e6 / hbm_peak,
+        "step_algorithmic": {"bytes": b_step_algo, **fractions(b_step_algo / ms_step / 1e6, hbm_peak),
                              "note": "read grid once + write CSR once, over the whole cold step"},
         "phases_ms": phases, "kernels": kern, "cells": cells_note,
         "warm": {"value": world * nc_owned / ((wl + wn) * 1e-3), "unit": UNIT, "ms_per_step": wl + wn,
                  "note": "symbolic plan reused (K1 + K2 numeric only)"},
-        "solve": solve,
+        "solve": solve, "verify": verify, "dist_parity": dist_parity,
         "e2e": {"value": world * nc_owned / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                "host_cpus_bound": len(numa_cpus) if numa_cpus else None},
-        "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks.summary(),
+                "host_cpus_bound": len(cx.numa_cpus) if cx.numa_cpus else None},
+        "cpu_baseline": cpu,
+        "gpu_launches": (launches_per_step * args.steps) if launches_per_step else None,
+        "gpu_launches_note": "kernel launches of one cold step counted by CUPTI (torch.profiler) x steps",
+        "clocks": clocks.summary(),
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    del keep
+    return line
+
+
+# ----------------------------------------------------------------------------------------------
+# config #3: Darcy RT0/P0 saddle system, 256^3, strong scaling
+# ----------------------------------------------------------------------------------------------
+def run_config3(args, cx: Ctx):
+    import pygeon_b200 as pg
+    from pygeon_b200 import darcy, engine
+    from pygeon_b200 import dist as pgd
+    from pygeon_b200.solvers import minres_device
+
+    torch, dev, world, rank = cx.torch, cx.dev, cx.world, cx.rank
+    hbm_peak = cx.hbm_peak
+    n = args.n3
+    dist_parity = pgd.self_check(6, 4 * world + 2)
+
+    lay = pgd.slab_layout(n, n, world, rank)
+    sd = pgd.local_slab_grid(lay, device=dev)
+    nc = sd.num_cells
+    cells_total = 6 * n ** 3
+    raw = engine.RawGrid.upload(sd, dev, signs=True)
+    raw.check = False
+    torch.cuda.synchronize()
+    ev = cx.ev
+
+    def device_step(split=None):
+        pack = engine.GridPack.from_raw(raw)
+        plan = engine.symbolic(pack, "darcy")
+        if split is not None:
+            split.record()
+        data = engine.numeric(plan, engine.local_matrices(pack, "darcy_saddle", plan=plan))
+        return pack, plan, data
+
+    for _ in range(max(args.warmup, 3)):
+        pack, plan, data = device_step()
+        del pack, plan, data
+    cx.barrier()
+    launches_per_step = count_launches(lambda: device_step())
+    start, stop = ev(), ev()
+    with ClockSampler(cx.local) as clocks:
+        cx.barrier()
+        start.record()
+        for _ in range(args.steps):
+            pack, plan, data = device_step()
+            del pack, data
+        stop.record()
+        cx.barrier()
+        ms_step = cx.max_over_ranks(start.elapsed_time(stop) / args.steps)
+        # warm part (K1 + K2 numeric) of one more step
+        mid, end = ev(), ev()
+        pack, plan, data = device_step(mid)
+        end.record()
+        torch.cuda.synchronize()
+        warm_ms = cx.max_over_ranks(mid.elapsed_time(end))
+        # ---- distributed MINRES on the assembled system -------------------------------------
+        D = pgd.build_dist_csr(plan.indptr, plan.indices, data, pgd.owned_mask(sd, "darcy"), pgd.global_keys(sd, "darcy"))
+        nnz_local = plan.nnz
+        del pack, plan, data
+        torch.cuda.empty_cache()
+        gen = torch.Generator(device=dev).manual_seed(rank)
+        b = torch.randn(D.n_owned, dtype=torch.float64, device=dev, generator=gen)
+        iters = args.minres_iters
+        solve = {}
+        variants = [("peer", pgd.dist_minres_peer)] + ([("nccl", pgd.dist_minres)] if world > 1 else [])
+        for name, fn in variants:
+            fn(D, b, rtol=0.0, maxiter=3)
+            cx.barrier()
+            c0, c1 = ev(), ev()
+            c0.record()
+            _, _, k, _ = fn(D, b, rtol=0.0, maxiter=iters)
+            c1.record()
+            cx.barrier()
+            ms = cx.max_over_ranks(c0.elapsed_time(c1) / max(k, 1))
+            ipb = 8 if D.indptr.dtype == torch.int64 else 4
+            byt = cx.sum_over_ranks(12.0 * D.nnz + ipb * (D.n_owned + 1) + 112.0 * D.n_owned)
+            solve[name] = {"iters": k, "ms_per_iter": ms, "bytes_per_iter": byt, **fractions(byt / ms / 1e6, hbm_peak, world)}
+        unknowns = int(cx.sum_over_ranks(D.n_owned))
+        nnz_total = int(cx.sum_over_ranks(D.nnz))
+        halo = cx.sum_over_ranks(sum(int(v.numel()) for v in D.send_idx.values()) * 8)
+        if world == 1:  # the single-GPU driver beside the one-rank peer path
+            A1 = engine.DeviceCSR((D.n_owned, D.n_owned), D.indptr, D.indices, D.data)
+            minres_device(A1, b, rtol=0.0, maxiter=3)
+            c0, c1 = ev(), ev()
+            c0.record()
+            _, si = minres_device(A1, b, rtol=0.0, maxiter=iters)
+            c1.record()
+            torch.cuda.synchronize()
+            ms = c0.elapsed_time(c1) / max(si.iterations, 1)
+            solve["single_gpu_driver"] = {"iters": si.iterations, "ms_per_iter": ms,
+                                          **fractions(solve["peer"]["bytes_per_iter"] / ms / 1e6, hbm_peak)}
+        pgd.peer_release(D)
+        del D
+        torch.cuda.empty_cache()
+
+    # ---- end to end: public host-in / host-out call on this rank's slab ------------------------
+    e2e = None
+    try:
+        keep = pin_grid(sd)
+        for _ in range(2):
+            engine.clear_cache(sd)
+            A = pg.darcy_saddle_matrix(sd)
+        engine.clear_cache(sd)
+        cx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            engine.clear_cache(sd)
+            A = pg.darcy_saddle_matrix(sd)
+        torch.cuda.synchronize()
+        e2e_s = cx.max_over_ranks((time.perf_counter() - t0) / 2)
+        h2d = sd.cell_faces.indices.nbytes + sd.cell_faces.data.nbytes + sd.face_nodes.indices.nbytes + sd.nodes.nbytes
+        d2h = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes
+        e2e = {"value": cells_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(cx.sum_over_ranks(h2d)),
+               "d2h_bytes_per_step": int(cx.sum_over_ranks(d2h)), "ms_per_step": e2e_s * 1e3, "steps": 2,
+               "call": "pg.darcy_saddle_matrix(sd) on every rank's slab (host grid arrays in, scipy csc out)"}
+        del A, keep
+    except (MemoryError, RuntimeError) as e:  # host / device memory at --gpus 1
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "skipped": repr(e)[:200]}
+        cx.barrier()
+    if rank != 0:
+        return None
+    cpu = cpu_baseline_leg(args, 3) if (world == 1 and not args.no_cpu) else None
+    mr = solve["peer"]
+    roof = {"bound": "hbm", "kernel": "distributed MINRES iteration: kd_spmv<MINRES> + kd_mr_c + kd_mr_d (pgb_dist_minres, "
+                                      "halo + global sums over NVLink peer memory)",
+            "achieved": mr["gbs"] / world, "peak": hbm_peak, "unit": "GB/s", "frac": mr["frac"],
+            "frac_nominal_8tbs": mr["frac_nominal_8tbs"], "traffic": None, "peak_source": cx.peak_src,
+            "aggregate_gbs": mr["gbs"], "ms_per_iter": mr["ms_per_iter"], "bytes_per_iter": mr["bytes_per_iter"],
+            "nccl_variant": solve.get("nccl"), "single_gpu_driver": solve.get("single_gpu_driver"),
+            "assembly": {"cold_ms": ms_step, "warm_ms": warm_ms, "cold_cells_per_s": cells_total / (ms_step * 1e-3),
+                         "warm_cells_per_s": cells_total / (warm_ms * 1e-3)},
+            "note": "achieved = per-GPU share of the algorithmic bytes of one MINRES iteration (12 nnz + 4|8 (n+1) + "
+                    "112 n) / CUDA-event time, max over ranks"}
+    conf = workload_config(3, n, world)
+    conf["dist_parity"] = "ok" if dist_parity["ok"] else "FAILED"
+    conf["unknowns"], conf["nnz"] = unknowns, nnz_total
+    line = {
+        "metric": METRIC, "value": cells_total / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf, "roofline": roof,
+        "solve": solve, "dist_parity": dist_parity, "halo_bytes_sent_per_iter_all_ranks": halo,
+        "cells": f"{nc} cells evaluated on rank 0 (owned slab + one halo layer), {cells_total} in total",
+        "e2e": e2e, "cpu_baseline": cpu,
+        "gpu_launches": (launches_per_step * args.steps) if launches_per_step else None,
+        "gpu_launches_note": "kernel launches of one cold step counted by CUPTI (torch.profiler) x steps",
+        "clocks": clocks.summary(),
+    }
+    return line
+
+
+def run_ours(args):
+    cx = Ctx(args)
+    try:
+        line = run_config2(args, cx) if args.config == 2 else run_config3(args, cx)
+        if line is not None:
+            print(json.dumps(line))
+    finally:
+        cx.close()
 
 
 def main():
@@ -453,11 +726,21 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ncube", dest="n", type=int, default=128, help="cubes per side of the structured tet grid (per GPU)")
-    ap.add_argument("--cpu-n", type=int, default=40, help="cubes per side of the CPU-baseline sample")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3],
+                    help="BASELINE config number (1-based): 2 = P1 stiffness 128^3 per GPU, 3 = Darcy saddle 256^3 strong "
+                         "scaling; default 2 at --gpus 1, 3 otherwise")
+    ap.add_argument("--ncube", dest="n", type=int, default=128, help="config 2: cubes per side (per GPU)")
+    ap.add_argument("--ncube3", dest="n3", type=int, default=256, help="config 3: cubes per side of the whole box")
+    ap.add_argument("--cpu-n", type=int, default=64, help="cubes per side of the CPU-arm sample")
     ap.add_argument("--cg-iters", type=int, default=300)
+    ap.add_argument("--minres-iters", type=int, default=50)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", dest="verify", action="store_false",
+                    help="skip the full-CSR oracle comparison of config 2 (about one minute of host time)")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    if args.config == 0:
+        args.config = 2 if max(world, args.gpus) == 1 else 3
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -29,8 +29,11 @@ def test_extract_rows_and_columns(n, dens, idx64):
     from pygeon_b200.engine import DeviceCSR
 
     rng = np.random.default_rng(n)
-    A = sps.random(n, n, dens, random_state=n, format="csr") + sps.eye(n, format="csr") * (rng.random() > 0.5)
-    A = sps.csr_array(A)
+    m = max(int(dens * n * n), 1)  # (sps.random draws without replacement from n^2 candidates: minutes at n = 7e4)
+    A = sps.csr_array((rng.normal(size=m), (rng.integers(0, n, m), rng.integers(0, n, m))), shape=(n, n))
+    A.sum_duplicates()
+    if rng.random() > 0.5:
+        A = sps.csr_array(A + sps.eye(n, format="csr"))
     if n > 300:  # one long row, some empty rows
         A = sps.csr_array(sps.vstack([sps.csr_array(np.ones((1, n))), A[1:]]))
         live = np.flatnonzero(rng.random(n) > 0.1)

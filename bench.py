@@ -469,6 +469,17 @@ def run_config2(args, cx: Ctx):
         solve = {"solver": "cg (device-resident recurrence, pgb_cg)", "iters": info.iterations, "ms_per_iter": cg_ms,
                  "bytes_per_iter": b_cg, **fractions(b_cg / cg_ms / 1e6, hbm_peak), "n": nn, "nnz": nnz,
                  "note": "vectors (17 MB each) are L2 resident at this size"}
+        # the multi-GPU kernels (pgb_dist_cg) on a one-rank communicator: their intrinsic cost without a peer
+        D1 = pgd.build_dist_csr(S.indptr, S.indices, S.data, torch.ones(nn, dtype=torch.bool), torch.arange(nn))
+        pgd.dist_cg_peer(D1, b, rtol=0.0, atol=0.0, maxiter=5)
+        torch.cuda.synchronize()
+        c0.record()
+        _, _, its1, _ = pgd.dist_cg_peer(D1, b, rtol=0.0, atol=0.0, maxiter=cg_iters)
+        c1.record()
+        torch.cuda.synchronize()
+        solve["peer_kernels_one_rank_ms_per_iter"] = c0.elapsed_time(c1) / max(its1, 1)
+        pgd.peer_release(D1)
+        del D1
     else:
         D = pgd.build_dist_csr(S.indptr, S.indices, S.data, pgd.owned_mask(sd, "lagrange1"),
                                pgd.global_keys(sd, "lagrange1"))

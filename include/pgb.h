@@ -161,10 +161,14 @@ enum {
                            (p,q) = (0,1),(0,2)[,(0,3)],(1,2)[,(1,3),(2,3)]              L = (d+1) + d(d+1)/2 */
   PGB_L2_STIFF = 15,    /* Lagrange2 stiffness (h1.py:545-599): |c| sum_jl Mhat_jl grad phi_i(x_j)^T K
                            grad phi_k(x_l); pg.WEIGHT is not read (as the reference)   L = (d+1) + d(d+1)/2 */
-  PGB_RT1_MASS = 16     /* RT1 mass (hdiv.py:555-621, a Python loop over the cells): |c| Psi (M2 x K) Psi^T with the
+  PGB_RT1_MASS = 16,    /* RT1 mass (hdiv.py:555-621, a Python loop over the cells): |c| Psi (M2 x K) Psi^T with the
                            P2 local mass M2 and the nodal values Psi of the basis (hdiv.py:676-744), evaluated as a
                            constant contraction of the Gram matrix of the cell's edge vectors (pgb_rt1_table.cuh);
                            pg.WEIGHT is not read; aux_bits from pgb_pack_rt1            L = d(d+2) */
+  PGB_RT1_DIVDIV = 17   /* RT1 stiffness (discretization.py:154-183 with the divergence of hdiv.py:813-865 into
+                           PwLinears and its mass, l2.py:63-86,457-470): w / (d^2 |c|) s_p s_q (Dv^T Mhat Dv)_pq with
+                           the constant nodal values Dv of the local divergences; aux_bits from pgb_pack_rt1
+                                                                                        L = d(d+2) */
 };
 int pgb_local_size(int kind, int dim); /* L */
 /* dst_pos (nullable): [nc*L] destination row of every local row (the inc_pos of a mode-0 plan);

@@ -123,6 +123,31 @@ def main():
             store[key + "_indices"] = refS.indices.astype(np.int32)
             store[key + "_data"] = refS.data
             store[key + "_refnnz"] = sps.csr_array(ref).nnz
+        # RT1 stiffness (range space PwLinears) on the structural pattern of the RT1 dofs; broken-P1 mass
+        ref = rt1_stiff = pg.RT1("key").assemble_stiff_matrix(g, data)
+        refS = fo.canonicalise(ref, fo.closed_form("rt1", "mass", g, data, "key", tabs))
+        store["rt1_stiff_indptr"], store["rt1_stiff_indices"] = refS.indptr.astype(np.int32), refS.indices.astype(np.int32)
+        store["rt1_stiff_data"], store["rt1_stiff_refnnz"] = refS.data, sps.csr_array(ref).nnz
+        for nm, mat in (("pwlinears_mass", pg.PwLinears("key").assemble_mass_matrix(g, data)),
+                        ("pwlinears_lumped", pg.PwLinears("key").assemble_lumped_matrix(g, data))):
+            mat = sps.csr_array(mat)
+            mat.sum_duplicates()
+            mat.sort_indices()
+            store[nm + "_indptr"], store[nm + "_indices"], store[nm + "_data"] = (
+                mat.indptr.astype(np.int32), mat.indices.astype(np.int32), mat.data)
+        # error_l2 of a perturbed interpolant against the analytical function (discretization.py:304-358)
+        fs = lambda x: np.sin(x[0]) + x[1] * x[2] + 2.0  # noqa: E731
+        fv = lambda x: np.array([x[0] + 1.0, x[1] * x[0], x[2] - x[0]])  # noqa: E731
+        for nm, d, f in (("lagrange1", pg.Lagrange1("key"), fs), ("rt0", pg.RT0("key"), fv),
+                         ("bdm1", pg.BDM1("key"), fv), ("nedelec0", pg.Nedelec0("key"), fv),
+                         ("p0", pg.PwConstants("key"), fs)):
+            if nm == "nedelec0" and dim == 2:
+                continue  # the reference's Nedelec0.interpolate reads ridge_peaks, empty in 2D (hcurl.py:160)
+            u = d.interpolate(g, f)
+            u = u * (1.0 + 0.05 * np.cos(np.arange(u.size)))
+            store["errl2_" + nm] = np.array([d.error_l2(g, u, f, data=data), d.error_l2(g, u, f, relative=False, data=data),
+                                             d.error_l2(g, u, f, poly_order=None, data=data)])
+            store["errl2_u_" + nm] = u
         # RT1 pieces assembled on the host around the path: divergence, lumped matrix
         rt1 = pg.RT1("key")
         for nm, mat in (("rt1_diff", rt1.assemble_diff_matrix(g)), ("rt1_lumped", rt1.assemble_lumped_matrix(g, data))):

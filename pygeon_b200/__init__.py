@@ -29,6 +29,11 @@ def __getattr__(name):
         from . import discretization as _d
 
         return getattr(_d, name)
+    if name in ("PwPolynomials", "PwLinears", "VecPwPolynomials", "VecPwConstants", "VecPwLinears", "get_PwPolynomials",
+                "proj_to_PwPolynomials"):
+        from . import broken as _b
+
+        return getattr(_b, name)
     if name in ("LinearSystem", "create_restriction"):
         from . import linear_system as _l
 

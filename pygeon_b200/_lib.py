@@ -115,6 +115,7 @@ KIND = {
     "l2_mass": 14,
     "l2_stiff": 15,
     "rt1_mass": 16,
+    "rt1_divdiv": 17,
 }
 NPART = 1184
 

@@ -308,11 +308,11 @@ __global__ void __launch_bounds__(KB) kd_spmv(DSpmv a, CommDev c, Halo h, unsign
 
 template <typename IP, int MODE>
 int launch_dspmv(const DSpmv& a, const CommDev& c, const Halo& h, unsigned long long hs, int slot,
-                 unsigned long long rs, unsigned* ticket, int tpr, int grid_cap, cudaStream_t s) {
+                 unsigned long long rs, unsigned* ticket, int tpr, cudaStream_t s) {
 #define PGB_DSPMV(T)                                                                                   \
   {                                                                                                    \
     int64_t ntiles = ((a.n + (KB / T) - 1) / (KB / T) + SPMV_UR - 1) / SPMV_UR;                         \
-    int g = (int)(ntiles < grid_cap ? (ntiles < 1 ? 1 : ntiles) : grid_cap);                           \
+    int g = resident_grid(kd_spmv<T, IP, MODE>, ntiles);                                               \
     kd_spmv<T, IP, MODE><<<g, KB, 0, s>>>(a, c, h, hs, slot, rs, ticket);                              \
   }
   switch (tpr) {
@@ -559,6 +559,10 @@ __global__ void __launch_bounds__(KB) kd_mr_c(int64_t n, double* __restrict__ y,
   publish(c, M_BETA, out_seq, parts + M_BETA * NPART, tickets + T_B, ws, &sh_last);
 }
 
+__device__ __noinline__ bool mr_scalar_step_call(MinresScal* s, int itn, double bt, double xx) {
+  return mr_scalar_step(s, itn, bt, xx, 0);  // out of line: keeps the registers of the streaming loop low
+}
+
 // Every block advances a private copy of the scalar state (identical on all blocks and ranks), block 0
 // stores it; then halo push of the new v, w = (v - oldeps w1 - delta w2) denom over w1, x += phi w,
 // v = psolve(r2) / beta; global x.x.
@@ -582,7 +586,7 @@ __global__ void __launch_bounds__(KB) kd_mr_d(int64_t n, int itn, double* __rest
   if (threadIdx.x == 0) {
     MinresScal s = *sc_old;
     s.alfa = alfa;
-    const bool stop = mr_scalar_step(&s, itn, bt, xx, 0);
+    const bool stop = mr_scalar_step_call(&s, itn, bt, xx);
     sh_stop = stop ? 1 : 0;
     coef[0] = s.oldeps; coef[1] = s.delta; coef[2] = s.denom; coef[3] = s.phi; coef[4] = s.inv_beta;
     if (blockIdx.x == 0) {
@@ -702,21 +706,10 @@ int ensure_resid(Comm* cm, int maxiter) {
   return 0;
 }
 
-int spmv_grid_cap() {
-  static int cap = 0;
-  if (!cap) {
-    int dev = 0, sms = PGB_SMS;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cap = 8 * sms;  // KB = 256 threads, <= 8 resident blocks per SM: every block is resident (they spin)
-    if (cap > NPART) cap = NPART;
-  }
-  return cap;
-}
-
-// vector kernels wait on flags written by kernels of OTHER ranks only, but all of their blocks must be able
-// to become resident for the last-block ticket to complete: the grids never exceed NPART = 8 x 148 blocks.
-int vgrid(int64_t n) { return vec_grid(n); }
+// The waits inside a kernel are on flags raised by kernels of OTHER ranks (which depend on EARLIER kernels
+// of this rank only), so no block ever waits for a block of its own grid; the grids are sized to one
+// resident wave anyway (resident_grid), which also removes the tail of late blocks.
+#define VGRID(kernel) resident_grid(kernel, pgb_cdiv(n, KB))
 
 int check_err(Comm* cm, cudaStream_t s, const char* what) {
   int err = 0;
@@ -860,31 +853,29 @@ extern "C" int pgb_dist_cg(void* comm, int64_t n_owned, int64_t ghost_start, int
   PGB_CHECK(cudaMemsetAsync(done, 0, sizeof(int), s));
   const unsigned long long base = cm->epoch;
   cm->epoch += 2ull * ((unsigned long long)maxiter + 8ull);
-  const int vg = vgrid(n);
   const int tpr = threads_per_row > 0 ? threads_per_row : 4;
   if (iters_host) *iters_host = 0;
   if (info_host) *info_host = 0;
 
-  kd_cg_init<<<vg, KB, 0, s>>>(n, b, dinv, r, x, cm->parts, c, base + 1, cm->tickets);
+  kd_cg_init<<<VGRID(kd_cg_init), KB, 0, s>>>(n, b, dinv, r, x, cm->parts, c, base + 1, cm->tickets);
   PGB_LAUNCH_CHECK();
 
   DSpmv a = {};
   a.n = n; a.ia = interior_lo; a.ib = interior_hi;
   a.indptr = indptr; a.indices = indices; a.data = data;
   a.y = q; a.parts = cm->parts + S_PQ * NPART; a.done = done;
-  const int cap = spmv_grid_cap();
   int launched = 0;
   for (int k = 0; k < maxiter; ++k) {
     if (*(volatile int*)cm->flag_host) break;
     const unsigned long long sq = base + 1 + (unsigned long long)k;  // rr/rho of iteration k; pq uses sq too
     double* p_new = pbuf[k & 1];
     const double* p_old = pbuf[(k + 1) & 1];
-    kd_cg_p<<<vg, KB, 0, s>>>(n, k, r, dinv, p_old, p_new, sc, done, cm->resid, cm->flag_dev, c, h, sq, sq);
+    kd_cg_p<<<VGRID(kd_cg_p), KB, 0, s>>>(n, k, r, dinv, p_old, p_new, sc, done, cm->resid, cm->flag_dev, c, h, sq, sq);
     a.x = p_new;
-    int rc = idx64 ? launch_dspmv<int64_t, SPMV_CG>(a, c, h, sq, S_PQ, sq, cm->tickets + T_B, tpr, cap, s)
-                   : launch_dspmv<int32_t, SPMV_CG>(a, c, h, sq, S_PQ, sq, cm->tickets + T_B, tpr, cap, s);
+    int rc = idx64 ? launch_dspmv<int64_t, SPMV_CG>(a, c, h, sq, S_PQ, sq, cm->tickets + T_B, tpr, s)
+                   : launch_dspmv<int32_t, SPMV_CG>(a, c, h, sq, S_PQ, sq, cm->tickets + T_B, tpr, s);
     if (rc) return rc;
-    kd_cg_xr<<<vg, KB, 0, s>>>(n, p_new, q, dinv, x, r, cm->parts, sc, done, c, sq, sq + 1, cm->tickets);
+    kd_cg_xr<<<VGRID(kd_cg_xr), KB, 0, s>>>(n, p_new, q, dinv, x, r, cm->parts, sc, done, c, sq, sq + 1, cm->tickets);
     PGB_LAUNCH_CHECK();
     ++launched;
   }
@@ -942,13 +933,12 @@ extern "C" int pgb_dist_minres(void* comm, int64_t n_owned, int64_t ghost_start,
   PGB_CHECK(cudaMemsetAsync(done, 0, sizeof(int), s));
   const unsigned long long base = cm->epoch;
   cm->epoch += 2ull * ((unsigned long long)maxiter + 8ull);
-  const int vg = vgrid(n);
   const int tpr = threads_per_row > 0 ? threads_per_row : 4;
   if (iters_host) *iters_host = 0;
   if (info_host) *info_host = 0;
 
-  kd_mr_init<<<vg, KB, 0, s>>>(n, b, dinv, rb[0], x, wb[0], wb[1], cm->parts, c, base + 1, cm->tickets);
-  kd_mr_start<<<vg, KB, 0, s>>>(n, rb[0], dinv, v, sc, done, out2, rtol, shift, maxiter, cm->resid_cap, c, h, base + 1,
+  kd_mr_init<<<VGRID(kd_mr_init), KB, 0, s>>>(n, b, dinv, rb[0], x, wb[0], wb[1], cm->parts, c, base + 1, cm->tickets);
+  kd_mr_start<<<VGRID(kd_mr_start), KB, 0, s>>>(n, rb[0], dinv, v, sc, done, out2, rtol, shift, maxiter, cm->resid_cap, c, h, base + 1,
                                 base + 1);
   PGB_LAUNCH_CHECK();
   double hb[2];
@@ -966,7 +956,6 @@ extern "C" int pgb_dist_minres(void* comm, int64_t n_owned, int64_t ghost_start,
   a.n = n; a.ia = interior_lo; a.ib = interior_hi;
   a.indptr = indptr; a.indices = indices; a.data = data;
   a.parts = cm->parts + M_ALFA * NPART; a.done = done;
-  const int cap = spmv_grid_cap();
   int itn = 0;
   while (itn < maxiter) {
     if (*(volatile int*)cm->flag_host) break;
@@ -977,16 +966,16 @@ extern "C" int pgb_dist_minres(void* comm, int64_t n_owned, int64_t ghost_start,
     a.x = v; a.y = y; a.r1 = r1; a.itn = itn; a.mr = s_old;
     // halo of v for iteration itn was pushed with sequence number base + itn (start: base + 1)
     int rc = idx64 ? launch_dspmv<int64_t, SPMV_MINRES>(a, c, h, base + (unsigned long long)itn, M_ALFA, sq,
-                                                        cm->tickets + T_A, tpr, cap, s)
+                                                        cm->tickets + T_A, tpr, s)
                    : launch_dspmv<int32_t, SPMV_MINRES>(a, c, h, base + (unsigned long long)itn, M_ALFA, sq,
-                                                        cm->tickets + T_A, tpr, cap, s);
+                                                        cm->tickets + T_A, tpr, s);
     if (rc) return rc;
-    kd_mr_c<<<vg, KB, 0, s>>>(n, y, r2, dinv, s_old, done, cm->parts, c, sq, sq, cm->tickets);
+    kd_mr_c<<<VGRID(kd_mr_c), KB, 0, s>>>(n, y, r2, dinv, s_old, done, cm->parts, c, sq, sq, cm->tickets);
     double* old_r1 = r1;
     r1 = r2;
     r2 = y;
     y = (old_r1 == r1) ? spare : old_r1;
-    kd_mr_d<<<vg, KB, 0, s>>>(n, itn, v, w_old, w_new, r2, dinv, x, s_old, s_new, done, cm->resid, cm->flag_dev,
+    kd_mr_d<<<VGRID(kd_mr_d), KB, 0, s>>>(n, itn, v, w_old, w_new, r2, dinv, x, s_old, s_new, done, cm->resid, cm->flag_dev,
                               cm->parts, c, h, sq, sq, sq - 1, sq, base + (unsigned long long)itn + 1, cm->tickets);
     PGB_LAUNCH_CHECK();
     double* t = w_old;

@@ -472,16 +472,17 @@ extern "C" int pgb_cg(int64_t n, const void* indptr, int idx64, const int32_t* i
   a.n = n; a.indptr = indptr; a.indices = indices; a.data = data;
   a.x = x; a.y = q;
   if (launch_spmv<SPMV_PLAIN>(a, idx64, tpr, s)) return 1;
-  k_cg_init<<<vg, KB, 0, s>>>(n, b, q, dinv, r, p_rr, p_rho, p_bb);
+  k_cg_init<<<resident_grid(k_cg_init, pgb_cdiv(n, KB)), KB, 0, s>>>(n, b, q, dinv, r, p_rr, p_rho, p_bb);
   PGB_LAUNCH_CHECK();
   a.x = p; a.y = q; a.parts = p_pq; a.cg = sc;
+  const int g_p = resident_grid(k_cg_p, pgb_cdiv(n, KB)), g_xr = resident_grid(k_cg_xr, pgb_cdiv(n, KB));
   int launched = 0;
   for (int k = 0; k <= maxiter; ++k) {
     if (*(volatile int*)S.flag_host) break;
     if (k == maxiter) break;
-    k_cg_p<<<vg, KB, 0, s>>>(n, k, r, dinv, p, p_rr, p_rho, p_bb, sc, S.resid, S.flag_dev);
+    k_cg_p<<<g_p, KB, 0, s>>>(n, k, r, dinv, p, p_rr, p_rho, p_bb, sc, S.resid, S.flag_dev);
     if (launch_spmv<SPMV_CG>(a, idx64, tpr, s)) return 1;
-    k_cg_xr<<<vg, KB, 0, s>>>(n, p, q, dinv, x, r, p_pq, p_rr, p_rho, sc);
+    k_cg_xr<<<g_xr, KB, 0, s>>>(n, p, q, dinv, x, r, p_pq, p_rr, p_rho, sc);
     PGB_LAUNCH_CHECK();
     ++launched;
   }
@@ -559,13 +560,14 @@ extern "C" int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_
   k_dot<<<vg, KB, 0, s>>>(n, x, x, p_xx);
   PGB_LAUNCH_CHECK();
   a.parts = p_alfa; a.mr = sc;
+  const int g_c = resident_grid(k_mr_c, pgb_cdiv(n, KB)), g_d = resident_grid(k_mr_d, pgb_cdiv(n, KB));
   int itn = 0;
   while (itn < maxiter) {
     if (*(volatile int*)S.flag_host) break;
     ++itn;
     a.x = v; a.y = y; a.r1 = r1; a.itn = itn;
     if (launch_spmv<SPMV_MINRES>(a, idx64, tpr, s)) return 1;
-    k_mr_c<<<vg, KB, 0, s>>>(n, y, r2, dinv, p_alfa, p_beta, sc);
+    k_mr_c<<<g_c, KB, 0, s>>>(n, y, r2, dinv, p_alfa, p_beta, sc);
     // rotate: r1 <- r2, r2 <- y, y <- a free buffer
     double* old_r1 = r1;
     r1 = r2;
@@ -573,7 +575,7 @@ extern "C" int pgb_minres(int64_t n, const void* indptr, int idx64, const int32_
     y = (old_r1 == r1) ? spare : old_r1;
     k_mr_scalars<<<1, KB, 0, s>>>(itn, p_beta, p_xx, sc, S.resid, S.flag_dev, 0);
     // scipy: w1 = w2; w2 = w; w = (v - oldeps w1 - delta w2) denom.  The new w overwrites w_{k-2}.
-    k_mr_d<<<vg, KB, 0, s>>>(n, v, w_old, w_new, r2, dinv, x, p_xx, sc);
+    k_mr_d<<<g_d, KB, 0, s>>>(n, v, w_old, w_new, r2, dinv, x, p_xx, sc);
     PGB_LAUNCH_CHECK();
     double* t = w_old;
     w_old = w_new;

@@ -2,6 +2,8 @@
 // pgb_dist.cu): block reductions, the scalar state of CG / MINRES, the sub-warp-per-row SpMV.
 #pragma once
 #include <math.h>
+#include <map>
+#include <mutex>
 #include "pgb_common.cuh"
 
 namespace {
@@ -238,6 +240,33 @@ int vec_grid(int64_t n) {
   if (g > NPART) g = NPART;
   if (g < 1) g = 1;
   return (int)g;
+}
+
+// Grid of a grid-stride kernel with KB threads per block: as many blocks as are resident at once
+// (occupancy x SMs: one wave, no tail of late blocks), at most NPART (one partial sum per block) and at
+// most `work_blocks`.  The occupancy of every kernel is looked up once.
+template <typename Kern>
+int resident_grid(Kern kernel, int64_t work_blocks) {
+  static std::mutex mu;
+  static std::map<const void*, int> cache;
+  int cap = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find((const void*)kernel);
+    if (it != cache.end()) cap = it->second;
+  }
+  if (!cap) {
+    int occ = 0, dev = 0, sms = PGB_SMS;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, KB, 0) != cudaSuccess || occ < 1) occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cap = occ * sms;
+    if (cap > NPART) cap = NPART;
+    std::lock_guard<std::mutex> lock(mu);
+    cache[(const void*)kernel] = cap;
+  }
+  int64_t g = work_blocks < cap ? work_blocks : cap;
+  return (int)(g < 1 ? 1 : g);
 }
 
 __device__ inline void mr_tests(MinresScal* sc, double ynorm) {

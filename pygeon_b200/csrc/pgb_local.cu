@@ -237,7 +237,7 @@ struct LocalSize {
                            : (KIND == PGB_P0_MASS)                            ? 1
                            : (KIND == PGB_DARCY_SADDLE)                       ? D + 2
                            : (KIND == PGB_L2_MASS || KIND == PGB_L2_STIFF)    ? (D + 1) + D * (D + 1) / 2
-                           : (KIND == PGB_RT1_MASS)                           ? D * (D + 2)
+                           : (KIND == PGB_RT1_MASS || KIND == PGB_RT1_DIVDIV) ? D * (D + 2)
                                                                               : D + 1;
 };
 
@@ -501,6 +501,40 @@ __global__ void __launch_bounds__(BLOCK) k_local(Params p) {
           emit(pp * L + qq, negq ? -(sp * v) : sp * v);
         }
       }
+    } else if constexpr (KIND == PGB_RT1_DIVDIV) {
+      // RT1 stiffness B^T M_P1 B (hdiv.py:813-865 + l2.py:63-86,457-470): the nodal values of the
+      // divergence of local function q are s_q Dv[r][q] / (d |c|) with the constant table
+      // Dv[r][q] = 1 + (d+1)([r == i_q] - [r == j_q]) (face function at node i of the face opposite node j;
+      // i = q / d, j = (d(d+1) - 1 - q) % (d+1)) and (d+1)[r == k] - 1 (cell function k), nodes in rank
+      // order; with Mhat = (1 1^T + I) / ((d+1)(d+2)) the local matrix is
+      // w / (d^2 |c| (d+1)(d+2)) s_p s_q (colsum_p colsum_q + sum_r Dv[r][p] Dv[r][q]).
+      constexpr int N = D + 1;
+      const unsigned bits = p.aux_bits[c];
+      const double scale = w / (D * D * g.vol * (D + 1) * (D + 2));
+      auto dv = [](int r, int q) -> double {
+        if (q < D * N) {
+          const int i = q / D, j = (D * N - 1 - q) % N;
+          return 1.0 + N * ((r == i ? 1.0 : 0.0) - (r == j ? 1.0 : 0.0));
+        }
+        return N * (r == q - D * N ? 1.0 : 0.0) - 1.0;
+      };
+#pragma unroll
+      for (int pp = 0; pp < L; ++pp) {
+        const bool negp = pp < D * N && ((bits >> (8 + (D * N - 1 - pp) % N)) & 1u);
+#pragma unroll
+        for (int qq = 0; qq < L; ++qq) {
+          const bool negq = qq < D * N && ((bits >> (8 + (D * N - 1 - qq) % N)) & 1u);
+          double sp = 0.0, sq = 0.0, pq = 0.0;  // folded at compile time: pp, qq, r are unrolled constants
+#pragma unroll
+          for (int r = 0; r < N; ++r) {
+            sp += dv(r, pp);
+            sq += dv(r, qq);
+            pq += dv(r, pp) * dv(r, qq);
+          }
+          const double v = scale * (sp * sq + pq);
+          emit(pp * L + qq, negp != negq ? -v : v);
+        }
+      }
     } else if constexpr (KIND == PGB_RT0_MASS) {
       double A[D + 1][D + 1];
       rt0_local<D, HAS_K>(g, Kr, p.sign_bits[c], w, A);
@@ -641,6 +675,7 @@ int dispatch(int kind, const Params& p, cudaStream_t s) {
     case PGB_L2_MASS: return launch<PGB_L2_MASS, D>(p, s);
     case PGB_L2_STIFF: return launch<PGB_L2_STIFF, D>(p, s);
     case PGB_RT1_MASS: return launch<PGB_RT1_MASS, D>(p, s);
+    case PGB_RT1_DIVDIV: return launch<PGB_RT1_DIVDIV, D>(p, s);
   }
   pgb_set_error("pgb_local_matrices: unknown kind %d", kind);
   return 2;
@@ -659,7 +694,8 @@ extern "C" int pgb_local_size(int kind, int dim) {
     case PGB_DARCY_SADDLE: return dim + 2;
     case PGB_L2_MASS:
     case PGB_L2_STIFF: return (dim + 1) + dim * (dim + 1) / 2;
-    case PGB_RT1_MASS: return dim * (dim + 2);
+    case PGB_RT1_MASS:
+    case PGB_RT1_DIVDIV: return dim * (dim + 2);
     default: return dim + 1;
   }
 }
@@ -674,7 +710,7 @@ extern "C" int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* 
       kind == PGB_RT0_DIVDIV || kind == PGB_BDM1_DIVDIV || kind == PGB_DARCY_SADDLE || kind == PGB_BDM1_LUMPED)
     PGB_REQUIRE(sign_bits, "pgb_local_matrices: sign_bits required");
   if (kind == PGB_BDM1_MASS || kind == PGB_BDM1_LUMPED || kind == PGB_N0_MASS ||
-      (kind == PGB_N0_CURLCURL && dim == 3) || kind == PGB_RT1_MASS)
+      (kind == PGB_N0_CURLCURL && dim == 3) || kind == PGB_RT1_MASS || kind == PGB_RT1_DIVDIV)
     PGB_REQUIRE(aux_bits, "pgb_local_matrices: aux_bits required");
   if (nc == 0) return 0;
   Params p;

@@ -110,6 +110,43 @@ class Discretization(abc.ABC):
         """``assemble_mass_matrix(sd) @ interpolate(sd, func)`` (``discretization.py:221-235``)."""
         return self.assemble_mass_matrix(sd) @ self.interpolate(sd, func)
 
+    # ---- inclusion into the broken polynomials and what is built on it ---------------------------
+    def proj_to_PwPolynomials(self, sd) -> sps.csc_array:
+        """Inclusion into the broken polynomial space of the same order (``discretization.py:270-282``)."""
+        raise NotImplementedError(f"{type(self).__name__}: the broken space of order {self.poly_order} is not "
+                                  "part of this package")
+
+    def eval_at_cell_centers(self, sd) -> sps.csc_array:
+        """Matrix evaluating a discrete function at the cell centres (``discretization.py:200-219``)."""
+        from . import broken
+
+        if self.ndof(sd) == 0:
+            return sps.csc_array((3 ** self.tensor_order, 0))
+        space = broken.get_PwPolynomials(self.poly_order, self.tensor_order)(self.keyword)
+        return (space.eval_at_cell_centers(sd) @ self.proj_to_PwPolynomials(sd)).tocsc()
+
+    def assemble_broken_grad_matrix(self, sd) -> sps.csc_array:
+        """Element-wise gradient (``discretization.py:284-302``)."""
+        from . import broken
+
+        space = broken.get_PwPolynomials(self.poly_order, self.tensor_order)(self.keyword)
+        return (space.assemble_broken_grad_matrix(sd) @ self.proj_to_PwPolynomials(sd)).tocsc()
+
+    def error_l2(self, sd, num_sol, ana_sol, relative: bool = True, poly_order: int | None = -1,
+                 data: dict | None = None) -> float:
+        """L2 error against an analytical solution (``discretization.py:304-358``): by default both are
+        compared in the broken polynomials of order max(poly_order of the space, 1); ``poly_order=None``
+        compares with the interpolant of the space itself."""
+        from . import broken
+
+        if poly_order == -1:
+            poly_order = max(self.poly_order, 1)
+        if poly_order is None:
+            return broken._interp_error(self, sd, num_sol, ana_sol, relative, data)
+        space = broken.get_PwPolynomials(poly_order, self.tensor_order)(self.keyword)
+        proj_sol = broken.proj_to_PwPolynomials(self, sd, poly_order) @ num_sol
+        return space.error_l2(sd, proj_sol, ana_sol, relative, poly_order=None, data=data)
+
     def interpolate(self, sd, func) -> np.ndarray:
         raise NotImplementedError
 
@@ -174,6 +211,23 @@ class PwConstants(Discretization):
     def get_range_discr_class(self, dim: int):
         raise NotImplementedError("There's no zero discretization in PyGeoN")
 
+    def ndof_per_cell(self, sd) -> int:
+        return 1
+
+    def proj_to_PwPolynomials(self, sd) -> sps.csc_array:
+        return sps.eye_array(self.ndof(sd)).tocsc()
+
+    def eval_at_cell_centers(self, sd) -> sps.csc_array:
+        """The dof is the cell integral: value = dof / |c| (``fem/l2.py:422-432``)."""
+        return sps.diags_array(1.0 / np.asarray(sd.cell_volumes)).tocsc()
+
+    def proj_to_higher_PwPolynomials(self, sd) -> sps.csc_array:
+        """Into the broken P1: the cell value at every node slot (``fem/l2.py:408-420``)."""
+        return sps.vstack([self.eval_at_cell_centers(sd)] * (sd.dim + 1)).tocsc()
+
+    def assemble_broken_grad_matrix(self, sd) -> sps.csc_array:
+        return sps.csc_array((3 * self.ndof(sd), self.ndof(sd)))
+
 
 class Lagrange1(Discretization):
     """``fem/h1.py:13-324``: nodal P1."""
@@ -215,6 +269,18 @@ class Lagrange1(Discretization):
     def interpolate(self, sd, func) -> np.ndarray:
         """Nodal values (``fem/h1.py:255-269``)."""
         return np.array(_eval_points(func, sd.nodes))
+
+    def proj_to_PwPolynomials(self, sd) -> sps.csc_array:
+        """``fem/h1.py:218-237``."""
+        from . import broken
+
+        return broken.lagrange1_to_pwlinears(sd)
+
+    def eval_at_cell_centers(self, sd) -> sps.csc_array:
+        """Average of the nodal values of every cell (``fem/h1.py:239-253``)."""
+        from . import broken
+
+        return (broken.PwLinears().eval_at_cell_centers(sd) @ broken.lagrange1_to_pwlinears(sd)).tocsc()
 
     def assemble_nat_bc(self, sd, func, b_faces) -> np.ndarray:
         """``(v, g)`` on the boundary faces by the midpoint value spread over the face's nodes
@@ -332,6 +398,12 @@ class RT0(Discretization):
     def get_range_discr_class(self, _dim: int):
         return PwConstants
 
+    def proj_to_PwPolynomials(self, sd) -> sps.csc_array:
+        """``fem/hdiv.py:255-274``."""
+        from . import broken
+
+        return broken.rt0_to_vecpwlinears(sd)
+
 
 class BDM1(Discretization):
     """``fem/hdiv.py:277-509``: d dofs per face, dof (f, pos) -> f + pos*num_faces."""
@@ -380,6 +452,12 @@ class BDM1(Discretization):
 
     def get_range_discr_class(self, _dim: int):
         return PwConstants
+
+    def proj_to_PwPolynomials(self, sd) -> sps.csc_array:
+        """``fem/hdiv.py:450-509``."""
+        from . import broken
+
+        return broken.bdm1_to_vecpwlinears(sd)
 
 
 class RT1(Discretization):
@@ -496,11 +574,20 @@ class RT1(Discretization):
         vals[: bdm1.ndof(sd)] = bdm1.assemble_nat_bc(sd, func, b_faces)
         return vals
 
-    def assemble_stiff_matrix_device(self, sd, data=None):
-        self.get_range_discr_class(sd.dim)
+    def assemble_stiff_matrix_device(self, sd, data: dict | None = None) -> engine.DeviceCSR:
+        w, _ = self._coefficients(sd, data)
+        return engine.assemble_device(self._space, "stiff", sd, w, None)
+
+    def assemble_stiff_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
+        """``div^T M_PwLinears div`` (``discretization.py:154-183`` with ``hdiv.py:813-865,958`` and the
+        broken-P1 mass ``l2.py:63-86``): K1 kind ``PGB_RT1_DIVDIV`` (only the weight enters)."""
+        w, _ = self._coefficients(sd, data)
+        return engine.assemble_host(self._space, "stiff", sd, w, None)
 
     def get_range_discr_class(self, _dim: int):
-        raise NotImplementedError("PwLinears (the range of RT1) is not part of this package")
+        from . import broken
+
+        return broken.PwLinears
 
 
 class Nedelec0(Discretization):
@@ -536,6 +623,12 @@ class Nedelec0(Discretization):
 
     def assemble_nat_bc(self, sd, func, b_faces) -> np.ndarray:
         raise NotImplementedError  # as the reference, fem/hcurl.py:108-126
+
+    def proj_to_PwPolynomials(self, sd) -> sps.csc_array:
+        """``fem/hcurl.py:44-61``."""
+        from . import broken
+
+        return broken.nedelec0_to_vecpwlinears(sd)
 
     def assemble_lumped_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
         """Row sums of the mass matrix on the diagonal (``fem/hcurl.py:63-80``)."""

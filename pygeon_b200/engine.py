@@ -263,6 +263,7 @@ class GridPack:
     _bdm1: tuple | None = None
     _rt1: tuple | None = None
     _darcy: object = None
+    _pwl: object = None
     _l2: object = None
     plans: dict = field(default_factory=dict)
 
@@ -401,6 +402,11 @@ class GridPack:
                     _lib.count(1)
                 self._l2 = out
             return self._l2, self.nn + self.ne
+        if space == "pwlinears":  # broken P1: dof (slot k, cell c) = k * num_cells + c (fem/l2.py:38-49)
+            if self._pwl is None:
+                cells = torch.arange(self.nc, dtype=_I32, device=self.device)
+                self._pwl = (cells[:, None] + self.nc * torch.arange(d + 1, dtype=_I32, device=self.device)[None, :]).contiguous()
+            return self._pwl, (d + 1) * self.nc
         if space == "darcy":  # RT0 x P0: faces of the cell, then num_faces + cell
             if self._darcy is None:
                 cells = torch.arange(self.nc, dtype=_I32, device=self.device) + self.nf
@@ -639,6 +645,9 @@ _FORMS = {
     ("rt0", "lumped"): "rt0_lumped",
     ("bdm1", "lumped"): "bdm1_lumped",
     ("rt1", "mass"): "rt1_mass",
+    ("rt1", "stiff"): "rt1_divdiv",
+    ("pwlinears", "mass"): "l1_mass",
+    ("pwlinears", "lumped"): "l1_lumped",
 }
 
 
@@ -656,7 +665,7 @@ def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None, plan: "C
         aux = pack.edges()[1]
     elif kind in ("bdm1_mass", "bdm1_lumped"):
         aux = pack.bdm1()[1]
-    elif kind == "rt1_mass":
+    elif kind in ("rt1_mass", "rt1_divdiv"):
         aux = pack.rt1()[1]
     with torch.cuda.device(dev):
         rowmajor = plan is not None and plan.mode == 0

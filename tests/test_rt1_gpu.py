@@ -109,3 +109,54 @@ def test_bitwise_reproducible_and_properties():
     assert pg.RT1().ndof(sd) == 3 * (sd.num_faces + sd.num_cells)
     with pytest.raises(NotImplementedError):
         pg.RT1().assemble_stiff_matrix(sd)
+
+
+# ---- round 2: RT1 stiffness (range space PwLinears), broken-P1 mass, error_l2 ---------------------------
+def _csr(golden, key, n):
+    z = golden.z
+    return sps.csr_array((z[key + "_data"], z[key + "_indices"], z[key + "_indptr"]), shape=(n, n))
+
+
+def test_rt1_stiffness_golden(golden):
+    """RT1.assemble_stiff_matrix = div^T M_PwLinears div (discretization.py:154-183, hdiv.py:813-865,958)
+    through K1 kind PGB_RT1_DIVDIV, against the reference's matrix on the structural pattern."""
+    sd = golden.sd
+    A = pg.RT1("key").assemble_stiff_matrix(sd, golden.data)
+    n = pg.RT1().ndof(sd)
+    ref = _csr(golden, "rt1_stiff", n).tocsc()
+    ref.sort_indices()
+    assert A.shape == (n, n)
+    assert np.array_equal(A.indptr, ref.indptr) and np.array_equal(A.indices, ref.indices)
+    assert np.abs(A.data - ref.data).max() <= 1e-12 * np.abs(ref.data).max()
+    # and equals B^T M B with this package's own divergence and broken-P1 mass
+    B = pg.RT1("key").assemble_diff_matrix(sd)
+    M = pg.PwLinears("key").assemble_mass_matrix(sd, golden.data)
+    assert abs(A - B.T @ M @ B).max() <= 1e-12 * abs(A).max()
+
+
+def test_pwlinears_mass_and_lumped_golden(golden):
+    sd = golden.sd
+    n = (sd.dim + 1) * sd.num_cells
+    for nm, A in (("pwlinears_mass", pg.PwLinears("key").assemble_mass_matrix(sd, golden.data)),
+                  ("pwlinears_lumped", pg.PwLinears("key").assemble_lumped_matrix(sd, golden.data))):
+        ref = _csr(golden, nm, n).tocsc()
+        ref.sort_indices()
+        assert isinstance(A, sps.csc_array) and A.shape == (n, n)
+        assert np.array_equal(A.indptr, ref.indptr) and np.array_equal(A.indices, ref.indices), nm
+        assert np.abs(A.data - ref.data).max() <= 1e-13 * np.abs(ref.data).max(), nm
+
+
+def test_error_l2_golden(golden):
+    """Discretization.error_l2 (discretization.py:304-358): default (compared in the broken P1 space),
+    absolute, and against the space's own interpolant."""
+    sd = golden.sd
+    fs = lambda x: np.sin(x[0]) + x[1] * x[2] + 2.0  # noqa: E731
+    fv = lambda x: np.array([x[0] + 1.0, x[1] * x[0], x[2] - x[0]])  # noqa: E731
+    for nm, d, f in (("lagrange1", pg.Lagrange1("key"), fs), ("rt0", pg.RT0("key"), fv), ("bdm1", pg.BDM1("key"), fv),
+                     ("nedelec0", pg.Nedelec0("key"), fv), ("p0", pg.PwConstants("key"), fs)):
+        if "errl2_" + nm not in golden.z.files:
+            continue
+        u, ref = golden.z["errl2_u_" + nm], golden.z["errl2_" + nm]
+        got = [d.error_l2(sd, u, f, data=golden.data), d.error_l2(sd, u, f, relative=False, data=golden.data),
+               d.error_l2(sd, u, f, poly_order=None, data=golden.data)]
+        assert np.allclose(got, ref, rtol=1e-10), (nm, got, ref)

@@ -242,7 +242,14 @@ int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mode, int64_t
                             int32_t* indices, uint32_t* seg, void* stream);
 /* mode 0 plans: vals_t holds the local rows in row-sorted order (K1 called with dst_pos = inc_pos).
  * flags bit 0: transpose the rows' entries through shared memory and write them with coalesced
- * stores (faster when nnz is comparable to n_coo; same values either way). */
+ * stores (faster when nnz is comparable to n_coo; same values either way).
+ * flags bit 1: bring the contiguous local rows of every block of 128 CSR rows into shared memory with
+ * the bulk-async copy engine (cp.async.bulk + mbarrier, 3-stage ring) instead of per-thread loads; same
+ * summation order, bit-identical values.
+ * flags bits 2-5: G = 2, 4 or 8 lanes per CSR row (0 = one thread per row): lane j sums the local rows
+ * j, j + G, ... of the row, the G partial sums of every column are then added in lane order; a warp-wide
+ * load covers G consecutive local rows per row (coalesced), consecutive lanes store consecutive entries.
+ * A fixed, reproducible summation order that differs from the one-thread-per-row order in the last bits. */
 int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, const uint32_t* row_start,
                          const uint8_t* slots, const void* indptr, int idx64, const double* vals_t,
                          double* data, int flags, void* stream);

@@ -1296,6 +1296,14 @@ extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mo
   return 0;
 }
 
+int pgb_numeric_bulk_launch(int L, int64_t n_rows, int caps, bool staged, int idx64, const uint32_t* row_start,
+                            const uint8_t* slots, const void* indptr, const double* vals_t, double* data,
+                            cudaStream_t s);
+
+int pgb_numeric_group_launch(int L, int G, int64_t n_rows, int caps, int idx64, const uint32_t* row_start,
+                             const uint8_t* slots, const void* indptr, const double* vals_t, double* data,
+                             cudaStream_t s);
+
 extern "C" int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, const uint32_t* row_start,
                                     const uint8_t* slots, const void* indptr, int idx64, const double* vals_t,
                                     double* data, int flags, void* stream) {
@@ -1304,6 +1312,14 @@ extern "C" int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, cons
   cudaStream_t s = (cudaStream_t)stream;
   int caps = max_row_nnz < 1 ? 1 : max_row_nnz;
   const bool staged = (flags & 1) != 0;
+  if (const int G = (flags >> 2) & 15) {  // G lanes per row, coalesced loads and stores (pgb_numeric_bulk.cu)
+    int rc = pgb_numeric_group_launch(L, G, n_rows, caps, idx64, row_start, slots, indptr, vals_t, data, s);
+    if (rc >= 0) return rc;
+  }
+  if (flags & 2) {  // bulk-async staging of the block's contiguous local rows (pgb_numeric_bulk.cu)
+    int rc = pgb_numeric_bulk_launch(L, n_rows, caps, staged, idx64, row_start, slots, indptr, vals_t, data, s);
+    if (rc >= 0) return rc;
+  }
   return idx64 ? launch_numeric_t<int64_t>(L, n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s)
                : launch_numeric_t<int32_t>(L, n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
 }

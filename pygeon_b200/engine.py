@@ -565,6 +565,7 @@ def extract_rows(indptr, indices, data, rows, col_map):
     return ip, ix, da
 
 
+numeric_flags = int(os.environ.get("PGB_NUMERIC_FLAGS", "4"))  # bit 1: bulk-async staging, bit 2: lane groups per row (pgb.h)
 symbolic_mode = 0  # 0 = two-level (default), 1 = full (row,col) radix sort; see include/pgb.h
 force_idx64 = False  # tests: emit int64 indptr even when nnz < 2^31
 
@@ -693,7 +694,10 @@ def numeric(plan: CsrPlan, vals: torch.Tensor, out=None) -> torch.Tensor:
         else:
             # coalesced output through shared memory when the matrix has about as many entries as
             # COO candidates (RT0, BDM1, N0, Darcy); not for P1 in 3D (6 candidates per entry)
-            staged = 1 if 3 * plan.nnz > plan.n_coo else 0
+            staged = (1 if 3 * plan.nnz > plan.n_coo else 0) | (numeric_flags & 2)
+            if numeric_flags & 4:  # G lanes per row from the average number of local rows per CSR row
+                avg = plan.n_coo / plan.L / max(plan.n_rows, 1)
+                staged |= (8 if avg >= 12 else 4 if avg >= 6 else 2 if avg >= 3 else 0) << 2
             check(lib.pgb_csr_numeric_rows(plan.n_rows, plan.L, plan.max_row_nnz, plan.row_start.data_ptr(),
                                            plan.slots.data_ptr(), plan.indptr.data_ptr(),
                                            1 if plan.indptr.dtype == torch.int64 else 0,

@@ -157,6 +157,8 @@ def cpu_workload(config: int, n_sample: int):
         g.compute_geometry()
         if config == 2:
             step = lambda: rpg.Lagrange1().assemble_stiff_matrix(g)  # noqa: E731  discretization.py:154-183
+        elif config == 4:
+            step = lambda: rpg.Nedelec0().assemble_stiff_matrix(g) + rpg.Nedelec0().assemble_mass_matrix(g)  # noqa: E731
         else:
             def step():  # darcy.ipynb cell 10 / test_laplacian_mixed.py:50
                 M = rpg.RT0().assemble_mass_matrix(g)
@@ -169,13 +171,16 @@ def cpu_workload(config: int, n_sample: int):
         sd.compute_geometry()
         if config == 2:
             step = lambda: fo.port_stiff("lagrange1", sd)  # noqa: E731
+        elif config == 4:
+            step = lambda: fo.port_stiff("nedelec0", sd) + fo.port_mass("nedelec0", sd)  # noqa: E731
         else:
             def step():
                 M = fo.port_mass("rt0", sd)
                 B = sps.diags_array(1.0 / sd.cell_volumes) @ sd.cell_faces.T
                 return sps.block_array([[M, -B.T], [B, None]]).tocsc()
         what = "oracle port of the reference algorithm (baseline/_ref absent)"
-    name = "pg.Lagrange1().assemble_stiff_matrix" if config == 2 else "RT0 mass + P0 mass @ div + block_array (Darcy saddle)"
+    name = {2: "pg.Lagrange1().assemble_stiff_matrix", 3: "RT0 mass + P0 mass @ div + block_array (Darcy saddle)",
+            4: "pg.Nedelec0().assemble_stiff_matrix + assemble_mass_matrix"}[config]
     return step, sd.num_cells, f"{name} on {n_sample}^3 structured tet cube ({sd.num_cells} tets); {what}", kind
 
 
@@ -202,7 +207,7 @@ def run_reference(args):
     times = time_cpu(step, args.steps, budget_s=150.0)
     dt = sum(times) / len(times)
     v = cells / dt
-    full = workload_config(cfg, args.n if cfg == 2 else args.n3, args.gpus)
+    full = workload_config(cfg, {2: args.n, 3: args.n3, 4: args.n4}[cfg], args.gpus)
     conf = {"workload": what + " per step; scipy sparse kernels are single-threaded",
             "n_per_side": args.cpu_n, "cells": cells, "extrapolated_to": full["workload"],
             "note": "CPU throughput is flat or falling with size (SURVEY section 6), so cells/s measured on the "
@@ -224,6 +229,12 @@ def workload_config(cfg, n, gpus):
                             f"({6 * n ** 3} tets, {(n + 1) ** 3} nodes) per GPU; BASELINE configs[1]",
                 "n_per_side": n, "cells_per_gpu": 6 * n ** 3, "parallelism": f"cell-partitioned x{gpus}",
                 "l2": "inputs larger than L2 (step working set > 5 GB)"}
+    if cfg == 4:
+        return {"workload": f"pg.Nedelec0 curl-curl + mass (Maxwell type) on {n}^3 structured Kuhn-tet cube "
+                            f"({6 * n ** 3} tets, {7 * n ** 3 + 9 * n ** 2 + 3 * n} edges), one symbolic plan, CG; "
+                            f"BASELINE configs[3], the same cells at every GPU count",
+                "n_per_side": n, "cells_total": 6 * n ** 3, "parallelism": f"cell-partitioned z-slabs x{gpus}",
+                "l2": "inputs larger than L2 (step working set > 10 GB per GPU)"}
     return {"workload": f"mixed Darcy RT0/P0 saddle system [[M,-B^T],[-B,0]] on {n}^3 structured Kuhn-tet cube "
                         f"({6 * n ** 3} tets, {12 * n ** 3 + 6 * n ** 2 + 6 * n ** 3} unknowns), one-pass assembly + MINRES; "
                         f"BASELINE configs[2], the same cells at every GPU count",
@@ -575,88 +586,108 @@ def run_config2(args, cx: Ctx):
 
 
 # ----------------------------------------------------------------------------------------------
-# config #3: Darcy RT0/P0 saddle system, 256^3, strong scaling
+# configs #3 / #4: one box cut into z-slabs over the N GPUs (strong scaling), assembly + distributed solve
 # ----------------------------------------------------------------------------------------------
-def run_config3(args, cx: Ctx):
+STRONG = {
+    3: {"space": "darcy", "kinds": ["darcy_saddle"], "solver": "minres", "vec_bytes": 112.0, "ridges": False,
+        "solver_name": "distributed MINRES iteration: kd_spmv<MINRES> + kd_mr_c + kd_mr_d (pgb_dist_minres"},
+    4: {"space": "nedelec0", "kinds": ["n0_curlcurl", "n0_mass"], "solver": "cg", "vec_bytes": 88.0, "ridges": True,
+        "solver_name": "distributed CG iteration: kd_cg_p + kd_spmv<CG> + kd_cg_xr (pgb_dist_cg"},
+}
+
+
+def run_strong(args, cx: Ctx, cfg: int):
     import pygeon_b200 as pg
-    from pygeon_b200 import darcy, engine
+    from pygeon_b200 import engine
     from pygeon_b200 import dist as pgd
-    from pygeon_b200.solvers import minres_device
+    from pygeon_b200.solvers import cg_device, minres_device
 
     torch, dev, world, rank = cx.torch, cx.dev, cx.world, cx.rank
     hbm_peak = cx.hbm_peak
-    n = args.n3
+    W = STRONG[cfg]
+    space, kinds = W["space"], W["kinds"]
+    n = args.n3 if cfg == 3 else args.n4
     dist_parity = pgd.self_check(6, 4 * world + 2)
 
     lay = pgd.slab_layout(n, n, world, rank)
     sd = pgd.local_slab_grid(lay, device=dev)
     nc = sd.num_cells
     cells_total = 6 * n ** 3
-    raw = engine.RawGrid.upload(sd, dev, signs=True)
+    raw = engine.RawGrid.upload(sd, dev, signs=True, ridges=W["ridges"])
     raw.check = False
     torch.cuda.synchronize()
     ev = cx.ev
 
     def device_step(split=None):
+        """pack + symbolic (one plan for all operators of the space) + K1 / K2 per operator, summed"""
         pack = engine.GridPack.from_raw(raw)
-        plan = engine.symbolic(pack, "darcy")
+        plan = engine.symbolic(pack, space)
         if split is not None:
             split.record()
-        data = engine.numeric(plan, engine.local_matrices(pack, "darcy_saddle", plan=plan))
+        data = None
+        for kind in kinds:
+            d = engine.numeric(plan, engine.local_matrices(pack, kind, plan=plan))
+            data = d if data is None else data.add_(d)
         return pack, plan, data
 
+    launches_per_step = count_launches(lambda: device_step())
+    torch.cuda.empty_cache()  # the warm-up steps below leave the caching allocator with exactly the blocks a step needs
     for _ in range(max(args.warmup, 3)):
         pack, plan, data = device_step()
         del pack, plan, data
     cx.barrier()
-    launches_per_step = count_launches(lambda: device_step())
     start, stop = ev(), ev()
     with ClockSampler(cx.local) as clocks:
         cx.barrier()
         start.record()
         for _ in range(args.steps):
             pack, plan, data = device_step()
-            del pack, data
+            del pack, plan, data  # nothing of a step survives into the next one
         stop.record()
         cx.barrier()
         ms_step = cx.max_over_ranks(start.elapsed_time(stop) / args.steps)
-        # warm part (K1 + K2 numeric) of one more step
         mid, end = ev(), ev()
         pack, plan, data = device_step(mid)
         end.record()
         torch.cuda.synchronize()
         warm_ms = cx.max_over_ranks(mid.elapsed_time(end))
-        # ---- distributed MINRES on the assembled system -------------------------------------
-        D = pgd.build_dist_csr(plan.indptr, plan.indices, data, pgd.owned_mask(sd, "darcy"), pgd.global_keys(sd, "darcy"))
-        nnz_local = plan.nnz
+        # ---- distributed solve on the assembled system ----------------------------------------
+        D = pgd.build_dist_csr(plan.indptr, plan.indices, data, pgd.owned_mask(sd, space), pgd.global_keys(sd, space))
         del pack, plan, data
         torch.cuda.empty_cache()
         gen = torch.Generator(device=dev).manual_seed(rank)
         b = torch.randn(D.n_owned, dtype=torch.float64, device=dev, generator=gen)
-        iters = args.minres_iters
+        iters = args.solve_iters
+        if W["solver"] == "minres":
+            variants = [("peer", lambda **kw: pgd.dist_minres_peer(D, b, rtol=0.0, **kw)),
+                        ("nccl", lambda **kw: pgd.dist_minres(D, b, rtol=0.0, **kw))]
+        else:
+            variants = [("peer", lambda **kw: pgd.dist_cg_peer(D, b, rtol=0.0, atol=0.0, **kw)),
+                        ("nccl", lambda **kw: pgd.dist_cg(D, b, rtol=0.0, atol=0.0, **kw))]
         solve = {}
-        variants = [("peer", pgd.dist_minres_peer)] + ([("nccl", pgd.dist_minres)] if world > 1 else [])
-        for name, fn in variants:
-            fn(D, b, rtol=0.0, maxiter=3)
+        for name, fn in variants[: (2 if world > 1 else 1)]:
+            fn(maxiter=3)
             cx.barrier()
             c0, c1 = ev(), ev()
             c0.record()
-            _, _, k, _ = fn(D, b, rtol=0.0, maxiter=iters)
+            _, _, k, _ = fn(maxiter=iters)
             c1.record()
             cx.barrier()
             ms = cx.max_over_ranks(c0.elapsed_time(c1) / max(k, 1))
             ipb = 8 if D.indptr.dtype == torch.int64 else 4
-            byt = cx.sum_over_ranks(12.0 * D.nnz + ipb * (D.n_owned + 1) + 112.0 * D.n_owned)
+            byt = cx.sum_over_ranks(12.0 * D.nnz + ipb * (D.n_owned + 1) + W["vec_bytes"] * D.n_owned)
             solve[name] = {"iters": k, "ms_per_iter": ms, "bytes_per_iter": byt, **fractions(byt / ms / 1e6, hbm_peak, world)}
         unknowns = int(cx.sum_over_ranks(D.n_owned))
         nnz_total = int(cx.sum_over_ranks(D.nnz))
         halo = cx.sum_over_ranks(sum(int(v.numel()) for v in D.send_idx.values()) * 8)
         if world == 1:  # the single-GPU driver beside the one-rank peer path
             A1 = engine.DeviceCSR((D.n_owned, D.n_owned), D.indptr, D.indices, D.data)
-            minres_device(A1, b, rtol=0.0, maxiter=3)
+            one = (lambda **kw: minres_device(A1, b, rtol=0.0, **kw)) if W["solver"] == "minres" else (
+                lambda **kw: cg_device(A1, b, rtol=0.0, atol=0.0, **kw))
+            one(maxiter=3)
             c0, c1 = ev(), ev()
             c0.record()
-            _, si = minres_device(A1, b, rtol=0.0, maxiter=iters)
+            _, si = one(maxiter=iters)
             c1.record()
             torch.cuda.synchronize()
             ms = c0.elapsed_time(c1) / max(si.iterations, 1)
@@ -666,48 +697,54 @@ def run_config3(args, cx: Ctx):
         del D
         torch.cuda.empty_cache()
 
-    # ---- end to end: public host-in / host-out call on this rank's slab ------------------------
+    # ---- end to end: public host-in / host-out calls on this rank's slab ------------------------
+    def public_call():
+        engine.clear_cache(sd)
+        if cfg == 3:
+            return [pg.darcy_saddle_matrix(sd)]
+        return [pg.Nedelec0().assemble_stiff_matrix(sd), pg.Nedelec0().assemble_mass_matrix(sd)]
+
     e2e = None
     try:
         keep = pin_grid(sd)
         for _ in range(2):
-            engine.clear_cache(sd)
-            A = pg.darcy_saddle_matrix(sd)
-        engine.clear_cache(sd)
+            mats = public_call()
         cx.barrier()
         t0 = time.perf_counter()
         for _ in range(2):
-            engine.clear_cache(sd)
-            A = pg.darcy_saddle_matrix(sd)
+            mats = public_call()
         torch.cuda.synchronize()
         e2e_s = cx.max_over_ranks((time.perf_counter() - t0) / 2)
         h2d = sd.cell_faces.indices.nbytes + sd.cell_faces.data.nbytes + sd.face_nodes.indices.nbytes + sd.nodes.nbytes
-        d2h = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes
+        if W["ridges"]:
+            h2d += sd.face_ridges.indices.nbytes + sd.face_ridges.data.nbytes + sd.ridge_peaks.indices.nbytes
+        d2h = sum(A.indptr.nbytes + A.indices.nbytes + A.data.nbytes for A in mats)
         e2e = {"value": cells_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(cx.sum_over_ranks(h2d)),
                "d2h_bytes_per_step": int(cx.sum_over_ranks(d2h)), "ms_per_step": e2e_s * 1e3, "steps": 2,
-               "call": "pg.darcy_saddle_matrix(sd) on every rank's slab (host grid arrays in, scipy csc out)"}
-        del A, keep
+               "call": ("pg.darcy_saddle_matrix(sd)" if cfg == 3 else
+                        "pg.Nedelec0().assemble_stiff_matrix(sd) + assemble_mass_matrix(sd)")
+                       + " on every rank's slab (host grid arrays in, scipy csc out)"}
+        del mats, keep
     except (MemoryError, RuntimeError) as e:  # host / device memory at --gpus 1
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "skipped": repr(e)[:200]}
         cx.barrier()
     if rank != 0:
         return None
-    cpu = cpu_baseline_leg(args, 3) if (world == 1 and not args.no_cpu) else None
-    mr = solve["peer"]
-    roof = {"bound": "hbm", "kernel": "distributed MINRES iteration: kd_spmv<MINRES> + kd_mr_c + kd_mr_d (pgb_dist_minres, "
-                                      "halo + global sums over NVLink peer memory)",
-            "achieved": mr["gbs"] / world, "peak": hbm_peak, "unit": "GB/s", "frac": mr["frac"],
-            "frac_nominal_8tbs": mr["frac_nominal_8tbs"], "traffic": None, "peak_source": cx.peak_src,
-            "aggregate_gbs": mr["gbs"], "ms_per_iter": mr["ms_per_iter"], "bytes_per_iter": mr["bytes_per_iter"],
+    cpu = cpu_baseline_leg(args, cfg) if (world == 1 and not args.no_cpu) else None
+    sv = solve["peer"]
+    roof = {"bound": "hbm", "kernel": W["solver_name"] + ", halo + global sums over NVLink peer memory)",
+            "achieved": sv["gbs"] / world, "peak": hbm_peak, "unit": "GB/s", "frac": sv["frac"],
+            "frac_nominal_8tbs": sv["frac_nominal_8tbs"], "traffic": None, "peak_source": cx.peak_src,
+            "aggregate_gbs": sv["gbs"], "ms_per_iter": sv["ms_per_iter"], "bytes_per_iter": sv["bytes_per_iter"],
             "nccl_variant": solve.get("nccl"), "single_gpu_driver": solve.get("single_gpu_driver"),
             "assembly": {"cold_ms": ms_step, "warm_ms": warm_ms, "cold_cells_per_s": cells_total / (ms_step * 1e-3),
                          "warm_cells_per_s": cells_total / (warm_ms * 1e-3)},
-            "note": "achieved = per-GPU share of the algorithmic bytes of one MINRES iteration (12 nnz + 4|8 (n+1) + "
-                    "112 n) / CUDA-event time, max over ranks"}
-    conf = workload_config(3, n, world)
+            "note": "achieved = per-GPU share of the algorithmic bytes of one solver iteration (12 nnz + 4|8 (n+1) + "
+                    f"{W['vec_bytes']:.0f} n) / CUDA-event time, max over ranks"}
+    conf = workload_config(cfg, n, world)
     conf["dist_parity"] = "ok" if dist_parity["ok"] else "FAILED"
     conf["unknowns"], conf["nnz"] = unknowns, nnz_total
-    line = {
+    return {
         "metric": METRIC, "value": cells_total / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf, "roofline": roof,
@@ -718,13 +755,12 @@ def run_config3(args, cx: Ctx):
         "gpu_launches_note": "kernel launches of one cold step counted by CUPTI (torch.profiler) x steps",
         "clocks": clocks.summary(),
     }
-    return line
 
 
 def run_ours(args):
     cx = Ctx(args)
     try:
-        line = run_config2(args, cx) if args.config == 2 else run_config3(args, cx)
+        line = run_config2(args, cx) if args.config == 2 else run_strong(args, cx, args.config)
         if line is not None:
             print(json.dumps(line))
     finally:
@@ -737,14 +773,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3],
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4],
                     help="BASELINE config number (1-based): 2 = P1 stiffness 128^3 per GPU, 3 = Darcy saddle 256^3 strong "
-                         "scaling; default 2 at --gpus 1, 3 otherwise")
+                         "scaling, 4 = Nedelec0 curl-curl + mass 192^3 strong scaling + CG; default 2 at --gpus 1, 3 otherwise")
     ap.add_argument("--ncube", dest="n", type=int, default=128, help="config 2: cubes per side (per GPU)")
     ap.add_argument("--ncube3", dest="n3", type=int, default=256, help="config 3: cubes per side of the whole box")
     ap.add_argument("--cpu-n", type=int, default=64, help="cubes per side of the CPU-arm sample")
     ap.add_argument("--cg-iters", type=int, default=300)
-    ap.add_argument("--minres-iters", type=int, default=50)
+    ap.add_argument("--ncube4", dest="n4", type=int, default=192, help="config 4: cubes per side of the whole box")
+    ap.add_argument("--solve-iters", "--minres-iters", dest="solve_iters", type=int, default=50)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-verify", dest="verify", action="store_false",
                     help="skip the full-CSR oracle comparison of config 2 (about one minute of host time)")

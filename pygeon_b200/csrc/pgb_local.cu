@@ -42,12 +42,19 @@ __device__ __forceinline__ void load_nodes(const Params& p, int64_t c, double (&
     int ids[4] = {cn.x, cn.y, cn.z, cn.w};
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
+#ifndef PGB_K1_LD128
+      // one padded node = one 32-byte sector = one 256-bit load (one L1 wavefront per lane instead of two)
+      const double* q = p.coords + 4 * (int64_t)ids[a];
+      double pad;
+      asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(X[a][0]), "=d"(X[a][1]), "=d"(X[a][2]), "=d"(pad) : "l"(q));
+#else
       const double2* q = reinterpret_cast<const double2*>(p.coords) + 2 * (int64_t)ids[a];
       double2 xy = __ldg(q);
       double2 z_ = __ldg(q + 1);
       X[a][0] = xy.x;
       X[a][1] = xy.y;
       X[a][2] = z_.x;
+#endif
     }
   } else {
 #pragma unroll

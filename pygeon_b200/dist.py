@@ -126,6 +126,8 @@ def _dof_z_range(sd: SimplexGrid, space: str):
 
 def owned_mask(sd: SimplexGrid, space: str) -> torch.Tensor:
     """True for the local dofs this rank owns (lowest rank with a cell touching the dof)."""
+    if getattr(sd, "_part", None) is not None:
+        return _part_owned_mask(sd, space)
     lay: SlabLayout = sd._layout
     zmin, zmax = _dof_z_range(sd, space)
     in_plane = zmin == zmax
@@ -138,7 +140,10 @@ def owned_mask(sd: SimplexGrid, space: str) -> torch.Tensor:
 
 
 def global_keys(sd: SimplexGrid, space: str) -> torch.Tensor:
-    """A partition-independent int64 key per local dof (lattice key shifted by the slab offset)."""
+    """A partition-independent int64 key per local dof (lattice key shifted by the slab offset; the global
+    dof id for a grid cut out of a global grid by :func:`partition_local_grid`)."""
+    if getattr(sd, "_part", None) is not None:
+        return _part_global_keys(sd, space)
     st = sd._structured
     lay: SlabLayout = sd._layout
     n, sh = st["n"], st["key_bits"]
@@ -154,6 +159,103 @@ def global_keys(sd: SimplexGrid, space: str) -> torch.Tensor:
     if space == "darcy":
         return torch.cat([global_keys(sd, "rt0"), global_keys(sd, "p0") + (1 << 60)])
     raise KeyError(space)
+
+
+# --------------------------------------------------------------------------------------
+# arbitrary cell partition of a global grid ("any cell partition + owner = lowest-rank cell
+# touching the dof")
+# --------------------------------------------------------------------------------------
+def partition_local_grid(sd: SimplexGrid, cell_owner: np.ndarray, rank: int) -> SimplexGrid:
+    """Local grid of ``rank`` for the cell partition ``cell_owner`` (one rank id per global cell): the
+    rank's own cells plus every cell that shares a node with one of them (all cells touching any dof
+    the rank can own), with nodes / faces / cells renumbered in ascending global order.  The returned
+    grid carries ``_part``: the global ids of its nodes / faces / cells / ridges and the owner of every
+    local cell, from which :func:`owned_mask` / :func:`global_keys` work for every space."""
+    import scipy.sparse as sps
+
+    d = sd.dim
+    cell_owner = np.asarray(cell_owner)
+    nc, nf, nn = sd.num_cells, sd.num_faces, sd.num_nodes
+    cf = sd.cell_faces.indices.reshape(nc, d + 1)
+    fn = sd.face_nodes.indices.reshape(nf, d)
+    cn = sd.cell_node_table()
+    mine = cell_owner == rank
+    node_hit = np.zeros(nn, dtype=bool)
+    node_hit[cn[mine].ravel()] = True
+    cells = np.flatnonzero(node_hit[cn].any(axis=1))  # own cells + one node-layer of halo cells
+    faces = np.unique(cf[cells].ravel())
+    nodes = np.unique(fn[faces].ravel())
+    f_new = -np.ones(nf, dtype=np.int64)
+    f_new[faces] = np.arange(faces.size)
+    n_new = -np.ones(nn, dtype=np.int64)
+    n_new[nodes] = np.arange(nodes.size)
+    lcf = f_new[cf[cells]]  # ascending inside a cell: the renumbering is monotone
+    lsg = np.asarray(sd.cell_faces.data).reshape(nc, d + 1)[cells]
+    lfn = n_new[fn[faces]]
+    cell_faces = sps.csc_array((lsg.ravel(), lcf.ravel(), np.arange(0, lcf.size + 1, d + 1)),
+                               shape=(faces.size, cells.size))
+    face_nodes = sps.csc_array((np.ones(lfn.size, dtype=bool), lfn.ravel(), np.arange(0, lfn.size + 1, d)),
+                               shape=(nodes.size, faces.size))
+    loc = SimplexGrid(d, np.asarray(sd.nodes)[:, nodes], face_nodes, cell_faces, f"{sd.name}_part{rank}")
+    loc.compute_connectivity()
+    part = {"rank": rank, "cells": cells, "faces": faces, "nodes": nodes, "cell_owner": cell_owner[cells],
+            "num_global": {"lagrange1": nn, "rt0": nf, "p0": nc}}
+    if d == 3:  # global ridge ids of the local ridges through their global (lo, hi) node pairs
+        rp = loc.ridge_peaks.indices.reshape(loc.num_ridges, 2)
+        g = nodes[rp]
+        grp = sd.ridge_peaks.indices.reshape(sd.num_ridges, 2).astype(np.int64)
+        gkey = grp.min(axis=1) * nn + grp.max(axis=1)
+        order = np.argsort(gkey)
+        want = g.min(axis=1) * nn + g.max(axis=1)
+        pos = np.searchsorted(gkey[order], want)
+        if np.any(gkey[order][np.minimum(pos, gkey.size - 1)] != want):
+            raise ValueError("a local ridge is missing from the global grid")
+        part["ridges"] = order[pos]
+        part["num_global"]["nedelec0"] = sd.num_ridges
+    else:
+        part["ridges"] = faces
+        part["num_global"]["nedelec0"] = nf
+    loc._part = part
+    return loc
+
+
+def _part_cell_dofs(sd: SimplexGrid, space: str) -> np.ndarray:
+    """(nc_local, k) local dof ids touched by every local cell."""
+    d, nc = sd.dim, sd.num_cells
+    if space == "lagrange1":
+        return sd.cell_node_table()
+    if space == "rt0":
+        return sd.cell_faces.indices.reshape(nc, d + 1)
+    if space == "p0":
+        return np.arange(nc)[:, None]
+    if space == "nedelec0":
+        if d == 2:
+            return sd.cell_faces.indices.reshape(nc, 3)
+        fr = sd.face_ridges.indices.reshape(sd.num_faces, 3)
+        return fr[sd.cell_faces.indices.reshape(nc, 4)].reshape(nc, 12)
+    raise KeyError(space)
+
+
+def _part_owned_mask(sd: SimplexGrid, space: str) -> torch.Tensor:
+    if space == "darcy":
+        return torch.cat([_part_owned_mask(sd, "rt0"), _part_owned_mask(sd, "p0")])
+    part = sd._part
+    dofs = _part_cell_dofs(sd, space)
+    ndof = {"lagrange1": sd.num_nodes, "rt0": sd.num_faces, "p0": sd.num_cells, "nedelec0": sd.num_edges}[space]
+    owner = np.full(ndof, np.iinfo(np.int64).max, dtype=np.int64)
+    np.minimum.at(owner, dofs.ravel(), np.repeat(part["cell_owner"].astype(np.int64), dofs.shape[1]))
+    # a dof is decided only if one of this rank's OWN cells touches it (then all its cells are local)
+    touched = np.zeros(ndof, dtype=bool)
+    touched[dofs[part["cell_owner"] == part["rank"]].ravel()] = True
+    return torch.from_numpy(touched & (owner == part["rank"]))
+
+
+def _part_global_keys(sd: SimplexGrid, space: str) -> torch.Tensor:
+    part = sd._part
+    if space == "darcy":
+        return torch.cat([_part_global_keys(sd, "rt0"), _part_global_keys(sd, "p0") + (1 << 60)])
+    ids = {"lagrange1": part["nodes"], "rt0": part["faces"], "p0": part["cells"], "nedelec0": part["ridges"]}[space]
+    return torch.from_numpy(np.asarray(ids, dtype=np.int64))
 
 
 # --------------------------------------------------------------------------------------

@@ -565,7 +565,9 @@ def extract_rows(indptr, indices, data, rows, col_map):
     return ip, ix, da
 
 
-numeric_flags = int(os.environ.get("PGB_NUMERIC_FLAGS", "4"))  # bit 1: bulk-async staging, bit 2: lane groups per row (pgb.h)
+# K2 numeric variant (pgb.h): 0 = one thread per row (the fastest for every space measured, profiles/r2_numeric_ab.txt),
+# bit 1: bulk-async staging of the block's local rows, bit 2: lane groups per row
+numeric_flags = int(os.environ.get("PGB_NUMERIC_FLAGS", "0"))
 symbolic_mode = 0  # 0 = two-level (default), 1 = full (row,col) radix sort; see include/pgb.h
 force_idx64 = False  # tests: emit int64 indptr even when nnz < 2^31
 

@@ -138,3 +138,73 @@ def test_slab_layout_covers_all_layers():
         assert all(a.z1 == b.z0 for a, b in zip(lays, lays[1:]))
         assert max(l.nz_owned for l in lays) - min(l.nz_owned for l in lays) <= 1
         assert not lays[-1].halo_top and all(l.halo_top for l in lays[:-1])
+
+
+# ---- arbitrary cell partition of an unstructured grid ------------------------------------
+def _worker_unstructured(rank, world, port, q, dim):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import sys
+
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from oracle import fem_oracle as fo
+        from pgb_helpers import delaunay_grid
+
+        full = delaunay_grid(dim, 250 if dim == 3 else 400, seed=3)
+        full.compute_geometry()
+        # a partition with ragged, non-convex interfaces: by angle around the centre
+        cc = full.cell_centers
+        ang = np.arctan2(cc[1] - 0.5, cc[0] - 0.5)
+        owner = np.floor((ang + np.pi) / (2 * np.pi) * world).astype(int).clip(0, world - 1)
+        sd = pd.partition_local_grid(full, owner, rank)
+        assert set(np.flatnonzero(owner == rank)) <= set(sd._part["cells"])
+        rng = np.random.default_rng(1)
+        for space, form in CASES:
+            kw = {"rot2d": False} if space == "lagrange1" else {}
+            Aloc = fo.closed_form(space, form, sd, **kw)
+            Aglob = fo.closed_form(space, form, full, **kw).tocsr()
+            D = pd.build_dist_csr(torch.from_numpy(Aloc.indptr.astype(np.int64)), torch.from_numpy(Aloc.indices),
+                                  torch.from_numpy(Aloc.data), pd.owned_mask(sd, space), pd.global_keys(sd, space))
+            keys = pd.global_keys(sd, space)
+            gid_owned = D.owned_keys.numpy()
+            allo = pd._all_gather_var(D.owned_keys)
+            assert np.array_equal(np.sort(torch.cat(allo).numpy()), np.arange(Aglob.shape[0])), space
+            cid = D.column_ids()
+            valid = (cid >= 0).numpy()
+            gcol = np.zeros(D.n_local, dtype=np.int64)
+            gcol[valid] = keys[cid[cid >= 0]].numpy()
+            loc = sps.csr_array((D.data.numpy(), D.indices.numpy(), D.indptr.numpy()), shape=(D.n_owned, D.n_local))
+            P = sps.csr_array((valid.astype(float), (np.arange(D.n_local), gcol)), shape=(D.n_local, Aglob.shape[1]))
+            assert abs(loc @ P - Aglob[gid_owned]).max() <= 1e-13 * abs(Aglob).max(), space
+            xg = rng.normal(size=Aglob.shape[1])
+            x = torch.zeros(D.n_local, dtype=torch.float64)
+            x[: D.n_owned] = torch.from_numpy(xg[gid_owned])
+            pd.halo_exchange(D, x)
+            assert np.array_equal(x.numpy()[valid], xg[gcol[valid]]), space
+            assert np.abs(loc @ x.numpy() - (Aglob @ xg)[gid_owned]).max() <= 1e-12 * np.abs(Aglob @ xg).max()
+            a, b = pd.interior_range(D)
+            ghost_rows = np.unique(loc.tocoo().row[loc.tocoo().col >= D.ghost_start])
+            assert not np.any((ghost_rows >= a) & (ghost_rows < b))
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, traceback.format_exc()))
+        raise
+
+
+@pytest.mark.parametrize("dim,world", [(2, 3), (3, 2)])
+def test_arbitrary_partition_gloo(dim, world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_unstructured, args=(r, world, port, q, dim)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res

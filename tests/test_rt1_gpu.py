@@ -107,8 +107,9 @@ def test_bitwise_reproducible_and_properties():
     u = pg.RT1().interpolate(sd, lambda x: np.array([1.0, -2.0, 0.5]))
     assert abs(u @ (M @ u) - 5.25) < 1e-11
     assert pg.RT1().ndof(sd) == 3 * (sd.num_faces + sd.num_cells)
-    with pytest.raises(NotImplementedError):
-        pg.RT1().assemble_stiff_matrix(sd)
+    # stiffness (round 2): symmetric positive semi-definite, kernel contains the divergence-free interpolant
+    S = pg.RT1().assemble_stiff_matrix(sd)
+    assert abs(S - S.T).max() <= 1e-12 * abs(S).max() and abs(u @ (S @ u)) < 1e-9
 
 
 # ---- round 2: RT1 stiffness (range space PwLinears), broken-P1 mass, error_l2 ---------------------------

@@ -166,12 +166,87 @@ class map_geometry:  # namespace like porepy's module of that name
         return None, None, None, None, R, keep, None
 
 
-class MortarGrid:  # only used as a base class / in annotations
-    pass
+class MortarGrid:
+    """Conforming mortar grid (the subset of `pp.MortarGrid` the reference reads, grids/mortar_grid.py): one
+    mortar cell per (primary face, secondary cell) pair, 0/1 projections, cell measures of the secondary
+    cells.  Restated from PorePy's documented behaviour for matching grids; PorePy itself is absent."""
+
+    def __init__(self, dim, face_up, cell_down, num_primary_faces, num_secondary_cells, cell_volumes, name="mortar"):
+        self.dim = int(dim)
+        self.name = name
+        self._face_up = np.asarray(face_up)
+        self._cell_down = np.asarray(cell_down)
+        self.num_cells = self._face_up.size
+        self._nf, self._nc = int(num_primary_faces), int(num_secondary_cells)
+        self._vol = np.asarray(cell_volumes, dtype=float)
+        self.tags = {}
+
+    def __hash__(self):
+        return id(self)
+
+    def __eq__(self, other):
+        return self is other
+
+    def compute_geometry(self):
+        self.cell_volumes = self._vol[self._cell_down].copy()
+
+    def primary_to_mortar_int(self):
+        m = np.arange(self.num_cells)
+        return sps.csc_array((np.ones(self.num_cells), (m, self._face_up)), shape=(self.num_cells, self._nf))
+
+    def secondary_to_mortar_int(self):
+        m = np.arange(self.num_cells)
+        return sps.csc_array((np.ones(self.num_cells), (m, self._cell_down)), shape=(self.num_cells, self._nc))
 
 
-class MixedDimensionalGrid:  # only used as a base class / in annotations
-    pass
+class MixedDimensionalGrid:
+    """Container of subdomains and interfaces with data dictionaries (the subset of
+    `pp.MixedDimensionalGrid` the reference's operator layer calls)."""
+
+    def __init__(self):
+        self._sds, self._intfs = [], []
+
+    def add_subdomains(self, sds):
+        for sd in sds if isinstance(sds, (list, tuple)) else [sds]:
+            self._sds.append((sd, {}))
+        self._sds.sort(key=lambda t: -t[0].dim)
+
+    def add_interface(self, intf, sd_pair, _map=None):
+        up, down = sd_pair if sd_pair[0].dim > sd_pair[1].dim else sd_pair[::-1]
+        self._intfs.append((intf, {}, (up, down)))
+        self._intfs.sort(key=lambda t: -t[0].dim)
+
+    def subdomains(self, return_data=False, dim=None):
+        sel = [(g, d) for g, d in self._sds if dim is None or g.dim == dim]
+        return sel if return_data else [g for g, _ in sel]
+
+    def interfaces(self, return_data=False, dim=None):
+        sel = [(g, d) for g, d, _ in self._intfs if dim is None or g.dim == dim]
+        return sel if return_data else [g for g, _ in sel]
+
+    def interface_to_subdomain_pair(self, intf):
+        return next(pair for g, _, pair in self._intfs if g is intf)
+
+    def subdomain_data(self, sd):
+        return next(d for g, d in self._sds if g is sd)
+
+    def interface_data(self, intf):
+        return next(d for g, d, _ in self._intfs if g is intf)
+
+    def num_subdomains(self):
+        return len(self._sds)
+
+    def num_interfaces(self):
+        return len(self._intfs)
+
+    def num_subdomain_cells(self, cond=None):
+        return int(sum(g.num_cells for g, _ in self._sds if cond is None or cond(g)))
+
+    def dim_max(self):
+        return max(g.dim for g, _ in self._sds)
+
+    def dim_min(self):
+        return min(g.dim for g, _ in self._sds)
 
 
 class _Dummy:

@@ -11,7 +11,7 @@ Importing the package never touches CUDA; the first assemble/solve call loads ``
 from .constants import *  # noqa: F401,F403
 from . import bmat, numerics  # noqa: F401
 from .grid import SimplexGrid, reference_element, structured_grid, unit_grid  # noqa: F401
-from .md_grid import MixedDimensionalGrid, MortarGrid, as_mdg  # noqa: F401
+from .md_grid import MixedDimensionalGrid, MortarGrid, as_mdg, fractured_unit_cube  # noqa: F401
 from .numerics.differentials import curl, div, grad  # noqa: F401
 from .numerics.innerproducts import (cell_mass, face_mass, lumped_cell_mass, lumped_face_mass,  # noqa: F401
                                      lumped_peak_mass, lumped_ridge_mass, peak_mass, ridge_mass)

@@ -143,10 +143,13 @@ class SimplexGrid:
         if not np.all(np.sign(out) == np.sign(s)):
             raise ValueError("cell_faces signs are inconsistent with the node-order normals")
 
+        # faces tagged as fracture / tip faces by a mixed-dimensional construction stay tagged and are not
+        # part of the domain boundary (PorePy's convention)
+        self.tags.setdefault("tip_faces", np.zeros(self.num_faces, dtype=bool))
+        self.tags.setdefault("fracture_faces", np.zeros(self.num_faces, dtype=bool))
         bnd = np.bincount(self.cell_faces.indices, minlength=self.num_faces) == 1
+        bnd &= ~(self.tags["tip_faces"] | self.tags["fracture_faces"])
         self.tags["domain_boundary_faces"] = bnd
-        self.tags["tip_faces"] = np.zeros(self.num_faces, dtype=bool)
-        self.tags["fracture_faces"] = np.zeros(self.num_faces, dtype=bool)
         bn = np.zeros(self.num_nodes, dtype=bool)
         bn[fn[bnd].ravel()] = True
         self.tags["domain_boundary_nodes"] = bn

@@ -283,6 +283,59 @@ class MixedDimensionalGrid:
                 f"dimensions {self.dim_max()}..{self.dim_min()}")
 
 
+def fractured_unit_cube(n: int, perturb: float = 0.0, seed: int = 0) -> MixedDimensionalGrid:
+    """Unit cube of ``n x n x n`` Kuhn cubes (``n`` even) cut by the horizontal fracture ``z = 1/2``: the 3D
+    grid is split along the fracture (nodes, ridges and faces of the plane exist once per side, as PorePy's
+    fracture meshing produces them), the fracture is the matching ``n x n`` structured triangle grid in that
+    plane, and one conforming mortar grid of ``2 * 2 n^2`` cells couples them.  A gmsh-free stand-in for
+    ``pp.mdg_library.cube_with_orthogonal_fractures`` (tests/conftest.py:277-282 of the reference) that
+    scales to any size; ``perturb`` moves the nodes off the fracture plane randomly."""
+    from .grid import SimplexGrid, structured_grid
+
+    if n % 2:
+        raise ValueError("n must be even")
+    h = n // 2
+    bot = structured_grid(3, n, nz=h, perturb=perturb, seed=seed)
+    top = structured_grid(3, n, nz=h, z0=h, perturb=perturb, seed=seed + 1)
+    nn_b, nf_b, nc_b = bot.num_nodes, bot.num_faces, bot.num_cells
+    nodes = np.hstack([bot.nodes, top.nodes])
+    face_nodes = sps.block_diag([bot.face_nodes.astype(float), top.face_nodes.astype(float)], format="csc").astype(bool)
+    cell_faces = sps.block_diag([bot.cell_faces, top.cell_faces], format="csc")
+    sd3 = SimplexGrid(3, nodes, face_nodes, cell_faces, "fractured_cube_3d")
+    sd2 = structured_grid(2, n)
+    sd2.nodes[2] = 0.5
+    sd2.name = "fracture_2d"
+    # fracture faces: the top plane of the bottom half, the bottom plane of the top half; a face of the plane
+    # is matched to the fracture cell with the same three lattice nodes
+    m2 = (n + 1) ** 2
+    fn3 = sd3.face_nodes.indices.reshape(sd3.num_faces, 3).astype(np.int64)
+    plane_b = np.flatnonzero((fn3[:nf_b] >= h * m2).all(axis=1))  # bottom half: nodes of its last layer
+    plane_t = nf_b + np.flatnonzero((fn3[nf_b:] - nn_b < m2).all(axis=1))  # top half: nodes of its first layer
+
+    def key(tri):
+        tri = np.sort(tri, axis=1)
+        return (tri[:, 0] * m2 + tri[:, 1]) * m2 + tri[:, 2]
+
+    cn2 = sd2.cell_node_table().astype(np.int64)
+    order = np.argsort(key(cn2))
+    sorted_keys = key(cn2)[order]
+    face_up, cell_down = [], []
+    for faces, shift in ((plane_b, h * m2), (plane_t, nn_b)):
+        pos = np.searchsorted(sorted_keys, key(fn3[faces] - shift))
+        if np.any(sorted_keys[np.minimum(pos, sorted_keys.size - 1)] != key(fn3[faces] - shift)):
+            raise RuntimeError("fracture faces do not match the fracture grid")
+        face_up.append(faces)
+        cell_down.append(order[pos])
+    face_up, cell_down = np.concatenate(face_up), np.concatenate(cell_down)
+    frac = np.zeros(sd3.num_faces, dtype=bool)
+    frac[face_up] = True
+    sd3.tags["fracture_faces"] = frac
+    mdg = MixedDimensionalGrid()
+    mdg.add_subdomains([sd3, sd2])
+    mdg.add_interface(MortarGrid(2, face_up, cell_down, "mortar_2d"), (sd3, sd2))
+    return mdg
+
+
 def as_mdg(obj) -> MixedDimensionalGrid:
     """A grid wrapped as a one-subdomain mixed-dimensional grid; a mixed-dimensional grid is returned
     unchanged (``filters/convert_from_pp.py:66-87``)."""

@@ -215,6 +215,7 @@ __device__ __forceinline__ void halo_wait(const CommDev& c, const Halo& h, unsig
 // ---- SpMV over the owned rows: rows without ghost columns [ia, ib) first, the interface rows after the halo ----
 struct DSpmv {
   int64_t n, ia, ib;
+  int32_t gs;             // first ghost column
   const void* indptr;
   const int32_t* indices;
   const double* data;
@@ -226,6 +227,16 @@ struct DSpmv {
   const int* done;
   int itn;
 };
+
+// Owned entries of x were written by an earlier kernel: read-only here, so they take the non-coherent path
+// like the single-GPU SpMV (measured: plain loads cost the kernel 10-20 %).  Ghost entries are stored by
+// the peers WHILE this kernel runs (before the flag this block waited for): coherent L2 loads.
+__device__ __forceinline__ double load_x(const double* x, int32_t c, int32_t gs) {
+  if (c < gs) return __ldg(x + c);
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(x + c) : "memory");
+  return v;
+}
 
 template <int TPR, typename IP, int MODE>
 __global__ void __launch_bounds__(KB) kd_spmv(DSpmv a, CommDev c, Halo h, unsigned long long halo_seq, int red_slot,
@@ -276,10 +287,10 @@ __global__ void __launch_bounds__(KB) kd_spmv(DSpmv a, CommDev c, Halo h, unsign
     }
     double s[UR];
 #pragma unroll
-    for (int u = 0; u < UR; ++u) s[u] = (ci[u] >= 0) ? dv[u] * a.x[ci[u]] : 0.0;
+    for (int u = 0; u < UR; ++u) s[u] = (ci[u] >= 0) ? dv[u] * load_x(a.x, ci[u], a.gs) : 0.0;
 #pragma unroll
     for (int u = 0; u < UR; ++u)
-      for (IP j = lo[u] + sub + TPR; j < hi[u]; j += TPR) s[u] += data[j] * a.x[indices[j]];
+      for (IP j = lo[u] + sub + TPR; j < hi[u]; j += TPR) s[u] += data[j] * load_x(a.x, indices[j], a.gs);
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
 #pragma unroll
@@ -290,10 +301,10 @@ __global__ void __launch_bounds__(KB) kd_spmv(DSpmv a, CommDev c, Halo h, unsign
       for (int u = 0; u < UR; ++u) {
         if (row[u] < a.n) {
           double sv = s[u];
-          const double xv = a.x[row[u]];
+          const double xv = __ldg(a.x + row[u]);  // owned entry
           if (MODE == SPMV_MINRES) {
             if (shift != 0.0) sv -= shift * xv;
-            if (a.itn >= 2) sv -= coef * a.r1[row[u]];
+            if (a.itn >= 2) sv -= coef * __ldg(a.r1 + row[u]);
           }
           dot += xv * sv;
           a.y[row[u]] = sv;
@@ -861,7 +872,7 @@ extern "C" int pgb_dist_cg(void* comm, int64_t n_owned, int64_t ghost_start, int
   PGB_LAUNCH_CHECK();
 
   DSpmv a = {};
-  a.n = n; a.ia = interior_lo; a.ib = interior_hi;
+  a.n = n; a.ia = interior_lo; a.ib = interior_hi; a.gs = (int32_t)ghost_start;
   a.indptr = indptr; a.indices = indices; a.data = data;
   a.y = q; a.parts = cm->parts + S_PQ * NPART; a.done = done;
   int launched = 0;
@@ -953,7 +964,7 @@ extern "C" int pgb_dist_minres(void* comm, int64_t n_owned, int64_t ghost_start,
   double* spare = rb[2];
   double *w_new = wb[0], *w_old = wb[1];
   DSpmv a = {};
-  a.n = n; a.ia = interior_lo; a.ib = interior_hi;
+  a.n = n; a.ia = interior_lo; a.ib = interior_hi; a.gs = (int32_t)ghost_start;
   a.indptr = indptr; a.indices = indices; a.data = data;
   a.parts = cm->parts + M_ALFA * NPART; a.done = done;
   int itn = 0;

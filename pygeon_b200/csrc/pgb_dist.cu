@@ -53,6 +53,7 @@ struct Comm {
   int* flag_dev = nullptr;
   void* scal = nullptr;         // device scalars (CgScal / 2 x MinresScal)
   double* parts = nullptr;      // device, NRED * NPART partial sums
+  double* gsum = nullptr;       // device, 2 * NRED completed global sums
   double* resid = nullptr;
   int resid_cap = 0;
 };
@@ -60,6 +61,7 @@ struct Comm {
 struct CommDev {
   int rank, world;
   Header* hdr[MAXW];
+  double* gsum;  // [2][NRED] completed global sums (device local)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -99,74 +101,77 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsign
   }
 }
 
-// every thread of the block obtains sum over ranks of slot `k` for sequence number `seq`
-__device__ __forceinline__ double global_sum(const CommDev& c, int k, unsigned long long seq, double* sh /*[1]*/) {
-  Header* h = c.hdr[c.rank];
-  const int par = (int)(seq & 1ull);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int q = 0; q < c.world; ++q) {
-      wait_flag(&h->red_flag[par][k][q], seq, h);
-      s += ld_volatile_f64(&h->red_val[par][k][q]);
-    }
-    *sh = s;
-  }
-  __syncthreads();
-  return *sh;
+// The global value of slot `k` for sequence number `seq`: completed by the tail of the kernel that produced
+// the partial sums (all_reduce_tail below), i.e. by an EARLIER kernel of this stream - a plain load.
+__device__ __forceinline__ double global_sum(const CommDev& c, int k, unsigned long long seq, double* /*sh*/) {
+  return c.gsum[(int)(seq & 1ull) * NRED + k];
 }
 
-// after write_partial(parts, ...) by every block: the last block to arrive sums the partials in a fixed
-// order and publishes the value to all ranks.  ticket: device counter, left at 0.
-__device__ __forceinline__ void publish(const CommDev& c, int k, unsigned long long seq, const double* parts,
-                                        unsigned* ticket, double* ws /*[KB/32]*/, int* sh_last) {
+// After write_partial(parts, ...) by every block: the last block to arrive (integer ticket) sums the partials
+// in index order, stores the value into slot [rank] of EVERY rank and raises the slot's flag (lane q talks to
+// rank q), then waits for the `world` flags at home and adds the slots in rank order: every rank computes
+// the same bits.  The all-reduce is complete when the kernel ends; consumers are later kernels and never
+// spin (one poller per rank instead of one per block).  NV = 1 or 2 values reduced by one pass.
+template <int NV>
+__device__ __forceinline__ void all_reduce_tail(const CommDev& c, const int (&k)[NV], unsigned long long seq,
+                                                const double* const (&parts)[NV], unsigned* ticket,
+                                                double* ws /*[NV * KB/32]*/, int* sh_last) {
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) *sh_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
   __syncthreads();
   if (!*sh_last) return;
   __threadfence();
-  double s = 0;
-  for (int i = threadIdx.x; i < NPART; i += KB) s += ld_volatile_f64(parts + i);
-  s = block_sum(s, ws);
-  if (threadIdx.x == 0) {
-    *ticket = 0;
-    const int par = (int)(seq & 1ull);
-    for (int q = 0; q < c.world; ++q) c.hdr[q]->red_val[par][k][c.rank] = s;
-    __threadfence_system();
-    for (int q = 0; q < c.world; ++q) st_release_sys(&c.hdr[q]->red_flag[par][k][c.rank], seq);
-  }
-}
-
-// two values published by one pass (same ticket)
-__device__ __forceinline__ void publish2(const CommDev& c, int k0, int k1, unsigned long long seq, const double* parts0,
-                                         const double* parts1, unsigned* ticket, double* ws /*[2*KB/32]*/,
-                                         int* sh_last) {
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) *sh_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-  __syncthreads();
-  if (!*sh_last) return;
-  __threadfence();
-  double v[2] = {0.0, 0.0};
+  double v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = 0.0;
   for (int i = threadIdx.x; i < NPART; i += KB) {
-    v[0] += ld_volatile_f64(parts0 + i);
-    v[1] += ld_volatile_f64(parts1 + i);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] += ld_volatile_f64(parts[j] + i);
   }
-  block_sum_n<2>(v, ws);
-  if (threadIdx.x == 0) {
-    *ticket = 0;
-    const int par = (int)(seq & 1ull);
-    for (int q = 0; q < c.world; ++q) {
-      c.hdr[q]->red_val[par][k0][c.rank] = v[0];
-      c.hdr[q]->red_val[par][k1][c.rank] = v[1];
-    }
+  block_sum_n<NV>(v, ws);
+  if (threadIdx.x >= 32) return;
+  const int q = threadIdx.x;  // lane q <-> rank q
+  const int par = (int)(seq & 1ull);
+  if (q == 0) *ticket = 0;
+  if (q < c.world) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) c.hdr[q]->red_val[par][k[j]][c.rank] = v[j];
     __threadfence_system();
-    for (int q = 0; q < c.world; ++q) {
-      st_release_sys(&c.hdr[q]->red_flag[par][k0][c.rank], seq);
-      st_release_sys(&c.hdr[q]->red_flag[par][k1][c.rank], seq);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) st_release_sys(&c.hdr[q]->red_flag[par][k[j]][c.rank], seq);
+  }
+  Header* mine = c.hdr[c.rank];
+  double got[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    got[j] = 0.0;
+    if (q < c.world) {
+      wait_flag(&mine->red_flag[par][k[j]][q], seq, mine);
+      got[j] = ld_volatile_f64(&mine->red_val[par][k[j]][q]);
     }
   }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    double tot = 0.0;
+    for (int r = 0; r < c.world; ++r) tot += __shfl_sync(FULL, got[j], r);  // rank order: identical on all ranks
+    if (q == 0) c.gsum[par * NRED + k[j]] = tot;
+  }
+}
+
+__device__ __forceinline__ void publish(const CommDev& c, int k, unsigned long long seq, const double* parts,
+                                        unsigned* ticket, double* ws, int* sh_last) {
+  const int ks[1] = {k};
+  const double* const ps[1] = {parts};
+  all_reduce_tail<1>(c, ks, seq, ps, ticket, ws, sh_last);
+}
+
+__device__ __forceinline__ void publish2(const CommDev& c, int k0, int k1, unsigned long long seq, const double* parts0,
+                                         const double* parts1, unsigned* ticket, double* ws, int* sh_last) {
+  const int ks[2] = {k0, k1};
+  const double* const ps[2] = {parts0, parts1};
+  all_reduce_tail<2>(c, ks, seq, ps, ticket, ws, sh_last);
 }
 
 // ---- halo description (device side) ------------------------------------------------------------------
@@ -667,6 +672,7 @@ __global__ void kd_mr_final(int itn, const MinresScal* sc_old, MinresScal* sc_ou
 int comm_dev(const Comm* cm, CommDev* out) {
   out->rank = cm->rank;
   out->world = cm->world;
+  out->gsum = cm->gsum;
   for (int q = 0; q < MAXW; ++q) out->hdr[q] = q < cm->world ? (Header*)cm->peer[q] : nullptr;
   return 0;
 }
@@ -754,6 +760,8 @@ extern "C" int pgb_comm_create(int rank, int world, int64_t arena_bytes, void** 
   PGB_CHECK(cudaMalloc(&cm->scal, 4096));
   PGB_CHECK(cudaMalloc((void**)&cm->parts, sizeof(double) * NRED * NPART));
   PGB_CHECK(cudaMemset(cm->parts, 0, sizeof(double) * NRED * NPART));
+  PGB_CHECK(cudaMalloc((void**)&cm->gsum, sizeof(double) * 2 * NRED));
+  PGB_CHECK(cudaMemset(cm->gsum, 0, sizeof(double) * 2 * NRED));
   cm->peer[rank] = cm->base;
   if (world > 1) PGB_CHECK(cudaIpcGetMemHandle(&cm->handle, cm->base));
   PGB_CHECK(cudaDeviceSynchronize());
@@ -797,6 +805,7 @@ extern "C" int pgb_comm_destroy(void* comm) {
   cudaFree(cm->tickets);
   cudaFree(cm->scal);
   cudaFree(cm->parts);
+  cudaFree(cm->gsum);
   if (cm->resid) cudaFree(cm->resid);
   cudaFreeHost(cm->flag_host);
   delete cm;

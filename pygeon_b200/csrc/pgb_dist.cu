@@ -233,15 +233,13 @@ struct DSpmv {
   int itn;
 };
 
-// Owned entries of x were written by an earlier kernel: read-only here, so they take the non-coherent path
-// like the single-GPU SpMV (measured: plain loads cost the kernel 10-20 %).  Ghost entries are stored by
-// the peers WHILE this kernel runs (before the flag this block waited for): coherent L2 loads.
-__device__ __forceinline__ double load_x(const double* x, int32_t c, int32_t gs) {
-  if (c < gs) return __ldg(x + c);
-  double v;
-  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(x + c) : "memory");
-  return v;
-}
+// x is read through the non-coherent path like the single-GPU SpMV (plain loads cost the kernel 10-20 %, a
+// per-element choice between the two paths 30 %: measured).  Owned entries were written by an earlier kernel.
+// Ghost entries are stored by the peers while this kernel runs, but always before the flag the block waits
+// for (halo_wait ends with a block barrier, which loads are not moved across), they are read only after
+// that wait, and no 128-byte line mixes owned and ghost entries (ghost_start is a multiple of 16), so a
+// line holding ghosts is first fetched when its data is final.
+__device__ __forceinline__ double load_x(const double* x, int32_t c) { return __ldg(x + c); }
 
 template <int TPR, typename IP, int MODE>
 __global__ void __launch_bounds__(KB) kd_spmv(DSpmv a, CommDev c, Halo h, unsigned long long halo_seq, int red_slot,
@@ -261,23 +259,26 @@ __global__ void __launch_bounds__(KB) kd_spmv(DSpmv a, CommDev c, Halo h, unsign
     shift = a.mr->shift;
     coef = (a.itn >= 2) ? a.mr->beta / a.mr->oldb : 0.0;
   }
-  const int64_t nint = a.ib - a.ia;
+  // rows are int32 ids; all row arithmetic in 32 bits (the kernel is close to issue bound at 2 lanes per row)
+  const uint32_t n32 = (uint32_t)a.n, ia = (uint32_t)a.ia, ib = (uint32_t)a.ib, nint = ib - ia;
   double dot = 0.0;
   bool waited = (h.nrecv == 0);
-  const int64_t ntiles = (a.n + RPB - 1) / RPB;
-  for (int64_t t = (int64_t)blockIdx.x * UR; t < ntiles; t += (int64_t)gridDim.x * UR) {
-    if (!waited && (t + UR) * RPB > nint) {  // this block reaches the interface rows
+  const uint32_t ntiles = (n32 + RPB - 1) / RPB;
+  for (uint32_t t = blockIdx.x * UR; t < ntiles; t += gridDim.x * UR) {
+    const bool inner = (t + UR) * RPB <= nint;  // block-uniform: the whole tile group lies in [ia, ib)
+    if (!waited && !inner) {                    // this block reaches the interface rows
       halo_wait(c, h, halo_seq);
       waited = true;
     }
-    int64_t row[UR];
+    uint32_t row[UR];
     IP lo[UR], hi[UR];
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
-      const int64_t v = (t + u) * RPB + grp;  // virtual row: interior first
-      const bool ok = v < a.n;
-      int64_t r = v < nint ? a.ia + v : (v - nint < a.ia ? v - nint : a.ib + (v - nint - a.ia));
-      row[u] = ok ? r : a.n;
+      const uint32_t v = (t + u) * RPB + grp;  // virtual row: interior first
+      const bool ok = v < n32;
+      uint32_t r = ia + v;
+      if (!inner) r = v < nint ? ia + v : (v - nint < ia ? v - nint : ib + (v - nint - ia));
+      row[u] = ok ? r : n32;
       lo[u] = ok ? ip[r] : (IP)0;
       hi[u] = ok ? ip[r + 1] : (IP)0;
     }
@@ -292,10 +293,10 @@ __global__ void __launch_bounds__(KB) kd_spmv(DSpmv a, CommDev c, Halo h, unsign
     }
     double s[UR];
 #pragma unroll
-    for (int u = 0; u < UR; ++u) s[u] = (ci[u] >= 0) ? dv[u] * load_x(a.x, ci[u], a.gs) : 0.0;
+    for (int u = 0; u < UR; ++u) s[u] = (ci[u] >= 0) ? dv[u] * load_x(a.x, ci[u]) : 0.0;
 #pragma unroll
     for (int u = 0; u < UR; ++u)
-      for (IP j = lo[u] + sub + TPR; j < hi[u]; j += TPR) s[u] += data[j] * load_x(a.x, indices[j], a.gs);
+      for (IP j = lo[u] + sub + TPR; j < hi[u]; j += TPR) s[u] += data[j] * load_x(a.x, indices[j]);
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
 #pragma unroll
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(KB) kd_spmv(DSpmv a, CommDev c, Halo h, unsign
     if (sub == 0) {
 #pragma unroll
       for (int u = 0; u < UR; ++u) {
-        if (row[u] < a.n) {
+        if (row[u] < n32) {
           double sv = s[u];
           const double xv = __ldg(a.x + row[u]);  // owned entry
           if (MODE == SPMV_MINRES) {

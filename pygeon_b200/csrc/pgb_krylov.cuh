@@ -134,14 +134,16 @@ __global__ void __launch_bounds__(KB) k_spmv(SpmvArgs a) {
     coef = (a.itn >= 2) ? a.mr->beta / a.mr->oldb : 0.0;
   }
   double dot = 0.0;
-  const int64_t ntiles = (a.n + RPB - 1) / RPB;
-  for (int64_t t = (int64_t)blockIdx.x * UR; t < ntiles; t += (int64_t)gridDim.x * UR) {
-    int64_t row[UR];
+  // row ids are int32: 32-bit row arithmetic (at 2-4 lanes per row the kernel is close to issue bound)
+  const uint32_t n32 = (uint32_t)a.n;
+  const uint32_t ntiles = (n32 + RPB - 1) / RPB;
+  for (uint32_t t = blockIdx.x * UR; t < ntiles; t += gridDim.x * UR) {
+    uint32_t row[UR];
     IP lo[UR], hi[UR];
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
       row[u] = (t + u) * RPB + grp;
-      bool ok = row[u] < a.n;
+      bool ok = row[u] < n32;
       lo[u] = ok ? ip[row[u]] : (IP)0;
       hi[u] = ok ? ip[row[u] + 1] : (IP)0;
     }
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(KB) k_spmv(SpmvArgs a) {
     if (sub == 0) {
 #pragma unroll
       for (int u = 0; u < UR; ++u) {
-        if (row[u] < a.n) {
+        if (row[u] < n32) {
           double sv = s[u];
           if (MODE == SPMV_MINRES) {
             double xv = a.x[row[u]];

@@ -907,11 +907,14 @@ template <int L, int BLK, typename IP, bool STAGED>
 int launch_numeric_t_b(int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots, const void* indptr,
                        const double* vals_t, double* data, cudaStream_t s) {
   size_t smem = (STAGED ? 2 : 1) * (size_t)caps * BLK * sizeof(double);  // accumulators (+ output staging)
-  static size_t attr = 48 * 1024;
-  if (smem > attr) {
+  static size_t attr[64];  // per device: function attributes belong to the device's context
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = (dev >= 0 && dev < 64) ? dev : 0;
+  if (smem > 48 * 1024 && smem > attr[dev]) {
     PGB_CHECK(cudaFuncSetAttribute(k_numeric_t<L, BLK, IP, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    attr = smem;
+    attr[dev] = smem;
   }
   k_numeric_t<L, BLK, IP, STAGED><<<(unsigned)pgb_cdiv(n_rows, BLK), BLK, smem, s>>>(
       n_rows, caps, row_start, slots, (const IP*)indptr, vals_t, data);

@@ -114,6 +114,33 @@ struct SpmvArgs {
   int itn;               // SPMV_MINRES: 1-based iteration
 };
 
+// Grid of a grid-stride kernel with KB threads per block: as many blocks as are resident at once
+// (occupancy x SMs: one wave, no tail of late blocks), at most NPART (one partial sum per block) and at
+// most `work_blocks`.  The occupancy of every kernel is looked up once.
+template <typename Kern>
+int resident_grid(Kern kernel, int64_t work_blocks) {
+  static std::mutex mu;
+  static std::map<const void*, int> cache;
+  int cap = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find((const void*)kernel);
+    if (it != cache.end()) cap = it->second;
+  }
+  if (!cap) {
+    int occ = 0, dev = 0, sms = PGB_SMS;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, KB, 0) != cudaSuccess || occ < 1) occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cap = occ * sms;
+    if (cap > NPART) cap = NPART;
+    std::lock_guard<std::mutex> lock(mu);
+    cache[(const void*)kernel] = cap;
+  }
+  int64_t g = work_blocks < cap ? work_blocks : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
 constexpr int SPMV_UR = 4;  // rows per sub-warp per outer iteration (loads of all rows issued together)
 
 template <int TPR, typename IP, int MODE>
@@ -193,19 +220,8 @@ __global__ void __launch_bounds__(KB) k_spmv(SpmvArgs a) {
 
 template <int TPR, typename IP, int MODE>
 int launch_spmv_t(const SpmvArgs& a, cudaStream_t s) {
-  static int grid = 0;
-  if (!grid) {
-    int occ = 0;
-    PGB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv<TPR, IP, MODE>, KB, 0));
-    int dev = 0, sms = PGB_SMS;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    grid = occ * sms;
-    if (grid > NPART) grid = NPART;
-    if (grid < 1) grid = 1;
-  }
   int64_t ntiles = ((a.n + (KB / TPR) - 1) / (KB / TPR) + SPMV_UR - 1) / SPMV_UR;
-  int g = (int)(ntiles < grid ? (ntiles < 1 ? 1 : ntiles) : grid);
+  int g = resident_grid(k_spmv<TPR, IP, MODE>, ntiles);  // one resident wave (all B200s of a node are alike)
   k_spmv<TPR, IP, MODE><<<g, KB, 0, s>>>(a);
   PGB_LAUNCH_CHECK();
   return 0;
@@ -242,33 +258,6 @@ int vec_grid(int64_t n) {
   if (g > NPART) g = NPART;
   if (g < 1) g = 1;
   return (int)g;
-}
-
-// Grid of a grid-stride kernel with KB threads per block: as many blocks as are resident at once
-// (occupancy x SMs: one wave, no tail of late blocks), at most NPART (one partial sum per block) and at
-// most `work_blocks`.  The occupancy of every kernel is looked up once.
-template <typename Kern>
-int resident_grid(Kern kernel, int64_t work_blocks) {
-  static std::mutex mu;
-  static std::map<const void*, int> cache;
-  int cap = 0;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    auto it = cache.find((const void*)kernel);
-    if (it != cache.end()) cap = it->second;
-  }
-  if (!cap) {
-    int occ = 0, dev = 0, sms = PGB_SMS;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, KB, 0) != cudaSuccess || occ < 1) occ = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cap = occ * sms;
-    if (cap > NPART) cap = NPART;
-    std::lock_guard<std::mutex> lock(mu);
-    cache[(const void*)kernel] = cap;
-  }
-  int64_t g = work_blocks < cap ? work_blocks : cap;
-  return (int)(g < 1 ? 1 : g);
 }
 
 __device__ inline void mr_tests(MinresScal* sc, double ynorm) {

@@ -190,6 +190,7 @@ struct Halo {
 template <typename F>
 __device__ __forceinline__ void halo_push(const CommDev& c, const Halo& h, int which, unsigned long long seq, F f,
                                           int* sh_last) {
+  if (h.nsend == 0) return;  // block-uniform: nothing to send (one rank, or an isolated partition)
   for (int s = 0; s < h.nsend; ++s) {
     const int q = h.send_peer[s];
     double* dst = (double*)((char*)c.hdr[q] + HEADER_BYTES + h.vec_off[which]) + h.send_dst[s];

@@ -276,6 +276,13 @@ int pgb_csr_extract_symbolic(int64_t n_out, const int32_t* rows, const void* ind
 int pgb_csr_extract_fill(int64_t n_out, const int32_t* rows, const void* indptr, int idx64,
                          const int32_t* indices, const double* data, const int32_t* col_map,
                          const int64_t* out_indptr, int32_t* out_indices, double* out_data, void* stream);
+/* flags[col] = 1 for every column referenced by the rows `rows` (NULL: all n_out rows): which local dofs the
+ * owned rows of a partition read (ghost detection).  touches[r] = 1 when row r has a column >= first_col:
+ * the interface rows that have to wait for the halo (the others are multiplied while it is in flight). */
+int pgb_csr_mark_columns(int64_t n_out, const int32_t* rows, const void* indptr, int idx64, const int32_t* indices,
+                         uint8_t* flags, void* stream);
+int pgb_csr_rows_touching(int64_t n, const void* indptr, int idx64, const int32_t* indices, int32_t first_col,
+                          uint8_t* touches, void* stream);
 /* diag[r] = A[r][r] (0 when the row has no diagonal entry). */
 int pgb_csr_diagonal(int64_t n, const void* indptr, int idx64, const int32_t* indices, const double* data,
                      double* diag, void* stream);

@@ -52,6 +52,8 @@ _SIGS = {
     "pgb_mask_to_map": (_i, [_l, _p, _p, _p, C.POINTER(C.c_int64), _p, _l, _p]),
     "pgb_csr_extract_symbolic": (_i, [_l, _p, _p, _i, _p, _p, _p, C.POINTER(C.c_int64), _p, _l, _p]),
     "pgb_csr_extract_fill": (_i, [_l, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "pgb_csr_mark_columns": (_i, [_l, _p, _p, _i, _p, _p, _p]),
+    "pgb_csr_rows_touching": (_i, [_l, _p, _i, _p, _i, _p, _p]),
     "pgb_csr_diagonal": (_i, [_l, _p, _i, _p, _p, _p, _p]),
     "pgb_darcy_block_jacobi": (_i, [_l, _l, _p, _i, _p, _p, _p, _p, _p]),
     "pgb_gather": (_i, [_l, _p, _p, _p, _d, _p, _p]),

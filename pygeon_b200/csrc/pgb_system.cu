@@ -247,6 +247,39 @@ __global__ void __launch_bounds__(SB) k_darcy_jacobi(int64_t n, int64_t nf, cons
   }
 }
 
+// flags[col] = 1 for every column referenced by the selected rows (rows == nullptr: all rows)
+template <typename IP>
+__global__ void __launch_bounds__(SB) k_mark_columns(int64_t n_out, const int32_t* __restrict__ rows,
+                                                     const IP* __restrict__ ip, const int32_t* __restrict__ indices,
+                                                     uint8_t* __restrict__ flags) {
+  const int sub = threadIdx.x % XT;
+  const int64_t gid = ((int64_t)blockIdx.x * SB + threadIdx.x) / XT;
+  const int64_t nsub = (int64_t)gridDim.x * (SB / XT);
+  for (int64_t i = gid; i < n_out; i += nsub) {
+    const int64_t r = rows ? rows[i] : i;
+    const IP lo = ip[r], hi = ip[r + 1];
+    for (IP j = lo + sub; j < hi; j += XT) flags[indices[j]] = 1;  // same value from every writer
+  }
+}
+
+// touches[r] = 1 when row r has an entry with column >= first
+template <typename IP>
+__global__ void __launch_bounds__(SB) k_rows_touching(int64_t n, const IP* __restrict__ ip,
+                                                      const int32_t* __restrict__ indices, int32_t first,
+                                                      uint8_t* __restrict__ touches) {
+  const int sub = threadIdx.x % XT;
+  const int64_t gid = ((int64_t)blockIdx.x * SB + threadIdx.x) / XT;
+  const int64_t nsub = (int64_t)gridDim.x * (SB / XT);
+  for (int64_t r = gid; r < n; r += nsub) {
+    const IP lo = ip[r], hi = ip[r + 1];
+    int hit = 0;
+    for (IP j = lo + sub; j < hi; j += XT) hit |= indices[j] >= first ? 1 : 0;
+#pragma unroll
+    for (int d = XT / 2; d > 0; d >>= 1) hit |= __shfl_xor_sync(FULL, hit, d);
+    if (sub == 0) touches[r] = (uint8_t)hit;
+  }
+}
+
 __global__ void __launch_bounds__(SB) k_gather(int64_t n, const int32_t* __restrict__ idx,
                                                const double* __restrict__ x, const double* __restrict__ y, double a,
                                                double* __restrict__ out) {
@@ -378,6 +411,28 @@ extern "C" int pgb_gather(int64_t n, const int32_t* idx, const double* x, const 
 extern "C" int pgb_scatter_add(int64_t n, const int32_t* idx, const double* src, double* dst, void* stream) {
   if (n == 0) return 0;
   k_scatter_add<<<grid_for(n, SB), SB, 0, (cudaStream_t)stream>>>(n, idx, src, dst);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_csr_mark_columns(int64_t n_out, const int32_t* rows, const void* indptr, int idx64,
+                                    const int32_t* indices, uint8_t* flags, void* stream) {
+  if (n_out == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned g = grid_for(n_out, SB / XT);
+  if (idx64) k_mark_columns<int64_t><<<g, SB, 0, s>>>(n_out, rows, (const int64_t*)indptr, indices, flags);
+  else k_mark_columns<int32_t><<<g, SB, 0, s>>>(n_out, rows, (const int32_t*)indptr, indices, flags);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_csr_rows_touching(int64_t n, const void* indptr, int idx64, const int32_t* indices,
+                                     int32_t first_col, uint8_t* touches, void* stream) {
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned g = grid_for(n, SB / XT);
+  if (idx64) k_rows_touching<int64_t><<<g, SB, 0, s>>>(n, (const int64_t*)indptr, indices, first_col, touches);
+  else k_rows_touching<int32_t><<<g, SB, 0, s>>>(n, (const int32_t*)indptr, indices, first_col, touches);
   PGB_LAUNCH_CHECK();
   return 0;
 }

@@ -342,11 +342,14 @@ def build_dist_csr(indptr, indices, data, owned: torch.Tensor, keys: torch.Tenso
         _, own32 = engine.mask_to_map(owned, want_newid=False)
         own = own32.long()
         n_owned = int(own.numel())
-        # referenced columns of the owned rows: one pass with the identity map, then a flag scatter
-        ip0, cols0, _ = engine.extract_rows(indptr, indices, data, own32, None)
+        # referenced columns of the owned rows: one marking pass over those rows (no per-entry temporary)
+        from ._lib import check, lib
+
         ref = torch.zeros(n_local, dtype=torch.bool, device=dev)
-        ref[cols0.long()] = True
-        del ip0, cols0
+        with torch.cuda.device(dev):
+            check(lib.pgb_csr_mark_columns(n_owned, own32.data_ptr(), indptr.data_ptr(),
+                                           1 if indptr.dtype == torch.int64 else 0, indices.data_ptr(),
+                                           ref.data_ptr(), torch.cuda.current_stream().cuda_stream))
     else:
         own = torch.nonzero(owned).flatten()
         n_owned = int(own.numel())
@@ -441,15 +444,24 @@ def interior_range(A: DistCSR) -> tuple[int, int]:
     planes shared with the lower / upper neighbour), so ``[a, b)`` holds nearly all rows: an SpMV over
     it needs no halo data and can run while ``halo_exchange`` is in flight; the two interface ranges
     ``[0, a)`` and ``[b, n_owned)`` follow.  (Pointer offsets are enough for a row-range SpMV: indptr
-    holds absolute positions.)  Not used by :func:`dist_spmv` yet, see DESIGN.md section 8."""
+    holds absolute positions.)  The peer-memory SpMV (``kd_spmv``) multiplies ``[a, b)`` while the halo is in flight."""
     n = A.n_owned
     if n == 0:
         return 0, 0
-    ip = A.indptr.to(torch.int64)
-    lens = ip[1:] - ip[:-1]
-    row_of = torch.repeat_interleave(torch.arange(n, device=ip.device), lens)
-    touches = torch.zeros(n, dtype=torch.bool, device=ip.device)
-    touches[row_of[A.indices.to(torch.int64) >= A.ghost_start]] = True
+    ip = A.indptr
+    if ip.device.type == "cuda":  # one pass over the rows (pgb_csr_rows_touching), O(rows) scratch
+        from ._lib import check, lib
+
+        touches = torch.zeros(n, dtype=torch.bool, device=ip.device)
+        with torch.cuda.device(ip.device):
+            check(lib.pgb_csr_rows_touching(n, ip.data_ptr(), 1 if ip.dtype == torch.int64 else 0, A.indices.data_ptr(),
+                                            A.ghost_start, touches.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    else:
+        ip = ip.to(torch.int64)
+        lens = ip[1:] - ip[:-1]
+        row_of = torch.repeat_interleave(torch.arange(n, device=ip.device), lens)
+        touches = torch.zeros(n, dtype=torch.bool, device=ip.device)
+        touches[row_of[A.indices.to(torch.int64) >= A.ghost_start]] = True
     if not bool(touches.any()):
         return 0, n
     # run lengths of the ghost-free rows: boundaries at the interface rows

@@ -778,7 +778,8 @@ def main():
                          "scaling, 4 = Nedelec0 curl-curl + mass 192^3 strong scaling + CG; default 2 at --gpus 1, 3 otherwise")
     ap.add_argument("--ncube", dest="n", type=int, default=128, help="config 2: cubes per side (per GPU)")
     ap.add_argument("--ncube3", dest="n3", type=int, default=256, help="config 3: cubes per side of the whole box")
-    ap.add_argument("--cpu-n", type=int, default=64, help="cubes per side of the CPU-arm sample")
+    ap.add_argument("--cpu-n", type=int, default=0,
+                    help="cubes per side of the CPU-arm sample (default 64 for config 2, 48 for the heavier 3 / 4)")
     ap.add_argument("--cg-iters", type=int, default=300)
     ap.add_argument("--ncube4", dest="n4", type=int, default=192, help="config 4: cubes per side of the whole box")
     ap.add_argument("--solve-iters", "--minres-iters", dest="solve_iters", type=int, default=50)
@@ -789,6 +790,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     if args.config == 0:
         args.config = 2 if max(world, args.gpus) == 1 else 3
+    if not args.cpu_n:
+        args.cpu_n = 64 if args.config == 2 else 48
     if args.impl == "reference":
         run_reference(args)
     else:

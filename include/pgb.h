@@ -15,6 +15,10 @@
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*)
  *     unless stated otherwise; return value 0 = ok, non-zero = error with
  *     pgb_last_error() describing it (thread-local);
+ *   - threading: one host thread per device (the model is one process per GPU).  Scratch of the Krylov drivers
+ *     and function-attribute caches are kept per (thread, device); the symbolic phase keeps the row ranges of
+ *     the last pgb_csr_symbolic_sort call in process-wide state (symbolic_finish must follow on the same
+ *     thread), so concurrent symbolic calls from several host threads are not supported;
  *   - ids are int32, values fp64, COO positions uint32 (n_coo < 2^32).
  *   - "slot a" of a cell is the a-th entry of its cell_faces column; local node a
  *     is the node opposite face slot a.

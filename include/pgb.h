@@ -169,10 +169,13 @@ enum {
                            P2 local mass M2 and the nodal values Psi of the basis (hdiv.py:676-744), evaluated as a
                            constant contraction of the Gram matrix of the cell's edge vectors (pgb_rt1_table.cuh);
                            pg.WEIGHT is not read; aux_bits from pgb_pack_rt1            L = d(d+2) */
-  PGB_RT1_DIVDIV = 17   /* RT1 stiffness (discretization.py:154-183 with the divergence of hdiv.py:813-865 into
+  PGB_RT1_DIVDIV = 17,  /* RT1 stiffness (discretization.py:154-183 with the divergence of hdiv.py:813-865 into
                            PwLinears and its mass, l2.py:63-86,457-470): w / (d^2 |c|) s_p s_q (Dv^T Mhat Dv)_pq with
                            the constant nodal values Dv of the local divergences; aux_bits from pgb_pack_rt1
                                                                                         L = d(d+2) */
+  PGB_RT1_LUMPED_CELL = 18 /* cell block of RT1.assemble_lumped_matrix (hdiv.py:970-1028): |c| (d+1)/(d+2) P^T K P with
+                           the cell functions at the cell centre P_i = (sum_j x_j - (d+1) x_i) / ((d+1)^2 d |c|);
+                           dofs (k, c) -> k * nc + c; aux_bits from pgb_pack_rt1                 L = d */
 };
 int pgb_local_size(int kind, int dim); /* L */
 /* dst_pos (nullable): [nc*L] destination row of every local row (the inc_pos of a mode-0 plan);

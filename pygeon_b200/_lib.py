@@ -118,6 +118,7 @@ KIND = {
     "l2_stiff": 15,
     "rt1_mass": 16,
     "rt1_divdiv": 17,
+    "rt1_lumped_cell": 18,
 }
 NPART = 1184
 

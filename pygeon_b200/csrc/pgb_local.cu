@@ -245,6 +245,7 @@ struct LocalSize {
                            : (KIND == PGB_DARCY_SADDLE)                       ? D + 2
                            : (KIND == PGB_L2_MASS || KIND == PGB_L2_STIFF)    ? (D + 1) + D * (D + 1) / 2
                            : (KIND == PGB_RT1_MASS || KIND == PGB_RT1_DIVDIV) ? D * (D + 2)
+                           : (KIND == PGB_RT1_LUMPED_CELL)                    ? D
                                                                               : D + 1;
 };
 
@@ -508,6 +509,35 @@ __global__ void __launch_bounds__(BLOCK) k_local(Params p) {
           emit(pp * L + qq, negq ? -(sp * v) : sp * v);
         }
       }
+    } else if constexpr (KIND == PGB_RT1_LUMPED_CELL) {
+      // cell block of the lumped RT1 mass (hdiv.py:970-1028): the d cell functions at the cell centre are
+      // P_i = (sum_j x_j - (d+1) x_i) / ((d+1)^2 d |c|), nodes in rank order; block = |c| (d+1)/(d+2) P^T K P
+      constexpr int N = D + 1;
+      const unsigned bits = p.aux_bits[c];
+      double S[D], P[D][D], KP[D][D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        S[i] = 0.0;
+#pragma unroll
+        for (int a = 0; a < N; ++a) S[i] += g.X[a][i];
+      }
+      const double sc = 1.0 / ((D + 1) * (D + 1) * D * g.vol);
+#pragma unroll
+      for (int r = 0; r < D; ++r) {
+        const unsigned slot = (bits >> (2 * r)) & 3u;
+#pragma unroll
+        for (int a = 0; a < N; ++a)
+          if (slot == (unsigned)a) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) P[r][i] = (S[i] - (D + 1) * g.X[a][i]) * sc;
+          }
+      }
+      apply_tensor<D, D, HAS_K>(Kr, P, KP);
+      const double f = g.vol * (D + 1) / (D + 2);
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) emit(i * L + j, f * dotd<D>(KP[i], P[j]));
     } else if constexpr (KIND == PGB_RT1_DIVDIV) {
       // RT1 stiffness B^T M_P1 B (hdiv.py:813-865 + l2.py:63-86,457-470): the nodal values of the
       // divergence of local function q are s_q Dv[r][q] / (d |c|) with the constant table
@@ -683,6 +713,7 @@ int dispatch(int kind, const Params& p, cudaStream_t s) {
     case PGB_L2_STIFF: return launch<PGB_L2_STIFF, D>(p, s);
     case PGB_RT1_MASS: return launch<PGB_RT1_MASS, D>(p, s);
     case PGB_RT1_DIVDIV: return launch<PGB_RT1_DIVDIV, D>(p, s);
+    case PGB_RT1_LUMPED_CELL: return launch<PGB_RT1_LUMPED_CELL, D>(p, s);
   }
   pgb_set_error("pgb_local_matrices: unknown kind %d", kind);
   return 2;
@@ -703,6 +734,7 @@ extern "C" int pgb_local_size(int kind, int dim) {
     case PGB_L2_STIFF: return (dim + 1) + dim * (dim + 1) / 2;
     case PGB_RT1_MASS:
     case PGB_RT1_DIVDIV: return dim * (dim + 2);
+    case PGB_RT1_LUMPED_CELL: return dim;
     default: return dim + 1;
   }
 }
@@ -717,7 +749,7 @@ extern "C" int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* 
       kind == PGB_RT0_DIVDIV || kind == PGB_BDM1_DIVDIV || kind == PGB_DARCY_SADDLE || kind == PGB_BDM1_LUMPED)
     PGB_REQUIRE(sign_bits, "pgb_local_matrices: sign_bits required");
   if (kind == PGB_BDM1_MASS || kind == PGB_BDM1_LUMPED || kind == PGB_N0_MASS ||
-      (kind == PGB_N0_CURLCURL && dim == 3) || kind == PGB_RT1_MASS || kind == PGB_RT1_DIVDIV)
+      (kind == PGB_N0_CURLCURL && dim == 3) || kind == PGB_RT1_MASS || kind == PGB_RT1_DIVDIV || kind == PGB_RT1_LUMPED_CELL)
     PGB_REQUIRE(aux_bits, "pgb_local_matrices: aux_bits required");
   if (nc == 0) return 0;
   Params p;

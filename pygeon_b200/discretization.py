@@ -543,17 +543,13 @@ class RT1(Discretization):
         return np.transpose(basis, (1, 0, 2)) / (d * sd.cell_volumes)[:, None, None]
 
     def assemble_lumped_matrix(self, sd, data: dict | None = None) -> sps.csc_array:
-        d, nc = sd.dim, sd.num_cells
+        """Egger & Radu lumping (``fem/hdiv.py:970-1028``): the BDM1 lumped block / (d+2) on the face dofs and
+        ``|c| (d+1)/(d+2) P^T K P`` on the d cell dofs of every cell - both through K1/K2 (kinds
+        ``PGB_BDM1_LUMPED`` and ``PGB_RT1_LUMPED_CELL``)."""
+        d = sd.dim
         bdm1_lumped = BDM1(self.keyword).assemble_lumped_matrix(sd, data) / (d + 2)
         _, K = self._coefficients(sd, data)
-        Kv = np.broadcast_to(np.eye(3)[:, :, None], (3, 3, nc)) if K is None else K
-        nodes_loc, _, _ = self._rank_tables(sd)
-        P = self._basis_at_center(sd, nodes_loc)  # (nc, 3, d)
-        A = np.einsum("cxi,xyc,cyj->cij", P, Kv, P) * (sd.cell_volumes * (d + 1) / (d + 2))[:, None, None]
-        loc = nc * np.arange(d)[None, :] + np.arange(nc)[:, None]
-        rows = np.broadcast_to(loc[:, :, None], A.shape)
-        cols = np.broadcast_to(loc[:, None, :], A.shape)
-        cell_block = sps.csc_array((A.ravel(), (rows.ravel(), cols.ravel())), shape=(nc * d, nc * d))
+        cell_block = engine.assemble_host("rt1cell", "lumped", sd, None, K)
         return sps.csc_array(sps.block_diag((bdm1_lumped, cell_block)))
 
     # ---- vectors -----------------------------------------------------------------------------------

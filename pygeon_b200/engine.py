@@ -264,6 +264,7 @@ class GridPack:
     _rt1: tuple | None = None
     _darcy: object = None
     _pwl: object = None
+    _rt1cell: object = None
     _l2: object = None
     plans: dict = field(default_factory=dict)
 
@@ -402,6 +403,11 @@ class GridPack:
                     _lib.count(1)
                 self._l2 = out
             return self._l2, self.nn + self.ne
+        if space == "rt1cell":  # the d cell functions of RT1, numbered (k, c) -> k * nc + c inside their block
+            if self._rt1cell is None:
+                cells = torch.arange(self.nc, dtype=_I32, device=self.device)
+                self._rt1cell = (cells[:, None] + self.nc * torch.arange(d, dtype=_I32, device=self.device)[None, :]).contiguous()
+            return self._rt1cell, d * self.nc
         if space == "pwlinears":  # broken P1: dof (slot k, cell c) = k * num_cells + c (fem/l2.py:38-49)
             if self._pwl is None:
                 cells = torch.arange(self.nc, dtype=_I32, device=self.device)
@@ -649,6 +655,7 @@ _FORMS = {
     ("bdm1", "lumped"): "bdm1_lumped",
     ("rt1", "mass"): "rt1_mass",
     ("rt1", "stiff"): "rt1_divdiv",
+    ("rt1cell", "lumped"): "rt1_lumped_cell",
     ("pwlinears", "mass"): "l1_mass",
     ("pwlinears", "lumped"): "l1_lumped",
 }
@@ -668,7 +675,7 @@ def local_matrices(pack: GridPack, kind: str, w=None, K=None, out=None, plan: "C
         aux = pack.edges()[1]
     elif kind in ("bdm1_mass", "bdm1_lumped"):
         aux = pack.bdm1()[1]
-    elif kind in ("rt1_mass", "rt1_divdiv"):
+    elif kind in ("rt1_mass", "rt1_divdiv", "rt1_lumped_cell"):
         aux = pack.rt1()[1]
     with torch.cuda.device(dev):
         rowmajor = plan is not None and plan.mode == 0

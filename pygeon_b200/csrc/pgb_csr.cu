@@ -940,6 +940,7 @@ template <typename IP>
 int launch_numeric_t(int L, int64_t n_rows, int caps, bool staged, const uint32_t* row_start, const uint8_t* slots,
                      const void* indptr, const double* vals_t, double* data, cudaStream_t s) {
   switch (L) {
+    case 2: return launch_numeric_t_l<2, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
     case 3: return launch_numeric_t_l<3, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
     case 4: return launch_numeric_t_l<4, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);
     case 5: return launch_numeric_t_l<5, IP>(n_rows, caps, staged, row_start, slots, indptr, vals_t, data, s);

@@ -178,6 +178,7 @@ int launch_rowthread(uint32_t max_inc, int L, int64_t row0, int64_t row1, int64_
 #define PGB_RT(MI, LL, N) \
   if (L == LL && mi == MI)  \
     return launch_rowthread_k<MI, LL, N>(row0, row1, n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, s)
+  PGB_RT(1, 2, 8);  PGB_RT(2, 2, 8);  // d x d cell blocks in 2D
   PGB_RT(1, 3, 8);  PGB_RT(2, 3, 8);  PGB_RT(4, 3, 16); PGB_RT(8, 3, 32); PGB_RT(16, 3, 64);
   PGB_RT(1, 4, 8);  PGB_RT(2, 4, 8);  PGB_RT(4, 4, 16); PGB_RT(8, 4, 32); PGB_RT(16, 4, 64);
   PGB_RT(1, 5, 8);  PGB_RT(2, 5, 16); PGB_RT(4, 5, 32); PGB_RT(8, 5, 64);

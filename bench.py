@@ -596,6 +596,66 @@ STRONG = {
 }
 
 
+def single_gpu_base(args, cx: Ctx, cfg: int):
+    """The same workload on ONE GPU, measured live by rank 0 of a multi-GPU run before the distributed part (the
+    other ranks wait): the base of the strong-scaling series, so that every multi-GPU line carries its own
+    single-GPU reference.  A short version of run_strong's device part: 3 cold steps, 10 solver iterations."""
+    import pygeon_b200 as pg  # noqa: F401
+    from pygeon_b200 import engine
+    from pygeon_b200 import dist as pgd
+    from pygeon_b200.solvers import cg_device, minres_device
+
+    torch, dev = cx.torch, cx.dev
+    W = STRONG[cfg]
+    n = args.n3 if cfg == 3 else args.n4
+    out = None
+    try:
+        sd = pgd.local_slab_grid(pgd.slab_layout(n, n, 1, 0), device=dev)
+        raw = engine.RawGrid.upload(sd, dev, signs=True, ridges=W["ridges"])
+        raw.check = False
+
+        def step():
+            pack = engine.GridPack.from_raw(raw)
+            plan = engine.symbolic(pack, W["space"])
+            data = None
+            for kind in W["kinds"]:
+                d = engine.numeric(plan, engine.local_matrices(pack, kind, plan=plan))
+                data = d if data is None else data.add_(d)
+            return plan, data
+
+        for _ in range(2):
+            plan, data = step()
+            del plan, data
+        torch.cuda.synchronize()
+        e0, e1 = cx.ev(), cx.ev()
+        e0.record()
+        for _ in range(3):
+            plan, data = step()
+            if _ < 2:
+                del plan, data
+        e1.record()
+        torch.cuda.synchronize()
+        cold_ms = e0.elapsed_time(e1) / 3
+        A = engine.DeviceCSR((plan.n_rows, plan.n_rows), plan.indptr, plan.indices, data)
+        b = torch.randn(plan.n_rows, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+        solve = (lambda k: minres_device(A, b, rtol=0.0, maxiter=k)) if W["solver"] == "minres" else (
+            lambda k: cg_device(A, b, rtol=0.0, atol=0.0, maxiter=k))
+        solve(3)
+        torch.cuda.synchronize()
+        e0.record()
+        _, si = solve(10)
+        e1.record()
+        torch.cuda.synchronize()
+        out = {"n_gpus": 1, "measured": "live by rank 0 of this run, before the distributed part",
+               "cold_ms": cold_ms, "value": 6 * n ** 3 / (cold_ms * 1e-3), "unit": UNIT,
+               "solver_ms_per_iter": e0.elapsed_time(e1) / max(si.iterations, 1), "unknowns": plan.n_rows, "nnz": plan.nnz}
+        del A, b, plan, data, raw, sd
+    except Exception as e:  # e.g. out of memory on a smaller GPU: the series then has no live base
+        out = {"n_gpus": 1, "skipped": repr(e)[:200]}
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_strong(args, cx: Ctx, cfg: int):
     import pygeon_b200 as pg
     from pygeon_b200 import engine
@@ -608,6 +668,11 @@ def run_strong(args, cx: Ctx, cfg: int):
     space, kinds = W["space"], W["kinds"]
     n = args.n3 if cfg == 3 else args.n4
     dist_parity = pgd.self_check(6, 4 * world + 2)
+    base = None
+    if world > 1 and not args.no_base:
+        if rank == 0:
+            base = single_gpu_base(args, cx, cfg)
+        cx.barrier()
 
     lay = pgd.slab_layout(n, n, world, rank)
     sd = pgd.local_slab_grid(lay, device=dev)
@@ -744,6 +809,8 @@ def run_strong(args, cx: Ctx, cfg: int):
     conf = workload_config(cfg, n, world)
     conf["dist_parity"] = "ok" if dist_parity["ok"] else "FAILED"
     conf["unknowns"], conf["nnz"] = unknowns, nnz_total
+    if base is not None:
+        conf["single_gpu_base"] = base  # raw values only: ratios are the reader's to compute
     return {
         "metric": METRIC, "value": cells_total / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -784,6 +851,8 @@ def main():
     ap.add_argument("--ncube4", dest="n4", type=int, default=192, help="config 4: cubes per side of the whole box")
     ap.add_argument("--solve-iters", "--minres-iters", dest="solve_iters", type=int, default=50)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-base", action="store_true",
+                    help="multi-GPU strong-scaling runs: skip the live single-GPU measurement of the same workload")
     ap.add_argument("--no-verify", dest="verify", action="store_false",
                     help="skip the full-CSR oracle comparison of config 2 (about one minute of host time)")
     args = ap.parse_args()

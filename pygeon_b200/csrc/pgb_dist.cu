@@ -243,7 +243,7 @@ struct DSpmv {
 __device__ __forceinline__ double load_x(const double* x, int32_t c) { return __ldg(x + c); }
 
 template <int TPR, typename IP, int MODE>
-__global__ void __launch_bounds__(KB) kd_spmv(DSpmv a, CommDev c, Halo h, unsigned long long halo_seq, int red_slot,
+__global__ void __launch_bounds__(KB, (sizeof(IP) == 4 && MODE == SPMV_MINRES) ? 6 : 0) kd_spmv(DSpmv a, CommDev c, Halo h, unsigned long long halo_seq, int red_slot,
                                               unsigned long long red_seq, unsigned* ticket) {
   __shared__ double ws[KB / 32];
   __shared__ int sh_last;

@@ -91,7 +91,7 @@ class MortarGrid:
         self.signed_mortar_to_primary = sps.csc_array(
             (sign, (self.face_up, m)), shape=(sd_up.num_faces, self.num_cells))
         self.cell_faces = sps.csc_array(-self.signed_mortar_to_primary @ self.secondary_to_mortar_int())
-        if self.dim >= 1:
+        if self.dim >= 2:
             self.compute_ridges()
 
     def compute_ridges(self) -> None:
@@ -101,6 +101,8 @@ class MortarGrid:
         their coordinates cell by cell, orientations from the mortar normal."""
         sd_up, sd_down = self.sd_pair
         d = self.dim
+        if d != 2:
+            raise NotImplementedError("only 3D-2D interfaces are supported (this package has no 1D grids)")
         nr_up, nf_down = sd_up.num_ridges, sd_down.num_faces
         rows_fr, cols_fr, vals_fr = [], [], []
         rows_rp, cols_rp, vals_rp = [], [], []
@@ -108,17 +110,12 @@ class MortarGrid:
         out_sign = np.asarray(cf_up.data)[cf_up.indptr[self.face_up]]
         normal_up = np.asarray(sd_up.face_normals)[:, self.face_up] * out_sign  # outward w.r.t. sd_up
         cfd, fru = sd_down.cell_faces, sd_up.face_ridges
-        nfc, nrf = d + 1, (2 if d == 1 else 3)
+        nfc, nrf = 3, 3
         faces_down = cfd.indices.reshape(sd_down.num_cells, nfc)[self.cell_down]  # (m, d+1)
         ridges_up = fru.indices.reshape(sd_up.num_faces, nrf)[self.face_up]  # (m, nrf)
-        if nfc != nrf:
-            raise NotImplementedError("only simplicial conforming interfaces are supported")
         fxyz = np.asarray(sd_down.face_centers)[:, faces_down]  # (3, m, k)
-        if d == 1:
-            rxyz = np.asarray(sd_up.nodes)[:, ridges_up]
-        else:
-            rp = sd_up.ridge_peaks.indices.reshape(sd_up.num_ridges, 2)
-            rxyz = np.asarray(sd_up.nodes)[:, rp[ridges_up]].mean(axis=3)
+        rp = sd_up.ridge_peaks.indices.reshape(sd_up.num_ridges, 2)
+        rxyz = np.asarray(sd_up.nodes)[:, rp[ridges_up]].mean(axis=3)
         # pair every low-dimensional face with the coinciding high-dimensional ridge
         dist = np.linalg.norm(fxyz[:, :, :, None] - rxyz[:, :, None, :], axis=0)  # (m, k, k)
         match = dist.argmin(axis=2)
@@ -126,27 +123,22 @@ class MortarGrid:
             raise ValueError("interface is not conforming: a face of the lower grid has no matching ridge")
         ridges_m = np.take_along_axis(ridges_up, match, axis=1)
         n_down = np.asarray(sd_down.face_normals)[:, faces_down]  # (3, m, k)
-        if d == 1:
-            R = np.asarray(sd_up.rotation_matrix)
-            rot = R.T @ np.array([[0.0, -1.0], [1.0, 0.0]]) @ R
-            orient = np.einsum("im,imk->mk", rot @ normal_up, n_down)
-        else:
-            tang = np.asarray(sd_up.edge_tangents)[:, ridges_m]  # (3, m, k)
-            prod = np.cross(tang, normal_up[:, :, None], axisa=0, axisb=0, axisc=0)
-            orient = np.einsum("imk,imk->mk", prod, n_down)
-            # ridge_peaks: nodes of the high-dimensional face matched to the cell's nodes below
-            Rd = np.asarray(sd_down.rotation_matrix)
-            normal_plane = np.cross(Rd[0], Rd[1])
-            cn = sd_down.cell_nodes().indices.reshape(sd_down.num_cells, 3)[self.cell_down]
-            fn = sd_up.face_nodes.indices.reshape(sd_up.num_faces, 3)[self.face_up]
-            pd = np.asarray(sd_down.nodes)[:, cn]
-            pu = np.asarray(sd_up.nodes)[:, fn]
-            dist2 = np.linalg.norm(pd[:, :, :, None] - pu[:, :, None, :], axis=0)
-            pm = np.take_along_axis(fn, dist2.argmin(axis=2), axis=1)
-            o_rp = -np.sign(normal_up.T @ normal_plane)  # (m,)
-            rows_rp.append(pm.ravel())
-            cols_rp.append(cn.ravel())
-            vals_rp.append(np.repeat(o_rp, 3))
+        tang = np.asarray(sd_up.edge_tangents)[:, ridges_m]  # (3, m, k)
+        prod = np.cross(tang, normal_up[:, :, None], axisa=0, axisb=0, axisc=0)
+        orient = np.einsum("imk,imk->mk", prod, n_down)
+        # ridge_peaks: nodes of the high-dimensional face matched to the cell's nodes below
+        Rd = np.asarray(sd_down.rotation_matrix)
+        normal_plane = np.cross(Rd[0], Rd[1])
+        cn = sd_down.cell_nodes().indices.reshape(sd_down.num_cells, 3)[self.cell_down]
+        fn = sd_up.face_nodes.indices.reshape(sd_up.num_faces, 3)[self.face_up]
+        pd = np.asarray(sd_down.nodes)[:, cn]
+        pu = np.asarray(sd_up.nodes)[:, fn]
+        dist2 = np.linalg.norm(pd[:, :, :, None] - pu[:, :, None, :], axis=0)
+        pm = np.take_along_axis(fn, dist2.argmin(axis=2), axis=1)
+        o_rp = -np.sign(normal_up.T @ normal_plane)  # (m,)
+        rows_rp.append(pm.ravel())
+        cols_rp.append(cn.ravel())
+        vals_rp.append(np.repeat(o_rp, 3))
         rows_fr.append(ridges_m.ravel())
         cols_fr.append(faces_down.ravel())
         vals_fr.append(np.sign(orient).ravel())

@@ -256,7 +256,9 @@ int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mode, int64_t
  * flags bits 2-5: G = 2, 4 or 8 lanes per CSR row (0 = one thread per row): lane j sums the local rows
  * j, j + G, ... of the row, the G partial sums of every column are then added in lane order; a warp-wide
  * load covers G consecutive local rows per row (coalesced), consecutive lanes store consecutive entries.
- * A fixed, reproducible summation order that differs from the one-thread-per-row order in the last bits. */
+ * A fixed, reproducible summation order that differs from the one-thread-per-row order in the last bits.
+ * flags bit 6: one thread per row with 2 instead of 4 local rows in flight and 75 % occupancy (A/B variant,
+ * measured slower). */
 int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, const uint32_t* row_start,
                          const uint8_t* slots, const void* indptr, int idx64, const double* vals_t,
                          double* data, int flags, void* stream);

@@ -599,11 +599,11 @@ __device__ __forceinline__ void load_slots(const uint8_t* __restrict__ p, uint32
 // away from the loads and the kernel gets 20 % slower, so the caller chooses (flags bit 0).
 // (Fetching the slot bytes of 4 local rows with one 16-byte load, rounds aligned to 16 bytes of the
 // slot array, was measured slower for every space.)
-template <int L, int BLK, typename IP, bool STAGED>
-__global__ void __launch_bounds__(BLK) k_numeric_t(int64_t n_rows, int caps, const uint32_t* __restrict__ row_start,
+template <int L, int BLK, typename IP, bool STAGED, int UV = 0>
+__global__ void __launch_bounds__(BLK, UV == 2 ? 1536 / BLK : 0) k_numeric_t(int64_t n_rows, int caps, const uint32_t* __restrict__ row_start,
                                                    const uint8_t* __restrict__ slots, const IP* __restrict__ indptr,
                                                    const double* __restrict__ vals_t, double* __restrict__ data) {
-  constexpr int U = (L <= 4) ? 4 : 2;  // local rows in flight per thread (8 measured slower)
+  constexpr int U = UV ? UV : ((L <= 4) ? 4 : 2);  // local rows in flight per thread (8 measured slower)
   constexpr int LP = (L + 3) & ~3;      // row pitch (values and slots)
   extern __shared__ double smem[];
   double* acc = smem;  // [slot][thread]
@@ -903,9 +903,19 @@ ChunkGrid chunk_grid(int64_t n) {
 }
 
 
+bool g_numeric_u2 = false;  // flags bit 6 of pgb_csr_numeric_rows: 2 local rows in flight, 75 % occupancy target
+
 template <int L, int BLK, typename IP, bool STAGED>
 int launch_numeric_t_b(int64_t n_rows, int caps, const uint32_t* row_start, const uint8_t* slots, const void* indptr,
                        const double* vals_t, double* data, cudaStream_t s) {
+  if constexpr (L == 4 && BLK == 128 && !STAGED) {
+    if (g_numeric_u2 && (size_t)caps * BLK * sizeof(double) <= 48 * 1024) {
+      k_numeric_t<L, BLK, IP, STAGED, 2><<<(unsigned)pgb_cdiv(n_rows, BLK), BLK, (size_t)caps * BLK * sizeof(double), s>>>(
+          n_rows, caps, row_start, slots, (const IP*)indptr, vals_t, data);
+      PGB_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   size_t smem = (STAGED ? 2 : 1) * (size_t)caps * BLK * sizeof(double);  // accumulators (+ output staging)
   static size_t attr[64];  // per device: function attributes belong to the device's context
   int dev = 0;
@@ -1316,6 +1326,7 @@ extern "C" int pgb_csr_numeric_rows(int64_t n_rows, int L, int max_row_nnz, cons
   cudaStream_t s = (cudaStream_t)stream;
   int caps = max_row_nnz < 1 ? 1 : max_row_nnz;
   const bool staged = (flags & 1) != 0;
+  g_numeric_u2 = (flags & 64) != 0;
   if (const int G = (flags >> 2) & 15) {  // G lanes per row, coalesced loads and stores (pgb_numeric_bulk.cu)
     int rc = pgb_numeric_group_launch(L, G, n_rows, caps, idx64, row_start, slots, indptr, vals_t, data, s);
     if (rc >= 0) return rc;

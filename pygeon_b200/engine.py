@@ -703,7 +703,7 @@ def numeric(plan: CsrPlan, vals: torch.Tensor, out=None) -> torch.Tensor:
         else:
             # coalesced output through shared memory when the matrix has about as many entries as
             # COO candidates (RT0, BDM1, N0, Darcy); not for P1 in 3D (6 candidates per entry)
-            staged = (1 if 3 * plan.nnz > plan.n_coo else 0) | (numeric_flags & 2)
+            staged = (1 if 3 * plan.nnz > plan.n_coo else 0) | (numeric_flags & (2 | 64))
             if numeric_flags & 4:  # G lanes per row from the average number of local rows per CSR row
                 avg = plan.n_coo / plan.L / max(plan.n_rows, 1)
                 staged |= (8 if avg >= 12 else 4 if avg >= 6 else 2 if avg >= 3 else 0) << 2

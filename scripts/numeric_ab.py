@@ -24,7 +24,7 @@ for space, kind in (("lagrange1", "l1_stiff"), ("rt0", "rt0_mass"), ("nedelec0",
     vals = engine.local_matrices(pack, kind, plan=plan)
     ref = None
     line = f"{space:10s} rows {plan.n_rows:>10d} nnz {plan.nnz:>11d}"
-    for flags in (0, 2, 4):
+    for flags in (0, 2, 4, 64):
         engine.numeric_flags = flags
         out = engine.numeric(plan, vals)
         torch.cuda.synchronize()

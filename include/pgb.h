@@ -292,6 +292,34 @@ int pgb_csr_mark_columns(int64_t n_out, const int32_t* rows, const void* indptr,
                          uint8_t* flags, void* stream);
 int pgb_csr_rows_touching(int64_t n, const void* indptr, int idx64, const int32_t* indices, int32_t first_col,
                           uint8_t* touches, void* stream);
+/* Block stacking in HBM: sps.block_array of CSR blocks (reference utils/bmat.py:9-99; the mixed-dimensional
+ * operators of numerics/innerproducts.py:162-232 and numerics/differentials.py:144-192; the saddle stack
+ * sps.block_array([[M, -B.T], [-B, None]]) of tutorials/fluid_flow/darcy.ipynb).  Per block row:
+ *   lens = 0;  pgb_csr_block_lengths for every block  ->  pgb_scan_i64 (exclusive, out[n] = total) = indptr;
+ *   cursor = copy of indptr;  pgb_csr_block_place for every block LEFT TO RIGHT (appends row r of the block,
+ *   columns shifted by col_offset, values times `scale`, at cursor[r] and advances the cursor).
+ * Scratch O(rows); the output rows are sorted when the blocks' rows are.  workspace of pgb_scan_i64:
+ * pgb_system_workspace_bytes(0) bytes. */
+int pgb_scan_i64(int64_t n, const int64_t* in, int64_t* out, int64_t* total_host, void* workspace,
+                 int64_t workspace_bytes, void* stream);
+int pgb_csr_block_lengths(int64_t n, const void* indptr, int idx64, int64_t* lens, void* stream);
+int pgb_csr_block_place(int64_t n, const void* indptr, int idx64, const int32_t* indices, const double* data,
+                        int32_t col_offset, double scale, int64_t* cursor, int32_t* out_indices, double* out_data,
+                        void* stream);
+/* data[(rows[i], rows[i])] += vals[i] for m DISTINCT rows (the mortar trace term S diag(1 / (|m| k_n)) S^T of
+ * the face mass matrix, innerproducts.py:210-227, which is diagonal on a conforming interface).  flag_dev: one
+ * int32 of device scratch.  Synchronises the stream; returns 1 when a listed row stores no diagonal entry. */
+int pgb_csr_add_diagonal(int64_t m, const int32_t* rows, const double* vals, const void* indptr, int idx64,
+                         const int32_t* indices, double* data, int32_t* flag_dev, void* stream);
+/* CSR arrays of the transpose (scipy's A.T.tocsr(): B -> B^T of the saddle blocks): stable radix sort of the
+ * column indices with the entry position as payload, so the entries of every output row are ordered by
+ * input row - deterministic, no atomics.  nnz < 2^32 - 4096, dimensions < 2^31; out_indptr has n_cols + 1
+ * entries of int32 (out_idx64 = 0) or int64.  Workspace: pgb_csr_transpose_workspace_bytes(nnz) (16 B / entry). */
+int64_t pgb_csr_transpose_workspace_bytes(int64_t nnz);
+int pgb_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const void* indptr, int idx64,
+                      const int32_t* indices, const double* data, void* out_indptr, int out_idx64,
+                      int32_t* out_indices, double* out_data, void* workspace, int64_t workspace_bytes,
+                      void* stream);
 /* diag[r] = A[r][r] (0 when the row has no diagonal entry). */
 int pgb_csr_diagonal(int64_t n, const void* indptr, int idx64, const int32_t* indices, const double* data,
                      double* diag, void* stream);

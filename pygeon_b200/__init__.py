@@ -50,8 +50,12 @@ def __getattr__(name):
         from . import device_system as _ds
 
         return getattr(_ds, name)
-    if name in ("DeviceCSR",):
+    if name in ("DeviceCSR", "device_bmat"):
         from . import engine as _e
 
         return getattr(_e, name)
+    if name in ("face_mass_device", "cell_div_device", "mdg_darcy_saddle_device"):
+        from . import md_system as _m
+
+        return getattr(_m, "darcy_saddle_device" if name == "mdg_darcy_saddle_device" else name)
     raise AttributeError(name)

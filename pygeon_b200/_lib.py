@@ -54,6 +54,12 @@ _SIGS = {
     "pgb_csr_extract_fill": (_i, [_l, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "pgb_csr_mark_columns": (_i, [_l, _p, _p, _i, _p, _p, _p]),
     "pgb_csr_rows_touching": (_i, [_l, _p, _i, _p, _i, _p, _p]),
+    "pgb_scan_i64": (_i, [_l, _p, _p, C.POINTER(C.c_int64), _p, _l, _p]),
+    "pgb_csr_block_lengths": (_i, [_l, _p, _i, _p, _p]),
+    "pgb_csr_block_place": (_i, [_l, _p, _i, _p, _p, _i, _d, _p, _p, _p, _p]),
+    "pgb_csr_add_diagonal": (_i, [_l, _p, _p, _p, _i, _p, _p, _p, _p]),
+    "pgb_csr_transpose_workspace_bytes": (_l, [_l]),
+    "pgb_csr_transpose": (_i, [_l, _l, _l, _p, _i, _p, _p, _p, _i, _p, _p, _p, _l, _p]),
     "pgb_csr_diagonal": (_i, [_l, _p, _i, _p, _p, _p, _p]),
     "pgb_darcy_block_jacobi": (_i, [_l, _l, _p, _i, _p, _p, _p, _p, _p]),
     "pgb_gather": (_i, [_l, _p, _p, _p, _d, _p, _p]),

@@ -1458,3 +1458,97 @@ extern "C" int pgb_ridges3d(int64_t nf, int64_t num_nodes, const int32_t* face_n
   *num_ridges_host = (int64_t)m[0];
   return 0;
 }
+
+// ---- CSR transpose (B -> B^T of the mixed-dimensional saddle blocks; scipy's .T.tocsr()) -------------------
+// A stable LSD radix sort of the column indices with the entry position as payload orders the entries by
+// (column, row): exactly the CSR arrays of the transpose, deterministic, no atomics.  Then the column
+// starts from the sorted keys and one pass that looks the row of every entry up in indptr.
+namespace {
+
+struct TrWs {
+  int64_t keys_a, keys_b, pay_a, pay_b, hist, parts, total;
+};
+TrWs transpose_ws(int64_t nnz) {
+  auto al = [](int64_t x) { return (x + 255) / 256 * 256; };
+  TrWs l = {};
+  int64_t o = 0;
+  l.parts = o;  o += al(2048 * 4);
+  l.hist = o;   o += al(pgb_cdiv(nnz > 0 ? nnz : 1, SORT_TILE) * RADIX * 4);
+  l.keys_a = o; o += al(nnz * 4);
+  l.keys_b = o; o += al(nnz * 4);
+  l.pay_a = o;  o += al(nnz * 4);
+  l.pay_b = o;  o += al(nnz * 4);
+  l.total = o;
+  return l;
+}
+
+template <typename IP>
+__global__ void __launch_bounds__(256) k_transpose_starts(const uint32_t* __restrict__ keys, uint32_t n, int64_t n_cols,
+                                                          IP* __restrict__ out_ip) {
+  uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k = keys[i];
+  uint32_t prev = (i == 0) ? 0xffffffffu : keys[i - 1];
+  if (k != prev)
+    for (uint32_t c = prev + 1u; c <= k; ++c) out_ip[c] = (IP)i;  // prev + 1 wraps to 0 for i == 0
+  if (i == n - 1)
+    for (int64_t c = (int64_t)k + 1; c <= n_cols; ++c) out_ip[c] = (IP)n;
+}
+
+template <typename IP>
+__global__ void __launch_bounds__(256) k_transpose_emit(uint32_t n, const uint32_t* __restrict__ perm,
+                                                        const IP* __restrict__ ip, int64_t n_rows,
+                                                        const double* __restrict__ data,
+                                                        int32_t* __restrict__ out_idx, double* __restrict__ out_val) {
+  uint32_t j = blockIdx.x * 256u + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t p = perm[j];
+  int64_t lo = 0, hi = n_rows;  // the last row r with ip[r] <= p (ip[n_rows] = n > p)
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)ip[mid] <= (int64_t)p) lo = mid;
+    else hi = mid;
+  }
+  out_idx[j] = (int32_t)lo;
+  out_val[j] = data[p];
+}
+
+}  // namespace
+
+extern "C" int64_t pgb_csr_transpose_workspace_bytes(int64_t nnz) { return transpose_ws(nnz).total; }
+
+extern "C" int pgb_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const void* indptr, int idx64,
+                                 const int32_t* indices, const double* data, void* out_indptr, int out_idx64,
+                                 int32_t* out_indices, double* out_data, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  PGB_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31) && n_cols >= 0 && n_cols < ((int64_t)1 << 31),
+              "pgb_csr_transpose: dimensions must be < 2^31");
+  PGB_REQUIRE(nnz >= 0 && nnz < ((int64_t)1 << 32) - SORT_TILE, "pgb_csr_transpose: nnz must be < 2^32");
+  if (nnz == 0) {
+    PGB_CHECK(cudaMemsetAsync(out_indptr, 0, (size_t)(n_cols + 1) * (out_idx64 ? 8 : 4), s));
+    return 0;
+  }
+  PGB_REQUIRE(out_idx64 || nnz < ((int64_t)1 << 31), "pgb_csr_transpose: int32 indptr cannot hold nnz");
+  TrWs l = transpose_ws(nnz);
+  PGB_REQUIRE(workspace_bytes >= l.total, "pgb_csr_transpose: workspace too small");
+  char* ws = (char*)workspace;
+  uint32_t* parts = (uint32_t*)(ws + l.parts);
+  uint32_t* hist = (uint32_t*)(ws + l.hist);
+  uint32_t* kbuf[2] = {(uint32_t*)(ws + l.keys_a), (uint32_t*)(ws + l.keys_b)};
+  uint32_t* pbuf[2] = {(uint32_t*)(ws + l.pay_a), (uint32_t*)(ws + l.pay_b)};
+  KeySrc<uint32_t> src{nullptr, indices, 1u, 1u, 0};  // first pass: key i = indices[i], payload i
+  if (radix_sort<uint32_t>(src, (uint32_t)nnz, bits_for(n_cols), kbuf, pbuf, hist, parts, s)) return 1;
+  const unsigned g = pgb_grid(nnz, 256);
+  if (out_idx64) k_transpose_starts<int64_t><<<g, 256, 0, s>>>(kbuf[0], (uint32_t)nnz, n_cols, (int64_t*)out_indptr);
+  else k_transpose_starts<int32_t><<<g, 256, 0, s>>>(kbuf[0], (uint32_t)nnz, n_cols, (int32_t*)out_indptr);
+  PGB_LAUNCH_CHECK();
+  if (idx64)
+    k_transpose_emit<int64_t><<<g, 256, 0, s>>>((uint32_t)nnz, pbuf[0], (const int64_t*)indptr, n_rows, data, out_indices,
+                                                 out_data);
+  else
+    k_transpose_emit<int32_t><<<g, 256, 0, s>>>((uint32_t)nnz, pbuf[0], (const int32_t*)indptr, n_rows, data, out_indices,
+                                                 out_data);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}

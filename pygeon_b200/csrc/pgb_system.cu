@@ -295,6 +295,55 @@ __global__ void __launch_bounds__(SB) k_scatter_add(int64_t n, const int32_t* __
     dst[idx[i]] += src[i];  // idx holds distinct positions
 }
 
+// ---- block stacking (sps.block_array of CSR blocks; utils/bmat.py, numerics/innerproducts.py:162-232) ------
+// Row r of a block row is the concatenation, left to right, of row r of its blocks with the columns shifted
+// by the block column's offset: sorted as long as every block row is.  Count: lens[r] += length of row r;
+// fill: one launch per block in left-to-right order, every row appended at its cursor; the cursors advance by a
+// k_block_lengths launch after it (no read / write race inside the fill).
+template <typename IP>
+__global__ void __launch_bounds__(SB) k_block_lengths(int64_t n, const IP* __restrict__ ip, int64_t* __restrict__ lens) {
+  for (int64_t r = (int64_t)blockIdx.x * SB + threadIdx.x; r < n; r += (int64_t)gridDim.x * SB)
+    lens[r] += (int64_t)(ip[r + 1] - ip[r]);
+}
+
+template <typename IP>
+__global__ void __launch_bounds__(SB) k_block_place(int64_t n, const IP* __restrict__ ip,
+                                                    const int32_t* __restrict__ indices,
+                                                    const double* __restrict__ data, int32_t col_off, double scale,
+                                                    const int64_t* __restrict__ cursor, int32_t* __restrict__ out_idx,
+                                                    double* __restrict__ out_val) {
+  const int sub = threadIdx.x % XT;
+  const int64_t gid = ((int64_t)blockIdx.x * SB + threadIdx.x) / XT;
+  const int64_t nsub = (int64_t)gridDim.x * (SB / XT);
+  for (int64_t r = gid; r < n; r += nsub) {
+    const IP lo = ip[r], hi = ip[r + 1];
+    const int64_t w = cursor[r];
+    for (IP j = lo + sub; j < hi; j += XT) {
+      out_idx[w + (int64_t)(j - lo)] = indices[j] + col_off;
+      out_val[w + (int64_t)(j - lo)] = scale * data[j];
+    }
+  }
+}
+
+// data[position of (rows[i], rows[i])] += vals[i]; rows distinct.  A row without a stored diagonal raises *missing.
+template <typename IP>
+__global__ void __launch_bounds__(SB) k_add_diagonal(int64_t m, const int32_t* __restrict__ rows,
+                                                     const double* __restrict__ vals, const IP* __restrict__ ip,
+                                                     const int32_t* __restrict__ indices, double* __restrict__ data,
+                                                     int32_t* missing) {
+  for (int64_t i = (int64_t)blockIdx.x * SB + threadIdx.x; i < m; i += (int64_t)gridDim.x * SB) {
+    const int32_t r = rows[i];
+    IP lo = ip[r], hi = ip[r + 1];
+    while (lo < hi) {  // sorted row: lower bound of r
+      const IP mid = lo + (hi - lo) / 2;
+      if (indices[mid] < r) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo < ip[r + 1] && indices[lo] == r) data[lo] += vals[i];
+    else atomicAdd(missing, 1);
+  }
+}
+
 unsigned grid_for(int64_t work_items, int per_block) {
   int64_t g = pgb_cdiv(work_items, per_block);
   const int64_t cap = (int64_t)PGB_SMS * 16;
@@ -434,5 +483,65 @@ extern "C" int pgb_csr_rows_touching(int64_t n, const void* indptr, int idx64, c
   if (idx64) k_rows_touching<int64_t><<<g, SB, 0, s>>>(n, (const int64_t*)indptr, indices, first_col, touches);
   else k_rows_touching<int32_t><<<g, SB, 0, s>>>(n, (const int32_t*)indptr, indices, first_col, touches);
   PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_scan_i64(int64_t n, const int64_t* in, int64_t* out, int64_t* total_host, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  PGB_REQUIRE(workspace_bytes >= (int64_t)sizeof(int64_t) * (SCAN_PARTS + 8), "pgb_scan_i64: workspace too small");
+  if (n == 0) {
+    PGB_CHECK(cudaMemsetAsync(out, 0, sizeof(int64_t), s));
+    if (total_host) *total_host = 0;
+    return 0;
+  }
+  if (scan64<int64_t>(in, out, n, (int64_t*)workspace, s)) return 1;
+  if (total_host) {
+    PGB_CHECK(cudaMemcpyAsync(total_host, out + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    PGB_CHECK(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+
+extern "C" int pgb_csr_block_lengths(int64_t n, const void* indptr, int idx64, int64_t* lens, void* stream) {
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned g = grid_for(n, SB);
+  if (idx64) k_block_lengths<int64_t><<<g, SB, 0, s>>>(n, (const int64_t*)indptr, lens);
+  else k_block_lengths<int32_t><<<g, SB, 0, s>>>(n, (const int32_t*)indptr, lens);
+  PGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pgb_csr_block_place(int64_t n, const void* indptr, int idx64, const int32_t* indices,
+                                   const double* data, int32_t col_offset, double scale, int64_t* cursor,
+                                   int32_t* out_indices, double* out_data, void* stream) {
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned g = grid_for(n, SB / XT);
+  if (idx64)
+    k_block_place<int64_t><<<g, SB, 0, s>>>(n, (const int64_t*)indptr, indices, data, col_offset, scale, cursor,
+                                             out_indices, out_data);
+  else
+    k_block_place<int32_t><<<g, SB, 0, s>>>(n, (const int32_t*)indptr, indices, data, col_offset, scale, cursor,
+                                             out_indices, out_data);
+  PGB_LAUNCH_CHECK();
+  return pgb_csr_block_lengths(n, indptr, idx64, cursor, stream);
+}
+
+extern "C" int pgb_csr_add_diagonal(int64_t m, const int32_t* rows, const double* vals, const void* indptr,
+                                    int idx64, const int32_t* indices, double* data, int32_t* flag_dev,
+                                    void* stream) {
+  if (m == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  PGB_CHECK(cudaMemsetAsync(flag_dev, 0, sizeof(int32_t), s));
+  const unsigned g = grid_for(m, SB);
+  if (idx64) k_add_diagonal<int64_t><<<g, SB, 0, s>>>(m, rows, vals, (const int64_t*)indptr, indices, data, flag_dev);
+  else k_add_diagonal<int32_t><<<g, SB, 0, s>>>(m, rows, vals, (const int32_t*)indptr, indices, data, flag_dev);
+  PGB_LAUNCH_CHECK();
+  int32_t missing = 0;
+  PGB_CHECK(cudaMemcpyAsync(&missing, flag_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PGB_CHECK(cudaStreamSynchronize(s));
+  PGB_REQUIRE(missing == 0, "pgb_csr_add_diagonal: a listed row has no stored diagonal entry");
   return 0;
 }

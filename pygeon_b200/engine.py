@@ -511,6 +511,39 @@ class DeviceCSR:
         ip, ix, da = extract_rows(self.indptr, self.indices, self.data, rows, col_map)
         return DeviceCSR((rows_out, n_cols), ip, ix, da, symmetric=self.symmetric)
 
+    def transpose(self) -> "DeviceCSR":
+        """CSR arrays of the transpose (``pgb_csr_transpose``: stable radix sort by column, deterministic)."""
+        m, n = self.shape
+        if self.symmetric and m == n:
+            return self
+        dev = self.data.device
+        nnz = self.nnz
+        it = torch.int64 if (nnz >= 2**31 or force_idx64) else _I32
+        ip = torch.empty(n + 1, dtype=it, device=dev)
+        ix = torch.empty(nnz, dtype=_I32, device=dev)
+        da = torch.empty(nnz, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            ws_bytes = int(lib.pgb_csr_transpose_workspace_bytes(nnz))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            check(lib.pgb_csr_transpose(m, n, nnz, self.indptr.data_ptr(), self.idx64, self.indices.data_ptr(),
+                                        self.data.data_ptr(), ip.data_ptr(), 1 if it == torch.int64 else 0,
+                                        ix.data_ptr(), da.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
+            _lib.count(2 + 5 * (((max(n, 2) - 1).bit_length() + 7) // 8))  # per radix pass: histogram, 3 scan kernels, scatter
+        return DeviceCSR((n, m), ip, ix, da, symmetric=False)
+
+    def add_diagonal(self, rows: torch.Tensor, vals: torch.Tensor) -> None:
+        """In place ``A[rows[i], rows[i]] += vals[i]`` for distinct rows whose diagonal entry is stored
+        (``pgb_csr_add_diagonal``)."""
+        dev = self.data.device
+        rows = rows.to(device=dev, dtype=_I32).contiguous()
+        vals = vals.to(device=dev, dtype=torch.float64).contiguous()
+        with torch.cuda.device(dev):
+            flag = torch.empty(1, dtype=_I32, device=dev)
+            check(lib.pgb_csr_add_diagonal(int(rows.numel()), rows.data_ptr(), vals.data_ptr(), self.indptr.data_ptr(),
+                                           self.idx64, self.indices.data_ptr(), self.data.data_ptr(), flag.data_ptr(),
+                                           _stream()))
+            _lib.count(1)
+
     @staticmethod
     def from_scipy(A, device=None) -> "DeviceCSR":
         dev = _device(device)
@@ -525,6 +558,70 @@ class DeviceCSR:
             _to_dev(A.data.astype(np.float64, copy=False), dev),
             symmetric=False,  # unknown: the arrays are CSR, a CSC copy is made by transposition
         )
+
+
+def device_bmat(blocks, device=None, symmetric: bool = False) -> DeviceCSR:
+    """``sps.block_array(blocks).tocsr()`` in HBM (``utils/bmat.py``; the block operators of
+    ``numerics/innerproducts.py:162-232`` / ``differentials.py:144-192``): ``blocks`` is a 2-D nested list
+    whose entries are ``DeviceCSR``, ``(DeviceCSR, scale)`` or ``None``.  Count -> scan -> place kernels
+    (``pgb_csr_block_lengths`` / ``pgb_scan_i64`` / ``pgb_csr_block_place``), O(rows) scratch."""
+    grid = [[(b, 1.0) if isinstance(b, DeviceCSR) else b for b in row] for row in blocks]
+    nbr, nbc = len(grid), len(grid[0])
+    if any(len(row) != nbc for row in grid):
+        raise ValueError("device_bmat: ragged block grid")
+    heights, widths = [None] * nbr, [None] * nbc
+    dev = None
+    for i, row in enumerate(grid):
+        for j, b in enumerate(row):
+            if b is None:
+                continue
+            A = b[0]
+            dev = A.data.device if dev is None else dev
+            if A.data.device != dev:
+                raise ValueError("device_bmat: blocks on different devices")
+            for sizes, k, v in ((heights, i, A.shape[0]), (widths, j, A.shape[1])):
+                if sizes[k] is not None and sizes[k] != v:
+                    raise ValueError(f"device_bmat: block ({i}, {j}) has shape {A.shape}, expected {heights[i]} x {widths[j]}")
+                sizes[k] = v
+    if dev is None or None in heights or None in widths:
+        raise ValueError("device_bmat: a block row or column holds no block (its size is unknown)")
+    row0 = np.concatenate([[0], np.cumsum(heights)]).astype(np.int64)
+    col0 = np.concatenate([[0], np.cumsum(widths)]).astype(np.int64)
+    n, m = int(row0[-1]), int(col0[-1])
+    if n >= 2**31 or m >= 2**31:
+        raise ValueError("device_bmat: dimensions must be < 2^31")
+    with torch.cuda.device(dev):
+        s = _stream()
+        lens = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        nl = 0
+        for i, row in enumerate(grid):
+            for b in row:
+                if b is not None and b[0].shape[0]:
+                    A = b[0]
+                    check(lib.pgb_csr_block_lengths(A.shape[0], A.indptr.data_ptr(), A.idx64,
+                                                    lens.data_ptr() + 8 * int(row0[i]), s))
+                    nl += 1
+        ws_bytes = int(lib.pgb_system_workspace_bytes(0))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ip = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        tot = C.c_int64(0)
+        check(lib.pgb_scan_i64(n, lens.data_ptr(), ip.data_ptr(), C.byref(tot), ws.data_ptr(), ws_bytes, s))
+        nnz = int(tot.value)
+        ix = torch.empty(nnz, dtype=_I32, device=dev)
+        da = torch.empty(nnz, dtype=torch.float64, device=dev)
+        cursor = lens  # reuse: the cursors start at the row starts
+        cursor.copy_(ip)
+        for i, row in enumerate(grid):
+            for j, b in enumerate(row):  # left to right: the columns of a row stay sorted
+                if b is not None and b[0].shape[0]:
+                    A, scale = b
+                    check(lib.pgb_csr_block_place(A.shape[0], A.indptr.data_ptr(), A.idx64, A.indices.data_ptr(),
+                                                  A.data.data_ptr(), int(col0[j]), float(scale),
+                                                  cursor.data_ptr() + 8 * int(row0[i]), ix.data_ptr(), da.data_ptr(), s))
+        _lib.count(3 * nl + 3)
+        if nnz < 2**31 and not force_idx64:
+            ip = ip.to(_I32)
+    return DeviceCSR((n, m), ip, ix, da, symmetric=symmetric)
 
 
 def mask_to_map(mask: torch.Tensor, want_newid: bool = True):

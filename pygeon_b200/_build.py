@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libpgb.so")
 SOURCES = ["pgb_api.cu", "pgb_pack.cu", "pgb_local.cu", "pgb_csr.cu", "pgb_rowsort.cu", "pgb_rowthread.cu",
-           "pgb_rowhash.cu", "pgb_rowlong.cu", "pgb_krylov.cu", "pgb_geometry.cu", "pgb_system.cu", "pgb_dist.cu", "pgb_numeric_bulk.cu"]
+           "pgb_rowhash.cu", "pgb_rowins.cu", "pgb_rowlong.cu", "pgb_krylov.cu", "pgb_geometry.cu", "pgb_system.cu", "pgb_dist.cu", "pgb_numeric_bulk.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", f"-I{INCLUDE}", f"-I{CSRC}",

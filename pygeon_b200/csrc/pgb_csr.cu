@@ -1083,7 +1083,7 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
       const uint32_t* rows;  // row list (then r0 = 0) or null
       int64_t r0, r1;
       uint32_t bound;  // largest incidence count
-      int kind;        // 0 k_rowthread, 1 k_rowhash, 2 k_rowsort, 3 k_rowlong
+      int kind;        // 0 k_rowthread, 1 k_rowhash, 2 k_rowsort, 3 k_rowlong, 4 k_rowins
     };
     auto bucket = [](uint32_t m) {
       uint32_t b = 1;
@@ -1213,6 +1213,17 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
       }
     }
     PGB_CHECK(cudaMemsetAsync(row_nnz + n_rows, 0, 2 * sizeof(uint32_t), s));
+    // hash-dedupe items whose rows fit one thread each go to k_rowins; the rows it cannot finish (too many
+    // distinct columns) come back in a list and are redone by k_rowhash
+    uint32_t* ins_ovf = kbuf[1];  // free in the counting-transpose mode
+    uint32_t ins_bound = 0;
+    if (!radix)
+      for (Item& x : items)
+        if (x.kind == 1 && rowins_applies(x.bound, L)) {
+          x.kind = 4;
+          ins_bound = x.bound > ins_bound ? x.bound : ins_bound;
+        }
+    if (ins_bound) PGB_CHECK(cudaMemsetAsync(ins_ovf, 0, sizeof(uint32_t), s));
     pt.mark();
     for (const Item& x : items) {
       const uint32_t mc = x.bound * (uint32_t)L;
@@ -1231,10 +1242,19 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
           rc = launch_rowsort(mc, L, x.rows, x.r0, x.r1, n_rows, row_start, pbuf[0], cell_dofs, slots, ucol, row_nnz,
                               meta + 4, s);
           break;
+        case 4:
+          rc = launch_rowins(L, x.rows, x.r0, x.r1, row_start, inc_rows, cell_dofs, perm_or_inc, slots, ucol, row_nnz,
+                             meta + 4, ins_ovf, s);
+          break;
         default:
           rc = launch_rowlong(L, x.rows, x.r0, x.r1, row_start, inc_rows, cell_dofs, perm_or_inc, slots, ucol, row_nnz,
                               meta + 4, meta + 5, s);
       }
+      if (rc) return rc;
+    }
+    if (ins_bound) {  // the rows k_rowins left (count on the device: no host read, a fixed grid loops over the list)
+      int rc = launch_rowhash_list(ins_bound * (uint32_t)L, L, ins_ovf, row_start, inc_rows, cell_dofs, perm_or_inc, slots,
+                                   (int32_t*)(ws + l.ucol), row_nnz, meta + 4, s);
       if (rc) return rc;
     }
     pt.mark();

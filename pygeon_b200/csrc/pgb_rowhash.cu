@@ -54,10 +54,11 @@ __device__ __forceinline__ void sort_uniques(uint32_t* ucols, int nu, const uint
 // G lanes per row (256/G rows per block), NPL incidences per lane (row capacity G*NPL incidences),
 // table of HS entries per row (at most 3/4 full)
 template <int G, int NPL, int L, int HS>
-__global__ void __launch_bounds__(256, (NPL == 1 && L <= 6) ? ((256 / G) * HS * 9 <= 20000 ? 8 : 5) : (NPL == 1 ? 5 : 1))
-k_rowhash(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ inc_tmp,
-          const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos, uint8_t* __restrict__ slots,
-          int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz, uint32_t* __restrict__ max_nnz) {
+__device__ __forceinline__ void rowhash_block(int64_t block_index, const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows,
+                                              const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ inc_tmp,
+                                              const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos,
+                                              uint8_t* __restrict__ slots, int32_t* __restrict__ ucol_tmp,
+                                              uint32_t* __restrict__ row_nnz, uint32_t* __restrict__ max_nnz) {
   constexpr int LP = (L + 3) & ~3;
   constexpr int RPB = 256 / G;  // rows per block
   __shared__ uint32_t s_key[RPB][HS];
@@ -68,7 +69,7 @@ k_rowhash(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const
   const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
   const int g = threadIdx.x / G;
   bool live;
-  const int64_t r = pick_row(rows, row0, n_rows, (int64_t)blockIdx.x * RPB + g, live);
+  const int64_t r = pick_row(rows, row0, n_rows, block_index * RPB + g, live);
   uint32_t* tkey = s_key[g];
   uint8_t* tslot = s_slot[g];
   uint32_t* ucols = s_ucol[g];
@@ -166,6 +167,32 @@ k_rowhash(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const
   }
 }
 
+#define PGB_RH_BOUNDS(G, NPL, L, HS) \
+  __launch_bounds__(256, (NPL == 1 && L <= 6) ? ((256 / G) * HS * 9 <= 20000 ? 8 : 5) : (NPL == 1 ? 5 : 1))
+
+template <int G, int NPL, int L, int HS>
+__global__ void PGB_RH_BOUNDS(G, NPL, L, HS)
+k_rowhash(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ inc_tmp,
+          const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos, uint8_t* __restrict__ slots,
+          int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz, uint32_t* __restrict__ max_nnz) {
+  rowhash_block<G, NPL, L, HS>((int64_t)blockIdx.x, rows, row0, n_rows, row_start, inc_tmp, dofs, inc_pos, slots, ucol_tmp, row_nnz,
+                               max_nnz);
+}
+
+// the rows of a list whose length is only known on the device (list[0] = count, list[1..] = rows: what k_rowins
+// could not finish): a fixed grid loops over the list, so that no host read decides the launch
+template <int G, int NPL, int L, int HS>
+__global__ void PGB_RH_BOUNDS(G, NPL, L, HS)
+k_rowhash_list(const uint32_t* __restrict__ list, const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ inc_tmp,
+               const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos, uint8_t* __restrict__ slots,
+               int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz, uint32_t* __restrict__ max_nnz) {
+  const int64_t n = (int64_t)list[0];
+  for (int64_t b = blockIdx.x; b * (256 / G) < n; b += gridDim.x) {
+    rowhash_block<G, NPL, L, HS>(b, list + 1, 0, n, row_start, inc_tmp, dofs, inc_pos, slots, ucol_tmp, row_nnz, max_nnz);
+    __syncthreads();  // the tables and wmax are reused by the next round
+  }
+}
+
 template <int G, int NPL, int HS>
 int launch_rowhash_l(int L, const uint32_t* rows, int64_t row0, int64_t n_rows, const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs,
                      uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz, uint32_t* max_nnz,
@@ -212,6 +239,25 @@ int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, const uint32_t* r
   }
   PGB_RHL(32, 4, 512);  // more than 32 incidences: more than 96 candidates
 #undef PGB_RHL
+}
+
+// rows of a device-side list (see k_rowhash_list); only the shapes k_rowins hands over: at most 32 incidences, L <= 4
+int launch_rowhash_list(uint32_t max_cand, int L, const uint32_t* list, const uint32_t* row_start, const uint32_t* inc_tmp,
+                        const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz,
+                        uint32_t* max_nnz, cudaStream_t s) {
+  const unsigned grid = (unsigned)(PGB_SMS * 4);
+#define PGB_RHX(LL, H) k_rowhash_list<32, 1, LL, H><<<grid, 256, 0, s>>>(list, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz)
+  if (L == 3) {
+    if (max_cand <= 96) PGB_RHX(3, 128); else PGB_RHX(3, 512);
+  } else if (L == 4) {
+    if (max_cand <= 96) PGB_RHX(4, 128); else PGB_RHX(4, 512);
+  } else {
+    pgb_set_error("k_rowhash_list: unsupported local size %d", L);
+    return 2;
+  }
+#undef PGB_RHX
+  PGB_LAUNCH_CHECK();
+  return 0;
 }
 
 // rows with many candidates but few distinct columns: dedupe by hashing, sort only the distinct ones

@@ -101,6 +101,34 @@ __device__ __forceinline__ void warp_bitonic_u32(uint32_t (&key)[NPL], int lane)
   }
 }
 
+// bitonic sorting network over N registers of one thread (no shuffles, no predicates: a compare-exchange is
+// two VIMNMX)
+template <int N, typename KeyT>
+__device__ __forceinline__ void reg_bitonic(KeyT (&a)[N]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int p = i ^ (k - 1);
+      if (i < p) {
+        KeyT lo = a[i] < a[p] ? a[i] : a[p], hi = a[i] < a[p] ? a[p] : a[i];
+        a[i] = lo, a[p] = hi;
+      }
+    }
+#pragma unroll
+    for (int j = k >> 2; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int p = i ^ j;
+        if (i < p) {
+          KeyT lo = a[i] < a[p] ? a[i] : a[p], hi = a[i] < a[p] ? a[p] : a[i];
+          a[i] = lo, a[p] = hi;
+        }
+      }
+    }
+  }
+}
+
 // dof row of one cell, vector loads where the row pitch allows
 template <int L>
 __device__ __forceinline__ void load_dofs(const int32_t* __restrict__ p, uint32_t (&d)[L]) {
@@ -150,6 +178,17 @@ bool rowhash_applies(uint32_t max_inc, uint32_t max_cand);
 int launch_rowhash(uint32_t max_inc, uint32_t max_cand, int L, const uint32_t* rows, int64_t row0, int64_t row1,
                    const uint32_t* row_start, const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
                    uint32_t* row_nnz, uint32_t* max_nnz, cudaStream_t s);
+
+int launch_rowhash_list(uint32_t max_cand, int L, const uint32_t* list, const uint32_t* row_start, const uint32_t* inc_tmp,
+                        const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol, uint32_t* row_nnz,
+                        uint32_t* max_nnz, cudaStream_t s);
+
+// k_rowins: one thread per row of 17..32 incident cells, private hash table (pgb_rowins.cu); rows with too many
+// distinct columns are appended to ovf (ovf[0] = count, ovf[1..] = rows) for k_rowhash
+bool rowins_applies(uint32_t max_inc, int L);
+int launch_rowins(int L, const uint32_t* rows, int64_t row0, int64_t row1, const uint32_t* row_start,
+                  const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
+                  uint32_t* row_nnz, uint32_t* max_nnz, uint32_t* ovf, cudaStream_t s);
 
 // k_rowlong: one block per row, up to LONG_MAX_INC incident cells (pgb_rowlong.cu); inc_tmp: the row
 // blocks in any order.  *overflow_flag is raised when a row has more than 255 distinct columns.

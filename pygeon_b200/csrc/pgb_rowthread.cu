@@ -12,32 +12,6 @@ using namespace pgb_rows;
 // so the row offsets, the incidences, the slot bytes and the unique columns are all accessed in
 // contiguous runs across the warp.  The thread also puts its (at most MI) incidences into canonical
 // order and records inc_pos, like k_rowhash.  Output identical to k_rowsort.
-template <int N, typename KeyT>
-__device__ __forceinline__ void reg_bitonic(KeyT (&a)[N]) {
-#pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const int p = i ^ (k - 1);
-      if (i < p) {
-        KeyT lo = a[i] < a[p] ? a[i] : a[p], hi = a[i] < a[p] ? a[p] : a[i];
-        a[i] = lo, a[p] = hi;
-      }
-    }
-#pragma unroll
-    for (int j = k >> 2; j > 0; j >>= 1) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        const int p = i ^ j;
-        if (i < p) {
-          KeyT lo = a[i] < a[p] ? a[i] : a[p], hi = a[i] < a[p] ? a[p] : a[i];
-          a[i] = lo, a[p] = hi;
-        }
-      }
-    }
-  }
-}
-
 // Block-compacted output: the 128 rows of a block stage their unique columns back to back in shared
 // memory (row order) and their slot bytes at the block-relative incidence position; both are then
 // written with coalesced stores: the columns to ucol_tmp[row_start[first]*L ...) (k_compact knows

@@ -1243,7 +1243,7 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
                               meta + 4, s);
           break;
         case 4:
-          rc = launch_rowins(L, x.rows, x.r0, x.r1, row_start, inc_rows, cell_dofs, perm_or_inc, slots, ucol, row_nnz,
+          rc = launch_rowins(x.bound, L, x.rows, x.r0, x.r1, row_start, inc_rows, cell_dofs, perm_or_inc, slots, ucol, row_nnz,
                              meta + 4, ins_ovf, s);
           break;
         default:

@@ -33,14 +33,14 @@ __device__ __forceinline__ uint32_t ins_hash(uint32_t c) { return (c * 265443576
 // RANGE: the block's rows are consecutive, so its incidences and slot words are one contiguous run each: they
 // are moved with coalesced loads / stores and redistributed through shared memory (a thread-per-row access
 // touches one 32-byte sector per lane and instruction; the kernel is bound by the L1 sector rate).
-template <int L, bool RANGE>
+template <int L, bool RANGE, int MI>
 __global__ void __launch_bounds__(INS_B, 7)
 k_rowins(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start,
          const uint32_t* __restrict__ inc_tmp, const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos,
          uint8_t* __restrict__ slots, int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz,
          uint32_t* __restrict__ max_nnz, uint32_t* __restrict__ ovf) {
   static_assert(L <= 4, "one slot word per incidence");
-  constexpr int B = INS_B, MI = INS_MI, HS = INS_HS;
+  constexpr int B = INS_B, HS = INS_HS, NW = 32;  // MI: incidences kept per row (24 or 32); NW: width of the network
   // the runs in global order are stored with one pad word per 32 (sw): thread t reads / writes around word 24 t,
   // which without the padding falls on 4 banks only
   __shared__ __align__(16) uint32_t s_inc[MI * B + MI * B / 32];  // incidences, then the table positions of their candidates
@@ -59,7 +59,9 @@ k_rowins(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const 
   }
   uint32_t rs0 = 0, n_blk = 0;  // RANGE: the block's run of incidences
   {
-    uint32_t inc[MI];
+    uint32_t inc[NW];
+#pragma unroll
+    for (int q = MI; q < NW; ++q) inc[q] = INS_EMPTY;
     if constexpr (RANGE) {
       const int64_t rb = row0 + (int64_t)blockIdx.x * B;
       const int64_t re = rb + B < n_rows ? rb + B : n_rows;
@@ -74,7 +76,7 @@ k_rowins(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const 
 #pragma unroll
       for (int q = 0; q < MI; ++q) inc[q] = ((uint32_t)q < cnt) ? inc_tmp[rs + q] : INS_EMPTY;
     }
-    reg_bitonic<MI, uint32_t>(inc);
+    reg_bitonic<NW, uint32_t>(inc);
 #pragma unroll
     for (int q = 0; q < MI; ++q) my_inc[q * B] = inc[q];
   }
@@ -193,19 +195,26 @@ bool rowins_applies(uint32_t max_inc, int L) {
   return !off && !g_force_bitonic && !g_force_key64 && max_inc > 16 && max_inc <= (uint32_t)INS_MI && (L == 3 || L == 4);
 }
 
-int launch_rowins(int L, const uint32_t* rows, int64_t row0, int64_t row1, const uint32_t* row_start,
+int launch_rowins(uint32_t max_inc, int L, const uint32_t* rows, int64_t row0, int64_t row1, const uint32_t* row_start,
                   const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
                   uint32_t* row_nnz, uint32_t* max_nnz, uint32_t* ovf, cudaStream_t s) {
   char name[64];
-  snprintf(name, sizeof(name), "k_rowins<%d>", L);
+  snprintf(name, sizeof(name), "k_rowins<%d,%d>", L, max_inc <= 24 ? 24 : 32);
   note_row_kernel(name);
   const unsigned grid = (unsigned)pgb_cdiv(row1 - row0, INS_B);
-#define PGB_RI(LL, RG) k_rowins<LL, RG><<<grid, INS_B, 0, s>>>(rows, row0, row1, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, ovf)
+#define PGB_RI(LL, RG, M) k_rowins<LL, RG, M><<<grid, INS_B, 0, s>>>(rows, row0, row1, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, ovf)
+#define PGB_RI2(LL, M)         \
+  do {                         \
+    if (rows) PGB_RI(LL, false, M); \
+    else PGB_RI(LL, true, M);  \
+  } while (0)
+  // 24 incidences (P1 on Kuhn tets) leave room for a seventh block per SM
   if (L == 3) {
-    if (rows) PGB_RI(3, false); else PGB_RI(3, true);
+    if (max_inc <= 24) PGB_RI2(3, 24); else PGB_RI2(3, 32);
   } else {
-    if (rows) PGB_RI(4, false); else PGB_RI(4, true);
+    if (max_inc <= 24) PGB_RI2(4, 24); else PGB_RI2(4, 32);
   }
+#undef PGB_RI2
 #undef PGB_RI
   PGB_LAUNCH_CHECK();
   return 0;

@@ -186,7 +186,7 @@ int launch_rowhash_list(uint32_t max_cand, int L, const uint32_t* list, const ui
 // k_rowins: one thread per row of 17..32 incident cells, private hash table (pgb_rowins.cu); rows with too many
 // distinct columns are appended to ovf (ovf[0] = count, ovf[1..] = rows) for k_rowhash
 bool rowins_applies(uint32_t max_inc, int L);
-int launch_rowins(int L, const uint32_t* rows, int64_t row0, int64_t row1, const uint32_t* row_start,
+int launch_rowins(uint32_t max_inc, int L, const uint32_t* rows, int64_t row0, int64_t row1, const uint32_t* row_start,
                   const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
                   uint32_t* row_nnz, uint32_t* max_nnz, uint32_t* ovf, cudaStream_t s);
 

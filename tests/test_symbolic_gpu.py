@@ -55,7 +55,7 @@ CASES = [
     (5, 2999, 3100, 8, "k_rowthread<8,5,64"),
     (3, 130, 131, 3, "k_rowthread<"),           # a single block, ragged last group       # k_rowthread MI=8
     (3, 6000, 2500, 16, "k_rowthread<16,3,64"),      # k_rowthread MI=16, 48 keys
-    (3, 6000, 2500, 30, "k_rowins<3>"),      # k_rowins; the hub row (> 24 distinct columns) comes back through k_rowhash_list
+    (3, 6000, 2500, 30, "k_rowins<3,"),      # k_rowins; the hub row (> 24 distinct columns) comes back through k_rowhash_list
     (3, 6000, 2500, 80, "k_rowhash<32,4,3,512>"),      # k_rowhash 32 lanes x 4, table 512
     (3, 6000, 2500, 150, "k_rowsort<32,16,3"),     # k_row_canon + k_rowsort (450 candidates)
     (3, 6000, 2500, 200, "k_rowlong<3>"),  # > 512 candidates: one block per row
@@ -65,8 +65,8 @@ CASES = [
     (4, 3000, 9000, 2, "k_rowthread<"),       # k_rowthread MI=2
     (4, 3000, 4000, 4, "k_rowthread<"),
     (4, 5000, 2500, 16, "k_rowthread<16,4,64"),      # k_rowthread MI=16, 64 keys
-    (4, 5000, 2500, 24, "k_rowins<4>"),      # k_rowins + k_rowhash_list (table 128)
-    (4, 5000, 2500, 32, "k_rowins<4>"),      # k_rowins + k_rowhash_list (table 512)
+    (4, 5000, 2500, 24, "k_rowins<4,24>"),      # k_rowins + k_rowhash_list (table 128)
+    (4, 5000, 2500, 32, "k_rowins<4,32>"),      # k_rowins + k_rowhash_list (table 512)
     (4, 5000, 2500, 60, "k_rowhash<32,4,4,512>"),      # 32 lanes x 4
     (4, 5000, 2500, 100, "k_rowsort<32,16,4"),     # k_rowsort
     (5, 3000, 9000, 2, "k_rowthread<"),

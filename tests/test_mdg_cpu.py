@@ -76,3 +76,31 @@ def test_mortar_and_block_operators_match_reference(cube):
     ref = rpg.numerics.innerproducts.mass_matrix(rm, 1, None, zero, keyword="flow")
     assert ours.nnz == intf.num_cells and same(ours, ref)
     assert pg.numerics.innerproducts.mass_matrix(mdg, 1, None, zero, keyword="flow", trace_contribution=False).nnz == 0
+
+
+def test_trace_term_is_diagonal_on_a_conforming_interface(cube):
+    """Host side of the device-resident face mass (md_system._trace_diagonal): the mortar trace term
+    S diag(1 / (|m| k_n)) S^T (innerproducts.py:207-224) touches one diagonal entry per fracture face of the 3D
+    grid; a non-diagonal term (non-conforming interface) is refused, not approximated."""
+    from pygeon_b200 import md_system
+
+    mdg = cube
+    intf, d_intf = mdg.interfaces(return_data=True)[0]
+    rng = np.random.default_rng(1)
+    kn = rng.uniform(0.5, 5.0, intf.num_cells)
+    d_intf.update({pg.PARAMETERS: {"flow": {pg.NORMAL_DIFFUSIVITY: kn}}})
+    rows, vals = md_system._trace_diagonal(intf, d_intf, "flow")
+    S = intf.signed_mortar_to_primary
+    T = sps.csr_array(S @ sps.diags_array(1.0 / intf.cell_volumes / kn) @ S.T)
+    assert rows.size == intf.num_cells and np.array_equal(np.unique(rows), rows)
+    assert np.array_equal(vals, T.diagonal()[rows]) and abs(T - sps.diags_array(T.diagonal())).max() == 0
+    sd3 = mdg.subdomains()[0]
+    assert np.all(sd3.tags["fracture_faces"][rows])
+
+    class Fake:  # two mortar cells on one primary face: the term couples them
+        signed_mortar_to_primary = sps.csc_array(np.array([[1.0, 0.0], [1.0, -1.0]]))
+        cell_volumes = np.ones(2)
+        num_cells = 2
+
+    with pytest.raises(NotImplementedError):
+        md_system._trace_diagonal(Fake(), {pg.PARAMETERS: {"flow": {pg.NORMAL_DIFFUSIVITY: np.ones(2)}}}, "flow")

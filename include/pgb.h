@@ -231,8 +231,9 @@ int pgb_local_matrices(int kind, int dim, int64_t nc, const int32_t* cell_nodes,
  */
 int64_t pgb_csr_workspace_bytes(int64_t nc, int L, int64_t n_rows, int mode);
 /* Optional CUDA-event timing of the phases of the two-level symbolic_sort (off by default):
- * out[0] counting (k_inc_count, scan, max, host read; mode 4: the radix sort), [1] placement of the
- * incidences (+ k_row_canon when the row kernel does not sort them itself; mode 4: row offsets),
+ * out[0] counting (k_inc_count, scan, max, host read with the placement kernel queued behind it; mode 4: the
+ * radix sort), [1] rest of the placement (+ k_row_canon when the row kernel does not sort the incidences itself;
+ * mode 4: row offsets),
  * [2] per-row kernel, [3] scan of the row counts. */
 void pgb_set_profile(int on);
 void pgb_get_phase_ms(double* out, int n);
@@ -244,6 +245,12 @@ int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell
                           void* workspace, int64_t workspace_bytes, uint32_t* perm_or_inc,
                           uint8_t* slots, uint32_t* row_start, int64_t* nnz_host,
                           int* max_row_nnz_host, void* stream);
+/* nnz_host == NULL: pgb_csr_symbolic_sort returns without waiting for the device (apart from its one small read of
+ * the chunk maxima, behind which the placement kernel is already queued); inc_pos / slots / row_start are
+ * complete in stream order, so the caller may queue K1 (pgb_local_matrices with dst_pos = inc_pos) at once and
+ * collect nnz / max_row_nnz afterwards with pgb_csr_symbolic_result (waits for an event recorded before that
+ * extra work; same return codes as the synchronous call, 3 = fall back to mode 1).  One pending call per device. */
+int pgb_csr_symbolic_result(int64_t* nnz_host, int* max_row_nnz_host);
 int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mode, int64_t nnz,
                             const void* workspace, const uint32_t* row_start, void* indptr, int idx64,
                             int32_t* indices, uint32_t* seg, void* stream);

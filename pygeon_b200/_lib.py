@@ -45,6 +45,7 @@ _SIGS = {
     "pgb_set_profile": (None, [_i]),
     "pgb_get_phase_ms": (None, [_p, _i]),
     "pgb_csr_symbolic_sort": (_i, [_l, _l, _i, _p, _i, _p, _l, _p, _p, _p, C.POINTER(C.c_int64), C.POINTER(_i), _p]),
+    "pgb_csr_symbolic_result": (_i, [C.POINTER(C.c_int64), C.POINTER(_i)]),
     "pgb_csr_symbolic_finish": (_i, [_l, _l, _i, _i, _l, _p, _p, _p, _i, _p, _p, _p]),
     "pgb_csr_numeric_rows": (_i, [_l, _i, _i, _p, _p, _p, _i, _p, _p, _i, _p]),
     "pgb_csr_numeric": (_i, [_l, _p, _p, _p, _p, _p]),

@@ -978,6 +978,49 @@ extern "C" int64_t pgb_csr_workspace_bytes(int64_t nc, int L, int64_t n_rows, in
   return ws_layout(nc * L * L, nc * L, n_rows, mode).total;
 }
 
+namespace {
+// per-device event and pinned words for the two host reads of a symbolic_sort call: the work queued behind the
+// read (the placement kernel, the caller's K1) keeps the GPU busy while the host waits for the event only
+struct SymHost {
+  cudaEvent_t ev = nullptr;
+  uint32_t* pin = nullptr;  // [4]: nnz, max incidences, max row nnz, k_rowlong overflow
+  bool pending = false;
+  int mode = 0;
+};
+SymHost g_sym_host[64];
+int sym_host(SymHost** out) {
+  int dev = 0;
+  PGB_CHECK(cudaGetDevice(&dev));
+  PGB_REQUIRE(dev >= 0 && dev < 64, "pgb_csr_symbolic_sort: device index out of range");
+  SymHost& h = g_sym_host[dev];
+  if (!h.ev) {
+    PGB_CHECK(cudaEventCreateWithFlags(&h.ev, cudaEventDisableTiming));
+    PGB_CHECK(cudaMallocHost(&h.pin, 4 * sizeof(uint32_t)));
+  }
+  *out = &h;
+  return 0;
+}
+int sym_result_check(const uint32_t* out2, int mode, int64_t* nnz_host, int* max_row_nnz_host) {
+  *nnz_host = (int64_t)out2[0];
+  if (max_row_nnz_host) *max_row_nnz_host = (int)out2[2];
+  if (mode != MODE_FULL_SORT && (out2[2] > 255u || out2[3] > 255u)) {
+    pgb_set_error("pgb_csr_symbolic_sort: a row has %u entries (> 255, the uint8 slot range); use mode 1",
+                  out2[2] > out2[3] ? out2[2] : out2[3]);
+    return 3;
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" int pgb_csr_symbolic_result(int64_t* nnz_host, int* max_row_nnz_host) {
+  SymHost* h = nullptr;
+  if (int rc = sym_host(&h)) return rc;
+  PGB_REQUIRE(h->pending, "pgb_csr_symbolic_result: no pgb_csr_symbolic_sort call with nnz_host == NULL is pending");
+  h->pending = false;
+  PGB_CHECK(cudaEventSynchronize(h->ev));
+  return sym_result_check(h->pin, h->mode, nnz_host, max_row_nnz_host);
+}
+
 extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const int32_t* cell_dofs, int mode,
                                      void* workspace, int64_t workspace_bytes, uint32_t* perm_or_inc,
                                      uint8_t* slots, uint32_t* row_start, int64_t* nnz_host,
@@ -992,7 +1035,10 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
   WsLayout l = ws_layout(n_coo, n_inc, n_rows, mode);
   PGB_REQUIRE(workspace_bytes >= l.total, "pgb_csr_symbolic_sort: workspace too small");
   g_row_kernel[0] = 0;
-  *nnz_host = 0;
+  SymHost* sh = nullptr;
+  if (int rc = sym_host(&sh)) return rc;
+  sh->pending = false;
+  if (nnz_host) *nnz_host = 0;
   if (max_row_nnz_host) *max_row_nnz_host = 0;
   char* ws = (char*)workspace;
   uint32_t* meta = (uint32_t*)(ws + l.meta);
@@ -1003,6 +1049,12 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
   PGB_CHECK(cudaMemcpyAsync(meta, m, sizeof(m), cudaMemcpyHostToDevice, s));
   if (n_coo == 0) {
     if (mode != MODE_FULL_SORT) PGB_CHECK(cudaMemsetAsync(row_start, 0, sizeof(uint32_t) * (n_rows + 1), s));
+    if (!nnz_host) {
+      for (int i = 0; i < 4; ++i) sh->pin[i] = 0u;
+      PGB_CHECK(cudaEventRecord(sh->ev, s));
+      sh->pending = true;
+      sh->mode = mode;
+    }
     return 0;
   }
 
@@ -1065,7 +1117,17 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     PGB_CHECK(cudaMemcpyAsync(h_pin + n_chunks, meta + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PGB_CHECK(cudaMemcpyAsync(chunk_max, chunk_max_d, sizeof(uint32_t) * n_chunks, cudaMemcpyDeviceToHost, s));
     PGB_CHECK(cudaMemcpyAsync(chunk_hist, chunk_hist_d, sizeof(uint32_t) * n_chunks * NCLS * 2, cudaMemcpyDeviceToHost, s));  // counts + maxima
-    PGB_CHECK(cudaStreamSynchronize(s));
+    if (!radix) {
+      // the placement does not depend on what the host decides from the chunk maxima, except for dofs with more
+      // than 255 incidences (saturated ranks: redone below with the overflow counters): it runs while the host
+      // waits for the read and builds the work items
+      PGB_CHECK(cudaEventRecord(sh->ev, s));
+      k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, nullptr, pbuf[1]);
+      PGB_LAUNCH_CHECK();
+      PGB_CHECK(cudaEventSynchronize(sh->ev));
+    } else {
+      PGB_CHECK(cudaStreamSynchronize(s));
+    }
     max_inc = h_pin[n_chunks];
     if (!radix) pt.mark();
     // rows beyond the capacity of k_rowsort go to k_rowlong (counting transpose only)
@@ -1189,14 +1251,13 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
       }
     }
     if (!radix) {
-      uint32_t* ovf = nullptr;
       if (max_inc > 255u) {  // saturated ranks: second counter per dof (row_nnz is free until the row kernels run)
-        ovf = row_nnz;
+        uint32_t* ovf = row_nnz;
         PGB_CHECK(cudaMemsetAsync(ovf, 0, sizeof(uint32_t) * n_rows, s));
+        k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, ovf, pbuf[1]);
+        PGB_LAUNCH_CHECK();
       }
-      k_inc_place<<<pgb_grid(pgb_cdiv(n_inc, 4), 256), 256, 0, s>>>((uint32_t)n_inc, cell_dofs, row_start, rank, ovf, pbuf[1]);
-      PGB_LAUNCH_CHECK();
-      inc_rows = pbuf[1];  // row blocks, each in arbitrary order
+      inc_rows = pbuf[1];  // row blocks, each in arbitrary order (placed before the host read above)
       for (const Item& x : items) {
         if (x.kind != 2) continue;  // only k_rowsort needs sorted row blocks
         const int64_t nr = x.r1 - x.r0;
@@ -1263,17 +1324,16 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     pt.mark();
     pt.finish();
   }
-  uint32_t out2[4] = {0, 0, 0, 0};  // nnz, max incidences, max row nnz, k_rowlong overflow (distinct columns of a row)
-  PGB_CHECK(cudaMemcpyAsync(out2, meta + 2, sizeof(out2), cudaMemcpyDeviceToHost, s));
-  PGB_CHECK(cudaStreamSynchronize(s));
-  *nnz_host = (int64_t)out2[0];
-  if (max_row_nnz_host) *max_row_nnz_host = (int)out2[2];
-  if (mode != MODE_FULL_SORT && (out2[2] > 255u || out2[3] > 255u)) {
-    pgb_set_error("pgb_csr_symbolic_sort: a row has %u entries (> 255, the uint8 slot range); use mode 1",
-                  out2[2] > out2[3] ? out2[2] : out2[3]);
-    return 3;
+  // nnz, max incidences, max row nnz, k_rowlong overflow (distinct columns of a row)
+  PGB_CHECK(cudaMemcpyAsync(sh->pin, meta + 2, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (!nnz_host) {  // the caller queues more work (K1 needs inc_pos only) and collects with pgb_csr_symbolic_result
+    PGB_CHECK(cudaEventRecord(sh->ev, s));
+    sh->pending = true;
+    sh->mode = mode;
+    return 0;
   }
-  return 0;
+  PGB_CHECK(cudaStreamSynchronize(s));
+  return sym_result_check(sh->pin, mode, nnz_host, max_row_nnz_host);
 }
 
 extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mode, int64_t nnz,

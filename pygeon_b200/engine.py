@@ -675,8 +675,24 @@ symbolic_mode = 0  # 0 = two-level (default), 1 = full (row,col) radix sort; see
 force_idx64 = False  # tests: emit int64 indptr even when nnz < 2^31
 
 
-def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
-    """Sort-by-(row,col) of the cell->dof incidences: CSR pattern + the gather plan."""
+_TOTAL_MEM: dict = {}
+
+
+def _total_memory(dev) -> int:
+    key = torch.device(dev).index or 0
+    if key not in _TOTAL_MEM:
+        _TOTAL_MEM[key] = int(torch.cuda.get_device_properties(key).total_memory)
+    return _TOTAL_MEM[key]
+
+
+def symbolic(pack: GridPack, space: str, mode: int | None = None, overlap=None) -> CsrPlan:
+    """Sort-by-(row,col) of the cell->dof incidences: CSR pattern + the gather plan.
+
+    ``overlap(partial_plan)``: called (two-level modes, plan not cached) once ``inc_pos`` is complete in stream
+    order but before the host waits for ``nnz``: what it queues - K1, which needs ``inc_pos`` only - keeps the GPU
+    busy while the host allocates ``indptr`` / ``indices`` and launches the compaction.  The partial plan has
+    ``mode == 0`` and no pattern yet; when the call has to fall back to the full sort afterwards, the caller
+    sees ``plan.mode == 1`` and must discard what the hook produced."""
     mode = symbolic_mode if mode is None else mode
     key = ("plan", space)
     if key in pack.plans:
@@ -699,9 +715,20 @@ def symbolic(pack: GridPack, space: str, mode: int | None = None) -> CsrPlan:
                 slots = torch.zeros((max(n_inc * ((L + 3) & ~3), 1),), dtype=torch.uint8, device=dev)
                 row_start = torch.empty((n_rows + 1,), dtype=_I32, device=dev)
             nnz, mx = C.c_int64(0), C.c_int(0)
-            rc = lib.pgb_csr_symbolic_sort(n_rows, nc, L, dofs.data_ptr(), mode, ws.data_ptr(), ws_bytes,
-                                           first.data_ptr(), _ptr(slots), _ptr(row_start), C.byref(nnz),
-                                           C.byref(mx), s)
+            if overlap is not None and mode != 1:
+                rc = lib.pgb_csr_symbolic_sort(n_rows, nc, L, dofs.data_ptr(), mode, ws.data_ptr(), ws_bytes,
+                                               first.data_ptr(), _ptr(slots), _ptr(row_start), None, None, s)
+                if rc == 0:
+                    # the hook's output (the local rows) then lives beside the workspace: only when both are small
+                    # against the device memory (no cudaMemGetInfo here: it costs more than the overlap gains)
+                    if 4 * (ws_bytes + n_inc * ((L + 3) & ~3) * 8) < _total_memory(dev):
+                        overlap(CsrPlan(n_rows, n_coo, -1, L, 0, None, None, inc_pos=first, row_start=row_start,
+                                        slots=slots, max_row_nnz=0))
+                    rc = lib.pgb_csr_symbolic_result(C.byref(nnz), C.byref(mx))
+            else:
+                rc = lib.pgb_csr_symbolic_sort(n_rows, nc, L, dofs.data_ptr(), mode, ws.data_ptr(), ws_bytes,
+                                               first.data_ptr(), _ptr(slots), _ptr(row_start), C.byref(nnz),
+                                               C.byref(mx), s)
             if rc == 3 and mode != 1:  # a dof shared by too many cells / a row too long for the register sort
                 mode = 1
                 del ws, first, slots, row_start
@@ -838,8 +865,9 @@ def clear_cache(sd) -> None:
 
 def assemble_on_pack(pack: GridPack, space: str, kind: str, wd=None, Kd=None):
     """symbolic (cached per pack) -> K1 (writing the local rows where the plan wants them) -> K2."""
-    plan = symbolic(pack, space)
-    vals = local_matrices(pack, kind, wd, Kd, plan=plan)
+    early = []  # cold plan: K1 is queued as soon as inc_pos exists, ahead of the host's wait for nnz
+    plan = symbolic(pack, space, overlap=lambda partial: early.append(local_matrices(pack, kind, wd, Kd, plan=partial)))
+    vals = early[0] if (early and plan.mode == 0) else local_matrices(pack, kind, wd, Kd, plan=plan)
     return plan, numeric(plan, vals)
 
 

@@ -136,3 +136,36 @@ def test_random_tables_all_modes(L, nc, n_rows, hub, kernel):
         assert err <= 1e-13 * np.abs(ref.data).max(), (mode, err)
     if hub <= 2048 and np.diff(ref.indptr).max() <= 255:
         assert first is not None  # the two-level path did run
+
+
+def test_overlap_hook_and_late_fallback():
+    """engine.symbolic(overlap=...): the hook runs once inc_pos is complete and before the host waits for nnz
+    (pgb_csr_symbolic_sort with nnz_host = NULL + pgb_csr_symbolic_result); the plan is the same as without the
+    hook; when a row turns out to have more than 255 entries - known only at the end - the call still falls
+    back to the full sort and reports mode 1."""
+    import torch
+
+    from pygeon_b200 import engine
+
+    dev = torch.device("cuda", 0)
+    dofs = _random_table(4, 5000, 2500, 24, seed=3)
+    dd = torch.from_numpy(dofs).to(dev)
+    seen = []
+    plan = engine.symbolic(_Table(dd, 2500, dev), "t", overlap=lambda p: seen.append((p.mode, p.nnz, p.inc_pos.clone())))
+    ref = engine.symbolic(_Table(dd, 2500, dev), "t")
+    assert len(seen) == 1 and seen[0][0] == 0 and seen[0][1] == -1 and plan.mode == 0
+    for a, b in ((plan.indptr, ref.indptr), (plan.indices, ref.indices), (plan.inc_pos, ref.inc_pos),
+                 (plan.slots, ref.slots), (plan.row_start, ref.row_start), (seen[0][2], ref.inc_pos)):
+        assert torch.equal(a, b)
+    # dof 0 in 150 cells whose other dofs are all different: 451 distinct columns in row 0
+    wide = np.arange(1, 1 + 150 * 3, dtype=np.int32).reshape(150, 3)
+    table = np.concatenate([np.zeros((150, 1), np.int32), wide], axis=1)
+    filler = (np.arange(2000)[:, None] % 1500 + np.arange(4)[None, :] + 460).astype(np.int32)
+    dofs = np.concatenate([table, filler])
+    dd = torch.from_numpy(dofs).to(dev)
+    seen = []
+    plan = engine.symbolic(_Table(dd, 2500, dev), "t", overlap=lambda p: seen.append(p.mode))
+    assert plan.mode == 1 and seen == [0]
+    vals = np.random.default_rng(0).uniform(0.5, 1.5, size=(dofs.shape[0], 4, 4))
+    ref = _oracle(dofs, 2500, vals)
+    assert np.array_equal(plan.indptr.cpu().numpy(), ref.indptr) and np.array_equal(plan.indices.cpu().numpy(), ref.indices)

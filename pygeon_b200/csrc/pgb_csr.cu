@@ -531,6 +531,34 @@ __global__ void __launch_bounds__(256) k_compact_groups(int64_t row0, int64_t ro
   if (last == n_rows && threadIdx.x == 0) indptr[n_rows] = (IP)row_off[n_rows];
 }
 
+// Rows [row0, row1) written by k_rowins (row0 a multiple of the group size): like k_compact_groups, except that
+// a group with flag != 0 keeps one segment per row (a row of it was handed to k_rowhash_list).
+template <typename IP>
+__global__ void __launch_bounds__(256) k_compact_ins(int64_t row0, int64_t row1, int64_t n_rows, int L, uint32_t grp,
+                                                     const uint32_t* __restrict__ row_start,
+                                                     const uint32_t* __restrict__ row_off,
+                                                     const uint8_t* __restrict__ flag,
+                                                     const int32_t* __restrict__ ucol_tmp, IP* __restrict__ indptr,
+                                                     int32_t* __restrict__ indices) {
+  const int64_t first = row0 + (int64_t)blockIdx.x * grp;
+  const int64_t last = first + grp < row1 ? first + grp : row1;
+  const uint32_t dst0 = row_off[first];
+  if (!flag[first]) {  // the flag is the same for every row of a group
+    const uint64_t src0 = (uint64_t)row_start[first] * (uint32_t)L;
+    const uint32_t len = row_off[last] - dst0;
+    for (uint32_t j = threadIdx.x; j < len; j += 256) indices[dst0 + j] = ucol_tmp[src0 + j];
+  } else {
+    const int gl = threadIdx.x & 7;
+    for (int64_t r = first + (threadIdx.x >> 3); r < last; r += 32) {
+      const uint32_t o0 = row_off[r], cnt = row_off[r + 1] - o0;
+      const uint64_t base = (uint64_t)row_start[r] * (uint32_t)L;
+      for (uint32_t k = gl; k < cnt; k += 8) indices[o0 + k] = ucol_tmp[base + k];
+    }
+  }
+  for (int64_t r = first + threadIdx.x; r < last; r += 256) indptr[r] = (IP)row_off[r];
+  if (last == n_rows && threadIdx.x == 0) indptr[n_rows] = (IP)row_off[n_rows];
+}
+
 // ---- numeric over row-sorted local rows (plans of the two-level symbolic) ------------------------
 // With such a plan K1 writes local row a of cell c straight to position inc_pos[c*L + a] of vals_t,
 // i.e. grouped by matrix row in ascending cell order (the order of the incidence transpose).  A CSR
@@ -844,8 +872,9 @@ struct PhaseTimer {
 struct RowRange {
   int64_t r0, r1;
   uint32_t max_inc;
-  int kind;  // 0: k_rowthread range (grouped scratch); 1: rows handled through the size-class lists (one scratch
-             // segment per row)
+  int kind;  // 0: k_rowthread range (grouped scratch); 1: one scratch segment per row (k_rowhash / k_rowsort /
+             // k_rowlong ranges, rows handled through the size-class lists); 2: k_rowins range (grouped scratch
+             // except where the per-row flag says otherwise)
 };
 std::vector<RowRange> g_ranges;
 const void* g_ranges_ws = nullptr;
@@ -1278,11 +1307,14 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
     // distinct columns) come back in a list and are redone by k_rowhash
     uint32_t* ins_ovf = kbuf[1];  // free in the counting-transpose mode
     uint32_t ins_bound = 0;
-    if (!radix)
+    if (!radix && n_rows <= 4 * n_inc)  // (the per-row flags of k_rowins live in the n_inc * 4 bytes of the rank array)
       for (Item& x : items)
         if (x.kind == 1 && rowins_applies(x.bound, L)) {
           x.kind = 4;
           ins_bound = x.bound > ins_bound ? x.bound : ins_bound;
+          if (!x.rows)  // a row range: its distinct columns are stored per block of rows (k_compact_ins)
+            for (RowRange& g : rg)
+              if (g.r0 == x.r0 && g.r1 == x.r1 && g.kind == 1) g.kind = 2;
         }
     if (ins_bound) PGB_CHECK(cudaMemsetAsync(ins_ovf, 0, sizeof(uint32_t), s));
     pt.mark();
@@ -1305,7 +1337,7 @@ extern "C" int pgb_csr_symbolic_sort(int64_t n_rows, int64_t nc, int L, const in
           break;
         case 4:
           rc = launch_rowins(x.bound, L, x.rows, x.r0, x.r1, row_start, inc_rows, cell_dofs, perm_or_inc, slots, ucol, row_nnz,
-                             meta + 4, ins_ovf, s);
+                             meta + 4, ins_ovf, rank /* free after the placement: per-row flags */, s);
           break;
         default:
           rc = launch_rowlong(L, x.rows, x.r0, x.r1, row_start, inc_rows, cell_dofs, perm_or_inc, slots, ucol, row_nnz,
@@ -1376,6 +1408,15 @@ extern "C" int pgb_csr_symbolic_finish(int64_t n_rows, int64_t nc, int L, int mo
         else
           k_compact_groups<int32_t><<<grid, 256, 0, s>>>(x.r0, x.r1, n_rows, L, ROWTHREAD_GROUP, row_start, row_off, ucol,
                                                         (int32_t*)indptr, indices);
+      } else if (x.kind == 2) {
+        const uint8_t* flag = (const uint8_t*)(ws + l.ikeys_a);
+        unsigned grid = (unsigned)pgb_cdiv(x.r1 - x.r0, (int64_t)ROWTHREAD_GROUP);
+        if (idx64)
+          k_compact_ins<int64_t><<<grid, 256, 0, s>>>(x.r0, x.r1, n_rows, L, ROWTHREAD_GROUP, row_start, row_off, flag, ucol,
+                                                     (int64_t*)indptr, indices);
+        else
+          k_compact_ins<int32_t><<<grid, 256, 0, s>>>(x.r0, x.r1, n_rows, L, ROWTHREAD_GROUP, row_start, row_off, flag, ucol,
+                                                     (int32_t*)indptr, indices);
       } else {
         unsigned grid = pgb_grid((x.r1 - x.r0 + 1) * 8, 256);
         if (idx64)

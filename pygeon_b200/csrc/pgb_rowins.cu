@@ -24,6 +24,7 @@ using namespace pgb_rows;
 // the overflow list (ovf[0] = count, ovf[1..] = rows).
 constexpr uint32_t INS_EMPTY = 0xffffffffu;
 constexpr int INS_B = 128;   // rows per block
+static_assert(INS_B == ROWTHREAD_GROUP, "k_compact_ins expects groups of ROWTHREAD_GROUP rows");
 constexpr int INS_MI = 32;   // incidences per row
 constexpr int INS_HS = 32;   // table entries
 constexpr int INS_CAP = 24;  // distinct columns (3/4 of the table)
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(INS_B, 7)
 k_rowins(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const uint32_t* __restrict__ row_start,
          const uint32_t* __restrict__ inc_tmp, const int32_t* __restrict__ dofs, uint32_t* __restrict__ inc_pos,
          uint8_t* __restrict__ slots, int32_t* __restrict__ ucol_tmp, uint32_t* __restrict__ row_nnz,
-         uint32_t* __restrict__ max_nnz, uint32_t* __restrict__ ovf) {
+         uint32_t* __restrict__ max_nnz, uint32_t* __restrict__ ovf, uint8_t* __restrict__ ovf_flag) {
   static_assert(L <= 4, "one slot word per incidence");
   constexpr int B = INS_B, HS = INS_HS, NW = 32;  // MI: incidences kept per row (24 or 32); NW: width of the network
   // the runs in global order are stored with one pad word per 32 (sw): thread t reads / writes around word 24 t,
@@ -125,13 +126,10 @@ k_rowins(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const 
     my_inc[q * B] = word;
   }
   // sorted distinct columns; their ranks replace the keys
-  {
-    uint32_t k[HS];
-#pragma unroll
-    for (int h = 0; h < HS; ++h) k[h] = my_key[h * B];
-    reg_bitonic<HS, uint32_t>(k);
+  uint32_t k[HS];
+  auto own_segment = [&]() {  // the row's distinct columns at the head of its own scratch segment
     const uint32_t base = rs * L;
-    if constexpr (L == 4) {  // 16-byte stores; the tail of the last group stays inside the row's own segment
+    if constexpr (L == 4) {  // 16-byte stores; the tail of the last group stays inside the segment
 #pragma unroll
       for (int g = 0; g < INS_CAP / 4; ++g)
         if ((uint32_t)(4 * g) < nu && !over)
@@ -141,6 +139,12 @@ k_rowins(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const 
       for (int e = 0; e < INS_CAP; ++e)
         if ((uint32_t)e < nu && !over) ucol_tmp[base + e] = (int32_t)k[e];
     }
+  };
+  {
+#pragma unroll
+    for (int h = 0; h < HS; ++h) k[h] = my_key[h * B];
+    reg_bitonic<HS, uint32_t>(k);
+    if constexpr (!RANGE) own_segment();  // row list: one scratch segment per row (k_compact)
     uint32_t pos[(INS_CAP + 3) / 4];
 #pragma unroll
     for (int e = 0; e < (INS_CAP + 3) / 4; ++e) pos[e] = 0;
@@ -172,7 +176,11 @@ k_rowins(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const 
   }
   const uint32_t mxw = __reduce_max_sync(FULL, over ? 0u : nu);
   if (lane == 0) s_m[w] = mxw;
-  __syncthreads();  // s_m; RANGE: nobody reads ranks from s_key any more
+  // s_m; RANGE: nobody reads ranks from s_key any more.  A block with a handed-over row keeps one scratch segment
+  // per row (the compact run could run into the segment k_rowhash_list fills): k_compact_ins reads the flag.
+  const int any_over = __syncthreads_or(over ? 1 : 0);
+  if constexpr (RANGE)
+    if (live) ovf_flag[r] = any_over ? 1 : 0;
   if (tid == 0) {
     uint32_t mx = s_m[0];
 #pragma unroll
@@ -181,8 +189,28 @@ k_rowins(const uint32_t* __restrict__ rows, int64_t row0, int64_t n_rows, const 
   }
   if constexpr (RANGE) {  // slot words: [q][thread] -> global order -> one coalesced run (rows handed to k_rowhash are rewritten there)
     for (uint32_t q = 0; q < cnt; ++q) s_key[sw(rs - rs0 + q)] = my_inc[q * B];
+    // distinct columns of the block's rows back to back: block scan of the row counts
+    const uint32_t incl = warp_incl_scan(nu);
+    __syncthreads();  // s_key staged, s_inc and s_m free
+    if (lane == 31) s_m[w] = incl;
     __syncthreads();
+    uint32_t off = incl - nu, btotal = 0;
+#pragma unroll
+    for (int i = 0; i < B / 32; ++i) {
+      if (i < w) off += s_m[i];
+      btotal += s_m[i];
+    }
+    if (any_over) {
+      own_segment();
+    } else {
+#pragma unroll
+      for (int e = 0; e < INS_CAP; ++e)
+        if ((uint32_t)e < nu) s_inc[off + e] = k[e];
+    }
     for (uint32_t j = tid; j < n_blk; j += B) out[rs0 + j] = s_key[sw(j)];
+    __syncthreads();
+    if (!any_over)
+      for (uint32_t j = tid; j < btotal; j += B) ucol_tmp[(uint64_t)rs0 * L + j] = (int32_t)s_inc[j];
   }
 }
 
@@ -197,12 +225,12 @@ bool rowins_applies(uint32_t max_inc, int L) {
 
 int launch_rowins(uint32_t max_inc, int L, const uint32_t* rows, int64_t row0, int64_t row1, const uint32_t* row_start,
                   const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
-                  uint32_t* row_nnz, uint32_t* max_nnz, uint32_t* ovf, cudaStream_t s) {
+                  uint32_t* row_nnz, uint32_t* max_nnz, uint32_t* ovf, uint8_t* ovf_flag, cudaStream_t s) {
   char name[64];
   snprintf(name, sizeof(name), "k_rowins<%d,%d>", L, max_inc <= 24 ? 24 : 32);
   note_row_kernel(name);
   const unsigned grid = (unsigned)pgb_cdiv(row1 - row0, INS_B);
-#define PGB_RI(LL, RG, M) k_rowins<LL, RG, M><<<grid, INS_B, 0, s>>>(rows, row0, row1, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, ovf)
+#define PGB_RI(LL, RG, M) k_rowins<LL, RG, M><<<grid, INS_B, 0, s>>>(rows, row0, row1, row_start, inc_tmp, dofs, inc_pos, slots, ucol, row_nnz, max_nnz, ovf, ovf_flag)
 #define PGB_RI2(LL, M)         \
   do {                         \
     if (rows) PGB_RI(LL, false, M); \

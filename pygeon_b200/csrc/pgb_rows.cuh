@@ -184,11 +184,14 @@ int launch_rowhash_list(uint32_t max_cand, int L, const uint32_t* list, const ui
                         uint32_t* max_nnz, cudaStream_t s);
 
 // k_rowins: one thread per row of 17..32 incident cells, private hash table (pgb_rowins.cu); rows with too many
-// distinct columns are appended to ovf (ovf[0] = count, ovf[1..] = rows) for k_rowhash
+// distinct columns are appended to ovf (ovf[0] = count, ovf[1..] = rows) for k_rowhash_list.  Row ranges
+// (rows == nullptr): the distinct columns of every block of ROWTHREAD_GROUP rows are stored back to back from
+// ucol[row_start[first] * L] (the handed-over rows excluded: ovf_flag[row] = 1, their columns are in the row's own
+// segment): k_compact_ins.  Row lists: one segment per row (k_compact).
 bool rowins_applies(uint32_t max_inc, int L);
 int launch_rowins(uint32_t max_inc, int L, const uint32_t* rows, int64_t row0, int64_t row1, const uint32_t* row_start,
                   const uint32_t* inc_tmp, const int32_t* dofs, uint32_t* inc_pos, uint8_t* slots, int32_t* ucol,
-                  uint32_t* row_nnz, uint32_t* max_nnz, uint32_t* ovf, cudaStream_t s);
+                  uint32_t* row_nnz, uint32_t* max_nnz, uint32_t* ovf, uint8_t* ovf_flag, cudaStream_t s);
 
 // k_rowlong: one block per row, up to LONG_MAX_INC incident cells (pgb_rowlong.cu); inc_tmp: the row
 // blocks in any order.  *overflow_flag is raised when a row has more than 255 distinct columns.

@@ -42,7 +42,7 @@ if ROOT not in sys.path:
 NOMINAL_HBM_GBS = 8000.0  # north_star's nominal HBM3e figure; the measured copy peak is what `frac` uses
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (profiles/: config #2, L1 stiffness on 128^3)
-TRAFFIC = {"symbolic_rows": 0.940e9, "local_matrices": 2.027e9, "csr_numeric": 2.069e9}
+TRAFFIC = {"symbolic_rows": 0.908e9, "local_matrices": 2.027e9, "csr_numeric": 2.069e9}
 
 METRIC = "cells assembled/s into CSR"
 UNIT = "cells/s"

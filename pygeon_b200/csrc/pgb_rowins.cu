@@ -11,17 +11,21 @@ using namespace pgb_rows;
 // k_rowhash spends one WARP on such a row: ~290 warp instructions, most lanes idle in the per-row steps
 // (table reset, compaction, sort of the 15 distinct columns).  Here a thread does the whole row:
 //   (1) its incidences go through a 32-key sorting network in registers (canonical ascending order) and are
-//       parked in shared memory, one column of a [32][128] array per thread;
-//   (2) every incident cell's dof row is inserted into the thread's own open-addressing table of 32 keys
-//       (shared memory, [h][thread]: bank = thread, so no conflicts whatever slot a lane probes); the table
-//       position of every candidate replaces the incidence in shared memory (4 x 1 byte);
+//       parked in shared memory, one column of a [24 or 32][128] array per thread;
+//   (2) every incident cell's dof row (one vector load, the next one prefetched) is inserted into the thread's
+//       own open-addressing table of 32 keys (shared memory, [h][thread]: bank = thread, so no conflicts
+//       whatever slot a lane probes, and no atomics); the table position of every candidate replaces the
+//       incidence in shared memory (4 x 1 byte);
 //   (3) the table goes through the same register network: the distinct columns come out sorted (EMPTY = max
 //       key sorts last); their ranks are written back into the table;
 //   (4) a candidate's slot is the rank stored at its table position.
-// ~3000 thread instructions per row, i.e. ~95 warp instructions per row when the rows of a warp are alike.
-// No shared-memory atomics, no __syncthreads (a thread touches only its own column), same outputs as
-// k_rowhash (tested bit for bit).  A row with more than CAP distinct columns is handed to k_rowhash through
-// the overflow list (ovf[0] = count, ovf[1..] = rows).
+// ~165 warp instructions per row on config #2 (345 M in all against 610 M for k_rowhash).  What bounds the
+// kernel is the L1 sector rate: a per-thread access costs one 32-byte sector per lane and instruction, so in a
+// row RANGE everything that is contiguous per block - the incidences, the slot words, the distinct columns -
+// is moved with coalesced loads / stores and redistributed through shared memory; the two accesses that
+// stay scattered (the cell's dof row, the inc_pos store) are inherent to the transpose.
+// Same outputs as k_rowhash (tested bit for bit).  A row with more than CAP distinct columns is handed to
+// k_rowhash_list through the overflow list (ovf[0] = count, ovf[1..] = rows).
 constexpr uint32_t INS_EMPTY = 0xffffffffu;
 constexpr int INS_B = 128;   // rows per block
 static_assert(INS_B == ROWTHREAD_GROUP, "k_compact_ins expects groups of ROWTHREAD_GROUP rows");

@@ -22,7 +22,9 @@ WANT = [
     ("kd_mr_d (K4)", r"7kd_mr_dE"),
     ("kd_cg_p (K4)", r"7kd_cg_pE"),
     ("k_cg_xr (K3)", r"7k_cg_xrE"),
-    ("k_rowhash<32, 1, 4, 128> (symbolic)", r"k_rowhashILi32ELi1ELi4ELi128EE"),
+    ("k_rowins<4, RANGE, 24> (symbolic, P1 rows in 3D)", r"k_rowinsILi4ELb1ELi24EE"),
+    ("k_rowhash<32, 1, 4, 128> (symbolic, round-1 kernel for those rows)", r"9k_rowhashILi32ELi1ELi4ELi128EE"),
+    ("k_compact_ins<int> (symbolic)", r"k_compact_insIiE"),
     ("k_extract_fill<int> (system)", r"k_extract_fillIiE"),
 ]
 KEY = re.compile(r"\b(LDG|STG|LDS|STS|ATOMS|ATOMG|ATOM|RED|UBLKCP|UTMALDG|SYNCS|LDGSTS|SHFL|DFMA|DADD|DMUL|MUFU|BAR|VIMNMX|MEMBAR|ERRBAR|CCTL)\S*")

@@ -814,11 +814,13 @@ int scan_u32(uint32_t* data, uint64_t n, uint32_t* parts, uint32_t* total_out, c
 template <typename KeyT>
 int radix_sort(KeySrc<KeyT> src, uint32_t n, int total_bits, KeyT* kbuf[2], uint32_t* pbuf[2], uint32_t* hist,
                uint32_t* parts, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};  // function attributes are per device
+  int dev = 0;
+  PGB_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     PGB_CHECK(cudaFuncSetAttribute(k_radix_scatter<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(ScatterSmem<KeyT>)));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int passes = (total_bits + RADIX_BITS - 1) / RADIX_BITS;
   const uint32_t ntiles = (uint32_t)pgb_cdiv((int64_t)n, SORT_TILE);

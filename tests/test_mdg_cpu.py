@@ -104,3 +104,20 @@ def test_trace_term_is_diagonal_on_a_conforming_interface(cube):
 
     with pytest.raises(NotImplementedError):
         md_system._trace_diagonal(Fake(), {pg.PARAMETERS: {"flow": {pg.NORMAL_DIFFUSIVITY: np.ones(2)}}}, "flow")
+
+
+def test_left_scaling_equals_the_sparse_product():
+    """md_system._left_scaled: rows of div scaled by the diagonal P0 mass == cell_mass @ div of the host route
+    (same pattern - exact zeros dropped - and bit-identical values); a non-diagonal factor takes the product."""
+    from pygeon_b200 import md_system
+
+    rng = np.random.default_rng(3)
+    D = sps.random_array((300, 500), density=0.02, rng=rng, format="csr")
+    D.data[::7] = 0.0  # explicit zeros (masked tip dofs)
+    d = rng.uniform(0.5, 2.0, 300)
+    d[5] = 0.0
+    for Cm in (sps.diags_array(d).tocsc(), sps.csc_array(sps.diags_array(d) + sps.eye_array(300, k=1) * 0.1)):
+        got, ref = md_system._left_scaled(Cm, D), sps.csr_array(Cm @ D)
+        ref.sort_indices(), got.sort_indices()  # (scipy's product has already dropped the exact zeros)
+        assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+        assert np.array_equal(got.data, ref.data)
